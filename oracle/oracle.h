@@ -1,0 +1,128 @@
+/*
+ * oracle.h -- CPU restatement of the schroedinger picture core.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference leg may load liboracle.so.  The product
+ * (schroedinger_b200/) never links, imports or calls it.
+ *
+ * Parity status: PINNED.  Every function here is checked bit-for-bit against
+ * the unmodified reference compiled into oracle/_ref/libschro_ref.so
+ * (oracle/build_ref.sh) by tests/test_oracle_vs_ref.py, and against the
+ * committed golden vectors in tests/golden/ (generated from that same
+ * reference build by tests/golden/make_golden.py).
+ *
+ * All functions use a flat C ABI (plain pointers, strides in BYTES).
+ * The identically shaped ref_* functions in oracle/ref_harness.c drive the
+ * real reference; the sb2_* functions in include/schro_b200.h are the product.
+ */
+#ifndef ORACLE_H
+#define ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Filter ids: reference schroedinger/schrobitstream.h:124-132 */
+enum {
+  ORACLE_WAVELET_DESLAURIERS_DUBUC_9_7 = 0,
+  ORACLE_WAVELET_LE_GALL_5_3 = 1,
+  ORACLE_WAVELET_DESLAURIERS_DUBUC_13_7 = 2,
+  ORACLE_WAVELET_HAAR_0 = 3,
+  ORACLE_WAVELET_HAAR_1 = 4,
+  ORACLE_WAVELET_FIDELITY = 5,
+  ORACLE_WAVELET_DAUBECHIES_9_7 = 6
+};
+
+/* ---- wavelets (oracle_wavelet.c) ---- */
+/* one level, in place; follows schro_wavelet_transform_2d
+ * (schroedinger/schrowaveletorc.c:60-117) */
+void oracle_wavelet_fwd (void *data, int stride, int width, int height,
+    int is_s32, int filter);
+/* one level, in place (dest == src); follows schro_wavelet_inverse_transform_2d
+ * (schroedinger/schrowaveletorc.c:121-188) */
+void oracle_wavelet_inv (void *data, int stride, int width, int height,
+    int is_s32, int filter);
+/* multi-level drivers on one component plane; follow
+ * schro_frame_iwt_transform (schroedinger/schroframe.c:1192-1228) and
+ * schro_decoder_inverse_iwt_transform (schroedinger/schrodecoder.c:1809-1853) */
+void oracle_iwt_fwd (void *data, int stride, int width, int height,
+    int is_s32, int filter, int depth);
+void oracle_iwt_inv (void *data, int stride, int width, int height,
+    int is_s32, int filter, int depth);
+
+/* ---- upsampled reference frames (oracle_frame.c) ---- */
+/* `data` points at pixel (0,0) of phase 0 of ONE component of an upsampled
+ * frame: 4 phase planes side by side in each row, phase p at
+ * data + (stride>>2)*p, every phase surrounded by `ext` border pixels
+ * (schroedinger/schroframe.c:60-191, 1917-1925). */
+/* schro_frame_mc_edgeextend on one plane (schroedinger/schroframe.c:1940-1997) */
+void oracle_mc_edgeextend (uint8_t *data, int stride, int width, int height,
+    int ext);
+/* schro_upsampled_frame_upsample on one component, phase 0 already
+ * edge-extended (schroedinger/schroframe.c:2000-2030) */
+void oracle_upsample (uint8_t *data, int stride, int width, int height,
+    int ext);
+/* schro_frame_downsample on one component (schroedinger/schroframe.c:1400-1513) */
+void oracle_downsample (uint8_t *dest, int dstride, int dwidth, int dheight,
+    const uint8_t *src, int sstride, int swidth, int sheight);
+
+/* ---- OBMC (oracle_motion.c) ---- */
+/* Same memory layout as SchroMotionVector (schroedinger/schromotion.h:20-37) */
+typedef struct {
+  uint32_t flags;               /* pred_mode:2 using_global:1 split:2 unused:3 scan:8 */
+  uint32_t metric;
+  uint32_t chroma_metric;
+  int16_t v[4];                 /* vec: dx[0],dx[1],dy[0],dy[1]   dc: dc[0],dc[1],dc[2] */
+} OracleMotionVector;
+
+typedef struct {
+  int xbsep, ybsep, xblen, yblen;       /* of THIS component */
+  int x_num_blocks, y_num_blocks;
+  int mv_precision;
+  int weight1, weight2, weight_bits;    /* picture_weight_1/2/bits */
+  int h_shift, v_shift;                 /* chroma shifts applied to vectors (0 for luma) */
+  int comp;                             /* component index (selects dc[k]) */
+} OracleObmcParams;
+
+/* One component of schro_motion_render_u8 (schroedinger/schromotion8.c:700-929).
+ * ref0/ref1: phase-0 pixel (0,0) of the upsampled references (ref1 may be NULL),
+ * rstride their 4-phase row stride.  acc (int16, may be NULL) receives what the
+ * reference leaves in `dest`.  add!=0: out = clamp_u8(residual + ((acc+32)>>6)),
+ * residual is s16 (res_is_s32==0) or s32.  add==0: dest=acc:=(acc-8160)>>6 and
+ * residual(s16) -= that. */
+void oracle_obmc_render (const OracleObmcParams *p, const OracleMotionVector *mvs,
+    const uint8_t *ref0, const uint8_t *ref1, int rstride,
+    int width, int height,
+    int16_t *acc, int acc_stride,
+    void *residual, int res_stride, int res_is_s32,
+    int add, uint8_t *out, int out_stride);
+
+/* ---- SAD / hierarchical block matching (oracle_hbm.c) ---- */
+/* schro_metric_absdiff_u8 (schroedinger/schrometric.c:10-29) */
+uint32_t oracle_sad_u8 (const uint8_t *a, int a_stride, const uint8_t *b,
+    int b_stride, int width, int height);
+
+typedef struct {
+  /* pixel (0,0) pointers of the three u8 components, edge-extended by `ext` */
+  const uint8_t *data[3];
+  int stride[3];
+  int width, height;            /* luma size */
+  int h_shift, v_shift;
+  int ext;
+} OraclePyrLevel;
+
+/* One call of schro_hierarchical_bm_scan_hint (schroedinger/schrohierbm.c:174-383).
+ * mf: output field (x_num_blocks*y_num_blocks), parent: field of level shift+1
+ * or NULL. */
+void oracle_hbm_scan_hint (const OraclePyrLevel *src, const OraclePyrLevel *ref,
+    int xbsep, int ybsep, int x_num_blocks, int y_num_blocks, int ref_index,
+    int shift, int h_range, int use_chroma,
+    const OracleMotionVector *parent, OracleMotionVector *mf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
