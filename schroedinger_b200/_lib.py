@@ -1,0 +1,57 @@
+"""ctypes loader for libschro_b200.so (the C-ABI declared in include/schro_b200.h)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libschro_b200.so")
+
+SB2_MAX_COMPONENTS = 4
+
+
+class Sb2Error(RuntimeError):
+    pass
+
+
+class Slab(ctypes.Structure):
+    """Mirror of ``sb2_slab`` (include/schro_b200.h)."""
+    _fields_ = [
+        ("base", ctypes.c_void_p),
+        ("picture_pitch", ctypes.c_size_t),
+        ("count", ctypes.c_int),
+        ("ncomp", ctypes.c_int),
+        ("offset", ctypes.c_size_t * SB2_MAX_COMPONENTS),
+        ("stride", ctypes.c_int * SB2_MAX_COMPONENTS),
+        ("width", ctypes.c_int * SB2_MAX_COMPONENTS),
+        ("height", ctypes.c_int * SB2_MAX_COMPONENTS),
+    ]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise Sb2Error(
+            f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()). "
+            "There is no CPU fallback for the picture core.")
+    return ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_LOCAL)
+
+
+lib = _load()
+
+lib.sb2_last_error.restype = ctypes.c_char_p
+lib.sb2_version.restype = ctypes.c_int
+lib.sb2_launch_count.restype = ctypes.c_ulonglong
+lib.sb2_iwt_workspace_bytes.restype = ctypes.c_size_t
+lib.sb2_iwt_workspace_bytes.argtypes = [ctypes.POINTER(Slab), ctypes.c_int, ctypes.c_int, ctypes.c_int]
+for _n in ("sb2_iwt_forward", "sb2_iwt_inverse"):
+    _f = getattr(lib, _n)
+    _f.restype = ctypes.c_int
+    _f.argtypes = [ctypes.POINTER(Slab), ctypes.POINTER(Slab), ctypes.c_int, ctypes.c_int,
+                   ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+
+
+def last_error():
+    return lib.sb2_last_error().decode()
+
+
+def check(rc, what="sb2 call"):
+    if rc != 0:
+        raise Sb2Error(f"{what} failed ({rc}): {last_error()}")

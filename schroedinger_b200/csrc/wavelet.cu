@@ -1,0 +1,603 @@
+// wavelet.cu -- Dirac integer lifting wavelets for sm_100a.
+//
+// Replaces, bit-exactly, the reference's one-level 2-D transforms
+//   schro_wavelet_transform_2d          (schroedinger/schrowaveletorc.c:60-117)
+//   schro_wavelet_inverse_transform_2d  (schroedinger/schrowaveletorc.c:121-188)
+// for all seven filters x {s16, s32} and the multi-level drivers around them
+// (schroedinger/schroframe.c:1192-1228, schroedinger/schrodecoder.c:1809-1853).
+//
+// Design (see DESIGN.md "wavelets"):
+//  * one CTA = one output tile of one level of one component of one picture;
+//    horizontal and vertical lifting are fused in shared memory so a level is a
+//    single read + single write of its sub-plane;
+//  * the arithmetic is plain lifting on polyphase arrays E[k]=x[2k], O[k]=x[2k+1]
+//    with taps clamped to [0,n-1]; the 16-bit variants reproduce Orc's wrap
+//    points (addw/subw/convlw wrap, mulswl/avgsw are wide) exactly;
+//  * levels never run in place: level l reads LL from a compact scratch plane and
+//    the three detail bands from the source plane, so tiles have no halo hazards
+//    and the only extra traffic is the (1/4 + 1/16 + ...) LL ping-pong.
+//
+// No tensor cores: nothing here is a contraction.  The kernel is HBM/LSU bound.
+
+#include "common.cuh"
+
+namespace sb2 {
+
+enum { K_A22, K_A11, K_M4, K_M2, K_F8A, K_F8B, K_COPY, K_HALF };
+
+struct Step {
+  int target;   // 0: update E from O, 1: update O from E
+  int kind;
+  int sign;     // forward direction
+  int tap0;     // offset of first tap in the source polyphase array
+  int p1, p2, p3;
+};
+
+// Forward lifting steps (inverse = reverse order, flipped sign).
+// Sources: schroedinger/schrowaveletorc.c:287-301 (DD9/7), :376-390 (LeGall),
+// :459-473 (DD13/7), :545-567 (Haar), :606-648 (Fidelity), :729-753 (Daub 9/7).
+__host__ __device__ constexpr Step step_of (int f, int s)
+{
+  switch (f) {
+    case 0: return s == 0 ? Step{1, K_M4, -1, -1, 8, 4, 0} : Step{0, K_A22, +1, -1, 0, 0, 0};
+    case 1: return s == 0 ? Step{1, K_A11, -1, 0, 0, 0, 0} : Step{0, K_A22, +1, -1, 0, 0, 0};
+    case 2: return s == 0 ? Step{1, K_M4, -1, -1, 8, 4, 0} : Step{0, K_M4, +1, -2, 16, 5, 0};
+    case 3:
+    case 4: return s == 0 ? Step{1, K_COPY, -1, 0, 0, 0, 0} : Step{0, K_HALF, +1, 0, 0, 0, 0};
+    case 5: return s == 0 ? Step{0, K_F8A, +1, -4, 128, 0, 0} : Step{1, K_F8B, +1, -3, 127, 0, 0};
+    default:
+      return s == 0 ? Step{1, K_M2, -1, 0, 6497, 2048, 12}
+           : s == 1 ? Step{0, K_M2, -1, -1, 217, 2048, 12}
+           : s == 2 ? Step{1, K_M2, +1, 0, 3616, 2048, 12}
+                    : Step{0, K_M2, +1, -1, 1817, 2048, 12};
+  }
+}
+__host__ __device__ constexpr int num_steps (int f) { return f == 6 ? 4 : 2; }
+// pre/post shift (schroedinger/schroorc.orc:770-807)
+__host__ __device__ constexpr int filter_shift (int f) { return (f == 3 || f == 5) ? 0 : 1; }
+// halo in polyphase samples = sum of the per-step reaches
+__host__ __device__ constexpr int filter_halo (int f)
+{
+  return f == 0 ? 3 : f == 1 ? 2 : f == 2 ? 4 : f == 5 ? 8 : f == 6 ? 4 : 0;
+}
+__host__ __device__ constexpr int kind_taps (int kind)
+{
+  return (kind == K_M4) ? 4 : (kind == K_F8A || kind == K_F8B) ? 8
+       : (kind == K_COPY || kind == K_HALF) ? 1 : 2;
+}
+
+// ---- exact arithmetic ------------------------------------------------------
+template <typename T> struct Ar;
+template <> struct Ar<int16_t> {
+  // storage wraps at 16 bit; products / mas accumulators are 32 bit wide
+  static __device__ __forceinline__ int wr (int x) { return (int) (short) x; }
+  static __device__ __forceinline__ int add (int a, int b) { return wr (a + b); }
+  static __device__ __forceinline__ int sub (int a, int b) { return wr (a - b); }
+  static __device__ __forceinline__ int wadd (int a, int b) { return a + b; }
+  static __device__ __forceinline__ int wsub (int a, int b) { return a - b; }
+  static __device__ __forceinline__ int wmul (int a, int b) { return a * b; }
+  static __device__ __forceinline__ int avg (int a, int b) { return (a + b + 1) >> 1; }
+};
+template <> struct Ar<int32_t> {
+  // everything wraps at 32 bit; avgsl is exact (64-bit in Orc's C emulation)
+  static __device__ __forceinline__ int wr (int x) { return x; }
+  static __device__ __forceinline__ int add (int a, int b) { return (int) ((unsigned) a + (unsigned) b); }
+  static __device__ __forceinline__ int sub (int a, int b) { return (int) ((unsigned) a - (unsigned) b); }
+  static __device__ __forceinline__ int wadd (int a, int b) { return add (a, b); }
+  static __device__ __forceinline__ int wsub (int a, int b) { return sub (a, b); }
+  static __device__ __forceinline__ int wmul (int a, int b) { return (int) ((unsigned) a * (unsigned) b); }
+  static __device__ __forceinline__ int avg (int a, int b) { return __rhadd (a, b); }
+};
+
+// term of one lifting step from its taps v[0..ntaps)
+template <typename T, int KIND>
+__device__ __forceinline__ int lift_term (const int *v, int p1, int p2, int p3)
+{
+  typedef Ar<T> A;
+  if (KIND == K_A22) {            // schroorc.orc:4-73
+    int t = A::add (v[0], v[1]);
+    t = A::add (t, 2);
+    return t >> 2;
+  } else if (KIND == K_A11) {     // avgsw / avgsl, schroorc.orc:76-134
+    return A::avg (v[0], v[1]);
+  } else if (KIND == K_M4) {      // mas4 1-9-9-1, schroorc.orc:295-411
+    int t = A::add (v[1], v[2]);
+    int u = A::add (v[0], v[3]);
+    int acc = A::wadd (A::wsub (A::wmul (t, 9), u), p1);
+    return acc >> p2;
+  } else if (KIND == K_M2) {      // mas2, schroorc.orc:221-292
+    int t = A::add (v[0], v[1]);
+    int acc = A::wadd (A::wmul (t, p1), p2);
+    return acc >> p3;
+  } else if (KIND == K_F8A || KIND == K_F8B) {   // plain-C mas8, schrowaveletorc.c:606-663
+    int acc = p1;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int w = (KIND == K_F8A)
+          ? (j == 0 || j == 7 ? -8 : j == 1 || j == 6 ? 21 : j == 2 || j == 5 ? -46 : 161)
+          : (j == 0 || j == 7 ? 2 : j == 1 || j == 6 ? -10 : j == 2 || j == 5 ? 25 : -81);
+      acc = A::wadd (acc, A::wmul (v[j], w));
+    }
+    return acc >> 8;
+  } else if (KIND == K_COPY) {
+    return v[0];
+  } else {                        // K_HALF: avgsw(x, 0)
+    return A::avg (v[0], 0);
+  }
+}
+
+// ---- kernel arguments ------------------------------------------------------
+struct LevelArgs {
+  PlaneSet dense;   // forward: input X;  inverse: output Y      (w x h, interleaved)
+  PlaneSet bands;   // the coefficient plane at this level's stride ([L|H] split rows)
+  PlaneSet ll;      // LL band (w/2 x h/2): forward output / inverse input
+  int w[SB2_MAX_COMPONENTS];
+  int h[SB2_MAX_COMPONENTS];
+  int ncomp;
+};
+
+constexpr int TWH = 64;    // tile width  in polyphase samples (128 output columns)
+constexpr int THH = 32;    // tile height in polyphase samples (64 output rows)
+constexpr int NTHREADS = 256;
+constexpr int NWARPS = NTHREADS / 32;
+
+template <typename T, int F> struct TileGeom {
+  static constexpr int VEC = 16 / (int) sizeof (T);
+  static constexpr int HP = filter_halo (F);
+  static constexpr int HK = ((HP + VEC - 1) / VEC) * VEC;     // horizontal halo (aligned)
+  static constexpr int PAD = VEC;                              // replicated border cells (>= 4)
+  static constexpr int NK = TWH + 2 * HK;
+  static constexpr int SEG = NK + 2 * PAD;
+  static constexpr int PITCH = 2 * SEG;
+  static constexpr int NR = 2 * (THH + 2 * HP);
+  static constexpr size_t SMEM = (size_t) NR * PITCH * sizeof (T);
+};
+
+// One vertical lifting step on the smem window.
+// Columns [c0, c1) of every row; polyphase rows ky in [ky_lo, ky_hi).
+template <typename T, int F, int S, bool INV>
+__device__ __forceinline__ void vert_step (T *sm, int pitch, int ky_lo, int ky_hi,
+    int c0, int c1, int warp, int lane)
+{
+  constexpr Step st = step_of (F, S);
+  constexpr int NT = kind_taps (st.kind);
+  constexpr int sign = INV ? -st.sign : st.sign;
+  for (int ky = ky_lo + warp; ky < ky_hi; ky += NWARPS) {
+    const T *src[NT];
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      int k = ky + st.tap0 + t;
+      k = min (max (k, ky_lo), ky_hi - 1);   // window == picture range at picture edges
+      src[t] = sm + (size_t) (2 * (k - ky_lo) + (1 - st.target)) * pitch;
+    }
+    T *dst = sm + (size_t) (2 * (ky - ky_lo) + st.target) * pitch;
+    for (int c = c0 + lane; c < c1; c += 32) {
+      int v[NT];
+#pragma unroll
+      for (int t = 0; t < NT; t++) v[t] = src[t][c];
+      int term = lift_term<T, st.kind> (v, st.p1, st.p2, st.p3);
+      int d = dst[c];
+      dst[c] = (T) (sign > 0 ? Ar<T>::add (d, term) : Ar<T>::sub (d, term));
+    }
+  }
+}
+
+// One horizontal lifting step: rows [r0, r1) of the window, nk samples per segment.
+// Segment cells [-PAD,0) and [nk, nk+PAD) hold the replicated border (extend_*).
+template <typename T, int F, int S, bool INV>
+__device__ __forceinline__ void horiz_step (T *sm, int r0, int r1, int nk,
+    int warp, int lane)
+{
+  typedef TileGeom<T, F> G;
+  constexpr Step st = step_of (F, S);
+  constexpr int NT = kind_taps (st.kind);
+  constexpr int sign = INV ? -st.sign : st.sign;
+  for (int r = r0 + warp; r < r1; r += NWARPS) {
+    T *dst = sm + (size_t) r * G::PITCH + st.target * G::SEG + G::PAD;
+    const T *src = sm + (size_t) r * G::PITCH + (1 - st.target) * G::SEG + G::PAD;
+    for (int j = lane; j < nk; j += 32) {
+      int v[NT];
+#pragma unroll
+      for (int t = 0; t < NT; t++) v[t] = src[j + st.tap0 + t];
+      int term = lift_term<T, st.kind> (v, st.p1, st.p2, st.p3);
+      int d = dst[j];
+      T nv = (T) (sign > 0 ? Ar<T>::add (d, term) : Ar<T>::sub (d, term));
+      dst[j] = nv;
+      if (j == 0) {
+#pragma unroll
+        for (int q = 1; q <= G::PAD; q++) dst[-q] = nv;
+      }
+      if (j == nk - 1) {
+#pragma unroll
+        for (int q = 0; q < G::PAD; q++) dst[nk + q] = nv;
+      }
+    }
+  }
+}
+
+template <typename T, int F, bool INV, int S>
+struct StepSeq {
+  // run all steps of the filter in lifting order for this direction
+  static __device__ __forceinline__ void vert (T *sm, int pitch, int ky_lo, int ky_hi,
+      int c0, int c1, int warp, int lane)
+  {
+    constexpr int NS = num_steps (F);
+    constexpr int s = INV ? NS - 1 - S : S;
+    vert_step<T, F, s, INV> (sm, pitch, ky_lo, ky_hi, c0, c1, warp, lane);
+    __syncthreads ();
+    if constexpr (S + 1 < NS)
+      StepSeq<T, F, INV, S + 1>::vert (sm, pitch, ky_lo, ky_hi, c0, c1, warp, lane);
+  }
+  static __device__ __forceinline__ void horiz (T *sm, int r0, int r1, int nk, int warp, int lane)
+  {
+    constexpr int NS = num_steps (F);
+    constexpr int s = INV ? NS - 1 - S : S;
+    horiz_step<T, F, s, INV> (sm, r0, r1, nk, warp, lane);
+    __syncthreads ();
+    if constexpr (S + 1 < NS)
+      StepSeq<T, F, INV, S + 1>::horiz (sm, r0, r1, nk, warp, lane);
+  }
+};
+
+template <typename T, int F, bool INV>
+__global__ void __launch_bounds__ (NTHREADS)
+wavelet_level_kernel (const LevelArgs a)
+{
+  typedef TileGeom<T, F> G;
+  extern __shared__ __align__ (16) unsigned char smem_raw[];
+  T *sm = reinterpret_cast<T *> (smem_raw);
+
+  const int comp = blockIdx.z % a.ncomp;
+  const int pic = blockIdx.z / a.ncomp;
+  const int w = a.w[comp], h = a.h[comp];
+  const int n = w >> 1, m = h >> 1;
+  const int kx0 = blockIdx.x * TWH, ky0 = blockIdx.y * THH;
+  if (kx0 >= n || ky0 >= m) return;
+
+  const int kx_lo = max (0, kx0 - G::HK), kx_hi = min (n, kx0 + TWH + G::HK);
+  const int ky_lo = max (0, ky0 - G::HP), ky_hi = min (m, ky0 + THH + G::HP);
+  const int nk = kx_hi - kx_lo;
+  const int nr = 2 * (ky_hi - ky_lo);
+  const int twh = min (TWH, n - kx0), thh = min (THH, m - ky0);
+  const int jo = kx0 - kx_lo;                // first output sample inside the segment
+  const int ro = 2 * (ky0 - ky_lo);          // first output row inside the window
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int SH = filter_shift (F);
+
+  T *dense = reinterpret_cast<T *> (plane_ptr (a.dense, pic, comp));
+  T *bands = reinterpret_cast<T *> (plane_ptr (a.bands, pic, comp));
+  T *ll = reinterpret_cast<T *> (plane_ptr (a.ll, pic, comp));
+  const size_t ds = a.dense.stride[comp] / sizeof (T);
+  const size_t bs = a.bands.stride[comp] / sizeof (T);
+  const size_t ls = a.ll.stride[comp] / sizeof (T);
+
+  if (INV) {
+    // ---- load [L|H] split rows: LL from `ll`, the three detail bands from `bands`
+    for (int lr = warp; lr < nr; lr += NWARPS) {
+      const int r = 2 * ky_lo + lr;
+      T *row = sm + (size_t) lr * G::PITCH + G::PAD;
+      const T *gl = (r & 1) ? bands + (size_t) r * bs + kx_lo : ll + (size_t) (r >> 1) * ls + kx_lo;
+      const T *gh = bands + (size_t) r * bs + n + kx_lo;
+      for (int j = lane; j < nk; j += 32) {
+        T vl = gl[j], vh = gh[j];
+        row[j] = vl;
+        row[G::SEG + j] = vh;
+        if (j == 0) {
+#pragma unroll
+          for (int q = 1; q <= G::PAD; q++) { row[-q] = vl; row[G::SEG - q] = vh; }
+        }
+        if (j == nk - 1) {
+#pragma unroll
+          for (int q = 0; q < G::PAD; q++) { row[nk + q] = vl; row[G::SEG + nk + q] = vh; }
+        }
+      }
+    }
+    __syncthreads ();
+    // ---- vertical un-lift on every column of the window (incl. replicated border cells)
+    StepSeq<T, F, true, 0>::vert (sm, G::PITCH, ky_lo, ky_hi, 0, G::PITCH, warp, lane);
+    // ---- horizontal un-lift on the output rows
+    StepSeq<T, F, true, 0>::horiz (sm, ro, ro + 2 * thh, nk, warp, lane);
+    // ---- interleave, (x+1)>>1, store
+    for (int lr = warp; lr < 2 * thh; lr += NWARPS) {
+      const int r = 2 * ky0 + lr;
+      const T *row = sm + (size_t) (ro + lr) * G::PITCH + G::PAD + jo;
+      T *out = dense + (size_t) r * ds + 2 * kx0;
+      for (int x = lane; x < 2 * twh; x += 32) {
+        int v = row[(x & 1) * G::SEG + (x >> 1)];
+        if (SH) v = Ar<T>::add (v, 1) >> 1;
+        out[x] = (T) v;
+      }
+    }
+  } else {
+    // ---- load interleaved rows, x<<1, de-interleave into [E|O] segments
+    for (int lr = warp; lr < nr; lr += NWARPS) {
+      const int r = 2 * ky_lo + lr;
+      T *row = sm + (size_t) lr * G::PITCH + G::PAD;
+      const T *in = dense + (size_t) r * ds + 2 * kx_lo;
+      for (int x = lane; x < 2 * nk; x += 32) {
+        int v = in[x];
+        if (SH) v = Ar<T>::add (v, v);
+        const int j = x >> 1, seg = x & 1;
+        T *cell = row + seg * G::SEG + j;
+        *cell = (T) v;
+        if (j == 0) {
+#pragma unroll
+          for (int q = 1; q <= G::PAD; q++) cell[-q] = (T) v;
+        }
+        if (j == nk - 1) {
+#pragma unroll
+          for (int q = 1; q <= G::PAD; q++) cell[q] = (T) v;
+        }
+      }
+    }
+    __syncthreads ();
+    // ---- horizontal lift on every row of the window
+    StepSeq<T, F, false, 0>::horiz (sm, 0, nr, nk, warp, lane);
+    // ---- vertical lift on every column of the window
+    StepSeq<T, F, false, 0>::vert (sm, G::PITCH, ky_lo, ky_hi, 0, G::PITCH, warp, lane);
+    // ---- store: LL (even rows, L half) to `ll`, everything else to `bands`
+    for (int lr = warp; lr < 2 * thh; lr += NWARPS) {
+      const int r = 2 * ky0 + lr;
+      const T *row = sm + (size_t) (ro + lr) * G::PITCH + G::PAD + jo;
+      T *ol = (r & 1) ? bands + (size_t) r * bs + kx0 : ll + (size_t) (r >> 1) * ls + kx0;
+      T *oh = bands + (size_t) r * bs + n + kx0;
+      for (int j = lane; j < twh; j += 32) {
+        ol[j] = row[j];
+        oh[j] = row[G::SEG + j];
+      }
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------
+
+template <typename T, int F, bool INV>
+static int launch_level (const LevelArgs &a, int count, cudaStream_t stream)
+{
+  typedef TileGeom<T, F> G;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute (wavelet_level_kernel<T, F, INV>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, (int) G::SMEM);
+    if (e != cudaSuccess) return check_cuda (e, "cudaFuncSetAttribute(wavelet)");
+    attr_set = true;
+  }
+  int maxn = 0, maxm = 0;
+  for (int c = 0; c < a.ncomp; c++) {
+    maxn = max (maxn, a.w[c] >> 1);
+    maxm = max (maxm, a.h[c] >> 1);
+  }
+  if (maxn == 0 || maxm == 0) return SB2_OK;
+  dim3 grid (ceil_div (maxn, TWH), ceil_div (maxm, THH), a.ncomp * count);
+  wavelet_level_kernel<T, F, INV><<<grid, NTHREADS, G::SMEM, stream>>> (a);
+  count_launch ();
+  return check_cuda (cudaGetLastError (), "wavelet_level_kernel launch");
+}
+
+template <typename T, bool INV>
+static int launch_level_f (int filter, const LevelArgs &a, int count, cudaStream_t s)
+{
+  switch (filter) {
+    case 0: return launch_level<T, 0, INV> (a, count, s);
+    case 1: return launch_level<T, 1, INV> (a, count, s);
+    case 2: return launch_level<T, 2, INV> (a, count, s);
+    case 3: return launch_level<T, 3, INV> (a, count, s);
+    case 4: return launch_level<T, 4, INV> (a, count, s);
+    case 5: return launch_level<T, 5, INV> (a, count, s);
+    case 6: return launch_level<T, 6, INV> (a, count, s);
+    default: return set_error (SB2_ERR_ARG, "bad wavelet filter index %d", filter);
+  }
+}
+
+static int launch_level_any (bool inv, int is_s32, int filter, const LevelArgs &a,
+    int count, cudaStream_t s)
+{
+  if (is_s32)
+    return inv ? launch_level_f<int32_t, true> (filter, a, count, s)
+               : launch_level_f<int32_t, false> (filter, a, count, s);
+  return inv ? launch_level_f<int16_t, true> (filter, a, count, s)
+             : launch_level_f<int16_t, false> (filter, a, count, s);
+}
+
+// Workspace: per picture, per component: T1 (w/2 x h/2), T0 (w/4 x h/4) and, for
+// in-place calls, a full-size plane F.  Strides are rounded up to 16 bytes.
+struct WsLayout {
+  size_t pic_pitch;
+  size_t off_t1[SB2_MAX_COMPONENTS], off_t0[SB2_MAX_COMPONENTS], off_full[SB2_MAX_COMPONENTS];
+  int stride_t1[SB2_MAX_COMPONENTS], stride_t0[SB2_MAX_COMPONENTS], stride_full[SB2_MAX_COMPONENTS];
+};
+
+static inline size_t round_up (size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static WsLayout ws_layout (const sb2_slab *s, int bpp, int depth, int in_place)
+{
+  WsLayout L;
+  size_t off = 0;
+  for (int c = 0; c < SB2_MAX_COMPONENTS; c++) {
+    L.off_t1[c] = L.off_t0[c] = L.off_full[c] = 0;
+    L.stride_t1[c] = L.stride_t0[c] = L.stride_full[c] = 0;
+    if (c >= s->ncomp) continue;
+    const int w = s->width[c], h = s->height[c];
+    if (depth > 1) {
+      L.stride_t1[c] = (int) round_up ((size_t) (w / 2) * bpp, 16);
+      L.off_t1[c] = off;
+      off += round_up ((size_t) L.stride_t1[c] * (h / 2), 256);
+    }
+    if (depth > 2) {
+      L.stride_t0[c] = (int) round_up ((size_t) (w / 4) * bpp, 16);
+      L.off_t0[c] = off;
+      off += round_up ((size_t) L.stride_t0[c] * (h / 4), 256);
+    }
+    if (in_place) {
+      L.stride_full[c] = (int) round_up ((size_t) w * bpp, 16);
+      L.off_full[c] = off;
+      off += round_up ((size_t) L.stride_full[c] * h, 256);
+    }
+  }
+  L.pic_pitch = round_up (off, 256);
+  return L;
+}
+
+static int validate (const sb2_slab *src, const sb2_slab *dst, int bpp, int depth)
+{
+  if (!src || !dst || !src->base || !dst->base)
+    return set_error (SB2_ERR_ARG, "null slab");
+  if (src->ncomp < 1 || src->ncomp > SB2_MAX_COMPONENTS || src->ncomp != dst->ncomp ||
+      src->count != dst->count || src->count < 1)
+    return set_error (SB2_ERR_ARG, "slab shapes differ (ncomp %d/%d count %d/%d)",
+        src->ncomp, dst->ncomp, src->count, dst->count);
+  if (depth < 1 || depth > 8) return set_error (SB2_ERR_ARG, "bad transform depth %d", depth);
+  for (int c = 0; c < src->ncomp; c++) {
+    if (src->width[c] != dst->width[c] || src->height[c] != dst->height[c])
+      return set_error (SB2_ERR_ARG, "component %d size differs", c);
+    if (src->width[c] <= 0 || src->height[c] <= 0 ||
+        (src->width[c] & ((1 << depth) - 1)) || (src->height[c] & ((1 << depth) - 1)))
+      return set_error (SB2_ERR_ARG, "component %d size %dx%d is not a multiple of 1<<%d",
+          c, src->width[c], src->height[c], depth);
+    if ((src->stride[c] % bpp) || (dst->stride[c] % bpp) || (src->offset[c] % bpp) ||
+        (dst->offset[c] % bpp))
+      return set_error (SB2_ERR_ARG, "component %d stride/offset not a multiple of the sample size", c);
+  }
+  return SB2_OK;
+}
+
+static bool slabs_alias (const sb2_slab *a, const sb2_slab *b)
+{
+  // conservative: any overlap of the two address ranges counts as aliasing
+  const char *a0 = (const char *) a->base, *b0 = (const char *) b->base;
+  const char *a1 = a0 + a->picture_pitch * (size_t) a->count;
+  const char *b1 = b0 + b->picture_pitch * (size_t) b->count;
+  if (a->count == 1) {
+    size_t ext = 0;
+    for (int c = 0; c < a->ncomp; c++)
+      ext = max (ext, a->offset[c] + (size_t) a->stride[c] * a->height[c]);
+    a1 = a0 + ext;
+  }
+  if (b->count == 1) {
+    size_t ext = 0;
+    for (int c = 0; c < b->ncomp; c++)
+      ext = max (ext, b->offset[c] + (size_t) b->stride[c] * b->height[c]);
+    b1 = b0 + ext;
+  }
+  return a0 < b1 && b0 < a1;
+}
+
+static PlaneSet ws_planeset (void *ws, const WsLayout &L, const size_t *off, const int *stride)
+{
+  PlaneSet p;
+  p.base = (char *) ws;
+  p.pic_pitch = L.pic_pitch;
+  for (int c = 0; c < SB2_MAX_COMPONENTS; c++) { p.off[c] = off[c]; p.stride[c] = stride[c]; }
+  return p;
+}
+
+static PlaneSet scaled (const PlaneSet &p, int shift)
+{
+  PlaneSet q = p;
+  for (int c = 0; c < SB2_MAX_COMPONENTS; c++) q.stride[c] = p.stride[c] << shift;
+  return q;
+}
+
+static int copy_back (const sb2_slab *dst, void *ws, const WsLayout &L, int bpp, cudaStream_t st)
+{
+  for (int p = 0; p < dst->count; p++) {
+    for (int c = 0; c < dst->ncomp; c++) {
+      cudaError_t e = cudaMemcpy2DAsync ((char *) dst->base + (size_t) p * dst->picture_pitch + dst->offset[c],
+          dst->stride[c], (char *) ws + (size_t) p * L.pic_pitch + L.off_full[c], L.stride_full[c],
+          (size_t) dst->width[c] * bpp, dst->height[c], cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return check_cuda (e, "cudaMemcpy2DAsync(copy back)");
+    }
+  }
+  return SB2_OK;
+}
+
+static int iwt_run (bool inv, const sb2_slab *src, const sb2_slab *dst, int is_s32, int filter,
+    int depth, void *workspace, size_t workspace_bytes, void *stream)
+{
+  const int bpp = is_s32 ? 4 : 2;
+  int rc = validate (src, dst, bpp, depth);
+  if (rc) return rc;
+  if (filter < 0 || filter > 6) return set_error (SB2_ERR_ARG, "bad wavelet filter index %d", filter);
+  const bool in_place = slabs_alias (src, dst);
+  const WsLayout L = ws_layout (src, bpp, depth, in_place);
+  const size_t need = L.pic_pitch * (size_t) src->count;
+  if (need > 0 && (!workspace || workspace_bytes < need))
+    return set_error (SB2_ERR_WORKSPACE, "wavelet workspace too small: need %zu bytes, have %zu",
+        need, workspace ? workspace_bytes : (size_t) 0);
+  cudaStream_t st = as_stream (stream);
+
+  const PlaneSet S = planeset_from_slab (src);
+  const PlaneSet D = planeset_from_slab (dst);
+  const PlaneSet T1 = ws_planeset (workspace, L, L.off_t1, L.stride_t1);
+  const PlaneSet T0 = ws_planeset (workspace, L, L.off_t0, L.stride_t0);
+  const PlaneSet FULL = ws_planeset (workspace, L, L.off_full, L.stride_full);
+
+  LevelArgs a;
+  a.ncomp = src->ncomp;
+  for (int c = 0; c < SB2_MAX_COMPONENTS; c++) a.w[c] = a.h[c] = 0;
+
+  if (!inv) {
+    // level l: X = (l==0 ? src : T[l&1]);  bands -> dst (stride<<l);
+    // LL -> (l==depth-1 ? dst (stride<<(l+1)) : T[(l+1)&1])
+    PlaneSet in0 = S;
+    if (in_place) {
+      // stage the input so level 0 can write its bands into dst == src
+      for (int p = 0; p < src->count; p++)
+        for (int c = 0; c < src->ncomp; c++) {
+          cudaError_t e = cudaMemcpy2DAsync ((char *) workspace + (size_t) p * L.pic_pitch + L.off_full[c],
+              L.stride_full[c], (char *) src->base + (size_t) p * src->picture_pitch + src->offset[c],
+              src->stride[c], (size_t) src->width[c] * bpp, src->height[c], cudaMemcpyDeviceToDevice, st);
+          if (e != cudaSuccess) return check_cuda (e, "cudaMemcpy2DAsync(stage in)");
+        }
+      in0 = FULL;
+    }
+    for (int l = 0; l < depth; l++) {
+      for (int c = 0; c < src->ncomp; c++) { a.w[c] = src->width[c] >> l; a.h[c] = src->height[c] >> l; }
+      a.dense = (l == 0) ? in0 : ((l & 1) ? T1 : T0);
+      a.bands = scaled (D, l);
+      a.ll = (l == depth - 1) ? scaled (D, l + 1) : (((l + 1) & 1) ? T1 : T0);
+      rc = launch_level_any (false, is_s32, filter, a, src->count, st);
+      if (rc) return rc;
+    }
+    return SB2_OK;
+  }
+
+  // inverse: level l = depth-1 .. 0
+  //   LL <- (l==depth-1 ? src (stride<<(l+1)) : T[(l+1)&1]);  bands <- src (stride<<l);
+  //   Y  -> (l==0 ? dst (or FULL when in place) : T[l&1])
+  for (int l = depth - 1; l >= 0; l--) {
+    for (int c = 0; c < src->ncomp; c++) { a.w[c] = src->width[c] >> l; a.h[c] = src->height[c] >> l; }
+    a.ll = (l == depth - 1) ? scaled (S, l + 1) : (((l + 1) & 1) ? T1 : T0);
+    a.bands = scaled (S, l);
+    a.dense = (l == 0) ? (in_place ? FULL : D) : ((l & 1) ? T1 : T0);
+    rc = launch_level_any (true, is_s32, filter, a, src->count, st);
+    if (rc) return rc;
+  }
+  if (in_place) return copy_back (dst, workspace, L, bpp, st);
+  return SB2_OK;
+}
+
+}  // namespace sb2
+
+extern "C" size_t
+sb2_iwt_workspace_bytes (const sb2_slab *slab, int is_s32, int depth, int in_place)
+{
+  if (!slab || slab->ncomp < 1 || slab->ncomp > SB2_MAX_COMPONENTS) return 0;
+  const sb2::WsLayout L = sb2::ws_layout (slab, is_s32 ? 4 : 2, depth, in_place);
+  return L.pic_pitch * (size_t) slab->count;
+}
+
+extern "C" int
+sb2_iwt_forward (const sb2_slab *src, const sb2_slab *dst, int is_s32, int filter, int depth,
+    void *workspace, size_t workspace_bytes, void *stream)
+{
+  return sb2::iwt_run (false, src, dst, is_s32, filter, depth, workspace, workspace_bytes, stream);
+}
+
+extern "C" int
+sb2_iwt_inverse (const sb2_slab *src, const sb2_slab *dst, int is_s32, int filter, int depth,
+    void *workspace, size_t workspace_bytes, void *stream)
+{
+  return sb2::iwt_run (true, src, dst, is_s32, filter, depth, workspace, workspace_bytes, stream);
+}

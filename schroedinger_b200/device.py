@@ -1,0 +1,172 @@
+"""Device-side picture slabs and thin wrappers over the sb2_* C-ABI.
+
+torch is used only for device memory, streams and host<->device copies
+(plumbing); all arithmetic happens in libschro_b200.so.
+
+Layout follows the reference's frame allocator
+(schroedinger/schroframe.c:60-191): planar components in one region, each
+plane surrounded by ``extension`` border pixels, row stride
+``ROUND_UP_16((w + 2*ext) * bpp)`` and x4 for "upsampled" frames whose four
+half-pel phase planes sit side by side in every row.  A slab repeats that
+frame layout ``count`` times at a fixed pitch so a batch is one launch.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import Slab, lib, check
+
+_BPP = {"u8": 1, "s16": 2, "s32": 4}
+_NP = {"u8": np.uint8, "s16": np.int16, "s32": np.int32}
+_TORCH = {"u8": torch.uint8, "s16": torch.int16, "s32": torch.int32}
+
+
+def _round_up(x, a):
+    return (x + a - 1) // a * a
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("schroedinger_b200 needs a CUDA device: there is no CPU fallback")
+
+
+class FrameLayout:
+    """Byte layout of one frame (all components), reference-compatible."""
+
+    def __init__(self, depth, comp_sizes, extension=0, upsampled=False):
+        self.depth = depth
+        self.bpp = _BPP[depth]
+        self.comp_sizes = [(int(w), int(h)) for (w, h) in comp_sizes]
+        self.extension = int(extension)
+        self.upsampled = bool(upsampled)
+        self.stride, self.length, self.offset = [], [], []
+        pos = 0
+        for (w, h) in self.comp_sizes:
+            stride = _round_up((w + 2 * self.extension) * self.bpp, 16)
+            if self.upsampled:
+                stride *= 4
+            length = stride * (h + 2 * self.extension)
+            self.stride.append(stride)
+            self.length.append(length)
+            # pixel (0,0) of (phase 0 of) the plane
+            self.offset.append(pos + stride * self.extension + self.bpp * self.extension)
+            pos += length
+        self.frame_bytes = pos
+        self.pitch = _round_up(pos, 256)
+
+    @staticmethod
+    def yuv420(depth, width, height, extension=0, upsampled=False):
+        cw, ch = (width + 1) // 2, (height + 1) // 2
+        return FrameLayout(depth, [(width, height), (cw, ch), (cw, ch)], extension, upsampled)
+
+
+class PictureSlab:
+    """``count`` frames of one layout in a single device allocation."""
+
+    def __init__(self, layout, count, device="cuda", zero=True):
+        require_cuda()
+        self.layout = layout
+        self.count = int(count)
+        alloc = torch.zeros if zero else torch.empty
+        self.buf = alloc(layout.pitch * self.count, dtype=torch.uint8, device=device)
+        self.slab = self._make_slab()
+
+    def _make_slab(self):
+        L = self.layout
+        s = Slab()
+        s.base = self.buf.data_ptr()
+        s.picture_pitch = L.pitch
+        s.count = self.count
+        s.ncomp = len(L.comp_sizes)
+        for c, (w, h) in enumerate(L.comp_sizes):
+            s.offset[c] = L.offset[c]
+            s.stride[c] = L.stride[c]
+            s.width[c] = w
+            s.height[c] = h
+        return s
+
+    @property
+    def nbytes(self):
+        return self.buf.numel()
+
+    def plane(self, pic, comp, phase=0, with_border=False):
+        """Strided torch view of one plane (of one phase) of one picture."""
+        L = self.layout
+        w, h = L.comp_sizes[comp]
+        ext = L.extension
+        start = pic * L.pitch + L.offset[comp]
+        if L.upsampled:
+            start += (L.stride[comp] >> 2) * phase
+        if with_border:
+            start -= L.stride[comp] * ext + L.bpp * ext
+            w, h = w + 2 * ext, h + 2 * ext
+        return _as_typed(self.buf, start, h, w, L.stride[comp], L.depth)
+
+    def upload(self, pic, comp, array, phase=0, with_border=False):
+        dst = self.plane(pic, comp, phase, with_border)
+        src = torch.from_numpy(np.ascontiguousarray(array, dtype=_NP[self.layout.depth]))
+        dst.copy_(src.to(dst.device, non_blocking=False))
+
+    def download(self, pic, comp, phase=0, with_border=False):
+        return self.plane(pic, comp, phase, with_border).cpu().numpy().copy()
+
+
+def _as_typed(buf, start, h, w, stride, depth):
+    bpp = _BPP[depth]
+    assert start % bpp == 0 and stride % bpp == 0
+    typed = buf.view(_TORCH[depth])
+    return torch.as_strided(typed, (h, w), (stride // bpp, 1), start // bpp)
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return ctypes.c_void_p(stream.cuda_stream)
+
+
+class Workspace:
+    """Grow-only device scratch buffer."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes):
+        if nbytes == 0:
+            return ctypes.c_void_p(0), 0
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        return ctypes.c_void_p(self.buf.data_ptr()), self.buf.numel()
+
+
+_default_ws = Workspace()
+
+
+def iwt_workspace_bytes(slab, depth_bits, transform_depth, in_place):
+    return lib.sb2_iwt_workspace_bytes(ctypes.byref(slab), 1 if depth_bits == "s32" else 0,
+                                       transform_depth, 1 if in_place else 0)
+
+
+def iwt_forward(src, dst, filter_index, transform_depth, workspace=None, stream=None):
+    """Multi-level forward transform of every component of every picture of ``src``
+    into ``dst`` (PictureSlab; may be the same slab)."""
+    _iwt(lib.sb2_iwt_forward, "sb2_iwt_forward", src, dst, filter_index, transform_depth,
+         workspace, stream)
+
+
+def iwt_inverse(src, dst, filter_index, transform_depth, workspace=None, stream=None):
+    _iwt(lib.sb2_iwt_inverse, "sb2_iwt_inverse", src, dst, filter_index, transform_depth,
+         workspace, stream)
+
+
+def _iwt(fn, name, src, dst, filter_index, transform_depth, workspace, stream):
+    require_cuda()
+    is_s32 = 1 if src.layout.depth == "s32" else 0
+    assert src.layout.depth == dst.layout.depth and src.layout.depth in ("s16", "s32")
+    in_place = src.buf.data_ptr() == dst.buf.data_ptr()
+    ws = workspace or _default_ws
+    need = lib.sb2_iwt_workspace_bytes(ctypes.byref(src.slab), is_s32, transform_depth,
+                                       1 if in_place else 0)
+    ptr, size = ws.get(need)
+    check(fn(ctypes.byref(src.slab), ctypes.byref(dst.slab), is_s32, filter_index,
+             transform_depth, ptr, size, _stream_ptr(stream)), name)

@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Quick device-resident timing of the wavelet transforms (development aid)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from schroedinger_b200 import device as dev
+
+def run(name, depth_name, filt, depth, w, h, count, inverse, iters=10):
+    layout = dev.FrameLayout.yuv420(depth_name, w, h)
+    a = dev.PictureSlab(layout, count, zero=False)
+    b = dev.PictureSlab(layout, count, zero=False)
+    a.buf.random_(0, 255)
+    fn = dev.iwt_inverse if inverse else dev.iwt_forward
+    for _ in range(3):
+        fn(a, b, filt, depth)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn(a, b, filt, depth)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    ncoef = sum(cw * ch for cw, ch in layout.comp_sizes)
+    alg = 2 * ncoef * layout.bpp * count
+    print(f"{name:28s} {count:4d} pics {ms:8.3f} ms  {count/ms*1e3:9.1f} pics/s  "
+          f"{alg/ms/1e6:8.1f} GB/s algorithmic ({alg/ms/1e6/6545.9*100:5.1f}% of 6545.9)")
+
+if __name__ == "__main__":
+    run("LeGall s16 1080p d4 fwd", "s16", 1, 4, 1920, 1088, 64, False)
+    run("LeGall s16 1080p d4 inv", "s16", 1, 4, 1920, 1088, 64, True)
+    run("DD9/7 s16 1080p d4 inv", "s16", 0, 4, 1920, 1088, 64, True)
+    run("DD9/7 s16 1080p d4 fwd", "s16", 0, 4, 1920, 1088, 64, False)
+    run("Daub s32 2160p d5 inv", "s32", 6, 5, 3840, 2176, 8, True)
+    run("Daub s32 2160p d5 fwd", "s32", 6, 5, 3840, 2176, 8, False)
+    run("Daub s32 2160p d1 inv", "s32", 6, 1, 3840, 2176, 8, True)
+    run("Fidelity s16 1080p d4 inv", "s16", 5, 4, 1920, 1088, 64, True)
+    run("Haar0 s16 1080p d4 inv", "s16", 3, 4, 1920, 1088, 64, True)
