@@ -47,6 +47,13 @@ int sb2_version (void);
 /* number of kernels this library has launched in the calling process */
 unsigned long long sb2_launch_count (void);
 
+/* Per-launch device timing (CUDA events on the launching stream): enable, run,
+ * synchronise the stream(s), then read (tag, milliseconds, algorithmic bytes). */
+void sb2_profile_enable (int on);
+void sb2_profile_reset (void);
+int sb2_profile_count (void);
+int sb2_profile_get (int index, char *tag, int tag_len, float *ms, double *bytes);
+
 /* ------------------------------------------------------------------------
  * Picture slabs.  A slab is `count` pictures laid out `picture_pitch` bytes
  * apart in one device allocation; every picture has `ncomp` component planes

@@ -1,0 +1,346 @@
+/*
+ * schro_b200_compat.h -- the reference's C API for the picture core, as exported
+ * by libschro_b200.so (host layer in schroedinger_b200/host/, C, calling the
+ * sb2_* CUDA layer of schro_b200.h).
+ *
+ * The structs below are layout-compatible with the reference's (same field
+ * order and types; tests/test_abi_layout.py compiles both headers and compares
+ * sizeof/offsetof where /root/reference is available), so a libschroedinger
+ * build can route these symbols here without touching callers.  Each
+ * declaration cites the reference declaration it stands in for.
+ *
+ * Frames may live in
+ *   - ordinary host memory           (malloc; copies are staged through pinned buffers),
+ *   - pinned host memory             (schro_memory_domain_new_pinned; direct DMA),
+ *   - device memory                  (schro_memory_domain_new_cuda; zero-copy),
+ * and every entry point accepts all three; the arithmetic always runs on the GPU.
+ * Errors follow the reference: log + abort (schroedinger/schrodebug.h:55-60).
+ */
+#ifndef SCHRO_B200_COMPAT_H
+#define SCHRO_B200_COMPAT_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef unsigned int schro_bool;          /* schroedinger/schroutils.h:26 */
+
+/* schroedinger/schroframe.h:22-44 */
+typedef enum _SchroFrameFormat {
+  SCHRO_FRAME_FORMAT_U8_444 = 0x00,
+  SCHRO_FRAME_FORMAT_U8_422 = 0x01,
+  SCHRO_FRAME_FORMAT_U8_420 = 0x03,
+  SCHRO_FRAME_FORMAT_S16_444 = 0x04,
+  SCHRO_FRAME_FORMAT_S16_422 = 0x05,
+  SCHRO_FRAME_FORMAT_S16_420 = 0x07,
+  SCHRO_FRAME_FORMAT_S32_444 = 0x08,
+  SCHRO_FRAME_FORMAT_S32_422 = 0x09,
+  SCHRO_FRAME_FORMAT_S32_420 = 0x0b
+} SchroFrameFormat;
+
+#define SCHRO_FRAME_FORMAT_DEPTH(format) ((format) & 0xc)
+#define SCHRO_FRAME_FORMAT_DEPTH_U8 0x00
+#define SCHRO_FRAME_FORMAT_DEPTH_S16 0x04
+#define SCHRO_FRAME_FORMAT_DEPTH_S32 0x08
+#define SCHRO_FRAME_FORMAT_H_SHIFT(format) ((format) & 0x1)
+#define SCHRO_FRAME_FORMAT_V_SHIFT(format) (((format)>>1) & 0x1)
+#define SCHRO_FRAME_CACHE_SIZE 32
+
+typedef struct _SchroFrame SchroFrame;
+typedef struct _SchroFrameData SchroFrameData;
+typedef struct _SchroMemoryDomain SchroMemoryDomain;
+typedef void (*SchroFrameFreeFunc) (SchroFrame *frame, void *priv);
+
+/* schroedinger/schroframe.h:58-67 */
+struct _SchroFrameData {
+  SchroFrameFormat format;
+  void *data;
+  int stride;
+  int width;
+  int height;
+  int length;
+  int h_shift;
+  int v_shift;
+};
+
+/* schroedinger/schroframe.h:69-94 */
+struct _SchroFrame {
+  int refcount;
+  SchroFrameFreeFunc free;
+  SchroMemoryDomain *domain;
+  void *regions[3];
+  void *priv;
+
+  SchroFrameFormat format;
+  int width;
+  int height;
+
+  SchroFrameData components[3];
+
+  int is_virtual;
+  int cached_lines[3][SCHRO_FRAME_CACHE_SIZE];
+  SchroFrame *virt_frame1;
+  SchroFrame *virt_frame2;
+  void (*render_line) (SchroFrame *frame, void *dest, int component, int i);
+  void *virt_priv;
+  void *virt_priv2;
+
+  int extension;
+  int cache_offset[3];
+  int is_upsampled;
+  schro_bool upsample_done;
+};
+
+/* schroedinger/schrodomain.h:13-28.  Only `flags`, `alloc`, `free` are used here;
+ * the slot cache is kept so the struct has the reference's size. */
+#define SCHRO_MEMORY_DOMAIN_SLOTS 1000
+struct _SchroMemoryDomain {
+  void *mutex;
+  unsigned int flags;
+  void *(*alloc) (int size);
+  void *(*alloc_2d) (int depth, int width, int height);
+  void (*free) (void *ptr, int size);
+  struct {
+    unsigned int flags;
+    void *ptr;
+    int size;
+    void *priv;
+  } slots[SCHRO_MEMORY_DOMAIN_SLOTS];
+};
+#define SCHRO_MEMORY_DOMAIN_CPU 0x0001
+#define SCHRO_MEMORY_DOMAIN_CUDA 0x0002
+#define SCHRO_MEMORY_DOMAIN_PINNED 0x0100      /* new: page-locked host memory */
+#define SCHRO_MEMORY_DOMAIN_SLOT_ALLOCATED 0x0001
+#define SCHRO_MEMORY_DOMAIN_SLOT_IN_USE 0x0002
+
+/* schroedinger/schrobitstream.h:79-86 */
+typedef enum _SchroChromaFormat {
+  SCHRO_CHROMA_444 = 0,
+  SCHRO_CHROMA_422,
+  SCHRO_CHROMA_420
+} SchroChromaFormat;
+#define SCHRO_CHROMA_FORMAT_H_SHIFT(format) (((format) == SCHRO_CHROMA_444)?0:1)
+#define SCHRO_CHROMA_FORMAT_V_SHIFT(format) (((format) == SCHRO_CHROMA_420)?1:0)
+
+/* schroedinger/schrovideoformat.h (struct _SchroVideoFormat) */
+typedef struct _SchroVideoFormat {
+  int index;
+  int width;
+  int height;
+  SchroChromaFormat chroma_format;
+  schro_bool interlaced;
+  schro_bool top_field_first;
+  int frame_rate_numerator;
+  int frame_rate_denominator;
+  int aspect_ratio_numerator;
+  int aspect_ratio_denominator;
+  int clean_width;
+  int clean_height;
+  int left_offset;
+  int top_offset;
+  int luma_offset;
+  int luma_excursion;
+  int chroma_offset;
+  int chroma_excursion;
+  int colour_primaries;
+  int colour_matrix;
+  int transfer_function;
+  int interlaced_coding;
+  int unused0;
+  int unused1;
+  int unused2;
+} SchroVideoFormat;
+
+#define SCHRO_LIMIT_TRANSFORM_DEPTH 6     /* schroedinger/schrolimits.h:21 */
+#define SCHRO_LIMIT_BLOCK_SIZE 64         /* schroedinger/schrolimits.h:67 */
+
+/* schroedinger/schroparams.h:18-29 */
+typedef struct _SchroGlobalMotion {
+  int b0, b1, a_exp, a00, a01, a10, a11, c_exp, c0, c1;
+} SchroGlobalMotion;
+
+/* schroedinger/schroparams.h:31-77 */
+typedef struct _SchroParams {
+  SchroVideoFormat *video_format;
+  int is_noarith;
+  int wavelet_filter_index;
+  int transform_depth;
+  int horiz_codeblocks[SCHRO_LIMIT_TRANSFORM_DEPTH + 1];
+  int vert_codeblocks[SCHRO_LIMIT_TRANSFORM_DEPTH + 1];
+  int codeblock_mode_index;
+  int num_refs;
+  int have_global_motion;
+  int xblen_luma;
+  int yblen_luma;
+  int xbsep_luma;
+  int ybsep_luma;
+  int mv_precision;
+  SchroGlobalMotion global_motion[2];
+  int picture_pred_mode;
+  int picture_weight_bits;
+  int picture_weight_1;
+  int picture_weight_2;
+  int is_lowdelay;
+  int n_horiz_slices;
+  int n_vert_slices;
+  int slice_bytes_num;
+  int slice_bytes_denom;
+  int quant_matrix[3 * SCHRO_LIMIT_TRANSFORM_DEPTH + 1];
+  int iwt_chroma_width;
+  int iwt_chroma_height;
+  int iwt_luma_width;
+  int iwt_luma_height;
+  int x_num_blocks;
+  int y_num_blocks;
+  int x_offset;
+  int y_offset;
+} SchroParams;
+
+/* schroedinger/schromotion.h:20-37 (20 bytes) */
+typedef struct _SchroMotionVector {
+  unsigned int pred_mode : 2;
+  unsigned int using_global : 1;
+  unsigned int split : 2;
+  unsigned int unused : 3;
+  unsigned int scan : 8;
+  uint32_t metric;
+  uint32_t chroma_metric;
+  union {
+    struct { int16_t dx[2]; int16_t dy[2]; } vec;
+    struct { int16_t dc[3]; } dc;
+  } u;
+} SchroMotionVector;
+
+/* schroedinger/schromotion.h:39-43 */
+typedef struct _SchroMotionField {
+  int x_num_blocks;
+  int y_num_blocks;
+  SchroMotionVector *motion_vectors;
+} SchroMotionField;
+
+/* schroedinger/schromotion.h:53-88.  Only src1, src2, motion_vectors and params
+ * are inputs; the rest is the reference renderer's scratch state, kept for layout. */
+typedef struct _SchroMotion {
+  SchroFrame *src1;
+  SchroFrame *src2;
+  SchroMotionVector *motion_vectors;
+  SchroParams *params;
+  int ref_weight_precision;
+  int ref1_weight;
+  int ref2_weight;
+  int mv_precision;
+  int xoffset;
+  int yoffset;
+  int xbsep;
+  int ybsep;
+  int xblen;
+  int yblen;
+  SchroFrameData block;
+  SchroFrameData alloc_block;
+  SchroFrameData obmc_weight;
+  SchroFrameData alloc_block_ref[2];
+  SchroFrameData block_ref[2];
+  int weight_x[SCHRO_LIMIT_BLOCK_SIZE];
+  int weight_y[SCHRO_LIMIT_BLOCK_SIZE];
+  int width;
+  int height;
+  int max_fast_x;
+  int max_fast_y;
+  schro_bool simple_weight;
+  schro_bool oneref_noscale;
+} SchroMotion;
+
+/* schroedinger/schromotionest.h:22-31 */
+typedef struct _SchroHierBm {
+  int ref_count;
+  int ref;
+  int hierarchy_levels;
+  SchroParams *params;
+  SchroFrame **downsampled_src;
+  SchroFrame **downsampled_ref;
+  SchroMotionField **downsampled_mf;
+  schro_bool use_chroma;
+} SchroHierBm;
+
+/* ---- library / domains -------------------------------------------------- */
+void schro_init (void);                                   /* schroedinger/schro.c:23 */
+/* schroedinger/schrocuda.h:9 (schro_memory_domain_new_cuda) */
+SchroMemoryDomain *schro_memory_domain_new_cuda (void);
+SchroMemoryDomain *schro_memory_domain_new_pinned (void); /* new: cudaHostAlloc'd frames */
+void schro_memory_domain_free (SchroMemoryDomain *domain); /* schroedinger/schrodomain.h:43 */
+void *schro_memory_domain_alloc (SchroMemoryDomain *domain, int size);      /* :45 */
+void schro_memory_domain_memfree (SchroMemoryDomain *domain, void *ptr);    /* :48 */
+
+/* ---- frames (schroedinger/schroframe.h:96-160) ---------------------------- */
+SchroFrame *schro_frame_new (void);
+SchroFrame *schro_frame_new_and_alloc (SchroMemoryDomain *domain,
+    SchroFrameFormat format, int width, int height);
+SchroFrame *schro_frame_new_and_alloc_extended (SchroMemoryDomain *domain,
+    SchroFrameFormat format, int width, int height, int extension);
+SchroFrame *schro_frame_new_and_alloc_full (SchroMemoryDomain *domain,
+    SchroFrameFormat format, int width, int height, int extension, int upsampled);
+SchroFrame *schro_frame_ref (SchroFrame *frame);
+void schro_frame_unref (SchroFrame *frame);
+/* schroedinger/schrocuda.h:14-16 / schrogpuframe.h:14-15: move a frame between domains */
+void schro_frame_to_gpu (SchroFrame *dest, SchroFrame *src);
+void schro_gpuframe_to_cpu (SchroFrame *dest, SchroFrame *src);
+
+void schro_upsampled_frame_get_framedata (SchroFrame *upframe,
+    SchroFrameData *fd, int up_index, int component);      /* schroframe.c:1917 */
+
+/* ---- wavelets (schroedinger/schrowavelet.h:12-14) ------------------------- */
+void schro_wavelet_transform_2d (SchroFrameData *fd, int type, int16_t *tmp);
+void schro_wavelet_inverse_transform_2d (SchroFrameData *fd_dest,
+    SchroFrameData *fd_src, int type, int16_t *tmp);
+/* frame-granular drivers: schroedinger/schroframe.c:1192 and the decoder's
+ * schro_decoder_inverse_iwt_transform (schroedinger/schrodecoder.c:1809), named as
+ * the reference's own testsuite/cuda/cuda.c:96 calls it */
+void schro_frame_iwt_transform (SchroFrame *frame, SchroParams *params);
+void schro_frame_inverse_iwt_transform (SchroFrame *frame, SchroParams *params);
+
+/* ---- upsample / downsample / edge extension (schroedinger/schroframe.h:130-160) */
+void schro_frame_downsample (SchroFrame *dest, SchroFrame *src);
+void schro_frame_upsample_horiz (SchroFrameData *dest, SchroFrameData *src);
+void schro_frame_upsample_vert (SchroFrameData *dest, SchroFrameData *src);
+void schro_frame_mc_edgeextend (SchroFrame *frame);
+void schro_upsampled_frame_upsample (SchroFrame *df);
+
+/* ---- OBMC (schroedinger/schromotion.h:90-102) ------------------------------ */
+SchroMotion *schro_motion_new (SchroParams *params, SchroFrame *ref1, SchroFrame *ref2);
+void schro_motion_free (SchroMotion *motion);
+void schro_motion_render (SchroMotion *motion, SchroFrame *dest,
+    SchroFrame *addframe, int add, SchroFrame *output_frame);
+void schro_motion_render_u8 (SchroMotion *motion, SchroFrame *dest,
+    SchroFrame *addframe, int add, SchroFrame *output_frame);
+void schro_motion_init_obmc_weight (SchroMotion *motion);
+
+/* ---- SAD primitives (schroedinger/schrometric.h:57-86) ---------------------- */
+int schro_metric_absdiff_u8 (uint8_t *a, int a_stride, uint8_t *b, int b_stride,
+    int width, int height);
+int schro_metric_get (SchroFrameData *src1, SchroFrameData *src2, int width, int height);
+int schro_metric_get_dc (SchroFrameData *src, int value, int width, int height);
+int schro_metric_get_biref (SchroFrameData *fd, SchroFrameData *src1, int weight1,
+    SchroFrameData *src2, int weight2, int shift, int width, int height);
+
+/* ---- hierarchical block matching (schroedinger/schromotionest.h:112-120) ---- */
+SchroMotionField *schro_motion_field_new (int x_num_blocks, int y_num_blocks);
+void schro_motion_field_free (SchroMotionField *field);
+/* schro_hbm_new (schroedinger/schrohierbm.c:25-64) takes a SchroEncoderFrame; this is
+ * the same constructor with the five fields it reads passed explicitly (INTEGRATION.md
+ * shows the one-line shim). frames[0] = full-resolution picture, frames[i] = level i. */
+SchroHierBm *schro_hbm_new_from_frames (SchroParams *params, int ref,
+    int hierarchy_levels, schro_bool use_chroma,
+    SchroFrame **src_frames, SchroFrame **ref_frames);
+SchroHierBm *schro_hbm_ref (SchroHierBm *schro_hbm);
+void schro_hbm_unref (SchroHierBm *schro_hbm);
+void schro_hbm_scan (SchroHierBm *schro_hbm);
+void schro_hierarchical_bm_scan_hint (SchroHierBm *schro_hbm, int shift, int h_range);
+SchroMotionField *schro_hbm_motion_field (SchroHierBm *schro_hbm, int level);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

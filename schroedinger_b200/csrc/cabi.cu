@@ -3,6 +3,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
+#include <vector>
 
 namespace sb2 {
 
@@ -27,6 +29,35 @@ int check_cuda (cudaError_t e, const char *what)
 
 void count_launch (unsigned n) { g_launches.fetch_add (n, std::memory_order_relaxed); }
 
+// ---- optional per-launch device timing (used by bench.py for the roofline) ----
+struct ProfRec { char tag[48]; cudaEvent_t e0, e1; double bytes; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static std::atomic<int> g_prof_on{0};
+
+bool profiling () { return g_prof_on.load (std::memory_order_relaxed) != 0; }
+
+int prof_begin (const char *tag, double bytes, cudaStream_t st)
+{
+  if (!profiling ()) return -1;
+  ProfRec r;
+  snprintf (r.tag, sizeof (r.tag), "%s", tag);
+  r.bytes = bytes;
+  cudaEventCreate (&r.e0);
+  cudaEventCreate (&r.e1);
+  cudaEventRecord (r.e0, st);
+  std::lock_guard<std::mutex> lk (g_prof_mu);
+  g_prof.push_back (r);
+  return (int) g_prof.size () - 1;
+}
+
+void prof_end (int id, cudaStream_t st)
+{
+  if (id < 0) return;
+  std::lock_guard<std::mutex> lk (g_prof_mu);
+  cudaEventRecord (g_prof[id].e1, st);
+}
+
 }  // namespace sb2
 
 extern "C" const char *sb2_last_error (void) { return sb2::g_err; }
@@ -34,4 +65,34 @@ extern "C" int sb2_version (void) { return 1; }
 extern "C" unsigned long long sb2_launch_count (void)
 {
   return sb2::g_launches.load (std::memory_order_relaxed);
+}
+
+// Per-launch CUDA-event timing on the launching stream.  Enable, run, synchronise,
+// then read the records back.
+extern "C" void sb2_profile_enable (int on)
+{
+  sb2::g_prof_on.store (on, std::memory_order_relaxed);
+}
+extern "C" void sb2_profile_reset (void)
+{
+  std::lock_guard<std::mutex> lk (sb2::g_prof_mu);
+  for (auto &r : sb2::g_prof) { cudaEventDestroy (r.e0); cudaEventDestroy (r.e1); }
+  sb2::g_prof.clear ();
+}
+extern "C" int sb2_profile_count (void)
+{
+  std::lock_guard<std::mutex> lk (sb2::g_prof_mu);
+  return (int) sb2::g_prof.size ();
+}
+extern "C" int sb2_profile_get (int i, char *tag, int tag_len, float *ms, double *bytes)
+{
+  std::lock_guard<std::mutex> lk (sb2::g_prof_mu);
+  if (i < 0 || i >= (int) sb2::g_prof.size ()) return SB2_ERR_ARG;
+  auto &r = sb2::g_prof[i];
+  if (tag && tag_len > 0) snprintf (tag, tag_len, "%s", r.tag);
+  if (bytes) *bytes = r.bytes;
+  float t = 0.f;
+  cudaError_t e = cudaEventElapsedTime (&t, r.e0, r.e1);
+  if (ms) *ms = t;
+  return e == cudaSuccess ? SB2_OK : SB2_ERR_CUDA;
 }

@@ -12,6 +12,15 @@ namespace sb2 {
 int set_error (int code, const char *fmt, ...);
 int check_cuda (cudaError_t e, const char *what);
 void count_launch (unsigned n = 1);
+// optional per-launch event timing (cabi.cu); tag names the kernel, bytes = algorithmic bytes
+bool profiling ();
+int prof_begin (const char *tag, double bytes, cudaStream_t st);
+void prof_end (int id, cudaStream_t st);
+struct LaunchScope {
+  int id; cudaStream_t st;
+  LaunchScope (const char *tag, double bytes, cudaStream_t s) : id (prof_begin (tag, bytes, s)), st (s) { count_launch (); }
+  ~LaunchScope () { prof_end (id, st); }
+};
 
 static inline cudaStream_t as_stream (void *s) { return reinterpret_cast<cudaStream_t> (s); }
 

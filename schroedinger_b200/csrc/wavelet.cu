@@ -20,6 +20,7 @@
 // No tensor cores: nothing here is a contraction.  The kernel is HBM/LSU bound.
 
 #include "common.cuh"
+#include <cstdio>
 
 namespace sb2 {
 
@@ -370,8 +371,17 @@ static int launch_level (const LevelArgs &a, int count, cudaStream_t stream)
   }
   if (maxn == 0 || maxm == 0) return SB2_OK;
   dim3 grid (ceil_div (maxn, TWH), ceil_div (maxm, THH), a.ncomp * count);
-  wavelet_level_kernel<T, F, INV><<<grid, NTHREADS, G::SMEM, stream>>> (a);
-  count_launch ();
+  {
+    char tag[48];
+    double bytes = 0;
+    if (profiling ()) {
+      snprintf (tag, sizeof (tag), "wavelet_%s_%s_f%d_w%d", INV ? "inv" : "fwd",
+          sizeof (T) == 4 ? "s32" : "s16", F, a.w[0]);
+      for (int c = 0; c < a.ncomp; c++) bytes += 2.0 * a.w[c] * a.h[c] * sizeof (T) * count;
+    }
+    LaunchScope scope (tag, bytes, stream);
+    wavelet_level_kernel<T, F, INV><<<grid, NTHREADS, G::SMEM, stream>>> (a);
+  }
   return check_cuda (cudaGetLastError (), "wavelet_level_kernel launch");
 }
 

@@ -1,0 +1,47 @@
+/* schro_host.h -- internals shared by the C host layer (schroedinger_b200/host/). */
+#ifndef SCHRO_HOST_H
+#define SCHRO_HOST_H
+
+#include <cuda_runtime_api.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "schro_b200.h"
+#include "schro_b200_compat.h"
+
+/* log + abort, like SCHRO_ASSERT / SCHRO_ERROR (schroedinger/schrodebug.h:55-60) */
+void sb2h_fatal (const char *func, const char *fmt, ...);
+#define SB2H_CHECK(rc, what) do { if ((rc) != 0) sb2h_fatal (__func__, "%s failed (%d): %s", what, (int) (rc), sb2_last_error ()); } while (0)
+#define SB2H_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) sb2h_fatal (__func__, "%s: %s", #call, cudaGetErrorString (e_)); } while (0)
+#define SB2H_ASSERT(cond) do { if (!(cond)) sb2h_fatal (__func__, "assertion failed: %s", #cond); } while (0)
+
+enum { SB2H_MEM_PAGEABLE = 0, SB2H_MEM_PINNED = 1, SB2H_MEM_DEVICE = 2 };
+int sb2h_mem_kind (const void *ptr);
+
+/* per-thread staging context: one stream, grow-only device and pinned buffers */
+enum { SB2H_BUF_IN = 0, SB2H_BUF_OUT, SB2H_BUF_WS, SB2H_BUF_AUX0, SB2H_BUF_AUX1, SB2H_BUF_AUX2,
+       SB2H_BUF_AUX3, SB2H_NBUF };
+typedef struct {
+  cudaStream_t stream;
+  void *dev[SB2H_NBUF];
+  size_t dev_size[SB2H_NBUF];
+} Sb2hContext;
+
+Sb2hContext *sb2h_context (void);
+void *sb2h_dev_buffer (Sb2hContext *cx, int which, size_t bytes);
+
+static inline int sb2h_bpp (SchroFrameFormat format)
+{
+  switch (SCHRO_FRAME_FORMAT_DEPTH (format)) {
+    case SCHRO_FRAME_FORMAT_DEPTH_U8: return 1;
+    case SCHRO_FRAME_FORMAT_DEPTH_S16: return 2;
+    default: return 4;
+  }
+}
+
+/* rows x row_bytes rectangle, host (any kind) or device on either side, on cx->stream.
+ * Pinned host memory is DMA'd asynchronously; pageable memory is staged by the CUDA
+ * runtime (slower, the documented slow path). */
+void sb2h_copy_rect (Sb2hContext *cx, void *dst, size_t dst_stride, const void *src,
+    size_t src_stride, size_t row_bytes, int rows);
+
+#endif

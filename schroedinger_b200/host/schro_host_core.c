@@ -1,0 +1,360 @@
+/*
+ * schro_host_core.c -- host-side plumbing of the drop-in layer: logging, memory
+ * domains, frame allocation and the per-thread staging context.
+ *
+ * Mirrors (own implementation, same behaviour):
+ *   schro_memory_domain_*             schroedinger/schrodomain.c:17-136
+ *   schro_memory_domain_new_cuda      schroedinger/schrocuda.c:60-71
+ *   schro_frame_new_and_alloc_full    schroedinger/schroframe.c:60-191
+ *   schro_frame_ref / unref           schroedinger/schroframe.c:748-813
+ *   schro_frame_to_gpu / gpuframe_to_cpu  schroedinger/schrogpuframe.c:480-609
+ */
+#include "schro_host.h"
+#include <pthread.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+void
+sb2h_fatal (const char *func, const char *fmt, ...)
+{
+  va_list ap;
+  fprintf (stderr, "SCHRO-B200 ERROR: %s: ", func);
+  va_start (ap, fmt);
+  vfprintf (stderr, fmt, ap);
+  va_end (ap);
+  fprintf (stderr, "\n");
+  abort ();
+}
+
+void
+schro_init (void)
+{
+  /* nothing to JIT: the kernels are compiled for sm_100a ahead of time.  Touch the
+   * runtime so that a missing GPU is reported here and not in the first picture. */
+  int n = 0;
+  if (cudaGetDeviceCount (&n) != cudaSuccess || n == 0)
+    sb2h_fatal (__func__, "no CUDA device: the B200 picture core has no CPU fallback");
+}
+
+int
+sb2h_mem_kind (const void *ptr)
+{
+  struct cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes (&at, ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError ();
+    return SB2H_MEM_PAGEABLE;
+  }
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged)
+    return SB2H_MEM_DEVICE;
+  if (at.type == cudaMemoryTypeHost)
+    return SB2H_MEM_PINNED;
+  return SB2H_MEM_PAGEABLE;
+}
+
+/* ---- per-thread context -------------------------------------------------- */
+static __thread Sb2hContext *tl_cx;
+
+Sb2hContext *
+sb2h_context (void)
+{
+  if (!tl_cx) {
+    tl_cx = calloc (1, sizeof (Sb2hContext));
+    SB2H_CUDA (cudaStreamCreateWithFlags (&tl_cx->stream, cudaStreamNonBlocking));
+  }
+  return tl_cx;
+}
+
+void *
+sb2h_dev_buffer (Sb2hContext *cx, int which, size_t bytes)
+{
+  if (bytes == 0) return NULL;
+  if (cx->dev_size[which] < bytes) {
+    if (cx->dev[which]) {
+      SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+      SB2H_CUDA (cudaFree (cx->dev[which]));
+    }
+    bytes = (bytes + 0xfffff) & ~(size_t) 0xfffff;
+    SB2H_CUDA (cudaMalloc (&cx->dev[which], bytes));
+    cx->dev_size[which] = bytes;
+  }
+  return cx->dev[which];
+}
+
+void
+sb2h_copy_rect (Sb2hContext *cx, void *dst, size_t dst_stride, const void *src,
+    size_t src_stride, size_t row_bytes, int rows)
+{
+  if (rows <= 0 || row_bytes == 0) return;
+  SB2H_CUDA (cudaMemcpy2DAsync (dst, dst_stride, src, src_stride, row_bytes, rows,
+          cudaMemcpyDefault, cx->stream));
+}
+
+/* ---- memory domains -------------------------------------------------------- */
+static void *
+cuda_alloc (int size)
+{
+  void *p = NULL;
+  SB2H_CUDA (cudaMalloc (&p, (size_t) size));
+  return p;
+}
+
+static void
+cuda_free (void *ptr, int size)
+{
+  (void) size;
+  SB2H_CUDA (cudaFree (ptr));
+}
+
+static void *
+pinned_alloc (int size)
+{
+  void *p = NULL;
+  SB2H_CUDA (cudaHostAlloc (&p, (size_t) size, cudaHostAllocPortable));
+  return p;
+}
+
+static void
+pinned_free (void *ptr, int size)
+{
+  (void) size;
+  SB2H_CUDA (cudaFreeHost (ptr));
+}
+
+static SchroMemoryDomain *
+domain_new (unsigned int flags, void *(*alloc) (int), void (*free_fn) (void *, int))
+{
+  SchroMemoryDomain *d = calloc (1, sizeof (SchroMemoryDomain));
+  pthread_mutex_t *mu = malloc (sizeof (pthread_mutex_t));
+  pthread_mutex_init (mu, NULL);
+  d->mutex = mu;
+  d->flags = flags;
+  d->alloc = alloc;
+  d->free = free_fn;
+  return d;
+}
+
+SchroMemoryDomain *
+schro_memory_domain_new_cuda (void)
+{
+  return domain_new (SCHRO_MEMORY_DOMAIN_CUDA, cuda_alloc, cuda_free);
+}
+
+SchroMemoryDomain *
+schro_memory_domain_new_pinned (void)
+{
+  return domain_new (SCHRO_MEMORY_DOMAIN_CPU | SCHRO_MEMORY_DOMAIN_PINNED, pinned_alloc,
+      pinned_free);
+}
+
+void
+schro_memory_domain_free (SchroMemoryDomain *domain)
+{
+  int i;
+  SB2H_ASSERT (domain != NULL);
+  for (i = 0; i < SCHRO_MEMORY_DOMAIN_SLOTS; i++) {
+    if (domain->slots[i].flags & SCHRO_MEMORY_DOMAIN_SLOT_ALLOCATED)
+      domain->free (domain->slots[i].ptr, domain->slots[i].size);
+  }
+  pthread_mutex_destroy (domain->mutex);
+  free (domain->mutex);
+  free (domain);
+}
+
+/* exact-size slot reuse, as the reference's buffer pool does */
+void *
+schro_memory_domain_alloc (SchroMemoryDomain *domain, int size)
+{
+  int i;
+  void *ptr = NULL;
+  SB2H_ASSERT (domain != NULL);
+  pthread_mutex_lock (domain->mutex);
+  for (i = 0; i < SCHRO_MEMORY_DOMAIN_SLOTS; i++) {
+    unsigned int f = domain->slots[i].flags;
+    if ((f & SCHRO_MEMORY_DOMAIN_SLOT_ALLOCATED) && !(f & SCHRO_MEMORY_DOMAIN_SLOT_IN_USE) &&
+        domain->slots[i].size == size) {
+      domain->slots[i].flags |= SCHRO_MEMORY_DOMAIN_SLOT_IN_USE;
+      ptr = domain->slots[i].ptr;
+      break;
+    }
+  }
+  if (!ptr) {
+    for (i = 0; i < SCHRO_MEMORY_DOMAIN_SLOTS; i++) {
+      if (!(domain->slots[i].flags & SCHRO_MEMORY_DOMAIN_SLOT_ALLOCATED)) {
+        domain->slots[i].flags = SCHRO_MEMORY_DOMAIN_SLOT_ALLOCATED | SCHRO_MEMORY_DOMAIN_SLOT_IN_USE;
+        domain->slots[i].size = size;
+        domain->slots[i].ptr = domain->alloc (size);
+        ptr = domain->slots[i].ptr;
+        break;
+      }
+    }
+  }
+  pthread_mutex_unlock (domain->mutex);
+  if (!ptr) sb2h_fatal (__func__, "memory domain out of slots");
+  return ptr;
+}
+
+void
+schro_memory_domain_memfree (SchroMemoryDomain *domain, void *ptr)
+{
+  int i;
+  SB2H_ASSERT (domain != NULL);
+  pthread_mutex_lock (domain->mutex);
+  for (i = 0; i < SCHRO_MEMORY_DOMAIN_SLOTS; i++) {
+    if ((domain->slots[i].flags & SCHRO_MEMORY_DOMAIN_SLOT_IN_USE) && domain->slots[i].ptr == ptr) {
+      domain->slots[i].flags &= ~SCHRO_MEMORY_DOMAIN_SLOT_IN_USE;
+      pthread_mutex_unlock (domain->mutex);
+      return;
+    }
+  }
+  pthread_mutex_unlock (domain->mutex);
+  sb2h_fatal (__func__, "pointer %p does not belong to this domain", ptr);
+}
+
+/* ---- frames ------------------------------------------------------------------ */
+static pthread_mutex_t frame_mutex = PTHREAD_MUTEX_INITIALIZER;
+
+SchroFrame *
+schro_frame_new (void)
+{
+  SchroFrame *frame = calloc (1, sizeof (SchroFrame));
+  frame->refcount = 1;
+  return frame;
+}
+
+#define RUP16(x) (((x) + 15) & ~15)
+
+SchroFrame *
+schro_frame_new_and_alloc_full (SchroMemoryDomain *domain, SchroFrameFormat format,
+    int width, int height, int extension, int upsampled)
+{
+  SchroFrame *frame = schro_frame_new ();
+  const int bpp = sb2h_bpp (format);
+  const int hs = SCHRO_FRAME_FORMAT_H_SHIFT (format), vs = SCHRO_FRAME_FORMAT_V_SHIFT (format);
+  size_t total = 0, pos = 0;
+  int k;
+
+  SB2H_ASSERT (width > 0 && height > 0);
+  if (format & 0x100) sb2h_fatal (__func__, "packed formats are outside the picture core");
+  frame->format = format;
+  frame->width = width;
+  frame->height = height;
+  frame->domain = domain;
+  frame->extension = extension;
+  frame->is_upsampled = upsampled;
+  for (k = 0; k < 3; k++) {
+    SchroFrameData *c = &frame->components[k];
+    c->format = format;
+    c->width = k ? (width + (1 << hs) - 1) >> hs : width;
+    c->height = k ? (height + (1 << vs) - 1) >> vs : height;
+    c->stride = RUP16 ((c->width + extension * 2) * bpp);
+    if (upsampled) c->stride *= 4;
+    c->length = c->stride * (c->height + extension * 2);
+    c->h_shift = k ? hs : 0;
+    c->v_shift = k ? vs : 0;
+    total += (size_t) c->length;
+  }
+  if (domain)
+    frame->regions[0] = schro_memory_domain_alloc (domain, (int) total);
+  else
+    frame->regions[0] = malloc (total);
+  for (k = 0; k < 3; k++) {
+    SchroFrameData *c = &frame->components[k];
+    c->data = (char *) frame->regions[0] + pos + (size_t) c->stride * extension + (size_t) bpp * extension;
+    pos += (size_t) c->length;
+  }
+  return frame;
+}
+
+SchroFrame *
+schro_frame_new_and_alloc_extended (SchroMemoryDomain *domain, SchroFrameFormat format,
+    int width, int height, int extension)
+{
+  return schro_frame_new_and_alloc_full (domain, format, width, height, extension, 0);
+}
+
+SchroFrame *
+schro_frame_new_and_alloc (SchroMemoryDomain *domain, SchroFrameFormat format, int width,
+    int height)
+{
+  return schro_frame_new_and_alloc_full (domain, format, width, height, 0, 0);
+}
+
+SchroFrame *
+schro_frame_ref (SchroFrame *frame)
+{
+  pthread_mutex_lock (&frame_mutex);
+  frame->refcount++;
+  pthread_mutex_unlock (&frame_mutex);
+  return frame;
+}
+
+void
+schro_frame_unref (SchroFrame *frame)
+{
+  int k, last;
+  SB2H_ASSERT (frame && frame->refcount > 0);
+  pthread_mutex_lock (&frame_mutex);
+  last = (--frame->refcount == 0);
+  pthread_mutex_unlock (&frame_mutex);
+  if (!last) return;
+  if (frame->free) frame->free (frame, frame->priv);
+  for (k = 0; k < 3; k++) {
+    if (frame->regions[k]) {
+      if (frame->domain) schro_memory_domain_memfree (frame->domain, frame->regions[k]);
+      else free (frame->regions[k]);
+    }
+  }
+  free (frame);
+}
+
+void
+schro_upsampled_frame_get_framedata (SchroFrame *upframe, SchroFrameData *fd, int up_index,
+    int component)
+{
+  SB2H_ASSERT (upframe->is_upsampled);
+  *fd = upframe->components[component];
+  fd->data = (char *) fd->data + (fd->stride >> 2) * up_index;
+}
+
+/* copy every component (with its borders and, for upsampled frames, all four phases) */
+static void
+frame_copy_all (SchroFrame *dest, SchroFrame *src)
+{
+  Sb2hContext *cx = sb2h_context ();
+  int k;
+  SB2H_ASSERT (dest->format == src->format && dest->width == src->width &&
+      dest->height == src->height);
+  for (k = 0; k < 3; k++) {
+    SchroFrameData *d = &dest->components[k], *s = &src->components[k];
+    const int bpp = sb2h_bpp (src->format);
+    if (dest->extension == src->extension && dest->is_upsampled == src->is_upsampled) {
+      /* same geometry: move the whole plane including borders / phases */
+      const int ext = src->extension;
+      char *dp = (char *) d->data - (size_t) d->stride * ext - (size_t) bpp * ext;
+      char *sp = (char *) s->data - (size_t) s->stride * ext - (size_t) bpp * ext;
+      SB2H_ASSERT (d->length == s->length);
+      SB2H_CUDA (cudaMemcpyAsync (dp, sp, (size_t) s->length, cudaMemcpyDefault, cx->stream));
+    } else {
+      sb2h_copy_rect (cx, d->data, d->stride, s->data, s->stride, (size_t) s->width * bpp,
+          s->height);
+    }
+  }
+  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  dest->upsample_done = (dest->is_upsampled == src->is_upsampled &&
+      dest->extension == src->extension) ? src->upsample_done : 0;
+}
+
+void
+schro_frame_to_gpu (SchroFrame *dest, SchroFrame *src)
+{
+  frame_copy_all (dest, src);
+}
+
+void
+schro_gpuframe_to_cpu (SchroFrame *dest, SchroFrame *src)
+{
+  frame_copy_all (dest, src);
+}

@@ -1,0 +1,178 @@
+/*
+ * schro_host_wavelet.c -- the reference's wavelet entry points on top of the CUDA layer.
+ *
+ *   schro_wavelet_transform_2d          schroedinger/schrowaveletorc.c:60-117
+ *   schro_wavelet_inverse_transform_2d  schroedinger/schrowaveletorc.c:121-188
+ *   schro_frame_iwt_transform           schroedinger/schroframe.c:1192-1228
+ *   schro_frame_inverse_iwt_transform   schroedinger/schrodecoder.c:1809-1853
+ *
+ * Host buffers are staged H2D / D2H on the calling thread's stream; device
+ * (CUDA-domain) buffers are transformed where they lie.  `tmp` is ignored (the
+ * kernels keep their line buffers in shared memory).
+ */
+#include "schro_host.h"
+#include <string.h>
+
+typedef struct {
+  void *data[3];
+  int stride[3], width[3], height[3];
+  int ncomp;
+} PlaneList;
+
+static size_t
+dense_layout (const PlaneList *pl, int bpp, sb2_slab *slab)
+{
+  size_t pos = 0;
+  int c;
+  memset (slab, 0, sizeof (*slab));
+  slab->count = 1;
+  slab->ncomp = pl->ncomp;
+  for (c = 0; c < pl->ncomp; c++) {
+    slab->stride[c] = (pl->width[c] * bpp + 15) & ~15;
+    slab->width[c] = pl->width[c];
+    slab->height[c] = pl->height[c];
+    slab->offset[c] = pos;
+    pos += ((size_t) slab->stride[c] * pl->height[c] + 255) & ~(size_t) 255;
+  }
+  slab->picture_pitch = pos;
+  return pos;
+}
+
+/* multi-level transform of up to three planes that share format and depth */
+static void
+run_planes (const PlaneList *src, const PlaneList *dst, int is_s32, int filter, int depth,
+    int inverse)
+{
+  Sb2hContext *cx = sb2h_context ();
+  const int bpp = is_s32 ? 4 : 2;
+  const int kind = sb2h_mem_kind (src->data[0]);
+  sb2_slab sin, sout;
+  size_t ws_bytes;
+  void *ws;
+  int c, rc;
+
+  if (kind == SB2H_MEM_DEVICE) {
+    /* zero-copy: describe the planes relative to the lowest address */
+    char *base = src->data[0], *dbase = dst->data[0];
+    int in_place = 1;
+    for (c = 0; c < src->ncomp; c++) {
+      if ((char *) src->data[c] < base) base = src->data[c];
+      if ((char *) dst->data[c] < dbase) dbase = dst->data[c];
+      if (src->data[c] != dst->data[c]) in_place = 0;
+    }
+    memset (&sin, 0, sizeof (sin));
+    sin.count = 1;
+    sin.ncomp = src->ncomp;
+    sout = sin;
+    sin.base = base;
+    sout.base = dbase;
+    for (c = 0; c < src->ncomp; c++) {
+      sin.offset[c] = (size_t) ((char *) src->data[c] - base);
+      sin.stride[c] = src->stride[c];
+      sin.width[c] = sout.width[c] = src->width[c];
+      sin.height[c] = sout.height[c] = src->height[c];
+      sout.offset[c] = (size_t) ((char *) dst->data[c] - dbase);
+      sout.stride[c] = dst->stride[c];
+    }
+    ws_bytes = sb2_iwt_workspace_bytes (&sin, is_s32, depth, 1);
+    ws = sb2h_dev_buffer (cx, SB2H_BUF_WS, ws_bytes);
+    (void) in_place;
+    rc = inverse ? sb2_iwt_inverse (&sin, &sout, is_s32, filter, depth, ws, ws_bytes, cx->stream)
+                 : sb2_iwt_forward (&sin, &sout, is_s32, filter, depth, ws, ws_bytes, cx->stream);
+    SB2H_CHECK (rc, inverse ? "sb2_iwt_inverse" : "sb2_iwt_forward");
+    SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+    return;
+  }
+
+  /* host memory: H2D, transform out of place, D2H */
+  {
+    size_t bytes = dense_layout (src, bpp, &sin);
+    sout = sin;
+    sin.base = sb2h_dev_buffer (cx, SB2H_BUF_IN, bytes);
+    sout.base = sb2h_dev_buffer (cx, SB2H_BUF_OUT, bytes);
+    ws_bytes = sb2_iwt_workspace_bytes (&sin, is_s32, depth, 0);
+    ws = sb2h_dev_buffer (cx, SB2H_BUF_WS, ws_bytes);
+    for (c = 0; c < src->ncomp; c++)
+      sb2h_copy_rect (cx, (char *) sin.base + sin.offset[c], sin.stride[c], src->data[c],
+          src->stride[c], (size_t) src->width[c] * bpp, src->height[c]);
+    rc = inverse ? sb2_iwt_inverse (&sin, &sout, is_s32, filter, depth, ws, ws_bytes, cx->stream)
+                 : sb2_iwt_forward (&sin, &sout, is_s32, filter, depth, ws, ws_bytes, cx->stream);
+    SB2H_CHECK (rc, inverse ? "sb2_iwt_inverse" : "sb2_iwt_forward");
+    for (c = 0; c < src->ncomp; c++)
+      sb2h_copy_rect (cx, dst->data[c], dst->stride[c], (char *) sout.base + sout.offset[c],
+          sout.stride[c], (size_t) src->width[c] * bpp, src->height[c]);
+    SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  }
+}
+
+static int
+depth_is_s32 (SchroFrameFormat format)
+{
+  int d = SCHRO_FRAME_FORMAT_DEPTH (format);
+  if (d == SCHRO_FRAME_FORMAT_DEPTH_S16) return 0;
+  if (d == SCHRO_FRAME_FORMAT_DEPTH_S32) return 1;
+  sb2h_fatal (__func__, "wavelets need an s16 or s32 frame (format 0x%x)", (unsigned) format);
+  return 0;
+}
+
+void
+schro_wavelet_transform_2d (SchroFrameData *fd, int filter, int16_t *tmp)
+{
+  PlaneList pl;
+  (void) tmp;
+  if (filter < 0 || filter > 6) sb2h_fatal (__func__, "bad filter %d", filter);
+  pl.ncomp = 1;
+  pl.data[0] = fd->data;
+  pl.stride[0] = fd->stride;
+  pl.width[0] = fd->width;
+  pl.height[0] = fd->height;
+  run_planes (&pl, &pl, depth_is_s32 (fd->format), filter, 1, 0);
+}
+
+void
+schro_wavelet_inverse_transform_2d (SchroFrameData *fd_dest, SchroFrameData *fd_src,
+    int filter, int16_t *tmp)
+{
+  PlaneList ps, pd;
+  (void) tmp;
+  if (filter < 0 || filter > 6) sb2h_fatal (__func__, "bad filter %d", filter);
+  SB2H_ASSERT (SCHRO_FRAME_FORMAT_DEPTH (fd_dest->format) == SCHRO_FRAME_FORMAT_DEPTH (fd_src->format));
+  SB2H_ASSERT (fd_dest->width == fd_src->width && fd_dest->height == fd_src->height);
+  ps.ncomp = pd.ncomp = 1;
+  ps.data[0] = fd_src->data;  ps.stride[0] = fd_src->stride;
+  ps.width[0] = fd_src->width; ps.height[0] = fd_src->height;
+  pd = ps;
+  pd.data[0] = fd_dest->data; pd.stride[0] = fd_dest->stride;
+  /* The reference leaves the vertically un-lifted rows in src when dest != src
+   * (schrowaveletorc.c:1483-1521) -- a side effect no caller relies on
+   * (all callers pass dest == src, schrodecoder.c:1835-1848); here src is left intact. */
+  run_planes (&ps, &pd, depth_is_s32 (fd_dest->format), filter, 1, 1);
+}
+
+static void
+frame_iwt (SchroFrame *frame, SchroParams *params, int inverse)
+{
+  PlaneList pl;
+  int k;
+  pl.ncomp = 3;
+  for (k = 0; k < 3; k++) {
+    pl.data[k] = frame->components[k].data;
+    pl.stride[k] = frame->components[k].stride;
+    pl.width[k] = k ? params->iwt_chroma_width : params->iwt_luma_width;
+    pl.height[k] = k ? params->iwt_chroma_height : params->iwt_luma_height;
+  }
+  run_planes (&pl, &pl, depth_is_s32 (frame->format), params->wavelet_filter_index,
+      params->transform_depth, inverse);
+}
+
+void
+schro_frame_iwt_transform (SchroFrame *frame, SchroParams *params)
+{
+  frame_iwt (frame, params, 0);
+}
+
+void
+schro_frame_inverse_iwt_transform (SchroFrame *frame, SchroParams *params)
+{
+  frame_iwt (frame, params, 1);
+}
