@@ -99,3 +99,262 @@ ref_iwt_inv (void *data, int stride, int width, int height, int is_s32,
   }
   free (tmp);
 }
+
+/* ---- frame operations ---------------------------------------------------- */
+/* A SchroFrame whose three components all alias one caller-owned plane (the operations
+ * below are idempotent per component, so running them three times is harmless). */
+static void
+fake_frame (SchroFrame *f, uint8_t *data, int stride, int width, int height, int ext,
+    int upsampled)
+{
+  int k;
+  memset (f, 0, sizeof (*f));
+  f->refcount = 1;
+  f->format = SCHRO_FRAME_FORMAT_U8_444;
+  f->width = width;
+  f->height = height;
+  f->extension = ext;
+  f->is_upsampled = upsampled;
+  for (k = 0; k < 3; k++) {
+    f->components[k].format = SCHRO_FRAME_FORMAT_U8_444;
+    f->components[k].data = data;
+    f->components[k].stride = stride;
+    f->components[k].width = width;
+    f->components[k].height = height;
+    f->components[k].length = stride * (height + 2 * ext);
+  }
+}
+
+/* schro_frame_mc_edgeextend (schroedinger/schroframe.c:1986) */
+void
+ref_mc_edgeextend (uint8_t *data, int stride, int width, int height, int ext)
+{
+  SchroFrame f;
+  ref_init ();
+  fake_frame (&f, data, stride, width, height, ext, 0);
+  schro_frame_mc_edgeextend (&f);
+}
+
+/* schro_upsampled_frame_upsample (schroedinger/schroframe.c:2000) */
+void
+ref_upsample (uint8_t *data, int stride, int width, int height, int ext)
+{
+  SchroFrame f;
+  ref_init ();
+  fake_frame (&f, data, stride, width, height, ext, 1);
+  schro_upsampled_frame_upsample (&f);
+}
+
+/* schro_frame_downsample (schroedinger/schroframe.c:1505) */
+void
+ref_downsample (uint8_t *dest, int dstride, int dwidth, int dheight,
+    const uint8_t *src, int sstride, int swidth, int sheight)
+{
+  SchroFrame fd, fs;
+  ref_init ();
+  fake_frame (&fd, dest, dstride, dwidth, dheight, 0, 0);
+  fake_frame (&fs, (uint8_t *) src, sstride, swidth, sheight, 0, 0);
+  schro_frame_downsample (&fd, &fs);
+}
+
+/* ---- OBMC ---------------------------------------------------------------- */
+typedef struct {
+  int width, height;            /* luma */
+  int chroma_format;            /* SchroChromaFormat */
+  int xbsep, ybsep, xblen, yblen;
+  int x_num_blocks, y_num_blocks;
+  int mv_precision, weight1, weight2, weight_bits, num_refs;
+} RefMotionParams;
+
+static void
+fake_frame3 (SchroFrame *f, SchroFrameFormat fmt, void **data, const int *stride, int width,
+    int height, int ext, int upsampled)
+{
+  int k;
+  int hs = SCHRO_FRAME_FORMAT_H_SHIFT (fmt), vs = SCHRO_FRAME_FORMAT_V_SHIFT (fmt);
+  memset (f, 0, sizeof (*f));
+  f->refcount = 1;
+  f->format = fmt;
+  f->width = width;
+  f->height = height;
+  f->extension = ext;
+  f->is_upsampled = upsampled;
+  f->upsample_done = upsampled;
+  for (k = 0; k < 3; k++) {
+    f->components[k].format = fmt;
+    f->components[k].data = data[k];
+    f->components[k].stride = stride[k];
+    f->components[k].width = k ? ROUND_UP_SHIFT (width, hs) : width;
+    f->components[k].height = k ? ROUND_UP_SHIFT (height, vs) : height;
+    f->components[k].h_shift = k ? hs : 0;
+    f->components[k].v_shift = k ? vs : 0;
+  }
+}
+
+/* schro_motion_render_u8 (schroedinger/schromotion8.c:700) or, with use_ref_renderer,
+ * the golden schro_motion_render_ref (schroedinger/schromotionref.c:245) */
+void
+ref_motion_render (const RefMotionParams *mp, const SchroMotionVector *mvs,
+    void **ref0, const int *ref0_stride, void **ref1, const int *ref1_stride,
+    void **acc, const int *acc_stride, void **residual, const int *res_stride,
+    int res_is_s32, int add, void **out, const int *out_stride, int use_ref_renderer)
+{
+  SchroVideoFormat vf;
+  SchroParams params;
+  SchroMotion *motion;
+  SchroFrame r0, r1, dest, addframe, output;
+  int cf = mp->chroma_format;
+  int n = mp->x_num_blocks * mp->y_num_blocks;
+
+  ref_init ();
+  memset (&vf, 0, sizeof (vf));
+  vf.width = mp->width;
+  vf.height = mp->height;
+  vf.chroma_format = cf;
+  memset (&params, 0, sizeof (params));
+  params.video_format = &vf;
+  params.num_refs = mp->num_refs;
+  params.xbsep_luma = mp->xbsep;
+  params.ybsep_luma = mp->ybsep;
+  params.xblen_luma = mp->xblen;
+  params.yblen_luma = mp->yblen;
+  params.mv_precision = mp->mv_precision;
+  params.picture_weight_1 = mp->weight1;
+  params.picture_weight_2 = mp->weight2;
+  params.picture_weight_bits = mp->weight_bits;
+  params.x_num_blocks = mp->x_num_blocks;
+  params.y_num_blocks = mp->y_num_blocks;
+  params.x_offset = (mp->xblen - mp->xbsep) / 2;
+  params.y_offset = (mp->yblen - mp->ybsep) / 2;
+
+  {
+    SchroFrameFormat u8 = schro_params_get_frame_format (8, cf);
+    SchroFrameFormat s16 = schro_params_get_frame_format (16, cf);
+    SchroFrameFormat s32 = schro_params_get_frame_format (32, cf);
+    fake_frame3 (&r0, u8, ref0, ref0_stride, mp->width, mp->height, 32, 1);
+    if (ref1) fake_frame3 (&r1, u8, ref1, ref1_stride, mp->width, mp->height, 32, 1);
+    fake_frame3 (&dest, s16, acc, acc_stride, mp->width, mp->height, 0, 0);
+    fake_frame3 (&addframe, res_is_s32 ? s32 : s16, residual, res_stride, mp->width, mp->height, 0, 0);
+    if (out) fake_frame3 (&output, u8, out, out_stride, mp->width, mp->height, 0, 0);
+  }
+  motion = schro_motion_new (&params, &r0, ref1 ? &r1 : NULL);
+  memcpy (motion->motion_vectors, mvs, sizeof (SchroMotionVector) * n);
+  if (use_ref_renderer)
+    schro_motion_render_ref (motion, &dest, &addframe, add, out ? &output : NULL);
+  else
+    schro_motion_render_u8 (motion, &dest, &addframe, add, out ? &output : NULL);
+  schro_motion_free (motion);
+}
+
+/* ---- hierarchical block matching ------------------------------------------ */
+typedef struct {
+  int width, height;            /* luma */
+  int chroma_format;
+  int xbsep, ybsep;
+  int levels;                   /* encoder->downsample_levels */
+  int use_chroma;               /* encoder->enable_chroma_me */
+  int ref_index;                /* 0 or 1 */
+  int level0_range;             /* >0: also run scan_hint(0, range) as schromotionest.c:123-127 */
+} RefHbmParams;
+
+static SchroFrame *
+load_frame (SchroFrameFormat fmt, int width, int height, void **data, const int *stride)
+{
+  SchroFrame *f = schro_frame_new_and_alloc_full (NULL, fmt, width, height, 32, TRUE);
+  int k, y;
+  for (k = 0; k < 3; k++) {
+    SchroFrameData *c = &f->components[k];
+    for (y = 0; y < c->height; y++)
+      memcpy (SCHRO_FRAME_DATA_GET_LINE (c, y), (uint8_t *) data[k] + (size_t) stride[k] * y, c->width);
+  }
+  schro_frame_mc_edgeextend (f);
+  return f;
+}
+
+/* Builds both pyramids with the reference's schro_encoder_frame_downsample
+ * (schroedinger/schroanalysis.c:9-28), then schro_hbm_new / schro_hbm_scan
+ * (schroedinger/schrohierbm.c:25-172) and optionally the level-0 refinement.
+ * fields: (levels+1) consecutive arrays of x_num_blocks*y_num_blocks vectors, index = level.
+ * pyr_out (optional): levels*3 pointers receiving the src pyramid planes (level 1.., dense). */
+void
+ref_hbm_run (const RefHbmParams *hp, void **src, const int *src_stride, void **ref,
+    const int *ref_stride, SchroMotionVector *fields, int *x_num_blocks, int *y_num_blocks,
+    void **pyr_out)
+{
+  SchroEncoder *enc = calloc (1, sizeof (SchroEncoder));
+  SchroEncoderFrame *fs = calloc (1, sizeof (SchroEncoderFrame));
+  SchroEncoderFrame *fr = calloc (1, sizeof (SchroEncoderFrame));
+  SchroVideoFormat vf;
+  SchroFrameFormat fmt;
+  SchroHierBm *hbm;
+  int i, n, l;
+
+  ref_init ();
+  memset (&vf, 0, sizeof (vf));
+  vf.width = hp->width;
+  vf.height = hp->height;
+  vf.chroma_format = hp->chroma_format;
+  fmt = schro_params_get_frame_format (8, hp->chroma_format);
+  enc->downsample_levels = hp->levels;
+  enc->enable_chroma_me = hp->use_chroma;
+  for (i = 0; i < 2; i++) {
+    SchroEncoderFrame *f = i ? fr : fs;
+    f->encoder = enc;
+    f->params.video_format = &vf;
+    f->params.xbsep_luma = hp->xbsep;
+    f->params.ybsep_luma = hp->ybsep;
+    f->params.xblen_luma = hp->xbsep;
+    f->params.yblen_luma = hp->ybsep;
+    f->params.num_refs = 1;
+    schro_params_calculate_mc_sizes (&f->params);
+  }
+  fs->filtered_frame = load_frame (fmt, hp->width, hp->height, src, src_stride);
+  fr->filtered_frame = load_frame (fmt, hp->width, hp->height, ref, ref_stride);
+  schro_encoder_frame_downsample (fs);
+  schro_encoder_frame_downsample (fr);
+  fs->ref_frame[hp->ref_index] = fr;
+
+  hbm = schro_hbm_new (fs, hp->ref_index);
+  schro_hbm_scan (hbm);
+  if (hp->level0_range > 0)
+    schro_hierarchical_bm_scan_hint (hbm, 0, hp->level0_range);
+
+  n = fs->params.x_num_blocks * fs->params.y_num_blocks;
+  *x_num_blocks = fs->params.x_num_blocks;
+  *y_num_blocks = fs->params.y_num_blocks;
+  for (l = 0; l <= hp->levels; l++) {
+    SchroMotionField *mf = schro_hbm_motion_field (hbm, l);
+    if (mf) memcpy (fields + (size_t) l * n, mf->motion_vectors, sizeof (SchroMotionVector) * n);
+    else memset (fields + (size_t) l * n, 0, sizeof (SchroMotionVector) * n);
+  }
+  if (pyr_out) {
+    for (l = 0; l < hp->levels; l++) {
+      int k, y;
+      for (k = 0; k < 3; k++) {
+        SchroFrameData *c = &fs->downsampled_frames[l]->components[k];
+        uint8_t *d = pyr_out[l * 3 + k];
+        if (!d) continue;
+        for (y = 0; y < c->height; y++)
+          memcpy (d + (size_t) c->width * y, SCHRO_FRAME_DATA_GET_LINE (c, y), c->width);
+      }
+    }
+  }
+  schro_hbm_unref (hbm);
+  for (i = 0; i < hp->levels; i++) {
+    schro_frame_unref (fs->downsampled_frames[i]);
+    schro_frame_unref (fr->downsampled_frames[i]);
+  }
+  schro_frame_unref (fs->filtered_frame);
+  schro_frame_unref (fr->filtered_frame);
+  free (fs);
+  free (fr);
+  free (enc);
+}
+
+/* schro_metric_absdiff_u8 (schroedinger/schrometric.c:10) */
+uint32_t
+ref_sad_u8 (const uint8_t *a, int a_stride, const uint8_t *b, int b_stride, int width, int height)
+{
+  ref_init ();
+  return (uint32_t) schro_metric_absdiff_u8 ((uint8_t *) a, a_stride, (uint8_t *) b, b_stride, width, height);
+}

@@ -37,6 +37,76 @@ def wavelet_golden(ref):
     print("wavelet.npz:", len(out), "arrays")
 
 
+def frame_golden(ref):
+    rng = np.random.default_rng(42)
+    out = {}
+    for idx, (w, h, ext) in enumerate(((20, 20, 4), (8, 8, 2), (5, 3, 3), (64, 48, 32), (9, 2, 8), (1, 1, 2))):
+        img = rng.integers(0, 256, size=(h, w)).astype(np.uint8)
+        pl = helpers.HostPlane(w, h, ext=ext, upsampled=True, fill=0x55)
+        pl.set_image(img)
+        helpers.cpu_edgeextend(ref, "ref", pl)
+        helpers.cpu_upsample(ref, "ref", pl)
+        out[f"up{idx}_img"] = img
+        out[f"up{idx}_ext"] = np.array([ext])
+        for p in range(4):
+            out[f"up{idx}_phase{p}"] = pl.phase(p).copy()
+    for idx, (w, h) in enumerate(((10, 10), (39, 39), (11, 7), (2, 2), (1, 5), (135, 99))):
+        img = rng.integers(0, 256, size=(h, w)).astype(np.uint8)
+        out[f"down{idx}_img"] = img
+        out[f"down{idx}_out"] = helpers.cpu_downsample(ref, "ref", img)
+    np.savez_compressed(os.path.join(helpers.GOLDEN_DIR, "frame.npz"), **out)
+    print("frame.npz:", len(out), "arrays")
+
+
+OBMC_GOLDEN_CASES = [
+    dict(width=64, height=48), dict(width=72, height=40, prec=0), dict(width=72, height=40, prec=1),
+    dict(width=72, height=40, prec=3), dict(width=64, height=48, weights=(3, 1, 2)),
+    dict(width=64, height=48, weights=(2, 3, 3)), dict(width=64, height=48, num_refs=1),
+    dict(width=96, height=64, xbsep=16, ybsep=16, xblen=24, yblen=24),
+    dict(width=64, height=48, xbsep=4, ybsep=4, xblen=6, yblen=6, chroma_format=0),
+    dict(width=64, height=48, res_is_s32=True), dict(width=66, height=50, span=300, outliers=0.05),
+]
+
+
+def motion_golden(ref):
+    """Inputs are regenerated from the seed by the test (ObmcCase is deterministic given the
+    oracle's upsampler, itself pinned by frame.npz); only the reference OUTPUTS are stored."""
+    oracle = helpers.load_oracle()
+    out = {}
+    for idx, kw in enumerate(OBMC_GOLDEN_CASES):
+        for add in (1, 0):
+            if not add and kw.get("res_is_s32"):
+                continue
+            case = helpers.ObmcCase(oracle, rng=np.random.default_rng(1000 + idx), **kw)
+            res = helpers.ref_obmc(ref, case, add)
+            res2 = helpers.ref_obmc(ref, case, add, use_ref_renderer=True)
+            for k in range(3):
+                for q, name in enumerate(("acc", "resid", "out")):
+                    if q == 2 and not add:
+                        continue
+                    out[f"c{idx}_add{add}_k{k}_{name}"] = res[k][q]
+                    if name != "acc" and not kw.get("res_is_s32"):   # golden per-pixel renderer agrees (it has no s32 path)
+                        assert np.array_equal(res[k][q], res2[k][q]), (kw, add, k, name)
+    np.savez_compressed(os.path.join(helpers.GOLDEN_DIR, "motion.npz"), **out)
+    print("motion.npz:", len(out), "arrays")
+
+
+HBM_GOLDEN_CASES = [(128, 96, 3, 0, 0, (5, 3)), (176, 144, 4, 0, 0, (5, 3)), (100, 70, 2, 0, 0, (-7, 4)),
+                    (128, 96, 3, 1, 1, (2, -6)), (352, 288, 4, 0, 0, (9, -5))]
+
+
+def hbm_golden(ref):
+    out = {}
+    for idx, (w, h, lv, uc, ri, pan) in enumerate(HBM_GOLDEN_CASES):
+        s, r = helpers.panning_pair(w, h, np.random.default_rng(2000 + idx), pan)
+        fields, pyr = helpers.ref_hbm(ref, s, r, w, h, levels=lv, use_chroma=uc, ref_index=ri)
+        out[f"h{idx}_fields"] = fields
+        for l in range(lv):
+            out[f"h{idx}_pyr{l}"] = pyr[l][0]
+    np.savez_compressed(os.path.join(helpers.GOLDEN_DIR, "hbm.npz"), **out)
+    print("hbm.npz:", len(out), "arrays")
+
+
 def main():
     ref = helpers.load_ref()
     if ref is None:

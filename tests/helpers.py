@@ -84,3 +84,322 @@ def patterns(h, w, dtype, rng, amp=255):
     pats.append(("dramp", ((xx + yy) * amp) // max(1, w + h - 2)))
     pats.append(("impulse", np.where((xx == w // 2) & (yy == h // 2), amp, 0)))
     return [(name, np.ascontiguousarray(p.astype(dtype))) for name, p in pats]
+
+
+# ---------------------------------------------------------------------------------------
+# frames, upsampled references, motion fields
+# ---------------------------------------------------------------------------------------
+MV_DTYPE = np.dtype([("flags", "<u4"), ("metric", "<u4"), ("chroma_metric", "<u4"),
+                     ("v", "<i2", (4,))])
+
+
+def round_up(x, a):
+    return (x + a - 1) // a * a
+
+
+class HostPlane:
+    """One u8 component with `ext` border pixels, optionally in the reference's 4-phase
+    "upsampled" row layout (schroedinger/schroframe.c:133-137, 1917-1925)."""
+
+    def __init__(self, width, height, ext=0, upsampled=False, fill=0):
+        self.w, self.h, self.ext, self.upsampled = width, height, ext, upsampled
+        self.stride = round_up(width + 2 * ext, 16) * (4 if upsampled else 1)
+        self.buf = np.full((height + 2 * ext, self.stride), fill, dtype=np.uint8)
+        self.origin = ext * self.stride + ext            # byte offset of pixel (0,0) of phase 0
+
+    @property
+    def ptr(self):
+        return ctypes.c_void_p(self.buf.ctypes.data + self.origin)
+
+    def phase(self, p=0, with_border=True):
+        q = (self.stride >> 2) * p if self.upsampled else 0
+        e = self.ext
+        if with_border:
+            return self.buf[:, q:q + self.w + 2 * e]
+        return self.buf[e:e + self.h, q + e:q + e + self.w]
+
+    def set_image(self, img):
+        self.phase(0, with_border=False)[...] = img
+
+
+def cpu_edgeextend(lib, prefix, plane):
+    fn = getattr(lib, f"{prefix}_mc_edgeextend")
+    fn.restype = None
+    fn(plane.ptr, plane.stride, plane.w, plane.h, plane.ext)
+
+
+def cpu_upsample(lib, prefix, plane):
+    fn = getattr(lib, f"{prefix}_upsample")
+    fn.restype = None
+    fn(plane.ptr, plane.stride, plane.w, plane.h, plane.ext)
+
+
+def cpu_downsample(lib, prefix, src):
+    """src: 2-D u8 array -> half-size array (schro_frame_downsample on one component)."""
+    h, w = src.shape
+    dst = np.zeros(((h + 1) // 2, (w + 1) // 2), np.uint8)
+    fn = getattr(lib, f"{prefix}_downsample")
+    fn.restype = None
+    fn(dst.ctypes.data_as(ctypes.c_void_p), dst.strides[0], dst.shape[1], dst.shape[0],
+       src.ctypes.data_as(ctypes.c_void_p), src.strides[0], w, h)
+    return dst
+
+
+def smooth_image(h, w, rng, noise=5):
+    """Smooth gradient + hash noise."""
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = 128 + 60 * np.sin(xx / 17.0) + 50 * np.cos(yy / 23.0) + 0.05 * (xx + yy)
+    img = base + rng.integers(-(1 << noise) // 2, (1 << noise) // 2 + 1, size=(h, w))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def make_upsampled_ref(oracle, width, height, rng, chroma_shift=(1, 1)):
+    """Three upsampled, edge-extended (ext 32) component planes of one reference picture."""
+    planes = []
+    for k in range(3):
+        w = width if k == 0 else (width + (1 << chroma_shift[0]) - 1) >> chroma_shift[0]
+        h = height if k == 0 else (height + (1 << chroma_shift[1]) - 1) >> chroma_shift[1]
+        pl = HostPlane(w, h, ext=32, upsampled=True)
+        pl.set_image(smooth_image(h, w, rng))
+        cpu_edgeextend(oracle, "oracle", pl)
+        cpu_upsample(oracle, "oracle", pl)
+        planes.append(pl)
+    return planes
+
+
+def make_mv_field(nbx, nby, rng, prec=2, span=64, outliers=0.01, modes=(0.12, 0.38, 0.25, 0.25),
+                  two_refs=True):
+    """pred_mode in {0:12%,1:38%,2:25%,3:25%}, vectors uniform in +-span
+    (+1% outliers +-4000), DC uniform +-127."""
+    n = nbx * nby
+    mv = np.zeros(n, dtype=MV_DTYPE)
+    p = np.array(modes, dtype=float)
+    if not two_refs:
+        p = np.array([p[0], p[1] + p[2] + p[3], 0, 0])
+    mode = rng.choice(4, size=n, p=p / p.sum())
+    v = rng.integers(-span, span + 1, size=(n, 4))
+    out = rng.random(n) < outliers
+    v[out] = rng.integers(-4000, 4001, size=(int(out.sum()), 4))
+    dc = rng.integers(-127, 128, size=(n, 4))
+    dc[:, 3] = 0
+    mv["v"] = np.where((mode == 0)[:, None], dc, v)
+    mv["flags"] = mode.astype(np.uint32)
+    return mv
+
+
+class ObmcCase:
+    """Everything one schro_motion_render call needs, as host arrays."""
+
+    def __init__(self, oracle, width, height, rng, xbsep=8, ybsep=8, xblen=12, yblen=12, prec=2,
+                 weights=(1, 1, 1), num_refs=2, chroma_format=2, res_is_s32=False, span=64,
+                 outliers=0.01):
+        self.width, self.height = width, height
+        self.chroma_format = chroma_format
+        self.hs = 0 if chroma_format == 0 else 1
+        self.vs = 1 if chroma_format == 2 else 0
+        self.xbsep, self.ybsep, self.xblen, self.yblen = xbsep, ybsep, xblen, yblen
+        self.prec, self.weights, self.num_refs = prec, weights, num_refs
+        self.nbx = 4 * ((width + 4 * xbsep - 1) // (4 * xbsep))
+        self.nby = 4 * ((height + 4 * ybsep - 1) // (4 * ybsep))
+        self.res_is_s32 = res_is_s32
+        self.ref0 = make_upsampled_ref(oracle, width, height, rng, (self.hs, self.vs))
+        self.ref1 = make_upsampled_ref(oracle, width, height, rng, (self.hs, self.vs)) if num_refs > 1 else None
+        self.mvs = make_mv_field(self.nbx, self.nby, rng, prec, span=span, outliers=outliers,
+                                 two_refs=num_refs > 1)
+        self.comp_sizes = [(p.w, p.h) for p in self.ref0]
+        rdt = np.int32 if res_is_s32 else np.int16
+        self.residual = [rng.integers(-32, 33, size=(h, w)).astype(rdt) for (w, h) in self.comp_sizes]
+
+    def comp_params(self, k):
+        hs, vs = (self.hs, self.vs) if k else (0, 0)
+        return dict(xbsep=self.xbsep >> hs, ybsep=self.ybsep >> vs, xblen=self.xblen >> hs,
+                    yblen=self.yblen >> vs, x_num_blocks=self.nbx, y_num_blocks=self.nby,
+                    mv_precision=self.prec, weight1=self.weights[0], weight2=self.weights[1],
+                    weight_bits=self.weights[2], h_shift=hs, v_shift=vs, comp=k)
+
+
+class OracleObmcParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in (
+        "xbsep", "ybsep", "xblen", "yblen", "x_num_blocks", "y_num_blocks", "mv_precision",
+        "weight1", "weight2", "weight_bits", "h_shift", "v_shift", "comp")]
+
+
+class RefMotionParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in (
+        "width", "height", "chroma_format", "xbsep", "ybsep", "xblen", "yblen", "x_num_blocks",
+        "y_num_blocks", "mv_precision", "weight1", "weight2", "weight_bits", "num_refs")]
+
+
+def oracle_obmc(oracle, case, add):
+    """-> per component (acc, residual_after, out) from the oracle."""
+    res = []
+    fn = oracle.oracle_obmc_render
+    fn.restype = None
+    for k, (w, h) in enumerate(case.comp_sizes):
+        p = OracleObmcParams(**case.comp_params(k))
+        acc = np.zeros((h, w), np.int16)
+        resid = case.residual[k].copy()
+        out = np.zeros((h, w), np.uint8)
+        r1 = case.ref1[k].ptr if case.ref1 else None
+        fn(ctypes.byref(p), case.mvs.ctypes.data_as(ctypes.c_void_p), case.ref0[k].ptr, r1,
+           case.ref0[k].stride, w, h, acc.ctypes.data_as(ctypes.c_void_p), acc.strides[0],
+           resid.ctypes.data_as(ctypes.c_void_p), resid.strides[0], 1 if case.res_is_s32 else 0,
+           1 if add else 0, out.ctypes.data_as(ctypes.c_void_p), out.strides[0])
+        res.append((acc, resid, out))
+    return res
+
+
+def ref_obmc(ref, case, add, use_ref_renderer=False):
+    """Same through the unmodified reference (schro_motion_render_u8 or _ref)."""
+    P = ctypes.c_void_p * 3
+    I = ctypes.c_int * 3
+    accs = [np.zeros((h, w), np.int16) for (w, h) in case.comp_sizes]
+    resid = [r.copy() for r in case.residual]
+    outs = [np.zeros((h, w), np.uint8) for (w, h) in case.comp_sizes]
+    mp = RefMotionParams(case.width, case.height, case.chroma_format, case.xbsep, case.ybsep,
+                         case.xblen, case.yblen, case.nbx, case.nby, case.prec, case.weights[0],
+                         case.weights[1], case.weights[2], case.num_refs)
+    r0 = P(*[p.ptr for p in case.ref0])
+    r0s = I(*[p.stride for p in case.ref0])
+    r1 = P(*[p.ptr for p in case.ref1]) if case.ref1 else None
+    r1s = I(*[p.stride for p in case.ref1]) if case.ref1 else None
+    fn = ref.ref_motion_render
+    fn.restype = None
+    fn(ctypes.byref(mp), case.mvs.ctypes.data_as(ctypes.c_void_p), r0, r0s, r1, r1s,
+       P(*[a.ctypes.data for a in accs]), I(*[a.strides[0] for a in accs]),
+       P(*[a.ctypes.data for a in resid]), I(*[a.strides[0] for a in resid]),
+       1 if case.res_is_s32 else 0, 1 if add else 0,
+       P(*[a.ctypes.data for a in outs]), I(*[a.strides[0] for a in outs]),
+       1 if use_ref_renderer else 0)
+    return list(zip(accs, resid, outs))
+
+
+# ---------------------------------------------------------------------------------------
+# pyramids and hierarchical block matching
+# ---------------------------------------------------------------------------------------
+class OraclePyrLevel(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p * 3), ("stride", ctypes.c_int * 3), ("width", ctypes.c_int),
+                ("height", ctypes.c_int), ("h_shift", ctypes.c_int), ("v_shift", ctypes.c_int),
+                ("ext", ctypes.c_int)]
+
+
+class RefHbmParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("width", "height", "chroma_format", "xbsep", "ybsep",
+                                            "levels", "use_chroma", "ref_index", "level0_range")]
+
+
+def panning_pair(width, height, rng, pan=(5, 3), noise=3):
+    """A textured base picture and a copy panned by `pan` pixels + noise (SURVEY.md 8d, C5);
+    returns (src_planes, ref_planes) as lists of three 2-D u8 arrays (4:2:0)."""
+    H, W = height + 64, width + 64
+    yy, xx = np.mgrid[0:H, 0:W]
+    base = (128 + 50 * np.sin(xx / 9.0) * np.cos(yy / 7.0) + 30 * np.sin((xx + 2 * yy) / 31.0)
+            + rng.integers(-20, 21, size=(H, W)))
+
+    def crop(ox, oy):
+        y = np.clip(base[32 + oy:32 + oy + height, 32 + ox:32 + ox + width]
+                    + rng.integers(-noise, noise + 1, size=(height, width)), 0, 255).astype(np.uint8)
+        c = y[::2, ::2]
+        return [y, np.ascontiguousarray(255 - c), np.ascontiguousarray((c // 2 + 64).astype(np.uint8))]
+
+    return crop(0, 0), crop(pan[0], pan[1])
+
+
+def build_pyramid(lib, prefix, planes, levels, ext_level0=32, ext=8):
+    """List (level 0..levels) of lists of three HostPlanes: level 0 = the picture (ext 32),
+    level i+1 = downsample of level i with extension max(xbsep, ybsep), edge-extended
+    (schroedinger/schroanalysis.c:9-28)."""
+    pyr = []
+    cur = []
+    for a in planes:
+        pl = HostPlane(a.shape[1], a.shape[0], ext=ext_level0)
+        pl.set_image(a)
+        cpu_edgeextend(lib, prefix, pl)
+        cur.append(pl)
+    pyr.append(cur)
+    for _ in range(levels):
+        nxt = []
+        for pl in cur:
+            d = cpu_downsample(lib, prefix, np.ascontiguousarray(pl.phase(0, with_border=False)))
+            q = HostPlane(d.shape[1], d.shape[0], ext=ext)
+            q.set_image(d)
+            cpu_edgeextend(lib, prefix, q)
+            nxt.append(q)
+        pyr.append(nxt)
+        cur = nxt
+    return pyr
+
+
+def pyr_level_struct(level_planes, hs=1, vs=1):
+    s = OraclePyrLevel()
+    for k, pl in enumerate(level_planes):
+        s.data[k] = pl.buf.ctypes.data + pl.origin
+        s.stride[k] = pl.stride
+    s.width, s.height = level_planes[0].w, level_planes[0].h
+    s.h_shift, s.v_shift = hs, vs
+    s.ext = level_planes[0].ext
+    return s
+
+
+def hbm_block_counts(width, height, xbsep, ybsep):
+    return (4 * ((width + 4 * xbsep - 1) // (4 * xbsep)), 4 * ((height + 4 * ybsep - 1) // (4 * ybsep)))
+
+
+def oracle_hbm(oracle, src_planes, ref_planes, width, height, xbsep=8, ybsep=8, levels=4,
+               use_chroma=0, ref_index=0, level0_range=3):
+    """schro_hbm_scan + optional level-0 refinement through the oracle -> fields[level]."""
+    ext = max(xbsep, ybsep)
+    ps = build_pyramid(oracle, "oracle", src_planes, levels, ext=ext)
+    pr = build_pyramid(oracle, "oracle", ref_planes, levels, ext=ext)
+    nbx, nby = hbm_block_counts(width, height, xbsep, ybsep)
+    fields = np.zeros((levels + 1, nbx * nby), dtype=MV_DTYPE)
+    fn = oracle.oracle_hbm_scan_hint
+    fn.restype = None
+    rng_ = 20
+    order = [(levels, rng_)]
+    r = rng_ >> 1
+    for l in range(levels - 1, 0, -1):
+        order.append((l, max(3, r)))
+        r >>= 1
+    if level0_range > 0:
+        order.append((0, level0_range))
+    for (l, hr) in order:
+        s, rr = pyr_level_struct(ps[l]), pyr_level_struct(pr[l])
+        parent = fields[l + 1].ctypes.data_as(ctypes.c_void_p) if l < levels else None
+        fn(ctypes.byref(s), ctypes.byref(rr), xbsep, ybsep, nbx, nby, ref_index, l, hr, use_chroma,
+           parent, fields[l].ctypes.data_as(ctypes.c_void_p))
+    return fields, ps, pr
+
+
+def ref_hbm(ref, src_planes, ref_planes, width, height, xbsep=8, ybsep=8, levels=4, use_chroma=0,
+            ref_index=0, level0_range=3):
+    nbx, nby = hbm_block_counts(width, height, xbsep, ybsep)
+    fields = np.zeros((levels + 1, nbx * nby), dtype=MV_DTYPE)
+    P = ctypes.c_void_p * 3
+    I = ctypes.c_int * 3
+    hp = RefHbmParams(width, height, 2, xbsep, ybsep, levels, use_chroma, ref_index, level0_range)
+    nx, ny = ctypes.c_int(), ctypes.c_int()
+    pyr = []
+    w, h = width, height
+    ptrs = (ctypes.c_void_p * (levels * 3))()
+    for l in range(levels):
+        w, h = (w + 1) // 2, (h + 1) // 2
+        lv = [np.zeros((h, w), np.uint8), np.zeros(((h + 1) // 2, (w + 1) // 2), np.uint8),
+              np.zeros(((h + 1) // 2, (w + 1) // 2), np.uint8)]
+        # chroma of level l+1 is the downsample of the chroma of level l
+        pyr.append(lv)
+    # chroma sizes follow their own halving chain
+    cw, ch = (width + 1) // 2, (height + 1) // 2
+    for l in range(levels):
+        cw, ch = (cw + 1) // 2, (ch + 1) // 2
+        pyr[l][1] = np.zeros((ch, cw), np.uint8)
+        pyr[l][2] = np.zeros((ch, cw), np.uint8)
+        for k in range(3):
+            ptrs[l * 3 + k] = pyr[l][k].ctypes.data
+    fn = ref.ref_hbm_run
+    fn.restype = None
+    fn(ctypes.byref(hp), P(*[a.ctypes.data for a in src_planes]), I(*[a.strides[0] for a in src_planes]),
+       P(*[a.ctypes.data for a in ref_planes]), I(*[a.strides[0] for a in ref_planes]),
+       fields.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nx), ctypes.byref(ny), ptrs)
+    assert (nx.value, ny.value) == (nbx, nby)
+    return fields, pyr
