@@ -99,6 +99,83 @@ int sb2_iwt_inverse (const sb2_slab *src, const sb2_slab *dst, int is_s32,
     int filter, int depth, void *workspace, size_t workspace_bytes,
     void *stream);
 
+/* ---- reference-frame preparation (u8) ------------------------------------ */
+
+/* Replicate the picture edge into the `extension` border pixels of every plane:
+ * schro_frame_mc_edgeextend (schroedinger/schroframe.c:1986-1997).  For frames in the
+ * 4-phase "upsampled" layout `phase` selects the phase plane (0 = the picture). */
+int sb2_mc_edgeextend (const sb2_slab *frames, int extension, int phase, void *stream);
+
+/* Fill half-pel phases 1..3 (and all their borders) of upsampled frames whose phase 0 is
+ * already edge-extended: schro_upsampled_frame_upsample (schroedinger/schroframe.c:2000-2030),
+ * i.e. schro_frame_upsample_vert / _horiz (:1557-1645) plus the border passes.
+ * stride[] is the 4-phase row stride; phase p starts (stride>>2)*p bytes into each row. */
+int sb2_upsample (const sb2_slab *frames, int extension, void *stream);
+
+/* dst = half-resolution src, (6,26,26,6) twice with an 8-bit intermediate:
+ * schro_frame_downsample (schroedinger/schroframe.c:1505-1513).  dst sizes must be
+ * (w+1)/2 x (h+1)/2 per component. */
+int sb2_downsample (const sb2_slab *src, const sb2_slab *dst, void *stream);
+
+/* ---- OBMC motion compensation ------------------------------------------- */
+
+/* The subset of SchroParams (schroedinger/schroparams.h:31-77) the renderer reads */
+typedef struct {
+  int xbsep, ybsep, xblen, yblen;       /* luma block separation / length */
+  int x_num_blocks, y_num_blocks;
+  int mv_precision;                     /* 0..3 */
+  int picture_weight_1, picture_weight_2, picture_weight_bits;
+  int chroma_h_shift, chroma_v_shift;   /* applied to components >= 1 (sizes and vectors) */
+} sb2_obmc_params;
+
+/* schro_motion_render / schro_motion_render_u8 (schroedinger/schromotion.c:95,
+ * schroedinger/schromotion8.c:700) for every picture of the slabs.
+ *   motion_vectors  device array of SchroMotionVector (20 bytes each,
+ *                   schroedinger/schromotion.h:20-37), x_num_blocks*y_num_blocks per picture,
+ *                   consecutive pictures `mv_picture_pitch` VECTORS apart
+ *   ref0 / ref1     upsampled (4-phase), edge-extended (extension >= 32) u8 references;
+ *                   ref1 may be NULL when no block uses it
+ *   acc             optional s16 slab receiving what the reference leaves in `dest`
+ *   add != 0        out(u8) = clamp(residual + ((acc+32)>>6)); residual s16 or s32
+ *   add == 0        t = (acc-8160)>>6; acc := t; residual(s16) -= t */
+int sb2_obmc_render (const sb2_obmc_params *params, const void *motion_vectors,
+    size_t mv_picture_pitch, const sb2_slab *ref0, const sb2_slab *ref1, const sb2_slab *acc,
+    const sb2_slab *residual, int residual_is_s32, int add, const sb2_slab *out, void *stream);
+
+/* ---- SAD / hierarchical block matching ----------------------------------- */
+
+typedef struct {
+  int xbsep, ybsep;                     /* luma block size used for matching (= separation) */
+  int x_num_blocks, y_num_blocks;
+  int ref_index;                        /* which of dx[2]/dy[2] is written (SchroHierBm.ref) */
+  int use_chroma;                       /* encoder->enable_chroma_me (4:2:0 only) */
+  int chroma_h_shift, chroma_v_shift;
+} sb2_hbm_params;
+
+size_t sb2_hbm_workspace_bytes (int y_num_blocks, int count);
+
+/* One level of hierarchical block matching for `count` independent (picture, reference)
+ * pairs: schro_hierarchical_bm_scan_hint (schroedinger/schrohierbm.c:174-383), including
+ * the candidate ranking (schro_metric_fast_block, schroedinger/schrometric.c:332-414) and
+ * the scan (schro_metric_scan_setup / _do_scan / _get_min, :31-214).
+ *   src_level / ref_level   pyramid level `shift` of both pictures: three u8 components,
+ *                           edge-extended by `extension` (32 at level 0, max(xbsep,ybsep) above)
+ *   parent_field            device field of level shift+1 (NULL for the coarsest level)
+ *   out_field               device field (x_num_blocks*y_num_blocks SchroMotionVector per
+ *                           pair, pairs `field_picture_pitch` vectors apart); every entry is
+ *                           initialised as schro_motion_field_set does, entries on the
+ *                           1<<shift grid receive the search result */
+int sb2_hbm_scan_hint (const sb2_hbm_params *params, const sb2_slab *src_level,
+    const sb2_slab *ref_level, int extension, int shift, int h_range,
+    const void *parent_field, void *out_field, size_t field_picture_pitch,
+    void *workspace, size_t workspace_bytes, void *stream);
+
+/* schro_metric_absdiff_u8 (schroedinger/schrometric.c:10-29) for `n` independent block
+ * pairs: sad[i] = SAD(a + a_offset[i], b + b_offset[i]) over width x height. */
+int sb2_sad_u8 (const uint8_t *a, int a_stride, const uint8_t *b, int b_stride,
+    const int64_t *a_offset, const int64_t *b_offset, int n, int width, int height,
+    uint32_t *sad, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

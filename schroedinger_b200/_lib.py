@@ -48,6 +48,32 @@ for _n in ("sb2_iwt_forward", "sb2_iwt_inverse"):
                    ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
 
 
+def _opt(name, restype, argtypes):
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = argtypes
+
+
+_SP = ctypes.POINTER(Slab)
+_opt("sb2_mc_edgeextend", ctypes.c_int, [_SP, ctypes.c_int, ctypes.c_int, ctypes.c_void_p])
+_opt("sb2_upsample", ctypes.c_int, [_SP, ctypes.c_int, ctypes.c_void_p])
+_opt("sb2_downsample", ctypes.c_int, [_SP, _SP, ctypes.c_void_p])
+_opt("sb2_obmc_render", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, _SP, _SP, _SP,
+                                      _SP, ctypes.c_int, ctypes.c_int, _SP, ctypes.c_void_p])
+_opt("sb2_hbm_workspace_bytes", ctypes.c_size_t, [ctypes.c_int, ctypes.c_int])
+_opt("sb2_hbm_scan_hint", ctypes.c_int, [ctypes.c_void_p, _SP, _SP, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                        ctypes.c_size_t, ctypes.c_void_p])
+_opt("sb2_sad_u8", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                 ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                 ctypes.c_void_p])
+_opt("sb2_profile_enable", None, [ctypes.c_int])
+_opt("sb2_profile_reset", None, [])
+_opt("sb2_profile_count", ctypes.c_int, [])
+_opt("sb2_profile_get", ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)])
+
+
 def last_error():
     return lib.sb2_last_error().decode()
 

@@ -1,0 +1,394 @@
+// hbm.cu -- SAD primitives and hierarchical block matching for sm_100a.
+//
+// Bit-exact replacement for one level of schro_hierarchical_bm_scan_hint
+// (schroedinger/schrohierbm.c:174-383) on top of schro_metric_scan_setup / _do_scan /
+// _get_min and schro_metric_fast_block (schroedinger/schrometric.c:31-214, 332-414).
+//
+// Parallel structure (DESIGN.md "block matching"): a block needs the already-computed
+// vectors of its left, upper and upper-left neighbours OF THE SAME LEVEL, so blocks form a
+// wavefront.  One warp owns one block row of one (picture, reference) pair and walks it
+// left to right; before block b it waits until the row above has published b+1 finished
+// blocks (acquire/release on a per-row progress counter).  Rows are handed to warps in
+// launch order, so a row only ever waits on a warp that is already resident.  Many pairs
+// run side by side in one launch to fill the machine.  Inside a block the 32 lanes split
+// the candidate SADs by pixel and the (2r+1)^2 scan positions by position; byte SADs use
+// __vsadu4, reductions use warp shuffles.
+
+#include "common.cuh"
+#include <climits>
+#include <cstdio>
+
+namespace sb2 {
+
+struct MotionVector {               // == SchroMotionVector (schroedinger/schromotion.h:20-37)
+  uint32_t flags;
+  uint32_t metric;
+  uint32_t chroma_metric;
+  int16_t v[4];
+};
+
+struct HbmArgs {
+  PlaneSet src, ref;                // 3 u8 components each, edge-extended by `ext`
+  const MotionVector *parent;       // field of level shift+1 or nullptr
+  MotionVector *field;              // output field
+  size_t field_pitch;               // vectors between pictures
+  int *progress;                    // [count][rows] finished blocks per row
+  int width, height;                // luma size of this pyramid level
+  int cw, ch;                       // chroma size
+  int hs, vs;
+  int ext;
+  int bw, bh;                       // xbsep_luma, ybsep_luma
+  int nbx, nby;
+  int ref_index;
+  int shift, h_range, use_chroma;
+  int rows, cols;                   // blocks at this level: ceil(nby/skip), ceil(nbx/skip)
+  int count;
+  uint32_t flags0;
+};
+
+__device__ __forceinline__ int clampi (int x, int lo, int hi) { return min (max (x, lo), hi); }
+
+__device__ __forceinline__ unsigned warp_sum (unsigned v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync (0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ unsigned long long warp_min64 (unsigned long long v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync (0xffffffffu, v, o);
+    v = t < v ? t : v;
+  }
+  return v;
+}
+
+// SAD of a w x h block read straight from global memory (L1/texture path), one lane
+__device__ __forceinline__ unsigned block_sad (const uint8_t *a, int as, const uint8_t *b, int bs, int w, int h)
+{
+  unsigned s = 0;
+  if (w == 8 && (((size_t) a | (size_t) as) & 7) == 0 && (bs & 3) == 0) {
+    // byte-SIMD path: 8-wide source rows are 8-byte aligned (x0 is a multiple of xbsep);
+    // the reference row starts anywhere, so it is assembled from aligned words
+    for (int y = 0; y < h; y++) {
+      const uint2 av = __ldg (reinterpret_cast<const uint2 *> (a + (ptrdiff_t) y * as));   // needs 8-byte alignment
+      const uint8_t *br = b + (ptrdiff_t) y * bs;
+      const size_t mis = (size_t) br & 3;
+      const unsigned *bw_ = reinterpret_cast<const unsigned *> (br - mis);
+      const unsigned w0 = __ldg (bw_), w1 = __ldg (bw_ + 1), w2 = mis ? __ldg (bw_ + 2) : 0u;
+      const unsigned sh = (unsigned) mis * 8;
+      const unsigned b0 = __funnelshift_r (w0, w1, sh), b1 = __funnelshift_r (w1, w2, sh);
+      s += __vsadu4 (av.x, b0) + __vsadu4 (av.y, b1);
+    }
+    return s;
+  }
+  for (int y = 0; y < h; y++) {
+    const uint8_t *ar = a + (ptrdiff_t) y * as, *br = b + (ptrdiff_t) y * bs;
+    for (int x = 0; x < w; x++) s += (unsigned) abs ((int) __ldg (ar + x) - (int) __ldg (br + x));
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__ (128)
+hbm_init_field_kernel (MotionVector *field, size_t n, uint32_t flags0)
+{
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+    MotionVector m;
+    m.flags = flags0;
+    m.metric = 0;
+    m.chroma_metric = 0;
+    m.v[0] = m.v[1] = m.v[2] = m.v[3] = 0;
+    field[i] = m;
+  }
+}
+
+__global__ void __launch_bounds__ (128)
+hbm_level_kernel (const HbmArgs A)
+{
+  const int lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gwarp >= A.rows * A.count) return;
+  const int row = gwarp / A.count, pic = gwarp % A.count;   // rows in launch order: row r before r+1
+  const int skip = 1 << A.shift, s = A.shift;
+  const int j = row * skip;
+  const int ri = A.ref_index;
+
+  const uint8_t *sp[3], *rp[3];
+  int ss[3], rs[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    sp[k] = reinterpret_cast<const uint8_t *> (plane_ptr (A.src, pic, k));
+    rp[k] = reinterpret_cast<const uint8_t *> (plane_ptr (A.ref, pic, k));
+    ss[k] = A.src.stride[k];
+    rs[k] = A.ref.stride[k];
+  }
+  MotionVector *mf = A.field + (size_t) pic * A.field_pitch;
+  const MotionVector *pf = A.parent ? A.parent + (size_t) pic * A.field_pitch : nullptr;
+  int *prog_me = A.progress + (size_t) pic * A.rows + row;
+  volatile int *prog_up = row > 0 ? A.progress + (size_t) pic * A.rows + row - 1 : nullptr;
+  const int hint_mask = ~((1 << (s + 1)) - 1);
+  const int y0 = (j * A.bh) >> s;
+
+  for (int bi = 0; bi < A.cols; bi++) {
+    const int i = bi * skip;
+    const int x0 = (i * A.bw) >> s;
+
+    // ---- wait for the row above: blocks bi (up) and bi-1 (up-left) must be final
+    if (prog_up) {
+      if (lane == 0) {
+        const int need = bi + 1;
+        while (*prog_up < need) __nanosleep (40);
+      }
+      __syncwarp ();
+      __threadfence ();
+    }
+
+    if (x0 < A.width && y0 < A.height) {
+      const int bw0 = min (A.width - x0, A.bw), bh0 = min (A.height - y0, A.bh);
+
+      // ---- candidates, one per lane 0..8 (schrohierbm.c:259-294) ------------------
+      // 0: zero   1..5: parents (0,0) (-1,0) (1,0) (0,-1) (0,1)   6: left 7: up 8: up-left
+      int cdx = 0, cdy = 0;
+      bool valid = false;
+      if (lane == 0) valid = true;
+      else if (lane <= 5) {
+        if (pf) {
+          const int ox = (lane == 2) ? -1 : (lane == 3) ? 1 : 0;
+          const int oy = (lane == 4) ? -1 : (lane == 5) ? 1 : 0;
+          const int ll = (i & hint_mask) + ox * skip * 2, kk = (j & hint_mask) + oy * skip * 2;
+          if (ll >= 0 && ll < A.nbx && kk >= 0 && kk < A.nby) {
+            const MotionVector *m = pf + (size_t) kk * A.nbx + ll;
+            cdx = m->v[ri]; cdy = m->v[2 + ri]; valid = true;
+          }
+        }
+      } else if (lane <= 8) {
+        const bool need_x = (lane == 6 || lane == 8), need_y = (lane == 7 || lane == 8);
+        if ((!need_x || i > 0) && (!need_y || j > 0)) {
+          const MotionVector *m = mf + (size_t) (j - (need_y ? skip : 0)) * A.nbx + (i - (need_x ? skip : 0));
+          // written by this warp (left) or published by the row above (acquired above)
+          cdx = ((volatile const int16_t *) m->v)[ri];
+          cdy = ((volatile const int16_t *) m->v)[2 + ri];
+          valid = true;
+        }
+      }
+      // de-duplicate keeping the LAST occurrence (schrohierbm.c:298-321)
+      bool dup = false;
+#pragma unroll
+      for (int k = 1; k < 9; k++) {
+        const int kdx = __shfl_sync (0xffffffffu, cdx, k), kdy = __shfl_sync (0xffffffffu, cdy, k);
+        const bool kv = __shfl_sync (0xffffffffu, (int) valid, k) != 0;
+        if (k > lane && kv && kdx == cdx && kdy == cdy) dup = true;
+      }
+      const unsigned cmask = __ballot_sync (0xffffffffu, valid && !dup && lane < 9);
+
+      // ---- rank candidates with the 3-component SAD (schrometric.c:332-375) --------
+      int best_k = -1;
+      unsigned best_metric = 0xffffffffu;
+      for (int k = 0; k < 9; k++) {
+        if (!((cmask >> k) & 1)) continue;
+        int dx = __shfl_sync (0xffffffffu, cdx, k) >> s;
+        int dy = __shfl_sync (0xffffffffu, cdy, k) >> s;
+        dx = clampi (dx + x0, -bw0, A.width) - x0;
+        dy = clampi (dy + y0, -bh0, A.height) - y0;
+        unsigned metric;
+        const int e = A.ext;
+        const bool ok = !(x0 < -e || y0 < -e || x0 + A.bw > A.width + e || y0 + A.bh > A.height + e) &&
+            !(x0 + dx < -e || y0 + dy < -e || x0 + dx + A.bw > A.width + e || y0 + dy + A.bh > A.height + e);
+        if (!ok) {
+          metric = (unsigned) INT_MAX;
+        } else {
+          unsigned part = 0;
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            const int hs = c ? A.hs : 0, vs = c ? A.vs : 0;
+            const int sx = x0 >> hs, sy = y0 >> vs, rx = (x0 + dx) >> hs, ry = (y0 + dy) >> vs;
+            const int w = min (max (0, (c ? A.cw : A.width) - sx), A.bw >> hs);
+            const int h = min (max (0, (c ? A.ch : A.height) - sy), A.bh >> vs);
+            for (int p = lane; p < w * h; p += 32) {
+              const int yy = p / w, xx = p - yy * w;
+              part += (unsigned) abs ((int) __ldg (sp[c] + (ptrdiff_t) (sy + yy) * ss[c] + sx + xx)
+                  - (int) __ldg (rp[c] + (ptrdiff_t) (ry + yy) * rs[c] + rx + xx));
+            }
+          }
+          metric = warp_sum (part);
+        }
+        // signed compare as the reference (int metric < int min_metric, starting at INT_MAX)
+        if ((int) metric < (int) (best_k < 0 ? (unsigned) INT_MAX : best_metric)) { best_metric = metric; best_k = k; }
+      }
+      if (best_k < 0) best_k = __ffs (cmask) - 1;    // every candidate invalid: the reference asserts
+
+      // ---- seed + scan window (schrohierbm.c:349-364, schrometric.c:174-214) --------
+      int dx = __shfl_sync (0xffffffffu, cdx, best_k) >> s;
+      int dy = __shfl_sync (0xffffffffu, cdy, best_k) >> s;
+      dx = max (-bw0 - x0, min (A.width - x0, dx));
+      dy = max (-bh0 - y0, min (A.height - y0, dy));
+      const int xmin = max (max (-bw0, x0 + dx - A.h_range), -A.ext);
+      const int ymin = max (max (-bh0, y0 + dy - A.h_range), -A.ext);
+      const int xmax = min (min (A.width, x0 + dx + A.h_range), A.width - bw0 + A.ext);
+      const int ymax = min (min (A.height, y0 + dy + A.h_range), A.height - bh0 + A.ext);
+      const int scan_w = xmax - xmin + 1, scan_h = ymax - ymin + 1;
+      const int seed_a = dx + x0 - xmin, seed_b = dy + y0 - ymin;
+
+      // ---- full search: lanes over positions, a (x) fastest across lanes ------------
+      // key = (metric, not-seed, a, b): seed wins ties, else first strict minimum in the
+      // reference's a-outer / b-inner order (schrometric.c:121-171)
+      unsigned long long best_key = ~0ull;
+      unsigned best_l = 0, best_c = 0;
+      const uint8_t *sblk = sp[0] + (ptrdiff_t) y0 * ss[0] + x0;
+      const int npos = scan_w * scan_h;
+      for (int p = lane; p < npos; p += 32) {
+        const int b = p / scan_w, a = p - b * scan_w;
+        const unsigned l = block_sad (sblk, ss[0], rp[0] + (ptrdiff_t) (ymin + b) * rs[0] + xmin + a, rs[0], bw0, bh0);
+        unsigned c = 0;
+        if (A.use_chroma) {
+          // chroma_metrics[a*scan_h+b] = sum_k SAD_k at (ref_x/2 + a/2, ref_y/2 + b/2)
+          // (schrometric.c:73-115; C division truncates toward zero)
+          const int cx = x0 / 2, cy = y0 / 2, crx = xmin / 2 + (a >> 1), cry = ymin / 2 + (b >> 1);
+          for (int k = 1; k < 3; k++)
+            c += block_sad (sp[k] + (ptrdiff_t) cy * ss[k] + cx, ss[k], rp[k] + (ptrdiff_t) cry * rs[k] + crx, rs[k],
+                bw0 / 2, bh0 / 2);
+        }
+        const unsigned tot = l + c;
+        const unsigned notseed = (a == seed_a && b == seed_b) ? 0u : 1u;
+        const unsigned long long key = ((unsigned long long) tot << 32) | (notseed << 24) | ((unsigned) a << 12) | (unsigned) b;
+        if (key < best_key) { best_key = key; best_l = l; best_c = c; }
+      }
+      const unsigned long long wkey = warp_min64 (best_key);
+      const unsigned owner = __ballot_sync (0xffffffffu, best_key == wkey);
+      const int ol = __ffs (owner) - 1;
+      best_l = __shfl_sync (0xffffffffu, best_l, ol);
+      best_c = __shfl_sync (0xffffffffu, best_c, ol);
+      if (lane == 0) {
+        const int a = (int) ((wkey >> 12) & 0xfff), b = (int) (wkey & 0xfff);
+        MotionVector *o = mf + (size_t) j * A.nbx + i;
+        o->metric = best_l;
+        o->chroma_metric = best_c;
+        o->v[ri] = (int16_t) ((xmin + a - x0) << s);
+        o->v[2 + ri] = (int16_t) ((ymin + b - y0) << s);
+        o->flags = A.flags0;
+      }
+    }
+    // ---- publish
+    __syncwarp ();
+    if (lane == 0) {
+      __threadfence ();
+      atomicExch (prog_me, bi + 1);
+    }
+    __syncwarp ();
+  }
+}
+
+}  // namespace sb2
+
+using namespace sb2;
+
+__global__ void __launch_bounds__ (128)
+sad_batch_kernel (const uint8_t *a, int as, const uint8_t *b, int bs, const int64_t *ao, const int64_t *bo,
+    int n, int w, int h, uint32_t *out)
+{
+  // one warp per block pair, lanes split the pixels (orc_sad_nxm_u8, schroorc.orc:1760-1811)
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= n) return;
+  const uint8_t *pa = a + ao[g], *pb = b + bo[g];
+  unsigned part = 0;
+  for (int p = lane; p < w * h; p += 32) {
+    const int y = p / w, x = p - y * w;
+    part += (unsigned) abs ((int) __ldg (pa + (ptrdiff_t) y * as + x) - (int) __ldg (pb + (ptrdiff_t) y * bs + x));
+  }
+  part = warp_sum (part);
+  if (lane == 0) out[g] = part;
+}
+
+extern "C" int
+sb2_sad_u8 (const uint8_t *a, int a_stride, const uint8_t *b, int b_stride, const int64_t *a_offset,
+    const int64_t *b_offset, int n, int width, int height, uint32_t *sad, void *stream)
+{
+  if (!a || !b || !a_offset || !b_offset || !sad || n < 0 || width < 1 || height < 1)
+    return sb2::set_error (SB2_ERR_ARG, "sb2_sad_u8: bad argument");
+  if (n == 0) return SB2_OK;
+  {
+    sb2::LaunchScope scope ("sad_batch", 2.0 * width * height * n, sb2::as_stream (stream));
+    sad_batch_kernel<<<sb2::ceil_div (n, 4), 128, 0, sb2::as_stream (stream)>>> (a, a_stride, b, b_stride,
+        a_offset, b_offset, n, width, height, sad);
+  }
+  return sb2::check_cuda (cudaGetLastError (), "sad_batch_kernel launch");
+}
+
+extern "C" size_t
+sb2_hbm_workspace_bytes (int y_num_blocks, int count)
+{
+  return (size_t) y_num_blocks * (size_t) count * sizeof (int) + 256;
+}
+
+extern "C" int
+sb2_hbm_scan_hint (const sb2_hbm_params *p, const sb2_slab *src_level, const sb2_slab *ref_level,
+    int extension, int shift, int h_range, const void *parent_field, void *out_field,
+    size_t field_picture_pitch, void *workspace, size_t workspace_bytes, void *stream)
+{
+  if (!p || !src_level || !ref_level || !out_field)
+    return set_error (SB2_ERR_ARG, "sb2_hbm_scan_hint: null argument");
+  if (src_level->ncomp != 3 || ref_level->ncomp != 3 || src_level->count != ref_level->count)
+    return set_error (SB2_ERR_ARG, "sb2_hbm_scan_hint: need two 3-component slabs of equal count");
+  if (shift < 0 || shift > 8 || h_range < 1 || 2 * h_range + 1 > 42)
+    return set_error (SB2_ERR_ARG, "sb2_hbm_scan_hint: shift %d / range %d out of range (SCHRO_LIMIT_METRIC_SCAN 42)", shift, h_range);
+  if (p->use_chroma && !(p->chroma_h_shift == 1 && p->chroma_v_shift == 1))
+    return set_error (SB2_ERR_UNSUPPORTED, "sb2_hbm_scan_hint: chroma ME is defined for 4:2:0 only");
+  if (p->ref_index < 0 || p->ref_index > 1) return set_error (SB2_ERR_ARG, "sb2_hbm_scan_hint: ref_index %d", p->ref_index);
+  const int count = src_level->count;
+  const int skip = 1 << shift;
+  HbmArgs A;
+  A.src = planeset_from_slab (src_level);
+  A.ref = planeset_from_slab (ref_level);
+  A.parent = static_cast<const MotionVector *> (parent_field);
+  A.field = static_cast<MotionVector *> (out_field);
+  A.field_pitch = field_picture_pitch;
+  A.width = src_level->width[0];
+  A.height = src_level->height[0];
+  A.cw = src_level->width[1];
+  A.ch = src_level->height[1];
+  A.hs = p->chroma_h_shift;
+  A.vs = p->chroma_v_shift;
+  A.ext = extension;
+  A.bw = p->xbsep;
+  A.bh = p->ybsep;
+  A.nbx = p->x_num_blocks;
+  A.nby = p->y_num_blocks;
+  A.ref_index = p->ref_index;
+  A.shift = shift;
+  A.h_range = h_range;
+  A.use_chroma = p->use_chroma;
+  A.rows = ceil_div (A.nby, skip);
+  A.cols = ceil_div (A.nbx, skip);
+  A.count = count;
+  const int split = shift > 1 ? 0 : (shift == 1 ? 1 : 2);
+  A.flags0 = (uint32_t) (p->ref_index + 1) | ((uint32_t) split << 3);
+  const size_t need = (size_t) A.rows * count * sizeof (int);
+  if (!workspace || workspace_bytes < need)
+    return set_error (SB2_ERR_WORKSPACE, "sb2_hbm_scan_hint: workspace %zu < %zu", workspace_bytes, need);
+  A.progress = static_cast<int *> (workspace);
+  cudaStream_t st = as_stream (stream);
+  cudaError_t e = cudaMemsetAsync (workspace, 0, need, st);
+  if (e != cudaSuccess) return check_cuda (e, "cudaMemsetAsync(progress)");
+  const size_t nfield = (size_t) A.nbx * A.nby;
+  for (int pic = 0; pic < count; pic++) {
+    // fields of different pictures may be field_picture_pitch apart: init each
+    LaunchScope scope ("hbm_init_field", (double) nfield * 20, st);
+    hbm_init_field_kernel<<<(unsigned) min ((size_t) 1024, (nfield + 127) / 128), 128, 0, st>>> (
+        A.field + (size_t) pic * field_picture_pitch, nfield, A.flags0);
+  }
+  // algorithmic bytes: both pyramids of this level once + the fields
+  double bytes = 0;
+  for (int c = 0; c < 3; c++) bytes += 2.0 * src_level->width[c] * src_level->height[c] * count;
+  bytes += (double) A.rows * A.cols * 20 * (parent_field ? 2 : 1) * count;
+  const int warps = A.rows * count;
+  {
+    char tag[48];
+    snprintf (tag, sizeof (tag), "hbm_level_s%d_r%d", shift, h_range);
+    LaunchScope scope (tag, bytes, st);
+    hbm_level_kernel<<<ceil_div (warps, 4), 128, 0, st>>> (A);
+  }
+  return check_cuda (cudaGetLastError (), "hbm_level_kernel launch");
+}

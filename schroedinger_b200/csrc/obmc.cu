@@ -1,0 +1,283 @@
+// obmc.cu -- overlapped-block motion-compensation renderer for sm_100a.
+//
+// Bit-exact replacement for schro_motion_render / schro_motion_render_u8
+// (schroedinger/schromotion.c:95-155, schroedinger/schromotion8.c:700-929).
+//
+// The reference scatters block by block into an s16 accumulator strip.  Here every
+// output pixel GATHERS the (at most four, for xblen <= 2*xbsep) blocks that cover it:
+// fetches the sub-pel reference sample from the four half-pel phase planes, applies the
+// prediction mode, multiplies by the OBMC window and finishes (residual add + clamp, or
+// residual subtract) in registers -- the accumulator never touches memory unless the
+// caller asks for it.  Equality with the reference holds modulo 2^16, which is exactly
+// what its Orc addw/mullw accumulate (schromotion8.c:15-167).
+
+#include "common.cuh"
+#include <cstdio>
+
+namespace sb2 {
+
+struct MotionVector {               // == SchroMotionVector, schroedinger/schromotion.h:20-37
+  uint32_t flags;                   // pred_mode:2 using_global:1 split:2 unused:3 scan:8
+  uint32_t metric;
+  uint32_t chroma_metric;
+  int16_t v[4];                     // vec: dx0 dx1 dy0 dy1 / dc: dc0 dc1 dc2
+};
+static_assert (sizeof (MotionVector) == 20, "SchroMotionVector is 20 bytes");
+
+struct ObmcArgs {
+  PlaneSet ref0, ref1, acc, res, out;
+  const MotionVector *mvs;
+  size_t mv_pitch;                  // vectors between consecutive pictures
+  int w[SB2_MAX_COMPONENTS], h[SB2_MAX_COMPONENTS];
+  int xbsep[SB2_MAX_COMPONENTS], ybsep[SB2_MAX_COMPONENTS];
+  int xblen[SB2_MAX_COMPONENTS], yblen[SB2_MAX_COMPONENTS];
+  int hs[SB2_MAX_COMPONENTS], vs[SB2_MAX_COMPONENTS];
+  unsigned char wx[SB2_MAX_COMPONENTS][64], wy[SB2_MAX_COMPONENTS][64];
+  int nbx, nby, prec, w1, w2, bits;
+  int ncomp, add, res_is_s32, has_ref1, has_acc;
+};
+
+__device__ __forceinline__ int w16 (int x) { return (int) (short) x; }
+__device__ __forceinline__ int clampi (int x, int lo, int hi) { return min (max (x, lo), hi); }
+
+// half-pel sample (u,v) + block pixel (a,b): phase ((v&1)<<1)|(u&1) at (u>>1, v>>1)
+// (schroedinger/schroframe.c:2186-2200)
+__device__ __forceinline__ int halfpel (const uint8_t *ref, int rstride, int u, int v, int a, int b)
+{
+  const int ph = ((v & 1) << 1) | (u & 1);
+  return __ldg (ref + (ptrdiff_t) ph * (rstride >> 2) + (ptrdiff_t) ((v >> 1) + b) * rstride + (u >> 1) + a);
+}
+
+// schromotion8.c:303-335 + schroframe.c:2288-2482
+__device__ __forceinline__ int fetch (const uint8_t *ref, int rstride, int prec, int bx, int by,
+    int dx, int dy, int max_fast_x, int max_fast_y, int a, int b)
+{
+  int px = (bx << prec) + dx, py = (by << prec) + dy;
+  const int e = 32 << prec;
+  px = clampi (px, -e, max_fast_x + e - 1);
+  py = clampi (py, -e, max_fast_y + e - 1);
+  if (prec == 0) return __ldg (ref + (ptrdiff_t) (py + b) * rstride + px + a);
+  if (prec == 1) return halfpel (ref, rstride, px, py, a, b);
+  if (prec == 2) { px <<= 1; py <<= 1; }
+  const int hx = px >> 2, hy = py >> 2, rx = px & 3, ry = py & 3;
+  const int s00 = halfpel (ref, rstride, hx, hy, a, b);
+  if ((rx | ry) == 0) return s00;
+  if (ry == 0 && rx == 2) return (s00 + halfpel (ref, rstride, hx + 1, hy, a, b) + 1) >> 1;
+  if (ry == 2 && rx == 0) return (s00 + halfpel (ref, rstride, hx, hy + 1, a, b) + 1) >> 1;
+  // orc_combine4_nxm_u8 (schroorc.orc:1635-1662): weights sum to 16, fits 16 bits
+  const int s01 = halfpel (ref, rstride, hx + 1, hy, a, b);
+  const int s10 = halfpel (ref, rstride, hx, hy + 1, a, b);
+  const int s11 = halfpel (ref, rstride, hx + 1, hy + 1, a, b);
+  return ((4 - ry) * (4 - rx) * s00 + (4 - ry) * rx * s01 + ry * (4 - rx) * s10 + ry * rx * s11 + 8) >> 4;
+}
+
+__global__ void __launch_bounds__ (256)
+obmc_kernel (const ObmcArgs A)
+{
+  const int comp = blockIdx.z % A.ncomp, pic = blockIdx.z / A.ncomp;
+  const int width = A.w[comp], height = A.h[comp];
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= width || y >= height) return;
+
+  const int xbsep = A.xbsep[comp], ybsep = A.ybsep[comp], xblen = A.xblen[comp], yblen = A.yblen[comp];
+  const int xoff = (xblen - xbsep) >> 1, yoff = (yblen - ybsep) >> 1;
+  const int prec = A.prec;
+  const int max_fast_x = (width - xblen) << prec, max_fast_y = (height - yblen) << prec;
+  const int max_x_blocks = min (A.nbx - 1, (width - xoff) / xbsep);
+  const int max_y_blocks = min (A.nby - 1, (height - yoff) / ybsep);
+  const bool simple = (A.w1 == 1 && A.w2 == 1 && A.bits == 1);
+  const bool noscale = (A.w1 + A.w2 == (1 << A.bits));
+  const unsigned char *wx = A.wx[comp], *wy = A.wy[comp];
+
+  const uint8_t *ref0 = reinterpret_cast<const uint8_t *> (plane_ptr (A.ref0, pic, comp));
+  const uint8_t *ref1 = A.has_ref1 ? reinterpret_cast<const uint8_t *> (plane_ptr (A.ref1, pic, comp)) : ref0;
+  const int rs0 = A.ref0.stride[comp], rs1 = A.has_ref1 ? A.ref1.stride[comp] : rs0;
+  const MotionVector *mvs = A.mvs + (size_t) pic * A.mv_pitch;
+
+  const int j0 = (y + yoff - yblen + 1 > 0) ? (y + yoff - yblen + ybsep) / ybsep : 0;
+  const int j1 = min (A.nby - 1, (y + yoff) / ybsep);
+  const int i0 = (x + xoff - xblen + 1 > 0) ? (x + xoff - xblen + xbsep) / xbsep : 0;
+  const int i1 = min (A.nbx - 1, (x + xoff) / xbsep);
+
+  int sum = 0;
+  for (int j = j0; j <= j1; j++) {
+    const int by = ybsep * j - yoff, b = y - by;
+    for (int i = i0; i <= i1; i++) {
+      const int bx = xbsep * i - xoff, a = x - bx;
+      const MotionVector *mv = mvs + (size_t) j * A.nbx + i;
+      // 20-byte struct: flags at +0, vectors at +12 (4-byte aligned)
+      const unsigned flags = __ldg (&mv->flags);
+      const int2 vv = make_int2 (__ldg (reinterpret_cast<const int *> (mv->v)),
+          __ldg (reinterpret_cast<const int *> (mv->v) + 1));
+      const int v0 = (short) (vv.x & 0xffff), v1 = vv.x >> 16, v2 = (short) (vv.y & 0xffff), v3 = vv.y >> 16;
+      const int mode = flags & 3;
+      const bool fast = (i >= 1 && i < max_x_blocks && j >= 1 && j < max_y_blocks);
+      int v;
+      if (mode == 0) {
+        const int dc = (comp == 0 ? v0 : comp == 1 ? v1 : v2) + 128;
+        v = fast ? w16 (dc) : (dc & 0xff);
+      } else if (mode == 3) {
+        const int s0 = fetch (ref0, rs0, prec, bx, by, v0 >> A.hs[comp], v2 >> A.vs[comp], max_fast_x, max_fast_y, a, b);
+        const int s1 = fetch (ref1, rs1, prec, bx, by, v1 >> A.hs[comp], v3 >> A.vs[comp], max_fast_x, max_fast_y, a, b);
+        if (simple) {
+          v = (s0 + s1 + 1) >> 1;
+        } else if (fast) {          // block_acc_biref, schromotion8.c:127-167
+          int t = w16 (s0 * w16 (A.w1 << (6 - A.bits)));
+          const int u = w16 (s1 * w16 (A.w2 << (6 - A.bits)));
+          t = w16 (t + u);
+          t = w16 (t + 32);
+          v = t >> 6;
+        } else {                    // orc_combine2_nxm_u8, schroorc.orc:1737-1756
+          int t = w16 (s0 * w16 (A.w1));
+          const int u = w16 (s1 * w16 (A.w2));
+          t = w16 (t + u);
+          t = w16 (t + ((1 << A.bits) >> 1));
+          v = clampi (t >> A.bits, 0, 255);
+        }
+      } else {
+        const int s = (mode == 1)
+            ? fetch (ref0, rs0, prec, bx, by, v0 >> A.hs[comp], v2 >> A.vs[comp], max_fast_x, max_fast_y, a, b)
+            : fetch (ref1, rs1, prec, bx, by, v1 >> A.hs[comp], v3 >> A.vs[comp], max_fast_x, max_fast_y, a, b);
+        if (fast) {
+          if (simple) v = s;
+          else {                    // block_acc_scaled, schromotion8.c:41-71
+            int t = w16 (s * w16 ((A.w1 + A.w2) << (6 - A.bits)));
+            t = w16 (t + 32);
+            v = t >> 6;
+          }
+        } else {
+          if (noscale) v = s;       // schromotion8.c:384-398
+          else v = ((s * (A.w1 + A.w2) + (1 << (A.bits - 1))) >> A.bits) & 0xff;
+        }
+      }
+      int w_x = wx[a], w_y = wy[b];
+      if (!fast) {
+        // border blocks absorb the weight of the missing neighbour (schromotion8.c:673-693)
+        if (x < xoff) w_x += wx[2 * xoff - a - 1];
+        if (x >= A.nbx * xbsep - xoff) w_x += wx[2 * (xblen - xoff) - a - 1];
+        if (y < yoff) w_y += wy[2 * yoff - b - 1];
+        if (y >= A.nby * ybsep - yoff) w_y += wy[2 * (yblen - yoff) - b - 1];
+      }
+      sum += v * w_x * w_y;
+    }
+  }
+
+  const int a16 = w16 (sum);
+  if (A.add) {
+    // orc_rrshift6_add_s16_2d / _s32_2d (schroorc.orc:636-660)
+    const char *rrow = plane_ptr (A.res, pic, comp) + (size_t) y * A.res.stride[comp];
+    const int r = A.res_is_s32 ? w16 (reinterpret_cast<const int *> (rrow)[x])
+                               : (int) reinterpret_cast<const short *> (rrow)[x];
+    int t = w16 (a16 + 32) >> 6;
+    t = w16 (r + t);
+    reinterpret_cast<uint8_t *> (plane_ptr (A.out, pic, comp))[(size_t) y * A.out.stride[comp] + x] =
+        (uint8_t) clampi (t, 0, 255);
+    if (A.has_acc)
+      reinterpret_cast<short *> (plane_ptr (A.acc, pic, comp) + (size_t) y * A.acc.stride[comp])[x] = (short) a16;
+  } else {
+    // orc_rrshift6_sub_s16_2d (schroorc.orc:663-673)
+    short *r = reinterpret_cast<short *> (plane_ptr (A.res, pic, comp) + (size_t) y * A.res.stride[comp]) + x;
+    const int t = w16 (a16 - 8160) >> 6;
+    *r = (short) w16 (*r - t);
+    if (A.has_acc)
+      reinterpret_cast<short *> (plane_ptr (A.acc, pic, comp) + (size_t) y * A.acc.stride[comp])[x] = (short) t;
+  }
+}
+
+// schroedinger/schromotion.c:40-79
+static int get_ramp (int x, int offset)
+{
+  if (offset == 1) return x == 0 ? 3 : 5;
+  return 1 + (6 * x + offset - 1) / (2 * offset - 1);
+}
+
+static void obmc_weights (unsigned char *w, int len, int off)
+{
+  for (int i = 0; i < len; i++) {
+    int v;
+    if (off == 0) v = 8;
+    else if (i < 2 * off) v = get_ramp (i, off);
+    else if (len - 1 - i < 2 * off) v = get_ramp (len - 1 - i, off);
+    else v = 8;
+    w[i] = (unsigned char) v;
+  }
+}
+
+}  // namespace sb2
+
+using namespace sb2;
+
+extern "C" int
+sb2_obmc_render (const sb2_obmc_params *p, const void *motion_vectors, size_t mv_picture_pitch,
+    const sb2_slab *ref0, const sb2_slab *ref1, const sb2_slab *acc, const sb2_slab *residual,
+    int residual_is_s32, int add, const sb2_slab *out, void *stream)
+{
+  if (!p || !motion_vectors || !ref0 || !residual)
+    return set_error (SB2_ERR_ARG, "sb2_obmc_render: null argument");
+  if (add && !out) return set_error (SB2_ERR_ARG, "sb2_obmc_render: add needs an output slab");
+  if (!add && residual_is_s32)
+    return set_error (SB2_ERR_UNSUPPORTED, "sb2_obmc_render: the subtract direction is s16 only (as the reference)");
+  if (p->mv_precision < 0 || p->mv_precision > 3)
+    return set_error (SB2_ERR_ARG, "sb2_obmc_render: mv_precision %d", p->mv_precision);
+  if (p->xblen < p->xbsep || p->yblen < p->ybsep || p->xblen > 64 || p->yblen > 64 || p->xbsep < 1 || p->ybsep < 1)
+    return set_error (SB2_ERR_ARG, "sb2_obmc_render: bad block geometry %dx%d sep %dx%d", p->xblen, p->yblen, p->xbsep, p->ybsep);
+  const int ncomp = residual->ncomp, count = residual->count;
+  if (ncomp < 1 || ncomp > SB2_MAX_COMPONENTS || ref0->ncomp != ncomp || ref0->count != count ||
+      (ref1 && (ref1->ncomp != ncomp || ref1->count != count)) || (out && (out->ncomp != ncomp || out->count != count)) ||
+      (acc && (acc->ncomp != ncomp || acc->count != count)))
+    return set_error (SB2_ERR_ARG, "sb2_obmc_render: slab shapes differ");
+
+  ObmcArgs A;
+  A.ref0 = planeset_from_slab (ref0);
+  A.ref1 = planeset_from_slab (ref1 ? ref1 : ref0);
+  A.acc = planeset_from_slab (acc ? acc : residual);
+  A.res = planeset_from_slab (residual);
+  A.out = planeset_from_slab (out ? out : residual);
+  A.mvs = static_cast<const MotionVector *> (motion_vectors);
+  A.mv_pitch = mv_picture_pitch;
+  A.nbx = p->x_num_blocks;
+  A.nby = p->y_num_blocks;
+  A.prec = p->mv_precision;
+  A.w1 = p->picture_weight_1;
+  A.w2 = p->picture_weight_2;
+  A.bits = p->picture_weight_bits;
+  A.ncomp = ncomp;
+  A.add = add;
+  A.res_is_s32 = residual_is_s32;
+  A.has_ref1 = ref1 != nullptr;
+  A.has_acc = acc != nullptr;
+  int maxw = 0, maxh = 0;
+  double bytes = 0;
+  for (int c = 0; c < SB2_MAX_COMPONENTS; c++) {
+    const int hs = c ? p->chroma_h_shift : 0, vs = c ? p->chroma_v_shift : 0;
+    A.w[c] = c < ncomp ? residual->width[c] : 0;
+    A.h[c] = c < ncomp ? residual->height[c] : 0;
+    A.hs[c] = hs;
+    A.vs[c] = vs;
+    A.xbsep[c] = p->xbsep >> hs;
+    A.ybsep[c] = p->ybsep >> vs;
+    A.xblen[c] = p->xblen >> hs;
+    A.yblen[c] = p->yblen >> vs;
+    if (c < ncomp) {
+      if (A.xbsep[c] < 1 || A.ybsep[c] < 1)
+        return set_error (SB2_ERR_ARG, "sb2_obmc_render: block separation vanishes in component %d", c);
+      if (A.nbx * A.xbsep[c] < A.w[c] || A.nby * A.ybsep[c] < A.h[c])
+        return set_error (SB2_ERR_ARG, "sb2_obmc_render: %dx%d blocks do not cover component %d", A.nbx, A.nby, c);
+      obmc_weights (A.wx[c], A.xblen[c], (A.xblen[c] - A.xbsep[c]) / 2);
+      obmc_weights (A.wy[c], A.yblen[c], (A.yblen[c] - A.ybsep[c]) / 2);
+      maxw = max (maxw, A.w[c]);
+      maxh = max (maxh, A.h[c]);
+      // algorithmic bytes: 4 phases of each reference + residual + output
+      const double px = (double) A.w[c] * A.h[c] * count;
+      bytes += px * (4.0 * (ref1 ? 2 : 1) + (residual_is_s32 ? 4 : 2) + (add ? 1 : 4));
+    }
+  }
+  bytes += (double) A.nbx * A.nby * 20 * count;
+  dim3 grid (ceil_div (maxw, 32), ceil_div (maxh, 8), ncomp * count);
+  {
+    LaunchScope scope (add ? "obmc_render_add" : "obmc_render_sub", bytes, as_stream (stream));
+    obmc_kernel<<<grid, 256, 0, as_stream (stream)>>> (A);
+  }
+  return check_cuda (cudaGetLastError (), "obmc_kernel launch");
+}

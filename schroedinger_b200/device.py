@@ -69,7 +69,8 @@ class PictureSlab:
         self.layout = layout
         self.count = int(count)
         alloc = torch.zeros if zero else torch.empty
-        self.buf = alloc(layout.pitch * self.count, dtype=torch.uint8, device=device)
+        # 256 spare bytes: the byte-SIMD SAD path reads whole aligned words
+        self.buf = alloc(layout.pitch * self.count + 256, dtype=torch.uint8, device=device)
         self.slab = self._make_slab()
 
     def _make_slab(self):
@@ -88,7 +89,7 @@ class PictureSlab:
 
     @property
     def nbytes(self):
-        return self.buf.numel()
+        return self.layout.pitch * self.count
 
     def plane(self, pic, comp, phase=0, with_border=False):
         """Strided torch view of one plane (of one phase) of one picture."""
@@ -170,3 +171,129 @@ def _iwt(fn, name, src, dst, filter_index, transform_depth, workspace, stream):
     ptr, size = ws.get(need)
     check(fn(ctypes.byref(src.slab), ctypes.byref(dst.slab), is_s32, filter_index,
              transform_depth, ptr, size, _stream_ptr(stream)), name)
+
+
+# ---------------------------------------------------------------------------------------
+# reference-frame preparation
+# ---------------------------------------------------------------------------------------
+def mc_edgeextend(frames, phase=0, stream=None):
+    """schro_frame_mc_edgeextend on every plane of every picture of an (extended) u8 slab."""
+    require_cuda()
+    check(lib.sb2_mc_edgeextend(ctypes.byref(frames.slab), frames.layout.extension, phase,
+                                _stream_ptr(stream)), "sb2_mc_edgeextend")
+
+
+def upsample(frames, stream=None):
+    """schro_upsampled_frame_upsample: phases 1..3 + borders from edge-extended phase 0."""
+    require_cuda()
+    assert frames.layout.upsampled and frames.layout.depth == "u8"
+    check(lib.sb2_upsample(ctypes.byref(frames.slab), frames.layout.extension, _stream_ptr(stream)),
+          "sb2_upsample")
+
+
+def downsample(src, dst, stream=None):
+    """schro_frame_downsample: dst = half-size src (per component)."""
+    require_cuda()
+    check(lib.sb2_downsample(ctypes.byref(src.slab), ctypes.byref(dst.slab), _stream_ptr(stream)),
+          "sb2_downsample")
+
+
+# ---------------------------------------------------------------------------------------
+# OBMC
+# ---------------------------------------------------------------------------------------
+class ObmcParams(ctypes.Structure):
+    """Mirror of sb2_obmc_params."""
+    _fields_ = [(n, ctypes.c_int) for n in (
+        "xbsep", "ybsep", "xblen", "yblen", "x_num_blocks", "y_num_blocks", "mv_precision",
+        "picture_weight_1", "picture_weight_2", "picture_weight_bits", "chroma_h_shift",
+        "chroma_v_shift")]
+
+
+def obmc_render(params, mvs, ref0, ref1, residual, add, out=None, acc=None, stream=None):
+    """schro_motion_render for every picture.  mvs: uint8 CUDA tensor holding
+    count x (x_num_blocks*y_num_blocks) SchroMotionVector structs (20 bytes each)."""
+    require_cuda()
+    n = params.x_num_blocks * params.y_num_blocks
+    assert mvs.is_cuda and mvs.dtype == torch.uint8 and mvs.numel() >= residual.count * n * 20
+    null = ctypes.POINTER(Slab)()
+    check(lib.sb2_obmc_render(
+        ctypes.byref(params), ctypes.c_void_p(mvs.data_ptr()), ctypes.c_size_t(n),
+        ctypes.byref(ref0.slab), ctypes.byref(ref1.slab) if ref1 is not None else null,
+        ctypes.byref(acc.slab) if acc is not None else null, ctypes.byref(residual.slab),
+        1 if residual.layout.depth == "s32" else 0, 1 if add else 0,
+        ctypes.byref(out.slab) if out is not None else null, _stream_ptr(stream)), "sb2_obmc_render")
+
+
+# ---------------------------------------------------------------------------------------
+# hierarchical block matching
+# ---------------------------------------------------------------------------------------
+class HbmParams(ctypes.Structure):
+    """Mirror of sb2_hbm_params."""
+    _fields_ = [(n, ctypes.c_int) for n in (
+        "xbsep", "ybsep", "x_num_blocks", "y_num_blocks", "ref_index", "use_chroma",
+        "chroma_h_shift", "chroma_v_shift")]
+
+
+def hbm_scan_hint(params, src_level, ref_level, shift, h_range, parent, out, workspace=None,
+                  stream=None):
+    """One schro_hierarchical_bm_scan_hint level for every (picture, reference) pair.
+    parent / out: uint8 CUDA tensors of count x nblocks x 20 bytes (parent may be None)."""
+    require_cuda()
+    n = params.x_num_blocks * params.y_num_blocks
+    ws = workspace or _default_ws
+    need = lib.sb2_hbm_workspace_bytes(params.y_num_blocks, src_level.count)
+    ptr, size = ws.get(need)
+    check(lib.sb2_hbm_scan_hint(
+        ctypes.byref(params), ctypes.byref(src_level.slab), ctypes.byref(ref_level.slab),
+        src_level.layout.extension, shift, h_range,
+        ctypes.c_void_p(parent.data_ptr()) if parent is not None else None,
+        ctypes.c_void_p(out.data_ptr()), ctypes.c_size_t(n), ptr, size, _stream_ptr(stream)),
+        "sb2_hbm_scan_hint")
+
+
+def hbm_level_ranges(levels, level0_range=3):
+    """(level, half_range) pairs in the order schro_hbm_scan (schrohierbm.c:158-172) and the
+    level-0 refinement (schromotionest.c:123-127) run them."""
+    order = [(levels, 20)]
+    r = 10
+    for l in range(levels - 1, 0, -1):
+        order.append((l, max(3, r)))
+        r >>= 1
+    if level0_range > 0:
+        order.append((0, level0_range))
+    return order
+
+
+class Pyramid:
+    """Downsampled copies of `count` u8 4:2:0 pictures: level 0 = the pictures (ext 32),
+    level i+1 = sb2_downsample(level i) with extension max(xbsep, ybsep), edge-extended
+    (schro_encoder_frame_downsample, schroedinger/schroanalysis.c:9-28)."""
+
+    def __init__(self, width, height, count, levels, ext=8, level0=None):
+        self.levels = levels
+        self.slabs = [level0 if level0 is not None else
+                      PictureSlab(FrameLayout.yuv420("u8", width, height, 32), count)]
+        w, h = width, height
+        cw, ch = (width + 1) // 2, (height + 1) // 2
+        for _ in range(levels):
+            w, h, cw, ch = (w + 1) // 2, (h + 1) // 2, (cw + 1) // 2, (ch + 1) // 2
+            self.slabs.append(PictureSlab(FrameLayout("u8", [(w, h), (cw, ch), (cw, ch)], ext), count))
+
+    def build(self, stream=None):
+        mc_edgeextend(self.slabs[0], stream=stream)
+        for l in range(self.levels):
+            downsample(self.slabs[l], self.slabs[l + 1], stream=stream)
+            mc_edgeextend(self.slabs[l + 1], stream=stream)
+
+
+def hbm_scan(params, src_pyr, ref_pyr, level0_range=3, fields=None, workspace=None, stream=None):
+    """schro_hbm_scan (+ level-0 refinement): returns a list fields[level] of uint8 CUDA tensors."""
+    levels = src_pyr.levels
+    count = src_pyr.slabs[0].count
+    n = params.x_num_blocks * params.y_num_blocks
+    if fields is None:
+        fields = [torch.empty(count * n * 20, dtype=torch.uint8, device="cuda") for _ in range(levels + 1)]
+    for (l, r) in hbm_level_ranges(levels, level0_range):
+        hbm_scan_hint(params, src_pyr.slabs[l], ref_pyr.slabs[l], l, r,
+                      fields[l + 1] if l < levels else None, fields[l], workspace, stream)
+    return fields

@@ -1,0 +1,103 @@
+"""GPU parity: edge extension, half-pel upsample (3 phases + every border) and pyramid
+downsample through the sb2_* C-ABI against the oracle, bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+ORACLE = helpers.load_oracle()
+GOLD = np.load(os.path.join(helpers.GOLDEN_DIR, "frame.npz"))
+
+
+def gpu_upsampled(imgs, ext):
+    """imgs: list of 2-D u8 component images of one picture -> per component (4 phase arrays)."""
+    from schroedinger_b200 import device as dev
+    lay = dev.FrameLayout("u8", [(a.shape[1], a.shape[0]) for a in imgs], ext, True)
+    slab = dev.PictureSlab(lay, 1)
+    slab.buf.fill_(0x55)
+    for c, a in enumerate(imgs):
+        slab.upload(0, c, a)
+    dev.mc_edgeextend(slab)
+    dev.upsample(slab)
+    return [[slab.download(0, c, phase=p, with_border=True) for p in range(4)] for c in range(len(imgs))]
+
+
+def oracle_upsampled(img, ext):
+    pl = helpers.HostPlane(img.shape[1], img.shape[0], ext=ext, upsampled=True, fill=0x55)
+    pl.set_image(img)
+    helpers.cpu_edgeextend(ORACLE, "oracle", pl)
+    helpers.cpu_upsample(ORACLE, "oracle", pl)
+    return [pl.phase(p).copy() for p in range(4)]
+
+
+def test_upsample_golden(cuda):
+    idx = 0
+    while f"up{idx}_img" in GOLD.files:
+        img, ext = GOLD[f"up{idx}_img"], int(GOLD[f"up{idx}_ext"][0])
+        got = gpu_upsampled([img], ext)[0]
+        for p in range(4):
+            assert np.array_equal(got[p], GOLD[f"up{idx}_phase{p}"]), (idx, p)
+        idx += 1
+    assert idx >= 6
+
+
+@pytest.mark.parametrize("shape", [(20, 20, 4), (8, 8, 2), (3, 5, 3), (2, 9, 8), (48, 64, 32),
+                                   (37, 100, 32), (9, 3, 4), (1, 1, 2), (5, 2, 1), (130, 70, 32),
+                                   (16, 200, 32), (270, 480, 32)])
+def test_upsample_sizes(cuda, shape):
+    h, w, ext = shape
+    rng = np.random.default_rng(h * 1000 + w)
+    for name, img in helpers.patterns(h, w, np.int16, rng)[:6] + [("noise", rng.integers(0, 256, size=(h, w)))]:
+        img = np.clip(img, 0, 255).astype(np.uint8)
+        got = gpu_upsampled([img], ext)[0]
+        want = oracle_upsampled(img, ext)
+        for p in range(4):
+            assert np.array_equal(got[p], want[p]), (shape, name, p)
+
+
+def test_upsample_420_frame_1080p(cuda):
+    rng = np.random.default_rng(11)
+    imgs = [helpers.smooth_image(1080, 1920, rng), helpers.smooth_image(540, 960, rng),
+            rng.integers(0, 256, size=(540, 960)).astype(np.uint8)]
+    got = gpu_upsampled(imgs, 32)
+    for c in range(3):
+        want = oracle_upsampled(imgs[c], 32)
+        for p in range(4):
+            assert np.array_equal(got[c][p], want[p]), (c, p)
+
+
+@pytest.mark.parametrize("shape", [(10, 10), (39, 39), (7, 11), (2, 2), (5, 1), (1, 7), (99, 135),
+                                   (1080, 1920), (16, 17), (33, 64)])
+def test_downsample(cuda, shape):
+    from schroedinger_b200 import device as dev
+    h, w = shape
+    rng = np.random.default_rng(h + w)
+    img = rng.integers(0, 256, size=(h, w)).astype(np.uint8)
+    src = dev.PictureSlab(dev.FrameLayout("u8", [(w, h)]), 1)
+    dst = dev.PictureSlab(dev.FrameLayout("u8", [((w + 1) // 2, (h + 1) // 2)], 8), 1)
+    src.upload(0, 0, img)
+    dev.downsample(src, dst)
+    dev.mc_edgeextend(dst)
+    want = helpers.cpu_downsample(ORACLE, "oracle", img)
+    assert np.array_equal(dst.download(0, 0), want)
+    pl = helpers.HostPlane(want.shape[1], want.shape[0], ext=8)
+    pl.set_image(want)
+    helpers.cpu_edgeextend(ORACLE, "oracle", pl)
+    assert np.array_equal(dst.download(0, 0, with_border=True), pl.phase(0))
+
+
+def test_downsample_golden(cuda):
+    from schroedinger_b200 import device as dev
+    idx = 0
+    while f"down{idx}_img" in GOLD.files:
+        img = GOLD[f"down{idx}_img"]
+        h, w = img.shape
+        src = dev.PictureSlab(dev.FrameLayout("u8", [(w, h)]), 1)
+        dst = dev.PictureSlab(dev.FrameLayout("u8", [((w + 1) // 2, (h + 1) // 2)]), 1)
+        src.upload(0, 0, img)
+        dev.downsample(src, dst)
+        assert np.array_equal(dst.download(0, 0), GOLD[f"down{idx}_out"]), idx
+        idx += 1
