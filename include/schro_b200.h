@@ -117,6 +117,11 @@ int sb2_upsample (const sb2_slab *frames, int extension, void *stream);
  * (w+1)/2 x (h+1)/2 per component. */
 int sb2_downsample (const sb2_slab *src, const sb2_slab *dst, void *stream);
 
+/* One-direction half-pel filter of a bare plane, no borders:
+ * schro_frame_upsample_horiz / schro_frame_upsample_vert (schroedinger/schroframe.c:1557, 1612) */
+int sb2_upsample_plane_1d (uint8_t *dst, int dst_stride, const uint8_t *src, int src_stride,
+    int width, int height, int vertical, void *stream);
+
 /* ---- OBMC motion compensation ------------------------------------------- */
 
 /* The subset of SchroParams (schroedinger/schroparams.h:31-77) the renderer reads */
@@ -175,6 +180,14 @@ int sb2_hbm_scan_hint (const sb2_hbm_params *params, const sb2_slab *src_level,
 int sb2_sad_u8 (const uint8_t *a, int a_stride, const uint8_t *b, int b_stride,
     const int64_t *a_offset, const int64_t *b_offset, int n, int width, int height,
     uint32_t *sad, void *stream);
+
+/* schro_metric_get_dc (schroedinger/schrometric.c:253) and schro_metric_get_biref (:272);
+ * one block, result in device memory */
+int sb2_sad_dc_u8 (const uint8_t *a, int a_stride, int value, int width, int height, int *sad,
+    void *stream);
+int sb2_sad_biref_u8 (const uint8_t *a, int a_stride, const uint8_t *src1, int src1_stride,
+    int weight1, const uint8_t *src2, int src2_stride, int weight2, int shift, int width,
+    int height, int *sad, void *stream);
 
 #ifdef __cplusplus
 }

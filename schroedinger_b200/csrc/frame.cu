@@ -178,6 +178,36 @@ downsample_kernel (const DownArgs a)
   }
 }
 
+// ---- standalone one-direction half-pel filters (schro_frame_upsample_horiz / _vert) ----
+__global__ void __launch_bounds__ (256)
+upsample_1d_kernel (uint8_t *dst, int ds, const uint8_t *src, int ss, int w, int h, int vertical)
+{
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  int acc = 16;
+  int v;
+  if (vertical) {
+    // schroframe.c:1612-1645: rows 0..h-2 filtered, last row copied
+    if (y == h - 1) v = src[(ptrdiff_t) y * ss + x];
+    else {
+      const int t[8] = { -1, 3, -7, 21, 21, -7, 3, -1 };
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc += t[j] * src[(ptrdiff_t) clampi (y + j - 3, 0, h - 1) * ss + x];
+      v = clamp255 (acc >> 5);
+    }
+  } else {
+    // schroframe.c:1515-1555: last column copied only when the row is longer than 8
+    if (x == w - 1 && w > 8) v = src[(ptrdiff_t) y * ss + x];
+    else {
+      const int t[8] = { -1, 3, -7, 21, 21, -7, 3, -1 };
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc += t[j] * src[(ptrdiff_t) y * ss + clampi (x + j - 3, 0, w - 1)];
+      v = clamp255 (acc >> 5);
+    }
+  }
+  dst[(ptrdiff_t) y * ds + x] = (uint8_t) v;
+}
+
 static int check_frame_slab (const sb2_slab *s, const char *who)
 {
   if (!s || !s->base) return set_error (SB2_ERR_ARG, "%s: null slab", who);
@@ -291,4 +321,17 @@ sb2_downsample (const sb2_slab *src, const sb2_slab *dst, void *stream)
     downsample_kernel<<<grid, 256, 0, as_stream (stream)>>> (a);
   }
   return check_cuda (cudaGetLastError (), "downsample_kernel launch");
+}
+
+extern "C" int
+sb2_upsample_plane_1d (uint8_t *dst, int dst_stride, const uint8_t *src, int src_stride, int width,
+    int height, int vertical, void *stream)
+{
+  if (!dst || !src || width < 1 || height < 1) return set_error (SB2_ERR_ARG, "sb2_upsample_plane_1d: bad argument");
+  dim3 grid (ceil_div (width, 32), ceil_div (height, 8));
+  {
+    LaunchScope scope (vertical ? "upsample_vert" : "upsample_horiz", 2.0 * width * height, as_stream (stream));
+    upsample_1d_kernel<<<grid, 256, 0, as_stream (stream)>>> (dst, dst_stride, src, src_stride, width, height, vertical);
+  }
+  return check_cuda (cudaGetLastError (), "upsample_1d_kernel launch");
 }

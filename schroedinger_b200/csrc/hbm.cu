@@ -302,6 +302,60 @@ sad_batch_kernel (const uint8_t *a, int as, const uint8_t *b, int bs, const int6
   if (lane == 0) out[g] = part;
 }
 
+__global__ void __launch_bounds__ (32)
+sad_dc_kernel (const uint8_t *a, int as, int value, int w, int h, int *out)
+{
+  // schro_metric_get_dc (schroedinger/schrometric.c:253-270)
+  unsigned part = 0;
+  for (int p = threadIdx.x; p < w * h; p += 32) {
+    const int y = p / w, x = p - y * w;
+    part += (unsigned) abs (value - (int) a[(ptrdiff_t) y * as + x]);
+  }
+  part = warp_sum (part);
+  if (threadIdx.x == 0) *out = (int) part;
+}
+
+__global__ void __launch_bounds__ (32)
+sad_biref_kernel (const uint8_t *a, int as, const uint8_t *s1, int s1s, int w1, const uint8_t *s2, int s2s,
+    int w2, int shift, int w, int h, int *out)
+{
+  // schro_metric_get_biref (schroedinger/schrometric.c:272-304)
+  const int offset = 1 << (shift - 1);
+  unsigned part = 0;
+  for (int p = threadIdx.x; p < w * h; p += 32) {
+    const int y = p / w, x = p - y * w;
+    const int v = ((int) s1[(ptrdiff_t) y * s1s + x] * w1 + (int) s2[(ptrdiff_t) y * s2s + x] * w2 + offset) >> shift;
+    part += (unsigned) abs ((int) a[(ptrdiff_t) y * as + x] - v);
+  }
+  part = warp_sum (part);
+  if (threadIdx.x == 0) *out = (int) part;
+}
+
+extern "C" int
+sb2_sad_dc_u8 (const uint8_t *a, int a_stride, int value, int width, int height, int *sad, void *stream)
+{
+  if (!a || !sad || width < 1 || height < 1) return sb2::set_error (SB2_ERR_ARG, "sb2_sad_dc_u8: bad argument");
+  {
+    sb2::LaunchScope scope ("sad_dc", 1.0 * width * height, sb2::as_stream (stream));
+    sad_dc_kernel<<<1, 32, 0, sb2::as_stream (stream)>>> (a, a_stride, value, width, height, sad);
+  }
+  return sb2::check_cuda (cudaGetLastError (), "sad_dc_kernel launch");
+}
+
+extern "C" int
+sb2_sad_biref_u8 (const uint8_t *a, int a_stride, const uint8_t *src1, int src1_stride, int weight1,
+    const uint8_t *src2, int src2_stride, int weight2, int shift, int width, int height, int *sad, void *stream)
+{
+  if (!a || !src1 || !src2 || !sad || width < 1 || height < 1 || shift < 1)
+    return sb2::set_error (SB2_ERR_ARG, "sb2_sad_biref_u8: bad argument");
+  {
+    sb2::LaunchScope scope ("sad_biref", 3.0 * width * height, sb2::as_stream (stream));
+    sad_biref_kernel<<<1, 32, 0, sb2::as_stream (stream)>>> (a, a_stride, src1, src1_stride, weight1, src2,
+        src2_stride, weight2, shift, width, height, sad);
+  }
+  return sb2::check_cuda (cudaGetLastError (), "sad_biref_kernel launch");
+}
+
 extern "C" int
 sb2_sad_u8 (const uint8_t *a, int a_stride, const uint8_t *b, int b_stride, const int64_t *a_offset,
     const int64_t *b_offset, int n, int width, int height, uint32_t *sad, void *stream)

@@ -1,0 +1,353 @@
+/*
+ * schro_host_frame.c -- the reference's frame-preparation, OBMC and SAD entry points on top
+ * of the CUDA layer.
+ *
+ *   schro_frame_mc_edgeextend        schroedinger/schroframe.c:1986-1997
+ *   schro_upsampled_frame_upsample   schroedinger/schroframe.c:2000-2030
+ *   schro_frame_upsample_horiz/vert  schroedinger/schroframe.c:1557-1645
+ *   schro_frame_downsample           schroedinger/schroframe.c:1505-1513
+ *   schro_motion_new / _free         schroedinger/schromotion.c:14-38
+ *   schro_motion_render[_u8]         schroedinger/schromotion.c:95-155, schromotion8.c:700
+ *   schro_motion_init_obmc_weight    schroedinger/schromotion.c:52-93
+ *   schro_metric_absdiff_u8 / _get / _get_dc / _get_biref   schroedinger/schrometric.c:10-304
+ *
+ * Frames in host memory are staged H2D / D2H on the calling thread's stream (whole frame
+ * regions in one DMA each); frames from the CUDA domain are used where they lie.
+ */
+#include "schro_host.h"
+#include <stdlib.h>
+#include <string.h>
+
+/* A frame as the CUDA layer sees it: a one-picture slab plus, for host frames, the
+ * device staging copy of the whole region. */
+typedef struct {
+  sb2_slab slab;
+  SchroFrame *frame;
+  void *dev_region;     /* NULL for device frames */
+  size_t region_bytes;
+  int bpp;
+} Staged;
+
+static size_t
+frame_region_bytes (const SchroFrame *f)
+{
+  return (size_t) f->components[0].length + (size_t) f->components[1].length +
+      (size_t) f->components[2].length;
+}
+
+static void
+stage_describe (Staged *s, SchroFrame *f, char *base)
+{
+  int k;
+  memset (&s->slab, 0, sizeof (s->slab));
+  s->slab.base = base;
+  s->slab.picture_pitch = s->region_bytes;
+  s->slab.count = 1;
+  s->slab.ncomp = 3;
+  for (k = 0; k < 3; k++) {
+    s->slab.offset[k] = (size_t) ((char *) f->components[k].data - (char *) f->regions[0]);
+    s->slab.stride[k] = f->components[k].stride;
+    s->slab.width[k] = f->components[k].width;
+    s->slab.height[k] = f->components[k].height;
+  }
+}
+
+/* upload != 0: copy the region to the device (host frames only) */
+static void
+stage_in (Sb2hContext *cx, Staged *s, SchroFrame *f, int which_buf, int upload)
+{
+  s->frame = f;
+  s->bpp = sb2h_bpp (f->format);
+  s->region_bytes = frame_region_bytes (f);
+  SB2H_ASSERT (f->regions[0] != NULL);
+  if (sb2h_mem_kind (f->regions[0]) == SB2H_MEM_DEVICE) {
+    s->dev_region = NULL;
+    stage_describe (s, f, f->regions[0]);
+    return;
+  }
+  s->dev_region = sb2h_dev_buffer (cx, which_buf, s->region_bytes + 256);
+  stage_describe (s, f, s->dev_region);
+  if (upload)
+    SB2H_CUDA (cudaMemcpyAsync (s->dev_region, f->regions[0], s->region_bytes, cudaMemcpyDefault,
+            cx->stream));
+}
+
+static void
+stage_out (Sb2hContext *cx, Staged *s)
+{
+  if (s->dev_region)
+    SB2H_CUDA (cudaMemcpyAsync (s->frame->regions[0], s->dev_region, s->region_bytes,
+            cudaMemcpyDefault, cx->stream));
+}
+
+static void
+require_u8 (const SchroFrame *f, const char *who)
+{
+  if (SCHRO_FRAME_FORMAT_DEPTH (f->format) != SCHRO_FRAME_FORMAT_DEPTH_U8)
+    sb2h_fatal (who, "needs a u8 frame (format 0x%x)", (unsigned) f->format);
+}
+
+void
+schro_frame_mc_edgeextend (SchroFrame *frame)
+{
+  Sb2hContext *cx = sb2h_context ();
+  Staged s;
+  require_u8 (frame, __func__);
+  stage_in (cx, &s, frame, SB2H_BUF_IN, 1);
+  SB2H_CHECK (sb2_mc_edgeextend (&s.slab, frame->extension, 0, cx->stream), "sb2_mc_edgeextend");
+  stage_out (cx, &s);
+  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+}
+
+void
+schro_upsampled_frame_upsample (SchroFrame *df)
+{
+  Sb2hContext *cx = sb2h_context ();
+  Staged s;
+  if (df->upsample_done) return;
+  SB2H_ASSERT (df->is_upsampled);
+  require_u8 (df, __func__);
+  df->upsample_done = 1;
+  stage_in (cx, &s, df, SB2H_BUF_IN, 1);
+  SB2H_CHECK (sb2_upsample (&s.slab, df->extension, cx->stream), "sb2_upsample");
+  stage_out (cx, &s);
+  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+}
+
+static void
+upsample_1d (SchroFrameData *dest, SchroFrameData *src, int vertical)
+{
+  Sb2hContext *cx = sb2h_context ();
+  const int w = src->width, h = vertical ? dest->height : dest->height;
+  if (SCHRO_FRAME_FORMAT_DEPTH (dest->format) != SCHRO_FRAME_FORMAT_DEPTH_U8 ||
+      src->format != dest->format)
+    sb2h_fatal (__func__, "unimplemented format (as the reference, schroframe.c:1563-1568)");
+  if (sb2h_mem_kind (src->data) == SB2H_MEM_DEVICE) {
+    SB2H_CHECK (sb2_upsample_plane_1d (dest->data, dest->stride, src->data, src->stride, w, h,
+            vertical, cx->stream), "sb2_upsample_plane_1d");
+  } else {
+    const size_t pitch = ((size_t) w + 15) & ~(size_t) 15;
+    uint8_t *din = sb2h_dev_buffer (cx, SB2H_BUF_IN, pitch * h);
+    uint8_t *dout = sb2h_dev_buffer (cx, SB2H_BUF_OUT, pitch * h);
+    sb2h_copy_rect (cx, din, pitch, src->data, src->stride, w, h);
+    SB2H_CHECK (sb2_upsample_plane_1d (dout, (int) pitch, din, (int) pitch, w, h, vertical,
+            cx->stream), "sb2_upsample_plane_1d");
+    sb2h_copy_rect (cx, dest->data, dest->stride, dout, pitch, w, h);
+  }
+  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+}
+
+void
+schro_frame_upsample_horiz (SchroFrameData *dest, SchroFrameData *src)
+{
+  upsample_1d (dest, src, 0);
+}
+
+void
+schro_frame_upsample_vert (SchroFrameData *dest, SchroFrameData *src)
+{
+  upsample_1d (dest, src, 1);
+}
+
+void
+schro_frame_downsample (SchroFrame *dest, SchroFrame *src)
+{
+  Sb2hContext *cx = sb2h_context ();
+  Staged s, d;
+  require_u8 (src, __func__);
+  require_u8 (dest, __func__);
+  stage_in (cx, &s, src, SB2H_BUF_IN, 1);
+  stage_in (cx, &d, dest, SB2H_BUF_OUT, 1);     /* keep dest's borders as they are */
+  SB2H_CHECK (sb2_downsample (&s.slab, &d.slab, cx->stream), "sb2_downsample");
+  stage_out (cx, &d);
+  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+}
+
+/* ---- OBMC ------------------------------------------------------------------ */
+SchroMotion *
+schro_motion_new (SchroParams *params, SchroFrame *ref1, SchroFrame *ref2)
+{
+  SchroMotion *motion = calloc (1, sizeof (SchroMotion));
+  motion->params = params;
+  motion->src1 = ref1;
+  motion->src2 = ref2;
+  motion->motion_vectors = calloc ((size_t) params->x_num_blocks * params->y_num_blocks,
+      sizeof (SchroMotionVector));
+  return motion;
+}
+
+void
+schro_motion_free (SchroMotion *motion)
+{
+  free (motion->motion_vectors);
+  free (motion);
+}
+
+static int
+ramp (int x, int offset)
+{
+  if (offset == 1) return x == 0 ? 3 : 5;
+  return 1 + (6 * x + offset - 1) / (2 * offset - 1);
+}
+
+/* Host-side table only (the kernels build their own copy); kept because it is public API. */
+void
+schro_motion_init_obmc_weight (SchroMotion *motion)
+{
+  int i, j;
+  for (i = 0; i < motion->xblen; i++) {
+    int w;
+    if (motion->xoffset == 0) w = 8;
+    else if (i < 2 * motion->xoffset) w = ramp (i, motion->xoffset);
+    else if (motion->xblen - 1 - i < 2 * motion->xoffset) w = ramp (motion->xblen - 1 - i, motion->xoffset);
+    else w = 8;
+    motion->weight_x[i] = w;
+  }
+  for (j = 0; j < motion->yblen; j++) {
+    int w;
+    if (motion->yoffset == 0) w = 8;
+    else if (j < 2 * motion->yoffset) w = ramp (j, motion->yoffset);
+    else if (motion->yblen - 1 - j < 2 * motion->yoffset) w = ramp (motion->yblen - 1 - j, motion->yoffset);
+    else w = 8;
+    motion->weight_y[j] = w;
+  }
+  if (motion->obmc_weight.data) {
+    for (j = 0; j < motion->yblen; j++) {
+      int16_t *row = (int16_t *) ((char *) motion->obmc_weight.data + (size_t) motion->obmc_weight.stride * j);
+      for (i = 0; i < motion->xblen; i++) row[i] = (int16_t) (motion->weight_x[i] * motion->weight_y[j]);
+    }
+  }
+}
+
+void
+schro_motion_render_u8 (SchroMotion *motion, SchroFrame *dest, SchroFrame *addframe, int add,
+    SchroFrame *output_frame)
+{
+  Sb2hContext *cx = sb2h_context ();
+  SchroParams *params = motion->params;
+  Staged r0, r1, acc, res, out;
+  sb2_obmc_params p;
+  const size_t nmv = (size_t) params->x_num_blocks * params->y_num_blocks;
+  void *dmv;
+  int res_is_s32;
+
+  if (params->num_refs == 1) SB2H_ASSERT (params->picture_weight_2 == 1);   /* schromotion8.c:711 */
+  if (params->have_global_motion)
+    sb2h_fatal (__func__, "global motion is outside the B200 picture core (the reference falls back to "
+        "its per-pixel renderer, schromotion.c:113-121)");
+  if (add && !output_frame) sb2h_fatal (__func__, "add needs an output frame");
+  require_u8 (motion->src1, __func__);
+  if (motion->src1->extension < 32 || !motion->src1->is_upsampled)
+    sb2h_fatal (__func__, "reference frames must be upsampled with extension >= 32");
+  res_is_s32 = SCHRO_FRAME_FORMAT_DEPTH (addframe->format) == SCHRO_FRAME_FORMAT_DEPTH_S32;
+
+  memset (&p, 0, sizeof (p));
+  p.xbsep = params->xbsep_luma;
+  p.ybsep = params->ybsep_luma;
+  p.xblen = params->xblen_luma;
+  p.yblen = params->yblen_luma;
+  p.x_num_blocks = params->x_num_blocks;
+  p.y_num_blocks = params->y_num_blocks;
+  p.mv_precision = params->mv_precision;
+  p.picture_weight_1 = params->picture_weight_1;
+  p.picture_weight_2 = params->picture_weight_2;
+  p.picture_weight_bits = params->picture_weight_bits;
+  p.chroma_h_shift = SCHRO_CHROMA_FORMAT_H_SHIFT (params->video_format->chroma_format);
+  p.chroma_v_shift = SCHRO_CHROMA_FORMAT_V_SHIFT (params->video_format->chroma_format);
+
+  stage_in (cx, &r0, motion->src1, SB2H_BUF_IN, 1);
+  if (motion->src2) stage_in (cx, &r1, motion->src2, SB2H_BUF_OUT, 1);
+  stage_in (cx, &acc, dest, SB2H_BUF_AUX0, 1);     /* keeps padding / borders of dest intact */
+  stage_in (cx, &res, addframe, SB2H_BUF_AUX1, 1);
+  if (output_frame) stage_in (cx, &out, output_frame, SB2H_BUF_AUX2, 1);
+  dmv = sb2h_dev_buffer (cx, SB2H_BUF_AUX3, nmv * sizeof (SchroMotionVector));
+  SB2H_CUDA (cudaMemcpyAsync (dmv, motion->motion_vectors, nmv * sizeof (SchroMotionVector),
+          cudaMemcpyDefault, cx->stream));
+  /* the kernel sizes its grid from the residual slab: all frames share the picture size */
+  SB2H_CHECK (sb2_obmc_render (&p, dmv, nmv, &r0.slab, motion->src2 ? &r1.slab : NULL, &acc.slab,
+          &res.slab, res_is_s32, add, output_frame ? &out.slab : NULL, cx->stream), "sb2_obmc_render");
+  stage_out (cx, &acc);
+  if (add) stage_out (cx, &out);
+  else stage_out (cx, &res);
+  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+}
+
+void
+schro_motion_render (SchroMotion *motion, SchroFrame *dest, SchroFrame *addframe, int add,
+    SchroFrame *output_frame)
+{
+  schro_motion_render_u8 (motion, dest, addframe, add, output_frame);
+}
+
+/* ---- SAD primitives ---------------------------------------------------------- */
+static const uint8_t *
+block_to_device (Sb2hContext *cx, int which, const uint8_t *p, int stride, int w, int h, int *dstride)
+{
+  if (sb2h_mem_kind (p) == SB2H_MEM_DEVICE) {
+    *dstride = stride;
+    return p;
+  }
+  {
+    const size_t pitch = ((size_t) w + 15) & ~(size_t) 15;
+    uint8_t *d = sb2h_dev_buffer (cx, which, pitch * h + 256);
+    sb2h_copy_rect (cx, d, pitch, p, (size_t) stride, (size_t) w, h);
+    *dstride = (int) pitch;
+    return d;
+  }
+}
+
+int
+schro_metric_absdiff_u8 (uint8_t *a, int a_stride, uint8_t *b, int b_stride, int width, int height)
+{
+  Sb2hContext *cx = sb2h_context ();
+  int as, bs;
+  const uint8_t *da = block_to_device (cx, SB2H_BUF_IN, a, a_stride, width, height, &as);
+  const uint8_t *db = block_to_device (cx, SB2H_BUF_OUT, b, b_stride, width, height, &bs);
+  int64_t *off = sb2h_dev_buffer (cx, SB2H_BUF_AUX0, 64);
+  uint32_t result = 0;
+  SB2H_CUDA (cudaMemsetAsync (off, 0, 64, cx->stream));
+  SB2H_CHECK (sb2_sad_u8 (da, as, db, bs, off, off + 1, 1, width, height, (uint32_t *) (off + 2),
+          cx->stream), "sb2_sad_u8");
+  SB2H_CUDA (cudaMemcpyAsync (&result, off + 2, sizeof (result), cudaMemcpyDefault, cx->stream));
+  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  return (int) result;
+}
+
+int
+schro_metric_get (SchroFrameData *src1, SchroFrameData *src2, int width, int height)
+{
+  return schro_metric_absdiff_u8 (src1->data, src1->stride, src2->data, src2->stride, width, height);
+}
+
+int
+schro_metric_get_dc (SchroFrameData *src, int value, int width, int height)
+{
+  Sb2hContext *cx = sb2h_context ();
+  int as, result = 0;
+  const uint8_t *da;
+  int *dres;
+  SB2H_ASSERT (src->width >= width && src->height >= height);
+  da = block_to_device (cx, SB2H_BUF_IN, src->data, src->stride, width, height, &as);
+  dres = sb2h_dev_buffer (cx, SB2H_BUF_AUX0, 64);
+  SB2H_CHECK (sb2_sad_dc_u8 (da, as, value, width, height, dres, cx->stream), "sb2_sad_dc_u8");
+  SB2H_CUDA (cudaMemcpyAsync (&result, dres, sizeof (result), cudaMemcpyDefault, cx->stream));
+  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  return result;
+}
+
+int
+schro_metric_get_biref (SchroFrameData *fd, SchroFrameData *src1, int weight1, SchroFrameData *src2,
+    int weight2, int shift, int width, int height)
+{
+  Sb2hContext *cx = sb2h_context ();
+  int as, s1s, s2s, result = 0;
+  const uint8_t *da = block_to_device (cx, SB2H_BUF_IN, fd->data, fd->stride, width, height, &as);
+  const uint8_t *d1 = block_to_device (cx, SB2H_BUF_OUT, src1->data, src1->stride, width, height, &s1s);
+  const uint8_t *d2 = block_to_device (cx, SB2H_BUF_AUX1, src2->data, src2->stride, width, height, &s2s);
+  int *dres = sb2h_dev_buffer (cx, SB2H_BUF_AUX0, 64);
+  SB2H_CHECK (sb2_sad_biref_u8 (da, as, d1, s1s, weight1, d2, s2s, weight2, shift, width, height, dres,
+          cx->stream), "sb2_sad_biref_u8");
+  SB2H_CUDA (cudaMemcpyAsync (&result, dres, sizeof (result), cudaMemcpyDefault, cx->stream));
+  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  return result;
+}

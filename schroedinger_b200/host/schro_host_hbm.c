@@ -1,0 +1,187 @@
+/*
+ * schro_host_hbm.c -- hierarchical block matching entry points on top of the CUDA layer.
+ *
+ *   schro_motion_field_new / _free          schroedinger/schromotionest.c:395-415
+ *   schro_hbm_new (as _new_from_frames)     schroedinger/schrohierbm.c:25-64
+ *   schro_hbm_ref / _unref                  schroedinger/schrohierbm.c:66-116
+ *   schro_hbm_motion_field                  schroedinger/schrohierbm.c:122-128
+ *   schro_hbm_scan                          schroedinger/schrohierbm.c:158-172
+ *   schro_hierarchical_bm_scan_hint         schroedinger/schrohierbm.c:174-383
+ *
+ * The pyramid levels are uploaded once per SchroHierBm (whole frame regions, borders
+ * included) and the motion fields stay on the device between levels; each level's field is
+ * also copied back into a host SchroMotionField, which is what callers read.
+ */
+#include "schro_host.h"
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+  SchroHierBm pub;                       /* the reference's struct, first */
+  void *dev_src[9], *dev_ref[9];         /* device copies of host pyramid levels (NULL: zero-copy) */
+  void *dev_field[9];                    /* device motion field per level */
+  void *dev_ws;
+  size_t ws_bytes;
+} Sb2hHierBm;
+
+SchroMotionField *
+schro_motion_field_new (int x_num_blocks, int y_num_blocks)
+{
+  SchroMotionField *mf = calloc (1, sizeof (SchroMotionField));
+  mf->x_num_blocks = x_num_blocks;
+  mf->y_num_blocks = y_num_blocks;
+  mf->motion_vectors = calloc ((size_t) x_num_blocks * y_num_blocks, sizeof (SchroMotionVector));
+  return mf;
+}
+
+void
+schro_motion_field_free (SchroMotionField *field)
+{
+  free (field->motion_vectors);
+  free (field);
+}
+
+SchroHierBm *
+schro_hbm_new_from_frames (SchroParams *params, int ref, int hierarchy_levels, schro_bool use_chroma,
+    SchroFrame **src_frames, SchroFrame **ref_frames)
+{
+  Sb2hHierBm *h = calloc (1, sizeof (Sb2hHierBm));
+  int i;
+  SB2H_ASSERT (hierarchy_levels >= 1 && hierarchy_levels <= 8);
+  h->pub.ref_count = 1;
+  h->pub.ref = ref;
+  h->pub.hierarchy_levels = hierarchy_levels;
+  h->pub.params = params;
+  h->pub.use_chroma = use_chroma ? 1 : 0;
+  h->pub.downsampled_src = calloc ((size_t) hierarchy_levels + 1, sizeof (SchroFrame *));
+  h->pub.downsampled_ref = calloc ((size_t) hierarchy_levels + 1, sizeof (SchroFrame *));
+  h->pub.downsampled_mf = calloc ((size_t) hierarchy_levels + 1, sizeof (SchroMotionField *));
+  for (i = 0; i <= hierarchy_levels; i++) {
+    SB2H_ASSERT (src_frames[i] && ref_frames[i]);
+    h->pub.downsampled_src[i] = schro_frame_ref (src_frames[i]);
+    h->pub.downsampled_ref[i] = schro_frame_ref (ref_frames[i]);
+  }
+  return &h->pub;
+}
+
+SchroHierBm *
+schro_hbm_ref (SchroHierBm *src)
+{
+  SB2H_ASSERT (src && src->ref_count > 0);
+  ++src->ref_count;
+  return src;
+}
+
+void
+schro_hbm_unref (SchroHierBm *hbm)
+{
+  Sb2hHierBm *h = (Sb2hHierBm *) hbm;
+  int i;
+  if (--hbm->ref_count > 0) return;
+  for (i = 0; i <= hbm->hierarchy_levels; i++) {
+    if (hbm->downsampled_src[i]) schro_frame_unref (hbm->downsampled_src[i]);
+    if (hbm->downsampled_ref[i]) schro_frame_unref (hbm->downsampled_ref[i]);
+    if (hbm->downsampled_mf[i]) schro_motion_field_free (hbm->downsampled_mf[i]);
+    if (h->dev_src[i]) cudaFree (h->dev_src[i]);
+    if (h->dev_ref[i]) cudaFree (h->dev_ref[i]);
+    if (h->dev_field[i]) cudaFree (h->dev_field[i]);
+  }
+  if (h->dev_ws) cudaFree (h->dev_ws);
+  free (hbm->downsampled_mf);
+  free (hbm->downsampled_ref);
+  free (hbm->downsampled_src);
+  free (h);
+}
+
+SchroMotionField *
+schro_hbm_motion_field (SchroHierBm *hbm, int level)
+{
+  SB2H_ASSERT (hbm && hbm->ref_count > 0 && level <= hbm->hierarchy_levels);
+  return hbm->downsampled_mf[level];
+}
+
+static void
+level_slab (Sb2hContext *cx, SchroFrame *f, void **cache, sb2_slab *slab)
+{
+  const size_t bytes = (size_t) f->components[0].length + f->components[1].length + f->components[2].length;
+  char *base;
+  int k;
+  if (SCHRO_FRAME_FORMAT_DEPTH (f->format) != SCHRO_FRAME_FORMAT_DEPTH_U8)
+    sb2h_fatal (__func__, "block matching needs u8 frames");
+  if (sb2h_mem_kind (f->regions[0]) == SB2H_MEM_DEVICE) {
+    base = f->regions[0];
+  } else {
+    if (!*cache) {
+      SB2H_CUDA (cudaMalloc (cache, bytes + 256));
+      SB2H_CUDA (cudaMemcpyAsync (*cache, f->regions[0], bytes, cudaMemcpyDefault, cx->stream));
+    }
+    base = *cache;
+  }
+  memset (slab, 0, sizeof (*slab));
+  slab->base = base;
+  slab->picture_pitch = bytes;
+  slab->count = 1;
+  slab->ncomp = 3;
+  for (k = 0; k < 3; k++) {
+    slab->offset[k] = (size_t) ((char *) f->components[k].data - (char *) f->regions[0]);
+    slab->stride[k] = f->components[k].stride;
+    slab->width[k] = f->components[k].width;
+    slab->height[k] = f->components[k].height;
+  }
+}
+
+void
+schro_hierarchical_bm_scan_hint (SchroHierBm *hbm, int shift, int h_range)
+{
+  Sb2hHierBm *h = (Sb2hHierBm *) hbm;
+  Sb2hContext *cx = sb2h_context ();
+  SchroParams *params = hbm->params;
+  SchroFrame *fs, *fr;
+  sb2_slab ss, rs;
+  sb2_hbm_params p;
+  SchroMotionField *mf;
+  const size_t n = (size_t) params->x_num_blocks * params->y_num_blocks;
+
+  SB2H_ASSERT (shift >= 0 && shift <= hbm->hierarchy_levels);
+  fs = hbm->downsampled_src[shift];
+  fr = hbm->downsampled_ref[shift];
+  level_slab (cx, fs, &h->dev_src[shift], &ss);
+  level_slab (cx, fr, &h->dev_ref[shift], &rs);
+  memset (&p, 0, sizeof (p));
+  p.xbsep = params->xbsep_luma;
+  p.ybsep = params->ybsep_luma;
+  p.x_num_blocks = params->x_num_blocks;
+  p.y_num_blocks = params->y_num_blocks;
+  p.ref_index = hbm->ref;
+  p.use_chroma = hbm->use_chroma;
+  p.chroma_h_shift = SCHRO_FRAME_FORMAT_H_SHIFT (fs->format);
+  p.chroma_v_shift = SCHRO_FRAME_FORMAT_V_SHIFT (fs->format);
+  if (!h->dev_ws) {
+    h->ws_bytes = sb2_hbm_workspace_bytes (params->y_num_blocks, 1);
+    SB2H_CUDA (cudaMalloc (&h->dev_ws, h->ws_bytes));
+  }
+  if (!h->dev_field[shift])
+    SB2H_CUDA (cudaMalloc (&h->dev_field[shift], n * sizeof (SchroMotionVector)));
+  SB2H_CHECK (sb2_hbm_scan_hint (&p, &ss, &rs, fs->extension, shift, h_range,
+          shift < hbm->hierarchy_levels ? h->dev_field[shift + 1] : NULL, h->dev_field[shift], n,
+          h->dev_ws, h->ws_bytes, cx->stream), "sb2_hbm_scan_hint");
+  /* schro_hbm_set_motion_field: a new field replaces the level's previous one */
+  mf = schro_motion_field_new (params->x_num_blocks, params->y_num_blocks);
+  SB2H_CUDA (cudaMemcpyAsync (mf->motion_vectors, h->dev_field[shift], n * sizeof (SchroMotionVector),
+          cudaMemcpyDefault, cx->stream));
+  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  if (hbm->downsampled_mf[shift]) schro_motion_field_free (hbm->downsampled_mf[shift]);
+  hbm->downsampled_mf[shift] = mf;
+}
+
+void
+schro_hbm_scan (SchroHierBm *hbm)
+{
+  int i, half_scan_range = 20;
+  const int n_levels = hbm->hierarchy_levels;
+  SB2H_ASSERT (n_levels > 0);
+  schro_hierarchical_bm_scan_hint (hbm, n_levels, half_scan_range);
+  half_scan_range >>= 1;
+  for (i = n_levels - 1; 1 <= i; --i, half_scan_range >>= 1)
+    schro_hierarchical_bm_scan_hint (hbm, i, half_scan_range > 3 ? half_scan_range : 3);
+}
