@@ -43,6 +43,9 @@ def workload_spec(name):
         return dict(width=1920, height=1080, iwt_w=1920, iwt_h=1088, depth_name="s16", filter=1,
                     transform_depth=4, batch=64,
                     label="1080p 4:2:0 8-bit: forward+inverse LeGall 5/3 4-level s16 (config 1)")
+    if name == "picture_core_cif":       # tiny, for CPU-side testing of bench.py itself
+        return dict(width=352, height=288, iwt_w=352, iwt_h=288, depth_name="s32", filter=6,
+                    transform_depth=5, batch=4, label="CIF test workload, all stages")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -118,6 +121,44 @@ def make_coeff_frame(spec, rng):
             for s in ((h, w), (h // 2, w // 2), (h // 2, w // 2))]
 
 
+def make_mv_field(nbx, nby, rng):
+    """modes {0:12%,1:38%,2:25%,3:25%}, vectors uniform +-64 quarter-pel
+    (+1% outliers +-4000), DC +-127."""
+    n = nbx * nby
+    mv = np.zeros(n, dtype=np.dtype([("flags", "<u4"), ("metric", "<u4"), ("chroma_metric", "<u4"),
+                                     ("v", "<i2", (4,))]))
+    mode = rng.choice(4, size=n, p=[0.12, 0.38, 0.25, 0.25])
+    v = rng.integers(-64, 65, size=(n, 4))
+    out = rng.random(n) < 0.01
+    v[out] = rng.integers(-4000, 4001, size=(int(out.sum()), 4))
+    dc = rng.integers(-127, 128, size=(n, 4))
+    dc[:, 3] = 0
+    mv["v"] = np.where((mode == 0)[:, None], dc, v)
+    mv["flags"] = mode.astype(np.uint32)
+    return mv
+
+
+def textured_frame(width, height, rng, pan=(0, 0)):
+    """One u8 4:2:0 picture: smooth texture + noise, optionally panned."""
+    yy, xx = np.mgrid[0:height, 0:width]
+    xx = xx + pan[0]
+    yy = yy + pan[1]
+    y = (128 + 50 * np.sin(xx / 9.0) * np.cos(yy / 7.0) + 30 * np.sin((xx + 2 * yy) / 31.0)
+         + rng.integers(-12, 13, size=(height, width)))
+    y = np.clip(y, 0, 255).astype(np.uint8)
+    c = y[::2, ::2]
+    return [y, np.ascontiguousarray(255 - c), np.ascontiguousarray((c // 2 + 64).astype(np.uint8))]
+
+
+HBM_LEVELS = 4
+BLOCK = dict(xbsep=8, ybsep=8, xblen=12, yblen=12, prec=2)
+
+
+def block_counts(width, height):
+    return (4 * ((width + 4 * BLOCK["xbsep"] - 1) // (4 * BLOCK["xbsep"])),
+            4 * ((height + 4 * BLOCK["ybsep"] - 1) // (4 * BLOCK["ybsep"])))
+
+
 class Stages:
     """Device-resident stages of one step.  Each stage launches on the current stream."""
 
@@ -125,6 +166,7 @@ class Stages:
         self.spec, self.torch, self.dev = spec, torch, dev
         self.stages = []
         B = spec["batch"]
+        W, H = spec["width"], spec["height"]
         rng = np.random.default_rng(2026)
         # ---- stage 1: inverse wavelet (BASELINE config 2/3) ----
         lay = dev.FrameLayout.yuv420(spec["depth_name"], spec["iwt_w"], spec["iwt_h"])
@@ -138,6 +180,7 @@ class Stages:
             self.coef.buf[p * lay.pitch:(p + 1) * lay.pitch].copy_(one)
         self.ws = dev.Workspace()
         ncoef = sum(w * h for w, h in lay.comp_sizes)
+        self.working_set = self.coef.nbytes + self.recon.nbytes
         self.stages.append(dict(
             name="iwt_inverse", frames=B, alg_bytes=2.0 * ncoef * lay.bpp * B,
             run=lambda: dev.iwt_inverse(self.coef, self.recon, spec["filter"],
@@ -147,10 +190,63 @@ class Stages:
                 name="iwt_forward", frames=B, alg_bytes=2.0 * ncoef * lay.bpp * B,
                 run=lambda: dev.iwt_forward(self.recon, self.coef, spec["filter"],
                                             spec["transform_depth"], self.ws)))
-        extra = getattr(dev, "bench_stages", None)
-        if extra and spec.get("full_core", True):
-            self.stages.extend(extra(spec, rng))
-        self.working_set = self.coef.nbytes + self.recon.nbytes
+        if not spec.get("full_core", True):
+            return
+        # ---- stage 2: OBMC render, residual = the wavelet output, 2 upsampled references ----
+        npix = W * H * 3 // 2
+        ref_lay = dev.FrameLayout.yuv420("u8", W, H, 32, True)
+        self.refs = [dev.PictureSlab(ref_lay, B) for _ in range(2)]
+        self.newref = dev.PictureSlab(ref_lay, B)          # the decoded picture = next reference
+        base = textured_frame(W, H, rng)
+        for r, slab in enumerate(self.refs):
+            fr = textured_frame(W, H, rng, pan=(5 * r, 3 * r))
+            for c in range(3):
+                slab.upload(0, c, fr[c])
+            one = slab.buf[:ref_lay.pitch]
+            for p in range(1, B):
+                slab.buf[p * ref_lay.pitch:(p + 1) * ref_lay.pitch].copy_(one)
+            dev.mc_edgeextend(slab)
+            dev.upsample(slab)
+        nbx, nby = block_counts(W, H)
+        self.nblocks = nbx * nby
+        mv = make_mv_field(nbx, nby, rng)
+        self.mvs = torch.from_numpy(np.tile(mv.view(np.uint8), B)).cuda()
+        self.obmc_params = dev.ObmcParams(BLOCK["xbsep"], BLOCK["ybsep"], BLOCK["xblen"], BLOCK["yblen"],
+                                          nbx, nby, BLOCK["prec"], 1, 1, 1, 1, 1)
+        self.resid = dev.SlabView(self.recon, [(W, H), (W // 2, H // 2), (W // 2, H // 2)])
+        bpp = lay.bpp
+        self.stages.append(dict(
+            name="obmc_render", frames=B,
+            alg_bytes=(npix * (2 * 4 + bpp + 1) + self.nblocks * 20.0) * B,
+            run=lambda: dev.obmc_render(self.obmc_params, self.mvs, self.refs[0], self.refs[1],
+                                        self.resid, 1, out=self.newref)))
+        # ---- stage 3: the decoded picture becomes a reference: edge-extend + half-pel upsample
+        self.stages.append(dict(
+            name="upsample", frames=B, alg_bytes=4.0 * npix * B,
+            run=lambda: (dev.mc_edgeextend(self.newref), dev.upsample(self.newref))))
+        # ---- stage 4: motion estimation: pyramids + hierarchical block matching vs ref 0 ----
+        self.src_pyr = dev.Pyramid(W, H, B, HBM_LEVELS, 8)
+        self.ref_pyr = dev.Pyramid(W, H, B, HBM_LEVELS, 8)
+        srcf = textured_frame(W, H, rng, pan=(5, 3))
+        for pyr, fr in ((self.src_pyr, srcf), (self.ref_pyr, base)):
+            for c in range(3):
+                pyr.slabs[0].upload(0, c, fr[c])
+            l0 = pyr.slabs[0]
+            one = l0.buf[:l0.layout.pitch]
+            for p in range(1, B):
+                l0.buf[p * l0.layout.pitch:(p + 1) * l0.layout.pitch].copy_(one)
+        self.hbm_params = dev.HbmParams(BLOCK["xbsep"], BLOCK["ybsep"], nbx, nby, 0, 0, 1, 1)
+        self.fields = [torch.empty(B * self.nblocks * 20, dtype=torch.uint8, device="cuda")
+                       for _ in range(HBM_LEVELS + 1)]
+        pyr_bytes = npix * (1 + 0.25 + 1 / 16 + 1 / 64) + npix * (0.25 + 1 / 16 + 1 / 64 + 1 / 256)
+        self.stages.append(dict(
+            name="pyramid", frames=B, alg_bytes=2 * pyr_bytes * B,
+            run=lambda: (self.src_pyr.build(), self.ref_pyr.build())))
+        self.stages.append(dict(
+            name="hier_block_match", frames=B,
+            alg_bytes=(2 * npix * 1.332 + self.nblocks * 20 * 1.34) * B,
+            run=lambda: dev.hbm_scan(self.hbm_params, self.src_pyr, self.ref_pyr, 3, self.fields, self.ws)))
+        self.working_set += sum(s.nbytes for s in self.refs) + self.newref.nbytes
 
     def step(self):
         for s in self.stages:
@@ -174,37 +270,141 @@ def collect_profile(lib):
 
 
 class HostFrames:
-    """Pinned host frames + the drop-in C API (schro_* symbols) for the e2e measurement."""
+    """The e2e arm: the same step through the drop-in C API (schro_* symbols of
+    libschro_b200.so) on pinned HOST frames, the way a decoder/encoder would drive it:
+    per picture the coefficient frame and the source picture go H2D, the decoded picture and
+    the motion fields come back D2H; reference pictures stay in the CUDA memory domain
+    (as with the reference's own use_cuda path, schrodecoder.c:1731-1736)."""
 
     def __init__(self, spec, lib, nthreads):
         from schroedinger_b200 import compat
         self.compat, self.lib, self.spec = compat, lib, spec
         self.nthreads = nthreads
+        self.full = spec.get("full_core", True)
         B = spec["batch"]
-        self.domain = compat.pinned_domain()
-        fmt = compat.FORMAT_S32_420 if spec["depth_name"] == "s32" else compat.FORMAT_S16_420
+        W, H = spec["width"], spec["height"]
+        self.pinned = compat.pinned_domain()
+        self.cuda = compat.cuda_domain()
+        s32 = spec["depth_name"] == "s32"
+        cfmt = compat.FORMAT_S32_420 if s32 else compat.FORMAT_S16_420
         rng = np.random.default_rng(7)
         planes = make_coeff_frame(spec, rng)
-        self.frames = []
+        A = compat.frame_new_and_alloc
+        self.coef_host = []
         for _ in range(B):
-            f = compat.frame_new_and_alloc(self.domain, fmt, spec["iwt_w"], spec["iwt_h"])
+            f = A(self.pinned, cfmt, spec["iwt_w"], spec["iwt_h"])
             for c in range(3):
                 compat.frame_plane(f, c)[...] = planes[c]
-            self.frames.append(f)
-        self.params = compat.make_params(spec["width"], spec["height"], spec["filter"],
-                                         spec["transform_depth"], spec["iwt_w"], spec["iwt_h"])
-        bpp = 4 if spec["depth_name"] == "s32" else 2
-        self.bytes_per_frame = int(spec["iwt_w"] * spec["iwt_h"] * 1.5 * bpp)
-        self.extra = getattr(compat, "bench_host_stages", None)
+            self.coef_host.append(f)
+        self.params = compat.make_params(W, H, spec["filter"], spec["transform_depth"], spec["iwt_w"],
+                                         spec["iwt_h"], num_refs=2, **{k: BLOCK[k] for k in ("xbsep", "ybsep", "xblen", "yblen")},
+                                         mv_precision=BLOCK["prec"])
+        bpp = 4 if s32 else 2
+        self.h2d = int(spec["iwt_w"] * spec["iwt_h"] * 1.5 * bpp)
+        self.d2h = self.h2d
+        if not self.full:
+            return
+        npix = W * H * 3 // 2
+        nb = self.params.x_num_blocks * self.params.y_num_blocks
+        self.h2d = int(spec["iwt_w"] * spec["iwt_h"] * 1.5 * bpp) + npix + nb * 20
+        self.d2h = npix + nb * 20 * (HBM_LEVELS + 1)
+        # reference pictures and the reference pyramid live on the device
+        self.refs = []
+        for r in range(2):
+            fr = textured_frame(W, H, rng, pan=(5 * r, 3 * r))
+            hf = A(None, compat.FORMAT_U8_420, W, H, 32, 1)
+            for c in range(3):
+                compat.frame_plane(hf, c)[...] = fr[c]
+            lib.schro_frame_mc_edgeextend(hf)
+            lib.schro_upsampled_frame_upsample(hf)
+            df = A(self.cuda, compat.FORMAT_U8_420, W, H, 32, 1)
+            lib.schro_frame_to_gpu(df, hf)
+            lib.schro_frame_unref(hf)
+            self.refs.append(df)
+        self.ref_pyr = self._pyramid_frames()
+        basef = textured_frame(W, H, rng)
+        hf = A(None, compat.FORMAT_U8_420, W, H, 32, 0)
+        for c in range(3):
+            compat.frame_plane(hf, c)[...] = basef[c]
+        lib.schro_frame_to_gpu(self.ref_pyr[0], hf)
+        lib.schro_frame_unref(hf)
+        self._build_pyramid(self.ref_pyr)
+        srcf = textured_frame(W, H, rng, pan=(5, 3))
+        self.src_host, self.out_host = [], []
+        for _ in range(B):
+            f = A(self.pinned, compat.FORMAT_U8_420, W, H, 0, 0)
+            for c in range(3):
+                compat.frame_plane(f, c)[...] = srcf[c]
+            self.src_host.append(f)
+            self.out_host.append(A(self.pinned, compat.FORMAT_U8_420, W, H, 0, 0))
+        mv = make_mv_field(self.params.x_num_blocks, self.params.y_num_blocks, rng)
+        # per-thread device frames
+        self.th = []
+        for _ in range(nthreads):
+            t = {}
+            t["coef"] = A(self.cuda, cfmt, spec["iwt_w"], spec["iwt_h"])
+            # the picture-size window of the coefficient frame (same memory)
+            view = compat.SchroFrame()
+            ctypes.memmove(ctypes.byref(view), t["coef"], ctypes.sizeof(view))
+            view.refcount, view.height = 1, H
+            for c in range(3):
+                view.components[c].height = H if c == 0 else H // 2
+            view.regions[0], view.domain = t["coef"].contents.regions[0], None
+            t["resid"] = view
+            t["acc"] = A(self.cuda, compat.FORMAT_S16_420, W, H)
+            t["out"] = A(self.cuda, compat.FORMAT_U8_420, W, H, 32, 1)
+            t["motion"] = lib.schro_motion_new(ctypes.byref(self.params), self.refs[0], self.refs[1])
+            ctypes.memmove(t["motion"].contents.motion_vectors, mv.ctypes.data, mv.nbytes)
+            t["src_pyr"] = self._pyramid_frames()
+            self.th.append(t)
+
+    def _pyramid_frames(self):
+        A, compat, W, H = self.compat.frame_new_and_alloc, self.compat, self.spec["width"], self.spec["height"]
+        frames = [A(self.cuda, compat.FORMAT_U8_420, W, H, 32, 0)]
+        w, h = W, H
+        for _ in range(HBM_LEVELS):
+            w, h = (w + 1) // 2, (h + 1) // 2
+            frames.append(A(self.cuda, compat.FORMAT_U8_420, w, h, 8, 0))
+        return frames
+
+    def _build_pyramid(self, frames):
+        lib = self.lib
+        lib.schro_frame_mc_edgeextend(frames[0])
+        for l in range(HBM_LEVELS):
+            lib.schro_frame_downsample(frames[l + 1], frames[l])
+            lib.schro_frame_mc_edgeextend(frames[l + 1])
+
+    def picture(self, t, i):
+        lib, th = self.lib, self.th[t] if self.full else None
+        if not self.full:
+            lib.schro_frame_inverse_iwt_transform(self.coef_host[i], ctypes.byref(self.params))
+            return
+        # decode side: coefficients in, decoded picture out
+        lib.schro_frame_to_gpu(th["coef"], self.coef_host[i])
+        lib.schro_frame_inverse_iwt_transform(th["coef"], ctypes.byref(self.params))
+        lib.schro_motion_render(th["motion"], th["acc"], ctypes.byref(th["resid"]), 1, th["out"])
+        lib.schro_frame_mc_edgeextend(th["out"])
+        th["out"].contents.upsample_done = 0
+        lib.schro_upsampled_frame_upsample(th["out"])
+        lib.schro_gpuframe_to_cpu(self.out_host[i], th["out"])
+        # encode side: source picture in, motion fields out
+        lib.schro_frame_to_gpu(th["src_pyr"][0], self.src_host[i])
+        self._build_pyramid(th["src_pyr"])
+        arr = self.compat.FrameP * (HBM_LEVELS + 1)
+        hbm = lib.schro_hbm_new_from_frames(ctypes.byref(self.params), 0, HBM_LEVELS, 0,
+                                            arr(*th["src_pyr"]), arr(*self.ref_pyr))
+        lib.schro_hbm_scan(hbm)
+        lib.schro_hierarchical_bm_scan_hint(hbm, 0, 3)
+        lib.schro_hbm_unref(hbm)
 
     def step(self):
-        """One e2e step: every picture of the batch through the drop-in API, pictures spread
-        over host threads (the reference's own threading model, one stream per thread)."""
-        lib, frames, params = self.lib, self.frames, self.params
+        """One e2e step: every picture of the batch, pictures spread over host threads (the
+        reference's own threading model); each thread owns a stream."""
+        n = len(self.coef_host)
 
         def work(tid):
-            for i in range(tid, len(frames), self.nthreads):
-                lib.schro_frame_inverse_iwt_transform(frames[i], ctypes.byref(params))
+            for i in range(tid, n, self.nthreads):
+                self.picture(tid, i)
 
         ts = [threading.Thread(target=work, args=(t,)) for t in range(self.nthreads)]
         for t in ts:
@@ -283,9 +483,12 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": B * args.steps * world / dt, "unit": "frames/s",
-               "h2d_bytes_per_step": hf.bytes_per_frame * B, "d2h_bytes_per_step": hf.bytes_per_frame * B,
-               "api": "schro_frame_inverse_iwt_transform on pinned host SchroFrames, "
-                      f"{nthreads} host threads/GPU, one stream each"}
+               "h2d_bytes_per_step": hf.h2d * B, "d2h_bytes_per_step": hf.d2h * B,
+               "api": "drop-in schro_* C API (schro_frame_to_gpu, schro_frame_inverse_iwt_transform, "
+                      "schro_motion_render, schro_frame_mc_edgeextend, schro_upsampled_frame_upsample, "
+                      "schro_frame_downsample, schro_hbm_scan, schro_hierarchical_bm_scan_hint, "
+                      f"schro_gpuframe_to_cpu) on pinned host SchroFrames, {nthreads} host threads/GPU, "
+                      "one stream each"}
     except Exception as ex:  # keep the device-resident number even if the host arm breaks
         e2e = {"value": None, "unit": "frames/s", "error": repr(ex)}
     clocks = sampler.stop() if rank == 0 else None
@@ -345,48 +548,120 @@ def load_cpu_lib():
     return ctypes.CDLL(port, mode=ctypes.RTLD_LOCAL), "port", "oracle"
 
 
-def cpu_pass(lib, prefix, spec, frames, nthreads):
-    """All stages of the step on `len(frames)` pictures, picture-parallel over host threads."""
-    is32 = 1 if spec["depth_name"] == "s32" else 0
-    fn = getattr(lib, f"{prefix}_iwt_inv")
-    fn.restype = None
+class CpuWorkload:
+    """The same step on the host: the reference's own C (oracle/_ref, kind "reference") or,
+    where that is not available, the oracle port.  One picture = inverse wavelet + OBMC render
+    + edge-extend/upsample of the decoded picture + pyramids + hierarchical block matching."""
 
-    def work(tid):
-        for i in range(tid, len(frames), nthreads):
-            for p in frames[i]:
-                fn(p.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(p.strides[0]), p.shape[1],
-                   p.shape[0], is32, spec["filter"], spec["transform_depth"])
-        extra = globals().get("cpu_extra_stages")
-        if extra:
-            extra(lib, prefix, spec, tid, nthreads, len(frames))
+    def __init__(self, spec, nthreads):
+        from tests import helpers as H
+        self.H, self.spec, self.nthreads = H, spec, nthreads
+        self.lib, self.kind, self.prefix = load_cpu_lib()
+        self.full = spec.get("full_core", True)
+        rng = np.random.default_rng(11)
+        self.base = make_coeff_frame(spec, rng)
+        self.coef = [[p.copy() for p in self.base] for _ in range(nthreads)]
+        if not self.full:
+            return
+        W, Hh = spec["width"], spec["height"]
+        self.W, self.Hh = W, Hh
+        self.nbx, self.nby = block_counts(W, Hh)
+        self.mvs = make_mv_field(self.nbx, self.nby, rng)
+        self.refs = []
+        for r in range(2):
+            fr = textured_frame(W, Hh, rng, pan=(5 * r, 3 * r))
+            planes = []
+            for c in range(3):
+                pl = H.HostPlane(fr[c].shape[1], fr[c].shape[0], ext=32, upsampled=True)
+                pl.set_image(fr[c])
+                H.cpu_edgeextend(self.lib, self.prefix, pl)
+                H.cpu_upsample(self.lib, self.prefix, pl)
+                planes.append(pl)
+            self.refs.append(planes)
+        self.src = textured_frame(W, Hh, rng, pan=(5, 3))
+        self.refpic = textured_frame(W, Hh, rng)
+        self.newref = [[H.HostPlane(p.w, p.h, ext=32, upsampled=True) for p in self.refs[0]]
+                       for _ in range(nthreads)]
+        self.acc = [[np.zeros((p.h, p.w), np.int16) for p in self.refs[0]] for _ in range(nthreads)]
+        # the reference initialises static tables lazily and not thread-safely
+        # (schromotion8.c:13-18): touch them once before the threads start
+        self.frame(0)
 
-    ts = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
-    t0 = time.perf_counter()
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join()
-    return time.perf_counter() - t0
+    def frame(self, t):
+        """All stages for one picture on thread slot t."""
+        lib, prefix, spec, H = self.lib, self.prefix, self.spec, self.H
+        is32 = 1 if spec["depth_name"] == "s32" else 0
+        fn = getattr(lib, f"{prefix}_iwt_inv")
+        fn.restype = None
+        for p in self.coef[t]:
+            fn(p.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(p.strides[0]), p.shape[1], p.shape[0],
+               is32, spec["filter"], spec["transform_depth"])
+        if not self.full:
+            return
+        P, I = ctypes.c_void_p * 3, ctypes.c_int * 3
+        resid, outp, sizes = self.coef[t], self.newref[t], [(p.w, p.h) for p in self.refs[0]]
+        if self.kind == "reference":
+            mp = H.RefMotionParams(self.W, self.Hh, 2, BLOCK["xbsep"], BLOCK["ybsep"], BLOCK["xblen"],
+                                   BLOCK["yblen"], self.nbx, self.nby, BLOCK["prec"], 1, 1, 1, 2)
+            f = lib.ref_motion_render
+            f.restype = None
+            f(ctypes.byref(mp), self.mvs.ctypes.data_as(ctypes.c_void_p),
+              P(*[p.ptr for p in self.refs[0]]), I(*[p.stride for p in self.refs[0]]),
+              P(*[p.ptr for p in self.refs[1]]), I(*[p.stride for p in self.refs[1]]),
+              P(*[a.ctypes.data for a in self.acc[t]]), I(*[a.strides[0] for a in self.acc[t]]),
+              P(*[a.ctypes.data for a in resid]), I(*[a.strides[0] for a in resid]), is32, 1,
+              P(*[p.ptr for p in outp]), I(*[p.stride for p in outp]), 0)
+        else:
+            f = lib.oracle_obmc_render
+            f.restype = None
+            for k, (w, h) in enumerate(sizes):
+                hs = 1 if k else 0
+                prm = H.OracleObmcParams(BLOCK["xbsep"] >> hs, BLOCK["ybsep"] >> hs, BLOCK["xblen"] >> hs,
+                                         BLOCK["yblen"] >> hs, self.nbx, self.nby, BLOCK["prec"], 1, 1, 1,
+                                         hs, hs, k)
+                f(ctypes.byref(prm), self.mvs.ctypes.data_as(ctypes.c_void_p), self.refs[0][k].ptr,
+                  self.refs[1][k].ptr, self.refs[0][k].stride, w, h,
+                  self.acc[t][k].ctypes.data_as(ctypes.c_void_p), self.acc[t][k].strides[0],
+                  resid[k].ctypes.data_as(ctypes.c_void_p), resid[k].strides[0], is32, 1, outp[k].ptr,
+                  outp[k].stride)
+        for pl in outp:
+            H.cpu_edgeextend(lib, prefix, pl)
+            H.cpu_upsample(lib, prefix, pl)
+        if self.kind == "reference":
+            H.ref_hbm(lib, self.src, self.refpic, self.W, self.Hh, BLOCK["xbsep"], BLOCK["ybsep"],
+                      HBM_LEVELS, 0, 0, 3)
+        else:
+            H.oracle_hbm(lib, self.src, self.refpic, self.W, self.Hh, BLOCK["xbsep"], BLOCK["ybsep"],
+                         HBM_LEVELS, 0, 0, 3)
+
+    def one_pass(self):
+        """nthreads pictures, one per host thread (the reference's picture-parallel model)."""
+        ts = [threading.Thread(target=self.frame, args=(t,)) for t in range(self.nthreads)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
 
 
 def cpu_baseline(spec, seconds=10.0, steps=None, warmup=1):
-    lib, kind, prefix = load_cpu_lib()
     cores = os.cpu_count() or 1
     nthreads = cores
-    rng = np.random.default_rng(11)
-    nframes = max(nthreads, 1)
-    base = make_coeff_frame(spec, rng)
-    frames = [[p.copy() for p in base] for _ in range(nframes)]
+    wl = CpuWorkload(spec, nthreads)
     for _ in range(warmup):
-        cpu_pass(lib, prefix, spec, frames, nthreads)
+        wl.one_pass()
     total, n = 0.0, 0
     while (steps is None and total < seconds and n < 50) or (steps is not None and n < steps):
-        total += cpu_pass(lib, prefix, spec, frames, nthreads)
+        total += wl.one_pass()
         n += 1
-    fps = nframes * n / total
-    return {"value": round(fps, 3), "unit": "frames/s", "cores": nthreads, "kind": kind,
-            "sample": f"{n} passes x {nframes} pictures of the same workload, picture-parallel on "
-                      f"{nthreads} host threads ({'unmodified reference C, -O3 -DDISABLE_ORC' if kind == 'reference' else 'oracle port'})",
+    fps = nthreads * n / total
+    what = ("unmodified reference C (gcc -O3 -DDISABLE_ORC: the plain-C Orc kernels, not liborc's SIMD JIT; "
+            "the five runtime-JIT OBMC kernels run through a C interpreter shim)"
+            if wl.kind == "reference" else "oracle port")
+    return {"value": round(fps, 3), "unit": "frames/s", "cores": nthreads, "kind": wl.kind,
+            "sample": f"{n} passes x {nthreads} pictures of the same workload "
+                      f"({'all stages' if wl.full else 'wavelet only'}), picture-parallel on {nthreads} host threads; {what}",
             "seconds": round(total, 2)}
 
 
@@ -397,7 +672,7 @@ def run_reference(args):
         return
     spec = workload_spec(args.workload)
     t0 = time.perf_counter()
-    cb = cpu_baseline(spec, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    cb = cpu_baseline(spec, steps=max(1, args.steps), warmup=1 if args.warmup > 0 else 0)
     out = {
         "impl": "reference",
         "metric": "frames/s at 2160p 4:2:0 (wavelet+OBMC+SAD); HBM GB/s as % of B200 peak",

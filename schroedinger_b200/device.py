@@ -113,6 +113,23 @@ class PictureSlab:
         return self.plane(pic, comp, phase, with_border).cpu().numpy().copy()
 
 
+class SlabView:
+    """The same device memory as another slab seen with different component sizes (e.g. the
+    picture-size window of an iwt-size coefficient frame)."""
+
+    def __init__(self, parent, comp_sizes):
+        import copy
+        self.layout = copy.copy(parent.layout)
+        self.layout.comp_sizes = [(int(w), int(h)) for (w, h) in comp_sizes]
+        self.count = parent.count
+        self.buf = parent.buf
+        self.slab = PictureSlab._make_slab(self)
+
+    plane = PictureSlab.plane
+    upload = PictureSlab.upload
+    download = PictureSlab.download
+
+
 def _as_typed(buf, start, h, w, stride, depth):
     bpp = _BPP[depth]
     assert start % bpp == 0 and stride % bpp == 0
