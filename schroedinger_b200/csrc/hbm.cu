@@ -104,13 +104,49 @@ hbm_init_field_kernel (MotionVector *field, size_t n, uint32_t flags0)
   }
 }
 
-__global__ void __launch_bounds__ (128)
+// acquire / release on the per-row progress counters
+__device__ __forceinline__ int ld_acquire (const int *p)
+{
+  int v;
+  asm volatile ("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release (int *p, int v)
+{
+  asm volatile ("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// 8 (or 4) bytes starting at any address, assembled from aligned 32-bit words
+__device__ __forceinline__ uint2 load8_unaligned (const uint8_t *p)
+{
+  const size_t mis = (size_t) p & 3;
+  const unsigned *w = reinterpret_cast<const unsigned *> (p - mis);
+  const unsigned w0 = __ldg (w), w1 = __ldg (w + 1), w2 = mis ? __ldg (w + 2) : 0u;
+  const unsigned sh = (unsigned) mis * 8;
+  return make_uint2 (__funnelshift_r (w0, w1, sh), __funnelshift_r (w1, w2, sh));
+}
+__device__ __forceinline__ unsigned load4_unaligned (const uint8_t *p)
+{
+  const size_t mis = (size_t) p & 3;
+  const unsigned *w = reinterpret_cast<const unsigned *> (p - mis);
+  const unsigned w0 = __ldg (w), w1 = mis ? __ldg (w + 1) : 0u;
+  return __funnelshift_r (w0, w1, (unsigned) mis * 8);
+}
+
+struct BlockShared {
+  int xmin, ymin, scan_w, scan_h, seed_a, seed_b;
+  unsigned long long key[16];
+  unsigned luma[16], chroma[16];
+};
+
+// One CTA (NW warps) owns one block row of one (picture, reference) pair.
+template <int NW>
+__global__ void __launch_bounds__ (32 * NW)
 hbm_level_kernel (const HbmArgs A)
 {
-  const int lane = threadIdx.x & 31;
-  const int gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (gwarp >= A.rows * A.count) return;
-  const int row = gwarp / A.count, pic = gwarp % A.count;   // rows in launch order: row r before r+1
+  __shared__ BlockShared sh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x / A.count, pic = blockIdx.x % A.count;   // row r is launched before r+1
   const int skip = 1 << A.shift, s = A.shift;
   const int j = row * skip;
   const int ri = A.ref_index;
@@ -127,120 +163,191 @@ hbm_level_kernel (const HbmArgs A)
   MotionVector *mf = A.field + (size_t) pic * A.field_pitch;
   const MotionVector *pf = A.parent ? A.parent + (size_t) pic * A.field_pitch : nullptr;
   int *prog_me = A.progress + (size_t) pic * A.rows + row;
-  volatile int *prog_up = row > 0 ? A.progress + (size_t) pic * A.rows + row - 1 : nullptr;
+  const int *prog_up = row > 0 ? A.progress + (size_t) pic * A.rows + row - 1 : nullptr;
   const int hint_mask = ~((1 << (s + 1)) - 1);
   const int y0 = (j * A.bh) >> s;
+  const int e = A.ext;
+  // every alignment assumption of the byte-SIMD paths, checked once
+  const bool simd_ok = A.bw == 8 && A.bh == 8 && A.hs == 1 && A.vs == 1 &&
+      ((((size_t) sp[0] | (size_t) ss[0]) & 7) == 0) && ((((size_t) sp[1] | (size_t) sp[2] | (size_t) ss[1] | (size_t) ss[2]) & 3) == 0) &&
+      ((((size_t) rp[0] | (size_t) rp[1] | (size_t) rp[2] | (size_t) rs[0] | (size_t) rs[1] | (size_t) rs[2]) & 3) == 0);
 
   for (int bi = 0; bi < A.cols; bi++) {
     const int i = bi * skip;
     const int x0 = (i * A.bw) >> s;
+    const bool active = x0 < A.width && y0 < A.height;
+    const int bw0 = min (A.width - x0, A.bw), bh0 = min (A.height - y0, A.bh);
 
-    // ---- wait for the row above: blocks bi (up) and bi-1 (up-left) must be final
-    if (prog_up) {
-      if (lane == 0) {
-        const int need = bi + 1;
-        while (*prog_up < need) __nanosleep (40);
+    if (warp == 0) {
+      // ---- wait until the row above has published blocks bi (up) and bi-1 (up-left)
+      if (prog_up && active) {
+        if (lane == 0) while (ld_acquire (prog_up) < bi + 1) { }
+        __syncwarp ();
       }
-      __syncwarp ();
-      __threadfence ();
-    }
-
-    if (x0 < A.width && y0 < A.height) {
-      const int bw0 = min (A.width - x0, A.bw), bh0 = min (A.height - y0, A.bh);
-
-      // ---- candidates, one per lane 0..8 (schrohierbm.c:259-294) ------------------
-      // 0: zero   1..5: parents (0,0) (-1,0) (1,0) (0,-1) (0,1)   6: left 7: up 8: up-left
-      int cdx = 0, cdy = 0;
-      bool valid = false;
-      if (lane == 0) valid = true;
-      else if (lane <= 5) {
-        if (pf) {
-          const int ox = (lane == 2) ? -1 : (lane == 3) ? 1 : 0;
-          const int oy = (lane == 4) ? -1 : (lane == 5) ? 1 : 0;
-          const int ll = (i & hint_mask) + ox * skip * 2, kk = (j & hint_mask) + oy * skip * 2;
-          if (ll >= 0 && ll < A.nbx && kk >= 0 && kk < A.nby) {
-            const MotionVector *m = pf + (size_t) kk * A.nbx + ll;
-            cdx = m->v[ri]; cdy = m->v[2 + ri]; valid = true;
-          }
-        }
-      } else if (lane <= 8) {
-        const bool need_x = (lane == 6 || lane == 8), need_y = (lane == 7 || lane == 8);
-        if ((!need_x || i > 0) && (!need_y || j > 0)) {
-          const MotionVector *m = mf + (size_t) (j - (need_y ? skip : 0)) * A.nbx + (i - (need_x ? skip : 0));
-          // written by this warp (left) or published by the row above (acquired above)
-          cdx = ((volatile const int16_t *) m->v)[ri];
-          cdy = ((volatile const int16_t *) m->v)[2 + ri];
-          valid = true;
-        }
-      }
-      // de-duplicate keeping the LAST occurrence (schrohierbm.c:298-321)
-      bool dup = false;
-#pragma unroll
-      for (int k = 1; k < 9; k++) {
-        const int kdx = __shfl_sync (0xffffffffu, cdx, k), kdy = __shfl_sync (0xffffffffu, cdy, k);
-        const bool kv = __shfl_sync (0xffffffffu, (int) valid, k) != 0;
-        if (k > lane && kv && kdx == cdx && kdy == cdy) dup = true;
-      }
-      const unsigned cmask = __ballot_sync (0xffffffffu, valid && !dup && lane < 9);
-
-      // ---- rank candidates with the 3-component SAD (schrometric.c:332-375) --------
-      int best_k = -1;
-      unsigned best_metric = 0xffffffffu;
-      for (int k = 0; k < 9; k++) {
-        if (!((cmask >> k) & 1)) continue;
-        int dx = __shfl_sync (0xffffffffu, cdx, k) >> s;
-        int dy = __shfl_sync (0xffffffffu, cdy, k) >> s;
-        dx = clampi (dx + x0, -bw0, A.width) - x0;
-        dy = clampi (dy + y0, -bh0, A.height) - y0;
-        unsigned metric;
-        const int e = A.ext;
-        const bool ok = !(x0 < -e || y0 < -e || x0 + A.bw > A.width + e || y0 + A.bh > A.height + e) &&
-            !(x0 + dx < -e || y0 + dy < -e || x0 + dx + A.bw > A.width + e || y0 + dy + A.bh > A.height + e);
-        if (!ok) {
-          metric = (unsigned) INT_MAX;
-        } else {
-          unsigned part = 0;
-#pragma unroll
-          for (int c = 0; c < 3; c++) {
-            const int hs = c ? A.hs : 0, vs = c ? A.vs : 0;
-            const int sx = x0 >> hs, sy = y0 >> vs, rx = (x0 + dx) >> hs, ry = (y0 + dy) >> vs;
-            const int w = min (max (0, (c ? A.cw : A.width) - sx), A.bw >> hs);
-            const int h = min (max (0, (c ? A.ch : A.height) - sy), A.bh >> vs);
-            for (int p = lane; p < w * h; p += 32) {
-              const int yy = p / w, xx = p - yy * w;
-              part += (unsigned) abs ((int) __ldg (sp[c] + (ptrdiff_t) (sy + yy) * ss[c] + sx + xx)
-                  - (int) __ldg (rp[c] + (ptrdiff_t) (ry + yy) * rs[c] + rx + xx));
+      if (active) {
+        // ---- candidates, one per lane 0..8 (schrohierbm.c:259-294) ------------------
+        // 0: zero   1..5: parents (0,0) (-1,0) (1,0) (0,-1) (0,1)   6: left 7: up 8: up-left
+        int cdx = 0, cdy = 0;
+        bool valid = false;
+        if (lane == 0) valid = true;
+        else if (lane <= 5) {
+          if (pf) {
+            const int ox = (lane == 2) ? -1 : (lane == 3) ? 1 : 0;
+            const int oy = (lane == 4) ? -1 : (lane == 5) ? 1 : 0;
+            const int ll = (i & hint_mask) + ox * skip * 2, kk = (j & hint_mask) + oy * skip * 2;
+            if (ll >= 0 && ll < A.nbx && kk >= 0 && kk < A.nby) {
+              const MotionVector *m = pf + (size_t) kk * A.nbx + ll;
+              cdx = m->v[ri]; cdy = m->v[2 + ri]; valid = true;
             }
           }
-          metric = warp_sum (part);
+        } else if (lane <= 8) {
+          const bool need_x = (lane == 6 || lane == 8), need_y = (lane == 7 || lane == 8);
+          if ((!need_x || i > 0) && (!need_y || j > 0)) {
+            const MotionVector *m = mf + (size_t) (j - (need_y ? skip : 0)) * A.nbx + (i - (need_x ? skip : 0));
+            // written by this CTA (left) or published by the row above (acquired above)
+            cdx = ((volatile const int16_t *) m->v)[ri];
+            cdy = ((volatile const int16_t *) m->v)[2 + ri];
+            valid = true;
+          }
         }
-        // signed compare as the reference (int metric < int min_metric, starting at INT_MAX)
-        if ((int) metric < (int) (best_k < 0 ? (unsigned) INT_MAX : best_metric)) { best_metric = metric; best_k = k; }
+        // de-duplicate keeping the LAST occurrence (schrohierbm.c:298-321)
+        bool dup = false;
+#pragma unroll
+        for (int k = 1; k < 9; k++) {
+          const int kdx = __shfl_sync (0xffffffffu, cdx, k), kdy = __shfl_sync (0xffffffffu, cdy, k);
+          const bool kv = __shfl_sync (0xffffffffu, (int) valid, k) != 0;
+          if (k > lane && kv && kdx == cdx && kdy == cdy) dup = true;
+        }
+        const unsigned cmask = __ballot_sync (0xffffffffu, valid && !dup && lane < 9);
+
+        // ---- rank candidates with the 3-component SAD (schrometric.c:332-375) --------
+        int best_k;
+        const bool full = simd_ok && x0 + 8 <= A.width && y0 + 8 <= A.height &&
+            (x0 >> 1) + 4 <= A.cw && (y0 >> 1) + 4 <= A.ch;
+        if (full) {
+          // three lanes per candidate: luma rows 0-3, luma rows 4-7, both chroma blocks
+          const int k = lane / 3, part = lane - 3 * k;
+          int dx = __shfl_sync (0xffffffffu, cdx, min (k, 8)) >> s;
+          int dy = __shfl_sync (0xffffffffu, cdy, min (k, 8)) >> s;
+          dx = clampi (dx + x0, -bw0, A.width) - x0;
+          dy = clampi (dy + y0, -bh0, A.height) - y0;
+          const bool mine = k < 9 && ((cmask >> k) & 1);
+          const bool ok = !(x0 < -e || y0 < -e || x0 + 8 > A.width + e || y0 + 8 > A.height + e) &&
+              !(x0 + dx < -e || y0 + dy < -e || x0 + dx + 8 > A.width + e || y0 + dy + 8 > A.height + e);
+          unsigned part_sad = 0;
+          if (mine && ok) {
+            if (part < 2) {
+              const uint8_t *a = sp[0] + (ptrdiff_t) (y0 + 4 * part) * ss[0] + x0;
+              const uint8_t *b = rp[0] + (ptrdiff_t) (y0 + dy + 4 * part) * rs[0] + x0 + dx;
+#pragma unroll
+              for (int y = 0; y < 4; y++) {
+                const uint2 av = __ldg (reinterpret_cast<const uint2 *> (a + (ptrdiff_t) y * ss[0]));
+                const uint2 bv = load8_unaligned (b + (ptrdiff_t) y * rs[0]);
+                part_sad += __vsadu4 (av.x, bv.x) + __vsadu4 (av.y, bv.y);
+              }
+            } else {
+              const int sx = x0 >> 1, sy = y0 >> 1, rx = (x0 + dx) >> 1, ry = (y0 + dy) >> 1;
+#pragma unroll
+              for (int c = 1; c < 3; c++) {
+#pragma unroll
+                for (int y = 0; y < 4; y++) {
+                  const unsigned av = __ldg (reinterpret_cast<const unsigned *> (sp[c] + (ptrdiff_t) (sy + y) * ss[c] + sx));
+                  const unsigned bv = load4_unaligned (rp[c] + (ptrdiff_t) (ry + y) * rs[c] + rx);
+                  part_sad += __vsadu4 (av, bv);
+                }
+              }
+            }
+          }
+          unsigned metric = part_sad + __shfl_down_sync (0xffffffffu, part_sad, 1);
+          metric += __shfl_down_sync (0xffffffffu, part_sad, 2);
+          if (!ok) metric = (unsigned) INT_MAX;
+          // first strict minimum in candidate order == min over (metric, k); INT_MAX never wins
+          unsigned long long key = ~0ull;
+          if (mine && part == 0 && metric < (unsigned) INT_MAX) key = ((unsigned long long) metric << 8) | (unsigned) k;
+          key = warp_min64 (key);
+          best_k = key == ~0ull ? __ffs (cmask) - 1 : (int) (key & 0xff);
+        } else {
+          best_k = -1;
+          unsigned best_metric = (unsigned) INT_MAX;
+          for (int k = 0; k < 9; k++) {
+            if (!((cmask >> k) & 1)) continue;
+            int dx = __shfl_sync (0xffffffffu, cdx, k) >> s;
+            int dy = __shfl_sync (0xffffffffu, cdy, k) >> s;
+            dx = clampi (dx + x0, -bw0, A.width) - x0;
+            dy = clampi (dy + y0, -bh0, A.height) - y0;
+            unsigned metric;
+            const bool ok = !(x0 < -e || y0 < -e || x0 + A.bw > A.width + e || y0 + A.bh > A.height + e) &&
+                !(x0 + dx < -e || y0 + dy < -e || x0 + dx + A.bw > A.width + e || y0 + dy + A.bh > A.height + e);
+            if (!ok) {
+              metric = (unsigned) INT_MAX;
+            } else {
+              unsigned part = 0;
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                const int hs = c ? A.hs : 0, vs = c ? A.vs : 0;
+                const int sx = x0 >> hs, sy = y0 >> vs, rx = (x0 + dx) >> hs, ry = (y0 + dy) >> vs;
+                const int w = min (max (0, (c ? A.cw : A.width) - sx), A.bw >> hs);
+                const int h = min (max (0, (c ? A.ch : A.height) - sy), A.bh >> vs);
+                for (int p = lane; p < w * h; p += 32) {
+                  const int yy = p / w, xx = p - yy * w;
+                  part += (unsigned) abs ((int) __ldg (sp[c] + (ptrdiff_t) (sy + yy) * ss[c] + sx + xx)
+                      - (int) __ldg (rp[c] + (ptrdiff_t) (ry + yy) * rs[c] + rx + xx));
+                }
+              }
+              metric = warp_sum (part);
+            }
+            if ((int) metric < (int) best_metric) { best_metric = metric; best_k = k; }
+          }
+          if (best_k < 0) best_k = __ffs (cmask) - 1;    // every candidate invalid: the reference asserts
+        }
+
+        // ---- seed + scan window (schrohierbm.c:349-364, schrometric.c:174-214) --------
+        int dx = __shfl_sync (0xffffffffu, cdx, best_k) >> s;
+        int dy = __shfl_sync (0xffffffffu, cdy, best_k) >> s;
+        dx = max (-bw0 - x0, min (A.width - x0, dx));
+        dy = max (-bh0 - y0, min (A.height - y0, dy));
+        if (lane == 0) {
+          const int xmin = max (max (-bw0, x0 + dx - A.h_range), -e);
+          const int ymin = max (max (-bh0, y0 + dy - A.h_range), -e);
+          const int xmax = min (min (A.width, x0 + dx + A.h_range), A.width - bw0 + e);
+          const int ymax = min (min (A.height, y0 + dy + A.h_range), A.height - bh0 + e);
+          sh.xmin = xmin; sh.ymin = ymin;
+          sh.scan_w = xmax - xmin + 1; sh.scan_h = ymax - ymin + 1;
+          sh.seed_a = dx + x0 - xmin; sh.seed_b = dy + y0 - ymin;
+        }
       }
-      if (best_k < 0) best_k = __ffs (cmask) - 1;    // every candidate invalid: the reference asserts
+    }
+    if (NW > 1) __syncthreads (); else __syncwarp ();
 
-      // ---- seed + scan window (schrohierbm.c:349-364, schrometric.c:174-214) --------
-      int dx = __shfl_sync (0xffffffffu, cdx, best_k) >> s;
-      int dy = __shfl_sync (0xffffffffu, cdy, best_k) >> s;
-      dx = max (-bw0 - x0, min (A.width - x0, dx));
-      dy = max (-bh0 - y0, min (A.height - y0, dy));
-      const int xmin = max (max (-bw0, x0 + dx - A.h_range), -A.ext);
-      const int ymin = max (max (-bh0, y0 + dy - A.h_range), -A.ext);
-      const int xmax = min (min (A.width, x0 + dx + A.h_range), A.width - bw0 + A.ext);
-      const int ymax = min (min (A.height, y0 + dy + A.h_range), A.height - bh0 + A.ext);
-      const int scan_w = xmax - xmin + 1, scan_h = ymax - ymin + 1;
-      const int seed_a = dx + x0 - xmin, seed_b = dy + y0 - ymin;
-
-      // ---- full search: lanes over positions, a (x) fastest across lanes ------------
+    if (active) {
+      const int xmin = sh.xmin, ymin = sh.ymin, scan_w = sh.scan_w, scan_h = sh.scan_h;
+      const int seed_a = sh.seed_a, seed_b = sh.seed_b;
+      // ---- full search: threads over positions, a (x) fastest across lanes ------------
       // key = (metric, not-seed, a, b): seed wins ties, else first strict minimum in the
       // reference's a-outer / b-inner order (schrometric.c:121-171)
       unsigned long long best_key = ~0ull;
       unsigned best_l = 0, best_c = 0;
       const uint8_t *sblk = sp[0] + (ptrdiff_t) y0 * ss[0] + x0;
       const int npos = scan_w * scan_h;
-      for (int p = lane; p < npos; p += 32) {
+      const bool fast8 = simd_ok && bw0 == 8 && bh0 == 8;
+      uint2 srow[8];
+      if (fast8) {
+#pragma unroll
+        for (int y = 0; y < 8; y++) srow[y] = __ldg (reinterpret_cast<const uint2 *> (sblk + (ptrdiff_t) y * ss[0]));
+      }
+      for (int p = threadIdx.x; p < npos; p += 32 * NW) {
         const int b = p / scan_w, a = p - b * scan_w;
-        const unsigned l = block_sad (sblk, ss[0], rp[0] + (ptrdiff_t) (ymin + b) * rs[0] + xmin + a, rs[0], bw0, bh0);
+        const uint8_t *rblk = rp[0] + (ptrdiff_t) (ymin + b) * rs[0] + xmin + a;
+        unsigned l = 0;
+        if (fast8) {
+#pragma unroll
+          for (int y = 0; y < 8; y++) {
+            const uint2 bv = load8_unaligned (rblk + (ptrdiff_t) y * rs[0]);
+            l += __vsadu4 (srow[y].x, bv.x) + __vsadu4 (srow[y].y, bv.y);
+          }
+        } else {
+          l = block_sad (sblk, ss[0], rblk, rs[0], bw0, bh0);
+        }
         unsigned c = 0;
         if (A.use_chroma) {
           // chroma_metrics[a*scan_h+b] = sum_k SAD_k at (ref_x/2 + a/2, ref_y/2 + b/2)
@@ -260,23 +367,30 @@ hbm_level_kernel (const HbmArgs A)
       const int ol = __ffs (owner) - 1;
       best_l = __shfl_sync (0xffffffffu, best_l, ol);
       best_c = __shfl_sync (0xffffffffu, best_c, ol);
-      if (lane == 0) {
-        const int a = (int) ((wkey >> 12) & 0xfff), b = (int) (wkey & 0xfff);
+      if (NW > 1) {
+        if (lane == 0) { sh.key[warp] = wkey; sh.luma[warp] = best_l; sh.chroma[warp] = best_c; }
+        __syncthreads ();
+      }
+      if (threadIdx.x == 0) {
+        unsigned long long k = wkey;
+        unsigned bl = best_l, bc = best_c;
+        if (NW > 1) {
+#pragma unroll
+          for (int w = 1; w < NW; w++)
+            if (sh.key[w] < k) { k = sh.key[w]; bl = sh.luma[w]; bc = sh.chroma[w]; }
+        }
+        const int a = (int) ((k >> 12) & 0xfff), b = (int) (k & 0xfff);
         MotionVector *o = mf + (size_t) j * A.nbx + i;
-        o->metric = best_l;
-        o->chroma_metric = best_c;
+        o->metric = bl;
+        o->chroma_metric = bc;
         o->v[ri] = (int16_t) ((xmin + a - x0) << s);
         o->v[2 + ri] = (int16_t) ((ymin + b - y0) << s);
         o->flags = A.flags0;
       }
     }
-    // ---- publish
-    __syncwarp ();
-    if (lane == 0) {
-      __threadfence ();
-      atomicExch (prog_me, bi + 1);
-    }
-    __syncwarp ();
+    // ---- publish (release orders the vector store of thread 0 before the counter)
+    if (threadIdx.x == 0) st_release (prog_me, bi + 1);
+    if (NW > 1) __syncthreads (); else __syncwarp ();
   }
 }
 
@@ -437,12 +551,17 @@ sb2_hbm_scan_hint (const sb2_hbm_params *p, const sb2_slab *src_level, const sb2
   double bytes = 0;
   for (int c = 0; c < 3; c++) bytes += 2.0 * src_level->width[c] * src_level->height[c] * count;
   bytes += (double) A.rows * A.cols * 20 * (parent_field ? 2 : 1) * count;
-  const int warps = A.rows * count;
+  const int ctas = A.rows * count;
+  const int npos = (2 * h_range + 1) * (2 * h_range + 1);
   {
     char tag[48];
     snprintf (tag, sizeof (tag), "hbm_level_s%d_r%d", shift, h_range);
     LaunchScope scope (tag, bytes, st);
-    hbm_level_kernel<<<ceil_div (warps, 4), 128, 0, st>>> (A);
+    // warps per block row: enough threads to cover the scan positions in few rounds
+    if (npos <= 64) hbm_level_kernel<2><<<ctas, 64, 0, st>>> (A);
+    else if (npos <= 128) hbm_level_kernel<4><<<ctas, 128, 0, st>>> (A);
+    else if (npos <= 512) hbm_level_kernel<8><<<ctas, 256, 0, st>>> (A);
+    else hbm_level_kernel<16><<<ctas, 512, 0, st>>> (A);
   }
   return check_cuda (cudaGetLastError (), "hbm_level_kernel launch");
 }

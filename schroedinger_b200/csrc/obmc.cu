@@ -185,6 +185,207 @@ obmc_kernel (const ObmcArgs A)
   }
 }
 
+// ---- v2: block table in shared memory + unified 4-tap fetch -------------------------
+// Every sub-pel case of schroframe.c:2288-2413 is the same 4-tap sum
+//   (w00*s00 + w01*s01 + w10*s10 + w11*s11 + 8) >> 4,  weights summing to 16:
+// the copy case is w00 = 16, the two avgub cases are 8/8 ((8a+8b+8)>>4 == (a+b+1)>>1),
+// prec 0/1 are single taps.  So the per-block work (vector decode, clamp, phase
+// selection, weights) is done once per CTA into a table and every pixel issues up to
+// 2x2 blocks x 2 refs x 4 taps of independent loads before any arithmetic.
+struct BlkRef { int o[4]; unsigned w; };
+struct BlkEnt { BlkRef r[2]; short mode, fast, dc, pad; };
+constexpr int OT_W = 32, OT_H = 8;            // pixel tile
+constexpr int MAX_ENT = 128;
+
+__device__ __forceinline__ void make_blkref (BlkRef &br, int rstride, int prec, int bx, int by, int dx, int dy,
+    int max_fast_x, int max_fast_y)
+{
+  int px = (bx << prec) + dx, py = (by << prec) + dy;
+  const int e = 32 << prec;
+  px = clampi (px, -e, max_fast_x + e - 1);
+  py = clampi (py, -e, max_fast_y + e - 1);
+  const int q = rstride >> 2;
+  if (prec == 0) {
+    br.o[0] = br.o[1] = br.o[2] = br.o[3] = py * rstride + px;
+    br.w = 16u;
+    return;
+  }
+  int rx = 0, ry = 0, hx = px, hy = py;
+  if (prec >= 2) {
+    if (prec == 2) { px <<= 1; py <<= 1; }
+    hx = px >> 2; hy = py >> 2; rx = px & 3; ry = py & 3;
+  }
+  // half-pel sample (u,v): phase ((v&1)<<1)|(u&1) at (u>>1, v>>1)
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const int u = hx + (t & 1), v = hy + (t >> 1);
+    br.o[t] = (((v & 1) << 1) | (u & 1)) * q + (v >> 1) * rstride + (u >> 1);
+  }
+  const unsigned w00 = (4 - ry) * (4 - rx), w01 = (4 - ry) * rx, w10 = ry * (4 - rx), w11 = ry * rx;
+  br.w = w00 | (w01 << 8) | (w10 << 16) | (w11 << 24);
+}
+
+__device__ __forceinline__ int fetch4 (const uint8_t *ref, const BlkRef &br, int pix)
+{
+  // taps with zero weight are not loaded
+  const unsigned w = br.w;
+  int acc = 8;
+  acc += (int) (w & 0xff) * (int) __ldg (ref + br.o[0] + pix);
+  if (w & 0x0000ff00u) acc += (int) ((w >> 8) & 0xff) * (int) __ldg (ref + br.o[1] + pix);
+  if (w & 0x00ff0000u) acc += (int) ((w >> 16) & 0xff) * (int) __ldg (ref + br.o[2] + pix);
+  if (w & 0xff000000u) acc += (int) (w >> 24) * (int) __ldg (ref + br.o[3] + pix);
+  return acc >> 4;
+}
+
+__global__ void __launch_bounds__ (256)
+obmc_kernel_v2 (const ObmcArgs A)
+{
+  __shared__ BlkEnt tab[MAX_ENT];
+  // OBMC window and per-column / per-row covering-block ranges: per-lane indexed, so they
+  // must not live in the (uniform-access) constant bank of the kernel arguments
+  __shared__ unsigned char s_wx[64], s_wy[64];
+  __shared__ short s_i0[OT_W], s_i1[OT_W], s_j0[OT_H], s_j1[OT_H];
+  const int comp = blockIdx.z % A.ncomp, pic = blockIdx.z / A.ncomp;
+  const int width = A.w[comp], height = A.h[comp];
+  const int tx0 = blockIdx.x * OT_W, ty0 = blockIdx.y * OT_H;
+  if (tx0 >= width || ty0 >= height) return;
+
+  const int xbsep = A.xbsep[comp], ybsep = A.ybsep[comp], xblen = A.xblen[comp], yblen = A.yblen[comp];
+  const int xoff = (xblen - xbsep) >> 1, yoff = (yblen - ybsep) >> 1;
+  const int prec = A.prec;
+  const int max_fast_x = (width - xblen) << prec, max_fast_y = (height - yblen) << prec;
+  const int max_x_blocks = min (A.nbx - 1, (width - xoff) / xbsep);
+  const int max_y_blocks = min (A.nby - 1, (height - yoff) / ybsep);
+  const bool simple = (A.w1 == 1 && A.w2 == 1 && A.bits == 1);
+  const bool noscale = (A.w1 + A.w2 == (1 << A.bits));
+  const unsigned char *wx = s_wx, *wy = s_wy;
+  if (threadIdx.x < 64) {
+    s_wx[threadIdx.x] = A.wx[comp][threadIdx.x];
+    s_wy[threadIdx.x] = A.wy[comp][threadIdx.x];
+  } else if (threadIdx.x < 64 + OT_W) {
+    const int x = tx0 + (int) threadIdx.x - 64;
+    s_i0[threadIdx.x - 64] = (short) ((x + xoff - xblen + 1 > 0) ? (x + xoff - xblen + xbsep) / xbsep : 0);
+    s_i1[threadIdx.x - 64] = (short) min (A.nbx - 1, (x + xoff) / xbsep);
+  } else if (threadIdx.x < 64 + OT_W + OT_H) {
+    const int y = ty0 + (int) threadIdx.x - 64 - OT_W;
+    s_j0[threadIdx.x - 64 - OT_W] = (short) ((y + yoff - yblen + 1 > 0) ? (y + yoff - yblen + ybsep) / ybsep : 0);
+    s_j1[threadIdx.x - 64 - OT_W] = (short) min (A.nby - 1, (y + yoff) / ybsep);
+  }
+
+  const uint8_t *ref0 = reinterpret_cast<const uint8_t *> (plane_ptr (A.ref0, pic, comp));
+  const uint8_t *ref1 = A.has_ref1 ? reinterpret_cast<const uint8_t *> (plane_ptr (A.ref1, pic, comp)) : ref0;
+  const int rs0 = A.ref0.stride[comp], rs1 = A.has_ref1 ? A.ref1.stride[comp] : rs0;
+  const MotionVector *mvs = A.mvs + (size_t) pic * A.mv_pitch;
+
+  // blocks overlapping this tile
+  const int x1 = min (tx0 + OT_W, width) - 1, y1 = min (ty0 + OT_H, height) - 1;
+  const int ti0 = (tx0 + xoff - xblen + 1 > 0) ? (tx0 + xoff - xblen + xbsep) / xbsep : 0;
+  const int ti1 = min (A.nbx - 1, (x1 + xoff) / xbsep);
+  const int tj0 = (ty0 + yoff - yblen + 1 > 0) ? (ty0 + yoff - yblen + ybsep) / ybsep : 0;
+  const int tj1 = min (A.nby - 1, (y1 + yoff) / ybsep);
+  const int tni = ti1 - ti0 + 1, tnj = tj1 - tj0 + 1;
+
+  for (int t = threadIdx.x; t < tni * tnj; t += blockDim.x) {
+    const int jj = t / tni, ii = t - jj * tni;
+    const int i = ti0 + ii, j = tj0 + jj;
+    const MotionVector *mv = mvs + (size_t) j * A.nbx + i;
+    const unsigned flags = __ldg (&mv->flags);
+    const int v01 = __ldg (reinterpret_cast<const int *> (mv->v)), v23 = __ldg (reinterpret_cast<const int *> (mv->v) + 1);
+    const int v0 = (short) (v01 & 0xffff), v1 = v01 >> 16, v2 = (short) (v23 & 0xffff), v3 = v23 >> 16;
+    BlkEnt e;
+    e.mode = (short) (flags & 3);
+    e.fast = (short) (i >= 1 && i < max_x_blocks && j >= 1 && j < max_y_blocks);
+    e.dc = (short) (comp == 0 ? v0 : comp == 1 ? v1 : v2);
+    e.pad = 0;
+    const int bx = xbsep * i - xoff, by = ybsep * j - yoff;
+    make_blkref (e.r[0], rs0, prec, bx, by, v0 >> A.hs[comp], v2 >> A.vs[comp], max_fast_x, max_fast_y);
+    make_blkref (e.r[1], rs1, prec, bx, by, v1 >> A.hs[comp], v3 >> A.vs[comp], max_fast_x, max_fast_y);
+    tab[t] = e;
+  }
+  __syncthreads ();
+
+  const int x = tx0 + (threadIdx.x & 31), y = ty0 + (threadIdx.x >> 5);
+  if (x >= width || y >= height) return;
+
+  const int j0 = s_j0[threadIdx.x >> 5], j1 = s_j1[threadIdx.x >> 5];
+  const int i0 = s_i0[threadIdx.x & 31], i1 = s_i1[threadIdx.x & 31];
+
+  int sum = 0;
+  for (int j = j0; j <= j1; j++) {
+    const int b = y - (ybsep * j - yoff);
+    for (int i = i0; i <= i1; i++) {
+      const int a = x - (xbsep * i - xoff);
+      const BlkEnt &e = tab[(j - tj0) * tni + (i - ti0)];
+      const int mode = e.mode;
+      const bool fast = e.fast != 0;
+      int s0 = 0, s1 = 0;
+      if (mode & 1) s0 = fetch4 (ref0, e.r[0], b * rs0 + a);
+      if (mode & 2) s1 = fetch4 (ref1, e.r[1], b * rs1 + a);
+      int v;
+      if (mode == 0) {
+        const int dc = (int) e.dc + 128;
+        v = fast ? w16 (dc) : (dc & 0xff);
+      } else if (mode == 3) {
+        if (simple) {
+          v = (s0 + s1 + 1) >> 1;
+        } else if (fast) {
+          int t = w16 (s0 * w16 (A.w1 << (6 - A.bits)));
+          const int u = w16 (s1 * w16 (A.w2 << (6 - A.bits)));
+          t = w16 (t + u);
+          t = w16 (t + 32);
+          v = t >> 6;
+        } else {
+          int t = w16 (s0 * w16 (A.w1));
+          const int u = w16 (s1 * w16 (A.w2));
+          t = w16 (t + u);
+          t = w16 (t + ((1 << A.bits) >> 1));
+          v = clampi (t >> A.bits, 0, 255);
+        }
+      } else {
+        const int s = (mode == 1) ? s0 : s1;
+        if (fast) {
+          if (simple) v = s;
+          else {
+            int t = w16 (s * w16 ((A.w1 + A.w2) << (6 - A.bits)));
+            t = w16 (t + 32);
+            v = t >> 6;
+          }
+        } else {
+          if (noscale) v = s;
+          else v = ((s * (A.w1 + A.w2) + (1 << (A.bits - 1))) >> A.bits) & 0xff;
+        }
+      }
+      int w_x = wx[a], w_y = wy[b];
+      if (!fast) {
+        if (x < xoff) w_x += wx[2 * xoff - a - 1];
+        if (x >= A.nbx * xbsep - xoff) w_x += wx[2 * (xblen - xoff) - a - 1];
+        if (y < yoff) w_y += wy[2 * yoff - b - 1];
+        if (y >= A.nby * ybsep - yoff) w_y += wy[2 * (yblen - yoff) - b - 1];
+      }
+      sum += v * w_x * w_y;
+    }
+  }
+
+  const int a16 = w16 (sum);
+  if (A.add) {
+    const char *rrow = plane_ptr (A.res, pic, comp) + (size_t) y * A.res.stride[comp];
+    const int r = A.res_is_s32 ? w16 (reinterpret_cast<const int *> (rrow)[x])
+                               : (int) reinterpret_cast<const short *> (rrow)[x];
+    int t = w16 (a16 + 32) >> 6;
+    t = w16 (r + t);
+    reinterpret_cast<uint8_t *> (plane_ptr (A.out, pic, comp))[(size_t) y * A.out.stride[comp] + x] =
+        (uint8_t) clampi (t, 0, 255);
+    if (A.has_acc)
+      reinterpret_cast<short *> (plane_ptr (A.acc, pic, comp) + (size_t) y * A.acc.stride[comp])[x] = (short) a16;
+  } else {
+    short *r = reinterpret_cast<short *> (plane_ptr (A.res, pic, comp) + (size_t) y * A.res.stride[comp]) + x;
+    const int t = w16 (a16 - 8160) >> 6;
+    *r = (short) w16 (*r - t);
+    if (A.has_acc)
+      reinterpret_cast<short *> (plane_ptr (A.acc, pic, comp) + (size_t) y * A.acc.stride[comp])[x] = (short) t;
+  }
+}
+
 // schroedinger/schromotion.c:40-79
 static int get_ramp (int x, int offset)
 {
@@ -277,7 +478,14 @@ sb2_obmc_render (const sb2_obmc_params *p, const void *motion_vectors, size_t mv
   dim3 grid (ceil_div (maxw, 32), ceil_div (maxh, 8), ncomp * count);
   {
     LaunchScope scope (add ? "obmc_render_add" : "obmc_render_sub", bytes, as_stream (stream));
-    obmc_kernel<<<grid, 256, 0, as_stream (stream)>>> (A);
+    // the table kernel needs every tile's block list to fit its shared-memory table
+    bool table_ok = true;
+    for (int c = 0; c < ncomp; c++) {
+      const int ni = (OT_W + A.xblen[c]) / A.xbsep[c] + 2, nj = (OT_H + A.yblen[c]) / A.ybsep[c] + 2;
+      if (ni * nj > MAX_ENT) table_ok = false;
+    }
+    if (table_ok) obmc_kernel_v2<<<grid, 256, 0, as_stream (stream)>>> (A);
+    else obmc_kernel<<<grid, 256, 0, as_stream (stream)>>> (A);
   }
   return check_cuda (cudaGetLastError (), "obmc_kernel launch");
 }

@@ -351,6 +351,204 @@ wavelet_level_kernel (const LevelArgs a)
   }
 }
 
+// ---- fast path: register-chunk lifting ----------------------------------------
+// The generic kernel above pays ~6 warp instructions per sample, almost all of them
+// shared-memory traffic of the step-by-step lifting.  The fast inverse kernel keeps every
+// lifting step in registers: a thread owns a chunk of C polyphase pairs (+HP halo pairs
+// each side), applies all steps of the filter to its private arrays E[] / O[] with
+// compile-time indices, and only the finished pairs are written out.  Vertical chunks are
+// loaded straight from global memory (lanes = consecutive columns, coalesced), their
+// results go to shared memory once; horizontal chunks are read from there (lanes =
+// consecutive rows, odd pitch => conflict-free), lifted, interleaved in place and copied
+// out with coalesced stores.  Picture edges re-extend (replicate) the arrays after every
+// step, exactly like the reference's extend_* helpers (schrowaveletorc.c:192-269).
+
+template <typename T, int F, bool INV, int S, int N>
+__device__ __forceinline__ void chunk_step (int (&E)[N], int (&O)[N])
+{
+  constexpr Step st = step_of (F, S);
+  constexpr int NT = kind_taps (st.kind);
+  constexpr int sign = INV ? -st.sign : st.sign;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    int v[NT];
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      const int idx = (k + st.tap0 + t) < 0 ? 0 : ((k + st.tap0 + t) > N - 1 ? N - 1 : (k + st.tap0 + t));
+      v[t] = st.target ? E[idx] : O[idx];
+    }
+    const int term = lift_term<T, st.kind> (v, st.p1, st.p2, st.p3);
+    if (st.target) O[k] = sign > 0 ? Ar<T>::add (O[k], term) : Ar<T>::sub (O[k], term);
+    else E[k] = sign > 0 ? Ar<T>::add (E[k], term) : Ar<T>::sub (E[k], term);
+  }
+}
+
+template <int N, int HP>
+__device__ __forceinline__ void chunk_extend (int (&X)[N], bool lo, bool hi)
+{
+  if (HP > 0) {
+    if (lo) {
+#pragma unroll
+      for (int h = 0; h < HP; h++) X[h] = X[HP];
+    }
+    if (hi) {
+#pragma unroll
+      for (int h = 0; h < HP; h++) X[N - 1 - h] = X[N - 1 - HP];
+    }
+  }
+}
+
+template <typename T, int F, bool INV, int N, int HP, int S>
+struct ChunkSeq {
+  static __device__ __forceinline__ void run (int (&E)[N], int (&O)[N], bool lo, bool hi)
+  {
+    constexpr int NS = num_steps (F);
+    constexpr int s = INV ? NS - 1 - S : S;
+    chunk_step<T, F, INV, s, N> (E, O);
+    if (step_of (F, s).target) chunk_extend<N, HP> (O, lo, hi);
+    else chunk_extend<N, HP> (E, lo, hi);
+    if constexpr (S + 1 < NS) ChunkSeq<T, F, INV, N, HP, S + 1>::run (E, O, lo, hi);
+  }
+};
+
+template <typename T, int F, bool INV, int N, int HP>
+__device__ __forceinline__ void chunk_lift (int (&E)[N], int (&O)[N], bool lo, bool hi)
+{
+  chunk_extend<N, HP> (E, lo, hi);
+  chunk_extend<N, HP> (O, lo, hi);
+  ChunkSeq<T, F, INV, N, HP, 0>::run (E, O, lo, hi);
+}
+
+template <typename T, int F> struct FastGeom {
+  static constexpr int VEC = 16 / (int) sizeof (T);
+  static constexpr int HP = filter_halo (F);
+  static constexpr int HK = ((HP + VEC - 1) / VEC) * VEC;
+  static constexpr int C = 16;                 // vertical chunk (polyphase rows)
+  static constexpr int CH = 16;                // horizontal chunk (polyphase columns)
+  static constexpr int NKV = TWH + 2 * HK;     // columns per segment held in shared memory
+  static constexpr int NV = C + 2 * HP;
+  static constexpr int NH = CH + 2 * HP;
+  // pitch in elements: an odd number of 32-bit words, so that lanes = rows hit distinct banks
+  static constexpr int PITCH = (sizeof (T) == 4) ? (2 * NKV + 1) : (2 * NKV + 2);
+  static constexpr int VITEMS = 2 * NKV * (THH / C);
+  static constexpr int HITEMS = 2 * THH * (TWH / CH);
+  static constexpr int NT = ((VITEMS > HITEMS ? VITEMS : HITEMS) + 31) / 32 * 32;
+  static constexpr size_t SMEM = (size_t) 2 * THH * PITCH * sizeof (T);
+  static_assert (sizeof (T) == 4 || ((2 * NKV + 2) / 2) % 2 == 1, "s16 pitch must be an odd number of words");
+};
+
+template <typename T, int F>
+__global__ void __launch_bounds__ (FastGeom<T, F>::NT)
+wavelet_inv_fast_kernel (const LevelArgs a)
+{
+  typedef FastGeom<T, F> G;
+  extern __shared__ __align__ (16) unsigned char smem_raw[];
+  T *sm = reinterpret_cast<T *> (smem_raw);
+
+  const int comp = blockIdx.z % a.ncomp, pic = blockIdx.z / a.ncomp;
+  const int w = a.w[comp], h = a.h[comp];
+  const int n = w >> 1, m = h >> 1;
+  const int kx0 = blockIdx.x * TWH, ky0 = blockIdx.y * THH;
+  if (kx0 >= n || ky0 >= m) return;
+  constexpr int SH = filter_shift (F);
+
+  T *dense = reinterpret_cast<T *> (plane_ptr (a.dense, pic, comp));
+  const T *bands = reinterpret_cast<const T *> (plane_ptr (a.bands, pic, comp));
+  const T *ll = reinterpret_cast<const T *> (plane_ptr (a.ll, pic, comp));
+  const size_t ds = a.dense.stride[comp] / sizeof (T);
+  const size_t bs = a.bands.stride[comp] / sizeof (T);
+  const size_t ls = a.ll.stride[comp] / sizeof (T);
+  const int tid = threadIdx.x;
+
+  // ---- vertical: one thread = one column of one segment x one chunk of C row pairs ----
+  if (tid < G::VITEMS) {
+    const int chunk = tid / (2 * G::NKV), col = tid - chunk * (2 * G::NKV);
+    const int seg = col >= G::NKV, cseg = col - seg * G::NKV;
+    const int kx = kx0 - G::HK + cseg;
+    const int kyc = ky0 + chunk * G::C;                 // first pair row of this chunk
+    if (kx >= 0 && kx < n && kyc < m) {
+      int E[G::NV], O[G::NV];
+      const T *pe = seg ? bands + n + kx : ll + kx;      // even rows: LL (seg 0) or HL (seg 1)
+      const size_t es = seg ? 2 * bs : ls;
+      const T *po = bands + bs + seg * n + kx;           // odd rows: LH / HH
+#pragma unroll
+      for (int r = 0; r < G::NV; r++) {
+        const int ky = kyc - G::HP + r;
+        const bool ok = ky >= 0 && ky < m;
+        E[r] = ok ? (int) pe[(size_t) ky * es] : 0;
+        O[r] = ok ? (int) po[(size_t) ky * 2 * bs] : 0;
+      }
+      chunk_lift<T, F, true, G::NV, G::HP> (E, O, kyc == 0, kyc + G::C >= m);
+      T *out = sm + (size_t) (chunk * 2 * G::C) * G::PITCH + col;
+#pragma unroll
+      for (int r = 0; r < G::C; r++) {
+        out[(size_t) (2 * r) * G::PITCH] = (T) E[G::HP + r];
+        out[(size_t) (2 * r + 1) * G::PITCH] = (T) O[G::HP + r];
+      }
+    }
+  }
+  __syncthreads ();
+
+  // ---- horizontal: one thread = one row x one chunk of CH column pairs; lanes = rows ----
+  const int hw = tid >> 5, lane = tid & 31;
+  const int q = hw % (TWH / G::CH);                      // chunk within the tile
+  const int row = (hw / (TWH / G::CH)) * 32 + lane;      // tile row
+  const int k0 = kx0 + q * G::CH;
+  const bool hact = tid < G::HITEMS && k0 < n && (2 * ky0 + row) < h;
+  int E[G::NH], O[G::NH];
+  if (hact) {
+    const T *rowp = sm + (size_t) row * G::PITCH + G::HK + q * G::CH - G::HP;
+#pragma unroll
+    for (int i = 0; i < G::NH; i++) {
+      E[i] = rowp[i];
+      O[i] = rowp[G::NKV + i];
+    }
+    chunk_lift<T, F, true, G::NH, G::HP> (E, O, k0 == 0, k0 + G::CH >= n);
+  }
+  __syncthreads ();
+  if (hact) {
+    // interleave + (x+1)>>1 in place: output column x of the tile at row*PITCH + x
+    T *orow = sm + (size_t) row * G::PITCH + 2 * q * G::CH;
+#pragma unroll
+    for (int i = 0; i < G::CH; i++) {
+      int e = E[G::HP + i], o = O[G::HP + i];
+      if (SH) { e = Ar<T>::add (e, 1) >> 1; o = Ar<T>::add (o, 1) >> 1; }
+      orow[2 * i] = (T) e;
+      orow[2 * i + 1] = (T) o;
+    }
+  }
+  __syncthreads ();
+
+  // ---- coalesced copy-out, 32 bits per lane ----
+  {
+    const int tw = min (2 * TWH, w - 2 * kx0);           // output columns of this tile
+    const int th = min (2 * THH, h - 2 * ky0);
+    constexpr int EPW = 4 / (int) sizeof (T);            // elements per 32-bit word
+    const int wpr = tw / EPW;                            // words per row (tw is a multiple of 32)
+    const int nwarps = G::NT / 32;
+    for (int r = hw; r < th; r += nwarps) {
+      const unsigned *src = reinterpret_cast<const unsigned *> (sm + (size_t) r * G::PITCH);
+      unsigned *dst = reinterpret_cast<unsigned *> (dense + (size_t) (2 * ky0 + r) * ds + 2 * kx0);
+      for (int x = lane; x < wpr; x += 32) dst[x] = src[x];
+    }
+  }
+}
+
+template <typename T, int F>
+static bool fast_inverse_ok (const LevelArgs &a)
+{
+  typedef FastGeom<T, F> G;
+  if (G::HP > 4) return false;                          // Fidelity: register arrays too large
+  for (int c = 0; c < a.ncomp; c++) {
+    const int n = a.w[c] >> 1, m = a.h[c] >> 1;
+    if (n % G::CH || m % G::C) return false;
+    // 32-bit copy-out: rows of the dense plane must be 4-byte aligned
+    if ((a.dense.stride[c] % 4) || (a.dense.off[c] % 4)) return false;
+  }
+  if (((size_t) a.dense.base % 4) || (a.dense.pic_pitch % 4)) return false;
+  return true;
+}
+
 // ---- host side ---------------------------------------------------------------
 
 template <typename T, int F, bool INV>
@@ -380,6 +578,19 @@ static int launch_level (const LevelArgs &a, int count, cudaStream_t stream)
       for (int c = 0; c < a.ncomp; c++) bytes += 2.0 * a.w[c] * a.h[c] * sizeof (T) * count;
     }
     LaunchScope scope (tag, bytes, stream);
+    if constexpr (INV) {
+      if (fast_inverse_ok<T, F> (a)) {
+        typedef FastGeom<T, F> FG;
+        static bool fast_attr = false;
+        if (!fast_attr) {
+          cudaFuncSetAttribute (wavelet_inv_fast_kernel<T, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+              (int) FG::SMEM);
+          fast_attr = true;
+        }
+        wavelet_inv_fast_kernel<T, F><<<grid, FG::NT, FG::SMEM, stream>>> (a);
+        return check_cuda (cudaGetLastError (), "wavelet_inv_fast_kernel launch");
+      }
+    }
     wavelet_level_kernel<T, F, INV><<<grid, NTHREADS, G::SMEM, stream>>> (a);
   }
   return check_cuda (cudaGetLastError (), "wavelet_level_kernel launch");

@@ -97,7 +97,8 @@ static void *
 cuda_alloc (int size)
 {
   void *p = NULL;
-  SB2H_CUDA (cudaMalloc (&p, (size_t) size));
+  /* 256 spare bytes: the byte-SIMD SAD kernels read whole aligned words */
+  SB2H_CUDA (cudaMalloc (&p, (size_t) size + 256));
   return p;
 }
 

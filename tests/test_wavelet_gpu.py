@@ -105,3 +105,20 @@ def test_batch_of_pictures_and_round_trip(cuda):
             want = helpers.cpu_wavelet(ORACLE, "oracle", "fwd", planes[p, k].copy(), 0, 3)
             assert np.array_equal(b.download(p, k), want)
             assert np.array_equal(c.download(p, k), planes[p, k])
+
+
+@pytest.mark.parametrize("dtype", [np.int16, np.int32])
+@pytest.mark.parametrize("filt", range(7))
+def test_fast_path_shapes(cuda, filt, dtype):
+    """Sizes whose half-width / half-height are multiples of 16 take the register-chunk
+    kernels: cover single-chunk planes (both edges in one chunk), partial tiles, several
+    tiles in both directions, and full-range values that wrap."""
+    rng = np.random.default_rng(300 + filt)
+    amp_full = 32767 if dtype == np.int16 else 2 ** 31 - 1
+    for (h, w) in ((32, 32), (32, 64), (64, 32), (96, 160), (128, 288), (192, 416), (544, 960)):
+        for amp in (255, amp_full):
+            a = rng.integers(-amp, amp + 1, size=(h, w)).astype(dtype)
+            for d in ("inv", "fwd"):
+                want = helpers.cpu_wavelet(ORACLE, "oracle", d, a.copy(), filt)
+                got = gpu_iwt(d, [a], filt, 1)[0]
+                assert np.array_equal(got, want), (filt, dtype, (h, w), amp, d)
