@@ -112,10 +112,19 @@ int sb2_mc_edgeextend (const sb2_slab *frames, int extension, int phase, void *s
  * stride[] is the 4-phase row stride; phase p starts (stride>>2)*p bytes into each row. */
 int sb2_upsample (const sb2_slab *frames, int extension, void *stream);
 
+/* sb2_mc_edgeextend (phase 0) + sb2_upsample in one launch: what the decoder does to every
+ * reconstructed reference picture (schroedinger/schrodecoder.c:2068-2087, 2120-2141). */
+int sb2_edgeextend_upsample (const sb2_slab *frames, int extension, void *stream);
+
 /* dst = half-resolution src, (6,26,26,6) twice with an 8-bit intermediate:
  * schro_frame_downsample (schroedinger/schroframe.c:1505-1513).  dst sizes must be
  * (w+1)/2 x (h+1)/2 per component. */
 int sb2_downsample (const sb2_slab *src, const sb2_slab *dst, void *stream);
+
+/* sb2_downsample followed by sb2_mc_edgeextend (dst, dst_extension) in one launch: one level
+ * of schro_encoder_frame_downsample (schroedinger/schroanalysis.c:17-27). */
+int sb2_downsample_edgeextend (const sb2_slab *src, const sb2_slab *dst, int dst_extension,
+    void *stream);
 
 /* One-direction half-pel filter of a bare plane, no borders:
  * schro_frame_upsample_horiz / schro_frame_upsample_vert (schroedinger/schroframe.c:1557, 1612) */

@@ -23,6 +23,7 @@ struct FrameArgs {
   int h[SB2_MAX_COMPONENTS];
   int ncomp;
   int ext;
+  int fuse_edge;                // upsample: also write the phase-0 border (edge extension)
 };
 
 __device__ __forceinline__ int clampi (int x, int lo, int hi) { return min (max (x, lo), hi); }
@@ -125,6 +126,7 @@ upsample_kernel (const FrameArgs a)
     else if (x < 0 || x >= w - 1) v3 = v2;
     else v3 = taps8 (&sv[ty][tx], 1);
     uint8_t *o = p0 + (ptrdiff_t) y * stride + x;
+    if (a.fuse_edge && (x < 0 || x >= w || y < 0 || y >= h)) o[0] = s0[ty + 3][tx + 3];
     o[q] = (uint8_t) v1;
     o[2 * q] = (uint8_t) v2;
     o[3 * q] = (uint8_t) v3;
@@ -137,6 +139,7 @@ struct DownArgs {
   int sw[SB2_MAX_COMPONENTS], sh[SB2_MAX_COMPONENTS];
   int dw[SB2_MAX_COMPONENTS], dh[SB2_MAX_COMPONENTS];
   int ncomp;
+  int dst_ext;                  // > 0: also replicate the result into dst's border
 };
 
 constexpr int DT_W = 32, DT_H = 8;                 // output tile
@@ -173,8 +176,18 @@ downsample_kernel (const DownArgs a)
     const int x = x0 + tx, y = y0 + ty;
     if (x >= dw || y >= dh) continue;
     const uint8_t *t = &sm[ty][2 * tx];
-    d[(ptrdiff_t) y * dstr + x] =
-        (uint8_t) clamp255 ((6 * ((int) t[0] + t[3]) + 26 * ((int) t[1] + t[2]) + 32) >> 6);
+    const uint8_t v = (uint8_t) clamp255 ((6 * ((int) t[0] + t[3]) + 26 * ((int) t[1] + t[2]) + 32) >> 6);
+    d[(ptrdiff_t) y * dstr + x] = v;
+    if (a.dst_ext > 0 && (x == 0 || x == dw - 1 || y == 0 || y == dh - 1)) {
+      // schro_frame_mc_edgeextend of the result: the thread owning an edge pixel writes its
+      // replicas (rows / columns outside the plane, corners included)
+      const int e = a.dst_ext;
+      const int qx0 = x == 0 ? -e : 0, qx1 = x == dw - 1 ? e : 0;
+      const int qy0 = y == 0 ? -e : 0, qy1 = y == dh - 1 ? e : 0;
+      for (int qy = qy0; qy <= qy1; qy++)
+        for (int qx = qx0; qx <= qx1; qx++)
+          if (qx || qy) d[(ptrdiff_t) (y + qy) * dstr + x + qx] = v;
+    }
   }
 }
 
@@ -225,6 +238,7 @@ static FrameArgs frame_args (const sb2_slab *s, int ext)
   a.planes = planeset_from_slab (s);
   a.ncomp = s->ncomp;
   a.ext = ext;
+  a.fuse_edge = 0;
   for (int c = 0; c < SB2_MAX_COMPONENTS; c++) {
     a.w[c] = c < s->ncomp ? s->width[c] : 0;
     a.h[c] = c < s->ncomp ? s->height[c] : 0;
@@ -260,8 +274,22 @@ sb2_mc_edgeextend (const sb2_slab *frames, int extension, int phase, void *strea
   return check_cuda (cudaGetLastError (), "edgeextend_kernel launch");
 }
 
+static int upsample_impl (const sb2_slab *frames, int extension, int fuse_edge, void *stream);
+
 extern "C" int
 sb2_upsample (const sb2_slab *frames, int extension, void *stream)
+{
+  return upsample_impl (frames, extension, 0, stream);
+}
+
+extern "C" int
+sb2_edgeextend_upsample (const sb2_slab *frames, int extension, void *stream)
+{
+  return upsample_impl (frames, extension, 1, stream);
+}
+
+static int
+upsample_impl (const sb2_slab *frames, int extension, int fuse_edge, void *stream)
 {
   int rc = check_frame_slab (frames, "sb2_upsample");
   if (rc) return rc;
@@ -269,6 +297,7 @@ sb2_upsample (const sb2_slab *frames, int extension, void *stream)
     if (frames->stride[c] % 4)
       return set_error (SB2_ERR_ARG, "sb2_upsample: stride %d of component %d is not 4-phase", frames->stride[c], c);
   FrameArgs a = frame_args (frames, extension);
+  a.fuse_edge = fuse_edge;
   int maxw = 0, maxh = 0;
   double bytes = 0;
   for (int c = 0; c < frames->ncomp; c++) {
@@ -286,8 +315,22 @@ sb2_upsample (const sb2_slab *frames, int extension, void *stream)
   return check_cuda (cudaGetLastError (), "upsample_kernel launch");
 }
 
+static int downsample_impl (const sb2_slab *src, const sb2_slab *dst, int dst_ext, void *stream);
+
 extern "C" int
 sb2_downsample (const sb2_slab *src, const sb2_slab *dst, void *stream)
+{
+  return downsample_impl (src, dst, 0, stream);
+}
+
+extern "C" int
+sb2_downsample_edgeextend (const sb2_slab *src, const sb2_slab *dst, int dst_extension, void *stream)
+{
+  return downsample_impl (src, dst, dst_extension, stream);
+}
+
+static int
+downsample_impl (const sb2_slab *src, const sb2_slab *dst, int dst_ext, void *stream)
 {
   int rc = check_frame_slab (src, "sb2_downsample(src)");
   if (rc) return rc;
@@ -299,6 +342,7 @@ sb2_downsample (const sb2_slab *src, const sb2_slab *dst, void *stream)
   a.src = planeset_from_slab (src);
   a.dst = planeset_from_slab (dst);
   a.ncomp = src->ncomp;
+  a.dst_ext = dst_ext;
   int maxw = 0, maxh = 0;
   double bytes = 0;
   for (int c = 0; c < SB2_MAX_COMPONENTS; c++) {

@@ -195,7 +195,7 @@ obmc_kernel (const ObmcArgs A)
 struct BlkRef { int o[4]; unsigned w; };
 struct BlkEnt { BlkRef r[2]; short mode, fast, dc, pad; };
 constexpr int OT_W = 32, OT_H = 8;            // pixel tile
-constexpr int MAX_ENT = 128;
+constexpr int MAX_ENT = 256;
 
 __device__ __forceinline__ void make_blkref (BlkRef &br, int rstride, int prec, int bx, int by, int dx, int dy,
     int max_fast_x, int max_fast_y)
@@ -386,6 +386,198 @@ obmc_kernel_v2 (const ObmcArgs A)
   }
 }
 
+// ---- v3: four horizontally adjacent pixels per thread ------------------------------
+// Same block table as v2; a thread owns pixels x..x+3 of one row and loops over the UNION
+// of the blocks covering them (2x2 for xblen <= 2*xbsep), with a zero window weight where a
+// pixel lies outside a block.  Table reads, mode logic and loop control are paid once per
+// four pixels, residual loads and output stores are 128 / 32 bits wide.
+constexpr int O3_W = 128, O3_H = 8;
+
+template <bool SIMPLE>
+__device__ __forceinline__ int obmc_combine (const ObmcArgs &A, int mode, bool fast, bool noscale, int dc, int s0, int s1)
+{
+  if (SIMPLE) {
+    const int avg = (s0 + s1 + 1) >> 1;
+    const int one = (mode == 1) ? s0 : s1;
+    const int dcv = fast ? w16 (dc + 128) : ((dc + 128) & 0xff);
+    return mode == 0 ? dcv : (mode == 3 ? avg : one);
+  }
+  if (mode == 0) return fast ? w16 (dc + 128) : ((dc + 128) & 0xff);
+  if (mode == 3) {
+    if (fast) {
+      int t = w16 (s0 * w16 (A.w1 << (6 - A.bits)));
+      const int u = w16 (s1 * w16 (A.w2 << (6 - A.bits)));
+      t = w16 (t + u);
+      t = w16 (t + 32);
+      return t >> 6;
+    }
+    int t = w16 (s0 * w16 (A.w1));
+    const int u = w16 (s1 * w16 (A.w2));
+    t = w16 (t + u);
+    t = w16 (t + ((1 << A.bits) >> 1));
+    return clampi (t >> A.bits, 0, 255);
+  }
+  const int s = (mode == 1) ? s0 : s1;
+  if (fast) {
+    int t = w16 (s * w16 ((A.w1 + A.w2) << (6 - A.bits)));
+    t = w16 (t + 32);
+    return t >> 6;
+  }
+  if (noscale) return s;
+  return ((s * (A.w1 + A.w2) + (1 << (A.bits - 1))) >> A.bits) & 0xff;
+}
+
+template <bool SIMPLE>
+__global__ void __launch_bounds__ (256)
+obmc_kernel_v3 (const ObmcArgs A)
+{
+  __shared__ __align__ (16) BlkEnt tab[MAX_ENT];
+  __shared__ unsigned char s_wx[64], s_wy[64];
+  __shared__ short s_i0[O3_W], s_i1[O3_W], s_j0[O3_H], s_j1[O3_H];
+  const int comp = blockIdx.z % A.ncomp, pic = blockIdx.z / A.ncomp;
+  const int width = A.w[comp], height = A.h[comp];
+  const int tx0 = blockIdx.x * O3_W, ty0 = blockIdx.y * O3_H;
+  if (tx0 >= width || ty0 >= height) return;
+
+  const int xbsep = A.xbsep[comp], ybsep = A.ybsep[comp], xblen = A.xblen[comp], yblen = A.yblen[comp];
+  const int xoff = (xblen - xbsep) >> 1, yoff = (yblen - ybsep) >> 1;
+  const int prec = A.prec;
+  const int max_fast_x = (width - xblen) << prec, max_fast_y = (height - yblen) << prec;
+  const int max_x_blocks = min (A.nbx - 1, (width - xoff) / xbsep);
+  const int max_y_blocks = min (A.nby - 1, (height - yoff) / ybsep);
+  const bool noscale = (A.w1 + A.w2 == (1 << A.bits));
+
+  if (threadIdx.x < 64) {
+    s_wx[threadIdx.x] = A.wx[comp][threadIdx.x];
+    s_wy[threadIdx.x] = A.wy[comp][threadIdx.x];
+  }
+  if (threadIdx.x < O3_W) {
+    const int x = min (tx0 + (int) threadIdx.x, width - 1);
+    s_i0[threadIdx.x] = (short) ((x + xoff - xblen + 1 > 0) ? (x + xoff - xblen + xbsep) / xbsep : 0);
+    s_i1[threadIdx.x] = (short) min (A.nbx - 1, (x + xoff) / xbsep);
+  } else if (threadIdx.x < O3_W + O3_H) {
+    const int y = min (ty0 + (int) threadIdx.x - O3_W, height - 1);
+    s_j0[threadIdx.x - O3_W] = (short) ((y + yoff - yblen + 1 > 0) ? (y + yoff - yblen + ybsep) / ybsep : 0);
+    s_j1[threadIdx.x - O3_W] = (short) min (A.nby - 1, (y + yoff) / ybsep);
+  }
+
+  const uint8_t *ref0 = reinterpret_cast<const uint8_t *> (plane_ptr (A.ref0, pic, comp));
+  const uint8_t *ref1 = A.has_ref1 ? reinterpret_cast<const uint8_t *> (plane_ptr (A.ref1, pic, comp)) : ref0;
+  const int rs0 = A.ref0.stride[comp], rs1 = A.has_ref1 ? A.ref1.stride[comp] : rs0;
+  const MotionVector *mvs = A.mvs + (size_t) pic * A.mv_pitch;
+
+  const int x1 = min (tx0 + O3_W, width) - 1, y1 = min (ty0 + O3_H, height) - 1;
+  const int ti0 = (tx0 + xoff - xblen + 1 > 0) ? (tx0 + xoff - xblen + xbsep) / xbsep : 0;
+  const int ti1 = min (A.nbx - 1, (x1 + xoff) / xbsep);
+  const int tj0 = (ty0 + yoff - yblen + 1 > 0) ? (ty0 + yoff - yblen + ybsep) / ybsep : 0;
+  const int tj1 = min (A.nby - 1, (y1 + yoff) / ybsep);
+  const int tni = ti1 - ti0 + 1, tnj = tj1 - tj0 + 1;
+
+  for (int t = threadIdx.x; t < tni * tnj; t += blockDim.x) {
+    const int jj = t / tni, ii = t - jj * tni;
+    const int i = ti0 + ii, j = tj0 + jj;
+    const MotionVector *mv = mvs + (size_t) j * A.nbx + i;
+    const unsigned flags = __ldg (&mv->flags);
+    const int v01 = __ldg (reinterpret_cast<const int *> (mv->v)), v23 = __ldg (reinterpret_cast<const int *> (mv->v) + 1);
+    const int v0 = (short) (v01 & 0xffff), v1 = v01 >> 16, v2 = (short) (v23 & 0xffff), v3 = v23 >> 16;
+    BlkEnt e;
+    e.mode = (short) (flags & 3);
+    e.fast = (short) (i >= 1 && i < max_x_blocks && j >= 1 && j < max_y_blocks);
+    e.dc = (short) (comp == 0 ? v0 : comp == 1 ? v1 : v2);
+    e.pad = 0;
+    const int bx = xbsep * i - xoff, by = ybsep * j - yoff;
+    make_blkref (e.r[0], rs0, prec, bx, by, v0 >> A.hs[comp], v2 >> A.vs[comp], max_fast_x, max_fast_y);
+    make_blkref (e.r[1], rs1, prec, bx, by, v1 >> A.hs[comp], v3 >> A.vs[comp], max_fast_x, max_fast_y);
+    tab[t] = e;
+  }
+  __syncthreads ();
+
+  const int lx = (threadIdx.x & 31) * 4;
+  const int x = tx0 + lx, y = ty0 + (threadIdx.x >> 5);
+  if (x >= width || y >= height) return;
+  const int npx = min (4, width - x);
+
+  const int j0 = s_j0[threadIdx.x >> 5], j1 = s_j1[threadIdx.x >> 5];
+  const int i0 = s_i0[lx], i1 = s_i1[lx + 3];
+
+  int sum[4] = { 0, 0, 0, 0 };
+  for (int j = j0; j <= j1; j++) {
+    const int b = y - (ybsep * j - yoff);
+    int wy_plain = s_wy[b], wy_fold = wy_plain;
+    if (y < yoff) wy_fold += s_wy[2 * yoff - b - 1];
+    if (y >= A.nby * ybsep - yoff) wy_fold += s_wy[2 * (yblen - yoff) - b - 1];
+    for (int i = i0; i <= i1; i++) {
+      const BlkEnt &e = tab[(j - tj0) * tni + (i - ti0)];
+      const int mode = e.mode;
+      const bool fast = e.fast != 0;
+      const int dc = e.dc;
+      const int bx = xbsep * i - xoff;
+      const int w_y = fast ? wy_plain : wy_fold;
+      const BlkRef r0 = e.r[0], r1 = e.r[1];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int a = x + k - bx;
+        const bool in = a >= 0 && a < xblen && k < npx;
+        const int ac = min (max (a, 0), xblen - 1);
+        int w_x = s_wx[ac];
+        if (!fast) {
+          if (x + k < xoff) w_x += s_wx[max (2 * xoff - ac - 1, 0)];
+          if (x + k >= A.nbx * xbsep - xoff) w_x += s_wx[min (max (2 * (xblen - xoff) - ac - 1, 0), 63)];
+        }
+        int s0 = 0, s1 = 0;
+        if (in && (mode & 1)) s0 = fetch4 (ref0, r0, b * rs0 + ac);
+        if (in && (mode & 2)) s1 = fetch4 (ref1, r1, b * rs1 + ac);
+        const int v = obmc_combine<SIMPLE> (A, mode, fast, noscale, dc, s0, s1);
+        sum[k] += in ? v * w_x * w_y : 0;
+      }
+    }
+  }
+
+  const size_t ro = (size_t) y * A.res.stride[comp];
+  if (A.add) {
+    int r[4];
+    const char *rrow = plane_ptr (A.res, pic, comp) + ro;
+    if (npx == 4) {
+      if (A.res_is_s32) {
+        const int4 q = *reinterpret_cast<const int4 *> (rrow + (size_t) x * 4);
+        r[0] = w16 (q.x); r[1] = w16 (q.y); r[2] = w16 (q.z); r[3] = w16 (q.w);
+      } else {
+        const int2 q = *reinterpret_cast<const int2 *> (rrow + (size_t) x * 2);
+        r[0] = (q.x << 16) >> 16; r[1] = q.x >> 16; r[2] = (q.y << 16) >> 16; r[3] = q.y >> 16;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        r[k] = k < npx ? (A.res_is_s32 ? w16 (reinterpret_cast<const int *> (rrow)[x + k])
+                                       : (int) reinterpret_cast<const short *> (rrow)[x + k]) : 0;
+    }
+    unsigned packed = 0;
+    int a16[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      a16[k] = w16 (sum[k]);
+      int t = w16 (a16[k] + 32) >> 6;
+      t = w16 (r[k] + t);
+      packed |= (unsigned) clampi (t, 0, 255) << (8 * k);
+    }
+    uint8_t *orow = reinterpret_cast<uint8_t *> (plane_ptr (A.out, pic, comp)) + (size_t) y * A.out.stride[comp] + x;
+    if (npx == 4) *reinterpret_cast<unsigned *> (orow) = packed;
+    else for (int k = 0; k < npx; k++) orow[k] = (uint8_t) (packed >> (8 * k));
+    if (A.has_acc) {
+      short *arow = reinterpret_cast<short *> (plane_ptr (A.acc, pic, comp) + (size_t) y * A.acc.stride[comp]) + x;
+      for (int k = 0; k < npx; k++) arow[k] = (short) a16[k];
+    }
+  } else {
+    short *rrow = reinterpret_cast<short *> (plane_ptr (A.res, pic, comp) + ro) + x;
+    short *arow = A.has_acc ? reinterpret_cast<short *> (plane_ptr (A.acc, pic, comp) + (size_t) y * A.acc.stride[comp]) + x : nullptr;
+    for (int k = 0; k < npx; k++) {
+      const int t = w16 (w16 (sum[k]) - 8160) >> 6;
+      rrow[k] = (short) w16 (rrow[k] - t);
+      if (arow) arow[k] = (short) t;
+    }
+  }
+}
+
 // schroedinger/schromotion.c:40-79
 static int get_ramp (int x, int offset)
 {
@@ -484,7 +676,22 @@ sb2_obmc_render (const sb2_obmc_params *p, const void *motion_vectors, size_t mv
       const int ni = (OT_W + A.xblen[c]) / A.xbsep[c] + 2, nj = (OT_H + A.yblen[c]) / A.ybsep[c] + 2;
       if (ni * nj > MAX_ENT) table_ok = false;
     }
-    if (table_ok) obmc_kernel_v2<<<grid, 256, 0, as_stream (stream)>>> (A);
+    // the 4-pixel kernel needs 4-byte aligned output rows and 16-byte aligned residual rows
+    bool v3_ok = table_ok;
+    for (int c = 0; c < ncomp && v3_ok; c++) {
+      const int ni = (O3_W + A.xblen[c]) / A.xbsep[c] + 2, nj = (O3_H + A.yblen[c]) / A.ybsep[c] + 2;
+      if (ni * nj > MAX_ENT) v3_ok = false;
+      if (out && ((out->stride[c] | out->offset[c]) & 3)) v3_ok = false;
+      if ((residual->stride[c] | residual->offset[c]) & 15) v3_ok = false;
+    }
+    if (out && (((size_t) out->base | out->picture_pitch) & 3)) v3_ok = false;
+    if (((size_t) residual->base | residual->picture_pitch) & 15) v3_ok = false;
+    const bool simple = (A.w1 == 1 && A.w2 == 1 && A.bits == 1);
+    if (v3_ok) {
+      dim3 g3 (ceil_div (maxw, O3_W), ceil_div (maxh, O3_H), ncomp * count);
+      if (simple) obmc_kernel_v3<true><<<g3, 256, 0, as_stream (stream)>>> (A);
+      else obmc_kernel_v3<false><<<g3, 256, 0, as_stream (stream)>>> (A);
+    } else if (table_ok) obmc_kernel_v2<<<grid, 256, 0, as_stream (stream)>>> (A);
     else obmc_kernel<<<grid, 256, 0, as_stream (stream)>>> (A);
   }
   return check_cuda (cudaGetLastError (), "obmc_kernel launch");

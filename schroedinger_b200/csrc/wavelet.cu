@@ -135,6 +135,8 @@ struct LevelArgs {
   int w[SB2_MAX_COMPONENTS];
   int h[SB2_MAX_COMPONENTS];
   int ncomp;
+  int comp_map[SB2_MAX_COMPONENTS];   // blockIdx.z % ncomp -> component (a launch may cover a subset)
+  int ncomp_total;                    // components per picture in the plane sets
 };
 
 constexpr int TWH = 64;    // tile width  in polyphase samples (128 output columns)
@@ -248,7 +250,7 @@ wavelet_level_kernel (const LevelArgs a)
   extern __shared__ __align__ (16) unsigned char smem_raw[];
   T *sm = reinterpret_cast<T *> (smem_raw);
 
-  const int comp = blockIdx.z % a.ncomp;
+  const int comp = a.comp_map[blockIdx.z % a.ncomp];
   const int pic = blockIdx.z / a.ncomp;
   const int w = a.w[comp], h = a.h[comp];
   const int n = w >> 1, m = h >> 1;
@@ -363,14 +365,36 @@ wavelet_level_kernel (const LevelArgs a)
 // out with coalesced stores.  Picture edges re-extend (replicate) the arrays after every
 // step, exactly like the reference's extend_* helpers (schrowaveletorc.c:192-269).
 
-template <typename T, int F, bool INV, int S, int N>
+// reach of one step to the left / right in the source array
+__host__ __device__ constexpr int step_reach_l (int f, int s) { return step_of (f, s).tap0 < 0 ? -step_of (f, s).tap0 : 0; }
+__host__ __device__ constexpr int step_reach_r (int f, int s)
+{
+  return step_of (f, s).tap0 + kind_taps (step_of (f, s).kind) - 1 > 0 ? step_of (f, s).tap0 + kind_taps (step_of (f, s).kind) - 1 : 0;
+}
+// total reach of the steps that still follow position `pos` (0-based, in execution order)
+__host__ __device__ constexpr int reach_after (int f, bool inv, int pos, bool left)
+{
+  int r = 0;
+  for (int p = pos + 1; p < num_steps (f); p++) {
+    const int s = inv ? num_steps (f) - 1 - p : p;
+    r += left ? step_reach_l (f, s) : step_reach_r (f, s);
+  }
+  return r;
+}
+
+// One lifting step on the private arrays.  Only the positions that later steps (and the
+// final C outputs at [HP, N-HP)) still depend on are computed.
+template <typename T, int F, bool INV, int POS, int N, int HP>
 __device__ __forceinline__ void chunk_step (int (&E)[N], int (&O)[N])
 {
+  constexpr int S = INV ? num_steps (F) - 1 - POS : POS;
   constexpr Step st = step_of (F, S);
   constexpr int NT = kind_taps (st.kind);
   constexpr int sign = INV ? -st.sign : st.sign;
+  constexpr int K0 = HP - reach_after (F, INV, POS, true) < 0 ? 0 : HP - reach_after (F, INV, POS, true);
+  constexpr int K1 = N - HP + reach_after (F, INV, POS, false) > N ? N : N - HP + reach_after (F, INV, POS, false);
 #pragma unroll
-  for (int k = 0; k < N; k++) {
+  for (int k = K0; k < K1; k++) {
     int v[NT];
 #pragma unroll
     for (int t = 0; t < NT; t++) {
@@ -404,7 +428,7 @@ struct ChunkSeq {
   {
     constexpr int NS = num_steps (F);
     constexpr int s = INV ? NS - 1 - S : S;
-    chunk_step<T, F, INV, s, N> (E, O);
+    chunk_step<T, F, INV, S, N, HP> (E, O);
     if (step_of (F, s).target) chunk_extend<N, HP> (O, lo, hi);
     else chunk_extend<N, HP> (E, lo, hi);
     if constexpr (S + 1 < NS) ChunkSeq<T, F, INV, N, HP, S + 1>::run (E, O, lo, hi);
@@ -419,33 +443,66 @@ __device__ __forceinline__ void chunk_lift (int (&E)[N], int (&O)[N], bool lo, b
   ChunkSeq<T, F, INV, N, HP, 0>::run (E, O, lo, hi);
 }
 
-template <typename T, int F> struct FastGeom {
+template <typename T, int F, int CS> struct FastGeom {
   static constexpr int VEC = 16 / (int) sizeof (T);
   static constexpr int HP = filter_halo (F);
-  static constexpr int HK = ((HP + VEC - 1) / VEC) * VEC;
-  static constexpr int C = 16;                 // vertical chunk (polyphase rows)
-  static constexpr int CH = 16;                // horizontal chunk (polyphase columns)
+  static constexpr int HK = ((HP + VEC - 1) / VEC) * VEC;   // horizontal halo, 16-byte granular
+  static constexpr int C = CS;                 // vertical chunk (polyphase rows)
+  static constexpr int CH = CS;                // horizontal chunk (polyphase columns)
   static constexpr int NKV = TWH + 2 * HK;     // columns per segment held in shared memory
   static constexpr int NV = C + 2 * HP;
-  static constexpr int NH = CH + 2 * HP;
-  // pitch in elements: an odd number of 32-bit words, so that lanes = rows hit distinct banks
-  static constexpr int PITCH = (sizeof (T) == 4) ? (2 * NKV + 1) : (2 * NKV + 2);
+  static constexpr int NH = CH + 2 * HK;
+  // row pitch: a multiple of 16 bytes that is 4 (mod 32) in 32-bit words, so that lanes =
+  // rows reading 128 bits each are conflict-free (a quarter warp covers all 32 banks)
+  static constexpr int MINW = 2 * NKV * (int) sizeof (T) / 4;
+  static constexpr int PITCHW = ((MINW - 4 + 31) / 32) * 32 + 4;
+  static constexpr int PITCH = PITCHW * 4 / (int) sizeof (T);
   static constexpr int VITEMS = 2 * NKV * (THH / C);
   static constexpr int HITEMS = 2 * THH * (TWH / CH);
   static constexpr int NT = ((VITEMS > HITEMS ? VITEMS : HITEMS) + 31) / 32 * 32;
   static constexpr size_t SMEM = (size_t) 2 * THH * PITCH * sizeof (T);
-  static_assert (sizeof (T) == 4 || ((2 * NKV + 2) / 2) % 2 == 1, "s16 pitch must be an odd number of words");
+  static_assert (PITCHW >= MINW && PITCHW % 32 == 4, "bad pitch");
 };
 
-template <typename T, int F>
-__global__ void __launch_bounds__ (FastGeom<T, F>::NT)
+// 16 bytes of shared memory <-> VEC ints
+template <typename T> struct Vec16;
+template <> struct Vec16<int32_t> {
+  static __device__ __forceinline__ void load (const int32_t *p, int *v)
+  {
+    const int4 q = *reinterpret_cast<const int4 *> (p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+  // 4 interleaved outputs (e0 o0 e1 o1)
+  static __device__ __forceinline__ void store_pairs (int32_t *p, const int *e, const int *o)
+  {
+    *reinterpret_cast<int4 *> (p) = make_int4 (e[0], o[0], e[1], o[1]);
+  }
+  static constexpr int PAIRS = 2;
+};
+template <> struct Vec16<int16_t> {
+  static __device__ __forceinline__ void load (const int16_t *p, int *v)
+  {
+    const int4 q = *reinterpret_cast<const int4 *> (p);
+    v[0] = (q.x << 16) >> 16; v[1] = q.x >> 16; v[2] = (q.y << 16) >> 16; v[3] = q.y >> 16;
+    v[4] = (q.z << 16) >> 16; v[5] = q.z >> 16; v[6] = (q.w << 16) >> 16; v[7] = q.w >> 16;
+  }
+  static __device__ __forceinline__ void store_pairs (int16_t *p, const int *e, const int *o)
+  {
+    *reinterpret_cast<int4 *> (p) = make_int4 ((e[0] & 0xffff) | (o[0] << 16), (e[1] & 0xffff) | (o[1] << 16),
+        (e[2] & 0xffff) | (o[2] << 16), (e[3] & 0xffff) | (o[3] << 16));
+  }
+  static constexpr int PAIRS = 4;
+};
+
+template <typename T, int F, int CS>
+__global__ void __launch_bounds__ (FastGeom<T, F, CS>::NT)
 wavelet_inv_fast_kernel (const LevelArgs a)
 {
-  typedef FastGeom<T, F> G;
+  typedef FastGeom<T, F, CS> G;
   extern __shared__ __align__ (16) unsigned char smem_raw[];
   T *sm = reinterpret_cast<T *> (smem_raw);
 
-  const int comp = blockIdx.z % a.ncomp, pic = blockIdx.z / a.ncomp;
+  const int comp = a.comp_map[blockIdx.z % a.ncomp], pic = blockIdx.z / a.ncomp;
   const int w = a.w[comp], h = a.h[comp];
   const int n = w >> 1, m = h >> 1;
   const int kx0 = blockIdx.x * TWH, ky0 = blockIdx.y * THH;
@@ -471,14 +528,25 @@ wavelet_inv_fast_kernel (const LevelArgs a)
       const T *pe = seg ? bands + n + kx : ll + kx;      // even rows: LL (seg 0) or HL (seg 1)
       const size_t es = seg ? 2 * bs : ls;
       const T *po = bands + bs + seg * n + kx;           // odd rows: LH / HH
+      const bool lo = kyc == 0, hi = kyc + G::C >= m;
+      if (!lo && !hi) {
+        pe += (size_t) (kyc - G::HP) * es;
+        po += (size_t) (kyc - G::HP) * 2 * bs;
 #pragma unroll
-      for (int r = 0; r < G::NV; r++) {
-        const int ky = kyc - G::HP + r;
-        const bool ok = ky >= 0 && ky < m;
-        E[r] = ok ? (int) pe[(size_t) ky * es] : 0;
-        O[r] = ok ? (int) po[(size_t) ky * 2 * bs] : 0;
+        for (int r = 0; r < G::NV; r++) {
+          E[r] = pe[(size_t) r * es];
+          O[r] = po[(size_t) r * 2 * bs];
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < G::NV; r++) {
+          const int ky = kyc - G::HP + r;
+          const bool ok = ky >= 0 && ky < m;
+          E[r] = ok ? (int) pe[(size_t) ky * es] : 0;
+          O[r] = ok ? (int) po[(size_t) ky * 2 * bs] : 0;
+        }
       }
-      chunk_lift<T, F, true, G::NV, G::HP> (E, O, kyc == 0, kyc + G::C >= m);
+      chunk_lift<T, F, true, G::NV, G::HP> (E, O, lo, hi);
       T *out = sm + (size_t) (chunk * 2 * G::C) * G::PITCH + col;
 #pragma unroll
       for (int r = 0; r < G::C; r++) {
@@ -497,62 +565,90 @@ wavelet_inv_fast_kernel (const LevelArgs a)
   const bool hact = tid < G::HITEMS && k0 < n && (2 * ky0 + row) < h;
   int E[G::NH], O[G::NH];
   if (hact) {
-    const T *rowp = sm + (size_t) row * G::PITCH + G::HK + q * G::CH - G::HP;
+    const T *rowp = sm + (size_t) row * G::PITCH + q * G::CH;     // = column kx0 - HK + q*CH
 #pragma unroll
-    for (int i = 0; i < G::NH; i++) {
-      E[i] = rowp[i];
-      O[i] = rowp[G::NKV + i];
+    for (int i = 0; i < G::NH; i += G::VEC) {
+      Vec16<T>::load (rowp + i, &E[i]);
+      Vec16<T>::load (rowp + G::NKV + i, &O[i]);
     }
-    chunk_lift<T, F, true, G::NH, G::HP> (E, O, k0 == 0, k0 + G::CH >= n);
+    chunk_lift<T, F, true, G::NH, G::HK> (E, O, k0 == 0, k0 + G::CH >= n);
   }
   __syncthreads ();
   if (hact) {
     // interleave + (x+1)>>1 in place: output column x of the tile at row*PITCH + x
     T *orow = sm + (size_t) row * G::PITCH + 2 * q * G::CH;
+    if (SH) {
 #pragma unroll
-    for (int i = 0; i < G::CH; i++) {
-      int e = E[G::HP + i], o = O[G::HP + i];
-      if (SH) { e = Ar<T>::add (e, 1) >> 1; o = Ar<T>::add (o, 1) >> 1; }
-      orow[2 * i] = (T) e;
-      orow[2 * i + 1] = (T) o;
+      for (int i = 0; i < G::CH; i++) {
+        E[G::HK + i] = Ar<T>::add (E[G::HK + i], 1) >> 1;
+        O[G::HK + i] = Ar<T>::add (O[G::HK + i], 1) >> 1;
+      }
     }
+#pragma unroll
+    for (int i = 0; i < G::CH; i += Vec16<T>::PAIRS)
+      Vec16<T>::store_pairs (orow + 2 * i, &E[G::HK + i], &O[G::HK + i]);
   }
   __syncthreads ();
 
-  // ---- coalesced copy-out, 32 bits per lane ----
+  // ---- coalesced copy-out, 128 bits per lane ----
   {
-    const int tw = min (2 * TWH, w - 2 * kx0);           // output columns of this tile
+    const int tw = min (2 * TWH, w - 2 * kx0);           // output columns of this tile (multiple of 32)
     const int th = min (2 * THH, h - 2 * ky0);
-    constexpr int EPW = 4 / (int) sizeof (T);            // elements per 32-bit word
-    const int wpr = tw / EPW;                            // words per row (tw is a multiple of 32)
-    const int nwarps = G::NT / 32;
-    for (int r = hw; r < th; r += nwarps) {
-      const unsigned *src = reinterpret_cast<const unsigned *> (sm + (size_t) r * G::PITCH);
-      unsigned *dst = reinterpret_cast<unsigned *> (dense + (size_t) (2 * ky0 + r) * ds + 2 * kx0);
-      for (int x = lane; x < wpr; x += 32) dst[x] = src[x];
+    const int vpr = tw / G::VEC;                         // 16-byte vectors per row
+    const int total = th * vpr;
+    for (int i = tid; i < total; i += G::NT) {
+      const int r = i / vpr, x = i - r * vpr;
+      const int4 v = *reinterpret_cast<const int4 *> (sm + (size_t) r * G::PITCH + x * G::VEC);
+      *reinterpret_cast<int4 *> (dense + (size_t) (2 * ky0 + r) * ds + 2 * kx0 + x * G::VEC) = v;
     }
   }
 }
 
+// chunk size (16, 8) usable by the fast inverse kernel for component c, or 0
 template <typename T, int F>
-static bool fast_inverse_ok (const LevelArgs &a)
+static int fast_inverse_chunk (const LevelArgs &a, int c)
 {
-  typedef FastGeom<T, F> G;
-  if (G::HP > 4) return false;                          // Fidelity: register arrays too large
-  for (int c = 0; c < a.ncomp; c++) {
-    const int n = a.w[c] >> 1, m = a.h[c] >> 1;
-    if (n % G::CH || m % G::C) return false;
-    // 32-bit copy-out: rows of the dense plane must be 4-byte aligned
-    if ((a.dense.stride[c] % 4) || (a.dense.off[c] % 4)) return false;
-  }
-  if (((size_t) a.dense.base % 4) || (a.dense.pic_pitch % 4)) return false;
-  return true;
+  if (filter_halo (F) > 4) return 0;                   // Fidelity: register arrays too large
+  // 128-bit copy-out: rows of the dense plane must be 16-byte aligned
+  if ((a.dense.stride[c] % 16) || (a.dense.off[c] % 16)) return 0;
+  if (((size_t) a.dense.base % 16) || (a.dense.pic_pitch % 16)) return 0;
+  const int n = a.w[c] >> 1, m = a.h[c] >> 1;
+  if (n % 16 == 0 && m % 16 == 0) return 16;
+  if (n % 8 == 0 && m % 8 == 0 && filter_halo (F) <= 4) return 8;
+  return 0;
 }
 
 // ---- host side ---------------------------------------------------------------
 
+template <typename T, int F, int CS>
+static int launch_fast_inverse (LevelArgs a, const int *comps, int nsel, int count, cudaStream_t stream,
+    const char *tag, double bytes)
+{
+  typedef FastGeom<T, F, CS> FG;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute (wavelet_inv_fast_kernel<T, F, CS>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FG::SMEM);
+    if (e != cudaSuccess) return check_cuda (e, "cudaFuncSetAttribute(wavelet fast)");
+    attr_set = true;
+  }
+  int maxn = 0, maxm = 0;
+  a.ncomp = nsel;
+  for (int i = 0; i < nsel; i++) {
+    a.comp_map[i] = comps[i];
+    maxn = max (maxn, a.w[comps[i]] >> 1);
+    maxm = max (maxm, a.h[comps[i]] >> 1);
+  }
+  dim3 grid (ceil_div (maxn, TWH), ceil_div (maxm, THH), nsel * count);
+  {
+    LaunchScope scope (tag, bytes, stream);
+    wavelet_inv_fast_kernel<T, F, CS><<<grid, FG::NT, FG::SMEM, stream>>> (a);
+  }
+  return check_cuda (cudaGetLastError (), "wavelet_inv_fast_kernel launch");
+}
+
 template <typename T, int F, bool INV>
-static int launch_level (const LevelArgs &a, int count, cudaStream_t stream)
+static int launch_level (const LevelArgs &a_in, int count, cudaStream_t stream)
 {
   typedef TileGeom<T, F> G;
   static bool attr_set = false;
@@ -562,38 +658,49 @@ static int launch_level (const LevelArgs &a, int count, cudaStream_t stream)
     if (e != cudaSuccess) return check_cuda (e, "cudaFuncSetAttribute(wavelet)");
     attr_set = true;
   }
-  int maxn = 0, maxm = 0;
-  for (int c = 0; c < a.ncomp; c++) {
-    maxn = max (maxn, a.w[c] >> 1);
-    maxm = max (maxm, a.h[c] >> 1);
+  LevelArgs a = a_in;
+  a.ncomp_total = a_in.ncomp;
+  // components are routed to the fastest kernel their size allows
+  int sel[3][SB2_MAX_COMPONENTS], nsel[3] = { 0, 0, 0 };     // 0: generic, 1: chunk 16, 2: chunk 8
+  for (int c = 0; c < a_in.ncomp; c++) {
+    if ((a.w[c] >> 1) == 0 || (a.h[c] >> 1) == 0) continue;
+    int cs = 0;
+    if constexpr (INV) cs = fast_inverse_chunk<T, F> (a, c);
+    const int k = cs == 16 ? 1 : cs == 8 ? 2 : 0;
+    sel[k][nsel[k]++] = c;
   }
-  if (maxn == 0 || maxm == 0) return SB2_OK;
-  dim3 grid (ceil_div (maxn, TWH), ceil_div (maxm, THH), a.ncomp * count);
-  {
-    char tag[48];
+  for (int k = 0; k < 3; k++) {
+    if (!nsel[k]) continue;
+    char tag[48] = "";
     double bytes = 0;
     if (profiling ()) {
-      snprintf (tag, sizeof (tag), "wavelet_%s_%s_f%d_w%d", INV ? "inv" : "fwd",
-          sizeof (T) == 4 ? "s32" : "s16", F, a.w[0]);
-      for (int c = 0; c < a.ncomp; c++) bytes += 2.0 * a.w[c] * a.h[c] * sizeof (T) * count;
+      snprintf (tag, sizeof (tag), "wavelet_%s_%s_f%d_w%d%s", INV ? "inv" : "fwd",
+          sizeof (T) == 4 ? "s32" : "s16", F, a.w[sel[k][0]], k == 0 ? "_generic" : "");
+      for (int i = 0; i < nsel[k]; i++) bytes += 2.0 * a.w[sel[k][i]] * a.h[sel[k][i]] * sizeof (T) * count;
     }
-    LaunchScope scope (tag, bytes, stream);
+    int rc = SB2_OK;
     if constexpr (INV) {
-      if (fast_inverse_ok<T, F> (a)) {
-        typedef FastGeom<T, F> FG;
-        static bool fast_attr = false;
-        if (!fast_attr) {
-          cudaFuncSetAttribute (wavelet_inv_fast_kernel<T, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-              (int) FG::SMEM);
-          fast_attr = true;
-        }
-        wavelet_inv_fast_kernel<T, F><<<grid, FG::NT, FG::SMEM, stream>>> (a);
-        return check_cuda (cudaGetLastError (), "wavelet_inv_fast_kernel launch");
-      }
+      if (k == 1) rc = launch_fast_inverse<T, F, 16> (a, sel[k], nsel[k], count, stream, tag, bytes);
+      if (k == 2) rc = launch_fast_inverse<T, F, 8> (a, sel[k], nsel[k], count, stream, tag, bytes);
     }
-    wavelet_level_kernel<T, F, INV><<<grid, NTHREADS, G::SMEM, stream>>> (a);
+    if (k == 0) {
+      int maxn = 0, maxm = 0;
+      a.ncomp = nsel[0];
+      for (int i = 0; i < nsel[0]; i++) {
+        a.comp_map[i] = sel[0][i];
+        maxn = max (maxn, a.w[sel[0][i]] >> 1);
+        maxm = max (maxm, a.h[sel[0][i]] >> 1);
+      }
+      dim3 grid (ceil_div (maxn, TWH), ceil_div (maxm, THH), nsel[0] * count);
+      {
+        LaunchScope scope (tag, bytes, stream);
+        wavelet_level_kernel<T, F, INV><<<grid, NTHREADS, G::SMEM, stream>>> (a);
+      }
+      rc = check_cuda (cudaGetLastError (), "wavelet_level_kernel launch");
+    }
+    if (rc) return rc;
   }
-  return check_cuda (cudaGetLastError (), "wavelet_level_kernel launch");
+  return SB2_OK;
 }
 
 template <typename T, bool INV>

@@ -208,6 +208,22 @@ def upsample(frames, stream=None):
           "sb2_upsample")
 
 
+def edgeextend_upsample(frames, stream=None):
+    """schro_frame_mc_edgeextend + schro_upsampled_frame_upsample fused into one launch."""
+    require_cuda()
+    assert frames.layout.upsampled and frames.layout.depth == "u8"
+    check(lib.sb2_edgeextend_upsample(ctypes.byref(frames.slab), frames.layout.extension,
+                                      _stream_ptr(stream)), "sb2_edgeextend_upsample")
+
+
+def downsample_edgeextend(src, dst, stream=None):
+    """schro_frame_downsample + schro_frame_mc_edgeextend(dst) fused into one launch."""
+    require_cuda()
+    check(lib.sb2_downsample_edgeextend(ctypes.byref(src.slab), ctypes.byref(dst.slab),
+                                        dst.layout.extension, _stream_ptr(stream)),
+          "sb2_downsample_edgeextend")
+
+
 def downsample(src, dst, stream=None):
     """schro_frame_downsample: dst = half-size src (per component)."""
     require_cuda()
@@ -296,11 +312,14 @@ class Pyramid:
             w, h, cw, ch = (w + 1) // 2, (h + 1) // 2, (cw + 1) // 2, (ch + 1) // 2
             self.slabs.append(PictureSlab(FrameLayout("u8", [(w, h), (cw, ch), (cw, ch)], ext), count))
 
-    def build(self, stream=None):
+    def build(self, stream=None, fused=True):
         mc_edgeextend(self.slabs[0], stream=stream)
         for l in range(self.levels):
-            downsample(self.slabs[l], self.slabs[l + 1], stream=stream)
-            mc_edgeextend(self.slabs[l + 1], stream=stream)
+            if fused:
+                downsample_edgeextend(self.slabs[l], self.slabs[l + 1], stream=stream)
+            else:
+                downsample(self.slabs[l], self.slabs[l + 1], stream=stream)
+                mc_edgeextend(self.slabs[l + 1], stream=stream)
 
 
 def hbm_scan(params, src_pyr, ref_pyr, level0_range=3, fields=None, workspace=None, stream=None):

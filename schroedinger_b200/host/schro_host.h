@@ -27,6 +27,10 @@ typedef struct {
 } Sb2hContext;
 
 Sb2hContext *sb2h_context (void);
+/* per-thread pool of device blocks, reused by exact size (no cudaMalloc / cudaFree -- and
+ * therefore no device-wide synchronisation -- in steady state) */
+void *sb2h_pool_alloc (size_t bytes);
+void sb2h_pool_free (void *ptr);
 void *sb2h_dev_buffer (Sb2hContext *cx, int which, size_t bytes);
 
 static inline int sb2h_bpp (SchroFrameFormat format)

@@ -83,6 +83,51 @@ sb2h_dev_buffer (Sb2hContext *cx, int which, size_t bytes)
   return cx->dev[which];
 }
 
+#define SB2H_POOL_SLOTS 64
+static __thread struct { void *ptr; size_t bytes; int in_use; } tl_pool[SB2H_POOL_SLOTS];
+
+void *
+sb2h_pool_alloc (size_t bytes)
+{
+  int i, free_slot = -1;
+  for (i = 0; i < SB2H_POOL_SLOTS; i++) {
+    if (tl_pool[i].ptr && !tl_pool[i].in_use && tl_pool[i].bytes == bytes) {
+      tl_pool[i].in_use = 1;
+      return tl_pool[i].ptr;
+    }
+    if (!tl_pool[i].ptr && free_slot < 0) free_slot = i;
+  }
+  if (free_slot < 0) {
+    /* pool full: recycle the first idle block of another size */
+    for (i = 0; i < SB2H_POOL_SLOTS; i++)
+      if (!tl_pool[i].in_use) {
+        SB2H_CUDA (cudaFree (tl_pool[i].ptr));
+        tl_pool[i].ptr = NULL;
+        free_slot = i;
+        break;
+      }
+    if (free_slot < 0) sb2h_fatal (__func__, "device block pool exhausted");
+  }
+  SB2H_CUDA (cudaMalloc (&tl_pool[free_slot].ptr, bytes + 256));
+  tl_pool[free_slot].bytes = bytes;
+  tl_pool[free_slot].in_use = 1;
+  return tl_pool[free_slot].ptr;
+}
+
+void
+sb2h_pool_free (void *ptr)
+{
+  int i;
+  if (!ptr) return;
+  for (i = 0; i < SB2H_POOL_SLOTS; i++)
+    if (tl_pool[i].ptr == ptr) {
+      tl_pool[i].in_use = 0;
+      return;
+    }
+  /* allocated by another thread's pool: release for real */
+  SB2H_CUDA (cudaFree (ptr));
+}
+
 void
 sb2h_copy_rect (Sb2hContext *cx, void *dst, size_t dst_stride, const void *src,
     size_t src_stride, size_t row_bytes, int rows)

@@ -82,11 +82,11 @@ schro_hbm_unref (SchroHierBm *hbm)
     if (hbm->downsampled_src[i]) schro_frame_unref (hbm->downsampled_src[i]);
     if (hbm->downsampled_ref[i]) schro_frame_unref (hbm->downsampled_ref[i]);
     if (hbm->downsampled_mf[i]) schro_motion_field_free (hbm->downsampled_mf[i]);
-    if (h->dev_src[i]) cudaFree (h->dev_src[i]);
-    if (h->dev_ref[i]) cudaFree (h->dev_ref[i]);
-    if (h->dev_field[i]) cudaFree (h->dev_field[i]);
+    sb2h_pool_free (h->dev_src[i]);
+    sb2h_pool_free (h->dev_ref[i]);
+    sb2h_pool_free (h->dev_field[i]);
   }
-  if (h->dev_ws) cudaFree (h->dev_ws);
+  sb2h_pool_free (h->dev_ws);
   free (hbm->downsampled_mf);
   free (hbm->downsampled_ref);
   free (hbm->downsampled_src);
@@ -112,7 +112,7 @@ level_slab (Sb2hContext *cx, SchroFrame *f, void **cache, sb2_slab *slab)
     base = f->regions[0];
   } else {
     if (!*cache) {
-      SB2H_CUDA (cudaMalloc (cache, bytes + 256));
+      *cache = sb2h_pool_alloc (bytes);
       SB2H_CUDA (cudaMemcpyAsync (*cache, f->regions[0], bytes, cudaMemcpyDefault, cx->stream));
     }
     base = *cache;
@@ -158,10 +158,10 @@ schro_hierarchical_bm_scan_hint (SchroHierBm *hbm, int shift, int h_range)
   p.chroma_v_shift = SCHRO_FRAME_FORMAT_V_SHIFT (fs->format);
   if (!h->dev_ws) {
     h->ws_bytes = sb2_hbm_workspace_bytes (params->y_num_blocks, 1);
-    SB2H_CUDA (cudaMalloc (&h->dev_ws, h->ws_bytes));
+    h->dev_ws = sb2h_pool_alloc (h->ws_bytes);
   }
   if (!h->dev_field[shift])
-    SB2H_CUDA (cudaMalloc (&h->dev_field[shift], n * sizeof (SchroMotionVector)));
+    h->dev_field[shift] = sb2h_pool_alloc (n * sizeof (SchroMotionVector));
   SB2H_CHECK (sb2_hbm_scan_hint (&p, &ss, &rs, fs->extension, shift, h_range,
           shift < hbm->hierarchy_levels ? h->dev_field[shift + 1] : NULL, h->dev_field[shift], n,
           h->dev_ws, h->ws_bytes, cx->stream), "sb2_hbm_scan_hint");

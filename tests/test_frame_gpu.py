@@ -101,3 +101,31 @@ def test_downsample_golden(cuda):
         dev.downsample(src, dst)
         assert np.array_equal(dst.download(0, 0), GOLD[f"down{idx}_out"]), idx
         idx += 1
+
+
+def test_fused_edgeextend_variants(cuda):
+    """sb2_edgeextend_upsample == mc_edgeextend + upsample, sb2_downsample_edgeextend ==
+    downsample + mc_edgeextend (the fused launches the pipeline uses)."""
+    from schroedinger_b200 import device as dev
+    rng = np.random.default_rng(17)
+    for (h, w) in ((70, 130), (16, 17), (1, 9), (5, 1), (270, 480)):
+        imgs = [rng.integers(0, 256, size=(h, w)).astype(np.uint8)]
+        lay = dev.FrameLayout("u8", [(w, h)], 32, True)
+        a, b = dev.PictureSlab(lay, 2), dev.PictureSlab(lay, 2)
+        for s in (a, b):
+            s.buf.fill_(0x77)
+            for p in range(2):
+                s.upload(p, 0, imgs[0])
+        dev.mc_edgeextend(a)
+        dev.upsample(a)
+        dev.edgeextend_upsample(b)
+        assert bool((a.buf[:a.nbytes] == b.buf[:b.nbytes]).all()), ("upsample", h, w)
+        src = dev.PictureSlab(dev.FrameLayout("u8", [(w, h)]), 2)
+        for p in range(2):
+            src.upload(p, 0, imgs[0])
+        dl = dev.FrameLayout("u8", [((w + 1) // 2, (h + 1) // 2)], 8)
+        d1, d2 = dev.PictureSlab(dl, 2), dev.PictureSlab(dl, 2)
+        dev.downsample(src, d1)
+        dev.mc_edgeextend(d1)
+        dev.downsample_edgeextend(src, d2)
+        assert bool((d1.buf[:d1.nbytes] == d2.buf[:d2.nbytes]).all()), ("downsample", h, w)
