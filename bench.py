@@ -307,6 +307,8 @@ class HostFrames:
         self.full = spec.get("full_core", True)
         B = spec["batch"]
         W, H = spec["width"], spec["height"]
+        import torch
+        lib.schro_b200_set_device(torch.cuda.current_device())
         self.pinned = compat.pinned_domain()
         self.cuda = compat.cuda_domain()
         s32 = spec["depth_name"] == "s32"

@@ -267,6 +267,9 @@ typedef struct _SchroHierBm {
 
 /* ---- library / domains -------------------------------------------------- */
 void schro_init (void);                                   /* schroedinger/schro.c:23 */
+/* new: the GPU this process's picture core runs on (default: the device current on the
+ * first thread that calls into the library); worker threads inherit it */
+void schro_b200_set_device (int device);
 /* schroedinger/schrocuda.h:9 (schro_memory_domain_new_cuda) */
 SchroMemoryDomain *schro_memory_domain_new_cuda (void);
 SchroMemoryDomain *schro_memory_domain_new_pinned (void); /* new: cudaHostAlloc'd frames */

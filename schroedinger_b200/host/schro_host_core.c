@@ -56,11 +56,29 @@ sb2h_mem_kind (const void *ptr)
 
 /* ---- per-thread context -------------------------------------------------- */
 static __thread Sb2hContext *tl_cx;
+/* The device of the first thread that enters the library becomes the process's device:
+ * worker threads created later start on device 0 by CUDA's rules, which is wrong for
+ * rank > 0 of a one-process-per-GPU job.  schro_b200_set_device overrides it. */
+static int g_device = -1;
+static pthread_mutex_t g_device_mutex = PTHREAD_MUTEX_INITIALIZER;
+
+void
+schro_b200_set_device (int device)
+{
+  pthread_mutex_lock (&g_device_mutex);
+  g_device = device;
+  pthread_mutex_unlock (&g_device_mutex);
+  SB2H_CUDA (cudaSetDevice (device));
+}
 
 Sb2hContext *
 sb2h_context (void)
 {
   if (!tl_cx) {
+    pthread_mutex_lock (&g_device_mutex);
+    if (g_device < 0) SB2H_CUDA (cudaGetDevice (&g_device));
+    pthread_mutex_unlock (&g_device_mutex);
+    SB2H_CUDA (cudaSetDevice (g_device));
     tl_cx = calloc (1, sizeof (Sb2hContext));
     SB2H_CUDA (cudaStreamCreateWithFlags (&tl_cx->stream, cudaStreamNonBlocking));
   }
