@@ -408,7 +408,12 @@ class HostFrames:
         # decode side: coefficients in, decoded picture out
         lib.schro_frame_to_gpu(th["coef"], self.coef_host[i])
         lib.schro_frame_inverse_iwt_transform(th["coef"], ctypes.byref(self.params))
-        lib.schro_motion_render(th["motion"], th["acc"], ctypes.byref(th["resid"]), 1, th["out"])
+        # the transform may have swapped the frame's device region: refresh the picture-size window
+        view, cf = th["resid"], th["coef"].contents
+        view.regions[0] = cf.regions[0]
+        for c in range(3):
+            view.components[c].data = cf.components[c].data
+        lib.schro_motion_render(th["motion"], th["acc"], ctypes.byref(view), 1, th["out"])
         lib.schro_frame_mc_edgeextend(th["out"])
         th["out"].contents.upsample_done = 0
         lib.schro_upsampled_frame_upsample(th["out"])

@@ -166,7 +166,7 @@ typedef struct {
   int chroma_h_shift, chroma_v_shift;
 } sb2_hbm_params;
 
-size_t sb2_hbm_workspace_bytes (int y_num_blocks, int count);
+size_t sb2_hbm_workspace_bytes (int x_num_blocks, int y_num_blocks, int count);
 
 /* One level of hierarchical block matching for `count` independent (picture, reference)
  * pairs: schro_hierarchical_bm_scan_hint (schroedinger/schrohierbm.c:174-383), including

@@ -32,7 +32,7 @@ struct HbmArgs {
   const MotionVector *parent;       // field of level shift+1 or nullptr
   MotionVector *field;              // output field
   size_t field_pitch;               // vectors between pictures
-  int *progress;                    // [count][rows] finished blocks per row
+  unsigned long long *words;        // [count][rows][cols] published results: bit 63 valid, dx<<16 | dy
   int width, height;                // luma size of this pyramid level
   int cw, ch;                       // chroma size
   int hs, vs;
@@ -104,16 +104,24 @@ hbm_init_field_kernel (MotionVector *field, size_t n, uint32_t flags0)
   }
 }
 
-// acquire / release on the per-row progress counters
-__device__ __forceinline__ int ld_acquire (const int *p)
+// Published block results.  A row's neighbours in the row below need only the vector of a
+// finished block, so the vector itself is the flag: one relaxed 64-bit word per block
+// (bit 63 = valid, dx in bits 16..31, dy in bits 0..15).  No fence on either side -- the
+// word is the data, single-copy atomic -- which takes two L2 round trips and two fences off
+// the per-block critical path compared with a progress counter + separate vector load.
+__device__ __forceinline__ unsigned long long ld_word (const unsigned long long *p)
 {
-  int v;
-  asm volatile ("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  unsigned long long v;
+  asm volatile ("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release (int *p, int v)
+__device__ __forceinline__ void st_word (unsigned long long *p, unsigned long long v)
 {
-  asm volatile ("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+  asm volatile ("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long pack_word (int dx, int dy)
+{
+  return (1ull << 63) | ((unsigned long long) (dx & 0xffff) << 16) | (unsigned long long) (dy & 0xffff);
 }
 
 // 8 (or 4) bytes starting at any address, assembled from aligned 32-bit words
@@ -135,6 +143,7 @@ __device__ __forceinline__ unsigned load4_unaligned (const uint8_t *p)
 
 struct BlockShared {
   int xmin, ymin, scan_w, scan_h, seed_a, seed_b;
+  int last_dx, last_dy;             // this row's previous block (the "left" candidate)
   unsigned long long key[16];
   unsigned luma[16], chroma[16];
 };
@@ -162,8 +171,10 @@ hbm_level_kernel (const HbmArgs A)
   }
   MotionVector *mf = A.field + (size_t) pic * A.field_pitch;
   const MotionVector *pf = A.parent ? A.parent + (size_t) pic * A.field_pitch : nullptr;
-  int *prog_me = A.progress + (size_t) pic * A.rows + row;
-  const int *prog_up = row > 0 ? A.progress + (size_t) pic * A.rows + row - 1 : nullptr;
+  unsigned long long *words_me = A.words + ((size_t) pic * A.rows + row) * A.cols;
+  const unsigned long long *words_up = row > 0 ? words_me - A.cols : nullptr;
+  if (threadIdx.x == 0) { sh.last_dx = 0; sh.last_dy = 0; }
+  if (NW > 1) __syncthreads (); else __syncwarp ();
   const int hint_mask = ~((1 << (s + 1)) - 1);
   const int y0 = (j * A.bh) >> s;
   const int e = A.ext;
@@ -178,143 +189,149 @@ hbm_level_kernel (const HbmArgs A)
     const bool active = x0 < A.width && y0 < A.height;
     const int bw0 = min (A.width - x0, A.bw), bh0 = min (A.height - y0, A.bh);
 
-    if (warp == 0) {
-      // ---- wait until the row above has published blocks bi (up) and bi-1 (up-left)
-      if (prog_up && active) {
-        if (lane == 0) while (ld_acquire (prog_up) < bi + 1) { }
-        __syncwarp ();
+    if (warp == 0 && active) {
+      // ---- phase A, before the wavefront dependency: candidates that do not depend on this
+      // level's neighbours -- 0: zero, 1..5: parents (0,0) (-1,0) (1,0) (0,-1) (0,1)
+      // (schrohierbm.c:259-277) -- and their ranking SADs
+      int cdx = 0, cdy = 0;
+      bool valid = false;
+      if (lane == 0) valid = true;
+      else if (lane <= 5 && pf) {
+        const int ox = (lane == 2) ? -1 : (lane == 3) ? 1 : 0;
+        const int oy = (lane == 4) ? -1 : (lane == 5) ? 1 : 0;
+        const int ll = (i & hint_mask) + ox * skip * 2, kk = (j & hint_mask) + oy * skip * 2;
+        if (ll >= 0 && ll < A.nbx && kk >= 0 && kk < A.nby) {
+          const MotionVector *m = pf + (size_t) kk * A.nbx + ll;
+          cdx = m->v[ri]; cdy = m->v[2 + ri]; valid = true;
+        }
       }
-      if (active) {
-        // ---- candidates, one per lane 0..8 (schrohierbm.c:259-294) ------------------
-        // 0: zero   1..5: parents (0,0) (-1,0) (1,0) (0,-1) (0,1)   6: left 7: up 8: up-left
-        int cdx = 0, cdy = 0;
-        bool valid = false;
-        if (lane == 0) valid = true;
-        else if (lane <= 5) {
-          if (pf) {
-            const int ox = (lane == 2) ? -1 : (lane == 3) ? 1 : 0;
-            const int oy = (lane == 4) ? -1 : (lane == 5) ? 1 : 0;
-            const int ll = (i & hint_mask) + ox * skip * 2, kk = (j & hint_mask) + oy * skip * 2;
-            if (ll >= 0 && ll < A.nbx && kk >= 0 && kk < A.nby) {
-              const MotionVector *m = pf + (size_t) kk * A.nbx + ll;
-              cdx = m->v[ri]; cdy = m->v[2 + ri]; valid = true;
-            }
-          }
-        } else if (lane <= 8) {
-          const bool need_x = (lane == 6 || lane == 8), need_y = (lane == 7 || lane == 8);
-          if ((!need_x || i > 0) && (!need_y || j > 0)) {
-            const MotionVector *m = mf + (size_t) (j - (need_y ? skip : 0)) * A.nbx + (i - (need_x ? skip : 0));
-            // written by this CTA (left) or published by the row above (acquired above)
-            cdx = ((volatile const int16_t *) m->v)[ri];
-            cdy = ((volatile const int16_t *) m->v)[2 + ri];
-            valid = true;
-          }
-        }
-        // de-duplicate keeping the LAST occurrence (schrohierbm.c:298-321)
-        bool dup = false;
+      const bool full = simd_ok && x0 + 8 <= A.width && y0 + 8 <= A.height &&
+          (x0 >> 1) + 4 <= A.cw && (y0 >> 1) + 4 <= A.ch;
+      // three lanes per candidate: luma rows 0-3, luma rows 4-7, both chroma blocks
+      const int ck = lane / 3, part = lane - 3 * ck;
+      unsigned metric = (unsigned) INT_MAX;        // candidate ck's SAD, valid in lane 3*ck
+      auto cand_sad = [&] (int kdx, int kdy, bool want) -> unsigned {
+        int dx = kdx >> s, dy = kdy >> s;
+        dx = clampi (dx + x0, -bw0, A.width) - x0;
+        dy = clampi (dy + y0, -bh0, A.height) - y0;
+        const bool ok = !(x0 < -e || y0 < -e || x0 + 8 > A.width + e || y0 + 8 > A.height + e) &&
+            !(x0 + dx < -e || y0 + dy < -e || x0 + dx + 8 > A.width + e || y0 + dy + 8 > A.height + e);
+        unsigned part_sad = 0;
+        if (ok && want) {
+          if (part < 2) {
+            const uint8_t *a = sp[0] + (ptrdiff_t) (y0 + 4 * part) * ss[0] + x0;
+            const uint8_t *b = rp[0] + (ptrdiff_t) (y0 + dy + 4 * part) * rs[0] + x0 + dx;
 #pragma unroll
-        for (int k = 1; k < 9; k++) {
-          const int kdx = __shfl_sync (0xffffffffu, cdx, k), kdy = __shfl_sync (0xffffffffu, cdy, k);
-          const bool kv = __shfl_sync (0xffffffffu, (int) valid, k) != 0;
-          if (k > lane && kv && kdx == cdx && kdy == cdy) dup = true;
-        }
-        const unsigned cmask = __ballot_sync (0xffffffffu, valid && !dup && lane < 9);
-
-        // ---- rank candidates with the 3-component SAD (schrometric.c:332-375) --------
-        int best_k;
-        const bool full = simd_ok && x0 + 8 <= A.width && y0 + 8 <= A.height &&
-            (x0 >> 1) + 4 <= A.cw && (y0 >> 1) + 4 <= A.ch;
-        if (full) {
-          // three lanes per candidate: luma rows 0-3, luma rows 4-7, both chroma blocks
-          const int k = lane / 3, part = lane - 3 * k;
-          int dx = __shfl_sync (0xffffffffu, cdx, min (k, 8)) >> s;
-          int dy = __shfl_sync (0xffffffffu, cdy, min (k, 8)) >> s;
-          dx = clampi (dx + x0, -bw0, A.width) - x0;
-          dy = clampi (dy + y0, -bh0, A.height) - y0;
-          const bool mine = k < 9 && ((cmask >> k) & 1);
-          const bool ok = !(x0 < -e || y0 < -e || x0 + 8 > A.width + e || y0 + 8 > A.height + e) &&
-              !(x0 + dx < -e || y0 + dy < -e || x0 + dx + 8 > A.width + e || y0 + dy + 8 > A.height + e);
-          unsigned part_sad = 0;
-          if (mine && ok) {
-            if (part < 2) {
-              const uint8_t *a = sp[0] + (ptrdiff_t) (y0 + 4 * part) * ss[0] + x0;
-              const uint8_t *b = rp[0] + (ptrdiff_t) (y0 + dy + 4 * part) * rs[0] + x0 + dx;
+            for (int y = 0; y < 4; y++) {
+              const uint2 av = __ldg (reinterpret_cast<const uint2 *> (a + (ptrdiff_t) y * ss[0]));
+              const uint2 bv = load8_unaligned (b + (ptrdiff_t) y * rs[0]);
+              part_sad += __vsadu4 (av.x, bv.x) + __vsadu4 (av.y, bv.y);
+            }
+          } else {
+            const int sx = x0 >> 1, sy = y0 >> 1, rx = (x0 + dx) >> 1, ry = (y0 + dy) >> 1;
+#pragma unroll
+            for (int c = 1; c < 3; c++) {
 #pragma unroll
               for (int y = 0; y < 4; y++) {
-                const uint2 av = __ldg (reinterpret_cast<const uint2 *> (a + (ptrdiff_t) y * ss[0]));
-                const uint2 bv = load8_unaligned (b + (ptrdiff_t) y * rs[0]);
-                part_sad += __vsadu4 (av.x, bv.x) + __vsadu4 (av.y, bv.y);
-              }
-            } else {
-              const int sx = x0 >> 1, sy = y0 >> 1, rx = (x0 + dx) >> 1, ry = (y0 + dy) >> 1;
-#pragma unroll
-              for (int c = 1; c < 3; c++) {
-#pragma unroll
-                for (int y = 0; y < 4; y++) {
-                  const unsigned av = __ldg (reinterpret_cast<const unsigned *> (sp[c] + (ptrdiff_t) (sy + y) * ss[c] + sx));
-                  const unsigned bv = load4_unaligned (rp[c] + (ptrdiff_t) (ry + y) * rs[c] + rx);
-                  part_sad += __vsadu4 (av, bv);
-                }
+                const unsigned av = __ldg (reinterpret_cast<const unsigned *> (sp[c] + (ptrdiff_t) (sy + y) * ss[c] + sx));
+                const unsigned bv = load4_unaligned (rp[c] + (ptrdiff_t) (ry + y) * rs[c] + rx);
+                part_sad += __vsadu4 (av, bv);
               }
             }
           }
-          unsigned metric = part_sad + __shfl_down_sync (0xffffffffu, part_sad, 1);
-          metric += __shfl_down_sync (0xffffffffu, part_sad, 2);
-          if (!ok) metric = (unsigned) INT_MAX;
-          // first strict minimum in candidate order == min over (metric, k); INT_MAX never wins
-          unsigned long long key = ~0ull;
-          if (mine && part == 0 && metric < (unsigned) INT_MAX) key = ((unsigned long long) metric << 8) | (unsigned) k;
-          key = warp_min64 (key);
-          best_k = key == ~0ull ? __ffs (cmask) - 1 : (int) (key & 0xff);
-        } else {
-          best_k = -1;
-          unsigned best_metric = (unsigned) INT_MAX;
-          for (int k = 0; k < 9; k++) {
-            if (!((cmask >> k) & 1)) continue;
-            int dx = __shfl_sync (0xffffffffu, cdx, k) >> s;
-            int dy = __shfl_sync (0xffffffffu, cdy, k) >> s;
-            dx = clampi (dx + x0, -bw0, A.width) - x0;
-            dy = clampi (dy + y0, -bh0, A.height) - y0;
-            unsigned metric;
-            const bool ok = !(x0 < -e || y0 < -e || x0 + A.bw > A.width + e || y0 + A.bh > A.height + e) &&
-                !(x0 + dx < -e || y0 + dy < -e || x0 + dx + A.bw > A.width + e || y0 + dy + A.bh > A.height + e);
-            if (!ok) {
-              metric = (unsigned) INT_MAX;
-            } else {
-              unsigned part = 0;
-#pragma unroll
-              for (int c = 0; c < 3; c++) {
-                const int hs = c ? A.hs : 0, vs = c ? A.vs : 0;
-                const int sx = x0 >> hs, sy = y0 >> vs, rx = (x0 + dx) >> hs, ry = (y0 + dy) >> vs;
-                const int w = min (max (0, (c ? A.cw : A.width) - sx), A.bw >> hs);
-                const int h = min (max (0, (c ? A.ch : A.height) - sy), A.bh >> vs);
-                for (int p = lane; p < w * h; p += 32) {
-                  const int yy = p / w, xx = p - yy * w;
-                  part += (unsigned) abs ((int) __ldg (sp[c] + (ptrdiff_t) (sy + yy) * ss[c] + sx + xx)
-                      - (int) __ldg (rp[c] + (ptrdiff_t) (ry + yy) * rs[c] + rx + xx));
-                }
-              }
-              metric = warp_sum (part);
-            }
-            if ((int) metric < (int) best_metric) { best_metric = metric; best_k = k; }
-          }
-          if (best_k < 0) best_k = __ffs (cmask) - 1;    // every candidate invalid: the reference asserts
         }
+        unsigned m = part_sad + __shfl_down_sync (0xffffffffu, part_sad, 1);
+        m += __shfl_down_sync (0xffffffffu, part_sad, 2);
+        return ok ? m : (unsigned) INT_MAX;
+      };
+      if (full) {
+        const int kdx = __shfl_sync (0xffffffffu, cdx, min (ck, 5)), kdy = __shfl_sync (0xffffffffu, cdy, min (ck, 5));
+        const bool kval = __shfl_sync (0xffffffffu, (int) valid, min (ck, 5)) != 0;
+        const unsigned m = cand_sad (kdx, kdy, ck < 6 && kval);
+        if (ck < 6) metric = m;
+      }
 
-        // ---- seed + scan window (schrohierbm.c:349-364, schrometric.c:174-214) --------
-        int dx = __shfl_sync (0xffffffffu, cdx, best_k) >> s;
-        int dy = __shfl_sync (0xffffffffu, cdy, best_k) >> s;
-        dx = max (-bw0 - x0, min (A.width - x0, dx));
-        dy = max (-bh0 - y0, min (A.height - y0, dy));
-        if (lane == 0) {
-          const int xmin = max (max (-bw0, x0 + dx - A.h_range), -e);
-          const int ymin = max (max (-bh0, y0 + dy - A.h_range), -e);
-          const int xmax = min (min (A.width, x0 + dx + A.h_range), A.width - bw0 + e);
-          const int ymax = min (min (A.height, y0 + dy + A.h_range), A.height - bh0 + e);
-          sh.xmin = xmin; sh.ymin = ymin;
-          sh.scan_w = xmax - xmin + 1; sh.scan_h = ymax - ymin + 1;
-          sh.seed_a = dx + x0 - xmin; sh.seed_b = dy + y0 - ymin;
+      // ---- phase B: 6: left 7: up 8: up-left of THIS level (schrohierbm.c:279-294).
+      // left comes from this CTA's previous block; up / up-left are polled straight out of
+      // the row above's published words (up-left was published before up)
+      if (lane == 6 && i > 0) {
+        cdx = sh.last_dx; cdy = sh.last_dy; valid = true;
+      } else if ((lane == 7 || (lane == 8 && i > 0)) && words_up) {
+        const unsigned long long *wp = words_up + bi - (lane == 8 ? 1 : 0);
+        unsigned long long wv;
+        do { wv = ld_word (wp); } while (!(wv >> 63));
+        cdx = (int) (short) (wv >> 16); cdy = (int) (short) wv; valid = true;
+      }
+      __syncwarp ();
+      // de-duplicate keeping the LAST occurrence (schrohierbm.c:298-321): a candidate is
+      // dropped when a later lane holds the same vector
+      const bool isc = valid && lane < 9;
+      const unsigned long long mkey = isc
+          ? ((1ull << 32) | ((unsigned long long) (cdx & 0xffff) << 16) | (unsigned long long) (cdy & 0xffff))
+          : ((unsigned long long) (2 + lane) << 32);
+      const unsigned same = __match_any_sync (0xffffffffu, mkey);
+      const bool dup = isc && (same >> (lane + 1)) != 0;
+      const unsigned cmask = __ballot_sync (0xffffffffu, isc && !dup);
+
+      // ---- rank candidates with the 3-component SAD (schrometric.c:332-375) --------
+      int best_k;
+      if (full) {
+        const int kdx = __shfl_sync (0xffffffffu, cdx, min (ck, 8)), kdy = __shfl_sync (0xffffffffu, cdy, min (ck, 8));
+        const unsigned m = cand_sad (kdx, kdy, ck >= 6 && ck < 9 && ((cmask >> min (ck, 8)) & 1));
+        if (ck >= 6 && ck < 9) metric = m;
+        // first strict minimum in candidate order == min over (metric, k); INT_MAX never wins
+        unsigned key = 0xffffffffu;
+        if (ck < 9 && part == 0 && ((cmask >> ck) & 1) && metric < (unsigned) INT_MAX) key = (metric << 8) | (unsigned) ck;
+        key = __reduce_min_sync (0xffffffffu, key);
+        best_k = key == 0xffffffffu ? __ffs (cmask) - 1 : (int) (key & 0xff);
+      } else {
+        best_k = -1;
+        unsigned best_metric = (unsigned) INT_MAX;
+        for (int k = 0; k < 9; k++) {
+          if (!((cmask >> k) & 1)) continue;
+          int dx = __shfl_sync (0xffffffffu, cdx, k) >> s;
+          int dy = __shfl_sync (0xffffffffu, cdy, k) >> s;
+          dx = clampi (dx + x0, -bw0, A.width) - x0;
+          dy = clampi (dy + y0, -bh0, A.height) - y0;
+          unsigned m;
+          const bool ok = !(x0 < -e || y0 < -e || x0 + A.bw > A.width + e || y0 + A.bh > A.height + e) &&
+              !(x0 + dx < -e || y0 + dy < -e || x0 + dx + A.bw > A.width + e || y0 + dy + A.bh > A.height + e);
+          if (!ok) {
+            m = (unsigned) INT_MAX;
+          } else {
+            unsigned part_sum = 0;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              const int hs = c ? A.hs : 0, vs = c ? A.vs : 0;
+              const int sx = x0 >> hs, sy = y0 >> vs, rx = (x0 + dx) >> hs, ry = (y0 + dy) >> vs;
+              const int w = min (max (0, (c ? A.cw : A.width) - sx), A.bw >> hs);
+              const int h = min (max (0, (c ? A.ch : A.height) - sy), A.bh >> vs);
+              for (int p = lane; p < w * h; p += 32) {
+                const int yy = p / w, xx = p - yy * w;
+                part_sum += (unsigned) abs ((int) __ldg (sp[c] + (ptrdiff_t) (sy + yy) * ss[c] + sx + xx)
+                    - (int) __ldg (rp[c] + (ptrdiff_t) (ry + yy) * rs[c] + rx + xx));
+              }
+            }
+            m = warp_sum (part_sum);
+          }
+          if ((int) m < (int) best_metric) { best_metric = m; best_k = k; }
         }
+        if (best_k < 0) best_k = __ffs (cmask) - 1;    // every candidate invalid: the reference asserts
+      }
+
+      // ---- seed + scan window (schrohierbm.c:349-364, schrometric.c:174-214) --------
+      int dx = __shfl_sync (0xffffffffu, cdx, best_k) >> s;
+      int dy = __shfl_sync (0xffffffffu, cdy, best_k) >> s;
+      dx = max (-bw0 - x0, min (A.width - x0, dx));
+      dy = max (-bh0 - y0, min (A.height - y0, dy));
+      if (lane == 0) {
+        const int xmin = max (max (-bw0, x0 + dx - A.h_range), -e);
+        const int ymin = max (max (-bh0, y0 + dy - A.h_range), -e);
+        const int xmax = min (min (A.width, x0 + dx + A.h_range), A.width - bw0 + e);
+        const int ymax = min (min (A.height, y0 + dy + A.h_range), A.height - bh0 + e);
+        sh.xmin = xmin; sh.ymin = ymin;
+        sh.scan_w = xmax - xmin + 1; sh.scan_h = ymax - ymin + 1;
+        sh.seed_a = dx + x0 - xmin; sh.seed_b = dy + y0 - ymin;
       }
     }
     if (NW > 1) __syncthreads (); else __syncwarp ();
@@ -362,7 +379,11 @@ hbm_level_kernel (const HbmArgs A)
         const unsigned long long key = ((unsigned long long) tot << 32) | (notseed << 24) | ((unsigned) a << 12) | (unsigned) b;
         if (key < best_key) { best_key = key; best_l = l; best_c = c; }
       }
-      const unsigned long long wkey = warp_min64 (best_key);
+      // min over (tot, low bits): two 32-bit REDUX instead of a 64-bit shuffle tree
+      const unsigned khi = (unsigned) (best_key >> 32), klo = (unsigned) best_key;
+      const unsigned mhi = __reduce_min_sync (0xffffffffu, khi);
+      const unsigned mlo = __reduce_min_sync (0xffffffffu, khi == mhi ? klo : 0xffffffffu);
+      const unsigned long long wkey = ((unsigned long long) mhi << 32) | mlo;
       const unsigned owner = __ballot_sync (0xffffffffu, best_key == wkey);
       const int ol = __ffs (owner) - 1;
       best_l = __shfl_sync (0xffffffffu, best_l, ol);
@@ -380,16 +401,22 @@ hbm_level_kernel (const HbmArgs A)
             if (sh.key[w] < k) { k = sh.key[w]; bl = sh.luma[w]; bc = sh.chroma[w]; }
         }
         const int a = (int) ((k >> 12) & 0xfff), b = (int) (k & 0xfff);
+        const int rdx = (xmin + a - x0) << s, rdy = (ymin + b - y0) << s;
+        // publish first (the row below is waiting on it), then fill in the output field
+        st_word (words_me + bi, pack_word ((int16_t) rdx, (int16_t) rdy));
+        sh.last_dx = (int16_t) rdx; sh.last_dy = (int16_t) rdy;
         MotionVector *o = mf + (size_t) j * A.nbx + i;
         o->metric = bl;
         o->chroma_metric = bc;
-        o->v[ri] = (int16_t) ((xmin + a - x0) << s);
-        o->v[2 + ri] = (int16_t) ((ymin + b - y0) << s);
+        o->v[ri] = (int16_t) rdx;
+        o->v[2 + ri] = (int16_t) rdy;
         o->flags = A.flags0;
       }
+    } else if (threadIdx.x == 0) {
+      // a block outside the picture keeps the zero vector of schro_motion_field_set
+      st_word (words_me + bi, pack_word (0, 0));
+      sh.last_dx = 0; sh.last_dy = 0;
     }
-    // ---- publish (release orders the vector store of thread 0 before the counter)
-    if (threadIdx.x == 0) st_release (prog_me, bi + 1);
     if (NW > 1) __syncthreads (); else __syncwarp ();
   }
 }
@@ -486,9 +513,10 @@ sb2_sad_u8 (const uint8_t *a, int a_stride, const uint8_t *b, int b_stride, cons
 }
 
 extern "C" size_t
-sb2_hbm_workspace_bytes (int y_num_blocks, int count)
+sb2_hbm_workspace_bytes (int x_num_blocks, int y_num_blocks, int count)
 {
-  return (size_t) y_num_blocks * (size_t) count * sizeof (int) + 256;
+  // one published word per block of the finest level (coarser levels use a prefix)
+  return (size_t) y_num_blocks * (size_t) x_num_blocks * (size_t) count * sizeof (unsigned long long) + 256;
 }
 
 extern "C" int
@@ -533,13 +561,13 @@ sb2_hbm_scan_hint (const sb2_hbm_params *p, const sb2_slab *src_level, const sb2
   A.count = count;
   const int split = shift > 1 ? 0 : (shift == 1 ? 1 : 2);
   A.flags0 = (uint32_t) (p->ref_index + 1) | ((uint32_t) split << 3);
-  const size_t need = (size_t) A.rows * count * sizeof (int);
+  const size_t need = (size_t) A.rows * A.cols * count * sizeof (unsigned long long);
   if (!workspace || workspace_bytes < need)
     return set_error (SB2_ERR_WORKSPACE, "sb2_hbm_scan_hint: workspace %zu < %zu", workspace_bytes, need);
-  A.progress = static_cast<int *> (workspace);
+  A.words = static_cast<unsigned long long *> (workspace);
   cudaStream_t st = as_stream (stream);
   cudaError_t e = cudaMemsetAsync (workspace, 0, need, st);
-  if (e != cudaSuccess) return check_cuda (e, "cudaMemsetAsync(progress)");
+  if (e != cudaSuccess) return check_cuda (e, "cudaMemsetAsync(words)");
   const size_t nfield = (size_t) A.nbx * A.nby;
   for (int pic = 0; pic < count; pic++) {
     // fields of different pictures may be field_picture_pitch apart: init each

@@ -274,7 +274,7 @@ def hbm_scan_hint(params, src_level, ref_level, shift, h_range, parent, out, wor
     require_cuda()
     n = params.x_num_blocks * params.y_num_blocks
     ws = workspace or _default_ws
-    need = lib.sb2_hbm_workspace_bytes(params.y_num_blocks, src_level.count)
+    need = lib.sb2_hbm_workspace_bytes(params.x_num_blocks, params.y_num_blocks, src_level.count)
     ptr, size = ws.get(need)
     check(lib.sb2_hbm_scan_hint(
         ctypes.byref(params), ctypes.byref(src_level.slab), ctypes.byref(ref_level.slab),

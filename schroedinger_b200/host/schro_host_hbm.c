@@ -157,7 +157,7 @@ schro_hierarchical_bm_scan_hint (SchroHierBm *hbm, int shift, int h_range)
   p.chroma_h_shift = SCHRO_FRAME_FORMAT_H_SHIFT (fs->format);
   p.chroma_v_shift = SCHRO_FRAME_FORMAT_V_SHIFT (fs->format);
   if (!h->dev_ws) {
-    h->ws_bytes = sb2_hbm_workspace_bytes (params->y_num_blocks, 1);
+    h->ws_bytes = sb2_hbm_workspace_bytes (params->x_num_blocks, params->y_num_blocks, 1);
     h->dev_ws = sb2h_pool_alloc (h->ws_bytes);
   }
   if (!h->dev_field[shift])
@@ -165,8 +165,12 @@ schro_hierarchical_bm_scan_hint (SchroHierBm *hbm, int shift, int h_range)
   SB2H_CHECK (sb2_hbm_scan_hint (&p, &ss, &rs, fs->extension, shift, h_range,
           shift < hbm->hierarchy_levels ? h->dev_field[shift + 1] : NULL, h->dev_field[shift], n,
           h->dev_ws, h->ws_bytes, cx->stream), "sb2_hbm_scan_hint");
-  /* schro_hbm_set_motion_field: a new field replaces the level's previous one */
-  mf = schro_motion_field_new (params->x_num_blocks, params->y_num_blocks);
+  /* schro_hbm_set_motion_field: a new field replaces the level's previous one (every entry
+   * is overwritten by the copy below, so no zero-fill) */
+  mf = malloc (sizeof (SchroMotionField));
+  mf->x_num_blocks = params->x_num_blocks;
+  mf->y_num_blocks = params->y_num_blocks;
+  mf->motion_vectors = malloc (n * sizeof (SchroMotionVector));
   SB2H_CUDA (cudaMemcpyAsync (mf->motion_vectors, h->dev_field[shift], n * sizeof (SchroMotionVector),
           cudaMemcpyDefault, cx->stream));
   SB2H_CUDA (cudaStreamSynchronize (cx->stream));

@@ -149,11 +149,64 @@ schro_wavelet_inverse_transform_2d (SchroFrameData *fd_dest, SchroFrameData *fd_
   run_planes (&ps, &pd, depth_is_s32 (fd_dest->format), filter, 1, 1);
 }
 
+/* CUDA-domain frame whose planes are exactly the transform area: transform out of place into
+ * a fresh region from the same domain and swap the regions -- "in place" for the caller, no
+ * staging copy and no copy back on the device. */
+static int
+frame_iwt_swap (SchroFrame *frame, SchroParams *params, int inverse)
+{
+  Sb2hContext *cx = sb2h_context ();
+  const int is_s32 = SCHRO_FRAME_FORMAT_DEPTH (frame->format) == SCHRO_FRAME_FORMAT_DEPTH_S32;
+  sb2_slab sin, sout;
+  size_t total = 0, ws_bytes;
+  char *old_region = frame->regions[0], *new_region;
+  void *ws;
+  int k, rc;
+
+  if (!frame->domain || !old_region || frame->extension != 0 || frame->is_upsampled) return 0;
+  if (sb2h_mem_kind (old_region) != SB2H_MEM_DEVICE) return 0;
+  for (k = 0; k < 3; k++) {
+    const SchroFrameData *c = &frame->components[k];
+    if (c->width != (k ? params->iwt_chroma_width : params->iwt_luma_width) ||
+        c->height != (k ? params->iwt_chroma_height : params->iwt_luma_height))
+      return 0;
+    total += (size_t) c->length;
+  }
+  memset (&sin, 0, sizeof (sin));
+  sin.base = old_region;
+  sin.picture_pitch = total;
+  sin.count = 1;
+  sin.ncomp = 3;
+  for (k = 0; k < 3; k++) {
+    sin.offset[k] = (size_t) ((char *) frame->components[k].data - old_region);
+    sin.stride[k] = frame->components[k].stride;
+    sin.width[k] = frame->components[k].width;
+    sin.height[k] = frame->components[k].height;
+  }
+  new_region = schro_memory_domain_alloc (frame->domain, (int) total);
+  sout = sin;
+  sout.base = new_region;
+  ws_bytes = sb2_iwt_workspace_bytes (&sin, is_s32, params->transform_depth, 0);
+  ws = sb2h_dev_buffer (cx, SB2H_BUF_WS, ws_bytes);
+  rc = inverse ? sb2_iwt_inverse (&sin, &sout, is_s32, params->wavelet_filter_index, params->transform_depth,
+                     ws, ws_bytes, cx->stream)
+               : sb2_iwt_forward (&sin, &sout, is_s32, params->wavelet_filter_index, params->transform_depth,
+                     ws, ws_bytes, cx->stream);
+  SB2H_CHECK (rc, inverse ? "sb2_iwt_inverse" : "sb2_iwt_forward");
+  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  for (k = 0; k < 3; k++)
+    frame->components[k].data = new_region + sin.offset[k];
+  frame->regions[0] = new_region;
+  schro_memory_domain_memfree (frame->domain, old_region);
+  return 1;
+}
+
 static void
 frame_iwt (SchroFrame *frame, SchroParams *params, int inverse)
 {
   PlaneList pl;
   int k;
+  if (frame_iwt_swap (frame, params, inverse)) return;
   pl.ncomp = 3;
   for (k = 0; k < 3; k++) {
     pl.data[k] = frame->components[k].data;
