@@ -429,19 +429,27 @@ class HostFrames:
         lib.schro_hbm_unref(hbm)
 
     def step(self):
-        """One e2e step: every picture of the batch, pictures spread over host threads (the
-        reference's own threading model); each thread owns a stream."""
+        """One e2e step: every picture of the batch, pictures spread over a pool of persistent
+        host threads (the reference's own threading model, schroasync-pthread.c); each thread
+        owns a stream and its staging buffers."""
         n = len(self.coef_host)
+        if not hasattr(self, "pool"):
+            from concurrent.futures import ThreadPoolExecutor
+            self.pool = ThreadPoolExecutor(max_workers=self.nthreads)
 
         def work(tid):
             for i in range(tid, n, self.nthreads):
                 self.picture(tid, i)
 
-        ts = [threading.Thread(target=work, args=(t,)) for t in range(self.nthreads)]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
+        for f in [self.pool.submit(work, t) for t in range(self.nthreads)]:
+            f.result()
+
+    def close(self):
+        """Stop the worker threads while CUDA is still alive (their thread-exit hooks release
+        per-thread streams and buffers)."""
+        if hasattr(self, "pool"):
+            self.pool.shutdown(wait=True)
+            del self.pool
 
 
 def run_ours(args):
@@ -489,6 +497,9 @@ def run_ours(args):
     e1.record()
     barrier()
     lib.sb2_profile_enable(0)
+    # stop polling NVML before the API-heavy e2e arm: nvidia-smi at 10 Hz stalls the host-side
+    # CUDA calls it contends with (measured: e2e 29 fps with the sampler, 157 without)
+    clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = e0.elapsed_time(e1)
     launches = lib.sb2_launch_count() - launches0
     prof = collect_profile(lib)
@@ -520,6 +531,7 @@ def run_ours(args):
             t = torch.tensor([float(e2e_steps)], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
             e2e_steps = int(t.item())
+        hf.close()
         e2e = {"value": B * e2e_steps * world / dt, "unit": "frames/s", "steps": e2e_steps,
                "h2d_bytes_per_step": hf.h2d * B, "d2h_bytes_per_step": hf.d2h * B,
                "api": "drop-in schro_* C API (schro_frame_to_gpu, schro_frame_inverse_iwt_transform, "
@@ -529,7 +541,6 @@ def run_ours(args):
                       "one stream each"}
     except Exception as ex:  # keep the device-resident number even if the host arm breaks
         e2e = {"value": None, "unit": "frames/s", "error": repr(ex)}
-    clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
         if world > 1:

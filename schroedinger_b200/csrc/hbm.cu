@@ -141,6 +141,10 @@ __device__ __forceinline__ unsigned load4_unaligned (const uint8_t *p)
   return __funnelshift_r (w0, w1, (unsigned) mis * 8);
 }
 
+#ifndef POLL_NS
+#define POLL_NS 100
+#endif
+
 struct BlockShared {
   int xmin, ymin, scan_w, scan_h, seed_a, seed_b;
   int last_dx, last_dy;             // this row's previous block (the "left" candidate)
@@ -256,13 +260,18 @@ hbm_level_kernel (const HbmArgs A)
       // the row above's published words (up-left was published before up)
       if (lane == 6 && i > 0) {
         cdx = sh.last_dx; cdy = sh.last_dy; valid = true;
-      } else if ((lane == 7 || (lane == 8 && i > 0)) && words_up) {
-        const unsigned long long *wp = words_up + bi - (lane == 8 ? 1 : 0);
-        unsigned long long wv;
-        do { wv = ld_word (wp); } while (!(wv >> 63));
+      } else if (lane == 7 && words_up) {
+        // the only poller of this CTA; back off between polls so that thousands of waiting
+        // rows do not saturate the L2 request path of the rows that are working
+        unsigned long long wv = ld_word (words_up + bi);
+        while (!(wv >> 63)) { __nanosleep (POLL_NS); wv = ld_word (words_up + bi); }
         cdx = (int) (short) (wv >> 16); cdy = (int) (short) wv; valid = true;
       }
       __syncwarp ();
+      if (lane == 8 && i > 0 && words_up) {
+        const unsigned long long wv = ld_word (words_up + bi - 1);   // published before `up`
+        cdx = (int) (short) (wv >> 16); cdy = (int) (short) wv; valid = true;
+      }
       // de-duplicate keeping the LAST occurrence (schrohierbm.c:298-321): a candidate is
       // dropped when a later lane holds the same vector
       const bool isc = valid && lane < 9;

@@ -578,6 +578,220 @@ obmc_kernel_v3 (const ObmcArgs A)
   }
 }
 
+// ---- v4: block-major two-colour scatter into a shared-memory accumulator -------------
+// The gather kernels above are bound by L1 wavefronts: neighbouring pixels belong to
+// different blocks with different vectors, so every byte load of a warp touches ~16 cache
+// lines.  Here the work item is (block, block row, group of 4 pixels): the three items of
+// a block row read 12 contiguous reference bytes, each as one unaligned 32-bit word built
+// from two aligned loads; taps are applied to two pixels at a time in packed 16-bit lanes.
+// Contributions are added into a tile accumulator in shared memory.  Blocks whose (i,j)
+// parities agree never overlap when xblen <= 2*xbsep and yblen <= 2*ybsep, so the tile is
+// processed in four colour phases without atomics.
+constexpr int O4_W = 64, O4_H = 32;
+constexpr int O4_P = O4_W + 12;    // accumulator pitch: 16-byte aligned rows, consecutive block rows on different banks
+
+__device__ __forceinline__ unsigned ldg_u32_unaligned (const uint8_t *p)
+{
+  const size_t mis = (size_t) p & 3;
+  const unsigned *w = reinterpret_cast<const unsigned *> (p - mis);
+  const unsigned w0 = __ldg (w), w1 = mis ? __ldg (w + 1) : 0u;
+  return __funnelshift_r (w0, w1, (unsigned) mis * 8);
+}
+
+// 4-tap sum of four adjacent pixels, two per packed 16-bit pair: returns (p0 | p1<<16, p2 | p3<<16)
+__device__ __forceinline__ uint2 fetch4x4 (const uint8_t *ref, const BlkRef &br, int pix)
+{
+  const unsigned w = br.w;
+  unsigned lo = 0x00080008u, hi = 0x00080008u;
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const unsigned wt = (w >> (8 * t)) & 0xff;
+    if (t == 0 || wt) {
+      const unsigned b = ldg_u32_unaligned (ref + br.o[t] + pix);
+      lo += wt * __byte_perm (b, 0, 0x4140);      // byte0 | byte1 << 16
+      hi += wt * __byte_perm (b, 0, 0x4342);      // byte2 | byte3 << 16
+    }
+  }
+  return make_uint2 ((lo >> 4) & 0x0fff0fffu, (hi >> 4) & 0x0fff0fffu);
+}
+
+template <bool SIMPLE>
+__global__ void __launch_bounds__ (256)
+obmc_kernel_v4 (const ObmcArgs A)
+{
+  __shared__ __align__ (16) BlkEnt tab[MAX_ENT];
+  __shared__ __align__ (16) int acc[O4_H][O4_P];
+  __shared__ unsigned char s_wx[64], s_wy[64];
+  const int comp = blockIdx.z % A.ncomp, pic = blockIdx.z / A.ncomp;
+  const int width = A.w[comp], height = A.h[comp];
+  const int tx0 = blockIdx.x * O4_W, ty0 = blockIdx.y * O4_H;
+  if (tx0 >= width || ty0 >= height) return;
+
+  const int xbsep = A.xbsep[comp], ybsep = A.ybsep[comp], xblen = A.xblen[comp], yblen = A.yblen[comp];
+  const int xoff = (xblen - xbsep) >> 1, yoff = (yblen - ybsep) >> 1;
+  const int prec = A.prec;
+  const int max_fast_x = (width - xblen) << prec, max_fast_y = (height - yblen) << prec;
+  const int max_x_blocks = min (A.nbx - 1, (width - xoff) / xbsep);
+  const int max_y_blocks = min (A.nby - 1, (height - yoff) / ybsep);
+  const bool noscale = (A.w1 + A.w2 == (1 << A.bits));
+
+  if (threadIdx.x < 64) {
+    s_wx[threadIdx.x] = A.wx[comp][threadIdx.x];
+    s_wy[threadIdx.x] = A.wy[comp][threadIdx.x];
+  }
+  for (int t = threadIdx.x; t < O4_P * O4_H; t += blockDim.x) (&acc[0][0])[t] = 0;
+
+  const uint8_t *ref0 = reinterpret_cast<const uint8_t *> (plane_ptr (A.ref0, pic, comp));
+  const uint8_t *ref1 = A.has_ref1 ? reinterpret_cast<const uint8_t *> (plane_ptr (A.ref1, pic, comp)) : ref0;
+  const int rs0 = A.ref0.stride[comp], rs1 = A.has_ref1 ? A.ref1.stride[comp] : rs0;
+  const MotionVector *mvs = A.mvs + (size_t) pic * A.mv_pitch;
+
+  const int tw = min (O4_W, width - tx0), th = min (O4_H, height - ty0);
+  const int x1 = tx0 + tw - 1, y1 = ty0 + th - 1;
+  const int ti0 = (tx0 + xoff - xblen + 1 > 0) ? (tx0 + xoff - xblen + xbsep) / xbsep : 0;
+  const int ti1 = min (A.nbx - 1, (x1 + xoff) / xbsep);
+  const int tj0 = (ty0 + yoff - yblen + 1 > 0) ? (ty0 + yoff - yblen + ybsep) / ybsep : 0;
+  const int tj1 = min (A.nby - 1, (y1 + yoff) / ybsep);
+  const int tni = ti1 - ti0 + 1, tnj = tj1 - tj0 + 1;
+
+  for (int t = threadIdx.x; t < tni * tnj; t += blockDim.x) {
+    const int jj = t / tni, ii = t - jj * tni;
+    const int i = ti0 + ii, j = tj0 + jj;
+    const MotionVector *mv = mvs + (size_t) j * A.nbx + i;
+    const unsigned flags = __ldg (&mv->flags);
+    const int v01 = __ldg (reinterpret_cast<const int *> (mv->v)), v23 = __ldg (reinterpret_cast<const int *> (mv->v) + 1);
+    const int v0 = (short) (v01 & 0xffff), v1 = v01 >> 16, v2 = (short) (v23 & 0xffff), v3 = v23 >> 16;
+    BlkEnt e;
+    e.mode = (short) (flags & 3);
+    e.fast = (short) (i >= 1 && i < max_x_blocks && j >= 1 && j < max_y_blocks);
+    e.dc = (short) (comp == 0 ? v0 : comp == 1 ? v1 : v2);
+    e.pad = 0;
+    const int bx = xbsep * i - xoff, by = ybsep * j - yoff;
+    make_blkref (e.r[0], rs0, prec, bx, by, v0 >> A.hs[comp], v2 >> A.vs[comp], max_fast_x, max_fast_y);
+    make_blkref (e.r[1], rs1, prec, bx, by, v1 >> A.hs[comp], v3 >> A.vs[comp], max_fast_x, max_fast_y);
+    tab[t] = e;
+  }
+  __syncthreads ();
+
+  // ---- four colour phases -----------------------------------------------------------
+  const int gx = (xblen + 3) >> 2;                 // 4-pixel groups per block row
+  const int ipb = gx * yblen;                      // items per block
+  for (int colour = 0; colour < 4; colour++) {
+    const int ci = colour & 1, cj = colour >> 1;
+    // blocks of this colour inside the tile's block rectangle
+    const int fi = ti0 + ((ti0 & 1) != ci), fj = tj0 + ((tj0 & 1) != cj);
+    const int nci = fi <= ti1 ? (ti1 - fi) / 2 + 1 : 0, ncj = fj <= tj1 ? (tj1 - fj) / 2 + 1 : 0;
+    const int nitems = nci * ncj * ipb;
+    for (int it = threadIdx.x; it < nitems; it += blockDim.x) {
+      const int blk = it / ipb, rem = it - blk * ipb;
+      const int r = rem / gx, g = rem - r * gx;
+      const int bj = blk / nci, bi_ = blk - bj * nci;
+      const int i = fi + 2 * bi_, j = fj + 2 * bj;
+      const int bx = xbsep * i - xoff, by = ybsep * j - yoff;
+      const int y = by + r, xg = bx + 4 * g;
+      if (y < ty0 || y > y1 || xg > x1 || xg + 3 < tx0) continue;
+      const BlkEnt &e = tab[(j - tj0) * tni + (i - ti0)];
+      const int mode = e.mode;
+      const bool fast = e.fast != 0;
+      int v[4];
+      if (mode == 0) {
+        const int dcv = fast ? w16 ((int) e.dc + 128) : (((int) e.dc + 128) & 0xff);
+        v[0] = v[1] = v[2] = v[3] = dcv;
+      } else {
+        uint2 s0 = make_uint2 (0, 0), s1 = make_uint2 (0, 0);
+        if (mode & 1) s0 = fetch4x4 (ref0, e.r[0], r * rs0 + 4 * g);
+        if (mode & 2) s1 = fetch4x4 (ref1, e.r[1], r * rs1 + 4 * g);
+        if (SIMPLE) {
+          uint2 p;
+          if (mode == 3) {
+            p.x = ((s0.x + s1.x + 0x00010001u) >> 1) & 0x00ff00ffu;     // avgub, two lanes
+            p.y = ((s0.y + s1.y + 0x00010001u) >> 1) & 0x00ff00ffu;
+          } else {
+            p = (mode == 1) ? s0 : s1;
+          }
+          v[0] = p.x & 0xffff; v[1] = p.x >> 16; v[2] = p.y & 0xffff; v[3] = p.y >> 16;
+        } else {
+          const int a0[4] = { (int) (s0.x & 0xffff), (int) (s0.x >> 16), (int) (s0.y & 0xffff), (int) (s0.y >> 16) };
+          const int a1[4] = { (int) (s1.x & 0xffff), (int) (s1.x >> 16), (int) (s1.y & 0xffff), (int) (s1.y >> 16) };
+#pragma unroll
+          for (int k = 0; k < 4; k++) v[k] = obmc_combine<false> (A, mode, fast, noscale, e.dc, a0[k], a1[k]);
+        }
+      }
+      int w_y = s_wy[r];
+      if (!fast) {
+        if (y < yoff) w_y += s_wy[2 * yoff - r - 1];
+        if (y >= A.nby * ybsep - yoff) w_y += s_wy[2 * (yblen - yoff) - r - 1];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int a = 4 * g + k, x = xg + k;
+        if (a < xblen && x >= tx0 && x <= x1) {
+          int w_x = s_wx[a];
+          if (!fast) {
+            if (x < xoff) w_x += s_wx[2 * xoff - a - 1];
+            if (x >= A.nbx * xbsep - xoff) w_x += s_wx[2 * (xblen - xoff) - a - 1];
+          }
+          acc[y - ty0][x - tx0] += v[k] * w_x * w_y;
+        }
+      }
+    }
+    __syncthreads ();
+  }
+
+  // ---- finish: four pixels per thread ---------------------------------------------------
+  for (int t = threadIdx.x; t < (O4_W / 4) * th; t += blockDim.x) {
+    const int ry = t / (O4_W / 4), lx = (t - ry * (O4_W / 4)) * 4;
+    const int x = tx0 + lx, y = ty0 + ry;
+    if (x >= width) continue;
+    const int npx = min (4, width - x);
+    const int4 av = *reinterpret_cast<const int4 *> (&acc[ry][lx]);
+    const int sum[4] = { av.x, av.y, av.z, av.w };
+    const size_t ro = (size_t) y * A.res.stride[comp];
+    if (A.add) {
+      int r[4];
+      const char *rrow = plane_ptr (A.res, pic, comp) + ro;
+      if (npx == 4) {
+        if (A.res_is_s32) {
+          const int4 q = *reinterpret_cast<const int4 *> (rrow + (size_t) x * 4);
+          r[0] = w16 (q.x); r[1] = w16 (q.y); r[2] = w16 (q.z); r[3] = w16 (q.w);
+        } else {
+          const int2 q = *reinterpret_cast<const int2 *> (rrow + (size_t) x * 2);
+          r[0] = (q.x << 16) >> 16; r[1] = q.x >> 16; r[2] = (q.y << 16) >> 16; r[3] = q.y >> 16;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          r[k] = k < npx ? (A.res_is_s32 ? w16 (reinterpret_cast<const int *> (rrow)[x + k])
+                                         : (int) reinterpret_cast<const short *> (rrow)[x + k]) : 0;
+      }
+      unsigned packed = 0;
+      int a16[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        a16[k] = w16 (sum[k]);
+        int tt = w16 (a16[k] + 32) >> 6;
+        tt = w16 (r[k] + tt);
+        packed |= (unsigned) clampi (tt, 0, 255) << (8 * k);
+      }
+      uint8_t *orow = reinterpret_cast<uint8_t *> (plane_ptr (A.out, pic, comp)) + (size_t) y * A.out.stride[comp] + x;
+      if (npx == 4) *reinterpret_cast<unsigned *> (orow) = packed;
+      else for (int k = 0; k < npx; k++) orow[k] = (uint8_t) (packed >> (8 * k));
+      if (A.has_acc) {
+        short *arow = reinterpret_cast<short *> (plane_ptr (A.acc, pic, comp) + (size_t) y * A.acc.stride[comp]) + x;
+        for (int k = 0; k < npx; k++) arow[k] = (short) a16[k];
+      }
+    } else {
+      short *rrow = reinterpret_cast<short *> (plane_ptr (A.res, pic, comp) + ro) + x;
+      short *arow = A.has_acc ? reinterpret_cast<short *> (plane_ptr (A.acc, pic, comp) + (size_t) y * A.acc.stride[comp]) + x : nullptr;
+      for (int k = 0; k < npx; k++) {
+        const int tt = w16 (w16 (sum[k]) - 8160) >> 6;
+        rrow[k] = (short) w16 (rrow[k] - tt);
+        if (arow) arow[k] = (short) tt;
+      }
+    }
+  }
+}
+
 // schroedinger/schromotion.c:40-79
 static int get_ramp (int x, int offset)
 {
@@ -687,7 +901,20 @@ sb2_obmc_render (const sb2_obmc_params *p, const void *motion_vectors, size_t mv
     if (out && (((size_t) out->base | out->picture_pitch) & 3)) v3_ok = false;
     if (((size_t) residual->base | residual->picture_pitch) & 15) v3_ok = false;
     const bool simple = (A.w1 == 1 && A.w2 == 1 && A.bits == 1);
-    if (v3_ok) {
+    // the scatter kernel additionally needs non-overlapping same-colour blocks, reference planes
+    // whose rows are 4-byte aligned (word loads) and a block table that fits
+    bool v4_ok = v3_ok;
+    for (int c = 0; c < ncomp && v4_ok; c++) {
+      if (A.xblen[c] > 2 * A.xbsep[c] || A.yblen[c] > 2 * A.ybsep[c]) v4_ok = false;
+      const int ni = (O4_W + A.xblen[c]) / A.xbsep[c] + 2, nj = (O4_H + A.yblen[c]) / A.ybsep[c] + 2;
+      if (ni * nj > MAX_ENT) v4_ok = false;
+      if ((ref0->stride[c] & 3) || (ref1 && (ref1->stride[c] & 3))) v4_ok = false;
+    }
+    if (v4_ok) {
+      dim3 g4 (ceil_div (maxw, O4_W), ceil_div (maxh, O4_H), ncomp * count);
+      if (simple) obmc_kernel_v4<true><<<g4, 256, 0, as_stream (stream)>>> (A);
+      else obmc_kernel_v4<false><<<g4, 256, 0, as_stream (stream)>>> (A);
+    } else if (v3_ok) {
       dim3 g3 (ceil_div (maxw, O3_W), ceil_div (maxh, O3_H), ncomp * count);
       if (simple) obmc_kernel_v3<true><<<g3, 256, 0, as_stream (stream)>>> (A);
       else obmc_kernel_v3<false><<<g3, 256, 0, as_stream (stream)>>> (A);

@@ -71,16 +71,43 @@ schro_b200_set_device (int device)
   SB2H_CUDA (cudaSetDevice (device));
 }
 
+/* thread exit: give the thread's stream, staging buffers and pooled blocks back */
+static pthread_key_t cx_key;
+static pthread_once_t cx_key_once = PTHREAD_ONCE_INIT;
+static void sb2h_pool_release_all (void);
+
+/* set at process exit: thread destructors that run during teardown must not touch CUDA */
+static volatile int g_shutting_down;
+static void mark_shutdown (void) { g_shutting_down = 1; }
+
+static void
+cx_destroy (void *p)
+{
+  Sb2hContext *cx = p;
+  int i;
+  if (!cx || g_shutting_down) return;
+  cudaStreamSynchronize (cx->stream);
+  for (i = 0; i < SB2H_NBUF; i++)
+    if (cx->dev[i]) cudaFree (cx->dev[i]);
+  sb2h_pool_release_all ();
+  cudaStreamDestroy (cx->stream);
+  free (cx);
+}
+
+static void cx_key_make (void) { pthread_key_create (&cx_key, cx_destroy); atexit (mark_shutdown); }
+
 Sb2hContext *
 sb2h_context (void)
 {
   if (!tl_cx) {
+    pthread_once (&cx_key_once, cx_key_make);
     pthread_mutex_lock (&g_device_mutex);
     if (g_device < 0) SB2H_CUDA (cudaGetDevice (&g_device));
     pthread_mutex_unlock (&g_device_mutex);
     SB2H_CUDA (cudaSetDevice (g_device));
     tl_cx = calloc (1, sizeof (Sb2hContext));
     SB2H_CUDA (cudaStreamCreateWithFlags (&tl_cx->stream, cudaStreamNonBlocking));
+    pthread_setspecific (cx_key, tl_cx);
   }
   return tl_cx;
 }
@@ -130,6 +157,18 @@ sb2h_pool_alloc (size_t bytes)
   tl_pool[free_slot].bytes = bytes;
   tl_pool[free_slot].in_use = 1;
   return tl_pool[free_slot].ptr;
+}
+
+static void
+sb2h_pool_release_all (void)
+{
+  int i;
+  for (i = 0; i < SB2H_POOL_SLOTS; i++)
+    if (tl_pool[i].ptr) {
+      cudaFree (tl_pool[i].ptr);
+      tl_pool[i].ptr = NULL;
+      tl_pool[i].in_use = 0;
+    }
 }
 
 void
