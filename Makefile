@@ -5,7 +5,7 @@ NVCC      ?= nvcc
 CC        ?= gcc
 CUDA_HOME ?= /usr/local/cuda
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Iinclude -Ischroedinger_b200/csrc
+NVFLAGS   := $(ARCH) $(EXTRA_NVFLAGS) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Iinclude -Ischroedinger_b200/csrc
 CFLAGS    := -std=gnu99 -O2 -Wall -fPIC -Iinclude -I$(CUDA_HOME)/include
 
 CU_SRCS   := $(wildcard schroedinger_b200/csrc/*.cu)

@@ -141,11 +141,27 @@ __device__ __forceinline__ unsigned load4_unaligned (const uint8_t *p)
   return __funnelshift_r (w0, w1, (unsigned) mis * 8);
 }
 
+#ifdef SB2_HBM_TRACE
+__device__ long long g_hbm_trace[512 * 8];
+#define TRACE(k) do { if (trace_on && threadIdx.x == 0 && bi < 512) g_hbm_trace[bi * 8 + (k)] = clock64 (); } while (0)
+#else
+#define TRACE(k) do { } while (0)
+#endif
+
 #ifndef POLL_NS
 #define POLL_NS 100
 #endif
 
+// candidates that do not depend on this level's neighbours, prepared one block ahead
+struct StaticCands {
+  int dx[6], dy[6];
+  unsigned metric[6];
+  unsigned valid;
+  int full;
+};
+
 struct BlockShared {
+  StaticCands stc[2];
   int xmin, ymin, scan_w, scan_h, seed_a, seed_b;
   int last_dx, last_dy;             // this row's previous block (the "left" candidate)
   unsigned long long key[16];
@@ -187,91 +203,116 @@ hbm_level_kernel (const HbmArgs A)
       ((((size_t) sp[0] | (size_t) ss[0]) & 7) == 0) && ((((size_t) sp[1] | (size_t) sp[2] | (size_t) ss[1] | (size_t) ss[2]) & 3) == 0) &&
       ((((size_t) rp[0] | (size_t) rp[1] | (size_t) rp[2] | (size_t) rs[0] | (size_t) rs[1] | (size_t) rs[2]) & 3) == 0);
 
+  // ranking SAD of one candidate vector for the block at (x0, y0): three lanes per candidate
+  // (luma rows 0-3, luma rows 4-7, both chroma blocks), result in the first of the three
+  auto cand_sad = [&] (int x0, int bw0, int bh0, int part, int kdx, int kdy, bool want) -> unsigned {
+    int dx = kdx >> s, dy = kdy >> s;
+    dx = clampi (dx + x0, -bw0, A.width) - x0;
+    dy = clampi (dy + y0, -bh0, A.height) - y0;
+    const bool ok = !(x0 < -e || y0 < -e || x0 + 8 > A.width + e || y0 + 8 > A.height + e) &&
+        !(x0 + dx < -e || y0 + dy < -e || x0 + dx + 8 > A.width + e || y0 + dy + 8 > A.height + e);
+    unsigned part_sad = 0;
+    if (ok && want) {
+      if (part < 2) {
+        const uint8_t *a = sp[0] + (ptrdiff_t) (y0 + 4 * part) * ss[0] + x0;
+        const uint8_t *b = rp[0] + (ptrdiff_t) (y0 + dy + 4 * part) * rs[0] + x0 + dx;
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+          const uint2 av = __ldg (reinterpret_cast<const uint2 *> (a + (ptrdiff_t) y * ss[0]));
+          const uint2 bv = load8_unaligned (b + (ptrdiff_t) y * rs[0]);
+          part_sad += __vsadu4 (av.x, bv.x) + __vsadu4 (av.y, bv.y);
+        }
+      } else {
+        const int sx = x0 >> 1, sy = y0 >> 1, rx = (x0 + dx) >> 1, ry = (y0 + dy) >> 1;
+#pragma unroll
+        for (int c = 1; c < 3; c++) {
+#pragma unroll
+          for (int y = 0; y < 4; y++) {
+            const unsigned av = __ldg (reinterpret_cast<const unsigned *> (sp[c] + (ptrdiff_t) (sy + y) * ss[c] + sx));
+            const unsigned bv = load4_unaligned (rp[c] + (ptrdiff_t) (ry + y) * rs[c] + rx);
+            part_sad += __vsadu4 (av, bv);
+          }
+        }
+      }
+    }
+    unsigned m = part_sad + __shfl_down_sync (0xffffffffu, part_sad, 1);
+    m += __shfl_down_sync (0xffffffffu, part_sad, 2);
+    return ok ? m : (unsigned) INT_MAX;
+  };
+  // static candidates of block `nb` into sh.stc[nb & 1]; executed by one whole warp
+  auto do_static = [&] (int nb) {
+    const int i = nb * skip;
+    const int x0 = (i * A.bw) >> s;
+    if (!(x0 < A.width && y0 < A.height)) return;
+    const int bw0 = min (A.width - x0, A.bw), bh0 = min (A.height - y0, A.bh);
+    int cdx = 0, cdy = 0;
+    bool valid = false;
+    if (lane == 0) valid = true;
+    else if (lane <= 5 && pf) {
+      const int ox = (lane == 2) ? -1 : (lane == 3) ? 1 : 0;
+      const int oy = (lane == 4) ? -1 : (lane == 5) ? 1 : 0;
+      const int ll = (i & hint_mask) + ox * skip * 2, kk = (j & hint_mask) + oy * skip * 2;
+      if (ll >= 0 && ll < A.nbx && kk >= 0 && kk < A.nby) {
+        const MotionVector *m = pf + (size_t) kk * A.nbx + ll;
+        cdx = m->v[ri]; cdy = m->v[2 + ri]; valid = true;
+      }
+    }
+    const bool full = simd_ok && x0 + 8 <= A.width && y0 + 8 <= A.height &&
+        (x0 >> 1) + 4 <= A.cw && (y0 >> 1) + 4 <= A.ch;
+    const int ck = lane / 3, part = lane - 3 * ck;
+    StaticCands &sc = sh.stc[nb & 1];
+    if (full) {
+      const int kdx = __shfl_sync (0xffffffffu, cdx, min (ck, 5)), kdy = __shfl_sync (0xffffffffu, cdy, min (ck, 5));
+      const bool kval = __shfl_sync (0xffffffffu, (int) valid, min (ck, 5)) != 0;
+      const unsigned m = cand_sad (x0, bw0, bh0, part, kdx, kdy, ck < 6 && kval);
+      if (ck < 6 && part == 0) sc.metric[ck] = m;
+    }
+    const unsigned vm = __ballot_sync (0xffffffffu, valid && lane < 6);
+    if (lane < 6) { sc.dx[lane] = cdx; sc.dy[lane] = cdy; }
+    if (lane == 0) { sc.valid = vm; sc.full = full; }
+  };
+  static_assert (NW >= 2, "one warp prepares the static candidates of the next block");
+  if (warp == 1) do_static (0);
+  __syncthreads ();
+
+#ifdef SB2_HBM_TRACE
+  const bool trace_on = (A.shift == 0 && row == 100 && pic == 0);
+#endif
   for (int bi = 0; bi < A.cols; bi++) {
+    TRACE (0);
     const int i = bi * skip;
     const int x0 = (i * A.bw) >> s;
     const bool active = x0 < A.width && y0 < A.height;
     const int bw0 = min (A.width - x0, A.bw), bh0 = min (A.height - y0, A.bh);
 
+    // ---- warp 1 runs one block ahead: static candidates of block bi+1 (zero + five parents,
+    // schrohierbm.c:259-277, and their ranking SADs) while warp 0 waits for / ranks block bi
+    if (warp == 1 && bi + 1 < A.cols) do_static (bi + 1);
+
     if (warp == 0 && active) {
-      // ---- phase A, before the wavefront dependency: candidates that do not depend on this
-      // level's neighbours -- 0: zero, 1..5: parents (0,0) (-1,0) (1,0) (0,-1) (0,1)
-      // (schrohierbm.c:259-277) -- and their ranking SADs
+      const StaticCands &sc = sh.stc[bi & 1];
       int cdx = 0, cdy = 0;
       bool valid = false;
-      if (lane == 0) valid = true;
-      else if (lane <= 5 && pf) {
-        const int ox = (lane == 2) ? -1 : (lane == 3) ? 1 : 0;
-        const int oy = (lane == 4) ? -1 : (lane == 5) ? 1 : 0;
-        const int ll = (i & hint_mask) + ox * skip * 2, kk = (j & hint_mask) + oy * skip * 2;
-        if (ll >= 0 && ll < A.nbx && kk >= 0 && kk < A.nby) {
-          const MotionVector *m = pf + (size_t) kk * A.nbx + ll;
-          cdx = m->v[ri]; cdy = m->v[2 + ri]; valid = true;
-        }
-      }
-      const bool full = simd_ok && x0 + 8 <= A.width && y0 + 8 <= A.height &&
-          (x0 >> 1) + 4 <= A.cw && (y0 >> 1) + 4 <= A.ch;
-      // three lanes per candidate: luma rows 0-3, luma rows 4-7, both chroma blocks
+      if (lane < 6) { cdx = sc.dx[lane]; cdy = sc.dy[lane]; valid = (sc.valid >> lane) & 1; }
+      const bool full = sc.full != 0;
       const int ck = lane / 3, part = lane - 3 * ck;
-      unsigned metric = (unsigned) INT_MAX;        // candidate ck's SAD, valid in lane 3*ck
-      auto cand_sad = [&] (int kdx, int kdy, bool want) -> unsigned {
-        int dx = kdx >> s, dy = kdy >> s;
-        dx = clampi (dx + x0, -bw0, A.width) - x0;
-        dy = clampi (dy + y0, -bh0, A.height) - y0;
-        const bool ok = !(x0 < -e || y0 < -e || x0 + 8 > A.width + e || y0 + 8 > A.height + e) &&
-            !(x0 + dx < -e || y0 + dy < -e || x0 + dx + 8 > A.width + e || y0 + dy + 8 > A.height + e);
-        unsigned part_sad = 0;
-        if (ok && want) {
-          if (part < 2) {
-            const uint8_t *a = sp[0] + (ptrdiff_t) (y0 + 4 * part) * ss[0] + x0;
-            const uint8_t *b = rp[0] + (ptrdiff_t) (y0 + dy + 4 * part) * rs[0] + x0 + dx;
-#pragma unroll
-            for (int y = 0; y < 4; y++) {
-              const uint2 av = __ldg (reinterpret_cast<const uint2 *> (a + (ptrdiff_t) y * ss[0]));
-              const uint2 bv = load8_unaligned (b + (ptrdiff_t) y * rs[0]);
-              part_sad += __vsadu4 (av.x, bv.x) + __vsadu4 (av.y, bv.y);
-            }
-          } else {
-            const int sx = x0 >> 1, sy = y0 >> 1, rx = (x0 + dx) >> 1, ry = (y0 + dy) >> 1;
-#pragma unroll
-            for (int c = 1; c < 3; c++) {
-#pragma unroll
-              for (int y = 0; y < 4; y++) {
-                const unsigned av = __ldg (reinterpret_cast<const unsigned *> (sp[c] + (ptrdiff_t) (sy + y) * ss[c] + sx));
-                const unsigned bv = load4_unaligned (rp[c] + (ptrdiff_t) (ry + y) * rs[c] + rx);
-                part_sad += __vsadu4 (av, bv);
-              }
-            }
-          }
-        }
-        unsigned m = part_sad + __shfl_down_sync (0xffffffffu, part_sad, 1);
-        m += __shfl_down_sync (0xffffffffu, part_sad, 2);
-        return ok ? m : (unsigned) INT_MAX;
-      };
-      if (full) {
-        const int kdx = __shfl_sync (0xffffffffu, cdx, min (ck, 5)), kdy = __shfl_sync (0xffffffffu, cdy, min (ck, 5));
-        const bool kval = __shfl_sync (0xffffffffu, (int) valid, min (ck, 5)) != 0;
-        const unsigned m = cand_sad (kdx, kdy, ck < 6 && kval);
-        if (ck < 6) metric = m;
-      }
+      unsigned metric = (part == 0 && ck < 6) ? sc.metric[ck] : (unsigned) INT_MAX;   // candidate ck's SAD in lane 3*ck
 
+      TRACE (1);
       // ---- phase B: 6: left 7: up 8: up-left of THIS level (schrohierbm.c:279-294).
       // left comes from this CTA's previous block; up / up-left are polled straight out of
       // the row above's published words (up-left was published before up)
       if (lane == 6 && i > 0) {
         cdx = sh.last_dx; cdy = sh.last_dy; valid = true;
-      } else if (lane == 7 && words_up) {
-        // the only poller of this CTA; back off between polls so that thousands of waiting
-        // rows do not saturate the L2 request path of the rows that are working
-        unsigned long long wv = ld_word (words_up + bi);
-        while (!(wv >> 63)) { __nanosleep (POLL_NS); wv = ld_word (words_up + bi); }
+      } else if ((lane == 7 || (lane == 8 && i > 0)) && words_up) {
+        // up and up-left are fetched concurrently (one L2 round trip when both are ready);
+        // back off between polls so that waiting rows do not crowd the L2 request path
+        const unsigned long long *wp = words_up + bi - (lane == 8 ? 1 : 0);
+        unsigned long long wv = ld_word (wp);
+        while (!(wv >> 63)) { __nanosleep (POLL_NS); wv = ld_word (wp); }
         cdx = (int) (short) (wv >> 16); cdy = (int) (short) wv; valid = true;
       }
       __syncwarp ();
-      if (lane == 8 && i > 0 && words_up) {
-        const unsigned long long wv = ld_word (words_up + bi - 1);   // published before `up`
-        cdx = (int) (short) (wv >> 16); cdy = (int) (short) wv; valid = true;
-      }
       // de-duplicate keeping the LAST occurrence (schrohierbm.c:298-321): a candidate is
       // dropped when a later lane holds the same vector
       const bool isc = valid && lane < 9;
@@ -282,12 +323,24 @@ hbm_level_kernel (const HbmArgs A)
       const bool dup = isc && (same >> (lane + 1)) != 0;
       const unsigned cmask = __ballot_sync (0xffffffffu, isc && !dup);
 
+      TRACE (2);
       // ---- rank candidates with the 3-component SAD (schrometric.c:332-375) --------
       int best_k;
       if (full) {
         const int kdx = __shfl_sync (0xffffffffu, cdx, min (ck, 8)), kdy = __shfl_sync (0xffffffffu, cdy, min (ck, 8));
-        const unsigned m = cand_sad (kdx, kdy, ck >= 6 && ck < 9 && ((cmask >> min (ck, 8)) & 1));
-        if (ck >= 6 && ck < 9) metric = m;
+        // A neighbour whose vector equals one of the static candidates (the usual case in
+        // coherent motion) has that candidate's SAD: reuse it instead of loading again.
+        // `same` (from the de-duplication match) lists the lanes 0..8 holding my vector.
+        const unsigned twins = __shfl_sync (0xffffffffu, same, min (ck, 8)) & 0x3fu;   // static lanes 0..5
+        const bool reuse = ck >= 6 && ck < 9 && twins != 0;
+        const int src_lane = 3 * (__ffs (twins | 0x80000000u) - 1);
+        const unsigned reused = __shfl_sync (0xffffffffu, metric, reuse ? src_lane : 0);
+        const bool need = ck >= 6 && ck < 9 && ((cmask >> min (ck, 8)) & 1) && !reuse;
+        if (__any_sync (0xffffffffu, need)) {
+          const unsigned m = cand_sad (x0, bw0, bh0, part, kdx, kdy, need);
+          if (need) metric = m;
+        }
+        if (reuse) metric = reused;
         // first strict minimum in candidate order == min over (metric, k); INT_MAX never wins
         unsigned key = 0xffffffffu;
         if (ck < 9 && part == 0 && ((cmask >> ck) & 1) && metric < (unsigned) INT_MAX) key = (metric << 8) | (unsigned) ck;
@@ -328,6 +381,7 @@ hbm_level_kernel (const HbmArgs A)
         if (best_k < 0) best_k = __ffs (cmask) - 1;    // every candidate invalid: the reference asserts
       }
 
+      TRACE (3);
       // ---- seed + scan window (schrohierbm.c:349-364, schrometric.c:174-214) --------
       int dx = __shfl_sync (0xffffffffu, cdx, best_k) >> s;
       int dy = __shfl_sync (0xffffffffu, cdy, best_k) >> s;
@@ -345,6 +399,7 @@ hbm_level_kernel (const HbmArgs A)
     }
     if (NW > 1) __syncthreads (); else __syncwarp ();
 
+    TRACE (4);
     if (active) {
       const int xmin = sh.xmin, ymin = sh.ymin, scan_w = sh.scan_w, scan_h = sh.scan_h;
       const int seed_a = sh.seed_a, seed_b = sh.seed_b;
@@ -389,6 +444,7 @@ hbm_level_kernel (const HbmArgs A)
         if (key < best_key) { best_key = key; best_l = l; best_c = c; }
       }
       // min over (tot, low bits): two 32-bit REDUX instead of a 64-bit shuffle tree
+      TRACE (5);
       const unsigned khi = (unsigned) (best_key >> 32), klo = (unsigned) best_key;
       const unsigned mhi = __reduce_min_sync (0xffffffffu, khi);
       const unsigned mlo = __reduce_min_sync (0xffffffffu, khi == mhi ? klo : 0xffffffffu);
@@ -411,6 +467,7 @@ hbm_level_kernel (const HbmArgs A)
         }
         const int a = (int) ((k >> 12) & 0xfff), b = (int) (k & 0xfff);
         const int rdx = (xmin + a - x0) << s, rdy = (ymin + b - y0) << s;
+        TRACE (6);
         // publish first (the row below is waiting on it), then fill in the output field
         st_word (words_me + bi, pack_word ((int16_t) rdx, (int16_t) rdy));
         sh.last_dx = (int16_t) rdx; sh.last_dy = (int16_t) rdy;
@@ -578,11 +635,17 @@ sb2_hbm_scan_hint (const sb2_hbm_params *p, const sb2_slab *src_level, const sb2
   cudaError_t e = cudaMemsetAsync (workspace, 0, need, st);
   if (e != cudaSuccess) return check_cuda (e, "cudaMemsetAsync(words)");
   const size_t nfield = (size_t) A.nbx * A.nby;
-  for (int pic = 0; pic < count; pic++) {
-    // fields of different pictures may be field_picture_pitch apart: init each
-    LaunchScope scope ("hbm_init_field", (double) nfield * 20, st);
-    hbm_init_field_kernel<<<(unsigned) min ((size_t) 1024, (nfield + 127) / 128), 128, 0, st>>> (
-        A.field + (size_t) pic * field_picture_pitch, nfield, A.flags0);
+  if (field_picture_pitch == nfield || count == 1) {
+    // contiguous fields: one launch initialises every pair's field
+    LaunchScope scope ("hbm_init_field", (double) nfield * 20 * count, st);
+    hbm_init_field_kernel<<<(unsigned) min ((size_t) 2048, (nfield * count + 127) / 128), 128, 0, st>>> (
+        A.field, nfield * count, A.flags0);
+  } else {
+    for (int pic = 0; pic < count; pic++) {
+      LaunchScope scope ("hbm_init_field", (double) nfield * 20, st);
+      hbm_init_field_kernel<<<(unsigned) min ((size_t) 1024, (nfield + 127) / 128), 128, 0, st>>> (
+          A.field + (size_t) pic * field_picture_pitch, nfield, A.flags0);
+    }
   }
   // algorithmic bytes: both pyramids of this level once + the fields
   double bytes = 0;
@@ -602,3 +665,10 @@ sb2_hbm_scan_hint (const sb2_hbm_params *p, const sb2_slab *src_level, const sb2
   }
   return check_cuda (cudaGetLastError (), "hbm_level_kernel launch");
 }
+
+#ifdef SB2_HBM_TRACE
+extern "C" int sb2_hbm_trace_read (long long *host, int n)
+{
+  return (int) cudaMemcpyFromSymbol (host, sb2::g_hbm_trace, sizeof (long long) * n);
+}
+#endif
