@@ -58,10 +58,6 @@ edgeextend_kernel (const FrameArgs a)
 }
 
 // ---- upsample ---------------------------------------------------------------------
-constexpr int UT_W = 64;     // output tile (extended coordinates)
-constexpr int UT_H = 16;
-constexpr int UP_W = UT_W + 8;            // phase-0 tile incl. 3 left / 4 right taps (+1 pad)
-constexpr int UP_H = UT_H + 7;
 
 __device__ __forceinline__ int taps8 (const uint8_t *s, int step)
 {
@@ -74,59 +70,145 @@ __device__ __forceinline__ int taps8 (const uint8_t *s, int step)
   return clamp255 (acc >> 5);
 }
 
-__global__ void __launch_bounds__ (256)
-upsample_kernel (const FrameArgs a)
+// ---- upsample, interior tiles: four pixels per thread, packed 16-bit arithmetic -------
+// For tiles that touch no picture edge every output is a plain 8-tap filter, so the
+// border rules vanish and a thread can produce four adjacent pixels of a phase at once:
+// pixel pairs ride in the two 16-bit lanes of a register (taps sum to 32, partial sums
+// stay below 2^15), the negative taps are folded in with a bias of 8192 = 256<<5 so no
+// lane ever borrows, and the final clamp is a packed min/max.  Tiles that do touch an
+// edge take the per-pixel path of the same kernel, which spells out the border rules.
+constexpr int U2_W = 128, U2_H = 16;             // output tile
+constexpr int U2_WORDS = U2_W / 4 + 2;           // tile words incl. one halo word each side
+constexpr int U2_PITCH = U2_WORDS + 1;
+
+// (-1,3,-7,21,21,-7,3,-1), +16 >> 5, clamp -- on two 16-bit lanes
+__device__ __forceinline__ unsigned taps8_x2 (const unsigned (&p)[8])
 {
-  __shared__ uint8_t s0[UP_H][UP_W];      // phase 0 at clamped coordinates
-  __shared__ uint8_t sv[UT_H][UP_W];      // vertical half-pel of the same columns
+  const unsigned s34 = p[3] + p[4], s25 = p[2] + p[5], s16 = p[1] + p[6], s07 = p[0] + p[7];
+  const unsigned a = 21u * s34 + 3u * s16 + 0x20102010u;     // +16 and the +8192 bias
+  const unsigned d = a - (7u * s25 + s07);
+  unsigned t = (d >> 5) & 0x07ff07ffu;
+  t = __vminu2 (__vmaxu2 (t, 0x01000100u), 0x01ff01ffu);
+  return t - 0x01000100u;
+}
+
+// vertical filter of one word column: rows r[0..7] hold 4 pixels each
+__device__ __forceinline__ unsigned taps8_vert4 (const unsigned (&r)[8])
+{
+  unsigned lo[8], hi[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    lo[j] = __byte_perm (r[j], 0, 0x4140);
+    hi[j] = __byte_perm (r[j], 0, 0x4342);
+  }
+  const unsigned o01 = taps8_x2 (lo), o23 = taps8_x2 (hi);
+  return __byte_perm (o01, o23, 0x6420);
+}
+
+// horizontal filter of pixels b[0..3] given the words holding b[-4..-1], b[0..3], b[4..7]
+__device__ __forceinline__ unsigned taps8_horiz4 (unsigned wm, unsigned w0, unsigned wp)
+{
+  unsigned u[8];                                   // u[j] = bytes b[j-3 .. j]
+  u[0] = __funnelshift_r (wm, w0, 8);
+  u[1] = __funnelshift_r (wm, w0, 16);
+  u[2] = __funnelshift_r (wm, w0, 24);
+  u[3] = w0;
+  u[4] = __funnelshift_r (w0, wp, 8);
+  u[5] = __funnelshift_r (w0, wp, 16);
+  u[6] = __funnelshift_r (w0, wp, 24);
+  u[7] = wp;
+  unsigned e[8], o[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    e[j] = __byte_perm (u[j], 0, 0x4240);          // (b[j-3], b[j-1]): taps of outputs 0 and 2
+    o[j] = __byte_perm (u[j], 0, 0x4341);          // (b[j-2], b[j]  ): taps of outputs 1 and 3
+  }
+  const unsigned o02 = taps8_x2 (e), o13 = taps8_x2 (o);
+  return __byte_perm (o02, o13, 0x6240);
+}
+
+__global__ void __launch_bounds__ (256)
+upsample_kernel_v2 (const FrameArgs a)
+{
+  __shared__ unsigned s0[U2_H + 7][U2_PITCH];      // phase 0, word c = pixels x0-4+4c ..
+  __shared__ unsigned sv[U2_H][U2_PITCH];          // vertical half-pel of the same words
 
   const int comp = blockIdx.z % a.ncomp, pic = blockIdx.z / a.ncomp;
   const int w = a.w[comp], h = a.h[comp], ext = a.ext;
-  const int x0 = blockIdx.x * UT_W - ext, y0 = blockIdx.y * UT_H - ext;
+  const int x0 = blockIdx.x * U2_W - ext, y0 = blockIdx.y * U2_H - ext;
   if (x0 >= w + ext || y0 >= h + ext) return;
   uint8_t *p0 = reinterpret_cast<uint8_t *> (plane_ptr (a.planes, pic, comp));
   const int stride = a.planes.stride[comp];
   const int q = stride >> 2;
+  const bool aligned = ((((size_t) p0 | (size_t) stride | (size_t) q) & 3) == 0) && ((x0 & 3) == 0);
+  // interior: every output is a plain filter and every tap lies inside the picture
+  const bool interior = aligned && x0 - 4 >= 0 && x0 + U2_W + 4 <= w - 1 && y0 - 3 >= 0 && y0 + U2_H + 4 <= h - 1;
 
-  // tile of phase 0: rows y0-3 .. y0+UT_H+3, columns x0-3 .. x0+UT_W+4, coordinates clamped
-  for (int i = threadIdx.x; i < UP_H * UP_W; i += blockDim.x) {
-    const int ty = i / UP_W, tx = i % UP_W;
+  if (interior) {
+    for (int i = threadIdx.x; i < (U2_H + 7) * U2_WORDS; i += blockDim.x) {
+      const int ty = i / U2_WORDS, c = i - ty * U2_WORDS;
+      s0[ty][c] = __ldg (reinterpret_cast<const unsigned *> (p0 + (ptrdiff_t) (y0 + ty - 3) * stride + x0 - 4) + c);
+    }
+    __syncthreads ();
+    for (int i = threadIdx.x; i < U2_H * U2_WORDS; i += blockDim.x) {
+      const int ty = i / U2_WORDS, c = i - ty * U2_WORDS;
+      unsigned r[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) r[j] = s0[ty + j][c];
+      const unsigned v = taps8_vert4 (r);
+      sv[ty][c] = v;
+      if (c >= 1 && c <= U2_W / 4)
+        *reinterpret_cast<unsigned *> (p0 + (ptrdiff_t) (y0 + ty) * stride + 2 * q + x0 - 4 + 4 * c) = v;
+    }
+    __syncthreads ();
+    for (int i = threadIdx.x; i < U2_H * (U2_W / 4); i += blockDim.x) {
+      const int ty = i / (U2_W / 4), c = i - ty * (U2_W / 4) + 1;
+      uint8_t *o = p0 + (ptrdiff_t) (y0 + ty) * stride + x0 - 4 + 4 * c;
+      *reinterpret_cast<unsigned *> (o + q) = taps8_horiz4 (s0[ty + 3][c - 1], s0[ty + 3][c], s0[ty + 3][c + 1]);
+      *reinterpret_cast<unsigned *> (o + 3 * q) = taps8_horiz4 (sv[ty][c - 1], sv[ty][c], sv[ty][c + 1]);
+    }
+    return;
+  }
+
+  // ---- edge tiles: per-pixel rules over the 128x16 tile.
+  // phase 1 (schroframe.c:2022-2024): horizontal filter of phase 0 row clamp(y); left border =
+  //   phase 0 column 0, columns >= w-1 = phase 0 column w-1
+  // phase 2 (:2018-2020): vertical filter; rows above = phase 0 row 0, last row and below =
+  //   phase 0 row h-1, side borders replicate phase 2 itself
+  // phase 3 (:2026-2028): horizontal filter of phase 2; rows above / last row and below are
+  //   copies of phase 1, side borders come from phase 2
+  uint8_t *b0 = reinterpret_cast<uint8_t *> (&s0[0][0]);
+  uint8_t *bv = reinterpret_cast<uint8_t *> (&sv[0][0]);
+  constexpr int BW = U2_W + 8;                     // byte tile width: x0-3 .. x0+U2_W+4
+  for (int i = threadIdx.x; i < (U2_H + 7) * BW; i += blockDim.x) {
+    const int ty = i / BW, tx = i - ty * BW;
     const int yy = clampi (y0 + ty - 3, 0, h - 1), xx = clampi (x0 + tx - 3, 0, w - 1);
-    s0[ty][tx] = p0[(ptrdiff_t) yy * stride + xx];
+    b0[ty * BW + tx] = p0[(ptrdiff_t) yy * stride + xx];
   }
   __syncthreads ();
-  // vertical phase of every tile column; rows >= h-1 are copies of the source row h-1,
-  // rows < 0 are never used as filter input (they take other sources below)
-  for (int i = threadIdx.x; i < UT_H * UP_W; i += blockDim.x) {
-    const int ty = i / UP_W, tx = i % UP_W;
+  for (int i = threadIdx.x; i < U2_H * BW; i += blockDim.x) {
+    const int ty = i / BW, tx = i - ty * BW;
     const int y = y0 + ty;
     int v;
-    if (y >= h - 1 || y < 0) v = s0[ty + 3][tx];     // s0 row ty+3 is clamp(y): row h-1 (or 0)
-    else v = taps8 (&s0[ty][tx], UP_W);
-    sv[ty][tx] = (uint8_t) v;
+    if (y >= h - 1 || y < 0) v = b0[(ty + 3) * BW + tx];
+    else v = taps8 (&b0[ty * BW + tx], BW);
+    bv[ty * BW + tx] = (uint8_t) v;
   }
   __syncthreads ();
-
-  for (int i = threadIdx.x; i < UT_H * UT_W; i += blockDim.x) {
-    const int ty = i / UT_W, tx = i % UT_W;
+  for (int i = threadIdx.x; i < U2_H * U2_W; i += blockDim.x) {
+    const int ty = i / U2_W, tx = i - ty * U2_W;
     const int x = x0 + tx, y = y0 + ty;
     if (x >= w + ext || y >= h + ext) continue;
-    // phase 1 (schroframe.c:2022-2024): horizontal filter of phase 0 row clamp(y); left
-    // border = phase 0 column 0, columns >= w-1 = phase 0 column w-1
     int v1;
-    if (x < 0 || x >= w - 1) v1 = s0[ty + 3][tx + 3];
-    else v1 = taps8 (&s0[ty + 3][tx], 1);
-    // phase 2 (:2018-2020): vertical filter; rows above = phase 0 row 0, last row and
-    // below = phase 0 row h-1, side borders replicate phase 2 itself
-    const int v2 = sv[ty][tx + 3];
-    // phase 3 (:2026-2028): horizontal filter of phase 2; rows above / last row and below
-    // are copies of phase 1, side borders come from phase 2
+    if (x < 0 || x >= w - 1) v1 = b0[(ty + 3) * BW + tx + 3];
+    else v1 = taps8 (&b0[(ty + 3) * BW + tx], 1);
+    const int v2 = bv[ty * BW + tx + 3];
     int v3;
     if (y < 0 || y >= h - 1) v3 = v1;
     else if (x < 0 || x >= w - 1) v3 = v2;
-    else v3 = taps8 (&sv[ty][tx], 1);
+    else v3 = taps8 (&bv[ty * BW + tx], 1);
     uint8_t *o = p0 + (ptrdiff_t) y * stride + x;
-    if (a.fuse_edge && (x < 0 || x >= w || y < 0 || y >= h)) o[0] = s0[ty + 3][tx + 3];
+    if (a.fuse_edge && (x < 0 || x >= w || y < 0 || y >= h)) o[0] = b0[(ty + 3) * BW + tx + 3];
     o[q] = (uint8_t) v1;
     o[2 * q] = (uint8_t) v2;
     o[3 * q] = (uint8_t) v3;
@@ -142,45 +224,90 @@ struct DownArgs {
   int dst_ext;                  // > 0: also replicate the result into dst's border
 };
 
-constexpr int DT_W = 32, DT_H = 8;                 // output tile
-constexpr int DS_W = 2 * DT_W + 2;                 // source columns 2x-1 .. 2x+2
+// ---- downsample, interior tiles: four output pixels per thread, packed arithmetic ------
+constexpr int D2_W = 64, D2_H = 8;                 // output tile
+constexpr int D2_WORDS = (2 * D2_W) / 4 + 3;       // tmp words: source columns 2*x0-4 .. 2*x0+2*D2_W+8
+constexpr int D2_BW = 2 * D2_W + 2;                // byte tile of the edge path
 
 __global__ void __launch_bounds__ (256)
-downsample_kernel (const DownArgs a)
+downsample_kernel_v2 (const DownArgs a)
 {
-  __shared__ uint8_t sm[DT_H][DS_W];               // vertically filtered rows (8-bit intermediate)
+  __shared__ unsigned st[D2_H][D2_WORDS + 1];      // vertically filtered source words
 
   const int comp = blockIdx.z % a.ncomp, pic = blockIdx.z / a.ncomp;
   const int sw = a.sw[comp], sh = a.sh[comp], dw = a.dw[comp], dh = a.dh[comp];
-  const int x0 = blockIdx.x * DT_W, y0 = blockIdx.y * DT_H;
+  const int x0 = blockIdx.x * D2_W, y0 = blockIdx.y * D2_H;
   if (x0 >= dw || y0 >= dh) return;
   const uint8_t *s = reinterpret_cast<const uint8_t *> (plane_ptr (a.src, pic, comp));
   uint8_t *d = reinterpret_cast<uint8_t *> (plane_ptr (a.dst, pic, comp));
   const int ss = a.src.stride[comp], dstr = a.dst.stride[comp];
+  const bool aligned = ((((size_t) s | (size_t) ss | (size_t) d | (size_t) dstr) & 3) == 0);
+  const bool interior = aligned && 2 * x0 - 4 >= 0 && 2 * x0 + 2 * D2_W + 8 <= sw &&
+      2 * y0 - 1 >= 0 && 2 * (y0 + D2_H - 1) + 2 <= sh - 1 && x0 + D2_W < dw && y0 + D2_H < dh && x0 > 0 && y0 > 0;
 
-  // orc_downsample_vert_u8 (schroorc.orc:1345-1368): (6(a+d) + 26(b+c) + 32) >> 6, u8
-  for (int i = threadIdx.x; i < DT_H * DS_W; i += blockDim.x) {
-    const int ty = i / DS_W, tx = i % DS_W;
+  if (interior) {
+    // vertical (6,26,26,6)+32 >> 6 on whole source words, straight from global memory
+    for (int i = threadIdx.x; i < D2_H * D2_WORDS; i += blockDim.x) {
+      const int ty = i / D2_WORDS, c = i - ty * D2_WORDS;
+      const unsigned *col = reinterpret_cast<const unsigned *> (s + (ptrdiff_t) (2 * (y0 + ty) - 1) * ss + 2 * x0 - 4) + c;
+      unsigned lo[4], hi[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const unsigned r = __ldg (reinterpret_cast<const unsigned *> (reinterpret_cast<const uint8_t *> (col) + (ptrdiff_t) j * ss));
+        lo[j] = __byte_perm (r, 0, 0x4140);
+        hi[j] = __byte_perm (r, 0, 0x4342);
+      }
+      const unsigned vlo = ((6u * (lo[0] + lo[3]) + 26u * (lo[1] + lo[2]) + 0x00200020u) >> 6) & 0x00ff00ffu;
+      const unsigned vhi = ((6u * (hi[0] + hi[3]) + 26u * (hi[1] + hi[2]) + 0x00200020u) >> 6) & 0x00ff00ffu;
+      st[ty][c] = __byte_perm (vlo, vhi, 0x6420);
+    }
+    __syncthreads ();
+    // horizontal pass: output pixels x..x+3 use b[-1..8], b[k] = tmp[2x+k]
+    for (int i = threadIdx.x; i < D2_H * (D2_W / 4); i += blockDim.x) {
+      const int ty = i / (D2_W / 4), g = i - ty * (D2_W / 4);
+      const unsigned *t = &st[ty][2 * g];          // t[0] = b[-4..-1], t[1] = b[0..3], t[2] = b[4..7], t[3] = b[8..11]
+      unsigned u[8];                                // u[k] = b[k-1 .. k+2]
+      u[0] = __funnelshift_r (t[0], t[1], 24);
+      u[1] = t[1];
+      u[2] = __funnelshift_r (t[1], t[2], 8);
+      u[3] = __funnelshift_r (t[1], t[2], 16);
+      u[4] = __funnelshift_r (t[1], t[2], 24);
+      u[5] = t[2];
+      u[6] = __funnelshift_r (t[2], t[3], 8);
+      u[7] = __funnelshift_r (t[2], t[3], 16);
+      unsigned p[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) p[k] = __byte_perm (u[k], 0, 0x4240);   // (b[k-1], b[k+1])
+      // outputs (0,1): 6*(b-1,b1) + 26*(b0,b2) + 26*(b1,b3) + 6*(b2,b4); outputs (2,3) four further on
+      const unsigned o01 = ((6u * (p[0] + p[3]) + 26u * (p[1] + p[2]) + 0x00200020u) >> 6) & 0x00ff00ffu;
+      const unsigned o23 = ((6u * (p[4] + p[7]) + 26u * (p[5] + p[6]) + 0x00200020u) >> 6) & 0x00ff00ffu;
+      *reinterpret_cast<unsigned *> (d + (ptrdiff_t) (y0 + ty) * dstr + x0 + 4 * g) = __byte_perm (o01, o23, 0x6420);
+    }
+    return;
+  }
+
+  // ---- edge tiles: per-pixel path with clamped indices and the fused border replication
+  uint8_t *sm = reinterpret_cast<uint8_t *> (&st[0][0]);
+  static_assert (D2_H * D2_BW <= D2_H * (D2_WORDS + 1) * 4, "byte tile fits");
+  for (int i = threadIdx.x; i < D2_H * D2_BW; i += blockDim.x) {
+    const int ty = i / D2_BW, tx = i - ty * D2_BW;
     const int y = y0 + ty;
     const int xx = clampi (2 * x0 - 1 + tx, 0, sw - 1);
     const int r0 = s[(ptrdiff_t) clampi (2 * y - 1, 0, sh - 1) * ss + xx];
     const int r1 = s[(ptrdiff_t) clampi (2 * y, 0, sh - 1) * ss + xx];
     const int r2 = s[(ptrdiff_t) clampi (2 * y + 1, 0, sh - 1) * ss + xx];
     const int r3 = s[(ptrdiff_t) clampi (2 * y + 2, 0, sh - 1) * ss + xx];
-    sm[ty][tx] = (uint8_t) ((6 * (r0 + r3) + 26 * (r1 + r2) + 32) >> 6);
+    sm[ty * D2_BW + tx] = (uint8_t) ((6 * (r0 + r3) + 26 * (r1 + r2) + 32) >> 6);
   }
   __syncthreads ();
-  // horizontal pass (schroframe.c:1449-1485)
-  for (int i = threadIdx.x; i < DT_H * DT_W; i += blockDim.x) {
-    const int ty = i / DT_W, tx = i % DT_W;
+  for (int i = threadIdx.x; i < D2_H * D2_W; i += blockDim.x) {
+    const int ty = i / D2_W, tx = i - ty * D2_W;
     const int x = x0 + tx, y = y0 + ty;
     if (x >= dw || y >= dh) continue;
-    const uint8_t *t = &sm[ty][2 * tx];
+    const uint8_t *t = &sm[ty * D2_BW + 2 * tx];
     const uint8_t v = (uint8_t) clamp255 ((6 * ((int) t[0] + t[3]) + 26 * ((int) t[1] + t[2]) + 32) >> 6);
     d[(ptrdiff_t) y * dstr + x] = v;
     if (a.dst_ext > 0 && (x == 0 || x == dw - 1 || y == 0 || y == dh - 1)) {
-      // schro_frame_mc_edgeextend of the result: the thread owning an edge pixel writes its
-      // replicas (rows / columns outside the plane, corners included)
       const int e = a.dst_ext;
       const int qx0 = x == 0 ? -e : 0, qx1 = x == dw - 1 ? e : 0;
       const int qy0 = y == 0 ? -e : 0, qy1 = y == dh - 1 ? e : 0;
@@ -307,10 +434,12 @@ upsample_impl (const sb2_slab *frames, int extension, int fuse_edge, void *strea
     bytes += ((double) frames->width[c] * frames->height[c]
         + 3.0 * (frames->width[c] + 2 * extension) * (frames->height[c] + 2 * extension)) * frames->count;
   }
-  dim3 grid (ceil_div (maxw, UT_W), ceil_div (maxh, UT_H), frames->ncomp * frames->count);
+  static_assert ((U2_H + 7) * (U2_W + 8) <= (U2_H + 7) * U2_PITCH * 4 && U2_H * (U2_W + 8) <= U2_H * U2_PITCH * 4,
+      "byte tiles of the edge path fit the word tiles");
+  dim3 grid (ceil_div (maxw, U2_W), ceil_div (maxh, U2_H), frames->ncomp * frames->count);
   {
     LaunchScope scope ("upsample", bytes, as_stream (stream));
-    upsample_kernel<<<grid, 256, 0, as_stream (stream)>>> (a);
+    upsample_kernel_v2<<<grid, 256, 0, as_stream (stream)>>> (a);
   }
   return check_cuda (cudaGetLastError (), "upsample_kernel launch");
 }
@@ -359,10 +488,10 @@ downsample_impl (const sb2_slab *src, const sb2_slab *dst, int dst_ext, void *st
       bytes += ((double) src->width[c] * src->height[c] + (double) dst->width[c] * dst->height[c]) * src->count;
     }
   }
-  dim3 grid (ceil_div (maxw, DT_W), ceil_div (maxh, DT_H), src->ncomp * src->count);
+  dim3 grid (ceil_div (maxw, D2_W), ceil_div (maxh, D2_H), src->ncomp * src->count);
   {
     LaunchScope scope ("downsample", bytes, as_stream (stream));
-    downsample_kernel<<<grid, 256, 0, as_stream (stream)>>> (a);
+    downsample_kernel_v2<<<grid, 256, 0, as_stream (stream)>>> (a);
   }
   return check_cuda (cudaGetLastError (), "downsample_kernel launch");
 }
