@@ -160,19 +160,40 @@ struct StaticCands {
   int full;
 };
 
+struct Win { int xmin, ymin, scan_w, scan_h, seed_a, seed_b; };
+
+// a speculative scan: the search result for seed (dx, dy), prepared one block ahead
+struct SpecScan {
+  int valid, dx, dy;
+  Win win;
+  unsigned long long key;
+  unsigned luma, chroma;
+};
+
 struct BlockShared {
   StaticCands stc[2];
-  int xmin, ymin, scan_w, scan_h, seed_a, seed_b;
+  SpecScan spec[2];
+  Win win;
   int last_dx, last_dy;             // this row's previous block (the "left" candidate)
   unsigned long long key[16];
   unsigned luma[16], chroma[16];
 };
 
 // One CTA (NW warps) owns one block row of one (picture, reference) pair.
-template <int NW>
+//
+// Per block the dependent chain is: neighbour vectors (poll) -> rank candidates -> scan around
+// the winner -> publish.  Everything that does not depend on the neighbours runs one block
+// ahead on warp 1: the static candidates (zero + five parents) with their ranking SADs.
+// SPEC additionally lets warp 1 scan speculatively around the best static candidate, so that a
+// ranking that picks the same seed finds its scan done.  Measured on the 2160p bench (noisy
+// panning content, B200): level 0 4.4 ms with SPEC vs 3.6 ms without -- warp 1 becomes the
+// longer loop and misses pay a single-warp scan -- so it is compiled out; kept because it
+// wins when vectors are coherent (hit rate near 1) and the chain is poll -> rank -> publish.
+template <int NW, bool SPEC = false>
 __global__ void __launch_bounds__ (32 * NW)
 hbm_level_kernel (const HbmArgs A)
 {
+  static_assert (NW >= 2, "one warp prepares the static candidates of the next block");
   __shared__ BlockShared sh;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = blockIdx.x / A.count, pic = blockIdx.x % A.count;   // row r is launched before r+1
@@ -193,10 +214,10 @@ hbm_level_kernel (const HbmArgs A)
   const MotionVector *pf = A.parent ? A.parent + (size_t) pic * A.field_pitch : nullptr;
   unsigned long long *words_me = A.words + ((size_t) pic * A.rows + row) * A.cols;
   const unsigned long long *words_up = row > 0 ? words_me - A.cols : nullptr;
-  if (threadIdx.x == 0) { sh.last_dx = 0; sh.last_dy = 0; }
-  if (NW > 1) __syncthreads (); else __syncwarp ();
+  if (threadIdx.x == 0) { sh.last_dx = 0; sh.last_dy = 0; sh.spec[0].valid = 0; sh.spec[1].valid = 0; }
   const int hint_mask = ~((1 << (s + 1)) - 1);
   const int y0 = (j * A.bh) >> s;
+  const int bh0 = min (A.height - y0, A.bh);
   const int e = A.ext;
   // every alignment assumption of the byte-SIMD paths, checked once
   const bool simd_ok = A.bw == 8 && A.bh == 8 && A.hs == 1 && A.vs == 1 &&
@@ -205,7 +226,7 @@ hbm_level_kernel (const HbmArgs A)
 
   // ranking SAD of one candidate vector for the block at (x0, y0): three lanes per candidate
   // (luma rows 0-3, luma rows 4-7, both chroma blocks), result in the first of the three
-  auto cand_sad = [&] (int x0, int bw0, int bh0, int part, int kdx, int kdy, bool want) -> unsigned {
+  auto cand_sad = [&] (int x0, int bw0, int part, int kdx, int kdy, bool want) -> unsigned {
     int dx = kdx >> s, dy = kdy >> s;
     dx = clampi (dx + x0, -bw0, A.width) - x0;
     dy = clampi (dy + y0, -bh0, A.height) - y0;
@@ -239,12 +260,101 @@ hbm_level_kernel (const HbmArgs A)
     m += __shfl_down_sync (0xffffffffu, part_sad, 2);
     return ok ? m : (unsigned) INT_MAX;
   };
-  // static candidates of block `nb` into sh.stc[nb & 1]; executed by one whole warp
+
+  // seed clamp + scan window (schrohierbm.c:349-364, schrometric.c:174-214); (dx, dy) in pixels
+  auto clamp_seed = [&] (int x0, int bw0, int &dx, int &dy) {
+    dx = max (-bw0 - x0, min (A.width - x0, dx));
+    dy = max (-bh0 - y0, min (A.height - y0, dy));
+  };
+  auto make_win = [&] (int x0, int bw0, int dx, int dy) -> Win {
+    Win w;
+    w.xmin = max (max (-bw0, x0 + dx - A.h_range), -e);
+    w.ymin = max (max (-bh0, y0 + dy - A.h_range), -e);
+    const int xmax = min (min (A.width, x0 + dx + A.h_range), A.width - bw0 + e);
+    const int ymax = min (min (A.height, y0 + dy + A.h_range), A.height - bh0 + e);
+    w.scan_w = xmax - w.xmin + 1;
+    w.scan_h = ymax - w.ymin + 1;
+    w.seed_a = dx + x0 - w.xmin;
+    w.seed_b = dy + y0 - w.ymin;
+    return w;
+  };
+
+  // full search over positions first, first+stride, ...: the calling warp's best
+  // key = (metric, not-seed, a, b) -- seed wins ties, else first strict minimum in the
+  // reference's a-outer / b-inner order (schrometric.c:121-171) -- with its luma / chroma SADs
+  auto scan_part = [&] (int x0, int bw0, const Win &wn, int first, int stride,
+      unsigned long long &wkey, unsigned &wl, unsigned &wc) {
+    unsigned long long best_key = ~0ull;
+    unsigned best_l = 0, best_c = 0;
+    const uint8_t *sblk = sp[0] + (ptrdiff_t) y0 * ss[0] + x0;
+    const int npos = wn.scan_w * wn.scan_h;
+    const bool fast8 = simd_ok && bw0 == 8 && bh0 == 8;
+    uint2 srow[8];
+    if (fast8) {
+#pragma unroll
+      for (int y = 0; y < 8; y++) srow[y] = __ldg (reinterpret_cast<const uint2 *> (sblk + (ptrdiff_t) y * ss[0]));
+    }
+    for (int p = first; p < npos; p += stride) {
+      const int b = p / wn.scan_w, a = p - b * wn.scan_w;
+      const uint8_t *rblk = rp[0] + (ptrdiff_t) (wn.ymin + b) * rs[0] + wn.xmin + a;
+      unsigned l = 0;
+      if (fast8) {
+#pragma unroll
+        for (int y = 0; y < 8; y++) {
+          const uint2 bv = load8_unaligned (rblk + (ptrdiff_t) y * rs[0]);
+          l += __vsadu4 (srow[y].x, bv.x) + __vsadu4 (srow[y].y, bv.y);
+        }
+      } else {
+        l = block_sad (sblk, ss[0], rblk, rs[0], bw0, bh0);
+      }
+      unsigned c = 0;
+      if (A.use_chroma) {
+        // chroma_metrics[a*scan_h+b] = sum_k SAD_k at (ref_x/2 + a/2, ref_y/2 + b/2)
+        // (schrometric.c:73-115; C division truncates toward zero)
+        const int cx = x0 / 2, cy = y0 / 2, crx = wn.xmin / 2 + (a >> 1), cry = wn.ymin / 2 + (b >> 1);
+        for (int k = 1; k < 3; k++)
+          c += block_sad (sp[k] + (ptrdiff_t) cy * ss[k] + cx, ss[k], rp[k] + (ptrdiff_t) cry * rs[k] + crx, rs[k],
+              bw0 / 2, bh0 / 2);
+      }
+      const unsigned tot = l + c;
+      const unsigned notseed = (a == wn.seed_a && b == wn.seed_b) ? 0u : 1u;
+      const unsigned long long key = ((unsigned long long) tot << 32) | (notseed << 24) | ((unsigned) a << 12) | (unsigned) b;
+      if (key < best_key) { best_key = key; best_l = l; best_c = c; }
+    }
+    // min over (tot, low bits): two 32-bit REDUX instead of a 64-bit shuffle tree
+    const unsigned khi = (unsigned) (best_key >> 32), klo = (unsigned) best_key;
+    const unsigned mhi = __reduce_min_sync (0xffffffffu, khi);
+    const unsigned mlo = __reduce_min_sync (0xffffffffu, khi == mhi ? klo : 0xffffffffu);
+    wkey = ((unsigned long long) mhi << 32) | mlo;
+    const unsigned owner = __ballot_sync (0xffffffffu, best_key == wkey);
+    const int ol = __ffs (owner) - 1;
+    wl = __shfl_sync (0xffffffffu, best_l, ol);
+    wc = __shfl_sync (0xffffffffu, best_c, ol);
+  };
+
+  // one thread: publish the vector (the row below is waiting on it), then fill the output field
+  auto publish = [&] (int bi, int i, int x0, const Win &wn, unsigned long long k, unsigned bl, unsigned bc) {
+    const int a = (int) ((k >> 12) & 0xfff), b = (int) (k & 0xfff);
+    const int rdx = (wn.xmin + a - x0) << s, rdy = (wn.ymin + b - y0) << s;
+    st_word (words_me + bi, pack_word ((int16_t) rdx, (int16_t) rdy));
+    sh.last_dx = (int16_t) rdx; sh.last_dy = (int16_t) rdy;
+    MotionVector *o = mf + (size_t) j * A.nbx + i;
+    o->metric = bl;
+    o->chroma_metric = bc;
+    o->v[ri] = (int16_t) rdx;
+    o->v[2 + ri] = (int16_t) rdy;
+    o->flags = A.flags0;
+  };
+
+  // static candidates of block `nb` (0: zero, 1..5: parents (0,0) (-1,0) (1,0) (0,-1) (0,1),
+  // schrohierbm.c:259-277) and their ranking SADs into sh.stc[nb & 1]; with SPEC also the scan
+  // around the best of them into sh.spec[nb & 1].  Executed by one whole warp.
   auto do_static = [&] (int nb) {
     const int i = nb * skip;
     const int x0 = (i * A.bw) >> s;
-    if (!(x0 < A.width && y0 < A.height)) return;
-    const int bw0 = min (A.width - x0, A.bw), bh0 = min (A.height - y0, A.bh);
+    SpecScan &spc = sh.spec[nb & 1];
+    if (!(x0 < A.width && y0 < A.height)) { if (lane == 0) spc.valid = 0; return; }
+    const int bw0 = min (A.width - x0, A.bw);
     int cdx = 0, cdy = 0;
     bool valid = false;
     if (lane == 0) valid = true;
@@ -261,17 +371,34 @@ hbm_level_kernel (const HbmArgs A)
         (x0 >> 1) + 4 <= A.cw && (y0 >> 1) + 4 <= A.ch;
     const int ck = lane / 3, part = lane - 3 * ck;
     StaticCands &sc = sh.stc[nb & 1];
+    unsigned m = (unsigned) INT_MAX;
     if (full) {
       const int kdx = __shfl_sync (0xffffffffu, cdx, min (ck, 5)), kdy = __shfl_sync (0xffffffffu, cdy, min (ck, 5));
       const bool kval = __shfl_sync (0xffffffffu, (int) valid, min (ck, 5)) != 0;
-      const unsigned m = cand_sad (x0, bw0, bh0, part, kdx, kdy, ck < 6 && kval);
+      m = cand_sad (x0, bw0, part, kdx, kdy, ck < 6 && kval);
       if (ck < 6 && part == 0) sc.metric[ck] = m;
     }
     const unsigned vm = __ballot_sync (0xffffffffu, valid && lane < 6);
     if (lane < 6) { sc.dx[lane] = cdx; sc.dy[lane] = cdy; }
     if (lane == 0) { sc.valid = vm; sc.full = full; }
+    if (SPEC) {
+      // speculate that the best static candidate will also win the full ranking
+      unsigned key = 0xffffffffu;
+      if (full && ck < 6 && part == 0 && ((vm >> ck) & 1) && m < (unsigned) INT_MAX) key = (m << 8) | (unsigned) ck;
+      key = __reduce_min_sync (0xffffffffu, key);
+      if (key == 0xffffffffu) { if (lane == 0) spc.valid = 0; return; }
+      const int bk = (int) (key & 0xff);
+      int dx = __shfl_sync (0xffffffffu, cdx, bk) >> s, dy = __shfl_sync (0xffffffffu, cdy, bk) >> s;
+      clamp_seed (x0, bw0, dx, dy);
+      const Win wn = make_win (x0, bw0, dx, dy);
+      unsigned long long wkey;
+      unsigned wl, wc;
+      scan_part (x0, bw0, wn, lane, 32, wkey, wl, wc);
+      if (lane == 0) { spc.dx = dx; spc.dy = dy; spc.win = wn; spc.key = wkey; spc.luma = wl; spc.chroma = wc; spc.valid = 1; }
+    }
   };
-  static_assert (NW >= 2, "one warp prepares the static candidates of the next block");
+
+  __syncthreads ();
   if (warp == 1) do_static (0);
   __syncthreads ();
 
@@ -283,10 +410,9 @@ hbm_level_kernel (const HbmArgs A)
     const int i = bi * skip;
     const int x0 = (i * A.bw) >> s;
     const bool active = x0 < A.width && y0 < A.height;
-    const int bw0 = min (A.width - x0, A.bw), bh0 = min (A.height - y0, A.bh);
+    const int bw0 = min (A.width - x0, A.bw);
 
-    // ---- warp 1 runs one block ahead: static candidates of block bi+1 (zero + five parents,
-    // schrohierbm.c:259-277, and their ranking SADs) while warp 0 waits for / ranks block bi
+    // ---- warp 1 runs one block ahead
     if (warp == 1 && bi + 1 < A.cols) do_static (bi + 1);
 
     if (warp == 0 && active) {
@@ -299,14 +425,13 @@ hbm_level_kernel (const HbmArgs A)
       unsigned metric = (part == 0 && ck < 6) ? sc.metric[ck] : (unsigned) INT_MAX;   // candidate ck's SAD in lane 3*ck
 
       TRACE (1);
-      // ---- phase B: 6: left 7: up 8: up-left of THIS level (schrohierbm.c:279-294).
-      // left comes from this CTA's previous block; up / up-left are polled straight out of
-      // the row above's published words (up-left was published before up)
+      // ---- 6: left 7: up 8: up-left of THIS level (schrohierbm.c:279-294).  left comes from
+      // this CTA's previous block; up / up-left are polled straight out of the row above's
+      // published words, concurrently (one L2 round trip when both are ready), backing off
+      // between polls so that waiting rows do not crowd the L2 request path
       if (lane == 6 && i > 0) {
         cdx = sh.last_dx; cdy = sh.last_dy; valid = true;
       } else if ((lane == 7 || (lane == 8 && i > 0)) && words_up) {
-        // up and up-left are fetched concurrently (one L2 round trip when both are ready);
-        // back off between polls so that waiting rows do not crowd the L2 request path
         const unsigned long long *wp = words_up + bi - (lane == 8 ? 1 : 0);
         unsigned long long wv = ld_word (wp);
         while (!(wv >> 63)) { __nanosleep (POLL_NS); wv = ld_word (wp); }
@@ -337,7 +462,7 @@ hbm_level_kernel (const HbmArgs A)
         const unsigned reused = __shfl_sync (0xffffffffu, metric, reuse ? src_lane : 0);
         const bool need = ck >= 6 && ck < 9 && ((cmask >> min (ck, 8)) & 1) && !reuse;
         if (__any_sync (0xffffffffu, need)) {
-          const unsigned m = cand_sad (x0, bw0, bh0, part, kdx, kdy, need);
+          const unsigned m = cand_sad (x0, bw0, part, kdx, kdy, need);
           if (need) metric = m;
         }
         if (reuse) metric = reused;
@@ -382,108 +507,53 @@ hbm_level_kernel (const HbmArgs A)
       }
 
       TRACE (3);
-      // ---- seed + scan window (schrohierbm.c:349-364, schrometric.c:174-214) --------
       int dx = __shfl_sync (0xffffffffu, cdx, best_k) >> s;
       int dy = __shfl_sync (0xffffffffu, cdy, best_k) >> s;
-      dx = max (-bw0 - x0, min (A.width - x0, dx));
-      dy = max (-bh0 - y0, min (A.height - y0, dy));
-      if (lane == 0) {
-        const int xmin = max (max (-bw0, x0 + dx - A.h_range), -e);
-        const int ymin = max (max (-bh0, y0 + dy - A.h_range), -e);
-        const int xmax = min (min (A.width, x0 + dx + A.h_range), A.width - bw0 + e);
-        const int ymax = min (min (A.height, y0 + dy + A.h_range), A.height - bh0 + e);
-        sh.xmin = xmin; sh.ymin = ymin;
-        sh.scan_w = xmax - xmin + 1; sh.scan_h = ymax - ymin + 1;
-        sh.seed_a = dx + x0 - xmin; sh.seed_b = dy + y0 - ymin;
+      clamp_seed (x0, bw0, dx, dy);
+      if (SPEC) {
+        // the scan for this seed may already be there
+        const SpecScan &spc = sh.spec[bi & 1];
+        if (spc.valid && spc.dx == dx && spc.dy == dy) {
+          if (lane == 0) publish (bi, i, x0, spc.win, spc.key, spc.luma, spc.chroma);
+        } else {
+          const Win wn = make_win (x0, bw0, dx, dy);
+          unsigned long long wkey;
+          unsigned wl, wc;
+          scan_part (x0, bw0, wn, lane, 32, wkey, wl, wc);
+          if (lane == 0) publish (bi, i, x0, wn, wkey, wl, wc);
+        }
+      } else if (lane == 0) {
+        sh.win = make_win (x0, bw0, dx, dy);
       }
     }
-    if (NW > 1) __syncthreads (); else __syncwarp ();
-
-    TRACE (4);
-    if (active) {
-      const int xmin = sh.xmin, ymin = sh.ymin, scan_w = sh.scan_w, scan_h = sh.scan_h;
-      const int seed_a = sh.seed_a, seed_b = sh.seed_b;
-      // ---- full search: threads over positions, a (x) fastest across lanes ------------
-      // key = (metric, not-seed, a, b): seed wins ties, else first strict minimum in the
-      // reference's a-outer / b-inner order (schrometric.c:121-171)
-      unsigned long long best_key = ~0ull;
-      unsigned best_l = 0, best_c = 0;
-      const uint8_t *sblk = sp[0] + (ptrdiff_t) y0 * ss[0] + x0;
-      const int npos = scan_w * scan_h;
-      const bool fast8 = simd_ok && bw0 == 8 && bh0 == 8;
-      uint2 srow[8];
-      if (fast8) {
-#pragma unroll
-        for (int y = 0; y < 8; y++) srow[y] = __ldg (reinterpret_cast<const uint2 *> (sblk + (ptrdiff_t) y * ss[0]));
-      }
-      for (int p = threadIdx.x; p < npos; p += 32 * NW) {
-        const int b = p / scan_w, a = p - b * scan_w;
-        const uint8_t *rblk = rp[0] + (ptrdiff_t) (ymin + b) * rs[0] + xmin + a;
-        unsigned l = 0;
-        if (fast8) {
-#pragma unroll
-          for (int y = 0; y < 8; y++) {
-            const uint2 bv = load8_unaligned (rblk + (ptrdiff_t) y * rs[0]);
-            l += __vsadu4 (srow[y].x, bv.x) + __vsadu4 (srow[y].y, bv.y);
-          }
-        } else {
-          l = block_sad (sblk, ss[0], rblk, rs[0], bw0, bh0);
-        }
-        unsigned c = 0;
-        if (A.use_chroma) {
-          // chroma_metrics[a*scan_h+b] = sum_k SAD_k at (ref_x/2 + a/2, ref_y/2 + b/2)
-          // (schrometric.c:73-115; C division truncates toward zero)
-          const int cx = x0 / 2, cy = y0 / 2, crx = xmin / 2 + (a >> 1), cry = ymin / 2 + (b >> 1);
-          for (int k = 1; k < 3; k++)
-            c += block_sad (sp[k] + (ptrdiff_t) cy * ss[k] + cx, ss[k], rp[k] + (ptrdiff_t) cry * rs[k] + crx, rs[k],
-                bw0 / 2, bh0 / 2);
-        }
-        const unsigned tot = l + c;
-        const unsigned notseed = (a == seed_a && b == seed_b) ? 0u : 1u;
-        const unsigned long long key = ((unsigned long long) tot << 32) | (notseed << 24) | ((unsigned) a << 12) | (unsigned) b;
-        if (key < best_key) { best_key = key; best_l = l; best_c = c; }
-      }
-      // min over (tot, low bits): two 32-bit REDUX instead of a 64-bit shuffle tree
-      TRACE (5);
-      const unsigned khi = (unsigned) (best_key >> 32), klo = (unsigned) best_key;
-      const unsigned mhi = __reduce_min_sync (0xffffffffu, khi);
-      const unsigned mlo = __reduce_min_sync (0xffffffffu, khi == mhi ? klo : 0xffffffffu);
-      const unsigned long long wkey = ((unsigned long long) mhi << 32) | mlo;
-      const unsigned owner = __ballot_sync (0xffffffffu, best_key == wkey);
-      const int ol = __ffs (owner) - 1;
-      best_l = __shfl_sync (0xffffffffu, best_l, ol);
-      best_c = __shfl_sync (0xffffffffu, best_c, ol);
-      if (NW > 1) {
-        if (lane == 0) { sh.key[warp] = wkey; sh.luma[warp] = best_l; sh.chroma[warp] = best_c; }
+    if (!SPEC) {
+      __syncthreads ();
+      TRACE (4);
+      if (active) {
+        const Win wn = sh.win;
+        unsigned long long wkey;
+        unsigned wl, wc;
+        scan_part (x0, bw0, wn, threadIdx.x, 32 * NW, wkey, wl, wc);
+        TRACE (5);
+        if (lane == 0) { sh.key[warp] = wkey; sh.luma[warp] = wl; sh.chroma[warp] = wc; }
         __syncthreads ();
-      }
-      if (threadIdx.x == 0) {
-        unsigned long long k = wkey;
-        unsigned bl = best_l, bc = best_c;
-        if (NW > 1) {
+        if (threadIdx.x == 0) {
+          unsigned long long k = sh.key[0];
+          unsigned bl = sh.luma[0], bc = sh.chroma[0];
 #pragma unroll
           for (int w = 1; w < NW; w++)
             if (sh.key[w] < k) { k = sh.key[w]; bl = sh.luma[w]; bc = sh.chroma[w]; }
+          TRACE (6);
+          publish (bi, i, x0, wn, k, bl, bc);
         }
-        const int a = (int) ((k >> 12) & 0xfff), b = (int) (k & 0xfff);
-        const int rdx = (xmin + a - x0) << s, rdy = (ymin + b - y0) << s;
-        TRACE (6);
-        // publish first (the row below is waiting on it), then fill in the output field
-        st_word (words_me + bi, pack_word ((int16_t) rdx, (int16_t) rdy));
-        sh.last_dx = (int16_t) rdx; sh.last_dy = (int16_t) rdy;
-        MotionVector *o = mf + (size_t) j * A.nbx + i;
-        o->metric = bl;
-        o->chroma_metric = bc;
-        o->v[ri] = (int16_t) rdx;
-        o->v[2 + ri] = (int16_t) rdy;
-        o->flags = A.flags0;
       }
-    } else if (threadIdx.x == 0) {
+    }
+    if (!active && threadIdx.x == 0) {
       // a block outside the picture keeps the zero vector of schro_motion_field_set
       st_word (words_me + bi, pack_word (0, 0));
       sh.last_dx = 0; sh.last_dy = 0;
     }
-    if (NW > 1) __syncthreads (); else __syncwarp ();
+    __syncthreads ();
   }
 }
 
