@@ -448,6 +448,15 @@ class HostFrames:
         """Stop the worker threads while CUDA is still alive (their thread-exit hooks release
         per-thread streams and buffers)."""
         if hasattr(self, "pool"):
+            import threading as _t
+            gate = _t.Barrier(self.nthreads)
+
+            def release():
+                gate.wait()                      # one task per worker thread
+                self.lib.schro_b200_thread_release()
+
+            for f in [self.pool.submit(release) for _ in range(self.nthreads)]:
+                f.result()
             self.pool.shutdown(wait=True)
             del self.pool
 

@@ -270,6 +270,9 @@ void schro_init (void);                                   /* schroedinger/schro.
 /* new: the GPU this process's picture core runs on (default: the device current on the
  * first thread that calls into the library); worker threads inherit it */
 void schro_b200_set_device (int device);
+/* new: release the calling thread's stream / staging buffers / device-block pool (call
+ * before a worker thread exits; long-lived workers never need it) */
+void schro_b200_thread_release (void);
 /* schroedinger/schrocuda.h:9 (schro_memory_domain_new_cuda) */
 SchroMemoryDomain *schro_memory_domain_new_cuda (void);
 SchroMemoryDomain *schro_memory_domain_new_pinned (void); /* new: cudaHostAlloc'd frames */

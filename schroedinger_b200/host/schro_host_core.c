@@ -71,43 +71,37 @@ schro_b200_set_device (int device)
   SB2H_CUDA (cudaSetDevice (device));
 }
 
-/* thread exit: give the thread's stream, staging buffers and pooled blocks back */
-static pthread_key_t cx_key;
-static pthread_once_t cx_key_once = PTHREAD_ONCE_INIT;
 static void sb2h_pool_release_all (void);
 
-/* set at process exit: thread destructors that run during teardown must not touch CUDA */
-static volatile int g_shutting_down;
-static void mark_shutdown (void) { g_shutting_down = 1; }
-
-static void
-cx_destroy (void *p)
+/* Give the calling thread's stream, staging buffers and pooled device blocks back.  Worker
+ * threads are expected to be long-lived (as SchroAsync's are); a thread that does exit
+ * should call this first.  There is deliberately no automatic thread-exit hook: it would
+ * also run during process teardown, after the CUDA runtime has been unloaded. */
+void
+schro_b200_thread_release (void)
 {
-  Sb2hContext *cx = p;
+  Sb2hContext *cx = tl_cx;
   int i;
-  if (!cx || g_shutting_down) return;
+  if (!cx) return;
   cudaStreamSynchronize (cx->stream);
   for (i = 0; i < SB2H_NBUF; i++)
     if (cx->dev[i]) cudaFree (cx->dev[i]);
   sb2h_pool_release_all ();
   cudaStreamDestroy (cx->stream);
   free (cx);
+  tl_cx = NULL;
 }
-
-static void cx_key_make (void) { pthread_key_create (&cx_key, cx_destroy); atexit (mark_shutdown); }
 
 Sb2hContext *
 sb2h_context (void)
 {
   if (!tl_cx) {
-    pthread_once (&cx_key_once, cx_key_make);
     pthread_mutex_lock (&g_device_mutex);
     if (g_device < 0) SB2H_CUDA (cudaGetDevice (&g_device));
     pthread_mutex_unlock (&g_device_mutex);
     SB2H_CUDA (cudaSetDevice (g_device));
     tl_cx = calloc (1, sizeof (Sb2hContext));
     SB2H_CUDA (cudaStreamCreateWithFlags (&tl_cx->stream, cudaStreamNonBlocking));
-    pthread_setspecific (cx_key, tl_cx);
   }
   return tl_cx;
 }
