@@ -138,13 +138,33 @@ def make_mv_field(nbx, nby, rng):
     return mv
 
 
+CONTENT = "natural"
+
+
 def textured_frame(width, height, rng, pan=(0, 0)):
-    """One u8 4:2:0 picture: smooth texture + noise, optionally panned."""
+    """One u8 4:2:0 picture: smooth texture + per-frame noise, optionally panned.
+
+    "natural" (default): 20 plane waves of random direction, wavelengths log-uniform in 24..600 px and
+    amplitude rising with wavelength -- no repeat inside any search window, so block matching finds the pan.
+    "periodic": the round-1a texture, one 56 x 44 px cell repeated; its aliases at the coarse pyramid levels
+    make the motion field incoherent (a worst case for the block matcher, kept for DESIGN.md's comparison)."""
     yy, xx = np.mgrid[0:height, 0:width]
-    xx = xx + pan[0]
-    yy = yy + pan[1]
-    y = (128 + 50 * np.sin(xx / 9.0) * np.cos(yy / 7.0) + 30 * np.sin((xx + 2 * yy) / 31.0)
-         + rng.integers(-12, 13, size=(height, width)))
+    xx = (xx + pan[0]).astype(np.float32)
+    yy = (yy + pan[1]).astype(np.float32)
+    if CONTENT == "periodic":
+        y = 128 + 50 * np.sin(xx / 9.0) * np.cos(yy / 7.0) + 30 * np.sin((xx + 2 * yy) / 31.0)
+    else:
+        wrng = np.random.default_rng(424242)                 # the texture itself is the same for every frame
+        lam = np.exp(wrng.uniform(np.log(24.0), np.log(600.0), 20))
+        ang = wrng.uniform(0, 2 * np.pi, 20)
+        ph = wrng.uniform(0, 2 * np.pi, 20)
+        amp = lam ** 0.6
+        amp *= 45.0 / np.sqrt(0.5 * np.sum(amp ** 2))
+        y = np.full((height, width), 128.0, np.float32)
+        for k in range(20):
+            kx, ky = 2 * np.pi / lam[k] * np.cos(ang[k]), 2 * np.pi / lam[k] * np.sin(ang[k])
+            y += np.float32(amp[k]) * np.sin(np.float32(kx) * xx + np.float32(ky) * yy + np.float32(ph[k]))
+    y = y + rng.integers(-12, 13, size=(height, width))
     y = np.clip(y, 0, 255).astype(np.uint8)
     c = y[::2, ::2]
     return [y, np.ascontiguousarray(255 - c), np.ascontiguousarray((c // 2 + 64).astype(np.uint8))]
@@ -520,7 +540,7 @@ def run_ours(args):
     # ---- e2e through the drop-in C API with pinned host frames ----
     e2e = None
     try:
-        nthreads = min(4, B)
+        nthreads = min(args.e2e_threads, B)
         hf = HostFrames(spec, lib, nthreads)
         for _ in range(3):
             hf.step()
@@ -585,7 +605,7 @@ def run_ours(args):
         "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "s32" if spec["depth_name"] == "s32" else "s16",
         "data": "synthetic",
-        "config": {"workload": args.workload, "what": spec["label"], "batch_per_gpu": B,
+        "config": {"workload": args.workload, "what": spec["label"], "content": args.content, "batch_per_gpu": B,
                    "stages": [s["name"] for s in st.stages],
                    "l2": f"inputs larger than L2: {st.working_set / 1e6:.0f} MB working set per step",
                    "parallelism": f"picture-parallel x{world}, no collective"},
@@ -745,7 +765,8 @@ def run_reference(args):
         "ms_per_step": round(cb["seconds"] / max(1, args.steps) * 1e3, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "s32" if spec["depth_name"] == "s32" else "s16",
         "data": "synthetic",
-        "config": {"workload": args.workload, "what": spec["label"], "batch_per_gpu": spec["batch"]},
+        "config": {"workload": args.workload, "what": spec["label"], "content": args.content,
+                   "batch_per_gpu": spec["batch"]},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": round(time.perf_counter() - t0, 2),
@@ -761,12 +782,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="picture_core_2160p")
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--content", default="natural", choices=["natural", "periodic"],
+                    help="texture of the synthetic pictures (see textured_frame)")
+    ap.add_argument("--e2e-threads", type=int, default=4, help="host threads driving the drop-in API in the e2e leg")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--overlap", action="store_true",
                     help="run the motion-estimation stages on a second stream (measured: no gain, "
                          "the wavefront kernel's resident rows already fill the register file)")
     args = ap.parse_args()
+    global CONTENT
+    CONTENT = args.content
     if args.impl == "reference":
         run_reference(args)
     else:

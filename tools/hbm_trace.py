@@ -3,6 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, bench
 from schroedinger_b200 import device as dev, lib
 spec = bench.workload_spec("picture_core_2160p"); spec["batch"] = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+bench.CONTENT = sys.argv[2] if len(sys.argv) > 2 else "natural"
 st = bench.Stages(spec, torch, dev)
 for _ in range(3): st.step()
 torch.cuda.synchronize()
@@ -10,8 +11,12 @@ buf = np.zeros(512 * 8, np.int64)
 lib.sb2_hbm_trace_read(buf.ctypes.data_as(ctypes.c_void_p), 512 * 8)
 t = buf.reshape(512, 8)[50:450]
 d = np.diff(t[:, :7], axis=1)
-names = ["A static cands", "wait+nbr+dedup", "rank (nbr SADs)", "seed+sync", "scan", "reduce+sync+sel"]
-print("batch", spec["batch"], "per-block cycles (row 100, level 0), median / mean:")
+names = ["wait slot", "poll+dedup", "rank", "seed+window", "scan", "reduce"] if os.environ.get("SB2_HBM_WINDOW") else ["A static cands", "poll+dedup", "rank (nbr SADs)", "seed+sync", "scan", "reduce+sync+sel"]
+print("batch", spec["batch"], bench.CONTENT, "per-block cycles (row 100, level 0), median / mean:")
 for k, n in enumerate(names): print(f"  {n:18s} {np.median(d[:,k]):8.0f} {d[:,k].mean():8.0f}")
 tot = np.diff(t[:, 0])
 print("  block-to-block     ", np.median(tot), tot.mean())
+
+cnt = np.zeros(8, np.uint64)
+lib.sb2_hbm_count_read(cnt.ctypes.data_as(ctypes.c_void_p))
+print("level-0 counters: blocks", cnt[0], "slow rank cands (chain)", cnt[1], "scan fallbacks", cnt[2], "slow static cands", cnt[3])
