@@ -17,7 +17,6 @@
 #include "common.cuh"
 #include <climits>
 #include <cstdio>
-#include <cstdlib>
 
 namespace sb2 {
 
@@ -144,12 +143,9 @@ __device__ __forceinline__ unsigned load4_unaligned (const uint8_t *p)
 
 #ifdef SB2_HBM_TRACE
 __device__ long long g_hbm_trace[512 * 8];
-__device__ unsigned long long g_hbm_count[8];
-#define COUNT(k) do { if (lane == 0 && A.shift == 0) atomicAdd (&g_hbm_count[k], 1ull); } while (0)
 #define TRACE(k) do { if (trace_on && threadIdx.x == 0 && bi < 512) g_hbm_trace[bi * 8 + (k)] = clock64 (); } while (0)
 #else
 #define TRACE(k) do { } while (0)
-#define COUNT(k) do { } while (0)
 #endif
 
 #ifndef POLL_NS
@@ -194,7 +190,7 @@ struct BlockShared {
 // longer loop and misses pay a single-warp scan -- so it is compiled out; kept because it
 // wins when vectors are coherent (hit rate near 1) and the chain is poll -> rank -> publish.
 template <int NW, bool SPEC = false>
-__global__ void __launch_bounds__ (32 * NW, NW == 2 ? 16 : 1)
+__global__ void __launch_bounds__ (32 * NW)
 hbm_level_kernel (const HbmArgs A)
 {
   static_assert (NW >= 2, "one warp prepares the static candidates of the next block");
@@ -562,637 +558,6 @@ hbm_level_kernel (const HbmArgs A)
 }
 
 
-// =============================================================================================
-// Window kernel: the same search, restructured so that nothing on the per-block dependent chain
-// touches global memory except the neighbour word (prefetched one block ahead).
-//
-// Two warps per block row.  Warp 1 (producer) runs ahead through a ring of D slots: for block nb
-// it reads the static candidates (zero + five parents), stages into shared memory the reference
-// window -- every displacement within +-RW of the block's own parent vector, luma and both
-// chroma planes, 16-byte chunks with addresses clamped to the edge-extended plane -- plus the
-// source block, and ranks the static candidates out of that window.  Warp 0 (chain) waits for
-// the slot, adds left / up / up-left, ranks, scans and publishes, all out of the slot.  A
-// candidate or scan window that leaves the staged window falls back to global-memory code
-// executed by the chain warp alone (bit-identical, slower, rare on coherent motion).
-// Partial blocks at the right / bottom picture edge use byte masks instead of a generic path.
-template <int RW> struct WinGeom {
-  static constexpr int LROWS = 2 * RW + 8;               // luma rows in the window
-  static constexpr int LCH = (2 * RW + 8 + 30) / 16;     // 16-byte chunks per luma row (any misalignment)
-  static constexpr int LP = LCH * 4;                     // luma pitch in 32-bit words
-  static constexpr int CROWS = RW + 6;
-  static constexpr int CCH = (RW + 6 + 30) / 16;
-  static constexpr int CP = CCH * 4;
-  static constexpr int NL = LROWS * LCH, NC = CROWS * CCH;
-  static constexpr int NCHUNK = NL + 2 * NC;
-  static constexpr int NT = (NCHUNK + 31) / 32;          // chunks per producer lane
-  static constexpr int MW = 2 * RW + 1;                  // luma SAD map is MW x MW displacements
-  static constexpr int CMW = RW + 2;                     // chroma SAD map is CMW x CMW chroma positions
-  static_assert (MW <= 16 && CMW <= 16, "map columns are spread over 16 lanes");
-};
-
-template <int RW> struct WinSlot {
-  uint4 win[WinGeom<RW>::NCHUNK];   // luma rows, then chroma 1 rows, then chroma 2 rows
-  uint2 src_l[8];                   // source block, bytes beyond (bw0, bh0) zeroed
-  unsigned src_c[2][4];
-  int cdx[6], cdy[6];               // static candidate vectors (full-resolution units)
-  unsigned metric[6];               // their ranking SADs
-  unsigned valid;
-  int xb, yt, cxb, cyt;             // picture coordinates of byte 0 / row 0 of the luma / chroma windows
-  int cxl;                          // chroma x of chroma-map column 0 (chroma-map row 0 is cyt)
-  int lo_dx, lo_dy;                 // the window holds displacements lo .. lo + 2 RW
-  // SAD maps, computed by the producer out of the window: lmap[b][a] = luma SAD of the source
-  // block at displacement (lo_dx + a, lo_dy + b); cmap[cb][ca] = both chroma SADs (ranking
-  // geometry) at chroma position (cxl + ca, cyt + cb)
-  unsigned short lmap[WinGeom<RW>::MW * WinGeom<RW>::MW];
-  unsigned short cmap[WinGeom<RW>::CMW * WinGeom<RW>::CMW];
-};
-
-__device__ __forceinline__ int ld_acquire_smem (const int *p)
-{
-  int v;
-  asm volatile ("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned) __cvta_generic_to_shared (p)) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_smem (int *p, int v)
-{
-  asm volatile ("st.release.cta.shared.s32 [%0], %1;" :: "r"((unsigned) __cvta_generic_to_shared (p)), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned byte_mask (int n)      // low n bytes, n clipped to 0..4
-{
-  return n >= 4 ? 0xffffffffu : n <= 0 ? 0u : ((1u << (8 * n)) - 1u);
-}
-
-// per-row / per-block geometry shared by both warps (warp-uniform)
-struct RowGeom {
-  int y0, bh0;                      // block row origin / clipped height
-  int rch, sch;                     // chroma rows in the ranking SAD / in the scan SAD
-};
-struct BlkGeom {
-  int x0, bw0;
-  bool active, full;                // full: no masking needed anywhere
-  unsigned mlo, mhi;                // luma byte masks (bw0)
-  unsigned rcm, scm;                // chroma byte masks: ranking (clipped to the plane) / scan (bw0 / 2)
-};
-
-template <int RW, bool MASKED>
-__device__ __forceinline__ unsigned win_luma_rows (const WinSlot<RW> &S, const uint2 *src, int x, int y, int r0, int nrows,
-    const BlkGeom &B)
-{
-  using G = WinGeom<RW>;
-  const int off = x - S.xb;
-  const unsigned *w = reinterpret_cast<const unsigned *> (S.win) + (y + r0 - S.yt) * G::LP + (off >> 2);
-  const unsigned sh = (unsigned) (off & 3) * 8;
-  unsigned acc = 0;
-#pragma unroll
-  for (int r = 0; r < 8; r++) {
-    if (r < nrows) {
-      const unsigned w0 = w[r * G::LP], w1 = w[r * G::LP + 1], w2 = w[r * G::LP + 2];
-      unsigned b0 = __funnelshift_r (w0, w1, sh), b1 = __funnelshift_r (w1, w2, sh);
-      if (MASKED) { b0 &= B.mlo; b1 &= B.mhi; }
-      acc += __vsadu4 (src[r].x, b0) + __vsadu4 (src[r].y, b1);
-    }
-  }
-  return acc;
-}
-
-// both chroma planes, 4-byte rows at chroma position (cx, cy); `mask` clips the width
-template <int RW>
-__device__ __forceinline__ unsigned win_chroma (const WinSlot<RW> &S, int cx, int cy, int nrows, unsigned mask)
-{
-  using G = WinGeom<RW>;
-  const int off = cx - S.cxb;
-  const unsigned sh = (unsigned) (off & 3) * 8;
-  unsigned acc = 0;
-#pragma unroll
-  for (int c = 0; c < 2; c++) {
-    const unsigned *w = reinterpret_cast<const unsigned *> (S.win + G::NL + c * G::NC) + (cy - S.cyt) * G::CP + (off >> 2);
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      if (r < nrows) {
-        const unsigned b = __funnelshift_r (w[r * G::CP], w[r * G::CP + 1], sh) & mask;
-        acc += __vsadu4 (S.src_c[c][r] & mask, b);
-      }
-    }
-  }
-  return acc;
-}
-
-template <int RW, int NP, int D>
-__global__ void __launch_bounds__ (32 * (1 + NP), NP == 1 ? 16 : 10)
-hbm_win_kernel (const HbmArgs A)
-{
-  using G = WinGeom<RW>;
-  __shared__ WinSlot<RW> ring[D];
-  __shared__ int ready[D];
-  __shared__ int consumed;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row = blockIdx.x / A.count, pic = blockIdx.x % A.count;   // row r is launched before r+1
-  const int skip = 1 << A.shift, s = A.shift;
-  const int j = row * skip;
-  const int ri = A.ref_index;
-  const int e = A.ext;
-
-  const uint8_t *sp[3], *rp[3];
-  int ss[3], rs[3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    sp[k] = reinterpret_cast<const uint8_t *> (plane_ptr (A.src, pic, k));
-    rp[k] = reinterpret_cast<const uint8_t *> (plane_ptr (A.ref, pic, k));
-    ss[k] = A.src.stride[k];
-    rs[k] = A.ref.stride[k];
-  }
-  MotionVector *mf = A.field + (size_t) pic * A.field_pitch;
-  const MotionVector *pf = A.parent ? A.parent + (size_t) pic * A.field_pitch : nullptr;
-  unsigned long long *words_me = A.words + ((size_t) pic * A.rows + row) * A.cols;
-  const unsigned long long *words_up = row > 0 ? words_me - A.cols : nullptr;
-  const int hint_mask = ~((1 << (s + 1)) - 1);
-
-  RowGeom R;
-  R.y0 = (j * A.bh) >> s;
-  R.bh0 = min (A.height - R.y0, 8);
-  R.rch = min (max (0, A.ch - (R.y0 >> 1)), 4);
-  R.sch = R.bh0 / 2;
-  const int y0 = R.y0, bh0 = R.bh0;
-  const bool row_active = y0 < A.height;
-
-  auto blk_geom = [&] (int nb) -> BlkGeom {
-    BlkGeom B;
-    B.x0 = ((nb * skip) * A.bw) >> s;
-    B.active = row_active && B.x0 < A.width;
-    B.bw0 = min (A.width - B.x0, 8);
-    const int rcw = min (max (0, A.cw - (B.x0 >> 1)), 4);
-    B.full = B.bw0 == 8 && bh0 == 8 && rcw == 4 && R.rch == 4;
-    B.mlo = byte_mask (B.bw0);
-    B.mhi = byte_mask (B.bw0 - 4);
-    B.rcm = byte_mask (rcw);
-    B.scm = byte_mask (B.bw0 / 2);
-    return B;
-  };
-
-  // clamp of a candidate vector (schrometric.c:343-352) and the legality test of the ranking SAD
-  auto cand_disp = [&] (const BlkGeom &B, int vx, int vy, int &dx, int &dy) -> bool {
-    dx = clampi ((vx >> s) + B.x0, -B.bw0, A.width) - B.x0;
-    dy = clampi ((vy >> s) + y0, -bh0, A.height) - y0;
-    return !(B.x0 < -e || y0 < -e || B.x0 + 8 > A.width + e || y0 + 8 > A.height + e) &&
-        !(B.x0 + dx < -e || y0 + dy < -e || B.x0 + dx + 8 > A.width + e || y0 + dy + 8 > A.height + e);
-  };
-  auto in_window = [&] (const WinSlot<RW> &S, int dx, int dy) -> bool {
-    return (unsigned) (dx - S.lo_dx) <= 2u * RW && (unsigned) (dy - S.lo_dy) <= 2u * RW;
-  };
-  // ranking SAD of one candidate out of the window: three lanes per candidate (luma rows 0-3,
-  // luma rows 4-7, chroma), summed into the first.  Returns INT_MAX for an illegal candidate;
-  // `slow` is set when a legal candidate lies outside the window.
-  auto cand_metric_win = [&] (const WinSlot<RW> &S, const BlkGeom &B, int part, int vx, int vy, bool want, bool &slow) -> unsigned {
-    int dx, dy;
-    const bool ok = cand_disp (B, vx, vy, dx, dy);
-    const bool inw = in_window (S, dx, dy);
-    slow = want && ok && !inw && !B.full;
-    unsigned ps = 0;
-    if (want && ok && !inw && B.full) {
-      // outside the staged window: the same three-lane split straight from global memory
-      if (part < 2) {
-        const uint8_t *b = rp[0] + (ptrdiff_t) (y0 + dy + 4 * part) * rs[0] + B.x0 + dx;
-#pragma unroll
-        for (int y = 0; y < 4; y++) {
-          const uint2 av = S.src_l[4 * part + y];
-          const uint2 bv = load8_unaligned (b + (ptrdiff_t) y * rs[0]);
-          ps += __vsadu4 (av.x, bv.x) + __vsadu4 (av.y, bv.y);
-        }
-      } else {
-        const int rx = (B.x0 + dx) >> 1, ry = (y0 + dy) >> 1;
-#pragma unroll
-        for (int c = 1; c < 3; c++) {
-#pragma unroll
-          for (int y = 0; y < 4; y++)
-            ps += __vsadu4 (S.src_c[c - 1][y], load4_unaligned (rp[c] + (ptrdiff_t) (ry + y) * rs[c] + rx));
-        }
-      }
-    } else if (want && ok && inw) {
-      if (part < 2) {
-        const int nr = min (4, bh0 - 4 * part);
-        ps = B.full ? win_luma_rows<RW, false> (S, S.src_l + 4 * part, B.x0 + dx, y0 + dy, 4 * part, 4, B)
-                    : win_luma_rows<RW, true> (S, S.src_l + 4 * part, B.x0 + dx, y0 + dy, 4 * part, min (nr, 4), B);
-      } else {
-        ps = win_chroma<RW> (S, (B.x0 + dx) >> 1, (y0 + dy) >> 1, R.rch, B.rcm);
-      }
-    }
-    unsigned m = ps + __shfl_down_sync (0xffffffffu, ps, 1);
-    m += __shfl_down_sync (0xffffffffu, ps, 2);
-    return ok ? m : (unsigned) INT_MAX;
-  };
-  // the same SAD straight from global memory, whole warp on one candidate (schrometric.c:332-375)
-  auto cand_metric_global = [&] (const BlkGeom &B, int vx, int vy) -> unsigned {
-    int dx, dy;
-    if (!cand_disp (B, vx, vy, dx, dy)) return (unsigned) INT_MAX;
-    unsigned part_sum = 0;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const int hs = c ? 1 : 0;
-      const int sx = B.x0 >> hs, sy = y0 >> hs, rx = (B.x0 + dx) >> hs, ry = (y0 + dy) >> hs;
-      const int w = min (max (0, (c ? A.cw : A.width) - sx), 8 >> hs);
-      const int h = min (max (0, (c ? A.ch : A.height) - sy), 8 >> hs);
-      for (int p = lane; p < w * h; p += 32) {
-        const int yy = p / w, xx = p - yy * w;
-        part_sum += (unsigned) abs ((int) __ldg (sp[c] + (ptrdiff_t) (sy + yy) * ss[c] + sx + xx)
-            - (int) __ldg (rp[c] + (ptrdiff_t) (ry + yy) * rs[c] + rx + xx));
-      }
-    }
-    return warp_sum (part_sum);
-  };
-  auto make_win = [&] (const BlkGeom &B, int dx, int dy) -> Win {
-    Win w;
-    w.xmin = max (max (-B.bw0, B.x0 + dx - A.h_range), -e);
-    w.ymin = max (max (-bh0, y0 + dy - A.h_range), -e);
-    const int xmax = min (min (A.width, B.x0 + dx + A.h_range), A.width - B.bw0 + e);
-    const int ymax = min (min (A.height, y0 + dy + A.h_range), A.height - bh0 + e);
-    w.scan_w = xmax - w.xmin + 1;
-    w.scan_h = ymax - w.ymin + 1;
-    w.seed_a = dx + B.x0 - w.xmin;
-    w.seed_b = dy + y0 - w.ymin;
-    return w;
-  };
-
-  // ranking SAD of an in-window displacement out of the maps
-  auto map_metric = [&] (const WinSlot<RW> &S, const BlkGeom &B, int dx, int dy) -> unsigned {
-    const unsigned l = S.lmap[(dy - S.lo_dy) * G::MW + (dx - S.lo_dx)];
-    const unsigned c = S.cmap[(((y0 + dy) >> 1) - S.cyt) * G::CMW + (((B.x0 + dx) >> 1) - S.cxl)];
-    return l + c;
-  };
-
-  if (threadIdx.x < D) ready[threadIdx.x] = 0;
-  if (threadIdx.x == 0) consumed = 0;
-  __syncthreads ();
-
-  if (warp >= 1) {
-    // =========================== producers ===========================
-    // producer q handles blocks q, q + NP, ...
-    const int q = warp - 1;
-    // which chunk of the window this lane moves in round t: plane | row | chunk-in-row
-    int cd[G::NT];
-#pragma unroll
-    for (int t = 0; t < G::NT; t++) {
-      const int idx = lane + 32 * t;
-      if (idx < G::NL) cd[t] = ((idx / G::LCH) << 8) | (idx % G::LCH);
-      else if (idx < G::NCHUNK) {
-        const int qq = idx - G::NL, pl = qq / G::NC, r = qq - pl * G::NC;
-        cd[t] = ((1 + pl) << 16) | ((r / G::CCH) << 8) | (r % G::CCH);
-      } else cd[t] = 3 << 16;
-    }
-    // static candidates of block nb: 0 zero, 1..5 parents (0,0) (-1,0) (1,0) (0,-1) (0,1)
-    // (schrohierbm.c:259-277), one per lane
-    auto load_static = [&] (int nb, int &vx, int &vy, bool &valid) {
-      vx = 0; vy = 0; valid = lane == 0;
-      if (lane >= 1 && lane <= 5 && pf && nb < A.cols) {
-        const int i = nb * skip;
-        const int ox = (lane == 2) ? -1 : (lane == 3) ? 1 : 0;
-        const int oy = (lane == 4) ? -1 : (lane == 5) ? 1 : 0;
-        const int ll = (i & hint_mask) + ox * skip * 2, kk = (j & hint_mask) + oy * skip * 2;
-        if (ll >= 0 && ll < A.nbx && kk >= 0 && kk < A.nby) {
-          const MotionVector *m = pf + (size_t) kk * A.nbx + ll;
-          vx = m->v[ri]; vy = m->v[2 + ri]; valid = true;
-        }
-      }
-    };
-    int nvx, nvy;
-    bool nvalid;
-    load_static (q, nvx, nvy, nvalid);
-    for (int nb = q; nb < A.cols; nb += NP) {
-      WinSlot<RW> &S = ring[nb % D];
-      const int vx = nvx, vy = nvy;
-      const bool valid = nvalid;
-      load_static (nb + NP, nvx, nvy, nvalid);            // parents of this producer's next block: in flight during this one
-      if (nb >= D) while (ld_acquire_smem (&consumed) < nb - D + 1) __nanosleep (20);
-      const BlkGeom B = blk_geom (nb);
-      if (B.active) {
-        // window centre: this block's own parent vector (else zero), clamped like a candidate
-        const int pvalid = __shfl_sync (0xffffffffu, (int) valid, 1);
-        const int cvx = pvalid ? __shfl_sync (0xffffffffu, vx, 1) : 0, cvy = pvalid ? __shfl_sync (0xffffffffu, vy, 1) : 0;
-        int cx, cy;
-        cand_disp (B, cvx, cvy, cx, cy);
-        const int xl = B.x0 + cx - RW, yt = y0 + cy - RW;
-        const int xb = xl - (int) ((size_t) (rp[0] + xl) & 15);
-        const int cxl = xl >> 1, cyt = yt >> 1;
-        const int cxb = cxl - (int) ((size_t) (rp[1] + cxl) & 15);
-        uint4 v[G::NT];
-#pragma unroll
-        for (int t = 0; t < G::NT; t++) {
-          const int pl = cd[t] >> 16, r = (cd[t] >> 8) & 0xff, c = cd[t] & 0xff;
-          if (pl < 3) {
-            const int ph = pl ? A.ch : A.height, st = pl == 0 ? rs[0] : pl == 1 ? rs[1] : rs[2];
-            const uint8_t *base = pl == 0 ? rp[0] : pl == 1 ? rp[1] : rp[2];
-            const int yy = clampi ((pl ? cyt : yt) + r, -e, ph + e - 1);
-            const int xx = clampi ((pl ? cxb : xb) + 16 * c, -e, -e + st - 16);
-            v[t] = __ldg (reinterpret_cast<const uint4 *> (base + (ptrdiff_t) yy * st + xx));
-          }
-        }
-        uint2 sl = make_uint2 (0, 0);
-        unsigned sc_ = 0;
-        if (lane < 8) {
-          if (lane < bh0) {
-            sl = __ldg (reinterpret_cast<const uint2 *> (sp[0] + (ptrdiff_t) (y0 + lane) * ss[0] + B.x0));
-            sl.x &= B.mlo; sl.y &= B.mhi;
-          }
-        } else if (lane < 16) {
-          const int c = (lane - 8) >> 2, r = lane & 3;
-          // rows beyond the plane are masked out by the row counts of the readers
-          const int yy = min ((y0 >> 1) + r, A.ch + e - 1);
-          sc_ = __ldg (reinterpret_cast<const unsigned *> (sp[1 + c] + (ptrdiff_t) yy * ss[1 + c] + (B.x0 >> 1)));
-        }
-#pragma unroll
-        for (int t = 0; t < G::NT; t++)
-          if (lane + 32 * t < G::NCHUNK) S.win[lane + 32 * t] = v[t];
-        if (lane < 8) S.src_l[lane] = sl;
-        else if (lane < 16) S.src_c[(lane - 8) >> 2][lane & 3] = sc_;
-        if (lane < 6) { S.cdx[lane] = vx; S.cdy[lane] = vy; }
-        const unsigned vm = __ballot_sync (0xffffffffu, valid && lane < 6);
-        if (lane == 0) {
-          S.valid = vm; S.xb = xb; S.yt = yt; S.cxb = cxb; S.cyt = cyt; S.cxl = cxl; S.lo_dx = cx - RW; S.lo_dy = cy - RW;
-        }
-        __syncwarp ();
-
-        // ---- luma SAD map.  Lane (a, h) owns map column a and source rows 4h..4h+3: it walks
-        // down the window once, each reference row feeding the (up to) four map rows it belongs to.
-        {
-          const int a = lane & 15, h = lane >> 4;
-          unsigned acc[G::MW];
-#pragma unroll
-          for (int b = 0; b < G::MW; b++) acc[b] = 0;
-          if (a < G::MW) {
-            uint2 sr[4];
-#pragma unroll
-            for (int y = 0; y < 4; y++) sr[y] = S.src_l[4 * h + y];
-            const int off = xl + a - xb;
-            const unsigned *w = reinterpret_cast<const unsigned *> (S.win) + (4 * h) * G::LP + (off >> 2);
-            const unsigned sh = (unsigned) (off & 3) * 8;
-#pragma unroll
-            for (int r = 0; r < G::MW + 3; r++) {
-              unsigned b0 = __funnelshift_r (w[r * G::LP], w[r * G::LP + 1], sh);
-              unsigned b1 = __funnelshift_r (w[r * G::LP + 1], w[r * G::LP + 2], sh);
-              if (!B.full) { b0 &= B.mlo; b1 &= B.mhi; }
-#pragma unroll
-              for (int y = 0; y < 4; y++) {
-                const int b = r - y;
-                if (b >= 0 && b < G::MW && (B.full || 4 * h + y < bh0))
-                  acc[b] += __vsadu4 (sr[y].x, b0) + __vsadu4 (sr[y].y, b1);
-              }
-            }
-          }
-#pragma unroll
-          for (int b = 0; b < G::MW; b++) {
-            const unsigned t = acc[b] + __shfl_xor_sync (0xffffffffu, acc[b], 16);
-            if (h == 0 && a < G::MW) S.lmap[b * G::MW + a] = (unsigned short) t;
-          }
-        }
-        // ---- chroma SAD map (ranking geometry: R.rch rows, width mask B.rcm); lane (ca, k)
-        {
-          const int ca = lane & 15, k = lane >> 4;
-          unsigned acc[G::CMW];
-#pragma unroll
-          for (int b = 0; b < G::CMW; b++) acc[b] = 0;
-          if (ca < G::CMW) {
-            unsigned sc[4];
-#pragma unroll
-            for (int y = 0; y < 4; y++) sc[y] = S.src_c[k][y] & B.rcm;
-            const int off = cxl + ca - cxb;
-            const unsigned *w = reinterpret_cast<const unsigned *> (S.win + G::NL + k * G::NC) + (off >> 2);
-            const unsigned sh = (unsigned) (off & 3) * 8;
-#pragma unroll
-            for (int r = 0; r < G::CMW + 3; r++) {
-              const unsigned bb = __funnelshift_r (w[r * G::CP], w[r * G::CP + 1], sh) & B.rcm;
-#pragma unroll
-              for (int y = 0; y < 4; y++) {
-                const int b = r - y;
-                if (b >= 0 && b < G::CMW && y < R.rch) acc[b] += __vsadu4 (sc[y], bb);
-              }
-            }
-          }
-#pragma unroll
-          for (int b = 0; b < G::CMW; b++) {
-            const unsigned t = acc[b] + __shfl_xor_sync (0xffffffffu, acc[b], 16);
-            if (k == 0 && ca < G::CMW) S.cmap[b * G::CMW + ca] = (unsigned short) t;
-          }
-        }
-        __syncwarp ();
-        // ---- rank the static candidates: a map lookup, or global memory when outside the window
-        unsigned m = (unsigned) INT_MAX;
-        bool far = false;
-        if (lane < 6 && valid) {
-          int dx, dy;
-          if (cand_disp (B, vx, vy, dx, dy)) {
-            if (in_window (S, dx, dy)) m = map_metric (S, B, dx, dy);
-            else far = true;
-          }
-        }
-        const unsigned farmask = __ballot_sync (0xffffffffu, far);
-        if (farmask) {
-          if (B.full) {
-            // all of them at once, three lanes per candidate
-            const int ck = lane / 3, part = lane - 3 * ck;
-            const int kvx = __shfl_sync (0xffffffffu, vx, min (ck, 5)), kvy = __shfl_sync (0xffffffffu, vy, min (ck, 5));
-            bool slow;
-            const unsigned mm = cand_metric_win (S, B, part, kvx, kvy, ck < 6 && ((farmask >> ck) & 1), slow);
-            const unsigned mine = __shfl_sync (0xffffffffu, mm, 3 * min (lane, 5));
-            if (far) m = mine;
-          } else {
-            unsigned fm = farmask;
-            while (fm) {
-              const int l = __ffs (fm) - 1;
-              fm &= fm - 1;
-              const unsigned mm = cand_metric_global (B, __shfl_sync (0xffffffffu, vx, l), __shfl_sync (0xffffffffu, vy, l));
-              if (lane == l) m = mm;
-            }
-          }
-          COUNT (3);
-        }
-        if (lane < 6) S.metric[lane] = m;
-      }
-      __syncwarp ();
-      if (lane == 0) st_release_smem (&ready[nb % D], nb + 1);
-    }
-    return;
-  }
-
-  // ============================= chain =============================
-  int last_dx = 0, last_dy = 0;
-  unsigned long long up_cur = 0, up_prev = 0;
-  if (words_up && row_active) up_cur = ld_word (words_up);
-#ifdef SB2_HBM_TRACE
-  const bool trace_on = (A.shift == 0 && row == 100 && pic == 0);
-#endif
-  for (int bi = 0; bi < A.cols; bi++) {
-    TRACE (0);
-    const BlkGeom B = blk_geom (bi);
-    const int i = bi * skip, x0 = B.x0;
-    const WinSlot<RW> &S = ring[bi % D];
-    while (ld_acquire_smem (&ready[bi % D]) != bi + 1) { }
-    TRACE (1);
-    if (!B.active) {
-      // a block outside the picture keeps the zero vector of schro_motion_field_set
-      if (lane == 0) { st_word (words_me + bi, pack_word (0, 0)); st_release_smem (&consumed, bi + 1); }
-      last_dx = 0; last_dy = 0;
-      continue;
-    }
-    // ---- candidates 0..5 static; 6: left 7: up 8: up-left of THIS level (schrohierbm.c:279-294)
-    if (words_up) while (!(up_cur >> 63)) { __nanosleep (POLL_NS); up_cur = ld_word (words_up + bi); }
-    unsigned long long up_next = 0;
-    if (words_up && bi + 1 < A.cols) up_next = ld_word (words_up + bi + 1);   // consumed by the next block
-    int cdx = 0, cdy = 0;
-    bool valid = false;
-    if (lane < 6) { cdx = S.cdx[lane]; cdy = S.cdy[lane]; valid = (S.valid >> lane) & 1; }
-    else if (lane == 6 && bi > 0) { cdx = last_dx; cdy = last_dy; valid = true; }
-    else if (lane == 7 && words_up) { cdx = (int) (short) (up_cur >> 16); cdy = (int) (short) up_cur; valid = true; }
-    else if (lane == 8 && bi > 0 && words_up) { cdx = (int) (short) (up_prev >> 16); cdy = (int) (short) up_prev; valid = true; }
-    // de-duplicate keeping the LAST occurrence (schrohierbm.c:298-321)
-    const bool isc = valid && lane < 9;
-    const unsigned long long mkey = isc
-        ? ((1ull << 32) | ((unsigned long long) (cdx & 0xffff) << 16) | (unsigned long long) (cdy & 0xffff))
-        : ((unsigned long long) (2 + lane) << 32);
-    const unsigned same = __match_any_sync (0xffffffffu, mkey);
-    const bool dup = isc && (same >> (lane + 1)) != 0;
-    const unsigned cmask = __ballot_sync (0xffffffffu, isc && !dup);
-    TRACE (2);
-
-    // ---- rank (schrometric.c:332-375): lane k holds candidate k.  Static SADs come with the
-    // slot; a neighbour's SAD is a map lookup, or global memory when it lies outside the window
-    unsigned metric = (unsigned) INT_MAX;
-    bool far = false;
-    if (lane < 6) metric = S.metric[lane];
-    else if (lane < 9 && ((cmask >> lane) & 1)) {
-      int ddx, ddy;
-      if (cand_disp (B, cdx, cdy, ddx, ddy)) {
-        if (in_window (S, ddx, ddy)) metric = map_metric (S, B, ddx, ddy);
-        else far = true;
-      }
-    }
-    unsigned farmask = __ballot_sync (0xffffffffu, far);
-    while (farmask) {
-      const int l = __ffs (farmask) - 1;
-      farmask &= farmask - 1;
-      const int fvx = __shfl_sync (0xffffffffu, cdx, l), fvy = __shfl_sync (0xffffffffu, cdy, l);
-      bool slow;
-      unsigned mm = cand_metric_win (S, B, lane, fvx, fvy, lane < 3, slow);     // lanes 0..2 = the three parts
-      mm = __shfl_sync (0xffffffffu, mm, 0);
-      if (__shfl_sync (0xffffffffu, (int) slow, 0)) mm = cand_metric_global (B, fvx, fvy);
-      if (lane == l) metric = mm;
-      COUNT (1);
-    }
-    // first strict minimum in candidate order == min over (metric, k); INT_MAX never wins
-    unsigned rkey = 0xffffffffu;
-    if (lane < 9 && ((cmask >> lane) & 1) && metric < (unsigned) INT_MAX) rkey = (metric << 8) | (unsigned) lane;
-    rkey = __reduce_min_sync (0xffffffffu, rkey);
-    const int best_k = rkey == 0xffffffffu ? __ffs (cmask) - 1 : (int) (rkey & 0xff);
-    TRACE (3);
-
-    // ---- scan around the winner (schrohierbm.c:349-364, schrometric.c:121-214)
-    int dx = __shfl_sync (0xffffffffu, cdx, best_k) >> s;
-    int dy = __shfl_sync (0xffffffffu, cdy, best_k) >> s;
-    dx = max (-B.bw0 - x0, min (A.width - x0, dx));
-    dy = max (-bh0 - y0, min (A.height - y0, dy));
-    const Win wn = make_win (B, dx, dy);
-    const int npos = wn.scan_w * wn.scan_h;
-    TRACE (4);
-    unsigned long long best_key = ~0ull;
-    unsigned best_l = 0, best_c = 0;
-    bool inw = wn.xmin - x0 >= S.lo_dx && wn.xmin + wn.scan_w - 1 - x0 <= S.lo_dx + 2 * RW &&
-        wn.ymin - y0 >= S.lo_dy && wn.ymin + wn.scan_h - 1 - y0 <= S.lo_dy + 2 * RW;
-    const int ccx0 = wn.xmin / 2, ccy0 = wn.ymin / 2;      // C division: truncates toward zero
-    if (A.use_chroma) {
-      // chroma positions ccx0 .. ccx0 + (scan_w-1)/2 (+3 bytes) must be staged too
-      inw = inw && ccx0 >= S.cxb && ccx0 + ((wn.scan_w - 1) >> 1) + 4 <= S.cxb + G::CP * 4 &&
-          ccy0 >= S.cyt && ccy0 + ((wn.scan_h - 1) >> 1) + 4 <= S.cyt + G::CROWS;
-    }
-    COUNT (0);
-    if (!inw) COUNT (2);
-    // chroma in the maps has the ranking geometry: the same as the scan's for a full block
-    bool inmap = inw && (!A.use_chroma || B.full);
-    if (inmap && A.use_chroma)
-      inmap = ccx0 >= S.cxl && ccx0 + ((wn.scan_w - 1) >> 1) < S.cxl + G::CMW && ccy0 + ((wn.scan_h - 1) >> 1) < S.cyt + G::CMW;
-    if (inmap) {
-      const float inv_w = __frcp_rn ((float) wn.scan_w);
-      const int mx0 = wn.xmin - x0 - S.lo_dx, my0 = wn.ymin - y0 - S.lo_dy;
-      for (int p = lane; p < npos; p += 32) {
-        const int b = (int) (((float) p + 0.5f) * inv_w), a = p - b * wn.scan_w;
-        const unsigned l = S.lmap[(my0 + b) * G::MW + mx0 + a];
-        unsigned c = 0;
-        if (A.use_chroma) c = S.cmap[(ccy0 + (b >> 1) - S.cyt) * G::CMW + (ccx0 + (a >> 1) - S.cxl)];
-        const unsigned notseed = (a == wn.seed_a && b == wn.seed_b) ? 0u : 1u;
-        const unsigned long long key = ((unsigned long long) (l + c) << 32) | (notseed << 24) | ((unsigned) a << 12) | (unsigned) b;
-        if (key < best_key) { best_key = key; best_l = l; best_c = c; }
-      }
-    } else if (inw) {
-      uint2 srow[8];
-#pragma unroll
-      for (int y = 0; y < 8; y++) srow[y] = S.src_l[y];
-      const float inv_w = __frcp_rn ((float) wn.scan_w);
-      for (int p = lane; p < npos; p += 32) {
-        const int b = (int) (((float) p + 0.5f) * inv_w), a = p - b * wn.scan_w;
-        const unsigned l = B.full ? win_luma_rows<RW, false> (S, srow, wn.xmin + a, wn.ymin + b, 0, 8, B)
-                                  : win_luma_rows<RW, true> (S, srow, wn.xmin + a, wn.ymin + b, 0, bh0, B);
-        unsigned c = 0;
-        if (A.use_chroma) c = win_chroma<RW> (S, ccx0 + (a >> 1), ccy0 + (b >> 1), R.sch, B.scm);
-        const unsigned notseed = (a == wn.seed_a && b == wn.seed_b) ? 0u : 1u;
-        const unsigned long long key = ((unsigned long long) (l + c) << 32) | (notseed << 24) | ((unsigned) a << 12) | (unsigned) b;
-        if (key < best_key) { best_key = key; best_l = l; best_c = c; }
-      }
-    } else {
-      const uint8_t *sblk = sp[0] + (ptrdiff_t) y0 * ss[0] + x0;
-      uint2 srow[8];
-#pragma unroll
-      for (int y = 0; y < 8; y++) srow[y] = S.src_l[y];
-      for (int p = lane; p < npos; p += 32) {
-        const int b = p / wn.scan_w, a = p - b * wn.scan_w;
-        const uint8_t *rblk = rp[0] + (ptrdiff_t) (wn.ymin + b) * rs[0] + wn.xmin + a;
-        unsigned l = 0;
-        if (B.full) {
-#pragma unroll
-          for (int y = 0; y < 8; y++) {
-            const uint2 bv = load8_unaligned (rblk + (ptrdiff_t) y * rs[0]);
-            l += __vsadu4 (srow[y].x, bv.x) + __vsadu4 (srow[y].y, bv.y);
-          }
-        } else {
-          l = block_sad (sblk, ss[0], rblk, rs[0], B.bw0, bh0);
-        }
-        unsigned c = 0;
-        if (A.use_chroma) {
-          const int cx = x0 / 2, cy = y0 / 2, crx = ccx0 + (a >> 1), cry = ccy0 + (b >> 1);
-          for (int k = 1; k < 3; k++)
-            c += block_sad (sp[k] + (ptrdiff_t) cy * ss[k] + cx, ss[k], rp[k] + (ptrdiff_t) cry * rs[k] + crx, rs[k],
-                B.bw0 / 2, bh0 / 2);
-        }
-        const unsigned notseed = (a == wn.seed_a && b == wn.seed_b) ? 0u : 1u;
-        const unsigned long long key = ((unsigned long long) (l + c) << 32) | (notseed << 24) | ((unsigned) a << 12) | (unsigned) b;
-        if (key < best_key) { best_key = key; best_l = l; best_c = c; }
-      }
-    }
-    __syncwarp ();
-    if (lane == 0) st_release_smem (&consumed, bi + 1);    // the slot may be refilled
-    TRACE (5);
-    // key = (metric, not-seed, a, b): the seed wins ties, else the first strict minimum in the
-    // reference's a-outer / b-inner order
-    const unsigned khi = (unsigned) (best_key >> 32), klo = (unsigned) best_key;
-    const unsigned mhi_ = __reduce_min_sync (0xffffffffu, khi);
-    const unsigned mlo_ = __reduce_min_sync (0xffffffffu, khi == mhi_ ? klo : 0xffffffffu);
-    const unsigned owner = __ballot_sync (0xffffffffu, khi == mhi_ && klo == mlo_);
-    const int ol = __ffs (owner) - 1;
-    const unsigned wl = __shfl_sync (0xffffffffu, best_l, ol), wc = __shfl_sync (0xffffffffu, best_c, ol);
-    const int ba = (int) ((mlo_ >> 12) & 0xfff), bb = (int) (mlo_ & 0xfff);
-    const int rdx = (int) (int16_t) ((wn.xmin + ba - x0) << s), rdy = (int) (int16_t) ((wn.ymin + bb - y0) << s);
-    TRACE (6);
-    if (lane == 0) st_word (words_me + bi, pack_word (rdx, rdy));   // the row below waits on this
-    last_dx = rdx; last_dy = rdy;
-    if (lane < 5) {
-      // the field entry was zero-initialised by this call, so whole words can be written
-      uint32_t *o = reinterpret_cast<uint32_t *> (mf + (size_t) j * A.nbx + i);
-      const unsigned vsh = ri ? 16 : 0;
-      const uint32_t val = lane == 0 ? A.flags0 : lane == 1 ? wl : lane == 2 ? wc
-          : lane == 3 ? ((uint32_t) (rdx & 0xffff) << vsh) : ((uint32_t) (rdy & 0xffff) << vsh);
-      o[lane] = val;
-    }
-    up_prev = up_cur;
-    up_cur = up_next;
-  }
-}
-
 }  // namespace sb2
 
 using namespace sb2;
@@ -1363,20 +728,8 @@ sb2_hbm_scan_hint (const sb2_hbm_params *p, const sb2_slab *src_level, const sb2
     char tag[48];
     snprintf (tag, sizeof (tag), "hbm_level_s%d_r%d", shift, h_range);
     LaunchScope scope (tag, bytes, st);
-    // window kernel: 8x8 blocks, 4:2:0, planes aligned for 16-byte chunk staging
-    bool win_ok = p->xbsep == 8 && p->ybsep == 8 && p->chroma_h_shift == 1 && p->chroma_v_shift == 1 &&
-        h_range <= 5 && extension >= 0 && getenv ("SB2_HBM_WINDOW");
-    for (int c = 0; c < 3 && win_ok; c++) {
-      const size_t ra = (size_t) ref_level->base + ref_level->offset[c] - (size_t) extension;
-      const size_t sa = (size_t) src_level->base + src_level->offset[c];
-      const size_t salign = c ? 3 : 7;
-      win_ok = ((ra | (size_t) ref_level->stride[c] | ref_level->picture_pitch) & 15) == 0 && ref_level->stride[c] >= 16 &&
-          ((sa | (size_t) src_level->stride[c] | src_level->picture_pitch) & salign) == 0;
-    }
-    if (win_ok) hbm_win_kernel<7, 1, 3><<<ctas, 64, 0, st>>> (A);
     // warps per block row: enough threads to cover the scan positions in few rounds
-    else if (npos <= 64 && getenv ("SB2_HBM_SPEC")) hbm_level_kernel<2, true><<<ctas, 64, 0, st>>> (A);
-    else if (npos <= 64) hbm_level_kernel<2><<<ctas, 64, 0, st>>> (A);
+    if (npos <= 64) hbm_level_kernel<2><<<ctas, 64, 0, st>>> (A);
     else if (npos <= 128) hbm_level_kernel<4><<<ctas, 128, 0, st>>> (A);
     else if (npos <= 512) hbm_level_kernel<8><<<ctas, 256, 0, st>>> (A);
     else hbm_level_kernel<16><<<ctas, 512, 0, st>>> (A);
@@ -1389,8 +742,5 @@ extern "C" int sb2_hbm_trace_read (long long *host, int n)
 {
   return (int) cudaMemcpyFromSymbol (host, sb2::g_hbm_trace, sizeof (long long) * n);
 }
-extern "C" int sb2_hbm_count_read (unsigned long long *host)
-{
-  return (int) cudaMemcpyFromSymbol (host, sb2::g_hbm_count, sizeof (unsigned long long) * 8);
-}
+
 #endif

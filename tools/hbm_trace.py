@@ -11,12 +11,9 @@ buf = np.zeros(512 * 8, np.int64)
 lib.sb2_hbm_trace_read(buf.ctypes.data_as(ctypes.c_void_p), 512 * 8)
 t = buf.reshape(512, 8)[50:450]
 d = np.diff(t[:, :7], axis=1)
-names = ["wait slot", "poll+dedup", "rank", "seed+window", "scan", "reduce"] if os.environ.get("SB2_HBM_WINDOW") else ["A static cands", "poll+dedup", "rank (nbr SADs)", "seed+sync", "scan", "reduce+sync+sel"]
+names = ["A static cands", "poll+dedup", "rank (nbr SADs)", "seed+sync", "scan", "reduce+sync+sel"]
 print("batch", spec["batch"], bench.CONTENT, "per-block cycles (row 100, level 0), median / mean:")
 for k, n in enumerate(names): print(f"  {n:18s} {np.median(d[:,k]):8.0f} {d[:,k].mean():8.0f}")
 tot = np.diff(t[:, 0])
 print("  block-to-block     ", np.median(tot), tot.mean())
 
-cnt = np.zeros(8, np.uint64)
-lib.sb2_hbm_count_read(cnt.ctypes.data_as(ctypes.c_void_p))
-print("level-0 counters: blocks", cnt[0], "slow rank cands (chain)", cnt[1], "scan fallbacks", cnt[2], "slow static cands", cnt[3])
