@@ -477,6 +477,16 @@ template <> struct Vec16<int32_t> {
   {
     *reinterpret_cast<int4 *> (p) = make_int4 (e[0], o[0], e[1], o[1]);
   }
+  // 4 interleaved inputs (e0 o0 e1 o1)
+  static __device__ __forceinline__ void load_pairs (const int32_t *p, int *e, int *o)
+  {
+    const int4 q = *reinterpret_cast<const int4 *> (p);
+    e[0] = q.x; o[0] = q.y; e[1] = q.z; o[1] = q.w;
+  }
+  static __device__ __forceinline__ void store (int32_t *p, const int *v)
+  {
+    *reinterpret_cast<int4 *> (p) = make_int4 (v[0], v[1], v[2], v[3]);
+  }
   static constexpr int PAIRS = 2;
 };
 template <> struct Vec16<int16_t> {
@@ -490,6 +500,17 @@ template <> struct Vec16<int16_t> {
   {
     *reinterpret_cast<int4 *> (p) = make_int4 ((e[0] & 0xffff) | (o[0] << 16), (e[1] & 0xffff) | (o[1] << 16),
         (e[2] & 0xffff) | (o[2] << 16), (e[3] & 0xffff) | (o[3] << 16));
+  }
+  static __device__ __forceinline__ void load_pairs (const int16_t *p, int *e, int *o)
+  {
+    const int4 q = *reinterpret_cast<const int4 *> (p);
+    e[0] = (q.x << 16) >> 16; o[0] = q.x >> 16; e[1] = (q.y << 16) >> 16; o[1] = q.y >> 16;
+    e[2] = (q.z << 16) >> 16; o[2] = q.z >> 16; e[3] = (q.w << 16) >> 16; o[3] = q.w >> 16;
+  }
+  static __device__ __forceinline__ void store (int16_t *p, const int *v)
+  {
+    *reinterpret_cast<int4 *> (p) = make_int4 ((v[0] & 0xffff) | (v[1] << 16), (v[2] & 0xffff) | (v[3] << 16),
+        (v[4] & 0xffff) | (v[5] << 16), (v[6] & 0xffff) | (v[7] << 16));
   }
   static constexpr int PAIRS = 4;
 };
@@ -604,6 +625,124 @@ wavelet_inv_fast_kernel (const LevelArgs a)
   }
 }
 
+
+// ---- fast forward kernel ---------------------------------------------------------------
+// Mirror image of the fast inverse kernel: the tile (with its halo) is copied in with
+// coalesced 128-bit loads, each thread lifts one row x one chunk of column pairs out of
+// shared memory (lanes = rows), writes the [L|H] split back, then one thread lifts one column
+// x one chunk of row pairs (lanes = columns) and stores the four bands straight to global
+// memory with coalesced scalar stores.
+template <typename T, int F, int CS> struct FwdGeom {
+  typedef FastGeom<T, F, CS> B;
+  static constexpr int ROWS = 2 * (THH + 2 * B::HP);          // input rows held in shared memory
+  static constexpr int HITEMS = (ROWS + 31) / 32 * 32 * (TWH / B::CH);     // lanes = rows, whole warps
+  static constexpr int VITEMS = 2 * TWH * (THH / B::C);
+  static constexpr int NT = ((VITEMS > HITEMS ? VITEMS : HITEMS) + 31) / 32 * 32;
+  static constexpr size_t SMEM = (size_t) ROWS * B::PITCH * sizeof (T);
+  static_assert (NT <= 1024, "too many items per tile");
+};
+
+template <typename T, int F, int CS>
+__global__ void __launch_bounds__ (FwdGeom<T, F, CS>::NT)
+wavelet_fwd_fast_kernel (const LevelArgs a)
+{
+  typedef FastGeom<T, F, CS> G;
+  typedef FwdGeom<T, F, CS> FG;
+  extern __shared__ __align__ (16) unsigned char smem_raw[];
+  T *sm = reinterpret_cast<T *> (smem_raw);
+
+  const int comp = a.comp_map[blockIdx.z % a.ncomp], pic = blockIdx.z / a.ncomp;
+  const int w = a.w[comp], h = a.h[comp];
+  const int n = w >> 1, m = h >> 1;
+  const int kx0 = blockIdx.x * TWH, ky0 = blockIdx.y * THH;
+  if (kx0 >= n || ky0 >= m) return;
+  constexpr int SH = filter_shift (F);
+
+  const T *dense = reinterpret_cast<const T *> (plane_ptr (a.dense, pic, comp));
+  T *bands = reinterpret_cast<T *> (plane_ptr (a.bands, pic, comp));
+  T *ll = reinterpret_cast<T *> (plane_ptr (a.ll, pic, comp));
+  const size_t ds = a.dense.stride[comp] / sizeof (T);
+  const size_t bs = a.bands.stride[comp] / sizeof (T);
+  const size_t ls = a.ll.stride[comp] / sizeof (T);
+  const int tid = threadIdx.x;
+
+  // shared-memory row r <-> picture row 2 (ky0 - HP) + r; column c <-> picture column 2 (kx0 - HK) + c
+  const int py0 = 2 * (ky0 - G::HP), px0 = 2 * (kx0 - G::HK);
+  // ---- coalesced copy-in, 128 bits per lane ----
+  {
+    const int r_lo = max (0, -py0), r_hi = min (FG::ROWS, h - py0);
+    const int c_lo = max (0, -px0), c_hi = min (2 * G::NKV, w - px0);      // multiples of VEC
+    const int vpr = (c_hi - c_lo) / G::VEC;
+    const int total = (r_hi - r_lo) * vpr;
+    for (int i = tid; i < total; i += FG::NT) {
+      const int r = r_lo + i / vpr, c = c_lo + (i % vpr) * G::VEC;
+      const int4 v = *reinterpret_cast<const int4 *> (dense + (size_t) (py0 + r) * ds + px0 + c);
+      *reinterpret_cast<int4 *> (sm + (size_t) r * G::PITCH + c) = v;
+    }
+  }
+  __syncthreads ();
+
+  // ---- horizontal: one thread = one row x one chunk of CH column pairs; lanes = rows ----
+  {
+    const int hw = tid >> 5, lane = tid & 31;
+    constexpr int CPR = TWH / G::CH;                       // chunks per row
+    const int q = hw % CPR;
+    const int row = (hw / CPR) * 32 + lane;                // shared-memory row
+    const int k0 = kx0 + q * G::CH;
+    const bool hact = tid < FG::HITEMS && row < FG::ROWS && k0 < n && py0 + row >= 0 && py0 + row < h;
+    int E[G::NH], O[G::NH];
+    if (hact) {
+      const T *rowp = sm + (size_t) row * G::PITCH + 2 * q * G::CH;     // pair k0 - HK
+#pragma unroll
+      for (int i = 0; i < G::NH; i += Vec16<T>::PAIRS)
+        Vec16<T>::load_pairs (rowp + 2 * i, &E[i], &O[i]);
+      if (SH) {
+#pragma unroll
+        for (int i = 0; i < G::NH; i++) { E[i] = Ar<T>::add (E[i], E[i]); O[i] = Ar<T>::add (O[i], O[i]); }
+      }
+      chunk_lift<T, F, false, G::NH, G::HK> (E, O, k0 == 0, k0 + G::CH >= n);
+    }
+    __syncthreads ();
+    if (hact) {
+      // split layout: L at column (pair - (kx0 - HK)), H at NKV + the same
+      T *orow = sm + (size_t) row * G::PITCH + q * G::CH + G::HK;
+#pragma unroll
+      for (int i = 0; i < G::CH; i += G::VEC) {
+        Vec16<T>::store (orow + i, &E[G::HK + i]);
+        Vec16<T>::store (orow + G::NKV + i, &O[G::HK + i]);
+      }
+    }
+  }
+  __syncthreads ();
+
+  // ---- vertical: one thread = one column x one chunk of C row pairs; lanes = columns ----
+  if (tid < FG::VITEMS) {
+    const int chunk = tid / (2 * TWH), col = tid - chunk * (2 * TWH);
+    const int seg = col >= TWH, cc = col - seg * TWH;
+    const int kx = kx0 + cc;
+    const int kyc = ky0 + chunk * G::C;
+    if (kx < n && kyc < m) {
+      int E[G::NV], O[G::NV];
+      const T *colp = sm + (size_t) (2 * chunk * G::C) * G::PITCH + seg * G::NKV + G::HK + cc;
+#pragma unroll
+      for (int r = 0; r < G::NV; r++) {
+        E[r] = colp[(size_t) (2 * r) * G::PITCH];
+        O[r] = colp[(size_t) (2 * r + 1) * G::PITCH];
+      }
+      chunk_lift<T, F, false, G::NV, G::HP> (E, O, kyc == 0, kyc + G::C >= m);
+      // even rows: LL (seg 0) to `ll`, HL (seg 1) to the band plane; odd rows: LH / HH
+      T *pe = seg ? bands + n + kx : ll + kx;
+      const size_t es = seg ? 2 * bs : ls;
+      T *po = bands + bs + seg * n + kx;
+#pragma unroll
+      for (int r = 0; r < G::C; r++) {
+        pe[(size_t) (kyc + r) * es] = (T) E[G::HP + r];
+        po[(size_t) (kyc + r) * 2 * bs] = (T) O[G::HP + r];
+      }
+    }
+  }
+}
+
 // chunk size (16, 8) usable by the fast inverse kernel for component c, or 0
 template <typename T, int F>
 static int fast_inverse_chunk (const LevelArgs &a, int c)
@@ -647,6 +786,33 @@ static int launch_fast_inverse (LevelArgs a, const int *comps, int nsel, int cou
   return check_cuda (cudaGetLastError (), "wavelet_inv_fast_kernel launch");
 }
 
+template <typename T, int F, int CS>
+static int launch_fast_forward (LevelArgs a, const int *comps, int nsel, int count, cudaStream_t stream,
+    const char *tag, double bytes)
+{
+  typedef FwdGeom<T, F, CS> FG;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute (wavelet_fwd_fast_kernel<T, F, CS>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FG::SMEM);
+    if (e != cudaSuccess) return check_cuda (e, "cudaFuncSetAttribute(wavelet fast forward)");
+    attr_set = true;
+  }
+  int maxn = 0, maxm = 0;
+  a.ncomp = nsel;
+  for (int i = 0; i < nsel; i++) {
+    a.comp_map[i] = comps[i];
+    maxn = max (maxn, a.w[comps[i]] >> 1);
+    maxm = max (maxm, a.h[comps[i]] >> 1);
+  }
+  dim3 grid (ceil_div (maxn, TWH), ceil_div (maxm, THH), nsel * count);
+  {
+    LaunchScope scope (tag, bytes, stream);
+    wavelet_fwd_fast_kernel<T, F, CS><<<grid, FG::NT, FG::SMEM, stream>>> (a);
+  }
+  return check_cuda (cudaGetLastError (), "wavelet_fwd_fast_kernel launch");
+}
+
 template <typename T, int F, bool INV>
 static int launch_level (const LevelArgs &a_in, int count, cudaStream_t stream)
 {
@@ -665,7 +831,7 @@ static int launch_level (const LevelArgs &a_in, int count, cudaStream_t stream)
   for (int c = 0; c < a_in.ncomp; c++) {
     if ((a.w[c] >> 1) == 0 || (a.h[c] >> 1) == 0) continue;
     int cs = 0;
-    if constexpr (INV) cs = fast_inverse_chunk<T, F> (a, c);
+    cs = fast_inverse_chunk<T, F> (a, c);      // the same constraints serve the forward kernel (dense = its input)
     const int k = cs == 16 ? 1 : cs == 8 ? 2 : 0;
     sel[k][nsel[k]++] = c;
   }
@@ -682,6 +848,9 @@ static int launch_level (const LevelArgs &a_in, int count, cudaStream_t stream)
     if constexpr (INV) {
       if (k == 1) rc = launch_fast_inverse<T, F, 16> (a, sel[k], nsel[k], count, stream, tag, bytes);
       if (k == 2) rc = launch_fast_inverse<T, F, 8> (a, sel[k], nsel[k], count, stream, tag, bytes);
+    } else {
+      if (k == 1) rc = launch_fast_forward<T, F, 16> (a, sel[k], nsel[k], count, stream, tag, bytes);
+      if (k == 2) rc = launch_fast_forward<T, F, 8> (a, sel[k], nsel[k], count, stream, tag, bytes);
     }
     if (k == 0) {
       int maxn = 0, maxm = 0;
