@@ -448,10 +448,60 @@ class HostFrames:
         lib.schro_hierarchical_bm_scan_hint(hbm, 0, 3)
         lib.schro_hbm_unref(hbm)
 
+    def native_start(self):
+        """Hand the frames to the pthread driver (bench_native/e2e_driver.c): from here on the
+        host side of a step is plain C calling the drop-in API, as a C application would."""
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bench_native", "libsb2_e2e_driver.so")
+        if not os.path.exists(path):
+            raise RuntimeError(path + " is missing: run `make` (or __graft_entry__.build())")
+        drv = ctypes.CDLL(path)
+        compat = self.compat
+        FP, n, T = compat.FrameP, len(self.coef_host), self.nthreads
+
+        class Job(ctypes.Structure):
+            _fields_ = [("nthreads", ctypes.c_int), ("npictures", ctypes.c_int), ("levels", ctypes.c_int),
+                        ("pic_height", ctypes.c_int), ("full_core", ctypes.c_int),
+                        ("params", ctypes.POINTER(compat.SchroParams)),
+                        ("coef_host", ctypes.POINTER(FP)), ("src_host", ctypes.POINTER(FP)),
+                        ("out_host", ctypes.POINTER(FP)), ("ref_pyr", ctypes.POINTER(FP)),
+                        ("coef_dev", ctypes.POINTER(FP)), ("acc_dev", ctypes.POINTER(FP)),
+                        ("out_dev", ctypes.POINTER(FP)),
+                        ("motion", ctypes.POINTER(ctypes.POINTER(compat.SchroMotion))),
+                        ("src_pyr", ctypes.POINTER(FP))]
+
+        def arr(frames):
+            a = (FP * max(1, len(frames)))(*frames)
+            self._keep.append(a)
+            return a
+
+        self._keep = []
+        job = Job()
+        job.nthreads, job.npictures, job.levels = T, n, HBM_LEVELS
+        job.pic_height, job.full_core = self.spec["height"], int(self.full)
+        job.params = ctypes.pointer(self.params)
+        job.coef_host = arr(self.coef_host)
+        if self.full:
+            job.src_host, job.out_host, job.ref_pyr = arr(self.src_host), arr(self.out_host), arr(self.ref_pyr)
+            job.coef_dev = arr([t["coef"] for t in self.th])
+            job.acc_dev = arr([t["acc"] for t in self.th])
+            job.out_dev = arr([t["out"] for t in self.th])
+            mo = (ctypes.POINTER(compat.SchroMotion) * T)(*[t["motion"] for t in self.th])
+            self._keep.append(mo)
+            job.motion = mo
+            job.src_pyr = arr([f for t in self.th for f in t["src_pyr"]])
+        drv.sb2_e2e_step.restype = ctypes.c_double
+        if drv.sb2_e2e_start(ctypes.byref(job)) != 0:
+            raise RuntimeError("sb2_e2e_start failed")
+        self._keep.append(job)
+        self.drv = drv
+
     def step(self):
         """One e2e step: every picture of the batch, pictures spread over a pool of persistent
         host threads (the reference's own threading model, schroasync-pthread.c); each thread
         owns a stream and its staging buffers."""
+        if hasattr(self, "drv"):
+            self.drv.sb2_e2e_step()
+            return
         n = len(self.coef_host)
         if not hasattr(self, "pool"):
             from concurrent.futures import ThreadPoolExecutor
@@ -467,6 +517,9 @@ class HostFrames:
     def close(self):
         """Stop the worker threads while CUDA is still alive (their thread-exit hooks release
         per-thread streams and buffers)."""
+        if hasattr(self, "drv"):
+            self.drv.sb2_e2e_stop()
+            del self.drv
         if hasattr(self, "pool"):
             import threading as _t
             gate = _t.Barrier(self.nthreads)
@@ -542,6 +595,8 @@ def run_ours(args):
     try:
         nthreads = min(args.e2e_threads, B)
         hf = HostFrames(spec, lib, nthreads)
+        if args.e2e_driver == "native":
+            hf.native_start()
         for _ in range(3):
             hf.step()
         barrier()
@@ -566,7 +621,7 @@ def run_ours(args):
                "api": "drop-in schro_* C API (schro_frame_to_gpu, schro_frame_inverse_iwt_transform, "
                       "schro_motion_render, schro_frame_mc_edgeextend, schro_upsampled_frame_upsample, "
                       "schro_frame_downsample, schro_hbm_scan, schro_hierarchical_bm_scan_hint, "
-                      f"schro_gpuframe_to_cpu) on pinned host SchroFrames, {nthreads} host threads/GPU, "
+                      f"schro_gpuframe_to_cpu) on pinned host SchroFrames, {nthreads} host threads/GPU ({args.e2e_driver} driver), "
                       "one stream each"}
     except Exception as ex:  # keep the device-resident number even if the host arm breaks
         e2e = {"value": None, "unit": "frames/s", "error": repr(ex)}
@@ -784,7 +839,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--content", default="natural", choices=["natural", "periodic"],
                     help="texture of the synthetic pictures (see textured_frame)")
-    ap.add_argument("--e2e-threads", type=int, default=4, help="host threads driving the drop-in API in the e2e leg")
+    ap.add_argument("--e2e-threads", type=int, default=8, help="host threads driving the drop-in API in the e2e leg")
+    ap.add_argument("--e2e-driver", default="native", choices=["native", "python"],
+                    help="host threads of the e2e leg: pthreads in bench_native/e2e_driver.c, or Python threads + ctypes")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--overlap", action="store_true",

@@ -1,0 +1,165 @@
+/*
+ * e2e_driver.c -- the host side of bench.py's end-to-end leg: a pool of pthreads drives the
+ * drop-in schro_* C API (libschro_b200.so) over pinned host frames, one picture per task,
+ * the way libschroedinger's own SchroAsync workers would (schroedinger/schroasync-pthread.c).
+ * Python only builds the frames and reads the clock; no interpreter lock sits between two
+ * API calls.  Benchmark infrastructure, not part of the product library.
+ */
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include "schro_b200_compat.h"
+
+typedef struct {
+  int nthreads, npictures, levels, pic_height, full_core;
+  SchroParams *params;
+  SchroFrame **coef_host;      /* [npictures] coefficient frames, page-locked */
+  SchroFrame **src_host;       /* [npictures] source pictures, page-locked */
+  SchroFrame **out_host;       /* [npictures] decoded pictures, page-locked */
+  SchroFrame **ref_pyr;        /* [levels + 1] reference pyramid, CUDA domain */
+  SchroFrame **coef_dev;       /* [nthreads] */
+  SchroFrame **acc_dev;        /* [nthreads] */
+  SchroFrame **out_dev;        /* [nthreads] upsampled, extension 32 */
+  SchroMotion **motion;        /* [nthreads] */
+  SchroFrame **src_pyr;        /* [nthreads * (levels + 1)] */
+} Sb2E2eJob;
+
+static Sb2E2eJob g_job;
+static pthread_t *g_threads;
+static pthread_barrier_t g_start, g_end;
+static volatile int g_quit;
+static volatile unsigned g_sink;
+
+/* optional per-call wall-clock accounting (summed over threads), read with sb2_e2e_times */
+enum { T_H2D_COEF, T_IWT, T_RENDER, T_EDGE_UPSAMPLE, T_D2H_OUT, T_H2D_SRC, T_PYRAMID, T_HBM_NEW, T_HBM_SCAN,
+       T_HBM_HINT, T_HBM_UNREF, T_N };
+static double g_times[64][T_N];
+static int g_timing;
+static inline double
+now (void)
+{
+  struct timespec a;
+  clock_gettime (CLOCK_MONOTONIC, &a);
+  return (double) a.tv_sec + 1e-9 * (double) a.tv_nsec;
+}
+#define TIMED(slot, stmt) do { if (g_timing) { const double t0_ = now (); stmt; g_times[t & 63][slot] += now () - t0_; } else { stmt; } } while (0)
+
+static void
+one_picture (int t, int i)
+{
+  const Sb2E2eJob *j = &g_job;
+  SchroFrame **pyr = j->src_pyr + (size_t) t * (j->levels + 1);
+  SchroFrame view;
+  SchroHierBm *hbm;
+  SchroMotionField *mf;
+  int c, l;
+
+  if (!j->full_core) {
+    schro_frame_inverse_iwt_transform (j->coef_host[i], j->params);
+    return;
+  }
+  /* decode side: coefficients in, decoded picture out */
+  TIMED (T_H2D_COEF, schro_frame_to_gpu (j->coef_dev[t], j->coef_host[i]));
+  TIMED (T_IWT, schro_frame_inverse_iwt_transform (j->coef_dev[t], j->params));
+  /* the picture-size window of the (padded) coefficient frame, same memory */
+  view = *j->coef_dev[t];
+  view.refcount = 1;
+  view.domain = NULL;
+  view.height = j->pic_height;
+  for (c = 0; c < 3; c++) view.components[c].height = c ? j->pic_height / 2 : j->pic_height;
+  TIMED (T_RENDER, schro_motion_render (j->motion[t], j->acc_dev[t], &view, 1, j->out_dev[t]));
+  TIMED (T_EDGE_UPSAMPLE, {
+    schro_frame_mc_edgeextend (j->out_dev[t]);
+    j->out_dev[t]->upsample_done = 0;
+    schro_upsampled_frame_upsample (j->out_dev[t]);
+  });
+  TIMED (T_D2H_OUT, schro_gpuframe_to_cpu (j->out_host[i], j->out_dev[t]));
+  /* encode side: source picture in, motion fields out */
+  TIMED (T_H2D_SRC, schro_frame_to_gpu (pyr[0], j->src_host[i]));
+  TIMED (T_PYRAMID, {
+    schro_frame_mc_edgeextend (pyr[0]);
+    for (l = 0; l < j->levels; l++) {
+      schro_frame_downsample (pyr[l + 1], pyr[l]);
+      schro_frame_mc_edgeextend (pyr[l + 1]);
+    }
+  });
+  TIMED (T_HBM_NEW, hbm = schro_hbm_new_from_frames (j->params, 0, j->levels, 0, pyr, j->ref_pyr));
+  TIMED (T_HBM_SCAN, schro_hbm_scan (hbm));
+  TIMED (T_HBM_HINT, schro_hierarchical_bm_scan_hint (hbm, 0, 3));
+  mf = schro_hbm_motion_field (hbm, 0);
+  g_sink += (unsigned) mf->motion_vectors[0].metric;      /* the host reads the result */
+  TIMED (T_HBM_UNREF, schro_hbm_unref (hbm));
+}
+
+static void *
+worker (void *arg)
+{
+  const int t = (int) (size_t) arg;
+  for (;;) {
+    int i;
+    pthread_barrier_wait (&g_start);
+    if (g_quit) break;
+    for (i = t; i < g_job.npictures; i += g_job.nthreads) one_picture (t, i);
+    pthread_barrier_wait (&g_end);
+  }
+  schro_b200_thread_release ();
+  return NULL;
+}
+
+int
+sb2_e2e_start (const Sb2E2eJob *job)
+{
+  int t;
+  g_job = *job;
+  g_quit = 0;
+  pthread_barrier_init (&g_start, NULL, (unsigned) job->nthreads + 1);
+  pthread_barrier_init (&g_end, NULL, (unsigned) job->nthreads + 1);
+  g_threads = calloc ((size_t) job->nthreads, sizeof (pthread_t));
+  for (t = 0; t < job->nthreads; t++)
+    if (pthread_create (&g_threads[t], NULL, worker, (void *) (size_t) t)) return -1;
+  return 0;
+}
+
+/* one step = every picture of the job once; returns wall seconds */
+double
+sb2_e2e_step (void)
+{
+  struct timespec a, b;
+  clock_gettime (CLOCK_MONOTONIC, &a);
+  pthread_barrier_wait (&g_start);
+  pthread_barrier_wait (&g_end);
+  clock_gettime (CLOCK_MONOTONIC, &b);
+  return (double) (b.tv_sec - a.tv_sec) + 1e-9 * (double) (b.tv_nsec - a.tv_nsec);
+}
+
+/* enable / read the per-call accounting: out[T_N] seconds summed over threads since enabling */
+int
+sb2_e2e_times (int enable, double *out)
+{
+  int t, k;
+  if (out)
+    for (k = 0; k < T_N; k++) {
+      out[k] = 0;
+      for (t = 0; t < 64; t++) out[k] += g_times[t][k];
+    }
+  if (enable >= 0) {
+    memset (g_times, 0, sizeof (g_times));
+    g_timing = enable;
+  }
+  return T_N;
+}
+
+void
+sb2_e2e_stop (void)
+{
+  int t;
+  if (!g_threads) return;
+  g_quit = 1;
+  pthread_barrier_wait (&g_start);
+  for (t = 0; t < g_job.nthreads; t++) pthread_join (g_threads[t], NULL);
+  free (g_threads);
+  g_threads = NULL;
+  pthread_barrier_destroy (&g_start);
+  pthread_barrier_destroy (&g_end);
+}

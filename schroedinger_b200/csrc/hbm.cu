@@ -190,7 +190,9 @@ struct BlockShared {
 // longer loop and misses pay a single-warp scan -- so it is compiled out; kept because it
 // wins when vectors are coherent (hit rate near 1) and the chain is poll -> rank -> publish.
 template <int NW, bool SPEC = false>
-__global__ void __launch_bounds__ (32 * NW)
+// 64 registers per thread: a row's CTA mostly waits, so its footprint in the register file --
+// not its instruction rate -- decides how many rows / pictures / other kernels an SM can host
+__global__ void __launch_bounds__ (32 * NW, 1024 / (32 * NW))
 hbm_level_kernel (const HbmArgs A)
 {
   static_assert (NW >= 2, "one warp prepares the static candidates of the next block");

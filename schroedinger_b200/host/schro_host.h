@@ -24,9 +24,27 @@ typedef struct {
   cudaStream_t stream;
   void *dev[SB2H_NBUF];
   size_t dev_size[SB2H_NBUF];
+  cudaEvent_t sync_ev;     /* blocking-sync event: waiting threads sleep instead of spinning */
+  volatile int dirty;      /* work was enqueued on `stream` that no call has waited for yet */
+  int slot;                /* index in the process-wide context table */
 } Sb2hContext;
 
 Sb2hContext *sb2h_context (void);
+
+/* Stream-ordered device frames.  Calls whose frames all live in device memory do not wait for
+ * the GPU: they enqueue on the calling thread's stream and return.  Ordering between threads
+ * is kept per frame region: sb2h_frame_wrote records the stream's position after a write,
+ * sb2h_frame_use makes the calling thread's stream wait for the last write made from another
+ * stream (read-after-write, write-after-write).  Memory handed back to a CUDA domain while
+ * any stream still has un-waited work is parked until that work has finished (core.c, limbo).
+ * Everything that makes results visible to the host (D2H copies, metrics, staged host frames)
+ * ends with sb2h_sync. */
+void sb2h_sync (Sb2hContext *cx);
+void sb2h_frame_use (Sb2hContext *cx, const void *region);
+void sb2h_frame_wrote (Sb2hContext *cx, const void *region);
+/* process-wide pool of page-locked host blocks, reused by exact size */
+void *sb2h_pinned_pool_alloc (size_t bytes);
+int sb2h_pinned_pool_free (void *ptr);     /* 0 if ptr is not a pool block */
 /* per-thread pool of device blocks, reused by exact size (no cudaMalloc / cudaFree -- and
  * therefore no device-wide synchronisation -- in steady state) */
 void *sb2h_pool_alloc (size_t bytes);

@@ -73,6 +73,9 @@ schro_b200_set_device (int device)
 
 static void sb2h_pool_release_all (void);
 
+#define SB2H_MAX_CTX 128
+static Sb2hContext *g_ctx[SB2H_MAX_CTX];        /* live per-thread contexts, under g_device_mutex */
+
 /* Give the calling thread's stream, staging buffers and pooled device blocks back.  Worker
  * threads are expected to be long-lived (as SchroAsync's are); a thread that does exit
  * should call this first.  There is deliberately no automatic thread-exit hook: it would
@@ -84,9 +87,13 @@ schro_b200_thread_release (void)
   int i;
   if (!cx) return;
   cudaStreamSynchronize (cx->stream);
+  pthread_mutex_lock (&g_device_mutex);
+  g_ctx[cx->slot] = NULL;
+  pthread_mutex_unlock (&g_device_mutex);
   for (i = 0; i < SB2H_NBUF; i++)
     if (cx->dev[i]) cudaFree (cx->dev[i]);
   sb2h_pool_release_all ();
+  cudaEventDestroy (cx->sync_ev);
   cudaStreamDestroy (cx->stream);
   free (cx);
   tl_cx = NULL;
@@ -96,14 +103,110 @@ Sb2hContext *
 sb2h_context (void)
 {
   if (!tl_cx) {
+    int i;
     pthread_mutex_lock (&g_device_mutex);
     if (g_device < 0) SB2H_CUDA (cudaGetDevice (&g_device));
     pthread_mutex_unlock (&g_device_mutex);
     SB2H_CUDA (cudaSetDevice (g_device));
     tl_cx = calloc (1, sizeof (Sb2hContext));
     SB2H_CUDA (cudaStreamCreateWithFlags (&tl_cx->stream, cudaStreamNonBlocking));
+    SB2H_CUDA (cudaEventCreateWithFlags (&tl_cx->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
+    pthread_mutex_lock (&g_device_mutex);
+    for (i = 0; i < SB2H_MAX_CTX && g_ctx[i]; i++) ;
+    if (i == SB2H_MAX_CTX) sb2h_fatal (__func__, "more than %d threads use the library", SB2H_MAX_CTX);
+    g_ctx[i] = tl_cx;
+    tl_cx->slot = i;
+    pthread_mutex_unlock (&g_device_mutex);
   }
   return tl_cx;
+}
+
+void
+sb2h_sync (Sb2hContext *cx)
+{
+  /* a worker that waits gives its core away (many workers share the host with the
+   * application's own threads); the price is a few tens of microseconds of wake-up latency */
+  SB2H_CUDA (cudaEventRecord (cx->sync_ev, cx->stream));
+  SB2H_CUDA (cudaEventSynchronize (cx->sync_ev));
+  cx->dirty = 0;
+}
+
+/* ---- last writer of a device region ------------------------------------------ */
+#define SB2H_NWRITE 8192
+static struct {
+  const void *key;
+  cudaEvent_t ev;
+  cudaStream_t stream;                 /* last writer */
+  unsigned long long users[SB2H_MAX_CTX / 64];   /* contexts that enqueued work on the region since it was allocated */
+} g_writes[SB2H_NWRITE];
+static pthread_mutex_t g_write_mutex = PTHREAD_MUTEX_INITIALIZER;
+
+static int
+write_slot (const void *key, int create)
+{
+  size_t h = (size_t) (((uintptr_t) key >> 8) * 2654435761u) % SB2H_NWRITE;
+  int i;
+  for (i = 0; i < SB2H_NWRITE; i++) {
+    const int k = (int) ((h + i) % SB2H_NWRITE);
+    if (g_writes[k].key == key) return k;
+    if (!g_writes[k].key) {
+      if (!create) return -1;
+      g_writes[k].key = key;                 /* keys are never removed: a region that is freed and */
+      return k;                              /* handed out again keeps its (by then complete) event */
+    }
+  }
+  return -1;
+}
+
+void
+sb2h_frame_use (Sb2hContext *cx, const void *region)
+{
+  int k;
+  pthread_mutex_lock (&g_write_mutex);
+  k = write_slot (region, 1);
+  if (k >= 0) {
+    if (g_writes[k].stream && g_writes[k].stream != cx->stream)
+      SB2H_CUDA (cudaStreamWaitEvent (cx->stream, g_writes[k].ev, 0));
+    g_writes[k].users[cx->slot / 64] |= 1ull << (cx->slot % 64);
+  }
+  pthread_mutex_unlock (&g_write_mutex);
+  if (k < 0) sb2h_sync (cx);     /* table full: at least order this thread */
+}
+
+/* which contexts may still have work in flight on `region`; forgets them (the region is being freed) */
+static int
+frame_take_users (const void *region, unsigned long long *users)
+{
+  int k, i, known;
+  pthread_mutex_lock (&g_write_mutex);
+  k = write_slot (region, 0);
+  known = k >= 0;
+  for (i = 0; i < SB2H_MAX_CTX / 64; i++) {
+    users[i] = known ? g_writes[k].users[i] : 0;
+    if (known) g_writes[k].users[i] = 0;
+  }
+  pthread_mutex_unlock (&g_write_mutex);
+  return known;
+}
+
+void
+sb2h_frame_wrote (Sb2hContext *cx, const void *region)
+{
+  int k;
+  pthread_mutex_lock (&g_write_mutex);
+  k = write_slot (region, 1);
+  if (k < 0) {
+    /* table full: fall back to waiting */
+    pthread_mutex_unlock (&g_write_mutex);
+    sb2h_sync (cx);
+    return;
+  }
+  if (!g_writes[k].ev) SB2H_CUDA (cudaEventCreateWithFlags (&g_writes[k].ev, cudaEventDisableTiming));
+  SB2H_CUDA (cudaEventRecord (g_writes[k].ev, cx->stream));
+  g_writes[k].stream = cx->stream;
+  g_writes[k].users[cx->slot / 64] |= 1ull << (cx->slot % 64);
+  pthread_mutex_unlock (&g_write_mutex);
+  cx->dirty = 1;
 }
 
 void *
@@ -112,7 +215,7 @@ sb2h_dev_buffer (Sb2hContext *cx, int which, size_t bytes)
   if (bytes == 0) return NULL;
   if (cx->dev_size[which] < bytes) {
     if (cx->dev[which]) {
-      SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+      sb2h_sync (cx);
       SB2H_CUDA (cudaFree (cx->dev[which]));
     }
     bytes = (bytes + 0xfffff) & ~(size_t) 0xfffff;
@@ -179,6 +282,61 @@ sb2h_pool_free (void *ptr)
   SB2H_CUDA (cudaFree (ptr));
 }
 
+/* process-wide pool of page-locked host blocks (motion fields coming back from the GPU) */
+#define SB2H_PINNED_SLOTS 256
+static struct { void *ptr; size_t bytes; int in_use; } g_pinned[SB2H_PINNED_SLOTS];
+static pthread_mutex_t g_pinned_mutex = PTHREAD_MUTEX_INITIALIZER;
+
+void *
+sb2h_pinned_pool_alloc (size_t bytes)
+{
+  int i, free_slot = -1;
+  void *p = NULL;
+  pthread_mutex_lock (&g_pinned_mutex);
+  for (i = 0; i < SB2H_PINNED_SLOTS; i++) {
+    if (g_pinned[i].ptr && !g_pinned[i].in_use && g_pinned[i].bytes == bytes) {
+      g_pinned[i].in_use = 1;
+      p = g_pinned[i].ptr;
+      break;
+    }
+    if (!g_pinned[i].ptr && free_slot < 0) free_slot = i;
+  }
+  if (!p) {
+    if (free_slot < 0) {
+      for (i = 0; i < SB2H_PINNED_SLOTS; i++)
+        if (!g_pinned[i].in_use) {
+          SB2H_CUDA (cudaFreeHost (g_pinned[i].ptr));
+          g_pinned[i].ptr = NULL;
+          free_slot = i;
+          break;
+        }
+      if (free_slot < 0) sb2h_fatal (__func__, "pinned block pool exhausted");
+    }
+    SB2H_CUDA (cudaHostAlloc (&g_pinned[free_slot].ptr, bytes, cudaHostAllocPortable));
+    g_pinned[free_slot].bytes = bytes;
+    g_pinned[free_slot].in_use = 1;
+    p = g_pinned[free_slot].ptr;
+  }
+  pthread_mutex_unlock (&g_pinned_mutex);
+  return p;
+}
+
+int
+sb2h_pinned_pool_free (void *ptr)
+{
+  int i, found = 0;
+  if (!ptr) return 0;
+  pthread_mutex_lock (&g_pinned_mutex);
+  for (i = 0; i < SB2H_PINNED_SLOTS; i++)
+    if (g_pinned[i].ptr == ptr) {
+      g_pinned[i].in_use = 0;
+      found = 1;
+      break;
+    }
+  pthread_mutex_unlock (&g_pinned_mutex);
+  return found;
+}
+
 void
 sb2h_copy_rect (Sb2hContext *cx, void *dst, size_t dst_stride, const void *src,
     size_t src_stride, size_t row_bytes, int rows)
@@ -189,6 +347,68 @@ sb2h_copy_rect (Sb2hContext *cx, void *dst, size_t dst_stride, const void *src,
 }
 
 /* ---- memory domains -------------------------------------------------------- */
+/* Blocks of a CUDA domain that were handed back while a thread that used them still had
+ * un-waited work on its stream: the slot stays marked in use until an event recorded on each
+ * such stream at the time of the free has completed, so nothing enqueued before the free can
+ * still touch the block when it is handed out again.  Reaped on every later alloc / free of
+ * the domain. */
+#define SB2H_LIMBO 256
+typedef struct {
+  SchroMemoryDomain *domain;
+  int slot, nev;
+  cudaEvent_t ev[SB2H_MAX_CTX];
+} Sb2hLimbo;
+static Sb2hLimbo *g_limbo[SB2H_LIMBO];
+static cudaEvent_t g_evpool[SB2H_LIMBO * 4];
+static int g_nevpool;
+static pthread_mutex_t g_limbo_mutex = PTHREAD_MUTEX_INITIALIZER;
+
+static cudaEvent_t
+evpool_get (void)
+{
+  cudaEvent_t e;
+  if (g_nevpool > 0) return g_evpool[--g_nevpool];
+  SB2H_CUDA (cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
+  return e;
+}
+
+static void
+evpool_put (cudaEvent_t e)
+{
+  if (g_nevpool < (int) (sizeof (g_evpool) / sizeof (g_evpool[0]))) g_evpool[g_nevpool++] = e;
+  else cudaEventDestroy (e);
+}
+
+/* domain->mutex held.  wait != 0: block until every parked block of the domain is free. */
+static void
+limbo_reap (SchroMemoryDomain *domain, int wait)
+{
+  int i, k;
+  pthread_mutex_lock (&g_limbo_mutex);
+  for (i = 0; i < SB2H_LIMBO; i++) {
+    Sb2hLimbo *l = g_limbo[i];
+    if (!l || l->domain != domain) continue;
+    for (k = 0; k < l->nev; ) {
+      cudaError_t e = wait ? cudaEventSynchronize (l->ev[k]) : cudaEventQuery (l->ev[k]);
+      if (e == cudaSuccess) {
+        evpool_put (l->ev[k]);
+        l->ev[k] = l->ev[--l->nev];
+      } else if (e == cudaErrorNotReady) {
+        k++;
+      } else {
+        sb2h_fatal (__func__, "event query: %s", cudaGetErrorString (e));
+      }
+    }
+    if (l->nev == 0) {
+      domain->slots[l->slot].flags &= ~SCHRO_MEMORY_DOMAIN_SLOT_IN_USE;
+      free (l);
+      g_limbo[i] = NULL;
+    }
+  }
+  pthread_mutex_unlock (&g_limbo_mutex);
+}
+
+
 static void *
 cuda_alloc (int size)
 {
@@ -251,6 +471,11 @@ schro_memory_domain_free (SchroMemoryDomain *domain)
 {
   int i;
   SB2H_ASSERT (domain != NULL);
+  if (domain->flags & SCHRO_MEMORY_DOMAIN_CUDA) {
+    pthread_mutex_lock (domain->mutex);
+    limbo_reap (domain, 1);
+    pthread_mutex_unlock (domain->mutex);
+  }
   for (i = 0; i < SCHRO_MEMORY_DOMAIN_SLOTS; i++) {
     if (domain->slots[i].flags & SCHRO_MEMORY_DOMAIN_SLOT_ALLOCATED)
       domain->free (domain->slots[i].ptr, domain->slots[i].size);
@@ -268,6 +493,7 @@ schro_memory_domain_alloc (SchroMemoryDomain *domain, int size)
   void *ptr = NULL;
   SB2H_ASSERT (domain != NULL);
   pthread_mutex_lock (domain->mutex);
+  if (domain->flags & SCHRO_MEMORY_DOMAIN_CUDA) limbo_reap (domain, 0);
   for (i = 0; i < SCHRO_MEMORY_DOMAIN_SLOTS; i++) {
     unsigned int f = domain->slots[i].flags;
     if ((f & SCHRO_MEMORY_DOMAIN_SLOT_ALLOCATED) && !(f & SCHRO_MEMORY_DOMAIN_SLOT_IN_USE) &&
@@ -275,6 +501,27 @@ schro_memory_domain_alloc (SchroMemoryDomain *domain, int size)
       domain->slots[i].flags |= SCHRO_MEMORY_DOMAIN_SLOT_IN_USE;
       ptr = domain->slots[i].ptr;
       break;
+    }
+  }
+  if (!ptr && (domain->flags & SCHRO_MEMORY_DOMAIN_CUDA)) {
+    /* a parked block of this size beats a new cudaMalloc (which would stall the whole device,
+     * and a caller that never waits would otherwise grow the domain without bound) */
+    int parked = 0;
+    pthread_mutex_lock (&g_limbo_mutex);
+    for (i = 0; i < SB2H_LIMBO; i++)
+      if (g_limbo[i] && g_limbo[i]->domain == domain && domain->slots[g_limbo[i]->slot].size == size) parked = 1;
+    pthread_mutex_unlock (&g_limbo_mutex);
+    if (parked) {
+      limbo_reap (domain, 1);
+      for (i = 0; i < SCHRO_MEMORY_DOMAIN_SLOTS; i++) {
+        unsigned int f = domain->slots[i].flags;
+        if ((f & SCHRO_MEMORY_DOMAIN_SLOT_ALLOCATED) && !(f & SCHRO_MEMORY_DOMAIN_SLOT_IN_USE) &&
+            domain->slots[i].size == size) {
+          domain->slots[i].flags |= SCHRO_MEMORY_DOMAIN_SLOT_IN_USE;
+          ptr = domain->slots[i].ptr;
+          break;
+        }
+      }
     }
   }
   if (!ptr) {
@@ -301,7 +548,44 @@ schro_memory_domain_memfree (SchroMemoryDomain *domain, void *ptr)
   pthread_mutex_lock (domain->mutex);
   for (i = 0; i < SCHRO_MEMORY_DOMAIN_SLOTS; i++) {
     if ((domain->slots[i].flags & SCHRO_MEMORY_DOMAIN_SLOT_IN_USE) && domain->slots[i].ptr == ptr) {
-      domain->slots[i].flags &= ~SCHRO_MEMORY_DOMAIN_SLOT_IN_USE;
+      Sb2hLimbo *l = NULL;
+      if (domain->flags & SCHRO_MEMORY_DOMAIN_CUDA) {
+        unsigned long long users[SB2H_MAX_CTX / 64];
+        int c, k;
+        limbo_reap (domain, 0);
+        l = calloc (1, sizeof (Sb2hLimbo));
+        l->domain = domain;
+        l->slot = i;
+        frame_take_users (ptr, users);
+        pthread_mutex_lock (&g_device_mutex);
+        for (c = 0; c < SB2H_MAX_CTX; c++)
+          if (g_ctx[c] && g_ctx[c]->dirty && ((users[c / 64] >> (c % 64)) & 1)) {
+            pthread_mutex_lock (&g_limbo_mutex);
+            l->ev[l->nev] = evpool_get ();
+            pthread_mutex_unlock (&g_limbo_mutex);
+            SB2H_CUDA (cudaEventRecord (l->ev[l->nev], g_ctx[c]->stream));
+            l->nev++;
+          }
+        pthread_mutex_unlock (&g_device_mutex);
+        if (l->nev) {
+          pthread_mutex_lock (&g_limbo_mutex);
+          for (k = 0; k < SB2H_LIMBO && g_limbo[k]; k++) ;
+          if (k < SB2H_LIMBO) g_limbo[k] = l;
+          pthread_mutex_unlock (&g_limbo_mutex);
+          if (k == SB2H_LIMBO) {
+            /* no room to park it: wait here */
+            for (c = 0; c < l->nev; c++) {
+              SB2H_CUDA (cudaEventSynchronize (l->ev[c]));
+              pthread_mutex_lock (&g_limbo_mutex);
+              evpool_put (l->ev[c]);
+              pthread_mutex_unlock (&g_limbo_mutex);
+            }
+            l->nev = 0;
+          }
+        }
+        if (l->nev == 0) { free (l); l = NULL; }
+      }
+      if (!l) domain->slots[i].flags &= ~SCHRO_MEMORY_DOMAIN_SLOT_IN_USE;
       pthread_mutex_unlock (domain->mutex);
       return;
     }
@@ -424,6 +708,8 @@ frame_copy_all (SchroFrame *dest, SchroFrame *src)
   int k;
   SB2H_ASSERT (dest->format == src->format && dest->width == src->width &&
       dest->height == src->height);
+  if (sb2h_mem_kind (src->regions[0]) == SB2H_MEM_DEVICE) sb2h_frame_use (cx, src->regions[0]);
+  if (sb2h_mem_kind (dest->regions[0]) == SB2H_MEM_DEVICE) sb2h_frame_use (cx, dest->regions[0]);
   for (k = 0; k < 3; k++) {
     SchroFrameData *d = &dest->components[k], *s = &src->components[k];
     const int bpp = sb2h_bpp (src->format);
@@ -439,7 +725,7 @@ frame_copy_all (SchroFrame *dest, SchroFrame *src)
           s->height);
     }
   }
-  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  sb2h_sync (cx);       /* the host side of the copy may be reused / read as soon as we return */
   dest->upsample_done = (dest->is_upsampled == src->is_upsampled &&
       dest->extension == src->extension) ? src->upsample_done : 0;
 }

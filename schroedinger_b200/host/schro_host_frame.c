@@ -63,6 +63,7 @@ stage_in (Sb2hContext *cx, Staged *s, SchroFrame *f, int which_buf, int upload)
   if (sb2h_mem_kind (f->regions[0]) == SB2H_MEM_DEVICE) {
     s->dev_region = NULL;
     stage_describe (s, f, f->regions[0]);
+    sb2h_frame_use (cx, f->regions[0]);
     return;
   }
   s->dev_region = sb2h_dev_buffer (cx, which_buf, s->region_bytes + 256);
@@ -78,6 +79,24 @@ stage_out (Sb2hContext *cx, Staged *s)
   if (s->dev_region)
     SB2H_CUDA (cudaMemcpyAsync (s->frame->regions[0], s->dev_region, s->region_bytes,
             cudaMemcpyDefault, cx->stream));
+}
+
+/* End of a call that used the staged frames st[0..n): if any of them lives in host memory its
+ * result must be there when the call returns, so wait; otherwise leave the work in flight and
+ * note which device frames (bit i of `written`) it writes. */
+static void
+stage_finish (Sb2hContext *cx, Staged **st, int n, unsigned written)
+{
+  int i, host = 0;
+  for (i = 0; i < n; i++)
+    if (st[i] && st[i]->dev_region) host = 1;
+  if (host) {
+    sb2h_sync (cx);
+    return;
+  }
+  for (i = 0; i < n; i++)
+    if (st[i] && ((written >> i) & 1)) sb2h_frame_wrote (cx, st[i]->frame->regions[0]);
+  cx->dirty = 1;
 }
 
 static void
@@ -96,7 +115,10 @@ schro_frame_mc_edgeextend (SchroFrame *frame)
   stage_in (cx, &s, frame, SB2H_BUF_IN, 1);
   SB2H_CHECK (sb2_mc_edgeextend (&s.slab, frame->extension, 0, cx->stream), "sb2_mc_edgeextend");
   stage_out (cx, &s);
-  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  {
+    Staged *st[1] = { &s };
+    stage_finish (cx, st, 1, 1u);
+  }
 }
 
 void
@@ -111,7 +133,10 @@ schro_upsampled_frame_upsample (SchroFrame *df)
   stage_in (cx, &s, df, SB2H_BUF_IN, 1);
   SB2H_CHECK (sb2_upsample (&s.slab, df->extension, cx->stream), "sb2_upsample");
   stage_out (cx, &s);
-  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  {
+    Staged *st[1] = { &s };
+    stage_finish (cx, st, 1, 1u);
+  }
 }
 
 static void
@@ -134,7 +159,7 @@ upsample_1d (SchroFrameData *dest, SchroFrameData *src, int vertical)
             cx->stream), "sb2_upsample_plane_1d");
     sb2h_copy_rect (cx, dest->data, dest->stride, dout, pitch, w, h);
   }
-  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  sb2h_sync (cx);
 }
 
 void
@@ -160,7 +185,10 @@ schro_frame_downsample (SchroFrame *dest, SchroFrame *src)
   stage_in (cx, &d, dest, SB2H_BUF_OUT, 1);     /* keep dest's borders as they are */
   SB2H_CHECK (sb2_downsample (&s.slab, &d.slab, cx->stream), "sb2_downsample");
   stage_out (cx, &d);
-  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  {
+    Staged *st[2] = { &s, &d };
+    stage_finish (cx, st, 2, 2u);
+  }
 }
 
 /* ---- OBMC ------------------------------------------------------------------ */
@@ -269,7 +297,13 @@ schro_motion_render_u8 (SchroMotion *motion, SchroFrame *dest, SchroFrame *addfr
   stage_out (cx, &acc);
   if (add) stage_out (cx, &out);
   else stage_out (cx, &res);
-  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  if (sb2h_mem_kind (motion->motion_vectors) != SB2H_MEM_PAGEABLE) {
+    /* vectors in page-locked memory are read by the DMA engine after the copy call returns */
+    sb2h_sync (cx);
+  } else {
+    Staged *st[5] = { &r0, motion->src2 ? &r1 : NULL, &acc, &res, output_frame ? &out : NULL };
+    stage_finish (cx, st, 5, 4u | (add ? 16u : 8u));
+  }
 }
 
 void
@@ -309,7 +343,7 @@ schro_metric_absdiff_u8 (uint8_t *a, int a_stride, uint8_t *b, int b_stride, int
   SB2H_CHECK (sb2_sad_u8 (da, as, db, bs, off, off + 1, 1, width, height, (uint32_t *) (off + 2),
           cx->stream), "sb2_sad_u8");
   SB2H_CUDA (cudaMemcpyAsync (&result, off + 2, sizeof (result), cudaMemcpyDefault, cx->stream));
-  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  sb2h_sync (cx);
   return (int) result;
 }
 
@@ -331,7 +365,7 @@ schro_metric_get_dc (SchroFrameData *src, int value, int width, int height)
   dres = sb2h_dev_buffer (cx, SB2H_BUF_AUX0, 64);
   SB2H_CHECK (sb2_sad_dc_u8 (da, as, value, width, height, dres, cx->stream), "sb2_sad_dc_u8");
   SB2H_CUDA (cudaMemcpyAsync (&result, dres, sizeof (result), cudaMemcpyDefault, cx->stream));
-  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  sb2h_sync (cx);
   return result;
 }
 
@@ -348,6 +382,6 @@ schro_metric_get_biref (SchroFrameData *fd, SchroFrameData *src1, int weight1, S
   SB2H_CHECK (sb2_sad_biref_u8 (da, as, d1, s1s, weight1, d2, s2s, weight2, shift, width, height, dres,
           cx->stream), "sb2_sad_biref_u8");
   SB2H_CUDA (cudaMemcpyAsync (&result, dres, sizeof (result), cudaMemcpyDefault, cx->stream));
-  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  sb2h_sync (cx);
   return result;
 }

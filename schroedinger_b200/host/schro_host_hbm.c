@@ -37,7 +37,8 @@ schro_motion_field_new (int x_num_blocks, int y_num_blocks)
 void
 schro_motion_field_free (SchroMotionField *field)
 {
-  free (field->motion_vectors);
+  /* fields that came back from the GPU live in pooled page-locked memory */
+  if (!sb2h_pinned_pool_free (field->motion_vectors)) free (field->motion_vectors);
   free (field);
 }
 
@@ -110,6 +111,7 @@ level_slab (Sb2hContext *cx, SchroFrame *f, void **cache, sb2_slab *slab)
     sb2h_fatal (__func__, "block matching needs u8 frames");
   if (sb2h_mem_kind (f->regions[0]) == SB2H_MEM_DEVICE) {
     base = f->regions[0];
+    sb2h_frame_use (cx, base);
   } else {
     if (!*cache) {
       *cache = sb2h_pool_alloc (bytes);
@@ -130,8 +132,10 @@ level_slab (Sb2hContext *cx, SchroFrame *f, void **cache, sb2_slab *slab)
   }
 }
 
-void
-schro_hierarchical_bm_scan_hint (SchroHierBm *hbm, int shift, int h_range)
+/* one level, left in flight on the thread's stream: kernel + asynchronous copy of the field
+ * into a page-locked host SchroMotionField */
+static void
+scan_level (SchroHierBm *hbm, int shift, int h_range)
 {
   Sb2hHierBm *h = (Sb2hHierBm *) hbm;
   Sb2hContext *cx = sb2h_context ();
@@ -170,12 +174,19 @@ schro_hierarchical_bm_scan_hint (SchroHierBm *hbm, int shift, int h_range)
   mf = malloc (sizeof (SchroMotionField));
   mf->x_num_blocks = params->x_num_blocks;
   mf->y_num_blocks = params->y_num_blocks;
-  mf->motion_vectors = malloc (n * sizeof (SchroMotionVector));
+  mf->motion_vectors = sb2h_pinned_pool_alloc (n * sizeof (SchroMotionVector));
   SB2H_CUDA (cudaMemcpyAsync (mf->motion_vectors, h->dev_field[shift], n * sizeof (SchroMotionVector),
           cudaMemcpyDefault, cx->stream));
-  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  cx->dirty = 1;
   if (hbm->downsampled_mf[shift]) schro_motion_field_free (hbm->downsampled_mf[shift]);
   hbm->downsampled_mf[shift] = mf;
+}
+
+void
+schro_hierarchical_bm_scan_hint (SchroHierBm *hbm, int shift, int h_range)
+{
+  scan_level (hbm, shift, h_range);
+  sb2h_sync (sb2h_context ());      /* the host field is read by the caller */
 }
 
 void
@@ -184,8 +195,10 @@ schro_hbm_scan (SchroHierBm *hbm)
   int i, half_scan_range = 20;
   const int n_levels = hbm->hierarchy_levels;
   SB2H_ASSERT (n_levels > 0);
-  schro_hierarchical_bm_scan_hint (hbm, n_levels, half_scan_range);
+  /* the levels chain on the stream; one wait at the end makes all host fields valid */
+  scan_level (hbm, n_levels, half_scan_range);
   half_scan_range >>= 1;
   for (i = n_levels - 1; 1 <= i; --i, half_scan_range >>= 1)
-    schro_hierarchical_bm_scan_hint (hbm, i, half_scan_range > 3 ? half_scan_range : 3);
+    scan_level (hbm, i, half_scan_range > 3 ? half_scan_range : 3);
+  sb2h_sync (sb2h_context ());
 }

@@ -80,7 +80,7 @@ run_planes (const PlaneList *src, const PlaneList *dst, int is_s32, int filter, 
     rc = inverse ? sb2_iwt_inverse (&sin, &sout, is_s32, filter, depth, ws, ws_bytes, cx->stream)
                  : sb2_iwt_forward (&sin, &sout, is_s32, filter, depth, ws, ws_bytes, cx->stream);
     SB2H_CHECK (rc, inverse ? "sb2_iwt_inverse" : "sb2_iwt_forward");
-    SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+    sb2h_sync (cx);
     return;
   }
 
@@ -101,7 +101,7 @@ run_planes (const PlaneList *src, const PlaneList *dst, int is_s32, int filter, 
     for (c = 0; c < src->ncomp; c++)
       sb2h_copy_rect (cx, dst->data[c], dst->stride[c], (char *) sout.base + sout.offset[c],
           sout.stride[c], (size_t) src->width[c] * bpp, src->height[c]);
-    SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+    sb2h_sync (cx);
   }
 }
 
@@ -183,7 +183,9 @@ frame_iwt_swap (SchroFrame *frame, SchroParams *params, int inverse)
     sin.width[k] = frame->components[k].width;
     sin.height[k] = frame->components[k].height;
   }
+  sb2h_frame_use (cx, old_region);
   new_region = schro_memory_domain_alloc (frame->domain, (int) total);
+  sb2h_frame_use (cx, new_region);
   sout = sin;
   sout.base = new_region;
   ws_bytes = sb2_iwt_workspace_bytes (&sin, is_s32, params->transform_depth, 0);
@@ -193,7 +195,9 @@ frame_iwt_swap (SchroFrame *frame, SchroParams *params, int inverse)
                : sb2_iwt_forward (&sin, &sout, is_s32, params->wavelet_filter_index, params->transform_depth,
                      ws, ws_bytes, cx->stream);
   SB2H_CHECK (rc, inverse ? "sb2_iwt_inverse" : "sb2_iwt_forward");
-  SB2H_CUDA (cudaStreamSynchronize (cx->stream));
+  /* no wait: the new region carries the write, the old one is parked by the domain until the
+   * transform (and anything else in flight) has finished reading it */
+  sb2h_frame_wrote (cx, new_region);
   for (k = 0; k < 3; k++)
     frame->components[k].data = new_region + sin.offset[k];
   frame->regions[0] = new_region;
