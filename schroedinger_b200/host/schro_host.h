@@ -24,6 +24,8 @@ typedef struct {
   cudaStream_t stream;
   void *dev[SB2H_NBUF];
   size_t dev_size[SB2H_NBUF];
+  cudaStream_t stream_hi;  /* highest-priority side stream for the latency-bound wavefront kernels */
+  cudaEvent_t ev_fork, ev_join;
   cudaEvent_t sync_ev;     /* blocking-sync event: waiting threads sleep instead of spinning */
   volatile int dirty;      /* work was enqueued on `stream` that no call has waited for yet */
   int slot;                /* index in the process-wide context table */

@@ -94,6 +94,9 @@ schro_b200_thread_release (void)
     if (cx->dev[i]) cudaFree (cx->dev[i]);
   sb2h_pool_release_all ();
   cudaEventDestroy (cx->sync_ev);
+  cudaEventDestroy (cx->ev_fork);
+  cudaEventDestroy (cx->ev_join);
+  cudaStreamDestroy (cx->stream_hi);
   cudaStreamDestroy (cx->stream);
   free (cx);
   tl_cx = NULL;
@@ -111,6 +114,13 @@ sb2h_context (void)
     tl_cx = calloc (1, sizeof (Sb2hContext));
     SB2H_CUDA (cudaStreamCreateWithFlags (&tl_cx->stream, cudaStreamNonBlocking));
     SB2H_CUDA (cudaEventCreateWithFlags (&tl_cx->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
+    {
+      int lo = 0, hi = 0;
+      SB2H_CUDA (cudaDeviceGetStreamPriorityRange (&lo, &hi));
+      SB2H_CUDA (cudaStreamCreateWithPriority (&tl_cx->stream_hi, cudaStreamNonBlocking, hi));
+      SB2H_CUDA (cudaEventCreateWithFlags (&tl_cx->ev_fork, cudaEventDisableTiming));
+      SB2H_CUDA (cudaEventCreateWithFlags (&tl_cx->ev_join, cudaEventDisableTiming));
+    }
     pthread_mutex_lock (&g_device_mutex);
     for (i = 0; i < SB2H_MAX_CTX && g_ctx[i]; i++) ;
     if (i == SB2H_MAX_CTX) sb2h_fatal (__func__, "more than %d threads use the library", SB2H_MAX_CTX);

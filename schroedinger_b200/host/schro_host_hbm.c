@@ -166,9 +166,17 @@ scan_level (SchroHierBm *hbm, int shift, int h_range)
   }
   if (!h->dev_field[shift])
     h->dev_field[shift] = sb2h_pool_alloc (n * sizeof (SchroMotionVector));
+  /* The block-matching kernels are dependency-latency bound: a block row makes progress only
+   * while every row above it is resident.  They run on the thread's highest-priority stream so
+   * that their CTAs are placed before those of the bandwidth kernels other threads have queued;
+   * cx->stream stays the ordering backbone (fork before, join after). */
+  SB2H_CUDA (cudaEventRecord (cx->ev_fork, cx->stream));
+  SB2H_CUDA (cudaStreamWaitEvent (cx->stream_hi, cx->ev_fork, 0));
   SB2H_CHECK (sb2_hbm_scan_hint (&p, &ss, &rs, fs->extension, shift, h_range,
           shift < hbm->hierarchy_levels ? h->dev_field[shift + 1] : NULL, h->dev_field[shift], n,
-          h->dev_ws, h->ws_bytes, cx->stream), "sb2_hbm_scan_hint");
+          h->dev_ws, h->ws_bytes, cx->stream_hi), "sb2_hbm_scan_hint");
+  SB2H_CUDA (cudaEventRecord (cx->ev_join, cx->stream_hi));
+  SB2H_CUDA (cudaStreamWaitEvent (cx->stream, cx->ev_join, 0));
   /* schro_hbm_set_motion_field: a new field replaces the level's previous one (every entry
    * is overwritten by the copy below, so no zero-fill) */
   mf = malloc (sizeof (SchroMotionField));
