@@ -593,6 +593,8 @@ def run_ours(args):
     # ---- e2e through the drop-in C API with pinned host frames ----
     e2e = None
     try:
+        if args.no_e2e:
+            raise RuntimeError("skipped (--no-e2e: profiler runs)")
         nthreads = min(args.e2e_threads, B)
         hf = HostFrames(spec, lib, nthreads)
         if args.e2e_driver == "native":
@@ -844,6 +846,7 @@ def main():
                     help="host threads of the e2e leg: pthreads in bench_native/e2e_driver.c, or Python threads + ctypes")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (for ncu runs of the timed region)")
     ap.add_argument("--overlap", action="store_true",
                     help="run the motion-estimation stages on a second stream (measured: no gain in the "
                          "device-resident loop, whose batched wavefronts already keep every SM occupied)")

@@ -578,15 +578,18 @@ obmc_kernel_v3 (const ObmcArgs A)
   }
 }
 
-// ---- v4: block-major two-colour scatter into a shared-memory accumulator -------------
+// ---- v4: block-major scatter into a shared-memory accumulator ---------------------------
 // The gather kernels above are bound by L1 wavefronts: neighbouring pixels belong to
 // different blocks with different vectors, so every byte load of a warp touches ~16 cache
 // lines.  Here the work item is (block, block row, group of 4 pixels): the three items of
 // a block row read 12 contiguous reference bytes, each as one unaligned 32-bit word built
 // from two aligned loads; taps are applied to two pixels at a time in packed 16-bit lanes.
-// Contributions are added into a tile accumulator in shared memory.  Blocks whose (i,j)
-// parities agree never overlap when xblen <= 2*xbsep and yblen <= 2*ybsep, so the tile is
-// processed in four colour phases without atomics.
+// Contributions are added into a tile accumulator in shared memory with atomics (integer
+// adds commute, so the sum is bit-exact whatever the order); a thread keeps its (row, group)
+// for every block it visits, so the item loop has no divisions and no barriers.
+#ifndef OBMC_MINB
+#define OBMC_MINB 6     // 40 registers: latency of the scattered reference loads is hidden by resident warps
+#endif
 constexpr int O4_W = 64, O4_H = 32;
 constexpr int O4_P = O4_W + 12;    // accumulator pitch: 16-byte aligned rows, consecutive block rows on different banks
 
@@ -616,7 +619,7 @@ __device__ __forceinline__ uint2 fetch4x4 (const uint8_t *ref, const BlkRef &br,
 }
 
 template <bool SIMPLE>
-__global__ void __launch_bounds__ (256)
+__global__ void __launch_bounds__ (256, OBMC_MINB)
 obmc_kernel_v4 (const ObmcArgs A)
 {
   __shared__ __align__ (16) BlkEnt tab[MAX_ENT];
@@ -673,70 +676,72 @@ obmc_kernel_v4 (const ObmcArgs A)
   }
   __syncthreads ();
 
-  // ---- four colour phases -----------------------------------------------------------
+  // ---- scatter: every (block, block row, 4-pixel group) item adds into the tile accumulator.
+  // A thread keeps the same (row, group) for every block it visits, so no per-item divisions;
+  // overlapping blocks meet in shared-memory atomics (integer adds commute: bit-exact in any order).
   const int gx = (xblen + 3) >> 2;                 // 4-pixel groups per block row
   const int ipb = gx * yblen;                      // items per block
-  for (int colour = 0; colour < 4; colour++) {
-    const int ci = colour & 1, cj = colour >> 1;
-    // blocks of this colour inside the tile's block rectangle
-    const int fi = ti0 + ((ti0 & 1) != ci), fj = tj0 + ((tj0 & 1) != cj);
-    const int nci = fi <= ti1 ? (ti1 - fi) / 2 + 1 : 0, ncj = fj <= tj1 ? (tj1 - fj) / 2 + 1 : 0;
-    const int nitems = nci * ncj * ipb;
-    for (int it = threadIdx.x; it < nitems; it += blockDim.x) {
-      const int blk = it / ipb, rem = it - blk * ipb;
-      const int r = rem / gx, g = rem - r * gx;
-      const int bj = blk / nci, bi_ = blk - bj * nci;
-      const int i = fi + 2 * bi_, j = fj + 2 * bj;
+  const int nslot = blockDim.x / ipb;              // blocks in flight per pass
+  const int slot = threadIdx.x / ipb, rem = threadIdx.x - slot * ipb;
+  const int r = rem / gx, g = rem - r * gx;
+  if (slot < nslot) {
+    int bi_ = slot % tni, bj = slot / tni;
+    const int step_i = nslot % tni, step_j = nslot / tni;
+    for (; bj < tnj; ) {
+      const int i = ti0 + bi_, j = tj0 + bj;
       const int bx = xbsep * i - xoff, by = ybsep * j - yoff;
       const int y = by + r, xg = bx + 4 * g;
-      if (y < ty0 || y > y1 || xg > x1 || xg + 3 < tx0) continue;
-      const BlkEnt &e = tab[(j - tj0) * tni + (i - ti0)];
-      const int mode = e.mode;
-      const bool fast = e.fast != 0;
-      int v[4];
-      if (mode == 0) {
-        const int dcv = fast ? w16 ((int) e.dc + 128) : (((int) e.dc + 128) & 0xff);
-        v[0] = v[1] = v[2] = v[3] = dcv;
-      } else {
-        uint2 s0 = make_uint2 (0, 0), s1 = make_uint2 (0, 0);
-        if (mode & 1) s0 = fetch4x4 (ref0, e.r[0], r * rs0 + 4 * g);
-        if (mode & 2) s1 = fetch4x4 (ref1, e.r[1], r * rs1 + 4 * g);
-        if (SIMPLE) {
-          uint2 p;
-          if (mode == 3) {
-            p.x = ((s0.x + s1.x + 0x00010001u) >> 1) & 0x00ff00ffu;     // avgub, two lanes
-            p.y = ((s0.y + s1.y + 0x00010001u) >> 1) & 0x00ff00ffu;
-          } else {
-            p = (mode == 1) ? s0 : s1;
-          }
-          v[0] = p.x & 0xffff; v[1] = p.x >> 16; v[2] = p.y & 0xffff; v[3] = p.y >> 16;
+      if (!(y < ty0 || y > y1 || xg > x1 || xg + 3 < tx0)) {
+        const BlkEnt &e = tab[bj * tni + bi_];
+        const int mode = e.mode;
+        const bool fast = e.fast != 0;
+        int v[4];
+        if (mode == 0) {
+          const int dcv = fast ? w16 ((int) e.dc + 128) : (((int) e.dc + 128) & 0xff);
+          v[0] = v[1] = v[2] = v[3] = dcv;
         } else {
-          const int a0[4] = { (int) (s0.x & 0xffff), (int) (s0.x >> 16), (int) (s0.y & 0xffff), (int) (s0.y >> 16) };
-          const int a1[4] = { (int) (s1.x & 0xffff), (int) (s1.x >> 16), (int) (s1.y & 0xffff), (int) (s1.y >> 16) };
+          uint2 s0 = make_uint2 (0, 0), s1 = make_uint2 (0, 0);
+          if (mode & 1) s0 = fetch4x4 (ref0, e.r[0], r * rs0 + 4 * g);
+          if (mode & 2) s1 = fetch4x4 (ref1, e.r[1], r * rs1 + 4 * g);
+          if (SIMPLE) {
+            uint2 p;
+            if (mode == 3) {
+              p.x = ((s0.x + s1.x + 0x00010001u) >> 1) & 0x00ff00ffu;     // avgub, two lanes
+              p.y = ((s0.y + s1.y + 0x00010001u) >> 1) & 0x00ff00ffu;
+            } else {
+              p = (mode == 1) ? s0 : s1;
+            }
+            v[0] = p.x & 0xffff; v[1] = p.x >> 16; v[2] = p.y & 0xffff; v[3] = p.y >> 16;
+          } else {
+            const int a0[4] = { (int) (s0.x & 0xffff), (int) (s0.x >> 16), (int) (s0.y & 0xffff), (int) (s0.y >> 16) };
+            const int a1[4] = { (int) (s1.x & 0xffff), (int) (s1.x >> 16), (int) (s1.y & 0xffff), (int) (s1.y >> 16) };
 #pragma unroll
-          for (int k = 0; k < 4; k++) v[k] = obmc_combine<false> (A, mode, fast, noscale, e.dc, a0[k], a1[k]);
-        }
-      }
-      int w_y = s_wy[r];
-      if (!fast) {
-        if (y < yoff) w_y += s_wy[2 * yoff - r - 1];
-        if (y >= A.nby * ybsep - yoff) w_y += s_wy[2 * (yblen - yoff) - r - 1];
-      }
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int a = 4 * g + k, x = xg + k;
-        if (a < xblen && x >= tx0 && x <= x1) {
-          int w_x = s_wx[a];
-          if (!fast) {
-            if (x < xoff) w_x += s_wx[2 * xoff - a - 1];
-            if (x >= A.nbx * xbsep - xoff) w_x += s_wx[2 * (xblen - xoff) - a - 1];
+            for (int k = 0; k < 4; k++) v[k] = obmc_combine<false> (A, mode, fast, noscale, e.dc, a0[k], a1[k]);
           }
-          acc[y - ty0][x - tx0] += v[k] * w_x * w_y;
+        }
+        int w_y = s_wy[r];
+        if (!fast) {
+          if (y < yoff) w_y += s_wy[2 * yoff - r - 1];
+          if (y >= A.nby * ybsep - yoff) w_y += s_wy[2 * (yblen - yoff) - r - 1];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int a = 4 * g + k, x = xg + k;
+          if (a < xblen && x >= tx0 && x <= x1) {
+            int w_x = s_wx[a];
+            if (!fast) {
+              if (x < xoff) w_x += s_wx[2 * xoff - a - 1];
+              if (x >= A.nbx * xbsep - xoff) w_x += s_wx[2 * (xblen - xoff) - a - 1];
+            }
+            atomicAdd (&acc[y - ty0][x - tx0], v[k] * w_x * w_y);
+          }
         }
       }
+      bi_ += step_i; bj += step_j;
+      if (bi_ >= tni) { bi_ -= tni; bj++; }
     }
-    __syncthreads ();
   }
+  __syncthreads ();
 
   // ---- finish: four pixels per thread ---------------------------------------------------
   for (int t = threadIdx.x; t < (O4_W / 4) * th; t += blockDim.x) {
@@ -905,7 +910,7 @@ sb2_obmc_render (const sb2_obmc_params *p, const void *motion_vectors, size_t mv
     // whose rows are 4-byte aligned (word loads) and a block table that fits
     bool v4_ok = v3_ok;
     for (int c = 0; c < ncomp && v4_ok; c++) {
-      if (A.xblen[c] > 2 * A.xbsep[c] || A.yblen[c] > 2 * A.ybsep[c]) v4_ok = false;
+      if (((A.xblen[c] + 3) >> 2) * A.yblen[c] > 256) v4_ok = false;     // one block's items must fit a CTA pass
       const int ni = (O4_W + A.xblen[c]) / A.xbsep[c] + 2, nj = (O4_H + A.yblen[c]) / A.ybsep[c] + 2;
       if (ni * nj > MAX_ENT) v4_ok = false;
       if ((ref0->stride[c] & 3) || (ref1 && (ref1->stride[c] & 3))) v4_ok = false;
