@@ -638,18 +638,27 @@ def run_ours(args):
     value = B * world * args.steps / (elapsed_ms * 1e-3)
     # dominant kernel = largest share of device time in the timed region
     dom_tag, dom = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, None)
+    # DRAM bytes per launch from the committed ncu capture (valid for the workload / batch it was taken at)
+    traffic = {}
+    try:
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
+        if tj["workload"] == args.workload and tj["batch_per_gpu"] == B and not args.overlap:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = None
     if dom:
         ach = dom["bytes"] / dom["launches"] / (dom["ms"] / dom["launches"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom_tag, "achieved": round(ach, 1), "peak": peak,
-                    "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+                    "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic.get(dom_tag),
+                    "alg_bytes_per_launch": round(dom["bytes"] / dom["launches"]),
                     "peak_source": peak_src, "launch_ms": round(dom["ms"] / dom["launches"], 4),
                     "share_of_step": round(dom["ms"] / max(1e-9, sum(r["ms"] for r in prof.values())), 3)}
     roofline_all = {}
     for k, v in sorted(prof.items()):
         a_ = v["bytes"] / max(v["ms"], 1e-9) / 1e6
         roofline_all[k] = {"achieved_GBps": round(a_, 1), "frac": round(a_ / peak, 4),
-                           "launch_ms": round(v["ms"] / v["launches"], 4),
+                           "launch_ms": round(v["ms"] / v["launches"], 4), "traffic": traffic.get(k),
                            "share_of_step": round(v["ms"] / max(1e-9, sum(r["ms"] for r in prof.values())), 3)}
     stage_report = {}
     for s in st.stages:
