@@ -141,6 +141,30 @@ __device__ __forceinline__ unsigned load4_unaligned (const uint8_t *p)
   return __funnelshift_r (w0, w1, (unsigned) mis * 8);
 }
 
+// The same with the alignment work hoisted out of the row loop: every row of a block starts at
+// the same byte offset inside its word (strides are multiples of 4), so the aligned base, the
+// shift and "needs a third word" are computed once per block position.
+struct RowRef { const unsigned *w; unsigned sh; bool three; };
+__device__ __forceinline__ RowRef row_ref (const uint8_t *p)
+{
+  RowRef r;
+  const unsigned mis = (unsigned) ((size_t) p & 3);
+  r.w = reinterpret_cast<const unsigned *> (p - mis);
+  r.sh = mis * 8;
+  r.three = mis != 0;
+  return r;
+}
+__device__ __forceinline__ uint2 row_load8 (const RowRef &r, int word_off)
+{
+  const unsigned w0 = __ldg (r.w + word_off), w1 = __ldg (r.w + word_off + 1), w2 = r.three ? __ldg (r.w + word_off + 2) : 0u;
+  return make_uint2 (__funnelshift_r (w0, w1, r.sh), __funnelshift_r (w1, w2, r.sh));
+}
+__device__ __forceinline__ unsigned row_load4 (const RowRef &r, int word_off)
+{
+  const unsigned w0 = __ldg (r.w + word_off), w1 = r.three ? __ldg (r.w + word_off + 1) : 0u;
+  return __funnelshift_r (w0, w1, r.sh);
+}
+
 #ifdef SB2_HBM_TRACE
 __device__ long long g_hbm_trace[512 * 8];
 #define TRACE(k) do { if (trace_on && threadIdx.x == 0 && bi < 512) g_hbm_trace[bi * 8 + (k)] = clock64 (); } while (0)
@@ -189,10 +213,14 @@ struct BlockShared {
 // panning content, B200): level 0 4.4 ms with SPEC vs 3.6 ms without -- warp 1 becomes the
 // longer loop and misses pay a single-warp scan -- so it is compiled out; kept because it
 // wins when vectors are coherent (hit rate near 1) and the chain is poll -> rank -> publish.
+// 64 registers per thread (85 for the two-warp variant, measured best at 32 pictures per launch):
+// a row's CTA mostly waits, so its footprint in the register file decides how many rows /
+// pictures / other kernels an SM can host, while too tight a cap makes the compiler recompute
+#ifndef SB2_HBM_THREADS_PER_SM
+#define SB2_HBM_THREADS_PER_SM 1024
+#endif
 template <int NW, bool SPEC = false>
-// 64 registers per thread: a row's CTA mostly waits, so its footprint in the register file --
-// not its instruction rate -- decides how many rows / pictures / other kernels an SM can host
-__global__ void __launch_bounds__ (32 * NW, 1024 / (32 * NW))
+__global__ void __launch_bounds__ (32 * NW, NW == 2 ? 12 : SB2_HBM_THREADS_PER_SM / (32 * NW))
 hbm_level_kernel (const HbmArgs A)
 {
   static_assert (NW >= 2, "one warp prepares the static candidates of the next block");
@@ -237,24 +265,25 @@ hbm_level_kernel (const HbmArgs A)
     unsigned part_sad = 0;
     if (ok && want) {
       if (part < 2) {
-        const uint8_t *a = sp[0] + (ptrdiff_t) (y0 + 4 * part) * ss[0] + x0;
-        const uint8_t *b = rp[0] + (ptrdiff_t) (y0 + dy + 4 * part) * rs[0] + x0 + dx;
+        const uint2 *a = reinterpret_cast<const uint2 *> (sp[0] + (ptrdiff_t) (y0 + 4 * part) * ss[0] + x0);
+        const RowRef b = row_ref (rp[0] + (ptrdiff_t) (y0 + dy + 4 * part) * rs[0] + x0 + dx);
+        const int asw = ss[0] >> 3, rsw = rs[0] >> 2;
 #pragma unroll
         for (int y = 0; y < 4; y++) {
-          const uint2 av = __ldg (reinterpret_cast<const uint2 *> (a + (ptrdiff_t) y * ss[0]));
-          const uint2 bv = load8_unaligned (b + (ptrdiff_t) y * rs[0]);
+          const uint2 av = __ldg (a + y * asw);
+          const uint2 bv = row_load8 (b, y * rsw);
           part_sad += __vsadu4 (av.x, bv.x) + __vsadu4 (av.y, bv.y);
         }
       } else {
         const int sx = x0 >> 1, sy = y0 >> 1, rx = (x0 + dx) >> 1, ry = (y0 + dy) >> 1;
 #pragma unroll
         for (int c = 1; c < 3; c++) {
+          const unsigned *a = reinterpret_cast<const unsigned *> (sp[c] + (ptrdiff_t) sy * ss[c] + sx);
+          const RowRef b = row_ref (rp[c] + (ptrdiff_t) ry * rs[c] + rx);
+          const int asw = ss[c] >> 2, rsw = rs[c] >> 2;
 #pragma unroll
-          for (int y = 0; y < 4; y++) {
-            const unsigned av = __ldg (reinterpret_cast<const unsigned *> (sp[c] + (ptrdiff_t) (sy + y) * ss[c] + sx));
-            const unsigned bv = load4_unaligned (rp[c] + (ptrdiff_t) (ry + y) * rs[c] + rx);
-            part_sad += __vsadu4 (av, bv);
-          }
+          for (int y = 0; y < 4; y++)
+            part_sad += __vsadu4 (__ldg (a + y * asw), row_load4 (b, y * rsw));
         }
       }
     }
@@ -296,14 +325,20 @@ hbm_level_kernel (const HbmArgs A)
 #pragma unroll
       for (int y = 0; y < 8; y++) srow[y] = __ldg (reinterpret_cast<const uint2 *> (sblk + (ptrdiff_t) y * ss[0]));
     }
+    // p / scan_w without an integer division: p < 2048 and scan_w <= 41, so the float quotient
+    // of (p + 0.5) is at least 0.5 / 41 away from an integer -- far beyond the rounding error
+    const float inv_w = __frcp_rn ((float) wn.scan_w);
+    const uint8_t *rwin = rp[0] + (ptrdiff_t) wn.ymin * rs[0] + wn.xmin;
+    const int rsw = rs[0] >> 2;
     for (int p = first; p < npos; p += stride) {
-      const int b = p / wn.scan_w, a = p - b * wn.scan_w;
-      const uint8_t *rblk = rp[0] + (ptrdiff_t) (wn.ymin + b) * rs[0] + wn.xmin + a;
+      const int b = (int) (((float) p + 0.5f) * inv_w), a = p - b * wn.scan_w;
+      const uint8_t *rblk = rwin + b * rs[0] + a;
       unsigned l = 0;
       if (fast8) {
+        const RowRef rr = row_ref (rblk);
 #pragma unroll
         for (int y = 0; y < 8; y++) {
-          const uint2 bv = load8_unaligned (rblk + (ptrdiff_t) y * rs[0]);
+          const uint2 bv = row_load8 (rr, y * rsw);
           l += __vsadu4 (srow[y].x, bv.x) + __vsadu4 (srow[y].y, bv.y);
         }
       } else {
