@@ -1,0 +1,193 @@
+"""GPU: the host layer's stream-ordered device frames under real threads.
+
+Calls on CUDA-domain frames return before the GPU has finished; these tests
+check the orderings the library promises: a frame written on one thread and read on another,
+memory handed back to a CUDA domain while work on it is still queued, and many workers
+hammering one domain -- always against the oracle, bit-exact."""
+import ctypes
+import threading
+
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+ORACLE = helpers.load_oracle()
+
+W, H, DEPTH, FILT = 704, 576, 4, 0          # big enough that a transform outlives the call that enqueued it
+
+
+def _coef_frames(compat, n, seed):
+    rng = np.random.default_rng(seed)
+    params = compat.make_params(W, H, FILT, DEPTH)
+    iw, ih = params.iwt_luma_width, params.iwt_luma_height
+    pinned = compat.pinned_domain()
+    frames, wants = [], []
+    for _ in range(n):
+        f = compat.frame_new_and_alloc(pinned, compat.FORMAT_S16_420, iw, ih)
+        want = []
+        for c in range(3):
+            v = compat.frame_plane(f, c)
+            v[...] = rng.integers(-255, 256, size=v.shape)
+            want.append(helpers.cpu_wavelet(ORACLE, "oracle", "inv", v.copy(), FILT, DEPTH))
+        frames.append(f)
+        wants.append(want)
+    return params, pinned, frames, wants
+
+
+def _run_threads(fns):
+    errs = []
+
+    def wrap(fn):
+        def go():
+            try:
+                fn()
+            except BaseException as e:       # noqa: BLE001 - report in the main thread
+                errs.append(e)
+        return go
+    ths = [threading.Thread(target=wrap(fn)) for fn in fns]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    if errs:
+        raise errs[0]
+
+
+def test_frame_written_on_one_thread_read_on_another(cuda):
+    """Thread A uploads + inverse-transforms a CUDA-domain frame and returns at once; thread B
+    downloads it.  B's copy must wait for A's kernels (last-writer event of the frame)."""
+    from schroedinger_b200 import compat, lib
+    n = 12
+    params, pinned, hosts, wants = _coef_frames(compat, n, 1)
+    cuda_dom = compat.cuda_domain()
+    iw, ih = params.iwt_luma_width, params.iwt_luma_height
+    dev = [compat.frame_new_and_alloc(cuda_dom, compat.FORMAT_S16_420, iw, ih) for _ in range(n)]
+    outs = [compat.frame_new_and_alloc(pinned, compat.FORMAT_S16_420, iw, ih) for _ in range(n)]
+    ready = [threading.Event() for _ in range(n)]
+
+    scratch = compat.frame_new_and_alloc(cuda_dom, compat.FORMAT_S16_420, iw, ih)
+
+    def producer():
+        for i in range(n):
+            lib.schro_frame_to_gpu(dev[i], hosts[i])
+            # a few milliseconds of queued work ahead of the transform B is going to wait for
+            for _ in range(6):
+                lib.schro_frame_iwt_transform(scratch, ctypes.byref(params))
+                lib.schro_frame_inverse_iwt_transform(scratch, ctypes.byref(params))
+            lib.schro_frame_inverse_iwt_transform(dev[i], ctypes.byref(params))   # in flight when we signal
+            ready[i].set()
+        lib.schro_b200_thread_release()
+
+    def consumer():
+        for i in range(n):
+            ready[i].wait()
+            lib.schro_gpuframe_to_cpu(outs[i], dev[i])
+        lib.schro_b200_thread_release()
+
+    _run_threads([producer, consumer])
+    for i in range(n):
+        for c in range(3):
+            assert np.array_equal(compat.frame_plane(outs[i], c), wants[i][c]), (i, c)
+    for f in dev + outs + hosts + [scratch]:
+        lib.schro_frame_unref(f)
+    lib.schro_memory_domain_free(cuda_dom)
+    lib.schro_memory_domain_free(pinned)
+
+
+def test_many_workers_share_one_cuda_domain(cuda):
+    """Eight workers allocate, transform (the in-place call swaps regions and hands the old one
+    back while the kernel that reads it is still queued), download and free frames of one
+    CUDA domain; a block must never be reused while work on it is in flight."""
+    from schroedinger_b200 import compat, lib
+    nthreads, rounds = 8, 6
+    params, pinned, hosts, wants = _coef_frames(compat, nthreads, 2)
+    cuda_dom = compat.cuda_domain()
+    iw, ih = params.iwt_luma_width, params.iwt_luma_height
+    outs = [compat.frame_new_and_alloc(pinned, compat.FORMAT_S16_420, iw, ih) for _ in range(nthreads)]
+    bad = []
+
+    def worker(t):
+        def go():
+            for r in range(rounds):
+                f = compat.frame_new_and_alloc(cuda_dom, compat.FORMAT_S16_420, iw, ih)
+                lib.schro_frame_to_gpu(f, hosts[t])
+                lib.schro_frame_inverse_iwt_transform(f, ctypes.byref(params))
+                lib.schro_gpuframe_to_cpu(outs[t], f)
+                lib.schro_frame_unref(f)
+                for c in range(3):
+                    if not np.array_equal(compat.frame_plane(outs[t], c), wants[t][c]):
+                        bad.append((t, r, c))
+            lib.schro_b200_thread_release()
+        return go
+
+    _run_threads([worker(t) for t in range(nthreads)])
+    assert not bad, bad[:5]
+    for f in outs + hosts:
+        lib.schro_frame_unref(f)
+    lib.schro_memory_domain_free(cuda_dom)
+    lib.schro_memory_domain_free(pinned)
+
+
+def test_block_matching_from_many_threads_matches_one_thread(cuda):
+    """schro_hbm_scan + level-0 refinement for the same (picture, reference) pair from six
+    threads at once (each on its own stream, the kernels on the high-priority side stream):
+    every thread must get the single-threaded field."""
+    from schroedinger_b200 import compat, lib
+    w, h, levels = 352, 288, 3
+    src, ref = helpers.panning_pair(w, h, np.random.default_rng(5))
+    params = compat.make_params(w, h, xbsep=8, ybsep=8, xblen=12, yblen=12)
+    oracle_fields, _, _ = helpers.oracle_hbm(ORACLE, src, ref, w, h, levels=levels)
+    cuda_dom = compat.cuda_domain()
+
+    def pyramid(img):
+        frames = []
+        cw, ch = w, h
+        for l in range(levels + 1):
+            f = compat.frame_new_and_alloc(cuda_dom, compat.FORMAT_U8_420, cw, ch, 32 if l == 0 else 8, 0)
+            frames.append(f)
+            cw, ch = (cw + 1) // 2, (ch + 1) // 2
+        host = compat.frame_new_and_alloc(None, compat.FORMAT_U8_420, w, h, 32, 0)
+        for c in range(3):
+            compat.frame_plane(host, c)[...] = img[c]
+        lib.schro_frame_to_gpu(frames[0], host)
+        lib.schro_frame_unref(host)
+        lib.schro_frame_mc_edgeextend(frames[0])
+        for l in range(levels):
+            lib.schro_frame_downsample(frames[l + 1], frames[l])
+            lib.schro_frame_mc_edgeextend(frames[l + 1])
+        return frames
+
+    sp, rp = pyramid(src), pyramid(ref)
+    arr = compat.FrameP * (levels + 1)
+    n = params.x_num_blocks * params.y_num_blocks
+
+    def field():
+        hbm = lib.schro_hbm_new_from_frames(ctypes.byref(params), 0, levels, 0, arr(*sp), arr(*rp))
+        lib.schro_hbm_scan(hbm)
+        lib.schro_hierarchical_bm_scan_hint(hbm, 0, 3)
+        mf = lib.schro_hbm_motion_field(hbm, 0)
+        out = np.ctypeslib.as_array(ctypes.cast(mf.contents.motion_vectors, ctypes.POINTER(ctypes.c_uint8)),
+                                    shape=(n * 20,)).copy()
+        lib.schro_hbm_unref(hbm)
+        return out
+
+    want = field()
+    for f in ("flags", "metric", "chroma_metric", "v"):
+        assert np.array_equal(want.view(helpers.MV_DTYPE)[f], oracle_fields[0][f]), f
+    got = [None] * 6
+
+    def worker(t):
+        def go():
+            for _ in range(3):
+                got[t] = field()
+            lib.schro_b200_thread_release()
+        return go
+
+    _run_threads([worker(t) for t in range(6)])
+    for t in range(6):
+        assert np.array_equal(got[t], want), t
+    for f in sp + rp:
+        lib.schro_frame_unref(f)
+    lib.schro_memory_domain_free(cuda_dom)
