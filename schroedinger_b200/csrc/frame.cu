@@ -77,7 +77,11 @@ __device__ __forceinline__ int taps8 (const uint8_t *s, int step)
 // stay below 2^15), the negative taps are folded in with a bias of 8192 = 256<<5 so no
 // lane ever borrows, and the final clamp is a packed min/max.  Tiles that do touch an
 // edge take the per-pixel path of the same kernel, which spells out the border rules.
-constexpr int U2_W = 128, U2_H = 16;             // output tile
+#ifndef U2_TW
+#define U2_TW 128
+#define U2_TH 64    // measured best of 64x32, 128x16/32/64, 256x16/32: less halo per tile, whole rounds of work items
+#endif
+constexpr int U2_W = U2_TW, U2_H = U2_TH;        // output tile
 constexpr int U2_WORDS = U2_W / 4 + 2;           // tile words incl. one halo word each side
 constexpr int U2_PITCH = U2_WORDS + 1;
 
@@ -225,7 +229,11 @@ struct DownArgs {
 };
 
 // ---- downsample, interior tiles: four output pixels per thread, packed arithmetic ------
-constexpr int D2_W = 64, D2_H = 8;                 // output tile
+#ifndef D2_TW
+#define D2_TW 64
+#define D2_TH 32
+#endif
+constexpr int D2_W = D2_TW, D2_H = D2_TH;                // output tile (measured best of 64x8, 64x16, 64x32, 128x8, 128x16: whole rounds of 256 work items)
 constexpr int D2_WORDS = (2 * D2_W) / 4 + 3;       // tmp words: source columns 2*x0-4 .. 2*x0+2*D2_W+8
 constexpr int D2_BW = 2 * D2_W + 2;                // byte tile of the edge path
 
