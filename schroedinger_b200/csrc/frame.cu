@@ -39,9 +39,40 @@ edgeextend_kernel (const FrameArgs a)
   const int w = a.w[comp], h = a.h[comp], ext = a.ext;
   uint8_t *p = reinterpret_cast<uint8_t *> (plane_ptr (a.planes, pic, comp));
   const int stride = a.planes.stride[comp];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  if (((((size_t) p | (size_t) stride) & 3) == 0) && (w & 3) == 0 && (ext & 3) == 0 && ext > 0) {
+    // word path.  Side strips: one item per (row, side, word of the strip), the edge pixel
+    // replicated into all four bytes.  Caps: one item per (word column incl. the corners, top /
+    // bottom), the source word of row 0 / h-1 (corner columns: the replicated corner pixel) stored
+    // to `ext` rows, consecutive threads on consecutive words.
+    const int wps = ext >> 2;                                   // words per strip
+    const int nside = h * 2 * wps;
+    for (int i = tid; i < nside; i += nth) {
+      const int y = i / (2 * wps), c = i - y * (2 * wps);
+      const bool right = c >= wps;
+      uint8_t *row = p + (ptrdiff_t) y * stride;
+      const unsigned v = right ? row[w - 1] : row[0];
+      unsigned *dst = reinterpret_cast<unsigned *> (right ? row + w : row - ext) + (right ? c - wps : c);
+      *dst = v * 0x01010101u;
+    }
+    const int wpr = (w + 2 * ext) >> 2;                         // words per extended row
+    for (int i = tid; i < 2 * wpr; i += nth) {
+      const bool bottom = i >= wpr;
+      const int c = bottom ? i - wpr : i;                       // word column of the extended row
+      const int x = 4 * c - ext;
+      const uint8_t *srow = p + (ptrdiff_t) (bottom ? h - 1 : 0) * stride;
+      unsigned v;
+      if (x < 0) v = srow[0] * 0x01010101u;
+      else if (x >= w) v = srow[w - 1] * 0x01010101u;
+      else v = *reinterpret_cast<const unsigned *> (srow + x);
+      uint8_t *d0 = p + (ptrdiff_t) (bottom ? h : -ext) * stride + x;
+      for (int r = 0; r < ext; r++) *reinterpret_cast<unsigned *> (d0 + (ptrdiff_t) r * stride) = v;
+    }
+    return;
+  }
   const int side = 2 * ext * (h + 2 * ext);       // left+right strips, all rows
   const int caps = 2 * ext * w;                   // top+bottom caps, interior columns
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < side + caps; i += gridDim.x * blockDim.x) {
+  for (int i = tid; i < side + caps; i += nth) {
     int x, y;
     if (i < side) {
       y = i / (2 * ext) - ext;
@@ -398,7 +429,8 @@ sb2_mc_edgeextend (const sb2_slab *frames, int extension, int phase, void *strea
   int maxn = 0;
   for (int c = 0; c < frames->ncomp; c++)
     maxn = max (maxn, 2 * extension * (frames->height[c] + 2 * extension) + 2 * extension * frames->width[c]);
-  dim3 grid (min (ceil_div (maxn, 256), 1024), 1, frames->ncomp * frames->count);
+  // items are words on the usual (aligned) path; both paths are grid-stride loops
+  dim3 grid (min (ceil_div (maxn / 8 + 1, 256), 1024), 1, frames->ncomp * frames->count);
   double bytes = 0;
   for (int c = 0; c < frames->ncomp; c++)
     bytes += 2.0 * (2 * extension * (frames->height[c] + 2 * extension) + 2 * extension * frames->width[c]) * frames->count;
