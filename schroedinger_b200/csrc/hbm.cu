@@ -6,13 +6,13 @@
 //
 // Parallel structure (DESIGN.md "block matching"): a block needs the already-computed
 // vectors of its left, upper and upper-left neighbours OF THE SAME LEVEL, so blocks form a
-// wavefront.  One warp owns one block row of one (picture, reference) pair and walks it
-// left to right; before block b it waits until the row above has published b+1 finished
-// blocks (acquire/release on a per-row progress counter).  Rows are handed to warps in
-// launch order, so a row only ever waits on a warp that is already resident.  Many pairs
-// run side by side in one launch to fill the machine.  Inside a block the 32 lanes split
-// the candidate SADs by pixel and the (2r+1)^2 scan positions by position; byte SADs use
-// __vsadu4, reductions use warp shuffles.
+// wavefront.  One CTA (2-16 warps) owns one block row of one (picture, reference) pair and
+// walks it left to right; a finished block publishes its vector as one relaxed 64-bit word
+// and the row below polls the two words it needs.  Rows are CTAs in launch order, so a row
+// only ever waits on a CTA that is already resident.  Many pairs run side by side in one
+// launch to fill the machine.  Inside a block three lanes per candidate compute the ranking
+// SADs, the threads split the (2r+1)^2 scan positions; byte SADs use __vsadu4, reductions
+// use REDUX / warp shuffles.
 
 #include "common.cuh"
 #include <climits>
@@ -186,17 +186,8 @@ struct StaticCands {
 
 struct Win { int xmin, ymin, scan_w, scan_h, seed_a, seed_b; };
 
-// a speculative scan: the search result for seed (dx, dy), prepared one block ahead
-struct SpecScan {
-  int valid, dx, dy;
-  Win win;
-  unsigned long long key;
-  unsigned luma, chroma;
-};
-
 struct BlockShared {
   StaticCands stc[2];
-  SpecScan spec[2];
   Win win;
   int last_dx, last_dy;             // this row's previous block (the "left" candidate)
   unsigned long long key[16];
@@ -208,18 +199,16 @@ struct BlockShared {
 // Per block the dependent chain is: neighbour vectors (poll) -> rank candidates -> scan around
 // the winner -> publish.  Everything that does not depend on the neighbours runs one block
 // ahead on warp 1: the static candidates (zero + five parents) with their ranking SADs.
-// SPEC additionally lets warp 1 scan speculatively around the best static candidate, so that a
-// ranking that picks the same seed finds its scan done.  Measured on the 2160p bench (noisy
-// panning content, B200): level 0 4.4 ms with SPEC vs 3.6 ms without -- warp 1 becomes the
-// longer loop and misses pay a single-warp scan -- so it is compiled out; kept because it
-// wins when vectors are coherent (hit rate near 1) and the chain is poll -> rank -> publish.
+// (Letting warp 1 also scan speculatively around the best static candidate was measured slower
+// -- 4.4 vs 3.6 ms at level 0: warp 1 becomes the longer loop -- and removed)
 // 64 registers per thread (85 for the two-warp variant, measured best at 32 pictures per launch):
 // a row's CTA mostly waits, so its footprint in the register file decides how many rows /
 // pictures / other kernels an SM can host, while too tight a cap makes the compiler recompute
+// addresses it could have kept.
 #ifndef SB2_HBM_THREADS_PER_SM
 #define SB2_HBM_THREADS_PER_SM 1024
 #endif
-template <int NW, bool SPEC = false>
+template <int NW>
 __global__ void __launch_bounds__ (32 * NW, NW == 2 ? 12 : SB2_HBM_THREADS_PER_SM / (32 * NW))
 hbm_level_kernel (const HbmArgs A)
 {
@@ -244,7 +233,7 @@ hbm_level_kernel (const HbmArgs A)
   const MotionVector *pf = A.parent ? A.parent + (size_t) pic * A.field_pitch : nullptr;
   unsigned long long *words_me = A.words + ((size_t) pic * A.rows + row) * A.cols;
   const unsigned long long *words_up = row > 0 ? words_me - A.cols : nullptr;
-  if (threadIdx.x == 0) { sh.last_dx = 0; sh.last_dy = 0; sh.spec[0].valid = 0; sh.spec[1].valid = 0; }
+  if (threadIdx.x == 0) { sh.last_dx = 0; sh.last_dy = 0; }
   const int hint_mask = ~((1 << (s + 1)) - 1);
   const int y0 = (j * A.bh) >> s;
   const int bh0 = min (A.height - y0, A.bh);
@@ -384,13 +373,11 @@ hbm_level_kernel (const HbmArgs A)
   };
 
   // static candidates of block `nb` (0: zero, 1..5: parents (0,0) (-1,0) (1,0) (0,-1) (0,1),
-  // schrohierbm.c:259-277) and their ranking SADs into sh.stc[nb & 1]; with SPEC also the scan
-  // around the best of them into sh.spec[nb & 1].  Executed by one whole warp.
+  // schrohierbm.c:259-277) and their ranking SADs into sh.stc[nb & 1].  Executed by one whole warp.
   auto do_static = [&] (int nb) {
     const int i = nb * skip;
     const int x0 = (i * A.bw) >> s;
-    SpecScan &spc = sh.spec[nb & 1];
-    if (!(x0 < A.width && y0 < A.height)) { if (lane == 0) spc.valid = 0; return; }
+    if (!(x0 < A.width && y0 < A.height)) return;
     const int bw0 = min (A.width - x0, A.bw);
     int cdx = 0, cdy = 0;
     bool valid = false;
@@ -418,21 +405,6 @@ hbm_level_kernel (const HbmArgs A)
     const unsigned vm = __ballot_sync (0xffffffffu, valid && lane < 6);
     if (lane < 6) { sc.dx[lane] = cdx; sc.dy[lane] = cdy; }
     if (lane == 0) { sc.valid = vm; sc.full = full; }
-    if (SPEC) {
-      // speculate that the best static candidate will also win the full ranking
-      unsigned key = 0xffffffffu;
-      if (full && ck < 6 && part == 0 && ((vm >> ck) & 1) && m < (unsigned) INT_MAX) key = (m << 8) | (unsigned) ck;
-      key = __reduce_min_sync (0xffffffffu, key);
-      if (key == 0xffffffffu) { if (lane == 0) spc.valid = 0; return; }
-      const int bk = (int) (key & 0xff);
-      int dx = __shfl_sync (0xffffffffu, cdx, bk) >> s, dy = __shfl_sync (0xffffffffu, cdy, bk) >> s;
-      clamp_seed (x0, bw0, dx, dy);
-      const Win wn = make_win (x0, bw0, dx, dy);
-      unsigned long long wkey;
-      unsigned wl, wc;
-      scan_part (x0, bw0, wn, lane, 32, wkey, wl, wc);
-      if (lane == 0) { spc.dx = dx; spc.dy = dy; spc.win = wn; spc.key = wkey; spc.luma = wl; spc.chroma = wc; spc.valid = 1; }
-    }
   };
 
   __syncthreads ();
@@ -547,42 +519,26 @@ hbm_level_kernel (const HbmArgs A)
       int dx = __shfl_sync (0xffffffffu, cdx, best_k) >> s;
       int dy = __shfl_sync (0xffffffffu, cdy, best_k) >> s;
       clamp_seed (x0, bw0, dx, dy);
-      if (SPEC) {
-        // the scan for this seed may already be there
-        const SpecScan &spc = sh.spec[bi & 1];
-        if (spc.valid && spc.dx == dx && spc.dy == dy) {
-          if (lane == 0) publish (bi, i, x0, spc.win, spc.key, spc.luma, spc.chroma);
-        } else {
-          const Win wn = make_win (x0, bw0, dx, dy);
-          unsigned long long wkey;
-          unsigned wl, wc;
-          scan_part (x0, bw0, wn, lane, 32, wkey, wl, wc);
-          if (lane == 0) publish (bi, i, x0, wn, wkey, wl, wc);
-        }
-      } else if (lane == 0) {
-        sh.win = make_win (x0, bw0, dx, dy);
-      }
+      if (lane == 0) sh.win = make_win (x0, bw0, dx, dy);
     }
-    if (!SPEC) {
+    __syncthreads ();
+    TRACE (4);
+    if (active) {
+      const Win wn = sh.win;
+      unsigned long long wkey;
+      unsigned wl, wc;
+      scan_part (x0, bw0, wn, threadIdx.x, 32 * NW, wkey, wl, wc);
+      TRACE (5);
+      if (lane == 0) { sh.key[warp] = wkey; sh.luma[warp] = wl; sh.chroma[warp] = wc; }
       __syncthreads ();
-      TRACE (4);
-      if (active) {
-        const Win wn = sh.win;
-        unsigned long long wkey;
-        unsigned wl, wc;
-        scan_part (x0, bw0, wn, threadIdx.x, 32 * NW, wkey, wl, wc);
-        TRACE (5);
-        if (lane == 0) { sh.key[warp] = wkey; sh.luma[warp] = wl; sh.chroma[warp] = wc; }
-        __syncthreads ();
-        if (threadIdx.x == 0) {
-          unsigned long long k = sh.key[0];
-          unsigned bl = sh.luma[0], bc = sh.chroma[0];
+      if (threadIdx.x == 0) {
+        unsigned long long k = sh.key[0];
+        unsigned bl = sh.luma[0], bc = sh.chroma[0];
 #pragma unroll
-          for (int w = 1; w < NW; w++)
-            if (sh.key[w] < k) { k = sh.key[w]; bl = sh.luma[w]; bc = sh.chroma[w]; }
-          TRACE (6);
-          publish (bi, i, x0, wn, k, bl, bc);
-        }
+        for (int w = 1; w < NW; w++)
+          if (sh.key[w] < k) { k = sh.key[w]; bl = sh.luma[w]; bc = sh.chroma[w]; }
+        TRACE (6);
+        publish (bi, i, x0, wn, k, bl, bc);
       }
     }
     if (!active && threadIdx.x == 0) {
