@@ -198,6 +198,22 @@ int sb2_sad_biref_u8 (const uint8_t *a, int a_stride, const uint8_t *src1, int s
     int weight1, const uint8_t *src2, int src2_stride, int weight2, int shift, int width,
     int height, int *sad, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Combine / convert glue between the stages.
+ * Depth codes: 0 = u8, 1 = s16, 2 = s32.  Planar slabs of equal component count.
+ *
+ * sb2_frame_convert: the planar, equal-chroma-format part of schro_frame_convert
+ *   (schroedinger/schroframe.c:870-978): depth conversion with the Orc programs' wrap and
+ *   saturation points (schroorc-dist.c: orc_offsetconvert_* / orc_convert_*), then crop or
+ *   edge extension (schrovirtframe.c:1824-1960): dst(x,y) = conv(src(min(x,sw-1), min(y,sh-1))).
+ * sb2_frame_add: schro_frame_add / schro_frame_subtract (schroedinger/schroframe.c:1012-1182):
+ *   dst (s16) +-= src (u8 or s16) over the common area of each component, 16-bit wrap.
+ * ---------------------------------------------------------------------- */
+int sb2_frame_convert (const sb2_slab *src, int src_depth, const sb2_slab *dst, int dst_depth,
+    void *stream);
+int sb2_frame_add (const sb2_slab *dst, const sb2_slab *src, int src_depth, int subtract,
+    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -309,6 +309,11 @@ void schro_frame_inverse_iwt_transform (SchroFrame *frame, SchroParams *params);
 
 /* ---- upsample / downsample / edge extension (schroedinger/schroframe.h:130-160) */
 void schro_frame_downsample (SchroFrame *dest, SchroFrame *src);
+/* schroedinger/schroframe.h:129-131 (schroframe.c:870, 1012, 1062): planar frames of equal chroma
+ * format; packed formats and chroma resampling abort with a message */
+void schro_frame_convert (SchroFrame *dest, SchroFrame *src);
+void schro_frame_add (SchroFrame *dest, SchroFrame *src);
+void schro_frame_subtract (SchroFrame *dest, SchroFrame *src);
 void schro_frame_upsample_horiz (SchroFrameData *dest, SchroFrameData *src);
 void schro_frame_upsample_vert (SchroFrameData *dest, SchroFrameData *src);
 void schro_frame_mc_edgeextend (SchroFrame *frame);

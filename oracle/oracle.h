@@ -125,4 +125,18 @@ void oracle_hbm_scan_hint (const OraclePyrLevel *src, const OraclePyrLevel *ref,
 #ifdef __cplusplus
 }
 #endif
+
+/* ---- combine / convert glue --------------------------------------
+ * depth: 0 u8, 1 s16, 2 s32.  One plane at a time.
+ * oracle_convert_plane: schro_frame_convert for planar frames of equal chroma format
+ *   (schroedinger/schroframe.c:870-978): depth conversion with Orc's semantics
+ *   (schroedinger/schroorc.orc:476-549), then crop or edge extension
+ *   (schroedinger/schrovirtframe.c:1824-1960): dest(x,y) = conv(src(min(x,sw-1), min(y,sh-1))).
+ * oracle_add_plane: schro_frame_add / schro_frame_subtract (schroedinger/schroframe.c:1012-1182):
+ *   dest (s16) +-= src (s16 or u8) over the common area, 16-bit wrap. */
+void oracle_convert_plane (void *dst, int dstride, int ddepth, int dwidth, int dheight,
+    const void *src, int sstride, int sdepth, int swidth, int sheight);
+void oracle_add_plane (int16_t *dst, int dstride, int dwidth, int dheight,
+    const void *src, int sstride, int sdepth, int swidth, int sheight, int subtract);
+
 #endif

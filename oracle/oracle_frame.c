@@ -138,3 +138,72 @@ oracle_downsample (uint8_t *dest, int dstride, int dwidth, int dheight,
   }
   free (tmp);
 }
+
+/* ---- combine / convert glue ------------------------------------------------------------ */
+static int
+load_sample (const void *row, int depth, int x)
+{
+  if (depth == 0) return ((const uint8_t *) row)[x];
+  if (depth == 1) return ((const int16_t *) row)[x];
+  return ((const int32_t *) row)[x];
+}
+
+/* one sample through the reference's converter chain (schroframe.c:905-925 picks the pair) */
+static int
+convert_sample (int v, int sdepth, int ddepth)
+{
+  if (sdepth == ddepth) return v;
+  if (ddepth == 0) {
+    int t;
+    if (sdepth == 1) {
+      t = (int16_t) (v + 128);                                   /* addw wraps (schroorc.orc:504-511) */
+    } else {
+      /* the shipped program (schroorc-dist.c:4274-4306, what the library runs) is addl, convsuslw,
+       * convsuswb: the sum wraps at 32 bits, saturates to 0..65535, and that word is then read as
+       * SIGNED by the byte narrowing -- so 32768..65535 come out as 0, not 255.  (schroorc.orc:513-521
+       * says convssslw; the generated file is the authority.) */
+      int32_t w = (int32_t) ((uint32_t) v + 128u);
+      t = (int16_t) (w < 0 ? 0 : w > 65535 ? 65535 : w);
+    }
+    return t < 0 ? 0 : t > 255 ? 255 : t;                        /* convsuswb */
+  }
+  if (ddepth == 1) {
+    if (sdepth == 0) return v - 128;                             /* convubw, subw (:524-531) */
+    return (int16_t) v;                                          /* convlw truncates (:483-487) */
+  }
+  if (sdepth == 0) return v - 128;                               /* convubw, subw, convswl (:533-540) */
+  return v;                                                      /* convswl (:497-501) */
+}
+
+void
+oracle_convert_plane (void *dst, int dstride, int ddepth, int dwidth, int dheight,
+    const void *src, int sstride, int sdepth, int swidth, int sheight)
+{
+  int x, y;
+  for (y = 0; y < dheight; y++) {
+    const uint8_t *srow = (const uint8_t *) src + (ptrdiff_t) (y < sheight ? y : sheight - 1) * sstride;
+    uint8_t *drow = (uint8_t *) dst + (ptrdiff_t) y * dstride;
+    for (x = 0; x < dwidth; x++) {
+      const int v = convert_sample (load_sample (srow, sdepth, x < swidth ? x : swidth - 1), sdepth, ddepth);
+      if (ddepth == 0) drow[x] = (uint8_t) v;
+      else if (ddepth == 1) ((int16_t *) drow)[x] = (int16_t) v;
+      else ((int32_t *) drow)[x] = v;
+    }
+  }
+}
+
+void
+oracle_add_plane (int16_t *dst, int dstride, int dwidth, int dheight,
+    const void *src, int sstride, int sdepth, int swidth, int sheight, int subtract)
+{
+  const int w = dwidth < swidth ? dwidth : swidth, h = dheight < sheight ? dheight : sheight;
+  int x, y;
+  for (y = 0; y < h; y++) {
+    const uint8_t *srow = (const uint8_t *) src + (ptrdiff_t) y * sstride;
+    int16_t *drow = (int16_t *) ((uint8_t *) dst + (ptrdiff_t) y * dstride);
+    for (x = 0; x < w; x++) {
+      const int v = load_sample (srow, sdepth, x);
+      drow[x] = (int16_t) (subtract ? drow[x] - v : drow[x] + v);   /* addw / subw wrap */
+    }
+  }
+}

@@ -23,6 +23,9 @@ ref_init (void)
 {
   if (!ref_inited) {
     schro_init ();
+    /* the reference creates its frame mutex in the first schro_frame_new (schroframe.c:36);
+     * the frames built on the stack below never go through it */
+    schro_frame_unref (schro_frame_new ());
     ref_inited = 1;
   }
 }
@@ -357,4 +360,39 @@ ref_sad_u8 (const uint8_t *a, int a_stride, const uint8_t *b, int b_stride, int 
 {
   ref_init ();
   return (uint32_t) schro_metric_absdiff_u8 ((uint8_t *) a, a_stride, (uint8_t *) b, b_stride, width, height);
+}
+
+/* ---- combine / convert glue --------------------------------------
+ * depth: 0 u8, 1 s16, 2 s32; 4:2:0 frames described by three planes each. */
+static SchroFrameFormat
+fmt420 (int depth)
+{
+  return depth == 0 ? SCHRO_FRAME_FORMAT_U8_420 : depth == 1 ? SCHRO_FRAME_FORMAT_S16_420
+      : SCHRO_FRAME_FORMAT_S32_420;
+}
+
+/* schro_frame_convert (schroedinger/schroframe.c:870) */
+void
+ref_frame_convert (void **dst, const int *dstride, int ddepth, int dwidth, int dheight,
+    void **src, const int *sstride, int sdepth, int swidth, int sheight)
+{
+  SchroFrame d, s;
+  ref_init ();
+  fake_frame3 (&d, fmt420 (ddepth), dst, dstride, dwidth, dheight, 0, 0);
+  fake_frame3 (&s, fmt420 (sdepth), src, sstride, swidth, sheight, 0, 0);
+  s.refcount = 1000;                 /* schro_frame_convert refs / unrefs its source */
+  schro_frame_convert (&d, &s);
+}
+
+/* schro_frame_add / schro_frame_subtract (schroedinger/schroframe.c:1012, 1062) */
+void
+ref_frame_add (void **dst, const int *dstride, int dwidth, int dheight,
+    void **src, const int *sstride, int sdepth, int swidth, int sheight, int subtract)
+{
+  SchroFrame d, s;
+  ref_init ();
+  fake_frame3 (&d, fmt420 (1), dst, dstride, dwidth, dheight, 0, 0);
+  fake_frame3 (&s, fmt420 (sdepth), src, sstride, swidth, sheight, 0, 0);
+  if (subtract) schro_frame_subtract (&d, &s);
+  else schro_frame_add (&d, &s);
 }

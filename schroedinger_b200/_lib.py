@@ -59,6 +59,8 @@ _opt("sb2_mc_edgeextend", ctypes.c_int, [_SP, ctypes.c_int, ctypes.c_int, ctypes
 _opt("sb2_upsample", ctypes.c_int, [_SP, ctypes.c_int, ctypes.c_void_p])
 _opt("sb2_downsample", ctypes.c_int, [_SP, _SP, ctypes.c_void_p])
 _opt("sb2_downsample_edgeextend", ctypes.c_int, [_SP, _SP, ctypes.c_int, ctypes.c_void_p])
+_opt("sb2_frame_convert", ctypes.c_int, [_SP, ctypes.c_int, _SP, ctypes.c_int, ctypes.c_void_p])
+_opt("sb2_frame_add", ctypes.c_int, [_SP, _SP, ctypes.c_int, ctypes.c_int, ctypes.c_void_p])
 _opt("sb2_edgeextend_upsample", ctypes.c_int, [_SP, ctypes.c_int, ctypes.c_void_p])
 _opt("sb2_obmc_render", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, _SP, _SP, _SP,
                                       _SP, ctypes.c_int, ctypes.c_int, _SP, ctypes.c_void_p])

@@ -150,6 +150,9 @@ _proto("schro_wavelet_inverse_transform_2d", None, [FrameDataP, FrameDataP, ctyp
 _proto("schro_frame_iwt_transform", None, [FrameP, ParamsP])
 _proto("schro_frame_inverse_iwt_transform", None, [FrameP, ParamsP])
 _proto("schro_frame_downsample", None, [FrameP, FrameP])
+_proto("schro_frame_convert", None, [FrameP, FrameP])
+_proto("schro_frame_add", None, [FrameP, FrameP])
+_proto("schro_frame_subtract", None, [FrameP, FrameP])
 _proto("schro_frame_upsample_horiz", None, [FrameDataP, FrameDataP])
 _proto("schro_frame_upsample_vert", None, [FrameDataP, FrameDataP])
 _proto("schro_frame_mc_edgeextend", None, [FrameP])

@@ -224,6 +224,24 @@ def downsample_edgeextend(src, dst, stream=None):
           "sb2_downsample_edgeextend")
 
 
+_DEPTH_CODE = {"u8": 0, "s16": 1, "s32": 2}
+
+
+def frame_convert(src, dst, stream=None):
+    """schro_frame_convert for planar slabs of equal chroma format: depth conversion (+-128 offset,
+    Orc's wrap / saturation points) with crop or edge extension to dst's size."""
+    require_cuda()
+    check(lib.sb2_frame_convert(ctypes.byref(src.slab), _DEPTH_CODE[src.layout.depth], ctypes.byref(dst.slab),
+                                _DEPTH_CODE[dst.layout.depth], _stream_ptr(stream)), "sb2_frame_convert")
+
+
+def frame_add(dst, src, subtract=False, stream=None):
+    """schro_frame_add / schro_frame_subtract: dst (s16) +-= src (u8 or s16) over the common area."""
+    require_cuda()
+    check(lib.sb2_frame_add(ctypes.byref(dst.slab), ctypes.byref(src.slab), _DEPTH_CODE[src.layout.depth],
+                            int(bool(subtract)), _stream_ptr(stream)), "sb2_frame_add")
+
+
 def downsample(src, dst, stream=None):
     """schro_frame_downsample: dst = half-size src (per component)."""
     require_cuda()

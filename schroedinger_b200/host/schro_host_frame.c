@@ -191,6 +191,71 @@ schro_frame_downsample (SchroFrame *dest, SchroFrame *src)
   }
 }
 
+/* ---- combine / convert glue (schroframe.c:870-1182) --------------------------- */
+static int
+depth_code (SchroFrameFormat format, const char *who)
+{
+  if (format & 0x100) sb2h_fatal (who, "packed formats are outside the picture core (format 0x%x)", (unsigned) format);
+  switch (SCHRO_FRAME_FORMAT_DEPTH (format)) {
+    case SCHRO_FRAME_FORMAT_DEPTH_U8: return 0;
+    case SCHRO_FRAME_FORMAT_DEPTH_S16: return 1;
+    default: return 2;
+  }
+}
+
+void
+schro_frame_convert (SchroFrame *dest, SchroFrame *src)
+{
+  Sb2hContext *cx = sb2h_context ();
+  Staged s, d;
+  const int sd = depth_code (src->format, __func__), dd = depth_code (dest->format, __func__);
+  SB2H_ASSERT (dest != NULL && src != NULL);
+  if ((dest->format & 3) != (src->format & 3))
+    sb2h_fatal (__func__, "chroma resampling is outside the picture core (formats 0x%x -> 0x%x)",
+        (unsigned) src->format, (unsigned) dest->format);
+  stage_in (cx, &s, src, SB2H_BUF_IN, 1);
+  stage_in (cx, &d, dest, SB2H_BUF_OUT, 1);      /* keep dest's borders as they are */
+  SB2H_CHECK (sb2_frame_convert (&s.slab, sd, &d.slab, dd, cx->stream), "sb2_frame_convert");
+  stage_out (cx, &d);
+  {
+    Staged *st[2] = { &s, &d };
+    stage_finish (cx, st, 2, 2u);
+  }
+}
+
+static void
+frame_add_sub (SchroFrame *dest, SchroFrame *src, int subtract, const char *who)
+{
+  Sb2hContext *cx = sb2h_context ();
+  Staged s, d;
+  const int sd = depth_code (src->format, who);
+  SB2H_ASSERT (dest != NULL && src != NULL);
+  /* the reference's tables (schroframe.c:984-1047): s16 += s16 | u8, same chroma format */
+  if (depth_code (dest->format, who) != 1 || sd > 1 || (dest->format & 3) != (src->format & 3))
+    sb2h_fatal (who, "%s function unimplemented (formats 0x%x, 0x%x)", subtract ? "subtract" : "add",
+        (unsigned) dest->format, (unsigned) src->format);
+  stage_in (cx, &s, src, SB2H_BUF_IN, 1);
+  stage_in (cx, &d, dest, SB2H_BUF_OUT, 1);
+  SB2H_CHECK (sb2_frame_add (&d.slab, &s.slab, sd, subtract, cx->stream), "sb2_frame_add");
+  stage_out (cx, &d);
+  {
+    Staged *st[2] = { &s, &d };
+    stage_finish (cx, st, 2, 2u);
+  }
+}
+
+void
+schro_frame_add (SchroFrame *dest, SchroFrame *src)
+{
+  frame_add_sub (dest, src, 0, __func__);
+}
+
+void
+schro_frame_subtract (SchroFrame *dest, SchroFrame *src)
+{
+  frame_add_sub (dest, src, 1, __func__);
+}
+
 /* ---- OBMC ------------------------------------------------------------------ */
 SchroMotion *
 schro_motion_new (SchroParams *params, SchroFrame *ref1, SchroFrame *ref2)

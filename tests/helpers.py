@@ -403,3 +403,71 @@ def ref_hbm(ref, src_planes, ref_planes, width, height, xbsep=8, ybsep=8, levels
        fields.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nx), ctypes.byref(ny), ptrs)
     assert (nx.value, ny.value) == (nbx, nby)
     return fields, pyr
+
+
+# ---- combine / convert glue --------------------------------------------
+DEPTH_DTYPE = {0: np.uint8, 1: np.int16, 2: np.int32}
+
+
+def chroma_size(w, h):
+    return (w + 1) // 2, (h + 1) // 2
+
+
+def random_planes(rng, depth, w, h, full_range=True):
+    """Three 4:2:0 planes of the given depth; full_range exercises every wrap / saturation point."""
+    cw, ch = chroma_size(w, h)
+    out = []
+    for (pw, ph) in ((w, h), (cw, ch), (cw, ch)):
+        if depth == 0:
+            a = rng.integers(0, 256, size=(ph, pw))
+        elif depth == 1:
+            a = rng.integers(-32768, 32768, size=(ph, pw)) if full_range else rng.integers(-600, 600, size=(ph, pw))
+        else:
+            a = rng.integers(-2 ** 31, 2 ** 31, size=(ph, pw)) if full_range else rng.integers(-70000, 70000, size=(ph, pw))
+            a[::3, ::5] = rng.integers(-400, 400, size=a[::3, ::5].shape)      # values near the u8 range too
+        out.append(np.ascontiguousarray(a.astype(DEPTH_DTYPE[depth])))
+    return out
+
+
+def oracle_convert(lib, src_planes, sdepth, sw, sh, ddepth, dw, dh):
+    lib.oracle_convert_plane.restype = None
+    cw, ch = chroma_size(dw, dh)
+    scw, sch = chroma_size(sw, sh)
+    out = []
+    for k, (pw, ph, spw, sph) in enumerate(((dw, dh, sw, sh), (cw, ch, scw, sch), (cw, ch, scw, sch))):
+        d = np.zeros((ph, pw), DEPTH_DTYPE[ddepth])
+        s = src_planes[k]
+        lib.oracle_convert_plane(_vp(d), ctypes.c_int(d.strides[0]), ddepth, pw, ph,
+                                 _vp(s), ctypes.c_int(s.strides[0]), sdepth, spw, sph)
+        out.append(d)
+    return out
+
+
+def ref_convert(lib, src_planes, sdepth, sw, sh, ddepth, dw, dh):
+    lib.ref_frame_convert.restype = None
+    cw, ch = chroma_size(dw, dh)
+    dst = [np.zeros((dh, dw), DEPTH_DTYPE[ddepth]), np.zeros((ch, cw), DEPTH_DTYPE[ddepth]),
+           np.zeros((ch, cw), DEPTH_DTYPE[ddepth])]
+    P3, I3 = ctypes.c_void_p * 3, ctypes.c_int * 3
+    lib.ref_frame_convert(P3(*[a.ctypes.data for a in dst]), I3(*[a.strides[0] for a in dst]), ddepth, dw, dh,
+                          P3(*[a.ctypes.data for a in src_planes]), I3(*[a.strides[0] for a in src_planes]),
+                          sdepth, sw, sh)
+    return dst
+
+
+def cpu_add(lib, prefix, dst_planes, dw, dh, src_planes, sdepth, sw, sh, subtract):
+    """{oracle_add_plane per plane, ref_frame_add per frame}: dst (s16) +-= src, in place on copies."""
+    dst = [a.copy() for a in dst_planes]
+    if prefix == "ref":
+        lib.ref_frame_add.restype = None
+        P3, I3 = ctypes.c_void_p * 3, ctypes.c_int * 3
+        lib.ref_frame_add(P3(*[a.ctypes.data for a in dst]), I3(*[a.strides[0] for a in dst]), dw, dh,
+                          P3(*[a.ctypes.data for a in src_planes]), I3(*[a.strides[0] for a in src_planes]),
+                          sdepth, sw, sh, int(subtract))
+        return dst
+    lib.oracle_add_plane.restype = None
+    for k in range(3):
+        d, s = dst[k], src_planes[k]
+        lib.oracle_add_plane(_vp(d), ctypes.c_int(d.strides[0]), d.shape[1], d.shape[0],
+                             _vp(s), ctypes.c_int(s.strides[0]), sdepth, s.shape[1], s.shape[0], int(subtract))
+    return dst

@@ -37,3 +37,28 @@ if __name__ == "__main__":
     run("Daub s32 2160p d1 inv", "s32", 6, 1, 3840, 2176, 8, True)
     run("Fidelity s16 1080p d4 inv", "s16", 5, 4, 1920, 1088, 64, True)
     run("Haar0 s16 1080p d4 inv", "s16", 3, 4, 1920, 1088, 64, True)
+
+
+def run_glue():
+    """combine / convert glue: bytes moved per second against the HBM peak"""
+    for (sd, dd, w, h, count) in (("s16", "u8", 1920, 1080, 64), ("s32", "u8", 3840, 2160, 16), ("u8", "s16", 1920, 1080, 64)):
+        a = dev.PictureSlab(dev.FrameLayout.yuv420(sd, w, h), count, zero=False)
+        b = dev.PictureSlab(dev.FrameLayout.yuv420(dd, w, h), count, zero=False)
+        a.buf.random_(0, 255)
+        for _ in range(3):
+            dev.frame_convert(a, b)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            dev.frame_convert(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        nbytes = w * h * 1.5 * (a.layout.bpp + b.layout.bpp) * count
+        print(f"convert {sd}->{dd} {w}x{h}       {count:4d} pics {ms:8.3f} ms  {count/ms*1e3:9.1f} pics/s  "
+              f"{nbytes/ms/1e6:8.1f} GB/s ({nbytes/ms/1e6/6545.9*100:5.1f}% of 6545.9)")
+
+
+if __name__ == "__main__":
+    run_glue()
