@@ -107,12 +107,41 @@ def hbm_golden(ref):
     print("hbm.npz:", len(out), "arrays")
 
 
+def glue_golden(ref):
+    """schro_frame_convert / schro_frame_add / schro_frame_subtract of the compiled reference."""
+    rng = np.random.default_rng(20261019)
+    out = {}
+    for sd, dd in ((0, 1), (0, 2), (1, 0), (2, 0), (1, 2), (2, 1)):
+        for (sw, sh), (dw, dh) in (((34, 22), (34, 22)), ((34, 22), (28, 18)), ((34, 22), (40, 24))):
+            src = helpers.random_planes(rng, sd, sw, sh, True)
+            if sd == 2:                       # keep the saturation thresholds of the narrowing in the fixture
+                src[0].flat[:8] = [-129, -128, 127, 128, 32639, 32640, 65407, 65408]
+            want = helpers.ref_convert(ref, src, sd, sw, sh, dd, dw, dh)
+            key = f"conv_{sd}{dd}_{sw}x{sh}_{dw}x{dh}"
+            for c in range(3):
+                out[f"{key}_in{c}"] = src[c]
+                out[f"{key}_out{c}"] = want[c]
+    for sd in (0, 1):
+        for sub in (0, 1):
+            for (sw, sh), (dw, dh) in (((34, 22), (34, 22)), ((30, 20), (34, 22)), ((34, 22), (30, 20))):
+                dst = helpers.random_planes(rng, 1, dw, dh, True)
+                src = helpers.random_planes(rng, sd, sw, sh, True)
+                want = helpers.cpu_add(ref, "ref", dst, dw, dh, src, sd, sw, sh, sub)
+                key = f"add_{sd}_{sub}_{sw}x{sh}_{dw}x{dh}"
+                for c in range(3):
+                    out[f"{key}_dst{c}"] = dst[c]
+                    out[f"{key}_src{c}"] = src[c]
+                    out[f"{key}_out{c}"] = want[c]
+    np.savez_compressed(os.path.join(helpers.GOLDEN_DIR, "glue.npz"), **out)
+    print("glue.npz:", len(out), "arrays")
+
+
 def main():
     ref = helpers.load_ref()
     if ref is None:
         raise SystemExit("oracle/_ref/libschro_ref.so missing: run `make ref` where /root/reference exists")
     wavelet_golden(ref)
-    for name in ("frame_golden", "motion_golden", "hbm_golden"):
+    for name in ("frame_golden", "motion_golden", "hbm_golden", "glue_golden"):
         fn = globals().get(name)
         if fn:
             fn(ref)

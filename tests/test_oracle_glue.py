@@ -55,3 +55,32 @@ def test_convert_known_answers():
     assert helpers.oracle_convert(ORACLE, u8, 0, 4, 1, 2, 6, 2)[0].tolist() == [[-128, -1, 0, 127, 127, 127]] * 2
     t = [np.array([[70000, -70000, 32768]], np.int32)] + [np.zeros((1, 2), np.int32)] * 2
     assert helpers.oracle_convert(ORACLE, t, 2, 3, 1, 1, 3, 1)[0][0].tolist() == [4464, -4464, -32768]   # convlw truncates
+
+
+def test_golden_fixtures():
+    """tests/golden/glue.npz: outputs of the compiled reference (made by tests/golden/make_golden.py),
+    readable where the reference itself is absent."""
+    import os
+    import re
+    g = np.load(os.path.join(helpers.GOLDEN_DIR, "glue.npz"))
+    nconv = nadd = 0
+    for key in sorted({k.rsplit("_", 1)[0] for k in g.files}):
+        m = re.match(r"conv_(\d)(\d)_(\d+)x(\d+)_(\d+)x(\d+)$", key)
+        if m:
+            sd, dd, sw, sh, dw, dh = map(int, m.groups())
+            src = [g[f"{key}_in{c}"] for c in range(3)]
+            got = helpers.oracle_convert(ORACLE, src, sd, sw, sh, dd, dw, dh)
+            for c in range(3):
+                assert np.array_equal(got[c], g[f"{key}_out{c}"]), (key, c)
+            nconv += 1
+            continue
+        m = re.match(r"add_(\d)_(\d)_(\d+)x(\d+)_(\d+)x(\d+)$", key)
+        if m:
+            sd, sub, sw, sh, dw, dh = map(int, m.groups())
+            dst = [g[f"{key}_dst{c}"] for c in range(3)]
+            src = [g[f"{key}_src{c}"] for c in range(3)]
+            got = helpers.cpu_add(ORACLE, "oracle", dst, dw, dh, src, sd, sw, sh, sub)
+            for c in range(3):
+                assert np.array_equal(got[c], g[f"{key}_out{c}"]), (key, c)
+            nadd += 1
+    assert nconv == 18 and nadd == 12, (nconv, nadd)
