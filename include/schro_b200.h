@@ -214,6 +214,28 @@ int sb2_frame_convert (const sb2_slab *src, int src_depth, const sb2_slab *dst, 
 int sb2_frame_add (const sb2_slab *dst, const sb2_slab *src, int src_depth, int subtract,
     void *stream);
 
+/* ------------------------------------------------------------------------
+ * Dequantisation of a coefficient frame in place: what
+ * schro_decoder_decode_subband applies codeblock by codeblock
+ * (schroedinger/schrodecoder.c:3395-3448, 3559-3576) with orc_dequantise_s16_ip_2d /
+ * _s32_ip_2d (schroedinger/schroorc.orc:1154-1168, 2148-2162), on the in-place subband layout
+ * (schroedinger/schroparams.c:319-352).
+ * quant (device): per picture `quant_picture_pitch` pairs apart; for every component, for band
+ * index 0..3*depth (schro_subband_get_position order), codeblock rows then columns: int32 pairs
+ * (quant_factor, quant_offset + 2) -- the values the decoder passes to the Orc kernel, e.g.
+ * schro_table_quant[i], schro_table_offset_1_2[i] + 2.  sb2_dequant_table_pairs = pairs per picture.
+ * horiz/vert_codeblocks: [0] for the LL band, [i + 1] for the bands of level i (SchroParams).
+ * ---------------------------------------------------------------------- */
+#define SB2_DEQUANT_MAX_LEVELS 6
+typedef struct {
+  int transform_depth;
+  int horiz_codeblocks[SB2_DEQUANT_MAX_LEVELS + 1];
+  int vert_codeblocks[SB2_DEQUANT_MAX_LEVELS + 1];
+} sb2_dequant_params;
+size_t sb2_dequant_table_pairs (const sb2_dequant_params *p, int ncomp);
+int sb2_dequantise (const sb2_slab *coeffs, int is_s32, const sb2_dequant_params *p,
+    const int32_t *quant, size_t quant_picture_pitch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -304,6 +304,10 @@ void schro_wavelet_inverse_transform_2d (SchroFrameData *fd_dest,
 /* frame-granular drivers: schroedinger/schroframe.c:1192 and the decoder's
  * schro_decoder_inverse_iwt_transform (schroedinger/schrodecoder.c:1809), named as
  * the reference's own testsuite/cuda/cuda.c:96 calls it */
+/* new: dequantise a frame of quantised coefficients in place on the GPU;
+ * pairs = (quant_factor, quant_offset + 2) per codeblock, see sb2_dequantise in schro_b200.h.
+ * Replaces the orc_dequantise_* calls of schro_decoder_decode_subband (schrodecoder.c:3395-3448). */
+void schro_b200_frame_dequantise (SchroFrame *frame, SchroParams *params, const int32_t *pairs);
 void schro_frame_iwt_transform (SchroFrame *frame, SchroParams *params);
 void schro_frame_inverse_iwt_transform (SchroFrame *frame, SchroParams *params);
 

@@ -139,4 +139,14 @@ void oracle_convert_plane (void *dst, int dstride, int ddepth, int dwidth, int d
 void oracle_add_plane (int16_t *dst, int dstride, int dwidth, int dheight,
     const void *src, int sstride, int sdepth, int swidth, int sheight, int subtract);
 
+
+/* ---- dequantisation of a coefficient frame in place ----------------
+ * What the decoder does per codeblock (schroedinger/schrodecoder.c:3395-3448) with
+ * orc_dequantise_s16_ip_2d / _s32_ip_2d (schroedinger/schroorc.orc:1154-1168, 2148-2162), for one
+ * component plane in the in-place subband layout (schro_subband_get_frame_data,
+ * schroedinger/schroparams.c:319-352).  quant: for band index 0..3*depth (schro_subband_get_position),
+ * then codeblock row, then codeblock column: (quant_factor, quant_offset + 2) pairs.
+ * hcb / vcb: codeblocks per band, [0] for the LL band, [i + 1] for the bands of level i. */
+void oracle_dequantise_plane (void *data, int stride, int width, int height, int is_s32,
+    int transform_depth, const int *hcb, const int *vcb, const int32_t *quant);
 #endif

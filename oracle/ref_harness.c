@@ -396,3 +396,65 @@ ref_frame_add (void **dst, const int *dstride, int dwidth, int dheight,
   if (subtract) schro_frame_subtract (&d, &s);
   else schro_frame_add (&d, &s);
 }
+
+/* ---- dequantisation: the reference's own subband geometry
+ * (schro_subband_get_frame_data, schro_subband_get_position) and Orc kernels, driven codeblock by
+ * codeblock the way schro_decoder_decode_subband does (schrodecoder.c:3559-3576, 3395-3448). */
+#include <schroedinger/schroorc.h>
+void
+ref_dequantise_plane (void *data, int stride, int width, int height, int is_s32,
+    int transform_depth, const int *hcb, const int *vcb, const int32_t *quant)
+{
+  SchroFrame f;
+  SchroParams params;
+  void *planes[3];
+  int strides[3], index;
+  ref_init ();
+  memset (&params, 0, sizeof (params));
+  params.transform_depth = transform_depth;
+  params.iwt_luma_width = width;
+  params.iwt_luma_height = height;
+  planes[0] = planes[1] = planes[2] = data;
+  strides[0] = strides[1] = strides[2] = stride;
+  fake_frame3 (&f, is_s32 ? SCHRO_FRAME_FORMAT_S32_444 : SCHRO_FRAME_FORMAT_S16_444, planes, strides, width, height, 0, 0);
+  for (index = 0; index <= 3 * transform_depth; index++) {
+    const int position = schro_subband_get_position (index);
+    const int nh = position == 0 ? hcb[0] : hcb[SCHRO_SUBBAND_SHIFT (position) + 1];
+    const int nv = position == 0 ? vcb[0] : vcb[SCHRO_SUBBAND_SHIFT (position) + 1];
+    SchroFrameData fd;
+    int x, y;
+    schro_subband_get_frame_data (&fd, &f, 0, position, &params);
+    for (y = 0; y < nv; y++) {
+      const int ymin = (fd.height * y) / nv, ymax = (fd.height * (y + 1)) / nv;
+      int xmin = 0, acc = 0;
+      const int cbw = fd.width / nh, inc = fd.width - nh * cbw;
+      for (x = 0; x < nh; x++) {
+        const int x0 = xmin;
+        xmin += cbw;
+        acc += inc;
+        if (acc >= nh) { acc -= nh; xmin++; }
+        if (xmin > x0 && ymax > ymin) {
+          if (is_s32)
+            orc_dequantise_s32_ip_2d (SCHRO_FRAME_DATA_GET_PIXEL_S32 (&fd, x0, ymin), fd.stride, quant[0], quant[1],
+                xmin - x0, ymax - ymin);
+          else
+            orc_dequantise_s16_ip_2d (SCHRO_FRAME_DATA_GET_PIXEL_S16 (&fd, x0, ymin), fd.stride, quant[0], quant[1],
+                xmin - x0, ymax - ymin);
+        }
+        quant += 2;
+      }
+    }
+  }
+}
+
+/* the reference's quantiser tables (schroedinger/schrotables.c): 61 entries each */
+void
+ref_quant_tables (uint32_t *factor, uint32_t *offset_intra, uint32_t *offset_inter)
+{
+  int i;
+  for (i = 0; i < 61; i++) {
+    factor[i] = schro_table_quant[i];
+    offset_intra[i] = schro_table_offset_1_2[i];
+    offset_inter[i] = schro_table_offset_3_8[i];
+  }
+}

@@ -61,6 +61,16 @@ _opt("sb2_downsample", ctypes.c_int, [_SP, _SP, ctypes.c_void_p])
 _opt("sb2_downsample_edgeextend", ctypes.c_int, [_SP, _SP, ctypes.c_int, ctypes.c_void_p])
 _opt("sb2_frame_convert", ctypes.c_int, [_SP, ctypes.c_int, _SP, ctypes.c_int, ctypes.c_void_p])
 _opt("sb2_frame_add", ctypes.c_int, [_SP, _SP, ctypes.c_int, ctypes.c_int, ctypes.c_void_p])
+
+
+class DequantParams(ctypes.Structure):
+    _fields_ = [("transform_depth", ctypes.c_int), ("horiz_codeblocks", ctypes.c_int * 7),
+                ("vert_codeblocks", ctypes.c_int * 7)]
+
+
+_opt("sb2_dequant_table_pairs", ctypes.c_size_t, [ctypes.POINTER(DequantParams), ctypes.c_int])
+_opt("sb2_dequantise", ctypes.c_int, [_SP, ctypes.c_int, ctypes.POINTER(DequantParams), ctypes.c_void_p,
+                                      ctypes.c_size_t, ctypes.c_void_p])
 _opt("sb2_edgeextend_upsample", ctypes.c_int, [_SP, ctypes.c_int, ctypes.c_void_p])
 _opt("sb2_obmc_render", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, _SP, _SP, _SP,
                                       _SP, ctypes.c_int, ctypes.c_int, _SP, ctypes.c_void_p])

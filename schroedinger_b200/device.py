@@ -242,6 +242,23 @@ def frame_add(dst, src, subtract=False, stream=None):
                             int(bool(subtract)), _stream_ptr(stream)), "sb2_frame_add")
 
 
+def dequantise(coeffs, depth, horiz_codeblocks, vert_codeblocks, quant, stream=None):
+    """Dequantise a coefficient slab in place.  quant: int32 CUDA tensor, per picture
+    sb2_dequant_table_pairs() (factor, offset + 2) pairs (see include/schro_b200.h)."""
+    from ._lib import DequantParams
+    require_cuda()
+    p = DequantParams()
+    p.transform_depth = depth
+    for i in range(7):
+        p.horiz_codeblocks[i] = horiz_codeblocks[i] if i < len(horiz_codeblocks) else 1
+        p.vert_codeblocks[i] = vert_codeblocks[i] if i < len(vert_codeblocks) else 1
+    pairs = lib.sb2_dequant_table_pairs(ctypes.byref(p), len(coeffs.layout.comp_sizes))
+    assert quant.dtype == torch.int32 and quant.numel() == 2 * pairs * coeffs.count, (quant.numel(), pairs)
+    check(lib.sb2_dequantise(ctypes.byref(coeffs.slab), 1 if coeffs.layout.depth == "s32" else 0, ctypes.byref(p),
+                             ctypes.c_void_p(quant.data_ptr()), ctypes.c_size_t(pairs), _stream_ptr(stream)),
+          "sb2_dequantise")
+
+
 def downsample(src, dst, stream=None):
     """schro_frame_downsample: dst = half-size src (per component)."""
     require_cuda()

@@ -233,3 +233,65 @@ schro_frame_inverse_iwt_transform (SchroFrame *frame, SchroParams *params)
 {
   frame_iwt (frame, params, 1);
 }
+
+/* ---- dequantisation on the device -------------------------------
+ * New entry point (the reference dequantises inside its entropy decoder, codeblock by codeblock:
+ * schrodecoder.c:3395-3448): the frame holds the QUANTISED coefficients in the in-place subband
+ * layout, `pairs` the (quant_factor, quant_offset + 2) of every codeblock in the order
+ * component, band index, codeblock row, codeblock column (include/schro_b200.h). */
+void
+schro_b200_frame_dequantise (SchroFrame *frame, SchroParams *params, const int32_t *pairs)
+{
+  Sb2hContext *cx = sb2h_context ();
+  const int is_s32 = depth_is_s32 (frame->format);
+  const int bpp = is_s32 ? 4 : 2;
+  sb2_dequant_params p;
+  sb2_slab slab;
+  size_t npairs, total = 0;
+  char *region = frame->regions[0], *dev_region;
+  void *dpairs;
+  int k, host;
+
+  SB2H_ASSERT (frame && params && pairs && region);
+  memset (&p, 0, sizeof (p));
+  p.transform_depth = params->transform_depth;
+  if (p.transform_depth < 1 || p.transform_depth > SB2_DEQUANT_MAX_LEVELS)
+    sb2h_fatal (__func__, "transform depth %d", p.transform_depth);
+  for (k = 0; k <= SB2_DEQUANT_MAX_LEVELS; k++) {
+    p.horiz_codeblocks[k] = k <= p.transform_depth && params->horiz_codeblocks[k] > 0 ? params->horiz_codeblocks[k] : 1;
+    p.vert_codeblocks[k] = k <= p.transform_depth && params->vert_codeblocks[k] > 0 ? params->vert_codeblocks[k] : 1;
+  }
+  npairs = sb2_dequant_table_pairs (&p, 3);
+  for (k = 0; k < 3; k++) total += (size_t) frame->components[k].length;
+  host = sb2h_mem_kind (region) != SB2H_MEM_DEVICE;
+  if (host) {
+    dev_region = sb2h_dev_buffer (cx, SB2H_BUF_IN, total + 256);
+    SB2H_CUDA (cudaMemcpyAsync (dev_region, region, total, cudaMemcpyDefault, cx->stream));
+  } else {
+    dev_region = region;
+    sb2h_frame_use (cx, region);
+  }
+  memset (&slab, 0, sizeof (slab));
+  slab.base = dev_region;
+  slab.picture_pitch = total;
+  slab.count = 1;
+  slab.ncomp = 3;
+  for (k = 0; k < 3; k++) {
+    slab.offset[k] = (size_t) ((char *) frame->components[k].data - region);
+    slab.stride[k] = frame->components[k].stride;
+    slab.width[k] = k ? params->iwt_chroma_width : params->iwt_luma_width;
+    slab.height[k] = k ? params->iwt_chroma_height : params->iwt_luma_height;
+  }
+  (void) bpp;
+  dpairs = sb2h_dev_buffer (cx, SB2H_BUF_AUX0, npairs * 2 * sizeof (int32_t));
+  SB2H_CUDA (cudaMemcpyAsync (dpairs, pairs, npairs * 2 * sizeof (int32_t), cudaMemcpyDefault, cx->stream));
+  SB2H_CHECK (sb2_dequantise (&slab, is_s32, &p, dpairs, npairs, cx->stream), "sb2_dequantise");
+  if (host) {
+    SB2H_CUDA (cudaMemcpyAsync (region, dev_region, total, cudaMemcpyDefault, cx->stream));
+    sb2h_sync (cx);
+  } else if (sb2h_mem_kind (pairs) != SB2H_MEM_PAGEABLE) {
+    sb2h_sync (cx);        /* a page-locked table is read by the DMA engine after the copy call returns */
+  } else {
+    sb2h_frame_wrote (cx, region);
+  }
+}

@@ -136,12 +136,32 @@ def glue_golden(ref):
     print("glue.npz:", len(out), "arrays")
 
 
+def dequant_golden(ref):
+    """orc_dequantise_s16_ip_2d / _s32_ip_2d over the reference's subband / codeblock geometry."""
+    from tests.test_oracle_dequant import CASES, make_case
+    rng = np.random.default_rng(20261020)
+    tables = helpers.ref_quant_tables(ref)
+    out = {"table_quant": tables[0], "table_offset_1_2": tables[1], "table_offset_3_8": tables[2]}
+    i = 0
+    for dtype in (np.int16, np.int32):
+        for (w, h, depth, hcb, vcb) in CASES:
+            for full in (False, True):
+                a, quant = make_case(rng, dtype, w, h, depth, hcb, vcb, tables, full)
+                out[f"c{i}_in"], out[f"c{i}_quant"] = a, quant
+                out[f"c{i}_depth"], out[f"c{i}_hcb"], out[f"c{i}_vcb"] = np.int32(depth), np.array(hcb), np.array(vcb)
+                out[f"c{i}_out"] = helpers.cpu_dequantise(ref, "ref", a, depth, hcb, vcb, quant)
+                i += 1
+    out["ncases"] = np.int32(i)
+    np.savez_compressed(os.path.join(helpers.GOLDEN_DIR, "dequant.npz"), **out)
+    print("dequant.npz:", i, "cases")
+
+
 def main():
     ref = helpers.load_ref()
     if ref is None:
         raise SystemExit("oracle/_ref/libschro_ref.so missing: run `make ref` where /root/reference exists")
     wavelet_golden(ref)
-    for name in ("frame_golden", "motion_golden", "hbm_golden", "glue_golden"):
+    for name in ("frame_golden", "motion_golden", "hbm_golden", "glue_golden", "dequant_golden"):
         fn = globals().get(name)
         if fn:
             fn(ref)

@@ -471,3 +471,33 @@ def cpu_add(lib, prefix, dst_planes, dw, dh, src_planes, sdepth, sw, sh, subtrac
         lib.oracle_add_plane(_vp(d), ctypes.c_int(d.strides[0]), d.shape[1], d.shape[0],
                              _vp(s), ctypes.c_int(s.strides[0]), sdepth, s.shape[1], s.shape[0], int(subtract))
     return dst
+
+
+# ---- dequantisation ---------------------------------------------------
+def dequant_table_size(depth, hcb, vcb):
+    """(factor, offset) pairs for one component: band index 0..3*depth, codeblock rows, columns."""
+    n = hcb[0] * vcb[0]
+    for level in range(depth):
+        n += 3 * hcb[level + 1] * vcb[level + 1]
+    return n
+
+
+def cpu_dequantise(lib, prefix, plane, depth, hcb, vcb, quant):
+    """{oracle,ref}_dequantise_plane in place on a copy; quant: int32 array of (factor, offset+2) pairs."""
+    a = np.ascontiguousarray(plane.copy())
+    fn = getattr(lib, f"{prefix}_dequantise_plane")
+    fn.restype = None
+    I8 = ctypes.c_int * 8
+    h = list(hcb) + [1] * (8 - len(hcb))
+    v = list(vcb) + [1] * (8 - len(vcb))
+    q = np.ascontiguousarray(quant, dtype=np.int32)
+    fn(_vp(a), ctypes.c_int(a.strides[0]), a.shape[1], a.shape[0], 1 if a.dtype == np.int32 else 0, depth,
+       I8(*h), I8(*v), _vp(q))
+    return a
+
+
+def ref_quant_tables(lib):
+    f, a, b = (np.zeros(61, np.uint32) for _ in range(3))
+    lib.ref_quant_tables.restype = None
+    lib.ref_quant_tables(_vp(f), _vp(a), _vp(b))
+    return f, a, b

@@ -62,3 +62,32 @@ def run_glue():
 
 if __name__ == "__main__":
     run_glue()
+
+
+def run_dequant():
+    """dequantisation in place"""
+    import numpy as np
+    for (name, w, h, count, depth) in (("s32", 3840, 2176, 16, 5), ("s16", 1920, 1088, 64, 4)):
+        a = dev.PictureSlab(dev.FrameLayout.yuv420(name, w, h), count, zero=False)
+        a.buf.random_(0, 8)
+        hcb = [1, 1, 2, 4, 8, 12][:depth + 1]
+        vcb = [1, 1, 2, 3, 6, 8][:depth + 1]
+        n = hcb[0] * vcb[0] + sum(3 * hcb[l + 1] * vcb[l + 1] for l in range(depth))
+        q = torch.tensor([[64, 34]] * (n * 3 * count), dtype=torch.int32, device="cuda").reshape(-1)
+        for _ in range(3):
+            dev.dequantise(a, depth, hcb, vcb, q)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            dev.dequantise(a, depth, hcb, vcb, q)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        nbytes = w * h * 1.5 * 2 * a.layout.bpp * count
+        print(f"dequantise {name} {w}x{h} d{depth}     {count:4d} pics {ms:8.3f} ms  {count/ms*1e3:9.1f} pics/s  "
+              f"{nbytes/ms/1e6:8.1f} GB/s ({nbytes/ms/1e6/6545.9*100:5.1f}% of 6545.9)")
+
+
+if __name__ == "__main__":
+    run_dequant()
