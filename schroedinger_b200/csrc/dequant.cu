@@ -17,6 +17,7 @@
 namespace sb2 {
 
 struct DequantArgs {
+  TileGrid tiles;
   PlaneSet planes;
   int w[SB2_MAX_COMPONENTS], h[SB2_MAX_COMPONENTS];
   int ncomp, depth;
@@ -50,9 +51,10 @@ template <typename T>
 __global__ void __launch_bounds__ (256)
 dequant_kernel (const DequantArgs a)
 {
-  const int comp = blockIdx.z % a.ncomp, pic = blockIdx.z / a.ncomp;
+  const TilePos tp = tile_pos (a.tiles);
+  const int comp = tp.comp, pic = blockIdx.y;
   const int w = a.w[comp], h = a.h[comp], D = a.depth;
-  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+  const int x0 = (tp.bx * blockDim.x + threadIdx.x) * 4, y = tp.by;
   if (x0 >= w || y >= h) return;
   T *row = reinterpret_cast<T *> (plane_ptr (a.planes, pic, comp) + (size_t) y * a.planes.stride[comp]);
   const int2 *q = a.quant + (size_t) pic * a.quant_pitch + (size_t) comp * a.comp_pairs;
@@ -196,7 +198,9 @@ sb2_dequantise (const sb2_slab *coeffs, int is_s32, const sb2_dequant_params *p,
     return set_error (SB2_ERR_ARG, "sb2_dequantise: table pitch %zu < %d pairs", quant_picture_pitch, a.comp_pairs * a.ncomp);
   a.quant = reinterpret_cast<const int2 *> (quant);
   a.quant_pitch = quant_picture_pitch;
-  dim3 grid (ceil_div (maxw, 4 * 256), maxh, a.ncomp * coeffs->count);
+  (void) maxw; (void) maxh;
+  if (coeffs->count > 65535) return set_error (SB2_ERR_ARG, "sb2_dequantise: at most 65535 pictures per call");
+  const dim3 grid = make_tile_grid (a.tiles, a.ncomp, a.w, a.h, 4 * 256, 1, coeffs->count);
   cudaStream_t st = as_stream (stream);
   {
     LaunchScope scope (is_s32 ? "dequantise_s32" : "dequantise_s16", bytes, st);

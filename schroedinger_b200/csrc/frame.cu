@@ -18,6 +18,7 @@
 namespace sb2 {
 
 struct FrameArgs {
+  TileGrid tiles;
   PlaneSet planes;              // phase-0 pixel (0,0) of every component
   int w[SB2_MAX_COMPONENTS];
   int h[SB2_MAX_COMPONENTS];
@@ -168,9 +169,10 @@ upsample_kernel_v2 (const FrameArgs a)
   __shared__ unsigned s0[U2_H + 7][U2_PITCH];      // phase 0, word c = pixels x0-4+4c ..
   __shared__ unsigned sv[U2_H][U2_PITCH];          // vertical half-pel of the same words
 
-  const int comp = blockIdx.z % a.ncomp, pic = blockIdx.z / a.ncomp;
+  const TilePos tp = tile_pos (a.tiles);
+  const int comp = tp.comp, pic = blockIdx.y;
   const int w = a.w[comp], h = a.h[comp], ext = a.ext;
-  const int x0 = blockIdx.x * U2_W - ext, y0 = blockIdx.y * U2_H - ext;
+  const int x0 = tp.bx * U2_W - ext, y0 = tp.by * U2_H - ext;
   if (x0 >= w + ext || y0 >= h + ext) return;
   uint8_t *p0 = reinterpret_cast<uint8_t *> (plane_ptr (a.planes, pic, comp));
   const int stride = a.planes.stride[comp];
@@ -252,6 +254,7 @@ upsample_kernel_v2 (const FrameArgs a)
 
 // ---- downsample ---------------------------------------------------------------------
 struct DownArgs {
+  TileGrid tiles;
   PlaneSet src, dst;
   int sw[SB2_MAX_COMPONENTS], sh[SB2_MAX_COMPONENTS];
   int dw[SB2_MAX_COMPONENTS], dh[SB2_MAX_COMPONENTS];
@@ -273,9 +276,10 @@ downsample_kernel_v2 (const DownArgs a)
 {
   __shared__ unsigned st[D2_H][D2_WORDS + 1];      // vertically filtered source words
 
-  const int comp = blockIdx.z % a.ncomp, pic = blockIdx.z / a.ncomp;
+  const TilePos tp = tile_pos (a.tiles);
+  const int comp = tp.comp, pic = blockIdx.y;
   const int sw = a.sw[comp], sh = a.sh[comp], dw = a.dw[comp], dh = a.dh[comp];
-  const int x0 = blockIdx.x * D2_W, y0 = blockIdx.y * D2_H;
+  const int x0 = tp.bx * D2_W, y0 = tp.by * D2_H;
   if (x0 >= dw || y0 >= dh) return;
   const uint8_t *s = reinterpret_cast<const uint8_t *> (plane_ptr (a.src, pic, comp));
   uint8_t *d = reinterpret_cast<uint8_t *> (plane_ptr (a.dst, pic, comp));
@@ -476,7 +480,11 @@ upsample_impl (const sb2_slab *frames, int extension, int fuse_edge, void *strea
   }
   static_assert ((U2_H + 7) * (U2_W + 8) <= (U2_H + 7) * U2_PITCH * 4 && U2_H * (U2_W + 8) <= U2_H * U2_PITCH * 4,
       "byte tiles of the edge path fit the word tiles");
-  dim3 grid (ceil_div (maxw, U2_W), ceil_div (maxh, U2_H), frames->ncomp * frames->count);
+  (void) maxw; (void) maxh;
+  int ew[SB2_MAX_COMPONENTS], eh[SB2_MAX_COMPONENTS];
+  for (int c = 0; c < frames->ncomp; c++) { ew[c] = frames->width[c] + 2 * extension; eh[c] = frames->height[c] + 2 * extension; }
+  if (frames->count > 65535) return set_error (SB2_ERR_ARG, "sb2_upsample: at most 65535 pictures per call");
+  const dim3 grid = make_tile_grid (a.tiles, frames->ncomp, ew, eh, U2_W, U2_H, frames->count);
   {
     LaunchScope scope ("upsample", bytes, as_stream (stream));
     upsample_kernel_v2<<<grid, 256, 0, as_stream (stream)>>> (a);
@@ -528,7 +536,9 @@ downsample_impl (const sb2_slab *src, const sb2_slab *dst, int dst_ext, void *st
       bytes += ((double) src->width[c] * src->height[c] + (double) dst->width[c] * dst->height[c]) * src->count;
     }
   }
-  dim3 grid (ceil_div (maxw, D2_W), ceil_div (maxh, D2_H), src->ncomp * src->count);
+  (void) maxw; (void) maxh;
+  if (src->count > 65535) return set_error (SB2_ERR_ARG, "sb2_downsample: at most 65535 pictures per call");
+  const dim3 grid = make_tile_grid (a.tiles, src->ncomp, a.dw, a.dh, D2_W, D2_H, src->count);
   {
     LaunchScope scope ("downsample", bytes, as_stream (stream));
     downsample_kernel_v2<<<grid, 256, 0, as_stream (stream)>>> (a);

@@ -15,6 +15,7 @@
 namespace sb2 {
 
 struct GlueArgs {
+  TileGrid tiles;
   PlaneSet src, dst;
   int sw[SB2_MAX_COMPONENTS], sh[SB2_MAX_COMPONENTS];
   int dw[SB2_MAX_COMPONENTS], dh[SB2_MAX_COMPONENTS];
@@ -93,9 +94,10 @@ convert_kernel (const GlueArgs a)
 {
   typedef typename Sample<SD>::T TS;
   typedef typename Sample<DD>::T TD;
-  const int comp = blockIdx.z % a.ncomp, pic = blockIdx.z / a.ncomp;
+  const TilePos tp = tile_pos (a.tiles);
+  const int comp = tp.comp, pic = blockIdx.y;
   const int dw = a.dw[comp], dh = a.dh[comp], sw = a.sw[comp], sh = a.sh[comp];
-  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y0 = blockIdx.y * GLUE_GROUPS;
+  const int x = (tp.bx * blockDim.x + threadIdx.x) * 4, y0 = tp.by * GLUE_GROUPS;
   if (x >= dw || y0 >= dh) return;
   const char *sbase = plane_ptr (a.src, pic, comp);
   char *dbase = plane_ptr (a.dst, pic, comp);
@@ -120,9 +122,10 @@ __global__ void __launch_bounds__ (256)
 add_kernel (const GlueArgs a, int subtract)
 {
   typedef typename Sample<SD>::T TS;
-  const int comp = blockIdx.z % a.ncomp, pic = blockIdx.z / a.ncomp;
+  const TilePos tp = tile_pos (a.tiles);
+  const int comp = tp.comp, pic = blockIdx.y;
   const int w = min (a.dw[comp], a.sw[comp]), h = min (a.dh[comp], a.sh[comp]);
-  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y0 = blockIdx.y * GLUE_GROUPS;
+  const int x = (tp.bx * blockDim.x + threadIdx.x) * 4, y0 = tp.by * GLUE_GROUPS;
   if (x >= w || y0 >= h) return;
   const char *sbase = plane_ptr (a.src, pic, comp);
   char *dbase = plane_ptr (a.dst, pic, comp);
@@ -170,7 +173,7 @@ glue_args (GlueArgs &a, const sb2_slab *src, const sb2_slab *dst, const char *wh
 }
 
 template <int SD, int DD>
-static void launch_convert (const GlueArgs &a, dim3 grid, cudaStream_t st) { convert_kernel<SD, DD><<<grid, 256, 0, st>>> (a); }
+static void launch_convert (const GlueArgs &a, const dim3 &grid, cudaStream_t st) { convert_kernel<SD, DD><<<grid, 256, 0, st>>> (a); }
 
 }  // namespace sb2
 
@@ -192,7 +195,9 @@ sb2_frame_convert (const sb2_slab *src, int src_depth, const sb2_slab *dst, int 
     maxh = max (maxh, a.dh[c]);
     bytes += (double) a.dw[c] * a.dh[c] * (bpp[src_depth] + bpp[dst_depth]) * src->count;
   }
-  dim3 grid (ceil_div (maxw, 4 * 256), ceil_div (maxh, GLUE_GROUPS), a.ncomp * src->count);
+  (void) maxw; (void) maxh;
+  if (src->count > 65535) return set_error (SB2_ERR_ARG, "sb2_frame_convert: at most 65535 pictures per call");
+  const dim3 grid = make_tile_grid (a.tiles, a.ncomp, a.dw, a.dh, 4 * 256, GLUE_GROUPS, src->count);
   cudaStream_t st = as_stream (stream);
   {
     LaunchScope scope ("frame_convert", bytes, st);
@@ -228,7 +233,11 @@ sb2_frame_add (const sb2_slab *dst, const sb2_slab *src, int src_depth, int subt
     maxh = max (maxh, h);
     bytes += (double) w * h * (4 + (src_depth ? 2 : 1)) * src->count;
   }
-  dim3 grid (ceil_div (maxw, 4 * 256), ceil_div (maxh, GLUE_GROUPS), a.ncomp * src->count);
+  (void) maxw; (void) maxh;
+  int cw[SB2_MAX_COMPONENTS], chh[SB2_MAX_COMPONENTS];
+  for (int c = 0; c < a.ncomp; c++) { cw[c] = min (a.dw[c], a.sw[c]); chh[c] = min (a.dh[c], a.sh[c]); }
+  if (src->count > 65535) return set_error (SB2_ERR_ARG, "sb2_frame_add: at most 65535 pictures per call");
+  const dim3 grid = make_tile_grid (a.tiles, a.ncomp, cw, chh, 4 * 256, GLUE_GROUPS, src->count);
   cudaStream_t st = as_stream (stream);
   {
     LaunchScope scope (subtract ? "frame_subtract" : "frame_add", bytes, st);

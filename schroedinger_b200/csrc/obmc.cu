@@ -922,6 +922,7 @@ sb2_obmc_render (const sb2_obmc_params *p, const void *motion_vectors, size_t mv
       if ((ref0->stride[c] & 3) || (ref1 && (ref1->stride[c] & 3))) v4_ok = false;
     }
     if (v4_ok) {
+      // (a compact grid without the out-of-plane chroma CTAs was measured 3 % slower here)
       dim3 g4 (ceil_div (maxw, O4_W), ceil_div (maxh, O4_H), ncomp * count);
       if (simple) obmc_kernel_v4<true><<<g4, 256, 0, as_stream (stream)>>> (A);
       else obmc_kernel_v4<false><<<g4, 256, 0, as_stream (stream)>>> (A);

@@ -135,9 +135,28 @@ struct LevelArgs {
   int w[SB2_MAX_COMPONENTS];
   int h[SB2_MAX_COMPONENTS];
   int ncomp;
-  int comp_map[SB2_MAX_COMPONENTS];   // blockIdx.z % ncomp -> component (a launch may cover a subset)
+  int comp_map[SB2_MAX_COMPONENTS];   // launch slot -> component (a launch may cover a subset)
+  // compact grid: blockIdx.x runs over the tiles of every selected component (no CTA is launched
+  // just to find itself outside a smaller chroma plane), blockIdx.y = picture
+  int tile_start[SB2_MAX_COMPONENTS + 1];
+  int tiles_x[SB2_MAX_COMPONENTS];
   int ncomp_total;                    // components per picture in the plane sets
 };
+
+struct TileId { int comp, bx, by; };
+__device__ __forceinline__ TileId level_tile (const LevelArgs &a)
+{
+  int t = blockIdx.x, ci = 0;
+#pragma unroll
+  for (int k = 1; k < SB2_MAX_COMPONENTS; k++)
+    if (k < a.ncomp && t >= a.tile_start[k]) ci = k;
+  t -= a.tile_start[ci];
+  TileId id;
+  id.comp = a.comp_map[ci];
+  id.by = t / a.tiles_x[ci];
+  id.bx = t - id.by * a.tiles_x[ci];
+  return id;
+}
 
 constexpr int TWH = 64;    // tile width  in polyphase samples (128 output columns)
 constexpr int THH = 32;    // tile height in polyphase samples (64 output rows)
@@ -250,11 +269,11 @@ wavelet_level_kernel (const LevelArgs a)
   extern __shared__ __align__ (16) unsigned char smem_raw[];
   T *sm = reinterpret_cast<T *> (smem_raw);
 
-  const int comp = a.comp_map[blockIdx.z % a.ncomp];
-  const int pic = blockIdx.z / a.ncomp;
+  const TileId tile = level_tile (a);
+  const int comp = tile.comp, pic = blockIdx.y;
   const int w = a.w[comp], h = a.h[comp];
   const int n = w >> 1, m = h >> 1;
-  const int kx0 = blockIdx.x * TWH, ky0 = blockIdx.y * THH;
+  const int kx0 = tile.bx * TWH, ky0 = tile.by * THH;
   if (kx0 >= n || ky0 >= m) return;
 
   const int kx_lo = max (0, kx0 - G::HK), kx_hi = min (n, kx0 + TWH + G::HK);
@@ -523,10 +542,11 @@ wavelet_inv_fast_kernel (const LevelArgs a)
   extern __shared__ __align__ (16) unsigned char smem_raw[];
   T *sm = reinterpret_cast<T *> (smem_raw);
 
-  const int comp = a.comp_map[blockIdx.z % a.ncomp], pic = blockIdx.z / a.ncomp;
+  const TileId tile = level_tile (a);
+  const int comp = tile.comp, pic = blockIdx.y;
   const int w = a.w[comp], h = a.h[comp];
   const int n = w >> 1, m = h >> 1;
-  const int kx0 = blockIdx.x * TWH, ky0 = blockIdx.y * THH;
+  const int kx0 = tile.bx * TWH, ky0 = tile.by * THH;
   if (kx0 >= n || ky0 >= m) return;
   constexpr int SH = filter_shift (F);
 
@@ -651,10 +671,11 @@ wavelet_fwd_fast_kernel (const LevelArgs a)
   extern __shared__ __align__ (16) unsigned char smem_raw[];
   T *sm = reinterpret_cast<T *> (smem_raw);
 
-  const int comp = a.comp_map[blockIdx.z % a.ncomp], pic = blockIdx.z / a.ncomp;
+  const TileId tile = level_tile (a);
+  const int comp = tile.comp, pic = blockIdx.y;
   const int w = a.w[comp], h = a.h[comp];
   const int n = w >> 1, m = h >> 1;
-  const int kx0 = blockIdx.x * TWH, ky0 = blockIdx.y * THH;
+  const int kx0 = tile.bx * TWH, ky0 = tile.by * THH;
   if (kx0 >= n || ky0 >= m) return;
   constexpr int SH = filter_shift (F);
 
@@ -759,6 +780,23 @@ static int fast_inverse_chunk (const LevelArgs &a, int c)
 
 // ---- host side ---------------------------------------------------------------
 
+// selects components `comps[0..nsel)` for a launch and lays their tiles out on blockIdx.x
+static dim3 level_grid (LevelArgs &a, const int *comps, int nsel, int count)
+{
+  a.ncomp = nsel;
+  int total = 0;
+  for (int i = 0; i < SB2_MAX_COMPONENTS; i++) { a.tile_start[i] = 0; a.tiles_x[i] = 1; }
+  for (int i = 0; i < nsel; i++) {
+    a.comp_map[i] = comps[i];
+    a.tile_start[i] = total;
+    a.tiles_x[i] = ceil_div (a.w[comps[i]] >> 1, TWH);
+    total += a.tiles_x[i] * ceil_div (a.h[comps[i]] >> 1, THH);
+  }
+  a.tile_start[nsel < SB2_MAX_COMPONENTS ? nsel : SB2_MAX_COMPONENTS] = total;
+  return dim3 (total, count, 1);
+}
+
+
 template <typename T, int F, int CS>
 static int launch_fast_inverse (LevelArgs a, const int *comps, int nsel, int count, cudaStream_t stream,
     const char *tag, double bytes)
@@ -771,14 +809,7 @@ static int launch_fast_inverse (LevelArgs a, const int *comps, int nsel, int cou
     if (e != cudaSuccess) return check_cuda (e, "cudaFuncSetAttribute(wavelet fast)");
     attr_set = true;
   }
-  int maxn = 0, maxm = 0;
-  a.ncomp = nsel;
-  for (int i = 0; i < nsel; i++) {
-    a.comp_map[i] = comps[i];
-    maxn = max (maxn, a.w[comps[i]] >> 1);
-    maxm = max (maxm, a.h[comps[i]] >> 1);
-  }
-  dim3 grid (ceil_div (maxn, TWH), ceil_div (maxm, THH), nsel * count);
+  const dim3 grid = level_grid (a, comps, nsel, count);
   {
     LaunchScope scope (tag, bytes, stream);
     wavelet_inv_fast_kernel<T, F, CS><<<grid, FG::NT, FG::SMEM, stream>>> (a);
@@ -798,14 +829,7 @@ static int launch_fast_forward (LevelArgs a, const int *comps, int nsel, int cou
     if (e != cudaSuccess) return check_cuda (e, "cudaFuncSetAttribute(wavelet fast forward)");
     attr_set = true;
   }
-  int maxn = 0, maxm = 0;
-  a.ncomp = nsel;
-  for (int i = 0; i < nsel; i++) {
-    a.comp_map[i] = comps[i];
-    maxn = max (maxn, a.w[comps[i]] >> 1);
-    maxm = max (maxm, a.h[comps[i]] >> 1);
-  }
-  dim3 grid (ceil_div (maxn, TWH), ceil_div (maxm, THH), nsel * count);
+  const dim3 grid = level_grid (a, comps, nsel, count);
   {
     LaunchScope scope (tag, bytes, stream);
     wavelet_fwd_fast_kernel<T, F, CS><<<grid, FG::NT, FG::SMEM, stream>>> (a);
@@ -853,14 +877,7 @@ static int launch_level (const LevelArgs &a_in, int count, cudaStream_t stream)
       if (k == 2) rc = launch_fast_forward<T, F, 8> (a, sel[k], nsel[k], count, stream, tag, bytes);
     }
     if (k == 0) {
-      int maxn = 0, maxm = 0;
-      a.ncomp = nsel[0];
-      for (int i = 0; i < nsel[0]; i++) {
-        a.comp_map[i] = sel[0][i];
-        maxn = max (maxn, a.w[sel[0][i]] >> 1);
-        maxm = max (maxm, a.h[sel[0][i]] >> 1);
-      }
-      dim3 grid (ceil_div (maxn, TWH), ceil_div (maxm, THH), nsel[0] * count);
+      const dim3 grid = level_grid (a, sel[0], nsel[0], count);
       {
         LaunchScope scope (tag, bytes, stream);
         wavelet_level_kernel<T, F, INV><<<grid, NTHREADS, G::SMEM, stream>>> (a);
@@ -945,6 +962,7 @@ static int validate (const sb2_slab *src, const sb2_slab *dst, int bpp, int dept
     return set_error (SB2_ERR_ARG, "slab shapes differ (ncomp %d/%d count %d/%d)",
         src->ncomp, dst->ncomp, src->count, dst->count);
   if (depth < 1 || depth > 8) return set_error (SB2_ERR_ARG, "bad transform depth %d", depth);
+  if (src->count > 65535) return set_error (SB2_ERR_ARG, "at most 65535 pictures per call (%d)", src->count);
   for (int c = 0; c < src->ncomp; c++) {
     if (src->width[c] != dst->width[c] || src->height[c] != dst->height[c])
       return set_error (SB2_ERR_ARG, "component %d size differs", c);
