@@ -81,9 +81,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, window=None):
+        """window = (t0, t1) in time.perf_counter() seconds: keep the samples that arrived while the
+        timed region ran (nvidia-smi needs a few hundred ms to start, so it is launched before the
+        warm-up and the samples are cut to the window afterwards)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -93,7 +96,9 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for (when, line) in self.lines:
+            if window and not (window[0] <= when <= window[1] + 0.12):
+                continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -561,27 +566,28 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
-        st.step()
-    barrier()
-
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(3, args.warmup)):
+        st.step()
+    barrier()
     lib.sb2_profile_reset()
     lib.sb2_profile_enable(1)
     launches0 = lib.sb2_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         st.step()
     e1.record()
     barrier()
+    t_end = time.perf_counter()
     lib.sb2_profile_enable(0)
     # stop polling NVML before the API-heavy e2e arm: nvidia-smi at 10 Hz stalls the host-side
     # CUDA calls it contends with (measured: e2e 29 fps with the sampler, 157 without)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop((t_begin, t_end)) if rank == 0 else None
     elapsed_ms = e0.elapsed_time(e1)
     launches = lib.sb2_launch_count() - launches0
     prof = collect_profile(lib)
@@ -843,7 +849,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="picture_core_2160p")
