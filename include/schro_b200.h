@@ -61,6 +61,7 @@ int sb2_profile_get (int index, char *tag, int tag_len, float *ms, double *bytes
  * frame, schroedinger/schroframe.c:60-191, repeated at a fixed pitch so that a
  * whole batch is one launch).  offset[] points at pixel (0,0) of the plane
  * (for extended / upsampled frames: of phase 0), stride[] is in bytes.
+ * A call takes at most 65535 pictures (they ride on the launch grid's y dimension).
  * ---------------------------------------------------------------------- */
 typedef struct {
   void *base;                       /* device */
