@@ -134,7 +134,8 @@ def _as_typed(buf, start, h, w, stride, depth):
     bpp = _BPP[depth]
     assert start % bpp == 0 and stride % bpp == 0
     typed = buf.view(_TORCH[depth])
-    return torch.as_strided(typed, (h, w), (stride // bpp, 1), start // bpp)
+    # as_strided's offset is absolute in the storage: honour a buffer that is itself a view
+    return torch.as_strided(typed, (h, w), (stride // bpp, 1), typed.storage_offset() + start // bpp)
 
 
 def _stream_ptr(stream):

@@ -29,5 +29,5 @@ tot = sum(v[0] for v in agg.values()); toti = sum(v[1] for v in agg.values())
 print('samples', tot, 'warp-instructions', toti)
 src = open(srcf).read().split('\n')
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-    line = src[k[1] - 1].strip()[:100] if k[1] > 0 else ''
+    line = src[k[1] - 1].strip()[:100] if (0 < k[1] <= len(src) and k[0] == srcf.split('/')[-1]) else ''
     print(f"{100*v[0]/tot:5.1f}%smp {100*v[1]/toti:5.1f}%ins sass={v[2]:4d} {k[0]}:{k[1]:5d}  {line}")
