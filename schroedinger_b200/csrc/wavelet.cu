@@ -768,13 +768,13 @@ wavelet_fwd_fast_kernel (const LevelArgs a)
 template <typename T, int F>
 static int fast_inverse_chunk (const LevelArgs &a, int c)
 {
-  if (filter_halo (F) > 4) return 0;                   // Fidelity: register arrays too large
   // 128-bit copy-out: rows of the dense plane must be 16-byte aligned
   if ((a.dense.stride[c] % 16) || (a.dense.off[c] % 16)) return 0;
   if (((size_t) a.dense.base % 16) || (a.dense.pic_pitch % 16)) return 0;
   const int n = a.w[c] >> 1, m = a.h[c] >> 1;
-  if (n % 16 == 0 && m % 16 == 0) return 16;
-  if (n % 8 == 0 && m % 8 == 0 && filter_halo (F) <= 4) return 8;
+  // Fidelity (halo 8) only with chunks of 8: with 16 the per-thread register arrays spill
+  if (n % 16 == 0 && m % 16 == 0 && filter_halo (F) <= 4) return 16;
+  if (n % 8 == 0 && m % 8 == 0) return 8;
   return 0;
 }
 
