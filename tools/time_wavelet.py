@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Quick device-resident timing of the wavelet transforms (development aid)."""
+"""Device-resident timing of the wavelet transforms, the convert glue and the dequantiser (development aid)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -27,18 +27,6 @@ def run(name, depth_name, filt, depth, w, h, count, inverse, iters=10):
     print(f"{name:28s} {count:4d} pics {ms:8.3f} ms  {count/ms*1e3:9.1f} pics/s  "
           f"{alg/ms/1e6:8.1f} GB/s algorithmic ({alg/ms/1e6/6545.9*100:5.1f}% of 6545.9)")
 
-if __name__ == "__main__":
-    run("LeGall s16 1080p d4 fwd", "s16", 1, 4, 1920, 1088, 64, False)
-    run("LeGall s16 1080p d4 inv", "s16", 1, 4, 1920, 1088, 64, True)
-    run("DD9/7 s16 1080p d4 inv", "s16", 0, 4, 1920, 1088, 64, True)
-    run("DD9/7 s16 1080p d4 fwd", "s16", 0, 4, 1920, 1088, 64, False)
-    run("Daub s32 2160p d5 inv", "s32", 6, 5, 3840, 2176, 8, True)
-    run("Daub s32 2160p d5 fwd", "s32", 6, 5, 3840, 2176, 8, False)
-    run("Daub s32 2160p d1 inv", "s32", 6, 1, 3840, 2176, 8, True)
-    run("Fidelity s16 1080p d4 inv", "s16", 5, 4, 1920, 1088, 64, True)
-    run("Haar0 s16 1080p d4 inv", "s16", 3, 4, 1920, 1088, 64, True)
-
-
 def run_glue():
     """combine / convert glue: bytes moved per second against the HBM peak"""
     for (sd, dd, w, h, count) in (("s16", "u8", 1920, 1080, 64), ("s32", "u8", 3840, 2160, 16), ("u8", "s16", 1920, 1080, 64)):
@@ -59,9 +47,6 @@ def run_glue():
         print(f"convert {sd}->{dd} {w}x{h}       {count:4d} pics {ms:8.3f} ms  {count/ms*1e3:9.1f} pics/s  "
               f"{nbytes/ms/1e6:8.1f} GB/s ({nbytes/ms/1e6/6545.9*100:5.1f}% of 6545.9)")
 
-
-if __name__ == "__main__":
-    run_glue()
 
 
 def run_dequant():
@@ -90,4 +75,14 @@ def run_dequant():
 
 
 if __name__ == "__main__":
+    run("LeGall s16 1080p d4 fwd", "s16", 1, 4, 1920, 1088, 64, False)
+    run("LeGall s16 1080p d4 inv", "s16", 1, 4, 1920, 1088, 64, True)
+    run("DD9/7 s16 1080p d4 inv", "s16", 0, 4, 1920, 1088, 64, True)
+    run("DD9/7 s16 1080p d4 fwd", "s16", 0, 4, 1920, 1088, 64, False)
+    run("Daub s32 2160p d5 inv", "s32", 6, 5, 3840, 2176, 8, True)
+    run("Daub s32 2160p d5 fwd", "s32", 6, 5, 3840, 2176, 8, False)
+    run("Daub s32 2160p d1 inv", "s32", 6, 1, 3840, 2176, 8, True)
+    run("Fidelity s16 1080p d4 inv", "s16", 5, 4, 1920, 1088, 64, True)
+    run("Haar0 s16 1080p d4 inv", "s16", 3, 4, 1920, 1088, 64, True)
+    run_glue()
     run_dequant()
