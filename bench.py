@@ -37,12 +37,12 @@ def workload_spec(name):
                           " + 4-level hierarchical SAD block matching")
     if name == "wavelet_1080p_dd97":
         return dict(width=1920, height=1080, iwt_w=1920, iwt_h=1088, depth_name="s16", filter=0,
-                    transform_depth=4, batch=64,
-                    label="1080p 4:2:0 8-bit: inverse Deslauriers-Dubuc 9/7 4-level s16 (config 2)")
+                    transform_depth=4, batch=64, full_core=False,
+                    label="1080p 4:2:0 8-bit: inverse Deslauriers-Dubuc 9/7 4-level s16 only (BASELINE configs[1])")
     if name == "wavelet_1080p_legall":
         return dict(width=1920, height=1080, iwt_w=1920, iwt_h=1088, depth_name="s16", filter=1,
-                    transform_depth=4, batch=64,
-                    label="1080p 4:2:0 8-bit: forward+inverse LeGall 5/3 4-level s16 (config 1)")
+                    transform_depth=4, batch=64, full_core=False,
+                    label="1080p 4:2:0 8-bit: inverse LeGall 5/3 4-level s16 only (BASELINE configs[0], inverse half)")
     if name == "picture_core_cif":       # tiny, for CPU-side testing of bench.py itself
         return dict(width=352, height=288, iwt_w=352, iwt_h=288, depth_name="s32", filter=6,
                     transform_depth=5, batch=4, label="CIF test workload, all stages")
@@ -626,11 +626,12 @@ def run_ours(args):
         hf.close()
         e2e = {"value": B * e2e_steps * world / dt, "unit": "frames/s", "steps": e2e_steps,
                "h2d_bytes_per_step": hf.h2d * B, "d2h_bytes_per_step": hf.d2h * B,
-               "api": "drop-in schro_* C API (schro_frame_to_gpu, schro_frame_inverse_iwt_transform, "
-                      "schro_motion_render, schro_frame_mc_edgeextend, schro_upsampled_frame_upsample, "
-                      "schro_frame_downsample, schro_hbm_scan, schro_hierarchical_bm_scan_hint, "
-                      f"schro_gpuframe_to_cpu) on pinned host SchroFrames, {nthreads} host threads/GPU ({args.e2e_driver} driver), "
-                      "one stream each"}
+               "api": ("drop-in schro_* C API (schro_frame_to_gpu, schro_frame_inverse_iwt_transform, "
+                       "schro_motion_render, schro_frame_mc_edgeextend, schro_upsampled_frame_upsample, "
+                       "schro_frame_downsample, schro_hbm_scan, schro_hierarchical_bm_scan_hint, "
+                       "schro_gpuframe_to_cpu)" if hf.full else
+                       "drop-in schro_frame_inverse_iwt_transform on the host frame (staged H2D, transform, D2H)")
+                      + f" on pinned host SchroFrames, {nthreads} host threads/GPU ({args.e2e_driver} driver), one stream each"}
     except Exception as ex:  # keep the device-resident number even if the host arm breaks
         e2e = {"value": None, "unit": "frames/s", "error": repr(ex)}
 
