@@ -61,9 +61,11 @@ for G in (1, 2, 4, 8):
         e0.record()
         cur = torch.cuda.current_stream()
         evs = []
-        for j in jobs:
+        for j in jobs:                       # fork every stream first: joining inside this loop would chain them
             j["st"].wait_stream(cur)
+        for j in jobs:
             dev.hbm_scan(prm, j["sp"], j["rp"], 3, j["fields"], j["ws"], stream=j["st"])
+        for j in jobs:
             cur.wait_stream(j["st"])
         e1.record()
         torch.cuda.synchronize()
