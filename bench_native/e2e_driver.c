@@ -45,6 +45,49 @@ now (void)
 }
 #define TIMED(slot, stmt) do { if (g_timing) { const double t0_ = now (); stmt; g_times[t & 63][slot] += now () - t0_; } else { stmt; } } while (0)
 
+/* development aid (SB2_E2E_STAGES=mask): run only some stages of a picture, to see which of them limit the
+ * threaded throughput.  1 = H2D coefficients, 2 = inverse wavelet + render + upsample, 4 = D2H picture,
+ * 8 = H2D source, 16 = pyramid, 32 = block matching */
+static int g_stage_mask = 0xff;
+static void
+partial_picture (int t, int i)
+{
+  const Sb2E2eJob *j = &g_job;
+  SchroFrame **pyr = j->src_pyr + (size_t) t * (j->levels + 1);
+  SchroFrame view;
+  int c, l;
+  if (g_stage_mask & 1) schro_frame_to_gpu (j->coef_dev[t], j->coef_host[i]);
+  if (g_stage_mask & 2) {
+    schro_frame_inverse_iwt_transform (j->coef_dev[t], j->params);
+    view = *j->coef_dev[t];
+    view.refcount = 1;
+    view.domain = NULL;
+    view.height = j->pic_height;
+    for (c = 0; c < 3; c++) view.components[c].height = c ? j->pic_height / 2 : j->pic_height;
+    schro_motion_render (j->motion[t], j->acc_dev[t], &view, 1, j->out_dev[t]);
+    schro_frame_mc_edgeextend (j->out_dev[t]);
+    j->out_dev[t]->upsample_done = 0;
+    schro_upsampled_frame_upsample (j->out_dev[t]);
+  }
+  if (g_stage_mask & 4) schro_gpuframe_to_cpu (j->out_host[i], j->out_dev[t]);
+  if (g_stage_mask & 8) schro_frame_to_gpu (pyr[0], j->src_host[i]);
+  if (g_stage_mask & 16) {
+    schro_frame_mc_edgeextend (pyr[0]);
+    for (l = 0; l < j->levels; l++) {
+      schro_frame_downsample (pyr[l + 1], pyr[l]);
+      schro_frame_mc_edgeextend (pyr[l + 1]);
+    }
+  }
+  if (g_stage_mask & 32) {
+    SchroHierBm *hbm = schro_hbm_new_from_frames (j->params, 0, j->levels, 0, pyr, j->ref_pyr);
+    schro_hbm_scan (hbm);
+    schro_hierarchical_bm_scan_hint (hbm, 0, 3);
+    g_sink += (unsigned) schro_hbm_motion_field (hbm, 0)->motion_vectors[0].metric;
+    schro_hbm_unref (hbm);
+  }
+  if (!(g_stage_mask & (4 | 32))) schro_b200_thread_sync ();
+}
+
 static void
 one_picture (int t, int i)
 {
@@ -59,6 +102,7 @@ one_picture (int t, int i)
     schro_frame_inverse_iwt_transform (j->coef_host[i], j->params);
     return;
   }
+  if (g_stage_mask != 0xff) { partial_picture (t, i); return; }
   /* decode side: coefficients in, decoded picture out */
   TIMED (T_H2D_COEF, schro_frame_to_gpu (j->coef_dev[t], j->coef_host[i]));
   TIMED (T_IWT, schro_frame_inverse_iwt_transform (j->coef_dev[t], j->params));
@@ -113,6 +157,7 @@ sb2_e2e_start (const Sb2E2eJob *job)
   int t;
   g_job = *job;
   g_quit = 0;
+  if (getenv ("SB2_E2E_STAGES")) g_stage_mask = atoi (getenv ("SB2_E2E_STAGES"));
   pthread_barrier_init (&g_start, NULL, (unsigned) job->nthreads + 1);
   pthread_barrier_init (&g_end, NULL, (unsigned) job->nthreads + 1);
   g_threads = calloc ((size_t) job->nthreads, sizeof (pthread_t));

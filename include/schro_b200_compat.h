@@ -273,6 +273,9 @@ void schro_b200_set_device (int device);
 /* new: release the calling thread's stream / staging buffers / device-block pool (call
  * before a worker thread exits; long-lived workers never need it) */
 void schro_b200_thread_release (void);
+/* new: wait until the work the calling thread has left in flight on device frames is done
+ * (calls that hand a result to the host already wait; this is for timing and for teardown) */
+void schro_b200_thread_sync (void);
 /* schroedinger/schrocuda.h:9 (schro_memory_domain_new_cuda) */
 SchroMemoryDomain *schro_memory_domain_new_cuda (void);
 SchroMemoryDomain *schro_memory_domain_new_pinned (void); /* new: cudaHostAlloc'd frames */

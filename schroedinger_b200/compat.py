@@ -136,6 +136,7 @@ def _proto(name, restype, argtypes):
 _proto("schro_init", None, [])
 _proto("schro_b200_set_device", None, [ctypes.c_int])
 _proto("schro_b200_thread_release", None, [])
+_proto("schro_b200_thread_sync", None, [])
 _proto("schro_memory_domain_new_cuda", ctypes.c_void_p, [])
 _proto("schro_memory_domain_new_pinned", ctypes.c_void_p, [])
 _proto("schro_memory_domain_free", None, [ctypes.c_void_p])

@@ -92,8 +92,11 @@ __device__ __forceinline__ unsigned block_sad (const uint8_t *a, int as, const u
 }
 
 __global__ void __launch_bounds__ (128)
-hbm_init_field_kernel (MotionVector *field, size_t n, uint32_t flags0)
+hbm_init_field_kernel (MotionVector *field, size_t n, uint32_t flags0, unsigned long long *words, size_t nwords)
 {
+  // the published-result words of the level start out invalid (same launch: one API call less per level)
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < nwords; i += (size_t) gridDim.x * blockDim.x)
+    words[i] = 0;
   for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
     MotionVector m;
     m.flags = flags0;
@@ -696,19 +699,18 @@ sb2_hbm_scan_hint (const sb2_hbm_params *p, const sb2_slab *src_level, const sb2
     return set_error (SB2_ERR_WORKSPACE, "sb2_hbm_scan_hint: workspace %zu < %zu", workspace_bytes, need);
   A.words = static_cast<unsigned long long *> (workspace);
   cudaStream_t st = as_stream (stream);
-  cudaError_t e = cudaMemsetAsync (workspace, 0, need, st);
-  if (e != cudaSuccess) return check_cuda (e, "cudaMemsetAsync(words)");
   const size_t nfield = (size_t) A.nbx * A.nby;
   if (field_picture_pitch == nfield || count == 1) {
     // contiguous fields: one launch initialises every pair's field
     LaunchScope scope ("hbm_init_field", (double) nfield * 20 * count, st);
     hbm_init_field_kernel<<<(unsigned) min ((size_t) 2048, (nfield * count + 127) / 128), 128, 0, st>>> (
-        A.field, nfield * count, A.flags0);
+        A.field, nfield * count, A.flags0, A.words, need / sizeof (unsigned long long));
   } else {
+    const size_t nwords = need / sizeof (unsigned long long) / count;
     for (int pic = 0; pic < count; pic++) {
       LaunchScope scope ("hbm_init_field", (double) nfield * 20, st);
       hbm_init_field_kernel<<<(unsigned) min ((size_t) 1024, (nfield + 127) / 128), 128, 0, st>>> (
-          A.field + (size_t) pic * field_picture_pitch, nfield, A.flags0);
+          A.field + (size_t) pic * field_picture_pitch, nfield, A.flags0, A.words + pic * nwords, nwords);
     }
   }
   // algorithmic bytes: both pyramids of this level once + the fields

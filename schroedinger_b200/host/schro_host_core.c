@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 void
 sb2h_fatal (const char *func, const char *fmt, ...)
@@ -56,6 +57,9 @@ sb2h_mem_kind (const void *ptr)
 
 /* ---- per-thread context -------------------------------------------------- */
 static __thread Sb2hContext *tl_cx;
+/* how sb2h_sync waits: 0 = cudaEventSynchronize on a blocking-sync event, N > 0 = poll with N-microsecond naps
+ * (SB2_HOST_WAIT_US; default 0: with as many workers as cores the naps cost more than the wake-ups) */
+static int g_wait_mode = 0;
 /* The device of the first thread that enters the library becomes the process's device:
  * worker threads created later start on device 0 by CUDA's rules, which is wrong for
  * rank > 0 of a one-process-per-GPU job.  schro_b200_set_device overrides it. */
@@ -80,6 +84,12 @@ static Sb2hContext *g_ctx[SB2H_MAX_CTX];        /* live per-thread contexts, und
  * threads are expected to be long-lived (as SchroAsync's are); a thread that does exit
  * should call this first.  There is deliberately no automatic thread-exit hook: it would
  * also run during process teardown, after the CUDA runtime has been unloaded. */
+void
+schro_b200_thread_sync (void)
+{
+  if (tl_cx) sb2h_sync (tl_cx);
+}
+
 void
 schro_b200_thread_release (void)
 {
@@ -109,6 +119,7 @@ sb2h_context (void)
     int i;
     pthread_mutex_lock (&g_device_mutex);
     if (g_device < 0) SB2H_CUDA (cudaGetDevice (&g_device));
+    if (getenv ("SB2_HOST_WAIT_US")) g_wait_mode = atoi (getenv ("SB2_HOST_WAIT_US"));
     pthread_mutex_unlock (&g_device_mutex);
     SB2H_CUDA (cudaSetDevice (g_device));
     tl_cx = calloc (1, sizeof (Sb2hContext));
@@ -137,7 +148,22 @@ sb2h_sync (Sb2hContext *cx)
   /* a worker that waits gives its core away (many workers share the host with the
    * application's own threads); the price is a few tens of microseconds of wake-up latency */
   SB2H_CUDA (cudaEventRecord (cx->sync_ev, cx->stream));
-  SB2H_CUDA (cudaEventSynchronize (cx->sync_ev));
+  if (g_wait_mode == 0) {
+    SB2H_CUDA (cudaEventSynchronize (cx->sync_ev));
+  } else {
+    /* poll: a few tens of microseconds of spinning for the short waits, then short sleeps.  The
+     * driver's interrupt-driven wait costs ~0.4 ms per wake-up once a wait is longer than its own
+     * spin phase, which every picture-sized transfer is. */
+    struct timespec t0, t, nap = { 0, g_wait_mode * 1000L };
+    clock_gettime (CLOCK_MONOTONIC, &t0);
+    for (;;) {
+      const cudaError_t e = cudaEventQuery (cx->sync_ev);
+      if (e == cudaSuccess) break;
+      if (e != cudaErrorNotReady) SB2H_CUDA (e);
+      clock_gettime (CLOCK_MONOTONIC, &t);
+      if ((t.tv_sec - t0.tv_sec) * 1000000000L + (t.tv_nsec - t0.tv_nsec) > 40000L) nanosleep (&nap, NULL);
+    }
+  }
   cx->dirty = 0;
 }
 

@@ -132,25 +132,54 @@ level_slab (Sb2hContext *cx, SchroFrame *f, void **cache, sb2_slab *slab)
   }
 }
 
-/* one level, left in flight on the thread's stream: kernel + asynchronous copy of the field
- * into a page-locked host SchroMotionField */
+typedef struct {
+  sb2_slab ss, rs;
+} LevelIn;
+
+/* Everything of a level that touches the thread's ordering stream: uploads of host pyramid
+ * levels, waits on other threads' writes of device frames, allocations.  Done for every level
+ * of a search before the one fork, so that the levels then chain on the priority stream alone. */
 static void
-scan_level (SchroHierBm *hbm, int shift, int h_range)
+prepare_level (Sb2hContext *cx, SchroHierBm *hbm, int shift, LevelIn *in)
 {
   Sb2hHierBm *h = (Sb2hHierBm *) hbm;
-  Sb2hContext *cx = sb2h_context ();
   SchroParams *params = hbm->params;
-  SchroFrame *fs, *fr;
-  sb2_slab ss, rs;
+  const size_t n = (size_t) params->x_num_blocks * params->y_num_blocks;
+  SB2H_ASSERT (shift >= 0 && shift <= hbm->hierarchy_levels);
+  level_slab (cx, hbm->downsampled_src[shift], &h->dev_src[shift], &in->ss);
+  level_slab (cx, hbm->downsampled_ref[shift], &h->dev_ref[shift], &in->rs);
+  if (!h->dev_ws) {
+    h->ws_bytes = sb2_hbm_workspace_bytes (params->x_num_blocks, params->y_num_blocks, 1);
+    h->dev_ws = sb2h_pool_alloc (h->ws_bytes);
+  }
+  if (!h->dev_field[shift])
+    h->dev_field[shift] = sb2h_pool_alloc (n * sizeof (SchroMotionVector));
+}
+
+/* The block-matching kernels are dependency-latency bound: a block row makes progress only
+ * while every row above it is resident.  They run on the thread's highest-priority stream so
+ * that their CTAs are placed before those of the bandwidth kernels other threads have queued.
+ * cx->stream stays the ordering backbone: one fork before the first level ... */
+static void
+fork_priority_stream (Sb2hContext *cx)
+{
+  SB2H_CUDA (cudaEventRecord (cx->ev_fork, cx->stream));
+  SB2H_CUDA (cudaStreamWaitEvent (cx->stream_hi, cx->ev_fork, 0));
+}
+
+/* ... and one level: the kernel on the priority stream, then the copy of its field into a
+ * page-locked host SchroMotionField on cx->stream behind an event.  The next level's kernel does
+ * not wait for that copy (the copy engine is shared with other threads' picture transfers). */
+static void
+launch_level (Sb2hContext *cx, SchroHierBm *hbm, int shift, int h_range, const LevelIn *in)
+{
+  Sb2hHierBm *h = (Sb2hHierBm *) hbm;
+  SchroParams *params = hbm->params;
+  SchroFrame *fs = hbm->downsampled_src[shift];
   sb2_hbm_params p;
   SchroMotionField *mf;
   const size_t n = (size_t) params->x_num_blocks * params->y_num_blocks;
 
-  SB2H_ASSERT (shift >= 0 && shift <= hbm->hierarchy_levels);
-  fs = hbm->downsampled_src[shift];
-  fr = hbm->downsampled_ref[shift];
-  level_slab (cx, fs, &h->dev_src[shift], &ss);
-  level_slab (cx, fr, &h->dev_ref[shift], &rs);
   memset (&p, 0, sizeof (p));
   p.xbsep = params->xbsep_luma;
   p.ybsep = params->ybsep_luma;
@@ -160,19 +189,7 @@ scan_level (SchroHierBm *hbm, int shift, int h_range)
   p.use_chroma = hbm->use_chroma;
   p.chroma_h_shift = SCHRO_FRAME_FORMAT_H_SHIFT (fs->format);
   p.chroma_v_shift = SCHRO_FRAME_FORMAT_V_SHIFT (fs->format);
-  if (!h->dev_ws) {
-    h->ws_bytes = sb2_hbm_workspace_bytes (params->x_num_blocks, params->y_num_blocks, 1);
-    h->dev_ws = sb2h_pool_alloc (h->ws_bytes);
-  }
-  if (!h->dev_field[shift])
-    h->dev_field[shift] = sb2h_pool_alloc (n * sizeof (SchroMotionVector));
-  /* The block-matching kernels are dependency-latency bound: a block row makes progress only
-   * while every row above it is resident.  They run on the thread's highest-priority stream so
-   * that their CTAs are placed before those of the bandwidth kernels other threads have queued;
-   * cx->stream stays the ordering backbone (fork before, join after). */
-  SB2H_CUDA (cudaEventRecord (cx->ev_fork, cx->stream));
-  SB2H_CUDA (cudaStreamWaitEvent (cx->stream_hi, cx->ev_fork, 0));
-  SB2H_CHECK (sb2_hbm_scan_hint (&p, &ss, &rs, fs->extension, shift, h_range,
+  SB2H_CHECK (sb2_hbm_scan_hint (&p, &in->ss, &in->rs, fs->extension, shift, h_range,
           shift < hbm->hierarchy_levels ? h->dev_field[shift + 1] : NULL, h->dev_field[shift], n,
           h->dev_ws, h->ws_bytes, cx->stream_hi), "sb2_hbm_scan_hint");
   SB2H_CUDA (cudaEventRecord (cx->ev_join, cx->stream_hi));
@@ -193,20 +210,28 @@ scan_level (SchroHierBm *hbm, int shift, int h_range)
 void
 schro_hierarchical_bm_scan_hint (SchroHierBm *hbm, int shift, int h_range)
 {
-  scan_level (hbm, shift, h_range);
-  sb2h_sync (sb2h_context ());      /* the host field is read by the caller */
+  Sb2hContext *cx = sb2h_context ();
+  LevelIn in;
+  prepare_level (cx, hbm, shift, &in);
+  fork_priority_stream (cx);
+  launch_level (cx, hbm, shift, h_range, &in);
+  sb2h_sync (cx);      /* the host field is read by the caller */
 }
 
 void
 schro_hbm_scan (SchroHierBm *hbm)
 {
+  Sb2hContext *cx = sb2h_context ();
+  LevelIn in[9];
   int i, half_scan_range = 20;
   const int n_levels = hbm->hierarchy_levels;
   SB2H_ASSERT (n_levels > 0);
-  /* the levels chain on the stream; one wait at the end makes all host fields valid */
-  scan_level (hbm, n_levels, half_scan_range);
+  for (i = n_levels; 1 <= i; --i) prepare_level (cx, hbm, i, &in[i]);
+  fork_priority_stream (cx);
+  /* the levels chain on the priority stream; one wait at the end makes all host fields valid */
+  launch_level (cx, hbm, n_levels, half_scan_range, &in[n_levels]);
   half_scan_range >>= 1;
   for (i = n_levels - 1; 1 <= i; --i, half_scan_range >>= 1)
-    scan_level (hbm, i, half_scan_range > 3 ? half_scan_range : 3);
-  sb2h_sync (sb2h_context ());
+    launch_level (cx, hbm, i, half_scan_range > 3 ? half_scan_range : 3, &in[i]);
+  sb2h_sync (cx);
 }

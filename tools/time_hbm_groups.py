@@ -47,7 +47,7 @@ class PyrGroup:
 
 
 torch.cuda.synchronize()
-for G in (1, 2, 4, 8):
+for G in [g for g in (1, 2, 4, 8, 16, 32) if g <= B]:
     per = B // G
     jobs = []
     for g in range(G):
