@@ -495,6 +495,8 @@ class HostFrames:
             job.motion = mo
             job.src_pyr = arr([f for t in self.th for f in t["src_pyr"]])
         drv.sb2_e2e_step.restype = ctypes.c_double
+        drv.sb2_e2e_run.restype = ctypes.c_double
+        drv.sb2_e2e_run.argtypes = [ctypes.c_int]
         if drv.sb2_e2e_start(ctypes.byref(job)) != 0:
             raise RuntimeError("sb2_e2e_start failed")
         self._keep.append(job)
@@ -611,8 +613,13 @@ def run_ours(args):
         e2e_steps = 0
         t0 = time.perf_counter()
         while e2e_steps < args.steps or (time.perf_counter() - t0 < 3.0 and e2e_steps < 50 * args.steps):
-            hf.step()
-            e2e_steps += 1
+            if args.e2e_driver == "native":
+                # the worker threads run the steps back to back (no barrier between two steps)
+                hf.drv.sb2_e2e_run(args.steps)
+                e2e_steps += args.steps
+            else:
+                hf.step()
+                e2e_steps += 1
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -857,7 +864,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--content", default="natural", choices=["natural", "periodic"],
                     help="texture of the synthetic pictures (see textured_frame)")
-    ap.add_argument("--e2e-threads", type=int, default=8, help="host threads driving the drop-in API in the e2e leg")
+    ap.add_argument("--e2e-threads", type=int, default=32, help="host threads driving the drop-in API in the e2e leg")
     ap.add_argument("--e2e-driver", default="native", choices=["native", "python"],
                     help="host threads of the e2e leg: pthreads in bench_native/e2e_driver.c, or Python threads + ctypes")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)

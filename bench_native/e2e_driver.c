@@ -28,7 +28,7 @@ typedef struct {
 static Sb2E2eJob g_job;
 static pthread_t *g_threads;
 static pthread_barrier_t g_start, g_end;
-static volatile int g_quit;
+static volatile int g_quit, g_passes = 1;
 static volatile unsigned g_sink;
 
 /* optional per-call wall-clock accounting (summed over threads), read with sb2_e2e_times */
@@ -141,10 +141,13 @@ worker (void *arg)
 {
   const int t = (int) (size_t) arg;
   for (;;) {
-    int i;
+    int i, s;
     pthread_barrier_wait (&g_start);
     if (g_quit) break;
-    for (i = t; i < g_job.npictures; i += g_job.nthreads) one_picture (t, i);
+    /* passes follow each other without a barrier: a thread that is done with its pictures of one
+     * step starts on the next step's, as the workers of a running codec would */
+    for (s = 0; s < g_passes; s++)
+      for (i = t; i < g_job.npictures; i += g_job.nthreads) one_picture (t, i);
     pthread_barrier_wait (&g_end);
   }
   schro_b200_thread_release ();
@@ -166,16 +169,23 @@ sb2_e2e_start (const Sb2E2eJob *job)
   return 0;
 }
 
-/* one step = every picture of the job once; returns wall seconds */
+/* `steps` steps, a step = every picture of the job once; returns wall seconds */
 double
-sb2_e2e_step (void)
+sb2_e2e_run (int steps)
 {
   struct timespec a, b;
+  g_passes = steps;
   clock_gettime (CLOCK_MONOTONIC, &a);
   pthread_barrier_wait (&g_start);
   pthread_barrier_wait (&g_end);
   clock_gettime (CLOCK_MONOTONIC, &b);
   return (double) (b.tv_sec - a.tv_sec) + 1e-9 * (double) (b.tv_nsec - a.tv_nsec);
+}
+
+double
+sb2_e2e_step (void)
+{
+  return sb2_e2e_run (1);
 }
 
 /* enable / read the per-call accounting: out[T_N] seconds summed over threads since enabling */

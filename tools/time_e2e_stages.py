@@ -10,16 +10,14 @@ import torch
 import bench
 from schroedinger_b200 import lib
 spec = bench.workload_spec("picture_core_2160p")
-spec["batch"] = 4 * nth
+spec["batch"] = max(32, nth)
 torch.cuda.set_device(0)
 hf = bench.HostFrames(spec, lib, nth)
 hf.native_start()
 for _ in range(2):
     hf.step()
-hf.drv.sb2_e2e_step.restype = ctypes.c_double
-N, wall = 5, 0.0
-for _ in range(N):
-    wall += hf.drv.sb2_e2e_step()
+N = 20
+wall = hf.drv.sb2_e2e_run(N)
 npic = N * spec["batch"]
 names = {1: "H2D coef", 2: "decode kernels", 4: "D2H picture", 8: "H2D source", 16: "pyramid", 32: "block matching"}
 what = "+".join(v for k, v in names.items() if mask & k)
