@@ -191,3 +191,35 @@ def test_block_matching_from_many_threads_matches_one_thread(cuda):
     for f in sp + rp:
         lib.schro_frame_unref(f)
     lib.schro_memory_domain_free(cuda_dom)
+
+
+def test_polling_wait_mode_and_thread_sync(cuda, monkeypatch):
+    """SB2_HOST_WAIT_US switches the host waits from the driver's blocking wait to polling (read
+    when a thread first enters the library); results are the same either way, and
+    schro_b200_thread_sync drains what a thread has left in flight on CUDA-domain frames."""
+    from schroedinger_b200 import compat, lib
+    params, pinned, hosts, wants = _coef_frames(compat, 2, 5)
+    cuda_dom = compat.cuda_domain()
+    iw, ih = params.iwt_luma_width, params.iwt_luma_height
+    outs = [compat.frame_new_and_alloc(pinned, compat.FORMAT_S16_420, iw, ih) for _ in range(2)]
+
+    def worker(t):
+        def go():
+            f = compat.frame_new_and_alloc(cuda_dom, compat.FORMAT_S16_420, iw, ih)
+            lib.schro_frame_to_gpu(f, hosts[t])
+            lib.schro_frame_inverse_iwt_transform(f, ctypes.byref(params))   # left in flight
+            lib.schro_b200_thread_sync()
+            lib.schro_gpuframe_to_cpu(outs[t], f)
+            lib.schro_frame_unref(f)
+            lib.schro_b200_thread_release()
+        return go
+
+    for t, mode in enumerate(("20", "0")):
+        monkeypatch.setenv("SB2_HOST_WAIT_US", mode)
+        _run_threads([worker(t)])
+        for c in range(3):
+            assert np.array_equal(compat.frame_plane(outs[t], c), wants[t][c]), (mode, c)
+    for f in outs + hosts:
+        lib.schro_frame_unref(f)
+    lib.schro_memory_domain_free(cuda_dom)
+    lib.schro_memory_domain_free(pinned)
