@@ -207,43 +207,15 @@ launch_level (Sb2hContext *cx, SchroHierBm *hbm, int shift, int h_range, const L
   hbm->downsampled_mf[shift] = mf;
 }
 
-/* Optional cap on the searches in flight at once (SB2_HBM_MAX_SEARCHES; 0 = no cap): a search is a chain of
- * latency-bound wavefronts, and past a point more of them on the GPU at once lower its throughput. */
-#include <semaphore.h>
-#include <pthread.h>
-static sem_t g_search_slots;
-static int g_search_cap = -1;
-static pthread_once_t g_search_once = PTHREAD_ONCE_INIT;
-static void
-search_cap_init (void)
-{
-  const char *e = getenv ("SB2_HBM_MAX_SEARCHES");
-  g_search_cap = e ? atoi (e) : 0;
-  if (g_search_cap > 0) sem_init (&g_search_slots, 0, (unsigned) g_search_cap);
-}
-static void
-search_enter (void)
-{
-  pthread_once (&g_search_once, search_cap_init);
-  if (g_search_cap > 0) while (sem_wait (&g_search_slots) != 0) { }
-}
-static void
-search_leave (void)
-{
-  if (g_search_cap > 0) sem_post (&g_search_slots);
-}
-
 void
 schro_hierarchical_bm_scan_hint (SchroHierBm *hbm, int shift, int h_range)
 {
   Sb2hContext *cx = sb2h_context ();
   LevelIn in;
   prepare_level (cx, hbm, shift, &in);
-  search_enter ();
   fork_priority_stream (cx);
   launch_level (cx, hbm, shift, h_range, &in);
   sb2h_sync (cx);      /* the host field is read by the caller */
-  search_leave ();
 }
 
 void
@@ -255,7 +227,6 @@ schro_hbm_scan (SchroHierBm *hbm)
   const int n_levels = hbm->hierarchy_levels;
   SB2H_ASSERT (n_levels > 0);
   for (i = n_levels; 1 <= i; --i) prepare_level (cx, hbm, i, &in[i]);
-  search_enter ();
   fork_priority_stream (cx);
   /* the levels chain on the priority stream; one wait at the end makes all host fields valid */
   launch_level (cx, hbm, n_levels, half_scan_range, &in[n_levels]);
@@ -263,5 +234,4 @@ schro_hbm_scan (SchroHierBm *hbm)
   for (i = n_levels - 1; 1 <= i; --i, half_scan_range >>= 1)
     launch_level (cx, hbm, i, half_scan_range > 3 ? half_scan_range : 3, &in[i]);
   sb2h_sync (cx);
-  search_leave ();
 }
