@@ -612,24 +612,29 @@ def run_ours(args):
         barrier()
         e2e_steps = 0
         t0 = time.perf_counter()
-        while e2e_steps < args.steps or (time.perf_counter() - t0 < 3.0 and e2e_steps < 50 * args.steps):
+        # chunks of K steps until at least 3 s have been timed; the ranks decide together whether to go
+        # on, so that every rank times the same number of steps (max time over ranks / common step count)
+        while True:
             if args.e2e_driver == "native":
                 # the worker threads run the steps back to back (no barrier between two steps)
                 hf.drv.sb2_e2e_run(args.steps)
-                e2e_steps += args.steps
             else:
-                hf.step()
-                e2e_steps += 1
+                for _ in range(args.steps):
+                    hf.step()
+            e2e_steps += args.steps
+            go_on = time.perf_counter() - t0 < 3.0 and e2e_steps < 50 * args.steps
+            if world > 1:
+                t = torch.tensor([1.0 if go_on else 0.0], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                go_on = bool(t.item() > 0.5)
+            if not go_on:
+                break
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        if world > 1:
-            t = torch.tensor([float(e2e_steps)], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            e2e_steps = int(t.item())
         hf.close()
         e2e = {"value": B * e2e_steps * world / dt, "unit": "frames/s", "steps": e2e_steps,
                "h2d_bytes_per_step": hf.h2d * B, "d2h_bytes_per_step": hf.d2h * B,
