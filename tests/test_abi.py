@@ -38,3 +38,13 @@ def test_argument_errors_do_not_need_a_gpu():
     rc = s.lib.sb2_iwt_forward(ctypes.byref(slab), ctypes.byref(slab), 0, 1, 1, None, 0, None)
     assert rc != 0
     assert "slab" in s.last_error()
+
+
+def test_e2e_driver_loads_and_exports_its_entry_points():
+    """bench.py's pthread driver (bench_native/e2e_driver.c) links against the drop-in library;
+    it must load without a GPU (nothing runs until a job is started)."""
+    path = os.path.join(helpers.ROOT, "bench_native", "libsb2_e2e_driver.so")
+    assert os.path.exists(path), "run `make` (or __graft_entry__.build())"
+    drv = ctypes.CDLL(path)
+    for name in ("sb2_e2e_start", "sb2_e2e_run", "sb2_e2e_step", "sb2_e2e_times", "sb2_e2e_stop"):
+        assert hasattr(drv, name), name
