@@ -16,7 +16,7 @@ ORACLE_SRCS := $(wildcard oracle/oracle_*.c)
 
 all: schroedinger_b200/libschro_b200.so bench_native/libsb2_e2e_driver.so oracle/liboracle.so ref
 
-build/%.o: schroedinger_b200/csrc/%.cu schroedinger_b200/csrc/common.cuh include/schro_b200.h
+build/%.o: schroedinger_b200/csrc/%.cu $(wildcard schroedinger_b200/csrc/*.cuh) include/schro_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

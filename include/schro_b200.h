@@ -150,7 +150,10 @@ typedef struct {
  *                   consecutive pictures `mv_picture_pitch` VECTORS apart
  *   ref0 / ref1     upsampled (4-phase), edge-extended (extension >= 32) u8 references;
  *                   ref1 may be NULL when no block uses it
- *   acc             optional s16 slab receiving what the reference leaves in `dest`
+ *   acc             optional s16 slab receiving what the reference leaves in `dest`.  Its plane
+ *                   sizes are the rendered area (schromotion8.c:722-751 takes them from dest);
+ *                   residual / out may be larger (an iwt-padded addframe), never smaller.
+ *                   Without acc the area is that of out (add) or residual (subtract).
  *   add != 0        out(u8) = clamp(residual + ((acc+32)>>6)); residual s16 or s32
  *   add == 0        t = (acc-8160)>>6; acc := t; residual(s16) -= t */
 int sb2_obmc_render (const sb2_obmc_params *params, const void *motion_vectors,
@@ -168,6 +171,12 @@ typedef struct {
 } sb2_hbm_params;
 
 size_t sb2_hbm_workspace_bytes (int x_num_blocks, int y_num_blocks, int count);
+
+/* Two kernels implement a level: the skewed multi-row wavefront (hbm_wave.cu) for 8x8 blocks,
+ * 4:2:0 and a luma-only scan -- the codec's defaults -- and a generic one for everything else.
+ * on != 0 forces the generic kernel for every geometry (tests compare the two); the
+ * environment variable SB2_HBM_GENERIC=1 does the same. */
+void sb2_hbm_force_generic (int on);
 
 /* One level of hierarchical block matching for `count` independent (picture, reference)
  * pairs: schro_hierarchical_bm_scan_hint (schroedinger/schrohierbm.c:174-383), including

@@ -75,6 +75,7 @@ _opt("sb2_edgeextend_upsample", ctypes.c_int, [_SP, ctypes.c_int, ctypes.c_void_
 _opt("sb2_obmc_render", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, _SP, _SP, _SP,
                                       _SP, ctypes.c_int, ctypes.c_int, _SP, ctypes.c_void_p])
 _opt("sb2_hbm_workspace_bytes", ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int])
+_opt("sb2_hbm_force_generic", None, [ctypes.c_int])
 _opt("sb2_hbm_scan_hint", ctypes.c_int, [ctypes.c_void_p, _SP, _SP, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                         ctypes.c_size_t, ctypes.c_void_p])

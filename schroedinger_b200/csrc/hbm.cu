@@ -8,92 +8,22 @@
 // vectors of its left, upper and upper-left neighbours OF THE SAME LEVEL, so blocks form a
 // wavefront.  One CTA (2-16 warps) owns one block row of one (picture, reference) pair and
 // walks it left to right; a finished block publishes its vector as one relaxed 64-bit word
-// and the row below polls the two words it needs.  Rows are CTAs in launch order, so a row
-// only ever waits on a CTA that is already resident.  Many pairs run side by side in one
+// and the row below polls the two words it needs.  Rows take their index from an atomic ticket, so
+// a row only ever waits on a CTA that has already started.  Many pairs run side by side in one
 // launch to fill the machine.  Inside a block three lanes per candidate compute the ranking
 // SADs, the threads split the (2r+1)^2 scan positions; byte SADs use __vsadu4, reductions
 // use REDUX / warp shuffles.
 
-#include "common.cuh"
-#include <climits>
-#include <cstdio>
+#include "hbm_common.cuh"
+#include <cstdlib>
 
 namespace sb2 {
 
-struct MotionVector {               // == SchroMotionVector (schroedinger/schromotion.h:20-37)
-  uint32_t flags;
-  uint32_t metric;
-  uint32_t chroma_metric;
-  int16_t v[4];
-};
-
-struct HbmArgs {
-  PlaneSet src, ref;                // 3 u8 components each, edge-extended by `ext`
-  const MotionVector *parent;       // field of level shift+1 or nullptr
-  MotionVector *field;              // output field
-  size_t field_pitch;               // vectors between pictures
-  unsigned long long *words;        // [count][rows][cols] published results: bit 63 valid, dx<<16 | dy
-  int width, height;                // luma size of this pyramid level
-  int cw, ch;                       // chroma size
-  int hs, vs;
-  int ext;
-  int bw, bh;                       // xbsep_luma, ybsep_luma
-  int nbx, nby;
-  int ref_index;
-  int shift, h_range, use_chroma;
-  int rows, cols;                   // blocks at this level: ceil(nby/skip), ceil(nbx/skip)
-  int count;
-  uint32_t flags0;
-};
-
-__device__ __forceinline__ int clampi (int x, int lo, int hi) { return min (max (x, lo), hi); }
-
-__device__ __forceinline__ unsigned warp_sum (unsigned v)
-{
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync (0xffffffffu, v, o);
-  return v;
-}
-
-__device__ __forceinline__ unsigned long long warp_min64 (unsigned long long v)
-{
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long t = __shfl_xor_sync (0xffffffffu, v, o);
-    v = t < v ? t : v;
-  }
-  return v;
-}
-
-// SAD of a w x h block read straight from global memory (L1/texture path), one lane
-__device__ __forceinline__ unsigned block_sad (const uint8_t *a, int as, const uint8_t *b, int bs, int w, int h)
-{
-  unsigned s = 0;
-  if (w == 8 && (((size_t) a | (size_t) as) & 7) == 0 && (bs & 3) == 0) {
-    // byte-SIMD path: 8-wide source rows are 8-byte aligned (x0 is a multiple of xbsep);
-    // the reference row starts anywhere, so it is assembled from aligned words
-    for (int y = 0; y < h; y++) {
-      const uint2 av = __ldg (reinterpret_cast<const uint2 *> (a + (ptrdiff_t) y * as));   // needs 8-byte alignment
-      const uint8_t *br = b + (ptrdiff_t) y * bs;
-      const size_t mis = (size_t) br & 3;
-      const unsigned *bw_ = reinterpret_cast<const unsigned *> (br - mis);
-      const unsigned w0 = __ldg (bw_), w1 = __ldg (bw_ + 1), w2 = mis ? __ldg (bw_ + 2) : 0u;
-      const unsigned sh = (unsigned) mis * 8;
-      const unsigned b0 = __funnelshift_r (w0, w1, sh), b1 = __funnelshift_r (w1, w2, sh);
-      s += __vsadu4 (av.x, b0) + __vsadu4 (av.y, b1);
-    }
-    return s;
-  }
-  for (int y = 0; y < h; y++) {
-    const uint8_t *ar = a + (ptrdiff_t) y * as, *br = b + (ptrdiff_t) y * bs;
-    for (int x = 0; x < w; x++) s += (unsigned) abs ((int) __ldg (ar + x) - (int) __ldg (br + x));
-  }
-  return s;
-}
-
 __global__ void __launch_bounds__ (128)
-hbm_init_field_kernel (MotionVector *field, size_t n, uint32_t flags0, unsigned long long *words, size_t nwords)
+hbm_init_field_kernel (MotionVector *field, size_t n, uint32_t flags0, unsigned long long *words, size_t nwords,
+    unsigned *ticket)
 {
+  if (ticket && blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0;
   // the published-result words of the level start out invalid (same launch: one API call less per level)
   for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < nwords; i += (size_t) gridDim.x * blockDim.x)
     words[i] = 0;
@@ -105,67 +35,6 @@ hbm_init_field_kernel (MotionVector *field, size_t n, uint32_t flags0, unsigned 
     m.v[0] = m.v[1] = m.v[2] = m.v[3] = 0;
     field[i] = m;
   }
-}
-
-// Published block results.  A row's neighbours in the row below need only the vector of a
-// finished block, so the vector itself is the flag: one relaxed 64-bit word per block
-// (bit 63 = valid, dx in bits 16..31, dy in bits 0..15).  No fence on either side -- the
-// word is the data, single-copy atomic -- which takes two L2 round trips and two fences off
-// the per-block critical path compared with a progress counter + separate vector load.
-__device__ __forceinline__ unsigned long long ld_word (const unsigned long long *p)
-{
-  unsigned long long v;
-  asm volatile ("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_word (unsigned long long *p, unsigned long long v)
-{
-  asm volatile ("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long pack_word (int dx, int dy)
-{
-  return (1ull << 63) | ((unsigned long long) (dx & 0xffff) << 16) | (unsigned long long) (dy & 0xffff);
-}
-
-// 8 (or 4) bytes starting at any address, assembled from aligned 32-bit words
-__device__ __forceinline__ uint2 load8_unaligned (const uint8_t *p)
-{
-  const size_t mis = (size_t) p & 3;
-  const unsigned *w = reinterpret_cast<const unsigned *> (p - mis);
-  const unsigned w0 = __ldg (w), w1 = __ldg (w + 1), w2 = mis ? __ldg (w + 2) : 0u;
-  const unsigned sh = (unsigned) mis * 8;
-  return make_uint2 (__funnelshift_r (w0, w1, sh), __funnelshift_r (w1, w2, sh));
-}
-__device__ __forceinline__ unsigned load4_unaligned (const uint8_t *p)
-{
-  const size_t mis = (size_t) p & 3;
-  const unsigned *w = reinterpret_cast<const unsigned *> (p - mis);
-  const unsigned w0 = __ldg (w), w1 = mis ? __ldg (w + 1) : 0u;
-  return __funnelshift_r (w0, w1, (unsigned) mis * 8);
-}
-
-// The same with the alignment work hoisted out of the row loop: every row of a block starts at
-// the same byte offset inside its word (strides are multiples of 4), so the aligned base, the
-// shift and "needs a third word" are computed once per block position.
-struct RowRef { const unsigned *w; unsigned sh; bool three; };
-__device__ __forceinline__ RowRef row_ref (const uint8_t *p)
-{
-  RowRef r;
-  const unsigned mis = (unsigned) ((size_t) p & 3);
-  r.w = reinterpret_cast<const unsigned *> (p - mis);
-  r.sh = mis * 8;
-  r.three = mis != 0;
-  return r;
-}
-__device__ __forceinline__ uint2 row_load8 (const RowRef &r, int word_off)
-{
-  const unsigned w0 = __ldg (r.w + word_off), w1 = __ldg (r.w + word_off + 1), w2 = r.three ? __ldg (r.w + word_off + 2) : 0u;
-  return make_uint2 (__funnelshift_r (w0, w1, r.sh), __funnelshift_r (w1, w2, r.sh));
-}
-__device__ __forceinline__ unsigned row_load4 (const RowRef &r, int word_off)
-{
-  const unsigned w0 = __ldg (r.w + word_off), w1 = r.three ? __ldg (r.w + word_off + 1) : 0u;
-  return __funnelshift_r (w0, w1, r.sh);
 }
 
 #ifdef SB2_HBM_TRACE
@@ -193,6 +62,7 @@ struct BlockShared {
   StaticCands stc[2];
   Win win;
   int last_dx, last_dy;             // this row's previous block (the "left" candidate)
+  unsigned ticket;
   unsigned long long key[16];
   unsigned luma[16], chroma[16];
 };
@@ -218,7 +88,11 @@ hbm_level_kernel (const HbmArgs A)
   static_assert (NW >= 2, "one warp prepares the static candidates of the next block");
   __shared__ BlockShared sh;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row = blockIdx.x / A.count, pic = blockIdx.x % A.count;   // row r is launched before r+1
+  // (row, picture) from an atomic ticket: the CTA of the row above holds a smaller ticket, so it
+  // has started -- forward progress does not depend on the order CTAs are dispatched in
+  if (threadIdx.x == 0) sh.ticket = atomicAdd (A.ticket, 1u);
+  __syncthreads ();
+  const int row = (int) (sh.ticket / (unsigned) A.count), pic = (int) (sh.ticket % (unsigned) A.count);
   const int skip = 1 << A.shift, s = A.shift;
   const int j = row * skip;
   const int ri = A.ref_index;
@@ -645,11 +519,26 @@ sb2_sad_u8 (const uint8_t *a, int a_stride, const uint8_t *b, int b_stride, cons
   return sb2::check_cuda (cudaGetLastError (), "sad_batch_kernel launch");
 }
 
+// workspace: [ticket, 256 B][published words, 8 B per block][static candidates, 64 B per block]
+static size_t ws_words_bytes (size_t blocks) { return (blocks * sizeof (unsigned long long) + 255) & ~(size_t) 255; }
+
 extern "C" size_t
 sb2_hbm_workspace_bytes (int x_num_blocks, int y_num_blocks, int count)
 {
-  // one published word per block of the finest level (coarser levels use a prefix)
-  return (size_t) y_num_blocks * (size_t) x_num_blocks * (size_t) count * sizeof (unsigned long long) + 256;
+  const size_t blocks = (size_t) y_num_blocks * (size_t) x_num_blocks * (size_t) count;
+  return 256 + ws_words_bytes (blocks) + blocks * 64 + 256;
+}
+
+// 0: pick by geometry, 1: always the generic one-row-per-CTA kernel (tests force it to cover both)
+static int g_force_generic = -1;
+extern "C" void sb2_hbm_force_generic (int on) { g_force_generic = on ? 1 : 0; }
+static bool force_generic ()
+{
+  if (g_force_generic < 0) {
+    const char *v = getenv ("SB2_HBM_GENERIC");
+    g_force_generic = (v && *v && *v != '0') ? 1 : 0;
+  }
+  return g_force_generic != 0;
 }
 
 extern "C" int
@@ -694,41 +583,49 @@ sb2_hbm_scan_hint (const sb2_hbm_params *p, const sb2_slab *src_level, const sb2
   A.count = count;
   const int split = shift > 1 ? 0 : (shift == 1 ? 1 : 2);
   A.flags0 = (uint32_t) (p->ref_index + 1) | ((uint32_t) split << 3);
-  const size_t need = (size_t) A.rows * A.cols * count * sizeof (unsigned long long);
-  if (!workspace || workspace_bytes < need)
-    return set_error (SB2_ERR_WORKSPACE, "sb2_hbm_scan_hint: workspace %zu < %zu", workspace_bytes, need);
-  A.words = static_cast<unsigned long long *> (workspace);
+  const size_t blocks = (size_t) A.rows * A.cols * count;
+  const size_t nwords = blocks;
+  const bool wave = !force_generic () && hbm_wave_supported (A, h_range);
+  const size_t need = 256 + ws_words_bytes (blocks) + (wave ? hbm_wave_workspace_bytes (A.rows, A.cols, count) : 0);
+  if (!workspace || workspace_bytes < need || ((size_t) workspace & 7) != 0)
+    return set_error (SB2_ERR_WORKSPACE, "sb2_hbm_scan_hint: workspace %zu < %zu (or not 8-byte aligned)", workspace_bytes, need);
+  A.ticket = static_cast<unsigned *> (workspace);
+  A.words = reinterpret_cast<unsigned long long *> (static_cast<char *> (workspace) + 256);
+  void *stat_ws = static_cast<char *> (workspace) + 256 + ws_words_bytes (blocks);
   cudaStream_t st = as_stream (stream);
   const size_t nfield = (size_t) A.nbx * A.nby;
   if (field_picture_pitch == nfield || count == 1) {
     // contiguous fields: one launch initialises every pair's field
     LaunchScope scope ("hbm_init_field", (double) nfield * 20 * count, st);
     hbm_init_field_kernel<<<(unsigned) min ((size_t) 2048, (nfield * count + 127) / 128), 128, 0, st>>> (
-        A.field, nfield * count, A.flags0, A.words, need / sizeof (unsigned long long));
+        A.field, nfield * count, A.flags0, A.words, nwords, A.ticket);
   } else {
-    const size_t nwords = need / sizeof (unsigned long long) / count;
     for (int pic = 0; pic < count; pic++) {
       LaunchScope scope ("hbm_init_field", (double) nfield * 20, st);
       hbm_init_field_kernel<<<(unsigned) min ((size_t) 1024, (nfield + 127) / 128), 128, 0, st>>> (
-          A.field + (size_t) pic * field_picture_pitch, nfield, A.flags0, A.words + pic * nwords, nwords);
+          A.field + (size_t) pic * field_picture_pitch, nfield, A.flags0, A.words + pic * (nwords / count),
+          nwords / count, A.ticket);
     }
   }
   // algorithmic bytes: both pyramids of this level once + the fields
   double bytes = 0;
   for (int c = 0; c < 3; c++) bytes += 2.0 * src_level->width[c] * src_level->height[c] * count;
   bytes += (double) A.rows * A.cols * 20 * (parent_field ? 2 : 1) * count;
+  if (wave) {
+    const int rc = hbm_wave_launch (A, h_range, stat_ws, workspace_bytes - (256 + ws_words_bytes (blocks)), st, bytes);
+    if (rc != SB2_OK) return rc;
+    return check_cuda (cudaGetLastError (), "hbm_wave_kernel launch");
+  }
   const int ctas = A.rows * count;
   const int npos = (2 * h_range + 1) * (2 * h_range + 1);
   {
     char tag[48];
-    snprintf (tag, sizeof (tag), "hbm_level_s%d_r%d", shift, h_range);
+    snprintf (tag, sizeof (tag), "hbm_generic_s%d_r%d", shift, h_range);
     LaunchScope scope (tag, bytes, st);
     // warps per block row: enough threads to cover the scan positions in few rounds -- unless the
     // launch has more rows than the GPU can hold at that width (148 SMs x 1024 threads at the 64
-    // register cap): then half as many warps per row keeps twice as many rows resident, which
-    // is worth more than the extra scan rounds (rows mostly wait on their neighbours)
+    // register cap): then half as many warps per row keeps twice as many rows resident
     int nw = npos <= 64 ? 2 : npos <= 128 ? 4 : npos <= 512 ? 8 : 16;
-    // (measured at 32 pictures: levels 2 / 3 / 4 1.38 / 0.75 / 0.43 -> 1.22 / 0.66 / 0.40 ms)
     while (nw > 2 && (long long) ctas * nw * 32 > 148LL * 1024) nw >>= 1;
     if (nw == 2) hbm_level_kernel<2><<<ctas, 64, 0, st>>> (A);
     else if (nw == 4) hbm_level_kernel<4><<<ctas, 128, 0, st>>> (A);

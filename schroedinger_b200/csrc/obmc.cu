@@ -867,10 +867,22 @@ sb2_obmc_render (const sb2_obmc_params *p, const void *motion_vectors, size_t mv
   A.has_acc = acc != nullptr;
   int maxw = 0, maxh = 0;
   double bytes = 0;
+  // The rendered area is that of `dest` (schromotion8.c:722-751: motion->width = comp->width of
+  // dest), i.e. of `acc`; callers pass a picture-size dest with an iwt-padded (taller) addframe
+  // (schrodecoder.c:1784, schroencoder.c:2447).  Without an acc slab the output (or, in the
+  // subtract direction, the residual) gives the size.  No plane may be smaller than that area.
+  const sb2_slab *area = acc ? acc : (add ? out : residual);
+  for (int c = 0; c < ncomp; c++) {
+    const sb2_slab *all[3] = { residual, out, acc };
+    for (const sb2_slab *s : all)
+      if (s && (s->width[c] < area->width[c] || s->height[c] < area->height[c]))
+        return set_error (SB2_ERR_ARG, "sb2_obmc_render: component %d: a %dx%d plane is smaller than the %dx%d render area",
+            c, s->width[c], s->height[c], area->width[c], area->height[c]);
+  }
   for (int c = 0; c < SB2_MAX_COMPONENTS; c++) {
     const int hs = c ? p->chroma_h_shift : 0, vs = c ? p->chroma_v_shift : 0;
-    A.w[c] = c < ncomp ? residual->width[c] : 0;
-    A.h[c] = c < ncomp ? residual->height[c] : 0;
+    A.w[c] = c < ncomp ? area->width[c] : 0;
+    A.h[c] = c < ncomp ? area->height[c] : 0;
     A.hs[c] = hs;
     A.vs[c] = vs;
     A.xbsep[c] = p->xbsep >> hs;

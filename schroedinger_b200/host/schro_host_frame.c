@@ -356,7 +356,7 @@ schro_motion_render_u8 (SchroMotion *motion, SchroFrame *dest, SchroFrame *addfr
   dmv = sb2h_dev_buffer (cx, SB2H_BUF_AUX3, nmv * sizeof (SchroMotionVector));
   SB2H_CUDA (cudaMemcpyAsync (dmv, motion->motion_vectors, nmv * sizeof (SchroMotionVector),
           cudaMemcpyDefault, cx->stream));
-  /* the kernel sizes its grid from the residual slab: all frames share the picture size */
+  /* the rendered area is dest's (schromotion8.c:722-751); addframe may be iwt-padded */
   SB2H_CHECK (sb2_obmc_render (&p, dmv, nmv, &r0.slab, motion->src2 ? &r1.slab : NULL, &acc.slab,
           &res.slab, res_is_s32, add, output_frame ? &out.slab : NULL, cx->stream), "sb2_obmc_render");
   stage_out (cx, &acc);

@@ -14,6 +14,37 @@ ORACLE = helpers.load_oracle()
 GOLD = np.load(os.path.join(helpers.GOLDEN_DIR, "hbm.npz"))
 
 
+@pytest.fixture(params=["wave", "generic"], autouse=True)
+def hbm_kernel(request):
+    """Every test of this file runs twice: with the kernel the library picks (the skewed wavefront
+    for 8x8 / 4:2:0 / luma-only scans) and with the generic one-row-per-CTA kernel forced."""
+    from schroedinger_b200 import lib
+    lib.sb2_hbm_force_generic(1 if request.param == "generic" else 0)
+    yield request.param
+    lib.sb2_hbm_force_generic(0)
+
+
+def launched_tags(fn):
+    """Run fn with per-launch profiling on; return the set of kernel tags it launched."""
+    import ctypes
+    from schroedinger_b200 import lib
+    lib.sb2_profile_reset()
+    lib.sb2_profile_enable(1)
+    try:
+        fn()
+        torch.cuda.synchronize()
+    finally:
+        lib.sb2_profile_enable(0)
+    tags = set()
+    buf = ctypes.create_string_buffer(64)
+    ms, by = ctypes.c_float(), ctypes.c_double()
+    for i in range(lib.sb2_profile_count()):
+        lib.sb2_profile_get(i, buf, 64, ctypes.byref(ms), ctypes.byref(by))
+        tags.add(buf.value.decode())
+    lib.sb2_profile_reset()
+    return tags
+
+
 def gpu_hbm(pairs, width, height, levels, use_chroma=0, ref_index=0, xbsep=8, ybsep=8, level0_range=3):
     """pairs: list of (src_planes, ref_planes); all pairs run in one slab / one launch per level."""
     from schroedinger_b200 import device as dev
@@ -70,6 +101,71 @@ def test_hbm_matches_oracle(cuda, case):
     got, _ = gpu_hbm([(s, r)], w, h, lv, uc, ri)
     for f in ("flags", "metric", "chroma_metric", "v"):
         assert np.array_equal(got[0][f], want[f]), (case, f)
+
+
+def test_hbm_kernel_selection(cuda, hbm_kernel):
+    """The codec's default geometry runs on the wavefront kernel, chroma ME / forced runs on the
+    generic one (so the parametrised tests above really cover both)."""
+    w, h, lv = 176, 144, 2
+    s, r = helpers.panning_pair(w, h, np.random.default_rng(9), (2, 1))
+    tags = launched_tags(lambda: gpu_hbm([(s, r)], w, h, lv))
+    if hbm_kernel == "wave":
+        assert any(t.startswith("hbm_level_s") for t in tags) and "hbm_static" in tags, tags
+        assert not any(t.startswith("hbm_generic") for t in tags), tags
+        tags = launched_tags(lambda: gpu_hbm([(s, r)], w, h, lv, use_chroma=1))
+    assert any(t.startswith("hbm_generic_s") for t in tags) and "hbm_static" not in tags, tags
+
+
+@pytest.mark.parametrize("case", [(90, 50, 2, (1, 1)), (172, 100, 3, (-3, 2)), (328, 200, 3, (7, -5)),
+                                  (1000, 540, 4, (5, 3))])
+def test_hbm_incoherent_content(cuda, case):
+    """Unrelated noise pictures: every neighbour proposes a different vector, so the ranking of
+    left / up / up-left and the de-duplication are exercised on every block; sizes leave partial
+    blocks at the right and bottom edges of several levels."""
+    w, h, lv, pan = case
+    rng = np.random.default_rng(w * 7 + h)
+    s, r = helpers.panning_pair(w, h, rng, pan, noise=60)
+    r = [rng.integers(0, 256, size=a.shape).astype(np.uint8) if k == 0 else a for k, a in enumerate(r)]
+    want, _, _ = helpers.oracle_hbm(ORACLE, s, r, w, h, levels=lv)
+    got, _ = gpu_hbm([(s, r)], w, h, lv)
+    for f in ("flags", "metric", "chroma_metric", "v"):
+        assert np.array_equal(got[0][f], want[f]), (case, f)
+
+
+@pytest.mark.parametrize("h_range", [1, 2, 3, 4, 5, 7, 10, 13, 20])
+def test_hbm_single_level_ranges(cuda, h_range):
+    """schro_hierarchical_bm_scan_hint called directly with every class of scan range (the
+    wavefront kernel has one instantiation per class) on a level with a parent field."""
+    import ctypes
+    from schroedinger_b200 import device as dev
+    w, h, lv = 232, 136, 2
+    s, r = helpers.panning_pair(w, h, np.random.default_rng(77 + h_range), (9, -6), noise=8)
+    ps = helpers.build_pyramid(ORACLE, "oracle", s, lv, ext=8)
+    pr = helpers.build_pyramid(ORACLE, "oracle", r, lv, ext=8)
+    nbx, nby = helpers.hbm_block_counts(w, h, 8, 8)
+    fn = ORACLE.oracle_hbm_scan_hint
+    fn.restype = None
+    want = np.zeros((lv + 1, nbx * nby), dtype=helpers.MV_DTYPE)
+    for (l, hr) in ((2, 20), (1, h_range)):
+        a, b = helpers.pyr_level_struct(ps[l]), helpers.pyr_level_struct(pr[l])
+        parent = want[l + 1].ctypes.data_as(ctypes.c_void_p) if l < lv else None
+        fn(ctypes.byref(a), ctypes.byref(b), 8, 8, nbx, nby, 0, l, hr, 0, parent,
+           want[l].ctypes.data_as(ctypes.c_void_p))
+    gs, gr = dev.Pyramid(w, h, 1, lv, 8), dev.Pyramid(w, h, 1, lv, 8)
+    for c in range(3):
+        gs.slabs[0].upload(0, c, s[c])
+        gr.slabs[0].upload(0, c, r[c])
+    gs.build()
+    gr.build()
+    prm = dev.HbmParams(8, 8, nbx, nby, 0, 0, 1, 1)
+    f2 = torch.empty(nbx * nby * 20, dtype=torch.uint8, device="cuda")
+    f1 = torch.empty(nbx * nby * 20, dtype=torch.uint8, device="cuda")
+    dev.hbm_scan_hint(prm, gs.slabs[2], gr.slabs[2], 2, 20, None, f2)
+    dev.hbm_scan_hint(prm, gs.slabs[1], gr.slabs[1], 1, h_range, f2, f1)
+    torch.cuda.synchronize()
+    got = f1.cpu().numpy().view(helpers.MV_DTYPE)
+    for f in ("flags", "metric", "chroma_metric", "v"):
+        assert np.array_equal(got[f], want[1][f]), (h_range, f)
 
 
 def test_sad_primitive(cuda):

@@ -1,3 +1,6 @@
+"""Development aid: per-step cycle breakdown of the wavefront block matcher (clock64 trace of one warp,
+level 0, row group 10, picture 0).  Build with `make EXTRA_NVFLAGS=-DSB2_HBM_TRACE` first.
+usage: python tools/hbm_trace.py [batch] [content]"""
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, bench
@@ -7,13 +10,12 @@ bench.CONTENT = sys.argv[2] if len(sys.argv) > 2 else "natural"
 st = bench.Stages(spec, torch, dev)
 for _ in range(3): st.step()
 torch.cuda.synchronize()
-buf = np.zeros(512 * 8, np.int64)
-lib.sb2_hbm_trace_read(buf.ctypes.data_as(ctypes.c_void_p), 512 * 8)
-t = buf.reshape(512, 8)[50:450]
+buf = np.zeros(1024 * 8, np.int64)
+lib.sb2_hbm_wave_trace_read(buf.ctypes.data_as(ctypes.c_void_p), 1024 * 8)
+t = buf.reshape(1024, 8)[20:460]
 d = np.diff(t[:, :7], axis=1)
-names = ["A static cands", "poll+dedup", "rank (nbr SADs)", "seed+sync", "scan", "reduce+sync+sel"]
-print("batch", spec["batch"], bench.CONTENT, "per-block cycles (row 100, level 0), median / mean:")
-for k, n in enumerate(names): print(f"  {n:18s} {np.median(d[:,k]):8.0f} {d[:,k].mean():8.0f}")
+names = ["neighbours (shfl / poll)", "match + twins", "rank (neighbour SADs)", "winner + window", "src rows + scan", "min-reduce"]
+print("batch", spec["batch"], bench.CONTENT, "per-step cycles (level 0, row group 10), median / mean:")
+for k, n in enumerate(names): print(f"  {n:26s} {np.median(d[:,k]):8.0f} {d[:,k].mean():8.0f}")
 tot = np.diff(t[:, 0])
-print("  block-to-block     ", np.median(tot), tot.mean())
-
+print("  step-to-step              ", np.median(tot), tot.mean())
