@@ -587,8 +587,8 @@ sb2_hbm_scan_hint (const sb2_hbm_params *p, const sb2_slab *src_level, const sb2
   const size_t nwords = blocks;
   const bool wave = !force_generic () && hbm_wave_supported (A, h_range);
   const size_t need = 256 + ws_words_bytes (blocks) + (wave ? hbm_wave_workspace_bytes (A.rows, A.cols, count) : 0);
-  if (!workspace || workspace_bytes < need || ((size_t) workspace & 7) != 0)
-    return set_error (SB2_ERR_WORKSPACE, "sb2_hbm_scan_hint: workspace %zu < %zu (or not 8-byte aligned)", workspace_bytes, need);
+  if (!workspace || workspace_bytes < need || ((size_t) workspace & 15) != 0)
+    return set_error (SB2_ERR_WORKSPACE, "sb2_hbm_scan_hint: workspace %zu < %zu (or not 16-byte aligned)", workspace_bytes, need);
   A.ticket = static_cast<unsigned *> (workspace);
   A.words = reinterpret_cast<unsigned long long *> (static_cast<char *> (workspace) + 256);
   void *stat_ws = static_cast<char *> (workspace) + 256 + ws_words_bytes (blocks);
