@@ -146,6 +146,36 @@ def make_mv_field(nbx, nby, rng):
 CONTENT = "natural"
 
 
+_CANVAS = {}
+CANVAS_MARGIN = 32
+
+
+def _texture_canvas(width, height):
+    """The noise-free luma texture on a canvas CANVAS_MARGIN pixels larger than the picture on every side
+    (computed once per size: panned pictures are crops of it)."""
+    key = (width, height, CONTENT)
+    if key not in _CANVAS:
+        m = CANVAS_MARGIN
+        yy, xx = np.mgrid[-m:height + m, -m:width + m]
+        xx = xx.astype(np.float32)
+        yy = yy.astype(np.float32)
+        if CONTENT == "periodic":
+            y = 128 + 50 * np.sin(xx / 9.0) * np.cos(yy / 7.0) + 30 * np.sin((xx + 2 * yy) / 31.0)
+        else:
+            wrng = np.random.default_rng(424242)                 # the texture itself is the same for every frame
+            lam = np.exp(wrng.uniform(np.log(24.0), np.log(600.0), 20))
+            ang = wrng.uniform(0, 2 * np.pi, 20)
+            ph = wrng.uniform(0, 2 * np.pi, 20)
+            amp = lam ** 0.6
+            amp *= 45.0 / np.sqrt(0.5 * np.sum(amp ** 2))
+            y = np.full(xx.shape, 128.0, np.float32)
+            for k in range(20):
+                kx, ky = 2 * np.pi / lam[k] * np.cos(ang[k]), 2 * np.pi / lam[k] * np.sin(ang[k])
+                y += np.float32(amp[k]) * np.sin(np.float32(kx) * xx + np.float32(ky) * yy + np.float32(ph[k]))
+        _CANVAS[key] = y.astype(np.float32)
+    return _CANVAS[key]
+
+
 def textured_frame(width, height, rng, pan=(0, 0)):
     """One u8 4:2:0 picture: smooth texture + per-frame noise, optionally panned.
 
@@ -153,26 +183,19 @@ def textured_frame(width, height, rng, pan=(0, 0)):
     amplitude rising with wavelength -- no repeat inside any search window, so block matching finds the pan.
     "periodic": the round-1a texture, one 56 x 44 px cell repeated; its aliases at the coarse pyramid levels
     make the motion field incoherent (a worst case for the block matcher, kept for DESIGN.md's comparison)."""
-    yy, xx = np.mgrid[0:height, 0:width]
-    xx = (xx + pan[0]).astype(np.float32)
-    yy = (yy + pan[1]).astype(np.float32)
-    if CONTENT == "periodic":
-        y = 128 + 50 * np.sin(xx / 9.0) * np.cos(yy / 7.0) + 30 * np.sin((xx + 2 * yy) / 31.0)
-    else:
-        wrng = np.random.default_rng(424242)                 # the texture itself is the same for every frame
-        lam = np.exp(wrng.uniform(np.log(24.0), np.log(600.0), 20))
-        ang = wrng.uniform(0, 2 * np.pi, 20)
-        ph = wrng.uniform(0, 2 * np.pi, 20)
-        amp = lam ** 0.6
-        amp *= 45.0 / np.sqrt(0.5 * np.sum(amp ** 2))
-        y = np.full((height, width), 128.0, np.float32)
-        for k in range(20):
-            kx, ky = 2 * np.pi / lam[k] * np.cos(ang[k]), 2 * np.pi / lam[k] * np.sin(ang[k])
-            y += np.float32(amp[k]) * np.sin(np.float32(kx) * xx + np.float32(ky) * yy + np.float32(ph[k]))
+    m = CANVAS_MARGIN
+    assert abs(pan[0]) <= m and abs(pan[1]) <= m
+    canvas = _texture_canvas(width, height)
+    y = canvas[m + pan[1]:m + pan[1] + height, m + pan[0]:m + pan[0] + width]
     y = y + rng.integers(-12, 13, size=(height, width))
     y = np.clip(y, 0, 255).astype(np.uint8)
     c = y[::2, ::2]
     return [y, np.ascontiguousarray(255 - c), np.ascontiguousarray((c // 2 + 64).astype(np.uint8))]
+
+
+def picture_pan(i):
+    """Every picture of a batch moves differently against its reference: (5,3) +- (2,1) pixels."""
+    return (5 + (i % 5) - 2, 3 + (i % 3) - 1)
 
 
 HBM_LEVELS = 4
@@ -197,12 +220,10 @@ class Stages:
         lay = dev.FrameLayout.yuv420(spec["depth_name"], spec["iwt_w"], spec["iwt_h"])
         self.coef = dev.PictureSlab(lay, B, zero=False)
         self.recon = dev.PictureSlab(lay, B, zero=False)
-        planes = make_coeff_frame(spec, rng)
-        for c in range(3):
-            self.coef.upload(0, c, planes[c])
-        one = self.coef.buf[:lay.pitch]
-        for p in range(1, B):
-            self.coef.buf[p * lay.pitch:(p + 1) * lay.pitch].copy_(one)
+        for p in range(B):                                   # every picture of the batch is different
+            planes = make_coeff_frame(spec, np.random.default_rng(2026 + p))
+            for c in range(3):
+                self.coef.upload(p, c, planes[c])
         self.ws = dev.Workspace()
         ncoef = sum(w * h for w, h in lay.comp_sizes)
         self.working_set = self.coef.nbytes + self.recon.nbytes
@@ -225,20 +246,17 @@ class Stages:
         ref_lay = dev.FrameLayout.yuv420("u8", W, H, 32, True)
         self.refs = [dev.PictureSlab(ref_lay, B) for _ in range(2)]
         self.newref = dev.PictureSlab(ref_lay, B)          # the decoded picture = next reference
-        base = textured_frame(W, H, rng)
         for r, slab in enumerate(self.refs):
-            fr = textured_frame(W, H, rng, pan=(5 * r, 3 * r))
-            for c in range(3):
-                slab.upload(0, c, fr[c])
-            one = slab.buf[:ref_lay.pitch]
-            for p in range(1, B):
-                slab.buf[p * ref_lay.pitch:(p + 1) * ref_lay.pitch].copy_(one)
+            for p in range(B):
+                fr = textured_frame(W, H, np.random.default_rng(3000 + 100 * r + p), pan=(5 * r, 3 * r))
+                for c in range(3):
+                    slab.upload(p, c, fr[c])
             dev.mc_edgeextend(slab)
             dev.upsample(slab)
         nbx, nby = block_counts(W, H)
         self.nblocks = nbx * nby
-        mv = make_mv_field(nbx, nby, rng)
-        self.mvs = torch.from_numpy(np.tile(mv.view(np.uint8), B)).cuda()
+        self.mvs = torch.from_numpy(np.concatenate(
+            [make_mv_field(nbx, nby, np.random.default_rng(4000 + p)).view(np.uint8) for p in range(B)])).cuda()
         self.obmc_params = dev.ObmcParams(BLOCK["xbsep"], BLOCK["ybsep"], BLOCK["xblen"], BLOCK["yblen"],
                                           nbx, nby, BLOCK["prec"], 1, 1, 1, 1, 1)
         self.resid = dev.SlabView(self.recon, [(W, H), (W // 2, H // 2), (W // 2, H // 2)])
@@ -255,14 +273,12 @@ class Stages:
         # ---- stage 4: motion estimation: pyramids + hierarchical block matching vs ref 0 ----
         self.src_pyr = dev.Pyramid(W, H, B, HBM_LEVELS, 8)
         self.ref_pyr = dev.Pyramid(W, H, B, HBM_LEVELS, 8)
-        srcf = textured_frame(W, H, rng, pan=(5, 3))
-        for pyr, fr in ((self.src_pyr, srcf), (self.ref_pyr, base)):
-            for c in range(3):
-                pyr.slabs[0].upload(0, c, fr[c])
-            l0 = pyr.slabs[0]
-            one = l0.buf[:l0.layout.pitch]
-            for p in range(1, B):
-                l0.buf[p * l0.layout.pitch:(p + 1) * l0.layout.pitch].copy_(one)
+        for p in range(B):                                   # own noise and own pan for every pair
+            srcf = textured_frame(W, H, np.random.default_rng(5000 + p), pan=picture_pan(p))
+            base = textured_frame(W, H, np.random.default_rng(6000 + p))
+            for pyr, fr in ((self.src_pyr, srcf), (self.ref_pyr, base)):
+                for c in range(3):
+                    pyr.slabs[0].upload(p, c, fr[c])
         self.hbm_params = dev.HbmParams(BLOCK["xbsep"], BLOCK["ybsep"], nbx, nby, 0, 0, 1, 1)
         self.fields = [torch.empty(B * self.nblocks * 20, dtype=torch.uint8, device="cuda")
                        for _ in range(HBM_LEVELS + 1)]
@@ -325,11 +341,14 @@ class HostFrames:
     the motion fields come back D2H; reference pictures stay in the CUDA memory domain
     (as with the reference's own use_cuda path, schrodecoder.c:1731-1736)."""
 
-    def __init__(self, spec, lib, nthreads):
+    def __init__(self, spec, lib, nthreads, widen=True):
+        """widen: the coefficients travel QUANTISED as s16 and are dequantised into the s32 coefficient
+        frame on the device (schro_b200_frame_dequantise_widen) -- half the upload of the s32 frame."""
         from schroedinger_b200 import compat
         self.compat, self.lib, self.spec = compat, lib, spec
         self.nthreads = nthreads
         self.full = spec.get("full_core", True)
+        self.widen = bool(widen and self.full and spec["depth_name"] == "s32")
         B = spec["batch"]
         W, H = spec["width"], spec["height"]
         import torch
@@ -339,17 +358,40 @@ class HostFrames:
         s32 = spec["depth_name"] == "s32"
         cfmt = compat.FORMAT_S32_420 if s32 else compat.FORMAT_S16_420
         rng = np.random.default_rng(7)
-        planes = make_coeff_frame(spec, rng)
         A = compat.frame_new_and_alloc
-        self.coef_host = []
-        for _ in range(B):
-            f = A(self.pinned, cfmt, spec["iwt_w"], spec["iwt_h"])
-            for c in range(3):
-                compat.frame_plane(f, c)[...] = planes[c]
-            self.coef_host.append(f)
         self.params = compat.make_params(W, H, spec["filter"], spec["transform_depth"], spec["iwt_w"],
                                          spec["iwt_h"], num_refs=2, **{k: BLOCK[k] for k in ("xbsep", "ybsep", "xblen", "yblen")},
                                          mv_precision=BLOCK["prec"])
+        self.coef_host, self.coef16_host, self.pairs = [], [], None
+        for i in range(B):
+            planes = make_coeff_frame(spec, np.random.default_rng(7000 + i))       # every picture differs
+            if self.widen:
+                # quantised values; with quantiser index 12 (factor 32: 8 x the value) the dequantised
+                # coefficients span the same +-512 as the s32 frames of the other leg
+                f = A(self.pinned, compat.FORMAT_S16_420, spec["iwt_w"], spec["iwt_h"])
+                for c in range(3):
+                    compat.frame_plane(f, c)[...] = (planes[c] >> 3).astype(np.int16)
+                self.coef16_host.append(f)
+            else:
+                f = A(self.pinned, cfmt, spec["iwt_w"], spec["iwt_h"])
+                for c in range(3):
+                    compat.frame_plane(f, c)[...] = planes[c]
+                self.coef_host.append(f)
+        if self.widen:
+            gold = np.load(os.path.join(ROOT, "tests", "golden", "dequant.npz"))
+            depth = spec["transform_depth"]
+            for l in range(depth + 1):
+                self.params.horiz_codeblocks[l] = self.params.vert_codeblocks[l] = 1 if l < 2 else min(8, 1 << (l - 1))
+            from schroedinger_b200._lib import DequantParams
+            dp = DequantParams()
+            dp.transform_depth = depth
+            for l in range(7):
+                dp.horiz_codeblocks[l] = self.params.horiz_codeblocks[l] if l <= depth else 1
+                dp.vert_codeblocks[l] = self.params.vert_codeblocks[l] if l <= depth else 1
+            npairs = lib.sb2_dequant_table_pairs(ctypes.byref(dp), 3)
+            self.pairs = np.empty((npairs, 2), np.int32)
+            self.pairs[:, 0] = int(gold["table_quant"][12])
+            self.pairs[:, 1] = int(gold["table_offset_1_2"][12]) + 2
         bpp = 4 if s32 else 2
         self.h2d = int(spec["iwt_w"] * spec["iwt_h"] * 1.5 * bpp)
         self.d2h = self.h2d
@@ -357,8 +399,9 @@ class HostFrames:
             return
         npix = W * H * 3 // 2
         nb = self.params.x_num_blocks * self.params.y_num_blocks
-        self.h2d = int(spec["iwt_w"] * spec["iwt_h"] * 1.5 * bpp) + npix + nb * 20
-        self.d2h = npix + nb * 20 * (HBM_LEVELS + 1)
+        coef_bytes = int(spec["iwt_w"] * spec["iwt_h"] * 1.5 * (2 if self.widen else bpp))
+        self.h2d = coef_bytes + (self.pairs.nbytes if self.widen else 0) + npix + nb * 20
+        self.d2h = npix + nb * 20                       # decoded picture + the level-0 motion field
         # reference pictures and the reference pyramid live on the device
         self.refs = []
         for r in range(2):
@@ -380,9 +423,9 @@ class HostFrames:
         lib.schro_frame_to_gpu(self.ref_pyr[0], hf)
         lib.schro_frame_unref(hf)
         self._build_pyramid(self.ref_pyr)
-        srcf = textured_frame(W, H, rng, pan=(5, 3))
         self.src_host, self.out_host = [], []
-        for _ in range(B):
+        for i in range(B):
+            srcf = textured_frame(W, H, np.random.default_rng(7100 + i), pan=picture_pan(i))
             f = A(self.pinned, compat.FORMAT_U8_420, W, H, 0, 0)
             for c in range(3):
                 compat.frame_plane(f, c)[...] = srcf[c]
@@ -394,14 +437,8 @@ class HostFrames:
         for _ in range(nthreads):
             t = {}
             t["coef"] = A(self.cuda, cfmt, spec["iwt_w"], spec["iwt_h"])
-            # the picture-size window of the coefficient frame (same memory)
-            view = compat.SchroFrame()
-            ctypes.memmove(ctypes.byref(view), t["coef"], ctypes.sizeof(view))
-            view.refcount, view.height = 1, H
-            for c in range(3):
-                view.components[c].height = H if c == 0 else H // 2
-            view.regions[0], view.domain = t["coef"].contents.regions[0], None
-            t["resid"] = view
+            if self.widen:
+                t["coef16"] = A(self.cuda, compat.FORMAT_S16_420, spec["iwt_w"], spec["iwt_h"])
             t["acc"] = A(self.cuda, compat.FORMAT_S16_420, W, H)
             t["out"] = A(self.cuda, compat.FORMAT_U8_420, W, H, 32, 1)
             t["motion"] = lib.schro_motion_new(ctypes.byref(self.params), self.refs[0], self.refs[1])
@@ -431,14 +468,15 @@ class HostFrames:
             lib.schro_frame_inverse_iwt_transform(self.coef_host[i], ctypes.byref(self.params))
             return
         # decode side: coefficients in, decoded picture out
-        lib.schro_frame_to_gpu(th["coef"], self.coef_host[i])
+        if self.widen:
+            lib.schro_frame_to_gpu(th["coef16"], self.coef16_host[i])
+            lib.schro_b200_frame_dequantise_widen(th["coef"], th["coef16"], ctypes.byref(self.params),
+                                                  self.pairs.ctypes.data_as(ctypes.c_void_p))
+        else:
+            lib.schro_frame_to_gpu(th["coef"], self.coef_host[i])
         lib.schro_frame_inverse_iwt_transform(th["coef"], ctypes.byref(self.params))
-        # the transform may have swapped the frame's device region: refresh the picture-size window
-        view, cf = th["resid"], th["coef"].contents
-        view.regions[0] = cf.regions[0]
-        for c in range(3):
-            view.components[c].data = cf.components[c].data
-        lib.schro_motion_render(th["motion"], th["acc"], ctypes.byref(view), 1, th["out"])
+        # dest (picture size) gives the rendered area, the iwt-padded coefficient frame is the addframe
+        lib.schro_motion_render(th["motion"], th["acc"], th["coef"], 1, th["out"])
         lib.schro_frame_mc_edgeextend(th["out"])
         th["out"].contents.upsample_done = 0
         lib.schro_upsampled_frame_upsample(th["out"])
@@ -451,6 +489,7 @@ class HostFrames:
                                             arr(*th["src_pyr"]), arr(*self.ref_pyr))
         lib.schro_hbm_scan(hbm)
         lib.schro_hierarchical_bm_scan_hint(hbm, 0, 3)
+        lib.schro_hbm_motion_field(hbm, 0)               # the host reads the finest field
         lib.schro_hbm_unref(hbm)
 
     def native_start(self):
@@ -461,7 +500,7 @@ class HostFrames:
             raise RuntimeError(path + " is missing: run `make` (or __graft_entry__.build())")
         drv = ctypes.CDLL(path)
         compat = self.compat
-        FP, n, T = compat.FrameP, len(self.coef_host), self.nthreads
+        FP, n, T = compat.FrameP, self.spec["batch"], self.nthreads
 
         class Job(ctypes.Structure):
             _fields_ = [("nthreads", ctypes.c_int), ("npictures", ctypes.c_int), ("levels", ctypes.c_int),
@@ -472,7 +511,9 @@ class HostFrames:
                         ("coef_dev", ctypes.POINTER(FP)), ("acc_dev", ctypes.POINTER(FP)),
                         ("out_dev", ctypes.POINTER(FP)),
                         ("motion", ctypes.POINTER(ctypes.POINTER(compat.SchroMotion))),
-                        ("src_pyr", ctypes.POINTER(FP))]
+                        ("src_pyr", ctypes.POINTER(FP)), ("widen", ctypes.c_int),
+                        ("coef16_host", ctypes.POINTER(FP)), ("coef16_dev", ctypes.POINTER(FP)),
+                        ("pairs", ctypes.c_void_p)]
 
         def arr(frames):
             a = (FP * max(1, len(frames)))(*frames)
@@ -485,6 +526,11 @@ class HostFrames:
         job.pic_height, job.full_core = self.spec["height"], int(self.full)
         job.params = ctypes.pointer(self.params)
         job.coef_host = arr(self.coef_host)
+        job.widen = int(self.widen)
+        if self.widen:
+            job.coef16_host = arr(self.coef16_host)
+            job.coef16_dev = arr([t["coef16"] for t in self.th])
+            job.pairs = self.pairs.ctypes.data
         if self.full:
             job.src_host, job.out_host, job.ref_pyr = arr(self.src_host), arr(self.out_host), arr(self.ref_pyr)
             job.coef_dev = arr([t["coef"] for t in self.th])
@@ -509,7 +555,7 @@ class HostFrames:
         if hasattr(self, "drv"):
             self.drv.sb2_e2e_step()
             return
-        n = len(self.coef_host)
+        n = self.spec["batch"]
         if not hasattr(self, "pool"):
             from concurrent.futures import ThreadPoolExecutor
             self.pool = ThreadPoolExecutor(max_workers=self.nthreads)
@@ -541,6 +587,44 @@ class HostFrames:
             del self.pool
 
 
+METRIC = "frames/s at 2160p 4:2:0 (wavelet+OBMC+SAD); HBM GB/s as % of B200 peak"
+
+
+def stage_names(spec):
+    if spec.get("full_core", True):
+        return ["iwt_inverse", "obmc_render", "upsample", "pyramid", "hier_block_match"]
+    return ["iwt_inverse"]
+
+
+def common_config(args, spec):
+    """The `config` object: identical in both arms (ours / --impl reference), functions of the workload only."""
+    bpp = 4 if spec["depth_name"] == "s32" else 2
+    B = spec["batch"]
+    ws = 2 * spec["iwt_w"] * spec["iwt_h"] * 1.5 * bpp * B
+    if spec.get("full_core", True):
+        ref_bytes = 4 * (spec["width"] + 64) * (spec["height"] + 64) * 1.5
+        ws += 3 * ref_bytes * B
+    return {"workload": args.workload, "what": spec["label"], "content": args.content, "batch_per_gpu": B,
+            "stages": stage_names(spec),
+            "pictures": "every picture of a batch differs (own coefficients, noise, motion field, pan)",
+            "l2": f"inputs larger than L2: about {ws / 1e6:.0f} MB touched per step on the GPU arm (L2 is 126 MB)",
+            "parallelism": "picture-parallel, one process per GPU, no collective"}
+
+
+def time_device_resident(torch, st, steps, warmup, barrier):
+    """W warm-up steps, then K steps between CUDA events on the launching stream; returns milliseconds."""
+    for _ in range(warmup):
+        st.step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        st.step()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -568,14 +652,23 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def all_ranks(value, op):
+        """max / min of a float over the ranks (device-side all-reduce; identity for one rank)"""
+        if world == 1:
+            return value
+        t = torch.tensor([value], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.MIN)
+        return float(t.item())
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # per-launch CUDA events (pooled: the warm-up creates them, the timed loop only records them)
+    lib.sb2_profile_enable(1)
     for _ in range(max(3, args.warmup)):
         st.step()
     barrier()
     lib.sb2_profile_reset()
-    lib.sb2_profile_enable(1)
     launches0 = lib.sb2_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -590,62 +683,82 @@ def run_ours(args):
     # stop polling NVML before the API-heavy e2e arm: nvidia-smi at 10 Hz stalls the host-side
     # CUDA calls it contends with (measured: e2e 29 fps with the sampler, 157 without)
     clocks = sampler.stop((t_begin, t_end)) if rank == 0 else None
-    elapsed_ms = e0.elapsed_time(e1)
     launches = lib.sb2_launch_count() - launches0
     prof = collect_profile(lib)
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
+    lib.sb2_profile_reset()
+    elapsed_ms = all_ranks(e0.elapsed_time(e1), "max")
 
     # ---- e2e through the drop-in C API with pinned host frames ----
-    e2e = None
-    try:
-        if args.no_e2e:
-            raise RuntimeError("skipped (--no-e2e: profiler runs)")
-        nthreads = min(args.e2e_threads, B)
-        hf = HostFrames(spec, lib, nthreads)
-        if args.e2e_driver == "native":
-            hf.native_start()
-        for _ in range(3):
-            hf.step()
+    def e2e_leg(widen):
+        """One end-to-end measurement.  Every collective sits outside the per-rank try blocks: the ranks
+        first agree that all of them are set up, then run chunks of K steps until 3 s have been timed,
+        deciding together when to stop (max time over ranks / common step count)."""
+        hf, err = None, None
+        try:
+            nthreads = min(args.e2e_threads, B)
+            hf = HostFrames(spec, lib, nthreads, widen=widen)
+            if args.e2e_driver == "native":
+                hf.native_start()
+            for _ in range(3):
+                hf.step()
+        except Exception as ex:                      # noqa: BLE001 - reported in the JSON line
+            err = repr(ex)
+        if all_ranks(0.0 if err else 1.0, "min") < 0.5:
+            if hf is not None:
+                hf.close()
+            return {"value": None, "unit": "frames/s", "error": err or "another rank failed to set up"}
         barrier()
-        e2e_steps = 0
-        t0 = time.perf_counter()
-        # chunks of K steps until at least 3 s have been timed; the ranks decide together whether to go
-        # on, so that every rank times the same number of steps (max time over ranks / common step count)
+        e2e_steps, t0 = 0, time.perf_counter()
         while True:
             if args.e2e_driver == "native":
-                # the worker threads run the steps back to back (no barrier between two steps)
-                hf.drv.sb2_e2e_run(args.steps)
+                hf.drv.sb2_e2e_run(args.steps)       # the worker threads run the steps back to back
             else:
                 for _ in range(args.steps):
                     hf.step()
             e2e_steps += args.steps
             go_on = time.perf_counter() - t0 < 3.0 and e2e_steps < 50 * args.steps
-            if world > 1:
-                t = torch.tensor([1.0 if go_on else 0.0], device="cuda", dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MIN)
-                go_on = bool(t.item() > 0.5)
-            if not go_on:
+            if all_ranks(1.0 if go_on else 0.0, "min") < 0.5:
                 break
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        hf.close()
-        e2e = {"value": B * e2e_steps * world / dt, "unit": "frames/s", "steps": e2e_steps,
+        dt = all_ranks(time.perf_counter() - t0, "max")
+        res = {"value": B * e2e_steps * world / dt, "unit": "frames/s", "steps": e2e_steps,
                "h2d_bytes_per_step": hf.h2d * B, "d2h_bytes_per_step": hf.d2h * B,
-               "api": ("drop-in schro_* C API (schro_frame_to_gpu, schro_frame_inverse_iwt_transform, "
-                       "schro_motion_render, schro_frame_mc_edgeextend, schro_upsampled_frame_upsample, "
-                       "schro_frame_downsample, schro_hbm_scan, schro_hierarchical_bm_scan_hint, "
-                       "schro_gpuframe_to_cpu)" if hf.full else
+               "coefficients": ("quantised s16 up, dequantised to s32 on the device" if hf.widen
+                                else ("dequantised s32 up" if spec["depth_name"] == "s32" else "s16 up")),
+               "api": ("drop-in schro_* C API (schro_frame_to_gpu, "
+                       + ("schro_b200_frame_dequantise_widen, " if hf.widen else "")
+                       + "schro_frame_inverse_iwt_transform, schro_motion_render, schro_frame_mc_edgeextend, "
+                       "schro_upsampled_frame_upsample, schro_frame_downsample, schro_hbm_scan, "
+                       "schro_hierarchical_bm_scan_hint, schro_hbm_motion_field, schro_gpuframe_to_cpu)" if hf.full else
                        "drop-in schro_frame_inverse_iwt_transform on the host frame (staged H2D, transform, D2H)")
-                      + f" on pinned host SchroFrames, {nthreads} host threads/GPU ({args.e2e_driver} driver), one stream each"}
-    except Exception as ex:  # keep the device-resident number even if the host arm breaks
-        e2e = {"value": None, "unit": "frames/s", "error": repr(ex)}
+                      + f" on pinned host SchroFrames, {min(args.e2e_threads, B)} host threads/GPU"
+                        f" ({args.e2e_driver} driver), one stream each"}
+        hf.close()
+        return res
+
+    if args.no_e2e:
+        e2e = {"value": None, "unit": "frames/s", "error": "skipped (--no-e2e: profiler runs)"}
+        e2e_s32 = None
+    else:
+        e2e = e2e_leg(True)
+        # the round-1 data path for comparison: dequantised s32 coefficients travel (twice the bytes)
+        e2e_s32 = e2e_leg(False) if (spec.get("full_core", True) and spec["depth_name"] == "s32") else None
+
+    # ---- the other BASELINE.json configurations that fit one GPU, device-resident, same script ----
+    other = {}
+    if args.workload == "picture_core_2160p" and not args.no_other:
+        del st                                        # its slabs go back to the allocator
+        torch.cuda.empty_cache()
+        for name in ("wavelet_1080p_dd97", "wavelet_1080p_legall"):
+            ospec = workload_spec(name)
+            ospec["overlap"] = False
+            ost = Stages(ospec, torch, dev)
+            ms = all_ranks(time_device_resident(torch, ost, 20, 3, barrier), "max")
+            alg = sum(s["alg_bytes"] for s in ost.stages)
+            other[name] = {"what": ospec["label"], "batch_per_gpu": ospec["batch"],
+                           "value": round(ospec["batch"] * world * 20 / (ms * 1e-3), 1), "unit": "frames/s",
+                           "alg_GBps": round(alg * 20 / (ms * 1e-3) / 1e9, 1)}
+            del ost
 
     if rank != 0:
         if world > 1:
@@ -657,47 +770,51 @@ def run_ours(args):
     value = B * world * args.steps / (elapsed_ms * 1e-3)
     # dominant kernel = largest share of device time in the timed region
     dom_tag, dom = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, None)
-    # DRAM bytes per launch from the committed ncu capture (valid for the workload / batch it was taken at)
-    traffic = {}
+    # DRAM bytes per launch come from the committed ncu capture of the same command (valid for the
+    # workload / batch it was taken at); the capture is named beside the number
+    traffic, traffic_src = {}, None
     try:
-        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         if tj["workload"] == args.workload and tj["batch_per_gpu"] == B and not args.overlap:
-            traffic = tj["dram_bytes_per_launch"]
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
     except Exception:
         pass
+    total_prof_ms = max(1e-9, sum(r["ms"] for r in prof.values()))
     roofline = None
     if dom:
         ach = dom["bytes"] / dom["launches"] / (dom["ms"] / dom["launches"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom_tag, "achieved": round(ach, 1), "peak": peak,
                     "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic.get(dom_tag),
+                    "traffic_source": traffic_src if traffic.get(dom_tag) is not None else None,
                     "alg_bytes_per_launch": round(dom["bytes"] / dom["launches"]),
                     "peak_source": peak_src, "launch_ms": round(dom["ms"] / dom["launches"], 4),
-                    "share_of_step": round(dom["ms"] / max(1e-9, sum(r["ms"] for r in prof.values())), 3)}
+                    "share_of_step": round(dom["ms"] / total_prof_ms, 3)}
     roofline_all = {}
     for k, v in sorted(prof.items()):
         a_ = v["bytes"] / max(v["ms"], 1e-9) / 1e6
         roofline_all[k] = {"achieved_GBps": round(a_, 1), "frac": round(a_ / peak, 4),
                            "launch_ms": round(v["ms"] / v["launches"], 4), "traffic": traffic.get(k),
-                           "share_of_step": round(v["ms"] / max(1e-9, sum(r["ms"] for r in prof.values())), 3)}
-    stage_report = {}
-    for s in st.stages:
-        stage_report[s["name"]] = {"frames": s["frames"], "alg_bytes": s["alg_bytes"]}
+                           "share_of_step": round(v["ms"] / total_prof_ms, 3)}
     kern = {k: {"ms_per_step": round(v["ms"] / args.steps, 4), "launches_per_step": v["launches"] // args.steps,
                 "alg_GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in sorted(prof.items())}
+    alg_step = sum(v["bytes"] for v in prof.values()) / args.steps
     out = {
-        "metric": "frames/s at 2160p 4:2:0 (wavelet+OBMC+SAD); HBM GB/s as % of B200 peak",
+        "metric": METRIC,
         "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "s32" if spec["depth_name"] == "s32" else "s16",
         "data": "synthetic",
-        "config": {"workload": args.workload, "what": spec["label"], "content": args.content, "batch_per_gpu": B,
-                   "stages": [s["name"] for s in st.stages],
-                   "l2": f"inputs larger than L2: {st.working_set / 1e6:.0f} MB working set per step",
-                   "parallelism": f"picture-parallel x{world}, no collective"},
+        "config": common_config(args, spec),
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_all": roofline_all,
+        "step_alg_GBps": round(alg_step / (ms_per_step * 1e-3) / 1e9, 1),
+        "step_frac_of_peak": round(alg_step / (ms_per_step * 1e-3) / 1e9 / peak, 4),
         "kernels": kern,
         "clocks": clocks,
     }
+    if e2e_s32 is not None:
+        out["e2e_s32"] = e2e_s32
+    if other:
+        out["other_configs"] = other
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(spec, seconds=args.cpu_seconds)
     print(json.dumps(out))
@@ -753,6 +870,7 @@ class CpuWorkload:
         self.newref = [[H.HostPlane(p.w, p.h, ext=32, upsampled=True) for p in self.refs[0]]
                        for _ in range(nthreads)]
         self.acc = [[np.zeros((p.h, p.w), np.int16) for p in self.refs[0]] for _ in range(nthreads)]
+        self.hbm_scratch = [{} for _ in range(nthreads)]      # pyramid / field buffers, allocated once
         # the reference initialises static tables lazily and not thread-safely
         # (schromotion8.c:13-18): touch them once before the threads start
         self.frame(0)
@@ -799,7 +917,7 @@ class CpuWorkload:
             H.cpu_upsample(lib, prefix, pl)
         if self.kind == "reference":
             H.ref_hbm(lib, self.src, self.refpic, self.W, self.Hh, BLOCK["xbsep"], BLOCK["ybsep"],
-                      HBM_LEVELS, 0, 0, 3)
+                      HBM_LEVELS, 0, 0, 3, scratch=self.hbm_scratch[t])
         else:
             H.oracle_hbm(lib, self.src, self.refpic, self.W, self.Hh, BLOCK["xbsep"], BLOCK["ybsep"],
                          HBM_LEVELS, 0, 0, 3)
@@ -841,17 +959,18 @@ def run_reference(args):
     if rank != 0:
         return
     spec = workload_spec(args.workload)
+    if args.batch:
+        spec["batch"] = args.batch
     t0 = time.perf_counter()
     cb = cpu_baseline(spec, steps=max(1, args.steps), warmup=1 if args.warmup > 0 else 0)
     out = {
         "impl": "reference",
-        "metric": "frames/s at 2160p 4:2:0 (wavelet+OBMC+SAD); HBM GB/s as % of B200 peak",
+        "metric": METRIC,
         "value": cb["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(cb["seconds"] / max(1, args.steps) * 1e3, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "s32" if spec["depth_name"] == "s32" else "s16",
         "data": "synthetic",
-        "config": {"workload": args.workload, "what": spec["label"], "content": args.content,
-                   "batch_per_gpu": spec["batch"]},
+        "config": common_config(args, spec),
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": round(time.perf_counter() - t0, 2),
@@ -875,6 +994,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (for ncu runs of the timed region)")
+    ap.add_argument("--no-other", action="store_true", help="skip the device-resident 1080p configurations")
     ap.add_argument("--overlap", action="store_true",
                     help="run the motion-estimation stages on a second stream (measured: no gain in the "
                          "device-resident loop, whose batched wavefronts already keep every SM occupied)")

@@ -23,6 +23,12 @@ typedef struct {
   SchroFrame **out_dev;        /* [nthreads] upsampled, extension 32 */
   SchroMotion **motion;        /* [nthreads] */
   SchroFrame **src_pyr;        /* [nthreads * (levels + 1)] */
+  /* widen != 0: the coefficients arrive QUANTISED as s16 (half the bytes of the s32 frame) and are
+   * dequantised into the s32 coefficient frame on the device (schro_b200_frame_dequantise_widen) */
+  int widen;
+  SchroFrame **coef16_host;    /* [npictures] quantised coefficients, s16, page-locked */
+  SchroFrame **coef16_dev;     /* [nthreads] */
+  const int32_t *pairs;        /* (quant_factor, quant_offset + 2) per codeblock */
 } Sb2E2eJob;
 
 static Sb2E2eJob g_job;
@@ -49,22 +55,29 @@ now (void)
  * threaded throughput.  1 = H2D coefficients, 2 = inverse wavelet + render + upsample, 4 = D2H picture,
  * 8 = H2D source, 16 = pyramid, 32 = block matching */
 static int g_stage_mask = 0xff;
+
+/* coefficients of picture i into thread t's device coefficient frame */
+static void
+upload_coefficients (const Sb2E2eJob *j, int t, int i)
+{
+  if (j->widen) {
+    schro_frame_to_gpu (j->coef16_dev[t], j->coef16_host[i]);
+    schro_b200_frame_dequantise_widen (j->coef_dev[t], j->coef16_dev[t], j->params, j->pairs);
+  } else {
+    schro_frame_to_gpu (j->coef_dev[t], j->coef_host[i]);
+  }
+}
+
 static void
 partial_picture (int t, int i)
 {
   const Sb2E2eJob *j = &g_job;
   SchroFrame **pyr = j->src_pyr + (size_t) t * (j->levels + 1);
-  SchroFrame view;
-  int c, l;
-  if (g_stage_mask & 1) schro_frame_to_gpu (j->coef_dev[t], j->coef_host[i]);
+  int l;
+  if (g_stage_mask & 1) upload_coefficients (j, t, i);
   if (g_stage_mask & 2) {
     schro_frame_inverse_iwt_transform (j->coef_dev[t], j->params);
-    view = *j->coef_dev[t];
-    view.refcount = 1;
-    view.domain = NULL;
-    view.height = j->pic_height;
-    for (c = 0; c < 3; c++) view.components[c].height = c ? j->pic_height / 2 : j->pic_height;
-    schro_motion_render (j->motion[t], j->acc_dev[t], &view, 1, j->out_dev[t]);
+    schro_motion_render (j->motion[t], j->acc_dev[t], j->coef_dev[t], 1, j->out_dev[t]);
     schro_frame_mc_edgeextend (j->out_dev[t]);
     j->out_dev[t]->upsample_done = 0;
     schro_upsampled_frame_upsample (j->out_dev[t]);
@@ -93,10 +106,9 @@ one_picture (int t, int i)
 {
   const Sb2E2eJob *j = &g_job;
   SchroFrame **pyr = j->src_pyr + (size_t) t * (j->levels + 1);
-  SchroFrame view;
   SchroHierBm *hbm;
   SchroMotionField *mf;
-  int c, l;
+  int l;
 
   if (!j->full_core) {
     schro_frame_inverse_iwt_transform (j->coef_host[i], j->params);
@@ -104,15 +116,11 @@ one_picture (int t, int i)
   }
   if (g_stage_mask != 0xff) { partial_picture (t, i); return; }
   /* decode side: coefficients in, decoded picture out */
-  TIMED (T_H2D_COEF, schro_frame_to_gpu (j->coef_dev[t], j->coef_host[i]));
+  TIMED (T_H2D_COEF, upload_coefficients (j, t, i));
   TIMED (T_IWT, schro_frame_inverse_iwt_transform (j->coef_dev[t], j->params));
-  /* the picture-size window of the (padded) coefficient frame, same memory */
-  view = *j->coef_dev[t];
-  view.refcount = 1;
-  view.domain = NULL;
-  view.height = j->pic_height;
-  for (c = 0; c < 3; c++) view.components[c].height = c ? j->pic_height / 2 : j->pic_height;
-  TIMED (T_RENDER, schro_motion_render (j->motion[t], j->acc_dev[t], &view, 1, j->out_dev[t]));
+  /* dest (picture size) gives the rendered area; the iwt-padded coefficient frame is the addframe,
+   * as in schrodecoder.c:1784 */
+  TIMED (T_RENDER, schro_motion_render (j->motion[t], j->acc_dev[t], j->coef_dev[t], 1, j->out_dev[t]));
   TIMED (T_EDGE_UPSAMPLE, {
     schro_frame_mc_edgeextend (j->out_dev[t]);
     j->out_dev[t]->upsample_done = 0;

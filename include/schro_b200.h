@@ -246,6 +246,13 @@ size_t sb2_dequant_table_pairs (const sb2_dequant_params *p, int ncomp);
 int sb2_dequantise (const sb2_slab *coeffs, int is_s32, const sb2_dequant_params *p,
     const int32_t *quant, size_t quant_picture_pitch, void *stream);
 
+/* The same for a >8-bit stream whose quantised coefficients fit 16 bits (what an entropy decoder
+ * produces for any practical quantiser): the input slab is s16, the arithmetic and the output slab
+ * are s32 -- exactly orc_dequantise_s32_ip_2d (schroedinger/schroorc.orc:2148-2162) on the
+ * sign-extended values -- so the host uploads half the bytes of the s32 coefficient frame. */
+int sb2_dequantise_widen (const sb2_slab *quantised_s16, const sb2_slab *coeffs_s32,
+    const sb2_dequant_params *p, const int32_t *quant, size_t quant_picture_pitch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -311,6 +311,10 @@ void schro_wavelet_inverse_transform_2d (SchroFrameData *fd_dest,
  * pairs = (quant_factor, quant_offset + 2) per codeblock, see sb2_dequantise in schro_b200.h.
  * Replaces the orc_dequantise_* calls of schro_decoder_decode_subband (schrodecoder.c:3395-3448). */
 void schro_b200_frame_dequantise (SchroFrame *frame, SchroParams *params, const int32_t *pairs);
+/* the same with an s16 source of quantised coefficients and an s32 destination (>8-bit streams whose
+ * quantised values fit 16 bits): half the upload of the s32 coefficient frame */
+void schro_b200_frame_dequantise_widen (SchroFrame *dest, SchroFrame *src, SchroParams *params,
+    const int32_t *pairs);
 void schro_frame_iwt_transform (SchroFrame *frame, SchroParams *params);
 void schro_frame_inverse_iwt_transform (SchroFrame *frame, SchroParams *params);
 

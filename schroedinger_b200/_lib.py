@@ -71,6 +71,8 @@ class DequantParams(ctypes.Structure):
 _opt("sb2_dequant_table_pairs", ctypes.c_size_t, [ctypes.POINTER(DequantParams), ctypes.c_int])
 _opt("sb2_dequantise", ctypes.c_int, [_SP, ctypes.c_int, ctypes.POINTER(DequantParams), ctypes.c_void_p,
                                       ctypes.c_size_t, ctypes.c_void_p])
+_opt("sb2_dequantise_widen", ctypes.c_int, [_SP, _SP, ctypes.POINTER(DequantParams), ctypes.c_void_p,
+                                            ctypes.c_size_t, ctypes.c_void_p])
 _opt("sb2_edgeextend_upsample", ctypes.c_int, [_SP, ctypes.c_int, ctypes.c_void_p])
 _opt("sb2_obmc_render", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, _SP, _SP, _SP,
                                       _SP, ctypes.c_int, ctypes.c_int, _SP, ctypes.c_void_p])

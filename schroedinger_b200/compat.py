@@ -149,6 +149,7 @@ _proto("schro_gpuframe_to_cpu", None, [FrameP, FrameP])
 _proto("schro_wavelet_transform_2d", None, [FrameDataP, ctypes.c_int, ctypes.c_void_p])
 _proto("schro_wavelet_inverse_transform_2d", None, [FrameDataP, FrameDataP, ctypes.c_int, ctypes.c_void_p])
 _proto("schro_b200_frame_dequantise", None, [FrameP, ParamsP, ctypes.c_void_p])
+_proto("schro_b200_frame_dequantise_widen", None, [FrameP, FrameP, ParamsP, ctypes.c_void_p])
 _proto("schro_frame_iwt_transform", None, [FrameP, ParamsP])
 _proto("schro_frame_inverse_iwt_transform", None, [FrameP, ParamsP])
 _proto("schro_frame_downsample", None, [FrameP, FrameP])

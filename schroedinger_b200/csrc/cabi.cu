@@ -30,12 +30,27 @@ int check_cuda (cudaError_t e, const char *what)
 void count_launch (unsigned n) { g_launches.fetch_add (n, std::memory_order_relaxed); }
 
 // ---- optional per-launch device timing (used by bench.py for the roofline) ----
+// Events come from a pool that survives sb2_profile_reset, so a measured loop pays two event
+// records per launch and no event creation.
 struct ProfRec { char tag[48]; cudaEvent_t e0, e1; double bytes; };
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_events;
 static std::atomic<int> g_prof_on{0};
 
 bool profiling () { return g_prof_on.load (std::memory_order_relaxed) != 0; }
+
+static cudaEvent_t prof_event ()
+{
+  if (!g_prof_events.empty ()) {
+    cudaEvent_t e = g_prof_events.back ();
+    g_prof_events.pop_back ();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate (&e);
+  return e;
+}
 
 int prof_begin (const char *tag, double bytes, cudaStream_t st)
 {
@@ -43,10 +58,10 @@ int prof_begin (const char *tag, double bytes, cudaStream_t st)
   ProfRec r;
   snprintf (r.tag, sizeof (r.tag), "%s", tag);
   r.bytes = bytes;
-  cudaEventCreate (&r.e0);
-  cudaEventCreate (&r.e1);
-  cudaEventRecord (r.e0, st);
   std::lock_guard<std::mutex> lk (g_prof_mu);
+  r.e0 = prof_event ();
+  r.e1 = prof_event ();
+  cudaEventRecord (r.e0, st);
   g_prof.push_back (r);
   return (int) g_prof.size () - 1;
 }
@@ -55,7 +70,7 @@ void prof_end (int id, cudaStream_t st)
 {
   if (id < 0) return;
   std::lock_guard<std::mutex> lk (g_prof_mu);
-  cudaEventRecord (g_prof[id].e1, st);
+  if (id < (int) g_prof.size ()) cudaEventRecord (g_prof[id].e1, st);
 }
 
 }  // namespace sb2
@@ -76,7 +91,7 @@ extern "C" void sb2_profile_enable (int on)
 extern "C" void sb2_profile_reset (void)
 {
   std::lock_guard<std::mutex> lk (sb2::g_prof_mu);
-  for (auto &r : sb2::g_prof) { cudaEventDestroy (r.e0); cudaEventDestroy (r.e1); }
+  for (auto &r : sb2::g_prof) { sb2::g_prof_events.push_back (r.e0); sb2::g_prof_events.push_back (r.e1); }
   sb2::g_prof.clear ();
 }
 extern "C" int sb2_profile_count (void)

@@ -18,7 +18,8 @@ namespace sb2 {
 
 struct DequantArgs {
   TileGrid tiles;
-  PlaneSet planes;
+  PlaneSet planes;                                 // input (quantised)
+  PlaneSet out;                                    // output: the same planes, or an s32 slab when widening
   int w[SB2_MAX_COMPONENTS], h[SB2_MAX_COMPONENTS];
   int ncomp, depth;
   int hcb[SB2_DEQUANT_MAX_LEVELS + 1], vcb[SB2_DEQUANT_MAX_LEVELS + 1];
@@ -47,7 +48,9 @@ __device__ __forceinline__ int dq32 (int v, int factor, int offset)
   return (int) ((unsigned) ((int) t >> 2) * (unsigned) sign);
 }
 
-template <typename T>
+// T = sample type of the input; WIDEN: s16 input, s32 arithmetic (orc_dequantise_s32_ip_2d on the
+// sign-extended values) and s32 output in a second slab -- the host uploads half the bytes
+template <typename T, bool WIDEN>
 __global__ void __launch_bounds__ (256)
 dequant_kernel (const DequantArgs a)
 {
@@ -111,7 +114,7 @@ dequant_kernel (const DequantArgs a)
       const int2 fo = __ldg (q + p0);
 #pragma unroll
       for (int k = 0; k < 4; k++)
-        if (v[k] != 0) v[k] = sizeof (T) == 2 ? dq16 (v[k], fo.x, fo.y) : dq32 (v[k], fo.x, fo.y);
+        if (v[k] != 0) v[k] = (sizeof (T) == 2 && !WIDEN) ? dq16 (v[k], fo.x, fo.y) : dq32 (v[k], fo.x, fo.y);
     } else {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -119,9 +122,17 @@ dequant_kernel (const DequantArgs a)
         int pk;
         locate (x0 + k, pk);
         const int2 fo = __ldg (q + pk);
-        v[k] = sizeof (T) == 2 ? dq16 (v[k], fo.x, fo.y) : dq32 (v[k], fo.x, fo.y);
+        v[k] = (sizeof (T) == 2 && !WIDEN) ? dq16 (v[k], fo.x, fo.y) : dq32 (v[k], fo.x, fo.y);
       }
     }
+  }
+  if (WIDEN) {
+    int *orow = reinterpret_cast<int *> (plane_ptr (a.out, pic, comp) + (size_t) y * a.out.stride[comp]);
+    if (x0 + 3 < w && (((size_t) (orow + x0)) & 15) == 0)
+      *reinterpret_cast<int4 *> (orow + x0) = make_int4 (v[0], v[1], v[2], v[3]);
+    else
+      for (int k = 0; k < 4 && x0 + k < w; k++) orow[x0 + k] = v[k];
+    return;
   }
   if (vec) {
     if (sizeof (T) == 2)
@@ -158,21 +169,23 @@ sb2_dequant_table_pairs (const sb2_dequant_params *p, int ncomp)
   return (size_t) dequant_layout (p, base) * (size_t) ncomp;
 }
 
-extern "C" int
-sb2_dequantise (const sb2_slab *coeffs, int is_s32, const sb2_dequant_params *p, const int32_t *quant,
-    size_t quant_picture_pitch, void *stream)
+static int
+dequantise_launch (const char *who, const sb2_slab *coeffs, const sb2_slab *out, int is_s32, const sb2_dequant_params *p,
+    const int32_t *quant, size_t quant_picture_pitch, void *stream)
 {
-  if (!coeffs || !coeffs->base || !p || !quant) return set_error (SB2_ERR_ARG, "sb2_dequantise: null argument");
+  if (!coeffs || !coeffs->base || !p || !quant) return set_error (SB2_ERR_ARG, "%s: null argument", who);
   if (coeffs->ncomp < 1 || coeffs->ncomp > SB2_MAX_COMPONENTS || coeffs->count < 1)
-    return set_error (SB2_ERR_ARG, "sb2_dequantise: bad slab");
+    return set_error (SB2_ERR_ARG, "%s: bad slab", who);
   if (p->transform_depth < 1 || p->transform_depth > SB2_DEQUANT_MAX_LEVELS)
-    return set_error (SB2_ERR_ARG, "sb2_dequantise: transform depth %d", p->transform_depth);
+    return set_error (SB2_ERR_ARG, "%s: transform depth %d", who, p->transform_depth);
+  if (out && (!out->base || out->ncomp != coeffs->ncomp || out->count != coeffs->count))
+    return set_error (SB2_ERR_ARG, "%s: output slab does not match the input", who);
   const int bpp = is_s32 ? 4 : 2;
   DequantArgs a;
   a.planes = planeset_from_slab (coeffs);
+  a.out = planeset_from_slab (out ? out : coeffs);
   a.ncomp = coeffs->ncomp;
   a.depth = p->transform_depth;
-  int maxw = 0, maxh = 0;
   double bytes = 0;
   for (int c = 0; c < SB2_MAX_COMPONENTS; c++) {
     a.w[c] = a.h[c] = 0;
@@ -180,32 +193,47 @@ sb2_dequantise (const sb2_slab *coeffs, int is_s32, const sb2_dequant_params *p,
     a.w[c] = coeffs->width[c];
     a.h[c] = coeffs->height[c];
     if (a.w[c] < 1 || a.h[c] < 1 || (a.w[c] & ((1 << a.depth) - 1)) || (a.h[c] & ((1 << a.depth) - 1)))
-      return set_error (SB2_ERR_ARG, "sb2_dequantise: component %d size %dx%d is not a multiple of 1<<%d", c, a.w[c],
+      return set_error (SB2_ERR_ARG, "%s: component %d size %dx%d is not a multiple of 1<<%d", who, c, a.w[c],
           a.h[c], a.depth);
     if ((coeffs->stride[c] % bpp) || (coeffs->offset[c] % bpp))
-      return set_error (SB2_ERR_ARG, "sb2_dequantise: component %d stride/offset not a multiple of the sample size", c);
-    maxw = max (maxw, a.w[c]);
-    maxh = max (maxh, a.h[c]);
-    bytes += 2.0 * a.w[c] * a.h[c] * bpp * coeffs->count;
+      return set_error (SB2_ERR_ARG, "%s: component %d stride/offset not a multiple of the sample size", who, c);
+    if (out && (out->width[c] != a.w[c] || out->height[c] != a.h[c] || (out->stride[c] % 4) || (out->offset[c] % 4)))
+      return set_error (SB2_ERR_ARG, "%s: output component %d differs in size or is not 4-byte aligned", who, c);
+    bytes += (double) a.w[c] * a.h[c] * (out ? 2 + 4 : 2 * bpp) * coeffs->count;
   }
   for (int l = 0; l <= SB2_DEQUANT_MAX_LEVELS; l++) {
     a.hcb[l] = l <= a.depth ? p->horiz_codeblocks[l] : 1;
     a.vcb[l] = l <= a.depth ? p->vert_codeblocks[l] : 1;
-    if (a.hcb[l] < 1 || a.vcb[l] < 1) return set_error (SB2_ERR_ARG, "sb2_dequantise: codeblock counts must be >= 1");
+    if (a.hcb[l] < 1 || a.vcb[l] < 1) return set_error (SB2_ERR_ARG, "%s: codeblock counts must be >= 1", who);
   }
   a.comp_pairs = dequant_layout (p, a.band_base);
   if (quant_picture_pitch < (size_t) a.comp_pairs * a.ncomp)
-    return set_error (SB2_ERR_ARG, "sb2_dequantise: table pitch %zu < %d pairs", quant_picture_pitch, a.comp_pairs * a.ncomp);
+    return set_error (SB2_ERR_ARG, "%s: table pitch %zu < %d pairs", who, quant_picture_pitch, a.comp_pairs * a.ncomp);
   a.quant = reinterpret_cast<const int2 *> (quant);
   a.quant_pitch = quant_picture_pitch;
-  (void) maxw; (void) maxh;
-  if (coeffs->count > 65535) return set_error (SB2_ERR_ARG, "sb2_dequantise: at most 65535 pictures per call");
+  if (coeffs->count > 65535) return set_error (SB2_ERR_ARG, "%s: at most 65535 pictures per call", who);
   const dim3 grid = make_tile_grid (a.tiles, a.ncomp, a.w, a.h, 4 * 256, 1, coeffs->count);
   cudaStream_t st = as_stream (stream);
   {
-    LaunchScope scope (is_s32 ? "dequantise_s32" : "dequantise_s16", bytes, st);
-    if (is_s32) dequant_kernel<int32_t><<<grid, 256, 0, st>>> (a);
-    else dequant_kernel<int16_t><<<grid, 256, 0, st>>> (a);
+    LaunchScope scope (out ? "dequantise_s16_to_s32" : is_s32 ? "dequantise_s32" : "dequantise_s16", bytes, st);
+    if (out) dequant_kernel<int16_t, true><<<grid, 256, 0, st>>> (a);
+    else if (is_s32) dequant_kernel<int32_t, false><<<grid, 256, 0, st>>> (a);
+    else dequant_kernel<int16_t, false><<<grid, 256, 0, st>>> (a);
   }
   return check_cuda (cudaGetLastError (), "dequant_kernel launch");
+}
+
+extern "C" int
+sb2_dequantise (const sb2_slab *coeffs, int is_s32, const sb2_dequant_params *p, const int32_t *quant,
+    size_t quant_picture_pitch, void *stream)
+{
+  return dequantise_launch ("sb2_dequantise", coeffs, nullptr, is_s32, p, quant, quant_picture_pitch, stream);
+}
+
+extern "C" int
+sb2_dequantise_widen (const sb2_slab *quantised_s16, const sb2_slab *coeffs_s32, const sb2_dequant_params *p,
+    const int32_t *quant, size_t quant_picture_pitch, void *stream)
+{
+  if (!coeffs_s32) return set_error (SB2_ERR_ARG, "sb2_dequantise_widen: null output slab");
+  return dequantise_launch ("sb2_dequantise_widen", quantised_s16, coeffs_s32, 0, p, quant, quant_picture_pitch, stream);
 }

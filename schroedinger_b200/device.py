@@ -260,6 +260,23 @@ def dequantise(coeffs, depth, horiz_codeblocks, vert_codeblocks, quant, stream=N
           "sb2_dequantise")
 
 
+def dequantise_widen(quantised, coeffs, depth, horiz_codeblocks, vert_codeblocks, quant, stream=None):
+    """s16 quantised coefficients -> dequantised s32 coefficients in a second slab (sb2_dequantise_widen)."""
+    from ._lib import DequantParams
+    require_cuda()
+    assert quantised.layout.depth == "s16" and coeffs.layout.depth == "s32"
+    p = DequantParams()
+    p.transform_depth = depth
+    for i in range(7):
+        p.horiz_codeblocks[i] = horiz_codeblocks[i] if i < len(horiz_codeblocks) else 1
+        p.vert_codeblocks[i] = vert_codeblocks[i] if i < len(vert_codeblocks) else 1
+    pairs = lib.sb2_dequant_table_pairs(ctypes.byref(p), len(coeffs.layout.comp_sizes))
+    assert quant.dtype == torch.int32 and quant.numel() == 2 * pairs * coeffs.count, (quant.numel(), pairs)
+    check(lib.sb2_dequantise_widen(ctypes.byref(quantised.slab), ctypes.byref(coeffs.slab), ctypes.byref(p),
+                                   ctypes.c_void_p(quant.data_ptr()), ctypes.c_size_t(pairs), _stream_ptr(stream)),
+          "sb2_dequantise_widen")
+
+
 def downsample(src, dst, stream=None):
     """schro_frame_downsample: dst = half-size src (per component)."""
     require_cuda()

@@ -44,11 +44,17 @@ Sb2hContext *sb2h_context (void);
 void sb2h_sync (Sb2hContext *cx);
 void sb2h_frame_use (Sb2hContext *cx, const void *region);
 void sb2h_frame_wrote (Sb2hContext *cx, const void *region);
+/* the same through a pointer INTO a region (plane pointers of a SchroFrameData): the containing
+ * CUDA-domain region is looked up by address; unknown device memory falls back to a device-wide wait */
+const void *sb2h_region_of (const void *ptr);
+void sb2h_ptr_use (Sb2hContext *cx, const void *ptr);
+void sb2h_ptr_wrote (Sb2hContext *cx, const void *ptr);
 /* process-wide pool of page-locked host blocks, reused by exact size */
 void *sb2h_pinned_pool_alloc (size_t bytes);
 int sb2h_pinned_pool_free (void *ptr);     /* 0 if ptr is not a pool block */
-/* per-thread pool of device blocks, reused by exact size (no cudaMalloc / cudaFree -- and
- * therefore no device-wide synchronisation -- in steady state) */
+/* process-wide pool of device blocks, reused by exact size (no cudaMalloc / cudaFree -- and
+ * therefore no device-wide synchronisation -- in steady state); a block may be freed by another
+ * thread than its allocator and while stream-ordered work on it is in flight (core.c) */
 void *sb2h_pool_alloc (size_t bytes);
 void sb2h_pool_free (void *ptr);
 void *sb2h_dev_buffer (Sb2hContext *cx, int which, size_t bytes);

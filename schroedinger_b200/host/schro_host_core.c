@@ -94,15 +94,17 @@ void
 schro_b200_thread_release (void)
 {
   Sb2hContext *cx = tl_cx;
-  int i;
+  int i, last;
   if (!cx) return;
   cudaStreamSynchronize (cx->stream);
   pthread_mutex_lock (&g_device_mutex);
   g_ctx[cx->slot] = NULL;
+  for (i = 0, last = 1; i < SB2H_MAX_CTX; i++)
+    if (g_ctx[i]) last = 0;
   pthread_mutex_unlock (&g_device_mutex);
   for (i = 0; i < SB2H_NBUF; i++)
     if (cx->dev[i]) cudaFree (cx->dev[i]);
-  sb2h_pool_release_all ();
+  if (last) sb2h_pool_release_all ();
   cudaEventDestroy (cx->sync_ev);
   cudaEventDestroy (cx->ev_fork);
   cudaEventDestroy (cx->ev_join);
@@ -261,61 +263,91 @@ sb2h_dev_buffer (Sb2hContext *cx, int which, size_t bytes)
   return cx->dev[which];
 }
 
-#define SB2H_POOL_SLOTS 64
-static __thread struct { void *ptr; size_t bytes; int in_use; } tl_pool[SB2H_POOL_SLOTS];
+/* Process-wide pool of device blocks, reused by exact size (no cudaMalloc / cudaFree -- and so no
+ * device-wide synchronisation -- in steady state).  A block may be handed back by another thread
+ * than the one that allocated it (SchroAsync moves the stages of a picture between workers), and
+ * while work that uses it is still in flight: the free records an event on the freeing thread's
+ * stream, and the next owner's streams wait for that event before they touch the block. */
+#define SB2H_POOL_SLOTS 2048
+static struct { void *ptr; size_t bytes; int in_use; cudaEvent_t ev; int ev_valid; } g_pool[SB2H_POOL_SLOTS];
+static pthread_mutex_t g_pool_mutex = PTHREAD_MUTEX_INITIALIZER;
 
 void *
 sb2h_pool_alloc (size_t bytes)
 {
-  int i, free_slot = -1;
+  Sb2hContext *cx = sb2h_context ();
+  int i, free_slot = -1, idle_slot = -1;
+  void *p;
+  pthread_mutex_lock (&g_pool_mutex);
   for (i = 0; i < SB2H_POOL_SLOTS; i++) {
-    if (tl_pool[i].ptr && !tl_pool[i].in_use && tl_pool[i].bytes == bytes) {
-      tl_pool[i].in_use = 1;
-      return tl_pool[i].ptr;
+    if (g_pool[i].ptr && !g_pool[i].in_use) {
+      if (g_pool[i].bytes == bytes) {
+        g_pool[i].in_use = 1;
+        p = g_pool[i].ptr;
+        if (g_pool[i].ev_valid) {
+          /* (under the lock: the event is re-recorded by the next free of this slot) */
+          SB2H_CUDA (cudaStreamWaitEvent (cx->stream, g_pool[i].ev, 0));
+          SB2H_CUDA (cudaStreamWaitEvent (cx->stream_hi, g_pool[i].ev, 0));
+        }
+        pthread_mutex_unlock (&g_pool_mutex);
+        return p;
+      }
+      if (idle_slot < 0) idle_slot = i;
     }
-    if (!tl_pool[i].ptr && free_slot < 0) free_slot = i;
+    if (!g_pool[i].ptr && free_slot < 0) free_slot = i;
   }
   if (free_slot < 0) {
-    /* pool full: recycle the first idle block of another size */
-    for (i = 0; i < SB2H_POOL_SLOTS; i++)
-      if (!tl_pool[i].in_use) {
-        SB2H_CUDA (cudaFree (tl_pool[i].ptr));
-        tl_pool[i].ptr = NULL;
-        free_slot = i;
-        break;
-      }
-    if (free_slot < 0) sb2h_fatal (__func__, "device block pool exhausted");
+    /* table full: recycle an idle block of another size */
+    if (idle_slot < 0) sb2h_fatal (__func__, "device block pool exhausted (%d blocks in use)", SB2H_POOL_SLOTS);
+    if (g_pool[idle_slot].ev_valid) SB2H_CUDA (cudaEventSynchronize (g_pool[idle_slot].ev));
+    SB2H_CUDA (cudaFree (g_pool[idle_slot].ptr));
+    g_pool[idle_slot].ptr = NULL;
+    free_slot = idle_slot;
   }
-  SB2H_CUDA (cudaMalloc (&tl_pool[free_slot].ptr, bytes + 256));
-  tl_pool[free_slot].bytes = bytes;
-  tl_pool[free_slot].in_use = 1;
-  return tl_pool[free_slot].ptr;
-}
-
-static void
-sb2h_pool_release_all (void)
-{
-  int i;
-  for (i = 0; i < SB2H_POOL_SLOTS; i++)
-    if (tl_pool[i].ptr) {
-      cudaFree (tl_pool[i].ptr);
-      tl_pool[i].ptr = NULL;
-      tl_pool[i].in_use = 0;
-    }
+  SB2H_CUDA (cudaMalloc (&g_pool[free_slot].ptr, bytes + 256));
+  g_pool[free_slot].bytes = bytes;
+  g_pool[free_slot].in_use = 1;
+  g_pool[free_slot].ev_valid = 0;
+  p = g_pool[free_slot].ptr;
+  pthread_mutex_unlock (&g_pool_mutex);
+  return p;
 }
 
 void
 sb2h_pool_free (void *ptr)
 {
+  Sb2hContext *cx;
   int i;
   if (!ptr) return;
+  cx = sb2h_context ();
+  pthread_mutex_lock (&g_pool_mutex);
   for (i = 0; i < SB2H_POOL_SLOTS; i++)
-    if (tl_pool[i].ptr == ptr) {
-      tl_pool[i].in_use = 0;
+    if (g_pool[i].ptr == ptr) {
+      if (!g_pool[i].ev) SB2H_CUDA (cudaEventCreateWithFlags (&g_pool[i].ev, cudaEventDisableTiming));
+      SB2H_CUDA (cudaEventRecord (g_pool[i].ev, cx->stream));
+      g_pool[i].ev_valid = 1;
+      g_pool[i].in_use = 0;
+      pthread_mutex_unlock (&g_pool_mutex);
       return;
     }
-  /* allocated by another thread's pool: release for real */
-  SB2H_CUDA (cudaFree (ptr));
+  pthread_mutex_unlock (&g_pool_mutex);
+  sb2h_fatal (__func__, "%p is not a pooled device block", ptr);
+}
+
+/* idle blocks go back to the driver when the last thread context is released */
+static void
+sb2h_pool_release_all (void)
+{
+  int i;
+  pthread_mutex_lock (&g_pool_mutex);
+  for (i = 0; i < SB2H_POOL_SLOTS; i++)
+    if (g_pool[i].ptr && !g_pool[i].in_use) {
+      cudaFree (g_pool[i].ptr);
+      g_pool[i].ptr = NULL;
+      if (g_pool[i].ev) { cudaEventDestroy (g_pool[i].ev); g_pool[i].ev = NULL; }
+      g_pool[i].ev_valid = 0;
+    }
+  pthread_mutex_unlock (&g_pool_mutex);
 }
 
 /* process-wide pool of page-locked host blocks (motion fields coming back from the GPU) */
@@ -445,19 +477,71 @@ limbo_reap (SchroMemoryDomain *domain, int wait)
 }
 
 
+/* Every region a CUDA domain owns, by address range: entry points that only see a plane pointer
+ * (SchroFrameData carries no frame, schroframe.h:58-68) find the region -- and with it the
+ * region's last-writer record -- from the pointer. */
+#define SB2H_NREGION 4096
+static struct { char *ptr; size_t size; } g_regions[SB2H_NREGION];
+static pthread_mutex_t g_region_mutex = PTHREAD_MUTEX_INITIALIZER;
+
+const void *
+sb2h_region_of (const void *ptr)
+{
+  const char *p = ptr, *base = NULL;
+  int i;
+  pthread_mutex_lock (&g_region_mutex);
+  for (i = 0; i < SB2H_NREGION; i++)
+    if (g_regions[i].ptr && p >= g_regions[i].ptr && p < g_regions[i].ptr + g_regions[i].size) {
+      base = g_regions[i].ptr;
+      break;
+    }
+  pthread_mutex_unlock (&g_region_mutex);
+  return base;
+}
+
+/* before a stream-ordered access through a bare device pointer: order it behind the last write of
+ * the containing region; memory this library does not know is ordered by a device-wide wait */
+void
+sb2h_ptr_use (Sb2hContext *cx, const void *ptr)
+{
+  const void *region = sb2h_region_of (ptr);
+  if (region) sb2h_frame_use (cx, region);
+  else SB2H_CUDA (cudaDeviceSynchronize ());
+}
+
+void
+sb2h_ptr_wrote (Sb2hContext *cx, const void *ptr)
+{
+  const void *region = sb2h_region_of (ptr);
+  if (region) sb2h_frame_wrote (cx, region);
+}
+
 static void *
 cuda_alloc (int size)
 {
   void *p = NULL;
+  int i;
   /* 256 spare bytes: the byte-SIMD SAD kernels read whole aligned words */
   SB2H_CUDA (cudaMalloc (&p, (size_t) size + 256));
+  pthread_mutex_lock (&g_region_mutex);
+  for (i = 0; i < SB2H_NREGION && g_regions[i].ptr; i++) ;
+  if (i < SB2H_NREGION) {
+    g_regions[i].ptr = p;
+    g_regions[i].size = (size_t) size + 256;
+  }
+  pthread_mutex_unlock (&g_region_mutex);
   return p;
 }
 
 static void
 cuda_free (void *ptr, int size)
 {
+  int i;
   (void) size;
+  pthread_mutex_lock (&g_region_mutex);
+  for (i = 0; i < SB2H_NREGION; i++)
+    if (g_regions[i].ptr == (char *) ptr) g_regions[i].ptr = NULL;
+  pthread_mutex_unlock (&g_region_mutex);
   SB2H_CUDA (cudaFree (ptr));
 }
 

@@ -147,9 +147,12 @@ upsample_1d (SchroFrameData *dest, SchroFrameData *src, int vertical)
   if (SCHRO_FRAME_FORMAT_DEPTH (dest->format) != SCHRO_FRAME_FORMAT_DEPTH_U8 ||
       src->format != dest->format)
     sb2h_fatal (__func__, "unimplemented format (as the reference, schroframe.c:1563-1568)");
-  if (sb2h_mem_kind (src->data) == SB2H_MEM_DEVICE) {
+  if (sb2h_mem_kind (src->data) == SB2H_MEM_DEVICE) sb2h_ptr_use (cx, src->data);
+  if (sb2h_mem_kind (dest->data) == SB2H_MEM_DEVICE) sb2h_ptr_use (cx, dest->data);
+  if (sb2h_mem_kind (src->data) == SB2H_MEM_DEVICE && sb2h_mem_kind (dest->data) == SB2H_MEM_DEVICE) {
     SB2H_CHECK (sb2_upsample_plane_1d (dest->data, dest->stride, src->data, src->stride, w, h,
             vertical, cx->stream), "sb2_upsample_plane_1d");
+    sb2h_ptr_wrote (cx, dest->data);
   } else {
     const size_t pitch = ((size_t) w + 15) & ~(size_t) 15;
     uint8_t *din = sb2h_dev_buffer (cx, SB2H_BUF_IN, pitch * h);
@@ -383,6 +386,7 @@ static const uint8_t *
 block_to_device (Sb2hContext *cx, int which, const uint8_t *p, int stride, int w, int h, int *dstride)
 {
   if (sb2h_mem_kind (p) == SB2H_MEM_DEVICE) {
+    sb2h_ptr_use (cx, p);          /* may still be written by another thread's stream-ordered call */
     *dstride = stride;
     return p;
   }

@@ -45,13 +45,20 @@ run_planes (const PlaneList *src, const PlaneList *dst, int is_s32, int filter, 
 {
   Sb2hContext *cx = sb2h_context ();
   const int bpp = is_s32 ? 4 : 2;
-  const int kind = sb2h_mem_kind (src->data[0]);
+  /* zero-copy needs BOTH sides on the device; any other combination is staged (the rectangle
+   * copies below take host or device memory on either side) */
+  const int on_device = sb2h_mem_kind (src->data[0]) == SB2H_MEM_DEVICE && sb2h_mem_kind (dst->data[0]) == SB2H_MEM_DEVICE;
   sb2_slab sin, sout;
   size_t ws_bytes;
   void *ws;
   int c, rc;
 
-  if (kind == SB2H_MEM_DEVICE) {
+  /* device planes may still be the target of another thread's stream-ordered call */
+  for (c = 0; c < src->ncomp; c++) {
+    if (sb2h_mem_kind (src->data[c]) == SB2H_MEM_DEVICE) sb2h_ptr_use (cx, src->data[c]);
+    if (dst->data[c] != src->data[c] && sb2h_mem_kind (dst->data[c]) == SB2H_MEM_DEVICE) sb2h_ptr_use (cx, dst->data[c]);
+  }
+  if (on_device) {
     /* zero-copy: describe the planes relative to the lowest address */
     char *base = src->data[0], *dbase = dst->data[0];
     int in_place = 1;
@@ -80,6 +87,7 @@ run_planes (const PlaneList *src, const PlaneList *dst, int is_s32, int filter, 
     rc = inverse ? sb2_iwt_inverse (&sin, &sout, is_s32, filter, depth, ws, ws_bytes, cx->stream)
                  : sb2_iwt_forward (&sin, &sout, is_s32, filter, depth, ws, ws_bytes, cx->stream);
     SB2H_CHECK (rc, inverse ? "sb2_iwt_inverse" : "sb2_iwt_forward");
+    for (c = 0; c < dst->ncomp; c++) sb2h_ptr_wrote (cx, dst->data[c]);
     sb2h_sync (cx);
     return;
   }
@@ -293,5 +301,86 @@ schro_b200_frame_dequantise (SchroFrame *frame, SchroParams *params, const int32
     sb2h_sync (cx);        /* a page-locked table is read by the DMA engine after the copy call returns */
   } else {
     sb2h_frame_wrote (cx, region);
+  }
+}
+
+/* The widening variant: `src` holds the quantised coefficients as s16 (what an entropy decoder
+ * produces for any practical quantiser), `dest` receives the dequantised s32 coefficient frame
+ * of a >8-bit stream (orc_dequantise_s32_ip_2d on the sign-extended values).  The host uploads
+ * half the bytes of the s32 frame.  Frames in host memory are staged; CUDA-domain frames are
+ * used where they lie and the call returns without waiting. */
+void
+schro_b200_frame_dequantise_widen (SchroFrame *dest, SchroFrame *src, SchroParams *params, const int32_t *pairs)
+{
+  Sb2hContext *cx = sb2h_context ();
+  sb2_dequant_params p;
+  sb2_slab in, out;
+  size_t npairs, tin = 0, tout = 0;
+  char *dev_in, *dev_out;
+  void *dpairs;
+  int k, host_in, host_out;
+
+  SB2H_ASSERT (dest && src && params && pairs && dest->regions[0] && src->regions[0]);
+  if (depth_is_s32 (src->format) || !depth_is_s32 (dest->format))
+    sb2h_fatal (__func__, "needs an s16 source and an s32 destination (formats 0x%x, 0x%x)",
+        (unsigned) src->format, (unsigned) dest->format);
+  memset (&p, 0, sizeof (p));
+  p.transform_depth = params->transform_depth;
+  if (p.transform_depth < 1 || p.transform_depth > SB2_DEQUANT_MAX_LEVELS)
+    sb2h_fatal (__func__, "transform depth %d", p.transform_depth);
+  for (k = 0; k <= SB2_DEQUANT_MAX_LEVELS; k++) {
+    p.horiz_codeblocks[k] = k <= p.transform_depth && params->horiz_codeblocks[k] > 0 ? params->horiz_codeblocks[k] : 1;
+    p.vert_codeblocks[k] = k <= p.transform_depth && params->vert_codeblocks[k] > 0 ? params->vert_codeblocks[k] : 1;
+  }
+  npairs = sb2_dequant_table_pairs (&p, 3);
+  for (k = 0; k < 3; k++) {
+    tin += (size_t) src->components[k].length;
+    tout += (size_t) dest->components[k].length;
+  }
+  host_in = sb2h_mem_kind (src->regions[0]) != SB2H_MEM_DEVICE;
+  host_out = sb2h_mem_kind (dest->regions[0]) != SB2H_MEM_DEVICE;
+  if (host_in) {
+    dev_in = sb2h_dev_buffer (cx, SB2H_BUF_IN, tin + 256);
+    SB2H_CUDA (cudaMemcpyAsync (dev_in, src->regions[0], tin, cudaMemcpyDefault, cx->stream));
+  } else {
+    dev_in = src->regions[0];
+    sb2h_frame_use (cx, dev_in);
+  }
+  if (host_out) dev_out = sb2h_dev_buffer (cx, SB2H_BUF_OUT, tout + 256);
+  else {
+    dev_out = dest->regions[0];
+    sb2h_frame_use (cx, dev_out);
+  }
+  memset (&in, 0, sizeof (in));
+  memset (&out, 0, sizeof (out));
+  in.base = dev_in;
+  out.base = dev_out;
+  in.picture_pitch = tin;
+  out.picture_pitch = tout;
+  in.count = out.count = 1;
+  in.ncomp = out.ncomp = 3;
+  for (k = 0; k < 3; k++) {
+    in.offset[k] = (size_t) ((char *) src->components[k].data - (char *) src->regions[0]);
+    out.offset[k] = (size_t) ((char *) dest->components[k].data - (char *) dest->regions[0]);
+    in.stride[k] = src->components[k].stride;
+    out.stride[k] = dest->components[k].stride;
+    in.width[k] = out.width[k] = k ? params->iwt_chroma_width : params->iwt_luma_width;
+    in.height[k] = out.height[k] = k ? params->iwt_chroma_height : params->iwt_luma_height;
+    if (src->components[k].width < in.width[k] || src->components[k].height < in.height[k] ||
+        dest->components[k].width < in.width[k] || dest->components[k].height < in.height[k])
+      sb2h_fatal (__func__, "component %d is smaller than the %dx%d coefficient plane", k, in.width[k], in.height[k]);
+  }
+  dpairs = sb2h_dev_buffer (cx, SB2H_BUF_AUX0, npairs * 2 * sizeof (int32_t));
+  SB2H_CUDA (cudaMemcpyAsync (dpairs, pairs, npairs * 2 * sizeof (int32_t), cudaMemcpyDefault, cx->stream));
+  SB2H_CHECK (sb2_dequantise_widen (&in, &out, &p, dpairs, npairs, cx->stream), "sb2_dequantise_widen");
+  if (host_out) {
+    SB2H_CUDA (cudaMemcpyAsync (dest->regions[0], dev_out, tout, cudaMemcpyDefault, cx->stream));
+    sb2h_sync (cx);
+  } else {
+    sb2h_frame_wrote (cx, dev_out);
+    cx->dirty = 1;
+    /* page-locked source or table memory is read by the DMA engine after the copy call returns */
+    if (sb2h_mem_kind (pairs) != SB2H_MEM_PAGEABLE || (host_in && sb2h_mem_kind (src->regions[0]) != SB2H_MEM_PAGEABLE))
+      sb2h_sync (cx);
   }
 }

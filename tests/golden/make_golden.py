@@ -150,6 +150,10 @@ def dequant_golden(ref):
                 out[f"c{i}_in"], out[f"c{i}_quant"] = a, quant
                 out[f"c{i}_depth"], out[f"c{i}_hcb"], out[f"c{i}_vcb"] = np.int32(depth), np.array(hcb), np.array(vcb)
                 out[f"c{i}_out"] = helpers.cpu_dequantise(ref, "ref", a, depth, hcb, vcb, quant)
+                if dtype == np.int16:
+                    # the widening variant (sb2_dequantise_widen): the reference's s32 program on the
+                    # sign-extended s16 input
+                    out[f"c{i}_wide"] = helpers.cpu_dequantise(ref, "ref", a.astype(np.int32), depth, hcb, vcb, quant)
                 i += 1
     out["ncases"] = np.int32(i)
     np.savez_compressed(os.path.join(helpers.GOLDEN_DIR, "dequant.npz"), **out)

@@ -372,30 +372,30 @@ def oracle_hbm(oracle, src_planes, ref_planes, width, height, xbsep=8, ybsep=8, 
 
 
 def ref_hbm(ref, src_planes, ref_planes, width, height, xbsep=8, ybsep=8, levels=4, use_chroma=0,
-            ref_index=0, level0_range=3):
+            ref_index=0, level0_range=3, scratch=None):
+    """schro_hbm_scan + level-0 refinement through the compiled reference.  scratch: a dict that keeps the
+    output buffers between calls (bench.py's CPU arm: no allocation inside its timed loop)."""
     nbx, nby = hbm_block_counts(width, height, xbsep, ybsep)
-    fields = np.zeros((levels + 1, nbx * nby), dtype=MV_DTYPE)
     P = ctypes.c_void_p * 3
     I = ctypes.c_int * 3
     hp = RefHbmParams(width, height, 2, xbsep, ybsep, levels, use_chroma, ref_index, level0_range)
     nx, ny = ctypes.c_int(), ctypes.c_int()
-    pyr = []
-    w, h = width, height
-    ptrs = (ctypes.c_void_p * (levels * 3))()
-    for l in range(levels):
-        w, h = (w + 1) // 2, (h + 1) // 2
-        lv = [np.zeros((h, w), np.uint8), np.zeros(((h + 1) // 2, (w + 1) // 2), np.uint8),
-              np.zeros(((h + 1) // 2, (w + 1) // 2), np.uint8)]
-        # chroma of level l+1 is the downsample of the chroma of level l
-        pyr.append(lv)
-    # chroma sizes follow their own halving chain
-    cw, ch = (width + 1) // 2, (height + 1) // 2
-    for l in range(levels):
-        cw, ch = (cw + 1) // 2, (ch + 1) // 2
-        pyr[l][1] = np.zeros((ch, cw), np.uint8)
-        pyr[l][2] = np.zeros((ch, cw), np.uint8)
-        for k in range(3):
-            ptrs[l * 3 + k] = pyr[l][k].ctypes.data
+    if scratch is not None and "fields" in scratch:
+        fields, pyr, ptrs = scratch["fields"], scratch["pyr"], scratch["ptrs"]
+    else:
+        fields = np.zeros((levels + 1, nbx * nby), dtype=MV_DTYPE)
+        pyr = []
+        ptrs = (ctypes.c_void_p * (levels * 3))()
+        w, h = width, height
+        # luma and chroma sizes follow their own halving chains
+        cw, ch = (width + 1) // 2, (height + 1) // 2
+        for l in range(levels):
+            w, h, cw, ch = (w + 1) // 2, (h + 1) // 2, (cw + 1) // 2, (ch + 1) // 2
+            pyr.append([np.zeros((h, w), np.uint8), np.zeros((ch, cw), np.uint8), np.zeros((ch, cw), np.uint8)])
+            for k in range(3):
+                ptrs[l * 3 + k] = pyr[l][k].ctypes.data
+        if scratch is not None:
+            scratch.update(fields=fields, pyr=pyr, ptrs=ptrs)
     fn = ref.ref_hbm_run
     fn.restype = None
     fn(ctypes.byref(hp), P(*[a.ctypes.data for a in src_planes]), I(*[a.strides[0] for a in src_planes]),

@@ -106,3 +106,90 @@ def test_frame_dequantise_then_inverse_transform(cuda, domain_kind):
         lib.schro_gpuframe_to_cpu(host, work)
     for c in range(3):
         assert np.array_equal(compat.frame_plane(host, c), want[c]), (domain_kind, c)
+
+
+# ---- widening variant: s16 quantised coefficients -> s32 coefficient frame --------------------
+def gpu_dequant_widen(planes_per_pic, depth, hcb, vcb, quant_per_pic):
+    import torch
+    from schroedinger_b200 import device as dev
+    sizes = [(p.shape[1], p.shape[0]) for p in planes_per_pic[0]]
+    src = dev.PictureSlab(dev.FrameLayout("s16", sizes), len(planes_per_pic))
+    dst = dev.PictureSlab(dev.FrameLayout("s32", sizes), len(planes_per_pic))
+    for i, planes in enumerate(planes_per_pic):
+        for c, a in enumerate(planes):
+            src.upload(i, c, a)
+    q = np.concatenate([np.concatenate([qq.reshape(-1) for qq in qs]) for qs in quant_per_pic]).astype(np.int32)
+    dev.dequantise_widen(src, dst, depth, hcb, vcb, torch.from_numpy(q).cuda())
+    return ([[dst.download(i, c) for c in range(len(planes))] for i, planes in enumerate(planes_per_pic)],
+            [[src.download(i, c) for c in range(len(planes))] for i, planes in enumerate(planes_per_pic)])
+
+
+def test_dequantise_widen_golden(cuda):
+    """the compiled reference's s32 program on the sign-extended s16 golden inputs (full-range values
+    included); the s16 source is left untouched"""
+    n = 0
+    for i in range(int(GOLD["ncases"])):
+        if f"c{i}_wide" not in GOLD.files:
+            continue
+        depth, hcb, vcb = int(GOLD[f"c{i}_depth"]), GOLD[f"c{i}_hcb"].tolist(), GOLD[f"c{i}_vcb"].tolist()
+        a = GOLD[f"c{i}_in"]
+        got, src_after = gpu_dequant_widen([[a]], depth, hcb, vcb, [[GOLD[f"c{i}_quant"]]])
+        assert got[0][0].dtype == np.int32 and np.array_equal(got[0][0], GOLD[f"c{i}_wide"]), i
+        assert np.array_equal(src_after[0][0], a), i
+        n += 1
+    assert n >= 10
+
+
+def test_dequantise_widen_2160p(cuda):
+    """BASELINE shape, two pictures x three components, against the oracle's s32 program"""
+    rng = np.random.default_rng(12)
+    depth, hcb, vcb = 5, [1, 1, 2, 4, 8, 12], [1, 1, 2, 3, 6, 8]
+    pics, quants, wants = [], [], []
+    for _ in range(2):
+        planes, qs, ws = [], [], []
+        for (pw, ph) in ((3840, 2176), (1920, 1088), (1920, 1088)):
+            a, q = make_case(rng, np.int16, pw, ph, depth, hcb, vcb, TABLES, False)
+            planes.append(a); qs.append(q)
+            ws.append(helpers.cpu_dequantise(ORACLE, "oracle", a.astype(np.int32), depth, hcb, vcb, q))
+        pics.append(planes); quants.append(qs); wants.append(ws)
+    got, _ = gpu_dequant_widen(pics, depth, hcb, vcb, quants)
+    for i in range(2):
+        for c in range(3):
+            assert np.array_equal(got[i][c], wants[i][c]), (i, c)
+
+
+@pytest.mark.parametrize("domain_kind", ["malloc", "pinned_to_cuda"])
+def test_frame_dequantise_widen_then_inverse_transform(cuda, domain_kind):
+    """What the e2e leg does per picture: s16 quantised coefficients (host) -> device s32 coefficient
+    frame -> inverse transform, through the drop-in layer."""
+    import ctypes
+    from schroedinger_b200 import compat, lib
+    rng = np.random.default_rng(78)
+    w, h, depth, filt = 352, 288, 4, 6
+    params = compat.make_params(w, h, filt, depth)
+    hcb, vcb = [1, 1, 2, 3, 4], [1, 1, 2, 2, 3]
+    for i in range(depth + 1):
+        params.horiz_codeblocks[i], params.vert_codeblocks[i] = hcb[i], vcb[i]
+    iw, ih = params.iwt_luma_width, params.iwt_luma_height
+    src_dom = compat.pinned_domain() if domain_kind != "malloc" else None
+    dst_dom = compat.cuda_domain() if domain_kind != "malloc" else None
+    src = compat.frame_new_and_alloc(src_dom, compat.FORMAT_S16_420, iw, ih)
+    dst = compat.frame_new_and_alloc(dst_dom, compat.FORMAT_S32_420, iw, ih)
+    out = compat.frame_new_and_alloc(None, compat.FORMAT_S32_420, iw, ih)
+    want, pairs = [], []
+    for c in range(3):
+        v = compat.frame_plane(src, c)
+        a, q = make_case(rng, np.int16, v.shape[1], v.shape[0], depth, hcb, vcb, TABLES, False)
+        v[...] = a
+        pairs.append(q)
+        d = helpers.cpu_dequantise(ORACLE, "oracle", a.astype(np.int32), depth, hcb, vcb, q)
+        want.append(helpers.cpu_wavelet(ORACLE, "oracle", "inv", d, filt, depth))
+    table = np.ascontiguousarray(np.concatenate([q.reshape(-1) for q in pairs]).astype(np.int32))
+    lib.schro_b200_frame_dequantise_widen(dst, src, ctypes.byref(params), table.ctypes.data_as(ctypes.c_void_p))
+    lib.schro_frame_inverse_iwt_transform(dst, ctypes.byref(params))
+    if dst_dom is not None:
+        lib.schro_gpuframe_to_cpu(out, dst)
+    else:
+        out = dst
+    for c in range(3):
+        assert np.array_equal(compat.frame_plane(out, c), want[c]), (domain_kind, c)

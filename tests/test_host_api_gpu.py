@@ -189,6 +189,81 @@ def test_motion_render_drop_in(cuda, add, domain_kind):
     lib.schro_motion_free(motion)
 
 
+@pytest.mark.parametrize("add", [1, 0])
+def test_motion_render_padded_addframe_1080p(cuda, add):
+    """Both reference call sites pass a picture-size dest and an iwt-PADDED addframe (1080 -> 1088 rows
+    at depth 4: schrodecoder.c:1784, schroencoder.c:2447); the rendered area is dest's
+    (schromotion8.c:722-751).  Nothing may be written below row 1080: not into the addframe's padding,
+    not into the output frame's border."""
+    from schroedinger_b200 import compat, lib
+    rng = np.random.default_rng(32)
+    w, h = 1920, 1080
+    case = helpers.ObmcCase(ORACLE, w, h, rng=rng)
+    want = helpers.oracle_obmc(ORACLE, case, add)
+    params = compat.make_params(w, h, 0, 4, num_refs=2, xblen=case.xblen, yblen=case.yblen,
+                                xbsep=case.xbsep, ybsep=case.ybsep, mv_precision=case.prec)
+    iw, ih = params.iwt_luma_width, params.iwt_luma_height
+    assert (iw, ih) == (1920, 1088)
+    dom = compat.cuda_domain()
+
+    def to_dev(host):
+        f = host.contents
+        d = compat.frame_new_and_alloc(dom, f.format, f.width, f.height, f.extension, f.is_upsampled)
+        lib.schro_frame_to_gpu(d, host)
+        return d
+
+    refs = []
+    for planes in (case.ref0, case.ref1):
+        f = _new_u8_frame(compat, lib, w, h, 32, True, [p.phase(0, with_border=False) for p in planes])
+        lib.schro_frame_mc_edgeextend(f)
+        lib.schro_upsampled_frame_upsample(f)
+        refs.append(to_dev(f))
+    dest_h = compat.frame_new_and_alloc(None, compat.FORMAT_S16_420, w, h)
+    addf_h = compat.frame_new_and_alloc(None, compat.FORMAT_S16_420, iw, ih)
+    outf_h = compat.frame_new_and_alloc(None, compat.FORMAT_U8_420, w, h, 32, 1)
+    pad = []
+    for c in range(3):
+        a = compat.frame_plane(addf_h, c)
+        a[...] = rng.integers(-3000, 3000, size=a.shape)            # padding rows carry a pattern
+        a[:case.residual[c].shape[0], :] = case.residual[c]
+        pad.append(a[case.residual[c].shape[0]:, :].copy())
+        compat.frame_plane(dest_h, c)[...] = 0
+    out_all = np.ctypeslib.as_array(ctypes.cast(outf_h.contents.regions[0], ctypes.POINTER(ctypes.c_uint8)),
+                                    shape=(sum(outf_h.contents.components[k].length for k in range(3)),))
+    out_all[...] = 0x5a
+    out_before = out_all.copy()
+    dest, addf, outf = to_dev(dest_h), to_dev(addf_h), to_dev(outf_h)
+    motion = lib.schro_motion_new(ctypes.byref(params), refs[0], refs[1])
+    ctypes.memmove(motion.contents.motion_vectors, case.mvs.ctypes.data, case.mvs.nbytes)
+    lib.schro_motion_render(motion, dest, addf, add, outf if add else None)
+    lib.schro_gpuframe_to_cpu(dest_h, dest)
+    lib.schro_gpuframe_to_cpu(addf_h, addf)
+    lib.schro_gpuframe_to_cpu(outf_h, outf)
+    for c in range(3):
+        rows = case.residual[c].shape[0]
+        assert np.array_equal(compat.frame_plane(dest_h, c), want[c][0]), ("acc", c)
+        assert np.array_equal(compat.frame_plane(addf_h, c)[rows:, :], pad[c]), ("addframe padding", c)
+        if add:
+            assert np.array_equal(compat.frame_plane(outf_h, c), want[c][2]), ("out", c)
+        else:
+            assert np.array_equal(compat.frame_plane(addf_h, c)[:rows, :], want[c][1]), ("residual", c)
+    if add:
+        # everything outside the three picture areas of the output frame is as it was
+        touched = out_all != out_before
+        inside = np.zeros_like(touched)
+        base = outf_h.contents.regions[0]
+        for k in range(3):
+            comp = outf_h.contents.components[k]
+            off = comp.data - base
+            for y in range(comp.height):
+                inside[off + y * comp.stride: off + y * comp.stride + comp.width] = True
+        assert not (touched & ~inside).any()
+    lib.schro_motion_free(motion)
+    for f in refs + [dest, addf, outf, dest_h, addf_h, outf_h]:
+        lib.schro_frame_unref(f)
+    lib.schro_memory_domain_free(dom)
+
+
 def test_hbm_drop_in(cuda):
     """Pyramid with schro_frame_downsample + schro_frame_mc_edgeextend (schroanalysis.c:9-28),
     then schro_hbm_scan and the level-0 refinement (schromotionest.c:76-77, 123-127)."""

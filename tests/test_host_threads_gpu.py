@@ -193,6 +193,76 @@ def test_block_matching_from_many_threads_matches_one_thread(cuda):
     lib.schro_memory_domain_free(cuda_dom)
 
 
+def test_block_matching_scan_on_one_thread_read_and_free_on_another(cuda):
+    """SchroAsync moves the stages of a picture between workers: thread A enqueues the search (and
+    returns without waiting -- the fields stay on the device), thread B reads level 0 and frees the
+    object.  Host pyramid frames make every search allocate pooled device blocks on A that B hands
+    back; far more than 64 rounds (the size of the per-thread pool this replaced)."""
+    import queue
+    from schroedinger_b200 import compat, lib
+    w, h, levels = 176, 144, 2
+    src, ref = helpers.panning_pair(w, h, np.random.default_rng(6), (2, -1))
+    params = compat.make_params(w, h, xbsep=8, ybsep=8, xblen=12, yblen=12)
+    want, _, _ = helpers.oracle_hbm(ORACLE, src, ref, w, h, levels=levels)
+
+    def pyramid(img):
+        frames = []
+        cw, ch = w, h
+        for l in range(levels + 1):
+            frames.append(compat.frame_new_and_alloc(None, compat.FORMAT_U8_420, cw, ch, 32 if l == 0 else 8, 0))
+            cw, ch = (cw + 1) // 2, (ch + 1) // 2
+        for c in range(3):
+            compat.frame_plane(frames[0], c)[...] = img[c]
+        lib.schro_frame_mc_edgeextend(frames[0])
+        for l in range(levels):
+            lib.schro_frame_downsample(frames[l + 1], frames[l])
+            lib.schro_frame_mc_edgeextend(frames[l + 1])
+        return frames
+
+    sp, rp = pyramid(src), pyramid(ref)
+    arr = compat.FrameP * (levels + 1)
+    n = params.x_num_blocks * params.y_num_blocks
+    rounds = 150
+    q = queue.Queue(maxsize=4)
+    bad = []
+
+    def producer():
+        for _ in range(rounds):
+            hbm = lib.schro_hbm_new_from_frames(ctypes.byref(params), 0, levels, 0, arr(*sp), arr(*rp))
+            lib.schro_hbm_scan(hbm)
+            lib.schro_hierarchical_bm_scan_hint(hbm, 0, 3)
+            q.put(hbm)
+        q.put(None)
+        lib.schro_b200_thread_release()
+
+    def consumer():
+        k = 0
+        while True:
+            hbm = q.get()
+            if hbm is None:
+                break
+            mf = lib.schro_hbm_motion_field(hbm, 0)
+            got = np.ctypeslib.as_array(ctypes.cast(mf.contents.motion_vectors, ctypes.POINTER(ctypes.c_uint8)),
+                                        shape=(n * 20,)).copy().view(helpers.MV_DTYPE)
+            for f in ("flags", "metric", "v"):
+                if not np.array_equal(got[f], want[0][f]):
+                    bad.append((k, f))
+            if k % 50 == 0:                      # now and then a coarser level too
+                mf1 = lib.schro_hbm_motion_field(hbm, 1)
+                g1 = np.ctypeslib.as_array(ctypes.cast(mf1.contents.motion_vectors, ctypes.POINTER(ctypes.c_uint8)),
+                                           shape=(n * 20,)).copy().view(helpers.MV_DTYPE)
+                if not np.array_equal(g1["v"], want[1]["v"]):
+                    bad.append((k, "level 1"))
+            lib.schro_hbm_unref(hbm)
+            k += 1
+        lib.schro_b200_thread_release()
+
+    _run_threads([producer, consumer])
+    assert not bad, bad[:5]
+    for f in sp + rp:
+        lib.schro_frame_unref(f)
+
+
 def test_polling_wait_mode_and_thread_sync(cuda, monkeypatch):
     """SB2_HOST_WAIT_US switches the host waits from the driver's blocking wait to polling (read
     when a thread first enters the library); results are the same either way, and
