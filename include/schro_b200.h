@@ -160,6 +160,14 @@ int sb2_obmc_render (const sb2_obmc_params *params, const void *motion_vectors,
     size_t mv_picture_pitch, const sb2_slab *ref0, const sb2_slab *ref1, const sb2_slab *acc,
     const sb2_slab *residual, int residual_is_s32, int add, const sb2_slab *out, void *stream);
 
+/* Three kernels implement the renderer: 1 = gather out of TMA-staged reference regions (block overlap
+ * of at most one block, 32-pixel borders: every Dirac preset), 2 = block-major scatter with
+ * shared-memory atomics, 3 = one thread per pixel (any geometry).  0 picks by geometry; tests force
+ * each (also: environment variable SB2_OBMC_KERNEL). */
+void sb2_obmc_force_kernel (int which);
+/* which of the three the calling thread's last sb2_obmc_render launched */
+int sb2_obmc_last_kernel (void);
+
 /* ---- SAD / hierarchical block matching ----------------------------------- */
 
 typedef struct {
@@ -199,6 +207,30 @@ int sb2_hbm_scan_hint (const sb2_hbm_params *params, const sb2_slab *src_level,
 int sb2_sad_u8 (const uint8_t *a, int a_stride, const uint8_t *b, int b_stride,
     const int64_t *a_offset, const int64_t *b_offset, int n, int width, int height,
     uint32_t *sad, void *stream);
+
+/* The metric-scan entry points on their own, batched: n independent scans / block SADs per launch.
+ * sb2_metric_scan = schro_metric_scan_do_scan (schroedinger/schrometric.c:31-116):
+ *   metrics[k][i * scan_height + j] = luma SAD of the block at (x, y) against (ref_x + i, ref_y + j);
+ *   chroma_metrics likewise (zero unless use_chroma; 42 x 42 entries per scan as SchroMetricScan,
+ *   schroedinger/schrometric.h:38-53).  The window comes from schro_metric_scan_setup (:174-214), which is
+ *   host arithmetic (host layer).
+ * sb2_metric_block_sad3 = schro_metric_fast_block / schro_metric_block_sad_slow (:332-414): Y + U + V SAD
+ *   of the block at (x, y) against (x + dx, y + dy), INT_MAX when a block leaves frame +- extension. */
+typedef struct {
+  int picture;                          /* index into the slabs */
+  int x, y, block_width, block_height;
+  int ref_x, ref_y, scan_width, scan_height;
+} sb2_metric_scan_desc;
+typedef struct {
+  int picture;
+  int x, y, dx, dy;
+} sb2_metric_block_desc;
+int sb2_metric_scan (const sb2_slab *src, const sb2_slab *ref, int chroma_h_shift, int chroma_v_shift,
+    int use_chroma, const sb2_metric_scan_desc *descs /* device */, int n, uint32_t *metrics /* device */,
+    uint32_t *chroma_metrics /* device or NULL */, void *stream);
+int sb2_metric_block_sad3 (const sb2_slab *src, const sb2_slab *ref, int extension, int block_width,
+    int block_height, int chroma_h_shift, int chroma_v_shift, const sb2_metric_block_desc *descs /* device */,
+    int n, int *metric /* device */, void *stream);
 
 /* schro_metric_get_dc (schroedinger/schrometric.c:253) and schro_metric_get_biref (:272);
  * one block, result in device memory */

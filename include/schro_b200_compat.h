@@ -19,6 +19,7 @@
 #ifndef SCHRO_B200_COMPAT_H
 #define SCHRO_B200_COMPAT_H
 
+#include <limits.h>
 #include <stdint.h>
 #include <stddef.h>
 
@@ -293,6 +294,11 @@ SchroFrame *schro_frame_new_and_alloc_full (SchroMemoryDomain *domain,
     SchroFrameFormat format, int width, int height, int extension, int upsampled);
 SchroFrame *schro_frame_ref (SchroFrame *frame);
 void schro_frame_unref (SchroFrame *frame);
+/* schroedinger/schroframe.c:699-724: a new frame of the same domain / format / size with the given
+ * extension and layout, filled by schro_frame_convert */
+SchroFrame *schro_frame_dup (SchroFrame *frame);
+SchroFrame *schro_frame_dup_extended (SchroFrame *frame, int extension);
+SchroFrame *schro_frame_dup_full (SchroFrame *frame, int extension, int is_upsampled);
 /* schroedinger/schrocuda.h:14-16 / schrogpuframe.h:14-15: move a frame between domains */
 void schro_frame_to_gpu (SchroFrame *dest, SchroFrame *src);
 void schro_gpuframe_to_cpu (SchroFrame *dest, SchroFrame *src);
@@ -339,6 +345,39 @@ void schro_motion_render_u8 (SchroMotion *motion, SchroFrame *dest,
     SchroFrame *addframe, int add, SchroFrame *output_frame);
 void schro_motion_init_obmc_weight (SchroMotion *motion);
 
+/* schroedinger/schrometric.h:16-53 */
+#define SCHRO_LIMIT_METRIC_SCAN 42
+#define SCHRO_METRIC_INVALID INT_MAX
+typedef struct _SchroMetricInfo SchroMetricInfo;
+struct _SchroMetricInfo {
+  SchroFrame *frame;
+  SchroFrame *ref_frame;
+  int block_width[3];
+  int block_height[3];
+  int h_shift[3];
+  int v_shift[3];
+  int (*metric) (SchroMetricInfo *info, int ref_x, int ref_y, int dx, int dy);
+  int (*metric_right) (SchroMetricInfo *info, int ref_x, int ref_y, int dx, int dy);
+  int (*metric_bottom) (SchroMetricInfo *info, int ref_x, int ref_y, int dx, int dy);
+  int (*metric_corner) (SchroMetricInfo *info, int ref_x, int ref_y, int dx, int dy);
+};
+typedef struct _SchroMetricScan {
+  SchroFrame *frame;
+  SchroFrame *ref_frame;
+  int block_width;
+  int block_height;
+  int x, y;
+  int ref_x, ref_y;
+  int scan_width;
+  int scan_height;
+  int gravity_scale;
+  int gravity_x, gravity_y;
+  int use_chroma;
+  /* output */
+  uint32_t metrics[SCHRO_LIMIT_METRIC_SCAN * SCHRO_LIMIT_METRIC_SCAN];
+  uint32_t chroma_metrics[SCHRO_LIMIT_METRIC_SCAN * SCHRO_LIMIT_METRIC_SCAN];
+} SchroMetricScan;
+
 /* ---- SAD primitives (schroedinger/schrometric.h:57-86) ---------------------- */
 int schro_metric_absdiff_u8 (uint8_t *a, int a_stride, uint8_t *b, int b_stride,
     int width, int height);
@@ -346,6 +385,16 @@ int schro_metric_get (SchroFrameData *src1, SchroFrameData *src2, int width, int
 int schro_metric_get_dc (SchroFrameData *src, int value, int width, int height);
 int schro_metric_get_biref (SchroFrameData *fd, SchroFrameData *src1, int weight1,
     SchroFrameData *src2, int weight2, int shift, int width, int height);
+/* the scan of one block (schroedinger/schrometric.c:31-214): window set-up (host arithmetic), the grid
+ * of SADs on the GPU (one launch, one wait -- callers with many blocks use sb2_metric_scan, which takes
+ * n scans per launch), arg-min with the reference's tie-break */
+void schro_metric_scan_setup (SchroMetricScan *scan, int dx, int dy, int dist, int use_chroma);
+void schro_metric_scan_do_scan (SchroMetricScan *scan);
+int schro_metric_scan_get_min (SchroMetricScan *scan, int *dx, int *dy, uint32_t *chroma_metric);
+/* 3-component block SAD of the candidate ranking (schroedinger/schrometric.c:332-414) */
+void schro_metric_info_init (SchroMetricInfo *info, SchroFrame *frame, SchroFrame *ref_frame,
+    int block_width, int block_height);
+int schro_metric_fast_block (SchroMetricInfo *info, int x, int y, int dx, int dy);
 
 /* ---- hierarchical block matching (schroedinger/schromotionest.h:112-120) ---- */
 SchroMotionField *schro_motion_field_new (int x_num_blocks, int y_num_blocks);

@@ -122,6 +122,20 @@ void oracle_hbm_scan_hint (const OraclePyrLevel *src, const OraclePyrLevel *ref,
     int shift, int h_range, int use_chroma,
     const OracleMotionVector *parent, OracleMotionVector *mf);
 
+/* The metric-scan entry points on their own (schroedinger/schrometric.c:31-214, 380-414):
+ * window set-up, the grid of SADs (metrics[i * scan_h + j], 42 x 42 arrays as SchroMetricScan has),
+ * the arg-min with the reference's tie-break, and the 3-component block SAD of the candidate ranking. */
+void oracle_metric_scan_setup (const OraclePyrLevel *f, int x, int y, int bw, int bh, int dx, int dy,
+    int dist, int *ref_x, int *ref_y, int *scan_w, int *scan_h);
+void oracle_metric_scan_do_scan (const OraclePyrLevel *src, const OraclePyrLevel *ref, int x, int y,
+    int bw, int bh, int ref_x, int ref_y, int scan_w, int scan_h, int use_chroma, uint32_t *metrics,
+    uint32_t *chroma_metrics);
+uint32_t oracle_metric_scan_get_min (const uint32_t *metrics, const uint32_t *chroma_metrics, int x, int y,
+    int ref_x, int ref_y, int scan_w, int scan_h, int gravity_x, int gravity_y, int use_chroma, int *dx,
+    int *dy, uint32_t *chroma_error);
+int oracle_metric_fast_block (const OraclePyrLevel *src, const OraclePyrLevel *ref, int bw, int bh, int x,
+    int y, int dx, int dy);
+
 #ifdef __cplusplus
 }
 #endif

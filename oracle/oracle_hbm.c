@@ -204,3 +204,93 @@ oracle_hbm_scan_hint (const OraclePyrLevel *src, const OraclePyrLevel *ref, int 
     }
   }
 }
+
+/* ---- the metric-scan entry points on their own (schrometric.c:31-214, 380-414) ------------- */
+
+/* schro_metric_scan_setup (:174-214): the scan window of a block at (x, y) around (dx, dy) */
+void
+oracle_metric_scan_setup (const OraclePyrLevel *f, int x, int y, int bw, int bh, int dx, int dy, int dist,
+    int *ref_x, int *ref_y, int *scan_w, int *scan_h)
+{
+  int xmin = maxi (maxi (-bw, x + dx - dist), -f->ext);
+  int ymin = maxi (maxi (-bh, y + dy - dist), -f->ext);
+  int xmax = mini (mini (f->width, x + dx + dist), f->width - bw + f->ext);
+  int ymax = mini (mini (f->height, y + dy + dist), f->height - bh + f->ext);
+  *ref_x = xmin;
+  *ref_y = ymin;
+  *scan_w = xmax - xmin + 1;
+  *scan_h = ymax - ymin + 1;
+}
+
+/* schro_metric_scan_do_scan (:31-116): metrics[i * scan_h + j] = luma SAD at (ref_x + i, ref_y + j);
+ * chroma_metrics = 0, or with use_chroma the sum of both chroma SADs computed on the sub-sampled grid
+ * and duplicated onto the luma grid exactly as the reference does (4:2:0 duplication, :73-115) */
+void
+oracle_metric_scan_do_scan (const OraclePyrLevel *src, const OraclePyrLevel *ref, int x, int y, int bw, int bh,
+    int ref_x, int ref_y, int scan_w, int scan_h, int use_chroma, uint32_t *metrics, uint32_t *chroma_metrics)
+{
+  int i, j, k;
+  for (i = 0; i < scan_w; i++)
+    for (j = 0; j < scan_h; j++)
+      metrics[i * scan_h + j] = oracle_sad_u8 (src->data[0] + (ptrdiff_t) src->stride[0] * y + x, src->stride[0],
+          ref->data[0] + (ptrdiff_t) ref->stride[0] * (ref_y + j) + ref_x + i, ref->stride[0], bw, bh);
+  memset (chroma_metrics, 0, sizeof (uint32_t) * 42 * 42);
+  if (!use_chroma) return;
+  {
+    const int skip_h = 1 << src->h_shift, skip_v = 1 << src->v_shift;
+    const int cx = x / skip_h, cy = y / skip_v, crx = ref_x / skip_h, cry = ref_y / skip_v;
+    const int cbw = bw / skip_h, cbh = bh / skip_v;
+    const int sw = scan_w / skip_h + scan_w % skip_h, sh = scan_h / skip_v + scan_h % skip_v;
+    uint32_t *tmp = calloc (42 * 42 * 4 + 64, sizeof (uint32_t));
+    for (k = 1; k < 3; k++) {
+      for (i = 0; i < sw; i++) {
+        for (j = 0; j < sh; j++) {
+          const uint32_t v = oracle_sad_u8 (src->data[k] + (ptrdiff_t) src->stride[k] * cy + cx, src->stride[k],
+              ref->data[k] + (ptrdiff_t) ref->stride[k] * (cry + j) + crx + i, ref->stride[k], cbw, cbh);
+          tmp[i * 2 * scan_h + j * 2] = v;
+          if (skip_v > 1) tmp[i * 2 * scan_h + 1 + j * 2] = v;
+        }
+        if (skip_h > 1)
+          for (j = 0; j < scan_h; j++) tmp[(i * 2 + 1) * scan_h + j] = tmp[i * 2 * scan_h + j];
+      }
+      for (j = 0; j < scan_h; j++)
+        for (i = 0; i < scan_w; i++) chroma_metrics[i * scan_h + j] += tmp[i * scan_h + j];
+    }
+    free (tmp);
+  }
+}
+
+/* schro_metric_scan_get_min (:121-171): the seed (gravity) wins ties, else the first strict minimum
+ * in x-outer / y-inner order; returns the luma metric */
+uint32_t
+oracle_metric_scan_get_min (const uint32_t *metrics, const uint32_t *chroma_metrics, int x, int y, int ref_x, int ref_y,
+    int scan_w, int scan_h, int gravity_x, int gravity_y, int use_chroma, int *dx, int *dy, uint32_t *chroma_error)
+{
+  int i = gravity_x + x - ref_x, j = gravity_y + y - ref_y;
+  uint32_t min_metric = metrics[j + i * scan_h], min_chroma = 0, min_total = 0;
+  if (use_chroma) {
+    min_chroma = chroma_metrics[j + i * scan_h];
+    min_total = min_metric + min_chroma;
+  }
+  for (i = 0; i < scan_w; i++)
+    for (j = 0; j < scan_h; j++) {
+      const uint32_t m = metrics[i * scan_h + j], c = chroma_metrics[i * scan_h + j];
+      if (use_chroma ? (m + c < min_total) : (m < min_metric)) {
+        min_total = m + c;
+        min_metric = m;
+        min_chroma = c;
+        *dx = ref_x + i - x;
+        *dy = ref_y + j - y;
+      }
+    }
+  *chroma_error = min_chroma;
+  return min_metric;
+}
+
+/* schro_metric_fast_block (:410-414) = schro_metric_block_sad_slow (:332-375) */
+int
+oracle_metric_fast_block (const OraclePyrLevel *src, const OraclePyrLevel *ref, int bw, int bh, int x, int y,
+    int dx, int dy)
+{
+  return block_sad3 (src, ref, bw, bh, x, y, dx, dy);
+}

@@ -30,7 +30,7 @@ ref_init (void)
   }
 }
 
-int oracle_ref_harness_version (void) { return 2; }
+int oracle_ref_harness_version (void) { return 3; }
 
 static void
 fill_fd (SchroFrameData *fd, void *data, int stride, int width, int height,
@@ -355,6 +355,48 @@ ref_hbm_run (const RefHbmParams *hp, void **src, const int *src_stride, void **r
 }
 
 /* schro_metric_absdiff_u8 (schroedinger/schrometric.c:10) */
+/* schro_metric_scan_setup / _do_scan / _get_min and schro_metric_fast_block
+ * (schroedinger/schrometric.c:31-214, 380-414) on two 4:2:0 u8 pictures loaded into frames with a
+ * 32-pixel border.  q: x, y, block_width, block_height, dx, dy, dist, use_chroma.  out: ref_x, ref_y,
+ * scan_width, scan_height, min dx, min dy, min metric, min chroma metric, fast_block metric. */
+void
+ref_metric_scan (int width, int height, void **src, const int *src_stride, void **ref, const int *ref_stride,
+    const int *q, int *out, uint32_t *metrics, uint32_t *chroma_metrics)
+{
+  SchroFrameFormat fmt;
+  SchroMetricScan *scan = calloc (1, sizeof (SchroMetricScan));
+  SchroMetricInfo info;
+  uint32_t chroma = 0;
+  int dx = q[4], dy = q[5];
+  ref_init ();
+  fmt = schro_params_get_frame_format (8, SCHRO_CHROMA_420);
+  scan->frame = load_frame (fmt, width, height, src, src_stride);
+  scan->ref_frame = load_frame (fmt, width, height, ref, ref_stride);
+  scan->x = q[0];
+  scan->y = q[1];
+  scan->block_width = q[2];
+  scan->block_height = q[3];
+  scan->gravity_x = dx;
+  scan->gravity_y = dy;
+  schro_metric_scan_setup (scan, dx, dy, q[6], q[7]);
+  schro_metric_scan_do_scan (scan);
+  out[6] = schro_metric_scan_get_min (scan, &dx, &dy, &chroma);
+  out[0] = scan->ref_x;
+  out[1] = scan->ref_y;
+  out[2] = scan->scan_width;
+  out[3] = scan->scan_height;
+  out[4] = dx;
+  out[5] = dy;
+  out[7] = (int) chroma;
+  memcpy (metrics, scan->metrics, sizeof (scan->metrics));
+  memcpy (chroma_metrics, scan->chroma_metrics, sizeof (scan->chroma_metrics));
+  schro_metric_info_init (&info, scan->frame, scan->ref_frame, q[2], q[3]);
+  out[8] = schro_metric_fast_block (&info, q[0], q[1], q[4], q[5]);
+  schro_frame_unref (scan->frame);
+  schro_frame_unref (scan->ref_frame);
+  free (scan);
+}
+
 uint32_t
 ref_sad_u8 (const uint8_t *a, int a_stride, const uint8_t *b, int b_stride, int width, int height)
 {

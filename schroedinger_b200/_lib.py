@@ -76,11 +76,17 @@ _opt("sb2_dequantise_widen", ctypes.c_int, [_SP, _SP, ctypes.POINTER(DequantPara
 _opt("sb2_edgeextend_upsample", ctypes.c_int, [_SP, ctypes.c_int, ctypes.c_void_p])
 _opt("sb2_obmc_render", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, _SP, _SP, _SP,
                                       _SP, ctypes.c_int, ctypes.c_int, _SP, ctypes.c_void_p])
+_opt("sb2_obmc_force_kernel", None, [ctypes.c_int])
+_opt("sb2_obmc_last_kernel", ctypes.c_int, [])
 _opt("sb2_hbm_workspace_bytes", ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int])
 _opt("sb2_hbm_force_generic", None, [ctypes.c_int])
 _opt("sb2_hbm_scan_hint", ctypes.c_int, [ctypes.c_void_p, _SP, _SP, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                         ctypes.c_size_t, ctypes.c_void_p])
+_opt("sb2_metric_scan", ctypes.c_int, [_SP, _SP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p])
+_opt("sb2_metric_block_sad3", ctypes.c_int, [_SP, _SP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p])
 _opt("sb2_sad_u8", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                  ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                  ctypes.c_void_p])

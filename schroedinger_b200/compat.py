@@ -164,6 +164,12 @@ _proto("schro_motion_new", ctypes.POINTER(SchroMotion), [ParamsP, FrameP, FrameP
 _proto("schro_motion_free", None, [ctypes.POINTER(SchroMotion)])
 _proto("schro_motion_render", None, [ctypes.POINTER(SchroMotion), FrameP, FrameP, ctypes.c_int, FrameP])
 _proto("schro_motion_render_u8", None, [ctypes.POINTER(SchroMotion), FrameP, FrameP, ctypes.c_int, FrameP])
+_proto("schro_metric_scan_setup", None, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int])
+_proto("schro_metric_scan_do_scan", None, [ctypes.c_void_p])
+_proto("schro_metric_scan_get_min", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p])
+_proto("schro_metric_info_init", None, [ctypes.c_void_p, FrameP, FrameP, ctypes.c_int, ctypes.c_int])
+_proto("schro_metric_fast_block", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int])
+_proto("schro_frame_dup_full", FrameP, [FrameP, ctypes.c_int, ctypes.c_int])
 _proto("schro_metric_absdiff_u8", ctypes.c_int,
        [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int])
 _proto("schro_hbm_new_from_frames", ctypes.POINTER(SchroHierBm),

@@ -479,6 +479,141 @@ sad_biref_kernel (const uint8_t *a, int as, const uint8_t *s1, int s1s, int w1, 
   if (threadIdx.x == 0) *out = (int) part;
 }
 
+// ---- the metric-scan entry points on their own (schrometric.c:31-214, 332-414) ---------------
+// One CTA per scan: the threads split the scan positions; metrics[i * scan_h + j] as
+// schro_metric_scan_do_scan lays them out.  Chroma (use_chroma) follows the reference's
+// duplication scheme: the chroma SADs are computed on the sub-sampled grid and entry (i, j) of the
+// luma grid reads (i >> h_shift, j >> v_shift) of it (:73-115).
+struct ScanArgs {
+  PlaneSet src, ref;
+  const sb2_metric_scan_desc *desc;
+  uint32_t *metrics, *chroma;           // n x 42*42 each (chroma may be null)
+  int hs, vs, use_chroma;
+};
+
+__global__ void __launch_bounds__ (128)
+metric_scan_kernel (const ScanArgs a)
+{
+  const sb2_metric_scan_desc d = a.desc[blockIdx.x];
+  const uint8_t *sp[3], *rp[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    sp[k] = reinterpret_cast<const uint8_t *> (plane_ptr (a.src, d.picture, k));
+    rp[k] = reinterpret_cast<const uint8_t *> (plane_ptr (a.ref, d.picture, k));
+  }
+  uint32_t *m = a.metrics + (size_t) blockIdx.x * (42 * 42);
+  uint32_t *cm = a.chroma ? a.chroma + (size_t) blockIdx.x * (42 * 42) : nullptr;
+  const int npos = d.scan_width * d.scan_height;
+  const int skip_h = 1 << a.hs, skip_v = 1 << a.vs;
+  for (int p = threadIdx.x; p < npos; p += blockDim.x) {
+    const int i = p / d.scan_height, j = p - i * d.scan_height;
+    m[p] = block_sad (sp[0] + (ptrdiff_t) d.y * a.src.stride[0] + d.x, a.src.stride[0],
+        rp[0] + (ptrdiff_t) (d.ref_y + j) * a.ref.stride[0] + d.ref_x + i, a.ref.stride[0], d.block_width, d.block_height);
+    if (cm) {
+      unsigned c = 0;
+      if (a.use_chroma) {
+        const int cx = d.x / skip_h, cy = d.y / skip_v, crx = d.ref_x / skip_h + (i >> a.hs), cry = d.ref_y / skip_v + (j >> a.vs);
+        for (int k = 1; k < 3; k++)
+          c += block_sad (sp[k] + (ptrdiff_t) cy * a.src.stride[k] + cx, a.src.stride[k],
+              rp[k] + (ptrdiff_t) cry * a.ref.stride[k] + crx, a.ref.stride[k], d.block_width / skip_h, d.block_height / skip_v);
+      }
+      cm[p] = c;
+    }
+  }
+}
+
+// schro_metric_block_sad_slow (schrometric.c:332-375) for n independent (block, vector) pairs: one warp each
+struct Sad3Args {
+  PlaneSet src, ref;
+  const sb2_metric_block_desc *desc;
+  int *out;
+  int n, width, height, cw, ch, ext, bw, bh, hs, vs;
+};
+
+__global__ void __launch_bounds__ (128)
+metric_block_sad3_kernel (const Sad3Args a)
+{
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= a.n) return;
+  const sb2_metric_block_desc d = a.desc[g];
+  const int e = a.ext;
+  const bool ok = !(d.x < -e || d.y < -e || d.x + a.bw > a.width + e || d.y + a.bh > a.height + e) &&
+      !(d.x + d.dx < -e || d.y + d.dy < -e || d.x + d.dx + a.bw > a.width + e || d.y + d.dy + a.bh > a.height + e);
+  unsigned part = 0;
+  if (ok) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const int hs = c ? a.hs : 0, vs = c ? a.vs : 0;
+      const int sx = d.x >> hs, sy = d.y >> vs, rx = (d.x + d.dx) >> hs, ry = (d.y + d.dy) >> vs;
+      const int w = min (max (0, (c ? a.cw : a.width) - sx), a.bw >> hs);
+      const int h = min (max (0, (c ? a.ch : a.height) - sy), a.bh >> vs);
+      const uint8_t *s = reinterpret_cast<const uint8_t *> (plane_ptr (a.src, d.picture, c));
+      const uint8_t *r = reinterpret_cast<const uint8_t *> (plane_ptr (a.ref, d.picture, c));
+      for (int p = lane; p < w * h; p += 32) {
+        const int yy = p / w, xx = p - yy * w;
+        part += (unsigned) abs ((int) __ldg (s + (ptrdiff_t) (sy + yy) * a.src.stride[c] + sx + xx)
+            - (int) __ldg (r + (ptrdiff_t) (ry + yy) * a.ref.stride[c] + rx + xx));
+      }
+    }
+  }
+  part = warp_sum (part);
+  if (lane == 0) a.out[g] = ok ? (int) part : INT_MAX;
+}
+
+extern "C" int
+sb2_metric_scan (const sb2_slab *src, const sb2_slab *ref, int chroma_h_shift, int chroma_v_shift, int use_chroma,
+    const sb2_metric_scan_desc *descs, int n, uint32_t *metrics, uint32_t *chroma_metrics, void *stream)
+{
+  if (!src || !ref || !descs || !metrics || n < 0 || src->ncomp != 3 || ref->ncomp != 3)
+    return set_error (SB2_ERR_ARG, "sb2_metric_scan: bad argument");
+  if (use_chroma && !chroma_metrics) return set_error (SB2_ERR_ARG, "sb2_metric_scan: chroma scan needs the chroma array");
+  if (n == 0) return SB2_OK;
+  ScanArgs a;
+  a.src = planeset_from_slab (src);
+  a.ref = planeset_from_slab (ref);
+  a.desc = descs;
+  a.metrics = metrics;
+  a.chroma = chroma_metrics;
+  a.hs = chroma_h_shift;
+  a.vs = chroma_v_shift;
+  a.use_chroma = use_chroma;
+  {
+    LaunchScope scope ("metric_scan", 0.0, as_stream (stream));
+    metric_scan_kernel<<<n, 128, 0, as_stream (stream)>>> (a);
+  }
+  return check_cuda (cudaGetLastError (), "metric_scan_kernel launch");
+}
+
+extern "C" int
+sb2_metric_block_sad3 (const sb2_slab *src, const sb2_slab *ref, int extension, int block_width, int block_height,
+    int chroma_h_shift, int chroma_v_shift, const sb2_metric_block_desc *descs, int n, int *metric, void *stream)
+{
+  if (!src || !ref || !descs || !metric || n < 0 || src->ncomp != 3 || ref->ncomp != 3 || block_width < 1 || block_height < 1)
+    return set_error (SB2_ERR_ARG, "sb2_metric_block_sad3: bad argument");
+  if (n == 0) return SB2_OK;
+  Sad3Args a;
+  a.src = planeset_from_slab (src);
+  a.ref = planeset_from_slab (ref);
+  a.desc = descs;
+  a.out = metric;
+  a.n = n;
+  a.width = src->width[0];
+  a.height = src->height[0];
+  a.cw = src->width[1];
+  a.ch = src->height[1];
+  a.ext = extension;
+  a.bw = block_width;
+  a.bh = block_height;
+  a.hs = chroma_h_shift;
+  a.vs = chroma_v_shift;
+  {
+    LaunchScope scope ("metric_block_sad3", 0.0, as_stream (stream));
+    metric_block_sad3_kernel<<<ceil_div (n, 4), 128, 0, as_stream (stream)>>> (a);
+  }
+  return check_cuda (cudaGetLastError (), "metric_block_sad3_kernel launch");
+}
+
 extern "C" int
 sb2_sad_dc_u8 (const uint8_t *a, int a_stride, int value, int width, int height, int *sad, void *stream)
 {

@@ -454,3 +454,176 @@ schro_metric_get_biref (SchroFrameData *fd, SchroFrameData *src1, int weight1, S
   sb2h_sync (cx);
   return result;
 }
+
+/* ---- the scan of one block and the 3-component block SAD (schrometric.c:31-214, 332-414) ---- */
+void
+schro_metric_scan_setup (SchroMetricScan *scan, int dx, int dy, int dist, int use_chroma)
+{
+  int xmin, xmax, ymin, ymax;
+  SB2H_ASSERT (scan && scan->frame && scan->ref_frame && dist > 0);
+  /* the window is clipped to the block-sized margin around the picture and to the frame's border */
+  xmin = scan->x + dx - dist;
+  xmax = scan->x + dx + dist;
+  ymin = scan->y + dy - dist;
+  ymax = scan->y + dy + dist;
+  if (xmin < -scan->block_width) xmin = -scan->block_width;
+  if (ymin < -scan->block_height) ymin = -scan->block_height;
+  if (xmax > scan->frame->width) xmax = scan->frame->width;
+  if (ymax > scan->frame->height) ymax = scan->frame->height;
+  if (xmin < -scan->frame->extension) xmin = -scan->frame->extension;
+  if (ymin < -scan->frame->extension) ymin = -scan->frame->extension;
+  if (xmax > scan->frame->width - scan->block_width + scan->frame->extension)
+    xmax = scan->frame->width - scan->block_width + scan->frame->extension;
+  if (ymax > scan->frame->height - scan->block_height + scan->frame->extension)
+    ymax = scan->frame->height - scan->block_height + scan->frame->extension;
+  scan->ref_x = xmin;
+  scan->ref_y = ymin;
+  scan->scan_width = xmax - xmin + 1;
+  scan->scan_height = ymax - ymin + 1;
+  scan->use_chroma = use_chroma;
+  SB2H_ASSERT (scan->scan_width <= SCHRO_LIMIT_METRIC_SCAN && scan->scan_height <= SCHRO_LIMIT_METRIC_SCAN);
+}
+
+void
+schro_metric_scan_do_scan (SchroMetricScan *scan)
+{
+  Sb2hContext *cx = sb2h_context ();
+  Staged s, r;
+  sb2_metric_scan_desc d;
+  char *dbuf;
+  const size_t grid = sizeof (uint32_t) * SCHRO_LIMIT_METRIC_SCAN * SCHRO_LIMIT_METRIC_SCAN;
+  const size_t used = sizeof (uint32_t) * (size_t) scan->scan_width * scan->scan_height;
+  const int hs = SCHRO_FRAME_FORMAT_H_SHIFT (scan->frame->format), vs = SCHRO_FRAME_FORMAT_V_SHIFT (scan->frame->format);
+  /* the reference's own preconditions (schrometric.c:38-45) */
+  SB2H_ASSERT (scan->scan_width > 0 && scan->scan_height > 0);
+  SB2H_ASSERT (scan->ref_x >= -scan->frame->extension && scan->ref_y >= -scan->frame->extension);
+  SB2H_ASSERT (scan->ref_x + scan->block_width + scan->scan_width - 1 <= scan->frame->width + scan->frame->extension);
+  SB2H_ASSERT (scan->ref_y + scan->block_height + scan->scan_height - 1 <= scan->frame->height + scan->frame->extension);
+  if (scan->use_chroma && !(hs == 1 && vs == 1))
+    sb2h_fatal (__func__, "chroma scans are defined for 4:2:0 only (the reference's duplication scheme, schrometric.c:73-115)");
+  require_u8 (scan->frame, __func__);
+  require_u8 (scan->ref_frame, __func__);
+  stage_in (cx, &s, scan->frame, SB2H_BUF_IN, 1);
+  stage_in (cx, &r, scan->ref_frame, SB2H_BUF_OUT, 1);
+  d.picture = 0;
+  d.x = scan->x;
+  d.y = scan->y;
+  d.block_width = scan->block_width;
+  d.block_height = scan->block_height;
+  d.ref_x = scan->ref_x;
+  d.ref_y = scan->ref_y;
+  d.scan_width = scan->scan_width;
+  d.scan_height = scan->scan_height;
+  dbuf = sb2h_dev_buffer (cx, SB2H_BUF_AUX0, 256 + 2 * grid);
+  SB2H_CUDA (cudaMemcpyAsync (dbuf, &d, sizeof (d), cudaMemcpyDefault, cx->stream));
+  SB2H_CHECK (sb2_metric_scan (&s.slab, &r.slab, hs, vs, scan->use_chroma, (const sb2_metric_scan_desc *) dbuf, 1,
+          (uint32_t *) (dbuf + 256), (uint32_t *) (dbuf + 256 + grid), cx->stream), "sb2_metric_scan");
+  memset (scan->chroma_metrics, 0, sizeof (scan->chroma_metrics));
+  SB2H_CUDA (cudaMemcpyAsync (scan->metrics, dbuf + 256, used, cudaMemcpyDefault, cx->stream));
+  if (scan->use_chroma)
+    SB2H_CUDA (cudaMemcpyAsync (scan->chroma_metrics, dbuf + 256 + grid, used, cudaMemcpyDefault, cx->stream));
+  sb2h_sync (cx);
+}
+
+int
+schro_metric_scan_get_min (SchroMetricScan *scan, int *dx, int *dy, uint32_t *chroma_error)
+{
+  /* the seed (gravity) position starts as the best, a later position replaces it only when strictly
+   * better, positions are visited column by column */
+  const int h = scan->scan_height;
+  int i = scan->gravity_x + scan->x - scan->ref_x, j = scan->gravity_y + scan->y - scan->ref_y;
+  uint32_t best = scan->metrics[j + i * h], best_chroma = 0, best_total = 0;
+  SB2H_ASSERT (scan->scan_width > 0 && scan->scan_height > 0);
+  if (scan->use_chroma) {
+    best_chroma = scan->chroma_metrics[j + i * h];
+    best_total = best + best_chroma;
+  }
+  for (i = 0; i < scan->scan_width; i++)
+    for (j = 0; j < h; j++) {
+      const uint32_t m = scan->metrics[i * h + j], c = scan->chroma_metrics[i * h + j];
+      const int better = scan->use_chroma ? (m + c < best_total) : (m < best);
+      if (better) {
+        best = m;
+        best_chroma = c;
+        best_total = m + c;
+        *dx = scan->ref_x + i - scan->x;
+        *dy = scan->ref_y + j - scan->y;
+      }
+    }
+  *chroma_error = best_chroma;
+  return (int) best;
+}
+
+static int
+metric_block_sad3 (SchroMetricInfo *info, int x, int y, int dx, int dy)
+{
+  Sb2hContext *cx = sb2h_context ();
+  Staged s, r;
+  sb2_metric_block_desc d;
+  char *dbuf;
+  int result = 0;
+  require_u8 (info->frame, __func__);
+  require_u8 (info->ref_frame, __func__);
+  stage_in (cx, &s, info->frame, SB2H_BUF_IN, 1);
+  stage_in (cx, &r, info->ref_frame, SB2H_BUF_OUT, 1);
+  d.picture = 0;
+  d.x = x;
+  d.y = y;
+  d.dx = dx;
+  d.dy = dy;
+  dbuf = sb2h_dev_buffer (cx, SB2H_BUF_AUX0, 512);
+  SB2H_CUDA (cudaMemcpyAsync (dbuf, &d, sizeof (d), cudaMemcpyDefault, cx->stream));
+  SB2H_CHECK (sb2_metric_block_sad3 (&s.slab, &r.slab, info->frame->extension, info->block_width[0], info->block_height[0],
+          info->h_shift[1], info->v_shift[1], (const sb2_metric_block_desc *) dbuf, 1, (int *) (dbuf + 256), cx->stream),
+      "sb2_metric_block_sad3");
+  SB2H_CUDA (cudaMemcpyAsync (&result, dbuf + 256, sizeof (result), cudaMemcpyDefault, cx->stream));
+  sb2h_sync (cx);
+  return result;
+}
+
+void
+schro_metric_info_init (SchroMetricInfo *info, SchroFrame *frame, SchroFrame *ref_frame, int block_width, int block_height)
+{
+  int k;
+  memset (info, 0, sizeof (*info));
+  info->frame = frame;
+  info->ref_frame = ref_frame;
+  for (k = 0; k < 3; k++) {
+    info->h_shift[k] = k ? SCHRO_FRAME_FORMAT_H_SHIFT (frame->format) : 0;
+    info->v_shift[k] = k ? SCHRO_FRAME_FORMAT_V_SHIFT (frame->format) : 0;
+    info->block_width[k] = block_width >> info->h_shift[k];
+    info->block_height[k] = block_height >> info->v_shift[k];
+  }
+  info->metric = metric_block_sad3;
+  info->metric_right = metric_block_sad3;
+  info->metric_bottom = metric_block_sad3;
+  info->metric_corner = metric_block_sad3;
+}
+
+int
+schro_metric_fast_block (SchroMetricInfo *info, int x, int y, int dx, int dy)
+{
+  return info->metric (info, x, y, dx, dy);
+}
+
+/* ---- schro_frame_dup* (schroframe.c:699-724) -------------------------------------------- */
+SchroFrame *
+schro_frame_dup_full (SchroFrame *frame, int extension, int is_upsampled)
+{
+  SchroFrame *dup = schro_frame_new_and_alloc_full (frame->domain, frame->format, frame->width, frame->height,
+      extension, is_upsampled);
+  schro_frame_convert (dup, frame);
+  return dup;
+}
+
+SchroFrame *
+schro_frame_dup_extended (SchroFrame *frame, int extension)
+{
+  return schro_frame_dup_full (frame, extension, 0);
+}
+
+SchroFrame *
+schro_frame_dup (SchroFrame *frame)
+{
+  return schro_frame_dup_extended (frame, 0);
+}

@@ -160,12 +160,28 @@ def dequant_golden(ref):
     print("dequant.npz:", i, "cases")
 
 
+def metric_scan_golden(ref):
+    """schro_metric_scan_setup / _do_scan / _get_min and schro_metric_fast_block of the compiled reference"""
+    from tests import test_oracle_metric_scan as t
+    t.REF = ref
+    src, rf = t.pictures()
+    out = {f"src{k}": src[k] for k in range(3)}
+    out.update({f"ref{k}": rf[k] for k in range(3)})
+    out["queries"] = np.array(t.QUERIES, np.int32)
+    for i, q in enumerate(t.QUERIES):
+        o, m, c = t.ref_scan(src, rf, q)
+        n = t.used(o)
+        out[f"q{i}_out"], out[f"q{i}_metrics"], out[f"q{i}_chroma"] = o, m[:n], c[:n]
+    np.savez_compressed(os.path.join(helpers.GOLDEN_DIR, "metric_scan.npz"), **out)
+    print("metric_scan.npz:", len(t.QUERIES), "queries")
+
+
 def main():
     ref = helpers.load_ref()
     if ref is None:
         raise SystemExit("oracle/_ref/libschro_ref.so missing: run `make ref` where /root/reference exists")
     wavelet_golden(ref)
-    for name in ("frame_golden", "motion_golden", "hbm_golden", "glue_golden", "dequant_golden"):
+    for name in ("frame_golden", "motion_golden", "hbm_golden", "glue_golden", "dequant_golden", "metric_scan_golden"):
         fn = globals().get(name)
         if fn:
             fn(ref)

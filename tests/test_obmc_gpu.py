@@ -12,6 +12,19 @@ from tests.golden import make_golden as mg
 pytestmark = pytest.mark.gpu
 ORACLE = helpers.load_oracle()
 GOLD = np.load(os.path.join(helpers.GOLDEN_DIR, "motion.npz"))
+KERNELS = {"auto": 0, "tma": 1, "scatter": 2, "pixel": 3}
+RAN = {k: 0 for k in KERNELS}
+
+
+@pytest.fixture(params=list(KERNELS), autouse=True)
+def obmc_kernel(request):
+    """Every test of this file runs four times: with the kernel the library picks and with each of the
+    three kernels forced (TMA-staged gather, block-major scatter, one thread per pixel).  A forced kernel
+    that does not cover a case's geometry makes gpu_obmc return None and the case is skipped for it."""
+    from schroedinger_b200 import lib
+    lib.sb2_obmc_force_kernel(KERNELS[request.param])
+    yield request.param
+    lib.sb2_obmc_force_kernel(0)
 
 
 def gpu_obmc(case, add, count=1):
@@ -43,7 +56,15 @@ def gpu_obmc(case, add, count=1):
     mvs = torch.from_numpy(np.tile(case.mvs.view(np.uint8), count)).cuda()
     prm = dev.ObmcParams(case.xbsep, case.ybsep, case.xblen, case.yblen, case.nbx, case.nby,
                          case.prec, case.weights[0], case.weights[1], case.weights[2], case.hs, case.vs)
-    dev.obmc_render(prm, mvs, refs[0], refs[1], res, add, out=out, acc=acc)
+    from schroedinger_b200 import lib, Sb2Error
+    try:
+        dev.obmc_render(prm, mvs, refs[0], refs[1], res, add, out=out, acc=acc)
+    except Sb2Error as ex:
+        if "does not cover this geometry" in str(ex):
+            return None
+        raise
+    which = lib.sb2_obmc_last_kernel()
+    RAN[{1: "tma", 2: "scatter", 3: "pixel"}[which]] += 1
     return [[(acc.download(p, c), res.download(p, c), out.download(p, c)) for c in range(3)]
             for p in range(count)]
 
@@ -54,7 +75,10 @@ def test_obmc_golden(cuda):
             if not add and kw.get("res_is_s32"):
                 continue
             case = helpers.ObmcCase(ORACLE, rng=np.random.default_rng(1000 + idx), **kw)
-            got = gpu_obmc(case, add)[0]
+            got = gpu_obmc(case, add)
+            if got is None:
+                continue
+            got = got[0]
             for k in range(3):
                 for q, name in enumerate(("acc", "resid", "out")):
                     if q == 2 and not add:
@@ -76,6 +100,8 @@ def test_obmc_matches_oracle(cuda, kw):
         case = helpers.ObmcCase(ORACLE, rng=np.random.default_rng(77), **kw)
         want = helpers.oracle_obmc(ORACLE, case, add)
         got = gpu_obmc(case, add, count=2)
+        if got is None:
+            continue
         for p in range(2):
             for k in range(3):
                 for q in range(3 if add else 2):
@@ -87,7 +113,20 @@ def test_obmc_1080p_config4(cuda):
     case = helpers.ObmcCase(ORACLE, 1920, 1080, rng=np.random.default_rng(4))
     for add in (1, 0):
         want = helpers.oracle_obmc(ORACLE, case, add)
-        got = gpu_obmc(case, add)[0]
+        got = gpu_obmc(case, add)
+        assert got is not None                      # the codec's default geometry runs on every kernel
+        got = got[0]
         for k in range(3):
             for q in range(3 if add else 2):
                 assert np.array_equal(got[k][q], want[k][q]), (add, k, q)
+
+
+def test_obmc_every_kernel_ran(cuda, obmc_kernel):
+    """(last in the file) the forced runs above really went through the kernel they name, and the
+    default choice for the codec's geometries is the TMA kernel"""
+    from schroedinger_b200 import lib
+    case = helpers.ObmcCase(ORACLE, 96, 64, rng=np.random.default_rng(5))
+    assert gpu_obmc(case, 1) is not None
+    want = {"auto": 1, "tma": 1, "scatter": 2, "pixel": 3}[obmc_kernel]
+    assert lib.sb2_obmc_last_kernel() == want
+    assert RAN["tma"] > 0 and (obmc_kernel in ("auto", "tma") or RAN[obmc_kernel] > 0)
