@@ -162,8 +162,8 @@ int sb2_obmc_render (const sb2_obmc_params *params, const void *motion_vectors,
 
 /* Three kernels implement the renderer: 1 = gather out of TMA-staged reference regions (block overlap
  * of at most one block, 32-pixel borders: every Dirac preset), 2 = block-major scatter with
- * shared-memory atomics, 3 = one thread per pixel (any geometry).  0 picks by geometry; tests force
- * each (also: environment variable SB2_OBMC_KERNEL). */
+ * shared-memory atomics (the default where it applies: measured faster), 3 = one thread per pixel
+ * (any geometry).  0 picks by geometry; tests force each (also: environment variable SB2_OBMC_KERNEL). */
 void sb2_obmc_force_kernel (int which);
 /* which of the three the calling thread's last sb2_obmc_render launched */
 int sb2_obmc_last_kernel (void);

@@ -3,7 +3,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libschro_b200.so")
+LIB_PATH = os.environ.get("SB2_LIB") or os.path.join(_HERE, "libschro_b200.so")   # (SB2_LIB: development builds)
 
 SB2_MAX_COMPONENTS = 4
 

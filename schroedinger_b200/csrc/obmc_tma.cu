@@ -36,6 +36,8 @@ constexpr int R5_MX = 16, R5_MY = 20;          // staged margin left / top of th
 constexpr int R5_W = 112, R5_H = 104;          // staged region: 16 + 64 + 32 columns, 20 + 64 + 20 rows
 constexpr int R5_ROW = 4 * R5_W;               // the copy lands as [row][phase][x]: bytes per row
 constexpr int R5_BYTES = R5_ROW * R5_H;        // 46592 per reference
+constexpr int R5_BIAS = 8192;                  // added to the stored tap offsets: a block that starts above / left of the region
+                                               // (only its lower / right part lies in the tile) has a negative corner offset
 constexpr int T5_MAXOUT = 32;                  // (block, reference) pairs of a tile whose window is not inside the staged region
 constexpr int T5_MAXB = 400;                   // blocks overlapping a tile (4:2:0 chroma with 6/4 blocks: 18 x 18)
 constexpr int BORDER = 32;                     // frame extension the renderer requires (schromotion8.c:303-335)
@@ -43,12 +45,13 @@ constexpr int BORDER = 32;                     // frame extension the renderer r
 struct Blk5 {
   short mode, fast, dc, staged;                // staged: bit r set = reference r's taps lie inside the staged region
   unsigned w[2];                               // tap weights, four bytes
-  unsigned short o[2][4];                      // byte offset of tap t of pixel (a = 0, b = 0) inside the staged region;
+  unsigned short o[2][4];                      // R5_BIAS + byte offset of tap t of pixel (a = 0, b = 0) inside the staged region;
                                                // not staged: o[r][0] = index into the outlier table
 };
 static_assert (sizeof (Blk5) == 32, "two 16-byte reads per table entry");
 
 struct ObmcMaps { CUtensorMap m[2][3]; };
+
 
 struct Smem5 {
   alignas (128) unsigned char ref[2][R5_BYTES + 128];      // [128 spare bytes][region] per reference: a group that starts
@@ -187,7 +190,7 @@ obmc_kernel_tma (const ObmcArgs A, const TileGrid tiles, const __grid_constant__
         const int ph = ((v & 1) << 1) | (u & 1);
         const int ox = (u >> 1) - rx0, oy = (v >> 1) - ry0;      // window corner inside the region
         inside = inside && ox + a_lo >= 0 && oy + b_lo >= 0 && ox + a_hi + 4 <= R5_W && oy + b_hi <= R5_H;
-        e.o[r][t2] = (unsigned short) (oy * R5_ROW + ph * R5_W + ox);
+        e.o[r][t2] = (unsigned short) (oy * R5_ROW + ph * R5_W + ox + R5_BIAS);
         go[t2] = ph * (rs >> 2) + (v >> 1) * rs + (u >> 1);
       }
       const bool used = (e.mode >> r) & 1;
@@ -243,7 +246,7 @@ obmc_kernel_tma (const ObmcArgs A, const TileGrid tiles, const __grid_constant__
       asm volatile ("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
           : "=r"(done) : "r"(bar) : "memory");
   }
-  const unsigned reg0 = smem_u32 (&S.ref[0][128]), reg1 = smem_u32 (&S.ref[1][128]);
+  const unsigned reg0 = smem_u32 (&S.ref[0][128]) - R5_BIAS, reg1 = smem_u32 (&S.ref[1][128]) - R5_BIAS;
 
 #pragma unroll 1
   for (int q = 0; q < T5_H / T5_ROWSTEP; q++) {
@@ -443,5 +446,6 @@ int obmc_tma_launch (const ObmcArgs &A, const sb2_slab *ref0, const sb2_slab *re
   else obmc_kernel_tma<false><<<grid, T5_THREADS, smem, st>>> (A, tiles, maps);
   return SB2_OK;
 }
+
 
 }  // namespace sb2
