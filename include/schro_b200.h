@@ -160,10 +160,11 @@ int sb2_obmc_render (const sb2_obmc_params *params, const void *motion_vectors,
     size_t mv_picture_pitch, const sb2_slab *ref0, const sb2_slab *ref1, const sb2_slab *acc,
     const sb2_slab *residual, int residual_is_s32, int add, const sb2_slab *out, void *stream);
 
-/* Three kernels implement the renderer: 1 = gather out of TMA-staged reference regions (block overlap
- * of at most one block, 32-pixel borders: every Dirac preset), 2 = block-major scatter with
- * shared-memory atomics (the default where it applies: measured faster), 3 = one thread per pixel
- * (any geometry).  0 picks by geometry; tests force each (also: environment variable SB2_OBMC_KERNEL). */
+/* Three kernels implement the renderer: 1 = one block per warp pass out of TMA-staged reference regions
+ * (blocks of at most 32 row x 8-pixel lanes, 32-pixel borders: every Dirac preset), 2 = block-major
+ * scatter out of global memory with shared-memory atomics (the default where it applies: measured
+ * faster), 3 = one thread per pixel (any geometry).  0 picks by geometry; tests force each (also:
+ * environment variable SB2_OBMC_KERNEL). */
 void sb2_obmc_force_kernel (int which);
 /* which of the three the calling thread's last sb2_obmc_render launched */
 int sb2_obmc_last_kernel (void);

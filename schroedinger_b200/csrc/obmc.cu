@@ -353,7 +353,7 @@ static void obmc_weights (unsigned char *w, int len, int off)
 
 using namespace sb2;
 
-// 0: pick by geometry; 1 / 2 / 3: force the TMA gather / scatter / per-pixel kernel (tests run every
+// 0: pick by geometry; 1 / 2 / 3: force the TMA block / scatter / per-pixel kernel (tests run every
 // case through all three); the environment variable SB2_OBMC_KERNEL sets the initial value
 static int g_obmc_variant = -1;
 static thread_local int g_obmc_last = 0;
@@ -464,14 +464,15 @@ sb2_obmc_render (const sb2_obmc_params *p, const void *motion_vectors, size_t mv
     }
     if (out && (((size_t) out->base | out->picture_pitch) & 3)) v4_ok = false;
     if (((size_t) residual->base | residual->picture_pitch) & 15) v4_ok = false;
-    // 1: the TMA-staged gather kernel (obmc_tma.cu): one block of overlap at most, 32-pixel borders.
-    // Measured at 2160p (32 pictures, +-16 pixel vectors): 7.2 ms against 5.6 ms for the scatter kernel
-    // (DESIGN.md 4.3), so it is the choice only where the scatter kernel does not apply -- or when forced
+    // 1: the block-per-warp kernel on TMA-staged reference regions (obmc_blocks.cu): blocks of at most
+    // 32 lanes (8-pixel items x rows), 32-pixel borders.  Measured at 2160p (32 pictures, +-16 pixel
+    // vectors): 6.2 ms against 5.6 ms for the scatter kernel, so it is the choice only
+    // where the scatter kernel does not apply -- or when forced
     if (force == 1 || (force == 0 && !v4_ok)) {
-      const int rc = obmc_tma_launch (A, ref0, ref1, count, as_stream (stream));
+      const int rc = obmc_blocks_launch (A, ref0, ref1, count, as_stream (stream));
       if (rc == SB2_OK) {
         g_obmc_last = 1;
-        return check_cuda (cudaGetLastError (), "obmc_kernel_tma launch");
+        return check_cuda (cudaGetLastError (), "obmc_kernel_blocks launch");
       }
       if (force == 1) return set_error (SB2_ERR_UNSUPPORTED, "sb2_obmc_render: the TMA kernel does not cover this geometry");
     }

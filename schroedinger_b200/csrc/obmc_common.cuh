@@ -1,6 +1,6 @@
 // obmc_common.cuh -- types and device helpers shared by the OBMC kernels (obmc.cu: the generic
-// per-pixel kernel, the scatter kernel and the C entry point; obmc_tma.cu: the TMA-staged gather
-// kernel).
+// per-pixel kernel, the scatter kernel and the C entry point; obmc_blocks.cu: the block-per-warp
+// kernel on TMA-staged reference regions).
 #pragma once
 #include "common.cuh"
 #include <cstdio>
@@ -174,9 +174,9 @@ __device__ __forceinline__ uint2 fetch4x4 (const uint8_t *ref, const BlkRef &br,
 }
 
 
-// obmc_tma.cu: the TMA-staged gather kernel for geometries whose overlap is at most one block
-// (xblen <= 2 xbsep, yblen <= 2 ybsep) on frames with a 32-pixel border.  obmc_tma_launch returns
-// SB2_OK when it launched, SB2_ERR_UNSUPPORTED when the caller should take another kernel.
-int obmc_tma_launch (const ObmcArgs &A, const sb2_slab *ref0, const sb2_slab *ref1, int count, cudaStream_t st);
+// obmc_blocks.cu: reference regions staged by TMA, one block per warp pass, for blocks of at most 32
+// (row, 8-pixel item) lanes on frames with a 32-pixel border.  Returns SB2_OK when it launched,
+// SB2_ERR_UNSUPPORTED when the caller should take another kernel.
+int obmc_blocks_launch (const ObmcArgs &A, const sb2_slab *ref0, const sb2_slab *ref1, int count, cudaStream_t st);
 
 }  // namespace sb2

@@ -19,7 +19,7 @@ RAN = {k: 0 for k in KERNELS}
 @pytest.fixture(params=list(KERNELS), autouse=True)
 def obmc_kernel(request):
     """Every test of this file runs four times: with the kernel the library picks and with each of the
-    three kernels forced (TMA-staged gather, block-major scatter, one thread per pixel).  A forced kernel
+    three kernels forced (block per warp on TMA-staged regions, block-major scatter, one thread per pixel).  A forced kernel
     that does not cover a case's geometry makes gpu_obmc return None and the case is skipped for it."""
     from schroedinger_b200 import lib
     lib.sb2_obmc_force_kernel(KERNELS[request.param])
