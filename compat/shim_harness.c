@@ -1,0 +1,49 @@
+/* compat/shim_harness.c -- TEST INFRASTRUCTURE for compat/schro_hbm_new.c.
+ *
+ * Compiled against the reference's headers together with the shim into oracle/_ref/libcompat_shim.so
+ * (oracle/build_ref.sh).  It builds the two SchroEncoderFrame structures schro_hbm_new reads -- as the
+ * reference declares them, schroencoder.h -- around frames and params supplied by the test, and calls
+ * schro_hbm_new (frame, 0) exactly as schro_encoder_predict_pel_picture does (schromotionest.c:76).
+ * schro_hbm_new_from_frames resolves to libschro_b200.so, loaded before this library. */
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <schroedinger/schro.h>
+#include <schroedinger/schroencoder.h>
+#include <schroedinger/schromotionest.h>
+
+void schro_debug_log (int level, const char *file, const char *function, int line, const char *format, ...)
+{
+  (void) level; (void) file; (void) function; (void) line; (void) format;
+}
+
+typedef struct {
+  SchroEncoder encoder;
+  SchroEncoderFrame frame, ref_frame;
+} ShimFixture;
+
+/* returns the SchroHierBm of schro_hbm_new (frame, 0); *fixture_out must outlive it (the matcher keeps
+ * a pointer to frame->params, as in the reference) and is released with compat_shim_free */
+SchroHierBm *
+compat_shim_hbm_new (SchroParams * params, int levels, int enable_chroma_me,
+    SchroFrame ** src, SchroFrame ** ref, void **fixture_out)
+{
+  ShimFixture *fx = calloc (1, sizeof (ShimFixture));
+  int i;
+  fx->encoder.downsample_levels = levels;
+  fx->encoder.enable_chroma_me = enable_chroma_me;
+  fx->frame.encoder = &fx->encoder;
+  fx->ref_frame.encoder = &fx->encoder;
+  fx->frame.params = *params;
+  fx->frame.ref_frame[0] = &fx->ref_frame;
+  fx->frame.filtered_frame = src[0];
+  fx->ref_frame.filtered_frame = ref[0];
+  for (i = 0; i < levels; i++) {
+    fx->frame.downsampled_frames[i] = src[i + 1];
+    fx->ref_frame.downsampled_frames[i] = ref[i + 1];
+  }
+  *fixture_out = fx;
+  return schro_hbm_new (&fx->frame, 0);
+}
+
+void compat_shim_free (void *fixture) { free (fixture); }
