@@ -100,6 +100,11 @@ int sb2_iwt_inverse (const sb2_slab *src, const sb2_slab *dst, int is_s32,
     int filter, int depth, void *workspace, size_t workspace_bytes,
     void *stream);
 
+/* A level is run by register-chunk kernels where a component's size allows (half-width and
+ * half-height multiples of 8 or 16) and by a generic tile kernel otherwise.  on != 0 sends every
+ * component to the generic kernel (tests run both on the same input; also SB2_IWT_GENERIC=1). */
+void sb2_iwt_force_generic (int on);
+
 /* ---- reference-frame preparation (u8) ------------------------------------ */
 
 /* Replicate the picture edge into the `extension` border pixels of every plane:

@@ -837,6 +837,16 @@ static int launch_fast_forward (LevelArgs a, const int *comps, int nsel, int cou
   return check_cuda (cudaGetLastError (), "wavelet_fwd_fast_kernel launch");
 }
 
+static int g_iwt_generic = -1;
+static bool iwt_generic_forced ()
+{
+  if (g_iwt_generic < 0) {
+    const char *v = getenv ("SB2_IWT_GENERIC");
+    g_iwt_generic = (v && atoi (v)) ? 1 : 0;
+  }
+  return g_iwt_generic != 0;
+}
+
 template <typename T, int F, bool INV>
 static int launch_level (const LevelArgs &a_in, int count, cudaStream_t stream)
 {
@@ -855,7 +865,7 @@ static int launch_level (const LevelArgs &a_in, int count, cudaStream_t stream)
   for (int c = 0; c < a_in.ncomp; c++) {
     if ((a.w[c] >> 1) == 0 || (a.h[c] >> 1) == 0) continue;
     int cs = 0;
-    cs = fast_inverse_chunk<T, F> (a, c);      // the same constraints serve the forward kernel (dense = its input)
+    if (!iwt_generic_forced ()) cs = fast_inverse_chunk<T, F> (a, c);      // the same constraints serve the forward kernel (dense = its input)
     const int k = cs == 16 ? 1 : cs == 8 ? 2 : 0;
     sel[k][nsel[k]++] = c;
   }
@@ -1116,3 +1126,5 @@ sb2_iwt_inverse (const sb2_slab *src, const sb2_slab *dst, int is_s32, int filte
 {
   return sb2::iwt_run (true, src, dst, is_s32, filter, depth, workspace, workspace_bytes, stream);
 }
+
+extern "C" void sb2_iwt_force_generic (int on) { sb2::g_iwt_generic = on ? 1 : 0; }

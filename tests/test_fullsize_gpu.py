@@ -44,6 +44,26 @@ def test_wavelet_2160p_oracle_and_round_trip(cuda, filt, depth_name, levels):
             assert np.array_equal(c.download(p, k), planes[p, k]), (filt, depth_name, p, k)
 
 
+@pytest.mark.parametrize("filt,depth_name,levels", [(f, "s32", 5) for f in range(7)] + [(0, "s16", 4), (1, "s16", 4), (6, "s16", 4)])
+def test_wavelet_2160p_inverse_of_random_coefficients(cuda, filt, depth_name, levels):
+    """The inverse on coefficients no forward transform produced (random, odd and even, every subband
+    as loud as the others): the lifting steps' rounding shifts see both parities everywhere, which a
+    forward -> inverse round trip never exercises.  Every plane of a padded 2160p picture == oracle."""
+    from schroedinger_b200 import device as dev
+    rng = np.random.default_rng(4320 + 10 * filt + (depth_name == "s16"))
+    dt = np.int32 if depth_name == "s32" else np.int16
+    layout = dev.FrameLayout.yuv420(depth_name, W, IWT_H)
+    a, b = dev.PictureSlab(layout, 1), dev.PictureSlab(layout, 1)
+    planes = []
+    for k, (w, h) in enumerate(layout.comp_sizes):
+        planes.append((rng.integers(-600, 601, size=(h, w)) | (rng.integers(0, 2, size=(h, w)))).astype(dt))
+        a.upload(0, k, planes[k])
+    dev.iwt_inverse(a, b, filt, levels)
+    for k in range(3):
+        want = helpers.cpu_wavelet(ORACLE, "oracle", "inv", planes[k].copy(), filt, levels)
+        assert np.array_equal(b.download(0, k), want), (filt, depth_name, k)
+
+
 def test_upsample_2160p_matches_oracle(cuda):
     rng = np.random.default_rng(12)
     imgs = [helpers.smooth_image(H, W, rng), rng.integers(0, 256, size=(H // 2, W // 2)).astype(np.uint8),

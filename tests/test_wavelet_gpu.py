@@ -122,3 +122,28 @@ def test_fast_path_shapes(cuda, filt, dtype):
                 want = helpers.cpu_wavelet(ORACLE, "oracle", d, a.copy(), filt)
                 got = gpu_iwt(d, [a], filt, 1)[0]
                 assert np.array_equal(got, want), (filt, dtype, (h, w), amp, d)
+
+
+@pytest.mark.parametrize("dtype", [np.int16, np.int32])
+@pytest.mark.parametrize("filt", range(7))
+def test_generic_kernel_forced_on_fast_path_shapes(cuda, filt, dtype):
+    """sb2_iwt_force_generic: the generic tile kernel on sizes the register-chunk kernels normally take
+    (so both implementations are checked on the same input), and the launch tags say which one ran."""
+    from schroedinger_b200 import lib
+    from tests.test_hbm_gpu import launched_tags
+    rng = np.random.default_rng(900 + filt)
+    for (h, w) in ((32, 64), (128, 288), (544, 960)):
+        a = rng.integers(-2000, 2001, size=(h, w)).astype(dtype)
+        for d in ("inv", "fwd"):
+            want = helpers.cpu_wavelet(ORACLE, "oracle", d, a.copy(), filt)
+            got = {}
+            tags = {}
+            for forced in (0, 1):
+                lib.sb2_iwt_force_generic(forced)
+                try:
+                    tags[forced] = launched_tags(lambda: got.__setitem__(forced, gpu_iwt(d, [a], filt, 1)[0]))
+                finally:
+                    lib.sb2_iwt_force_generic(0)
+                assert np.array_equal(got[forced], want), (filt, dtype, (h, w), d, forced)
+            assert all(t.endswith("_generic") for t in tags[1]) and tags[1]
+            assert not any(t.endswith("_generic") for t in tags[0]) and tags[0]
