@@ -122,6 +122,13 @@ int sb2_upsample (const sb2_slab *frames, int extension, void *stream);
  * reconstructed reference picture (schroedinger/schrodecoder.c:2068-2087, 2120-2141). */
 int sb2_edgeextend_upsample (const sb2_slab *frames, int extension, void *stream);
 
+/* Two kernels implement the upsampler: 1 = whole words and dp4a (needs 4-byte aligned rows in every
+ * phase plane and an extension that is a multiple of 4: the codec's layouts), 2 = one pixel at a time
+ * (anything).  0 picks by alignment; tests force each (also: environment variable SB2_UPSAMPLE_KERNEL). */
+void sb2_upsample_force_kernel (int which);
+/* which of the two the calling thread's last sb2_upsample / sb2_edgeextend_upsample launched */
+int sb2_upsample_last_kernel (void);
+
 /* dst = half-resolution src, (6,26,26,6) twice with an 8-bit intermediate:
  * schro_frame_downsample (schroedinger/schroframe.c:1505-1513).  dst sizes must be
  * (w+1)/2 x (h+1)/2 per component. */

@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 namespace sb2 {
 
@@ -102,47 +103,48 @@ __device__ __forceinline__ int taps8 (const uint8_t *s, int step)
   return clamp255 (acc >> 5);
 }
 
-// ---- upsample, interior tiles: four pixels per thread, packed 16-bit arithmetic -------
-// For tiles that touch no picture edge every output is a plain 8-tap filter, so the
-// border rules vanish and a thread can produce four adjacent pixels of a phase at once:
-// pixel pairs ride in the two 16-bit lanes of a register (taps sum to 32, partial sums
-// stay below 2^15), the negative taps are folded in with a bias of 8192 = 256<<5 so no
-// lane ever borrows, and the final clamp is a packed min/max.  Tiles that do touch an
-// edge take the per-pixel path of the same kernel, which spells out the border rules.
-#ifndef U2_TW
-#define U2_TW 128
-#define U2_TH 64    // measured best of 64x32, 128x16/32/64, 256x16/32: less halo per tile, whole rounds of work items
-#endif
-constexpr int U2_W = U2_TW, U2_H = U2_TH;        // output tile
-constexpr int U2_WORDS = U2_W / 4 + 2;           // tile words incl. one halo word each side
-constexpr int U2_PITCH = U2_WORDS + 1;
+// ---- upsample, the usual case: whole words, dp4a ------------------------------------------
+// Every pixel of the four extended phase planes is a function of E, the edge-replicated phase 0
+// (E(x,y) = phase0[clamp y][clamp x]):
+//   phase 1 = horizontal filter of E, except columns x < 0 and x >= w-1: E itself   (schroframe.c:2022-2024)
+//   phase 2 = vertical filter of E,   except rows y < 0 and y >= h-1:    E itself   (:2018-2020)
+//   phase 3 = horizontal filter of phase 2, except rows y < 0 / y >= h-1: phase 1, and there
+//             columns x < 0 / x >= w-1: phase 2                                      (:2026-2028)
+// so one kernel serves interior and border tiles alike: the tile of E is loaded with clamped
+// coordinates, the filters run on whole 4-pixel words everywhere and the exceptions are a word
+// select per row (vertical) or a byte mask per word (horizontal).
+//   * 8 taps x 4 pixels = 8 dp4a: a pixel's window is two words of four bytes, u8 data times s8
+//     taps (-1,3,-7,21 | 21,-7,3,-1), chained through the accumulator that starts at the rounding 16;
+//   * horizontally the eight byte windows of a word come from three funnel shifts on each side;
+//   * vertically a thread walks down a word column: the window words G_k(s) = byte k of rows
+//     s..s+3 slide by one PRMT per pixel per row, and each is used twice (low taps of row s,
+//     high taps of row s-4);
+//   * >> 5, then cvt.pack.sat (I2IP) clamps and packs two pixels an instruction.
+constexpr int U3_W = 128, U3_H = 56;             // output tile; 34 word columns x 7 strips of 8 rows = 238 of 256 threads
+constexpr int U3_RS = 8;                         // rows per vertical strip
+constexpr int U3_WORDS = U3_W / 4 + 2;           // tile words incl. one halo word each side
+constexpr int U3_PITCH = U3_WORDS + 1;
+constexpr unsigned TAPS_LO = 0x15f903ffu;        // bytes (-1, 3, -7, 21)
+constexpr unsigned TAPS_HI = 0xff03f915u;        // bytes (21, -7, 3, -1)
 
-// (-1,3,-7,21,21,-7,3,-1), +16 >> 5, clamp -- on two 16-bit lanes
-__device__ __forceinline__ unsigned taps8_x2 (const unsigned (&p)[8])
+__device__ __forceinline__ int dp4a_us (unsigned data, unsigned taps, int acc)
 {
-  const unsigned s34 = p[3] + p[4], s25 = p[2] + p[5], s16 = p[1] + p[6], s07 = p[0] + p[7];
-  const unsigned a = 21u * s34 + 3u * s16 + 0x20102010u;     // +16 and the +8192 bias
-  const unsigned d = a - (7u * s25 + s07);
-  unsigned t = (d >> 5) & 0x07ff07ffu;
-  t = __vminu2 (__vmaxu2 (t, 0x01000100u), 0x01ff01ffu);
-  return t - 0x01000100u;
+  int d;
+  asm ("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(data), "r"(taps), "r"(acc));
+  return d;
 }
 
-// vertical filter of one word column: rows r[0..7] hold 4 pixels each
-__device__ __forceinline__ unsigned taps8_vert4 (const unsigned (&r)[8])
+// clamp four sums >> 5 to bytes and pack them, pixel 0 lowest
+__device__ __forceinline__ unsigned pack4_sat (int a0, int a1, int a2, int a3)
 {
-  unsigned lo[8], hi[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    lo[j] = __byte_perm (r[j], 0, 0x4140);
-    hi[j] = __byte_perm (r[j], 0, 0x4342);
-  }
-  const unsigned o01 = taps8_x2 (lo), o23 = taps8_x2 (hi);
-  return __byte_perm (o01, o23, 0x6420);
+  unsigned hi, d;
+  asm ("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(a3 >> 5), "r"(a2 >> 5), "r"(0));
+  asm ("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a1 >> 5), "r"(a0 >> 5), "r"(hi));
+  return d;
 }
 
 // horizontal filter of pixels b[0..3] given the words holding b[-4..-1], b[0..3], b[4..7]
-__device__ __forceinline__ unsigned taps8_horiz4 (unsigned wm, unsigned w0, unsigned wp)
+__device__ __forceinline__ unsigned horiz4_dp4a (unsigned wm, unsigned w0, unsigned wp)
 {
   unsigned u[8];                                   // u[j] = bytes b[j-3 .. j]
   u[0] = __funnelshift_r (wm, w0, 8);
@@ -153,21 +155,177 @@ __device__ __forceinline__ unsigned taps8_horiz4 (unsigned wm, unsigned w0, unsi
   u[5] = __funnelshift_r (w0, wp, 16);
   u[6] = __funnelshift_r (w0, wp, 24);
   u[7] = wp;
-  unsigned e[8], o[8];
+  int acc[4];
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    e[j] = __byte_perm (u[j], 0, 0x4240);          // (b[j-3], b[j-1]): taps of outputs 0 and 2
-    o[j] = __byte_perm (u[j], 0, 0x4341);          // (b[j-2], b[j]  ): taps of outputs 1 and 3
+  for (int i = 0; i < 4; i++) acc[i] = dp4a_us (u[i + 4], TAPS_HI, dp4a_us (u[i], TAPS_LO, 16));
+  return pack4_sat (acc[0], acc[1], acc[2], acc[3]);
+}
+
+// bytes of a word starting at column x that lie in [lo, hi]
+__device__ __forceinline__ unsigned byte_mask (int x, int lo, int hi)
+{
+  unsigned m = 0xffffffffu;
+  const int cut_lo = lo - x, cut_hi = x + 3 - hi;
+  if (cut_lo > 0) m = cut_lo >= 4 ? 0u : m << (8 * cut_lo);
+  if (cut_hi > 0) m = cut_hi >= 4 ? 0u : m & (0xffffffffu >> (8 * cut_hi));
+  return m;
+}
+
+// store the bytes of `v` selected by `m` (a whole word when all four are)
+__device__ __forceinline__ void store_masked (uint8_t *p, unsigned v, unsigned m)
+{
+  if (m == 0xffffffffu) *reinterpret_cast<unsigned *> (p) = v;
+  else {
+#pragma unroll
+    for (int k = 0; k < 4; k++) if ((m >> (8 * k)) & 1) p[k] = (uint8_t) (v >> (8 * k));
   }
-  const unsigned o02 = taps8_x2 (e), o13 = taps8_x2 (o);
-  return __byte_perm (o02, o13, 0x6240);
+}
+
+// EDGE = false: a tile whose every tap, every output and every store lies inside the picture proper
+// (nine tiles in ten at 2160p) -- no clamps, no masks, no exception rows, loop bounds known at compile time.
+template <bool EDGE>
+__device__ __forceinline__ void upsample_tile_words (const FrameArgs &a, unsigned (&s0)[U3_H + 7][U3_PITCH],
+    unsigned (&sv)[U3_H][U3_PITCH], uint8_t *p0, int stride, int w, int h, int x0, int y0)
+{
+  const int ext = a.ext, q = stride >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // ---- E: a warp per row (32 words = one 128-byte line), then the two halo words of every row
+  if (!EDGE) {
+    const uint8_t *src = p0 + (ptrdiff_t) (y0 - 3 + warp) * stride + x0 + 4 * lane;
+#pragma unroll
+    for (int ty = warp; ty < U3_H + 7; ty += 8, src += (ptrdiff_t) 8 * stride)
+      s0[ty][lane + 1] = __ldg (reinterpret_cast<const unsigned *> (src));
+    if (threadIdx.x < 2 * (U3_H + 7)) {
+      const int ty = threadIdx.x >> 1, c = (threadIdx.x & 1) * (U3_WORDS - 1);
+      s0[ty][c] = __ldg (reinterpret_cast<const unsigned *> (p0 + (ptrdiff_t) (y0 - 3 + ty) * stride + x0 - 4 + 4 * c));
+    }
+  } else {
+    // clamped rows; words that straddle a picture edge are gathered byte by byte
+    for (int i = threadIdx.x; i < (U3_H + 7) * U3_WORDS; i += blockDim.x) {
+      const int ty = i / U3_WORDS, c = i - ty * U3_WORDS;
+      const int yy = clampi (y0 + ty - 3, 0, h - 1), x = x0 - 4 + 4 * c;
+      const uint8_t *row = p0 + (ptrdiff_t) yy * stride;
+      unsigned v;
+      if (x >= 0 && x + 3 <= w - 1) v = __ldg (reinterpret_cast<const unsigned *> (row + x));
+      else {
+        v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) v |= (unsigned) row[clampi (x + k, 0, w - 1)] << (8 * k);
+      }
+      s0[ty][c] = v;
+    }
+  }
+  __syncthreads ();
+
+  // ---- phase 2: a thread owns word column c over a strip of U3_RS rows
+  if (threadIdx.x < U3_WORDS * (U3_H / U3_RS)) {
+    const int strip = threadIdx.x / U3_WORDS, c = threadIdx.x - strip * U3_WORDS;
+    const int t0 = strip * U3_RS;
+    const int x = x0 - 4 + 4 * c;
+    const bool mine = c >= 1 && c <= U3_W / 4;                // halo columns are computed for phase 3, not stored
+    const unsigned xm = !mine ? 0u : EDGE ? byte_mask (x, -ext, w + ext - 1) : 0xffffffffu;
+    uint8_t *dst = p0 + (ptrdiff_t) (y0 + t0) * stride + 2 * q + x;
+    unsigned g[5][4];                              // g[s % 5][k] = byte k of rows s .. s+3
+#pragma unroll
+    for (int k = 0; k < 4; k++) g[1][k] = 0;               // (slot of s = -4, the first window shifted in)
+#pragma unroll
+    for (int t = 0; t < U3_RS + 7; t++) {
+      // row t0 + t enters the window: slot (t - 3) now holds rows t0+t-3 .. t0+t
+      const unsigned r = s0[t0 + t][c];
+      const int cur = (t + 2) % 5, prev = (t + 1) % 5;        // slot of s = t - 3 (cur), of s - 1 (prev); t < 3 primes
+#pragma unroll
+      for (int k = 0; k < 4; k++) g[cur][k] = __byte_perm (g[prev][k], r, 0x0321 | ((4 + k) << 12));
+      if (t >= 7) {
+        const int ty = t0 + t - 7, y = y0 + ty;              // output row: low taps rows ty..ty+3 (s = t-7), high taps s = t-3
+        const int lo = (t - 7 + 5) % 5;                      // slot of s = t - 7
+        int acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc[k] = dp4a_us (g[cur][k], TAPS_HI, dp4a_us (g[lo][k], TAPS_LO, 16));
+        unsigned v = pack4_sat (acc[0], acc[1], acc[2], acc[3]);
+        if (EDGE && (y < 0 || y >= h - 1)) v = s0[ty + 3][c];
+        sv[ty][c] = v;
+        if (!EDGE) { if (mine) *reinterpret_cast<unsigned *> (dst) = v; }
+        else if (xm && y < h + ext) store_masked (dst, v, xm);
+        dst += stride;
+      }
+    }
+  }
+  __syncthreads ();
+
+  // ---- phases 1 and 3 (and the phase-0 border when asked): a warp per row, a word per lane
+  const int c = lane + 1, x = x0 + 4 * lane;
+  if (EDGE && x >= w + ext) return;
+  const unsigned xm = EDGE ? byte_mask (x, -ext, w + ext - 1) : 0xffffffffu;
+  const unsigned fm = EDGE ? byte_mask (x, 0, w - 2) : 0xffffffffu;     // columns that are filtered
+  uint8_t *o = p0 + (ptrdiff_t) (y0 + warp) * stride + x;
+#pragma unroll
+  for (int ty = warp; ty < U3_H; ty += 8, o += (ptrdiff_t) 8 * stride) {
+    const int y = y0 + ty;
+    if (EDGE && y >= h + ext) break;
+    const unsigned e = s0[ty + 3][c], v2 = sv[ty][c];
+    unsigned v1 = e, v3;
+    if (!EDGE) {
+      v1 = horiz4_dp4a (s0[ty + 3][c - 1], e, s0[ty + 3][c + 1]);
+      v3 = horiz4_dp4a (sv[ty][c - 1], v2, sv[ty][c + 1]);
+      *reinterpret_cast<unsigned *> (o + q) = v1;
+      *reinterpret_cast<unsigned *> (o + 3 * q) = v3;
+    } else {
+      if (fm) {
+        const unsigned f = horiz4_dp4a (s0[ty + 3][c - 1], e, s0[ty + 3][c + 1]);
+        v1 = (f & fm) | (e & ~fm);
+      }
+      v3 = v1;
+      if (y >= 0 && y < h - 1) {
+        v3 = v2;
+        if (fm) {
+          const unsigned f = horiz4_dp4a (sv[ty][c - 1], v2, sv[ty][c + 1]);
+          v3 = (f & fm) | (v2 & ~fm);
+        }
+      }
+      store_masked (o + q, v1, xm);
+      store_masked (o + 3 * q, v3, xm);
+      if (a.fuse_edge) {
+        const unsigned om = (y < 0 || y >= h) ? xm : (xm & ~byte_mask (x, 0, w - 1));     // outside the picture
+        if (om) store_masked (o, e, om);
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__ (256)
-upsample_kernel_v2 (const FrameArgs a)
+upsample_kernel_words (const FrameArgs a)
 {
-  __shared__ unsigned s0[U2_H + 7][U2_PITCH];      // phase 0, word c = pixels x0-4+4c ..
-  __shared__ unsigned sv[U2_H][U2_PITCH];          // vertical half-pel of the same words
+  __shared__ unsigned s0[U3_H + 7][U3_PITCH];      // E: word c = pixels x0-4+4c .., row t = y0-3+t
+  __shared__ unsigned sv[U3_H][U3_PITCH];          // phase 2 of the same words
+  static_assert (U3_W == 128 && U3_H % 8 == 0, "a warp per row of 32 words, eight rows a round");
+
+  const TilePos tp = tile_pos (a.tiles);
+  const int comp = tp.comp, pic = blockIdx.y;
+  const int w = a.w[comp], h = a.h[comp], ext = a.ext;
+  const int x0 = tp.bx * U3_W - ext, y0 = tp.by * U3_H - ext;
+  if (x0 >= w + ext || y0 >= h + ext) return;
+  uint8_t *p0 = reinterpret_cast<uint8_t *> (plane_ptr (a.planes, pic, comp));
+  const int stride = a.planes.stride[comp];
+  const bool interior = x0 - 4 >= 0 && x0 + U3_W + 3 <= w - 2 && y0 - 3 >= 0 && y0 + U3_H - 1 + 4 <= h - 2;
+  if (interior) upsample_tile_words<false> (a, s0, sv, p0, stride, w, h, x0, y0);
+  else upsample_tile_words<true> (a, s0, sv, p0, stride, w, h, x0, y0);
+}
+
+// ---- upsample, any alignment: one pixel at a time ---------------------------------------
+#ifndef U2_TW
+#define U2_TW 128
+#define U2_TH 64
+#endif
+constexpr int U2_W = U2_TW, U2_H = U2_TH;        // output tile
+constexpr int U2_WORDS = U2_W / 4 + 2;
+constexpr int U2_PITCH = U2_WORDS + 1;
+
+__global__ void __launch_bounds__ (256)
+upsample_kernel_pixel (const FrameArgs a)
+{
+  __shared__ unsigned s0[U2_H + 7][U2_PITCH];
+  __shared__ unsigned sv[U2_H][U2_PITCH];
 
   const TilePos tp = tile_pos (a.tiles);
   const int comp = tp.comp, pic = blockIdx.y;
@@ -177,37 +335,8 @@ upsample_kernel_v2 (const FrameArgs a)
   uint8_t *p0 = reinterpret_cast<uint8_t *> (plane_ptr (a.planes, pic, comp));
   const int stride = a.planes.stride[comp];
   const int q = stride >> 2;
-  const bool aligned = ((((size_t) p0 | (size_t) stride | (size_t) q) & 3) == 0) && ((x0 & 3) == 0);
-  // interior: every output is a plain filter and every tap lies inside the picture
-  const bool interior = aligned && x0 - 4 >= 0 && x0 + U2_W + 4 <= w - 1 && y0 - 3 >= 0 && y0 + U2_H + 4 <= h - 1;
 
-  if (interior) {
-    for (int i = threadIdx.x; i < (U2_H + 7) * U2_WORDS; i += blockDim.x) {
-      const int ty = i / U2_WORDS, c = i - ty * U2_WORDS;
-      s0[ty][c] = __ldg (reinterpret_cast<const unsigned *> (p0 + (ptrdiff_t) (y0 + ty - 3) * stride + x0 - 4) + c);
-    }
-    __syncthreads ();
-    for (int i = threadIdx.x; i < U2_H * U2_WORDS; i += blockDim.x) {
-      const int ty = i / U2_WORDS, c = i - ty * U2_WORDS;
-      unsigned r[8];
-#pragma unroll
-      for (int j = 0; j < 8; j++) r[j] = s0[ty + j][c];
-      const unsigned v = taps8_vert4 (r);
-      sv[ty][c] = v;
-      if (c >= 1 && c <= U2_W / 4)
-        *reinterpret_cast<unsigned *> (p0 + (ptrdiff_t) (y0 + ty) * stride + 2 * q + x0 - 4 + 4 * c) = v;
-    }
-    __syncthreads ();
-    for (int i = threadIdx.x; i < U2_H * (U2_W / 4); i += blockDim.x) {
-      const int ty = i / (U2_W / 4), c = i - ty * (U2_W / 4) + 1;
-      uint8_t *o = p0 + (ptrdiff_t) (y0 + ty) * stride + x0 - 4 + 4 * c;
-      *reinterpret_cast<unsigned *> (o + q) = taps8_horiz4 (s0[ty + 3][c - 1], s0[ty + 3][c], s0[ty + 3][c + 1]);
-      *reinterpret_cast<unsigned *> (o + 3 * q) = taps8_horiz4 (sv[ty][c - 1], sv[ty][c], sv[ty][c + 1]);
-    }
-    return;
-  }
-
-  // ---- edge tiles: per-pixel rules over the 128x16 tile.
+  // per-pixel rules over the tile.
   // phase 1 (schroframe.c:2022-2024): horizontal filter of phase 0 row clamp(y); left border =
   //   phase 0 column 0, columns >= w-1 = phase 0 column w-1
   // phase 2 (:2018-2020): vertical filter; rows above = phase 0 row 0, last row and below =
@@ -447,6 +576,21 @@ sb2_mc_edgeextend (const sb2_slab *frames, int extension, int phase, void *strea
 
 static int upsample_impl (const sb2_slab *frames, int extension, int fuse_edge, void *stream);
 
+// 0: by alignment; 1 / 2: force the word (dp4a) / per-pixel kernel; SB2_UPSAMPLE_KERNEL sets the initial value
+static int g_upsample_variant = -1;
+static thread_local int g_upsample_last = 0;
+extern "C" void sb2_upsample_force_kernel (int which) { g_upsample_variant = which < 0 || which > 2 ? 0 : which; }
+extern "C" int sb2_upsample_last_kernel (void) { return g_upsample_last; }
+static int upsample_forced ()
+{
+  if (g_upsample_variant < 0) {
+    const char *v = getenv ("SB2_UPSAMPLE_KERNEL");
+    g_upsample_variant = v ? atoi (v) : 0;
+    if (g_upsample_variant < 0 || g_upsample_variant > 2) g_upsample_variant = 0;
+  }
+  return g_upsample_variant;
+}
+
 extern "C" int
 sb2_upsample (const sb2_slab *frames, int extension, void *stream)
 {
@@ -479,15 +623,27 @@ upsample_impl (const sb2_slab *frames, int extension, int fuse_edge, void *strea
         + 3.0 * (frames->width[c] + 2 * extension) * (frames->height[c] + 2 * extension)) * frames->count;
   }
   static_assert ((U2_H + 7) * (U2_W + 8) <= (U2_H + 7) * U2_PITCH * 4 && U2_H * (U2_W + 8) <= U2_H * U2_PITCH * 4,
-      "byte tiles of the edge path fit the word tiles");
+      "byte tiles of the pixel kernel fit the word tiles");
   (void) maxw; (void) maxh;
   int ew[SB2_MAX_COMPONENTS], eh[SB2_MAX_COMPONENTS];
   for (int c = 0; c < frames->ncomp; c++) { ew[c] = frames->width[c] + 2 * extension; eh[c] = frames->height[c] + 2 * extension; }
   if (frames->count > 65535) return set_error (SB2_ERR_ARG, "sb2_upsample: at most 65535 pictures per call");
-  const dim3 grid = make_tile_grid (a.tiles, frames->ncomp, ew, eh, U2_W, U2_H, frames->count);
-  {
+  // the word kernel needs every row of every phase plane 4-byte aligned, and tiles that start on a word
+  bool words = (extension & 3) == 0 && (((size_t) frames->base | frames->picture_pitch) & 3) == 0;
+  for (int c = 0; c < frames->ncomp; c++)
+    if ((frames->offset[c] | (size_t) frames->stride[c] | (size_t) (frames->stride[c] >> 2)) & 3) words = false;
+  const int force = upsample_forced ();
+  if (force == 1 && !words) return set_error (SB2_ERR_UNSUPPORTED, "sb2_upsample: the word kernel needs 4-byte aligned phase rows");
+  if (force == 2) words = false;
+  g_upsample_last = words ? 1 : 2;
+  if (words) {
+    const dim3 grid = make_tile_grid (a.tiles, frames->ncomp, ew, eh, U3_W, U3_H, frames->count);
     LaunchScope scope ("upsample", bytes, as_stream (stream));
-    upsample_kernel_v2<<<grid, 256, 0, as_stream (stream)>>> (a);
+    upsample_kernel_words<<<grid, 256, 0, as_stream (stream)>>> (a);
+  } else {
+    const dim3 grid = make_tile_grid (a.tiles, frames->ncomp, ew, eh, U2_W, U2_H, frames->count);
+    LaunchScope scope ("upsample_pixel", bytes, as_stream (stream));
+    upsample_kernel_pixel<<<grid, 256, 0, as_stream (stream)>>> (a);
   }
   return check_cuda (cudaGetLastError (), "upsample_kernel launch");
 }

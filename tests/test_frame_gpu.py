@@ -12,16 +12,39 @@ ORACLE = helpers.load_oracle()
 GOLD = np.load(os.path.join(helpers.GOLDEN_DIR, "frame.npz"))
 
 
+UP_KERNELS = {"auto": 0, "words": 1, "pixel": 2}
+UP_RAN = {1: 0, 2: 0}
+
+
+@pytest.fixture(params=list(UP_KERNELS))
+def up_kernel(request):
+    """The upsample tests run three times: the kernel the library picks (whole words + dp4a when every
+    phase row is 4-byte aligned, else one pixel at a time) and each of the two forced.  The word kernel
+    forced on a layout it cannot take raises, and the case is skipped for it."""
+    from schroedinger_b200 import lib
+    lib.sb2_upsample_force_kernel(UP_KERNELS[request.param])
+    yield request.param
+    lib.sb2_upsample_force_kernel(0)
+
+
 def gpu_upsampled(imgs, ext):
-    """imgs: list of 2-D u8 component images of one picture -> per component (4 phase arrays)."""
-    from schroedinger_b200 import device as dev
+    """imgs: list of 2-D u8 component images of one picture -> per component (4 phase arrays);
+    None when the forced kernel does not take this layout."""
+    from schroedinger_b200 import device as dev, lib
+    from schroedinger_b200._lib import Sb2Error
     lay = dev.FrameLayout("u8", [(a.shape[1], a.shape[0]) for a in imgs], ext, True)
     slab = dev.PictureSlab(lay, 1)
     slab.buf.fill_(0x55)
     for c, a in enumerate(imgs):
         slab.upload(0, c, a)
     dev.mc_edgeextend(slab)
-    dev.upsample(slab)
+    try:
+        dev.upsample(slab)
+    except Sb2Error as ex:
+        if "word kernel needs" in str(ex):
+            return None
+        raise
+    UP_RAN[lib.sb2_upsample_last_kernel()] += 1
     return [[slab.download(0, c, phase=p, with_border=True) for p in range(4)] for c in range(len(imgs))]
 
 
@@ -33,13 +56,14 @@ def oracle_upsampled(img, ext):
     return [pl.phase(p).copy() for p in range(4)]
 
 
-def test_upsample_golden(cuda):
+def test_upsample_golden(cuda, up_kernel):
     idx = 0
     while f"up{idx}_img" in GOLD.files:
         img, ext = GOLD[f"up{idx}_img"], int(GOLD[f"up{idx}_ext"][0])
-        got = gpu_upsampled([img], ext)[0]
-        for p in range(4):
-            assert np.array_equal(got[p], GOLD[f"up{idx}_phase{p}"]), (idx, p)
+        got = gpu_upsampled([img], ext)
+        if got is not None:
+            for p in range(4):
+                assert np.array_equal(got[0][p], GOLD[f"up{idx}_phase{p}"]), (idx, p)
         idx += 1
     assert idx >= 6
 
@@ -47,18 +71,21 @@ def test_upsample_golden(cuda):
 @pytest.mark.parametrize("shape", [(20, 20, 4), (8, 8, 2), (3, 5, 3), (2, 9, 8), (48, 64, 32),
                                    (37, 100, 32), (9, 3, 4), (1, 1, 2), (5, 2, 1), (130, 70, 32),
                                    (16, 200, 32), (270, 480, 32)])
-def test_upsample_sizes(cuda, shape):
+def test_upsample_sizes(cuda, shape, up_kernel):
     h, w, ext = shape
     rng = np.random.default_rng(h * 1000 + w)
     for name, img in helpers.patterns(h, w, np.int16, rng)[:6] + [("noise", rng.integers(0, 256, size=(h, w)))]:
         img = np.clip(img, 0, 255).astype(np.uint8)
-        got = gpu_upsampled([img], ext)[0]
+        got = gpu_upsampled([img], ext)
+        if got is None:
+            return
+        got = got[0]
         want = oracle_upsampled(img, ext)
         for p in range(4):
             assert np.array_equal(got[p], want[p]), (shape, name, p)
 
 
-def test_upsample_420_frame_1080p(cuda):
+def test_upsample_420_frame_1080p(cuda, up_kernel):
     rng = np.random.default_rng(11)
     imgs = [helpers.smooth_image(1080, 1920, rng), helpers.smooth_image(540, 960, rng),
             rng.integers(0, 256, size=(540, 960)).astype(np.uint8)]
@@ -103,7 +130,7 @@ def test_downsample_golden(cuda):
         idx += 1
 
 
-def test_fused_edgeextend_variants(cuda):
+def test_fused_edgeextend_variants(cuda, up_kernel):
     """sb2_edgeextend_upsample == mc_edgeextend + upsample, sb2_downsample_edgeextend ==
     downsample + mc_edgeextend (the fused launches the pipeline uses)."""
     from schroedinger_b200 import device as dev
@@ -129,3 +156,13 @@ def test_fused_edgeextend_variants(cuda):
         dev.mc_edgeextend(d1)
         dev.downsample_edgeextend(src, d2)
         assert bool((d1.buf[:d1.nbytes] == d2.buf[:d2.nbytes]).all()), ("downsample", h, w)
+
+
+def test_upsample_both_kernels_ran(cuda, up_kernel):
+    """(last in the file) forcing really selects: the codec's layout (32-pixel border) takes the word
+    kernel by default, and both kernels were exercised by the tests above."""
+    from schroedinger_b200 import lib
+    img = np.random.default_rng(3).integers(0, 256, size=(40, 72)).astype(np.uint8)
+    assert gpu_upsampled([img], 32) is not None
+    assert lib.sb2_upsample_last_kernel() == {"auto": 1, "words": 1, "pixel": 2}[up_kernel]
+    assert UP_RAN[1] > 0 and UP_RAN[2] > 0
