@@ -139,6 +139,11 @@ int sb2_downsample (const sb2_slab *src, const sb2_slab *dst, void *stream);
 int sb2_downsample_edgeextend (const sb2_slab *src, const sb2_slab *dst, int dst_extension,
     void *stream);
 
+/* As for the upsampler: 1 = whole words (4-byte aligned rows on both sides), 2 = one pixel at a time;
+ * 0 picks by alignment (also: environment variable SB2_DOWNSAMPLE_KERNEL). */
+void sb2_downsample_force_kernel (int which);
+int sb2_downsample_last_kernel (void);
+
 /* One-direction half-pel filter of a bare plane, no borders:
  * schro_frame_upsample_horiz / schro_frame_upsample_vert (schroedinger/schroframe.c:1557, 1612) */
 int sb2_upsample_plane_1d (uint8_t *dst, int dst_stride, const uint8_t *src, int src_stride,

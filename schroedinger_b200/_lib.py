@@ -83,6 +83,8 @@ _opt("sb2_hbm_force_generic", None, [ctypes.c_int])
 _opt("sb2_iwt_force_generic", None, [ctypes.c_int])
 _opt("sb2_upsample_force_kernel", None, [ctypes.c_int])
 _opt("sb2_upsample_last_kernel", ctypes.c_int, [])
+_opt("sb2_downsample_force_kernel", None, [ctypes.c_int])
+_opt("sb2_downsample_last_kernel", ctypes.c_int, [])
 _opt("sb2_hbm_scan_hint", ctypes.c_int, [ctypes.c_void_p, _SP, _SP, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                         ctypes.c_size_t, ctypes.c_void_p])

@@ -134,12 +134,13 @@ __device__ __forceinline__ int dp4a_us (unsigned data, unsigned taps, int acc)
   return d;
 }
 
-// clamp four sums >> 5 to bytes and pack them, pixel 0 lowest
+// clamp four sums >> SHIFT to bytes and pack them, pixel 0 lowest
+template <int SHIFT = 5>
 __device__ __forceinline__ unsigned pack4_sat (int a0, int a1, int a2, int a3)
 {
   unsigned hi, d;
-  asm ("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(a3 >> 5), "r"(a2 >> 5), "r"(0));
-  asm ("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a1 >> 5), "r"(a0 >> 5), "r"(hi));
+  asm ("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(a3 >> SHIFT), "r"(a2 >> SHIFT), "r"(0));
+  asm ("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a1 >> SHIFT), "r"(a0 >> SHIFT), "r"(hi));
   return d;
 }
 
@@ -391,19 +392,116 @@ struct DownArgs {
   int dst_ext;                  // > 0: also replicate the result into dst's border
 };
 
-// ---- downsample, interior tiles: four output pixels per thread, packed arithmetic ------
+// ---- downsample, the usual case: whole words ----------------------------------------------
+// Vertical (6,26,26,6)+32 >> 6 on source words (two pixels per 16-bit lane pair), result in shared
+// memory; horizontal: an output pixel's four taps are one unaligned word of that intermediate --
+// a funnel shift and one dp4a.  Clamped loads make border tiles the same computation as interior
+// ones (the intermediate of a clamped column is the clamped column of the intermediate); only their
+// stores differ (partial words, the fused border replication).
 #ifndef D2_TW
 #define D2_TW 64
 #define D2_TH 32
 #endif
-constexpr int D2_W = D2_TW, D2_H = D2_TH;                // output tile (measured best of 64x8, 64x16, 64x32, 128x8, 128x16: whole rounds of 256 work items)
-constexpr int D2_WORDS = (2 * D2_W) / 4 + 3;       // tmp words: source columns 2*x0-4 .. 2*x0+2*D2_W+8
-constexpr int D2_BW = 2 * D2_W + 2;                // byte tile of the edge path
+constexpr int D2_W = D2_TW, D2_H = D2_TH;                // output tile
+constexpr int D2_WORDS = (2 * D2_W) / 4 + 3;       // intermediate words: source columns 2*x0-4 .. 2*x0+2*D2_W+8
+constexpr int D2_BW = 2 * D2_W + 2;                // byte tile of the per-pixel kernel
+constexpr unsigned DTAPS = 0x061a1a06u;            // bytes (6, 26, 26, 6)
+static_assert (D2_W == 64 && D2_H == 32 && D2_WORDS == 35, "thread maps of downsample_tile_words");
+
+template <bool EDGE>
+__device__ __forceinline__ void downsample_tile_words (const DownArgs &a, unsigned (&st)[D2_H][D2_WORDS + 1],
+    uint8_t *so, const uint8_t *s, uint8_t *d, int ss, int dstr, int sw, int sh, int dw, int dh, int x0, int y0)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // ---- vertical: word c of intermediate row ty from source rows 2y-1 .. 2y+2
+  auto vert_word = [&] (int ty, int c) {
+    unsigned r[4];
+    const int x = 2 * x0 - 4 + 4 * c, yb = 2 * (y0 + ty) - 1;
+    if (!EDGE) {
+      const uint8_t *col = s + (ptrdiff_t) yb * ss + x;
+#pragma unroll
+      for (int j = 0; j < 4; j++) r[j] = __ldg (reinterpret_cast<const unsigned *> (col + (ptrdiff_t) j * ss));
+    } else {
+      const bool whole = x >= 0 && x + 3 <= sw - 1;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint8_t *row = s + (ptrdiff_t) clampi (yb + j, 0, sh - 1) * ss;
+        if (whole) r[j] = __ldg (reinterpret_cast<const unsigned *> (row + x));
+        else {
+          r[j] = 0;
+#pragma unroll
+          for (int k = 0; k < 4; k++) r[j] |= (unsigned) row[clampi (x + k, 0, sw - 1)] << (8 * k);
+        }
+      }
+    }
+    unsigned lo[4], hi[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      lo[j] = __byte_perm (r[j], 0, 0x4140);
+      hi[j] = __byte_perm (r[j], 0, 0x4342);
+    }
+    const unsigned vlo = ((6u * (lo[0] + lo[3]) + 26u * (lo[1] + lo[2]) + 0x00200020u) >> 6) & 0x00ff00ffu;
+    const unsigned vhi = ((6u * (hi[0] + hi[3]) + 26u * (hi[1] + hi[2]) + 0x00200020u) >> 6) & 0x00ff00ffu;
+    st[ty][c] = __byte_perm (vlo, vhi, 0x6420);
+  };
+#pragma unroll
+  for (int ty = warp; ty < D2_H; ty += 8) vert_word (ty, lane);
+  if (threadIdx.x < 3 * D2_H) vert_word (threadIdx.x / 3, 32 + threadIdx.x % 3);
+  __syncthreads ();
+
+  // ---- horizontal: output pixels x..x+3 use b[-1..8], b[k] = intermediate[2x+k]
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const int ty = (threadIdx.x >> 4) + 16 * it, g = threadIdx.x & 15;
+    const unsigned *t = &st[ty][2 * g];            // t[0] = b[-4..-1], t[1] = b[0..3], t[2] = b[4..7], t[3] = b[8..11]
+    const unsigned t0 = t[0], t1 = t[1], t2 = t[2], t3 = t[3];
+    const int o0 = (int) __dp4a (__funnelshift_r (t0, t1, 24), DTAPS, 32u);    // b[-1..2]
+    const int o1 = (int) __dp4a (__funnelshift_r (t1, t2, 8), DTAPS, 32u);     // b[1..4]
+    const int o2 = (int) __dp4a (__funnelshift_r (t1, t2, 24), DTAPS, 32u);    // b[3..6]
+    const int o3 = (int) __dp4a (__funnelshift_r (t2, t3, 8), DTAPS, 32u);     // b[5..8]
+    const unsigned v = pack4_sat<6> (o0, o1, o2, o3);
+    if (!EDGE) *reinterpret_cast<unsigned *> (d + (ptrdiff_t) (y0 + ty) * dstr + x0 + 4 * g) = v;
+    else reinterpret_cast<unsigned *> (so)[ty * (D2_W / 4) + g] = v;
+  }
+  if (!EDGE) return;
+  __syncthreads ();
+  // ---- border tiles: the words inside the plane ...
+  for (int i = threadIdx.x; i < D2_H * (D2_W / 4); i += blockDim.x) {
+    const int ty = i / (D2_W / 4), g = i - ty * (D2_W / 4);
+    const int x = x0 + 4 * g, y = y0 + ty;
+    if (x >= dw || y >= dh) continue;
+    const unsigned v = reinterpret_cast<const unsigned *> (so)[i];
+    uint8_t *o = d + (ptrdiff_t) y * dstr + x;
+    if (x + 3 < dw) *reinterpret_cast<unsigned *> (o) = v;
+    else for (int k = 0; x + k < dw; k++) o[k] = (uint8_t) (v >> (8 * k));
+  }
+  // ... and the fused edge extension (schro_frame_mc_edgeextend on the result): every border position
+  // whose nearest plane pixel belongs to this tile, a warp per row of the tile grown by the extension
+  const int e = a.dst_ext;
+  if (e <= 0) return;
+  for (int ry = warp; ry < D2_H + 2 * e; ry += 8) {
+    const int y = y0 - e + ry;
+    if (y >= dh + e) break;
+    const int cy = clampi (y, 0, dh - 1);
+    if (cy < y0 || cy >= y0 + D2_H) continue;
+    const bool row_inside = y >= 0 && y < dh;
+    for (int rx = lane; rx < D2_W + 2 * e; rx += 32) {
+      const int x = x0 - e + rx;
+      if (x >= dw + e) break;
+      if (row_inside && x >= 0 && x < dw) continue;            // a plane pixel: stored above
+      const int cx = clampi (x, 0, dw - 1);
+      if (cx < x0 || cx >= x0 + D2_W) continue;                // another tile's pixel
+      d[(ptrdiff_t) y * dstr + x] = so[(cy - y0) * D2_W + cx - x0];
+    }
+  }
+}
 
 __global__ void __launch_bounds__ (256)
-downsample_kernel_v2 (const DownArgs a)
+downsample_kernel_words (const DownArgs a)
 {
   __shared__ unsigned st[D2_H][D2_WORDS + 1];      // vertically filtered source words
+  __shared__ __align__ (4) uint8_t so[D2_H * D2_W];   // border tiles: the tile's output before the store pass
 
   const TilePos tp = tile_pos (a.tiles);
   const int comp = tp.comp, pic = blockIdx.y;
@@ -413,52 +511,29 @@ downsample_kernel_v2 (const DownArgs a)
   const uint8_t *s = reinterpret_cast<const uint8_t *> (plane_ptr (a.src, pic, comp));
   uint8_t *d = reinterpret_cast<uint8_t *> (plane_ptr (a.dst, pic, comp));
   const int ss = a.src.stride[comp], dstr = a.dst.stride[comp];
-  const bool aligned = ((((size_t) s | (size_t) ss | (size_t) d | (size_t) dstr) & 3) == 0);
-  const bool interior = aligned && 2 * x0 - 4 >= 0 && 2 * x0 + 2 * D2_W + 8 <= sw &&
+  // interior: every tap inside the source, every output inside the destination and away from its edges
+  const bool interior = 2 * x0 - 4 >= 0 && 2 * x0 + 2 * D2_W + 8 <= sw &&
       2 * y0 - 1 >= 0 && 2 * (y0 + D2_H - 1) + 2 <= sh - 1 && x0 + D2_W < dw && y0 + D2_H < dh && x0 > 0 && y0 > 0;
+  if (interior) downsample_tile_words<false> (a, st, so, s, d, ss, dstr, sw, sh, dw, dh, x0, y0);
+  else downsample_tile_words<true> (a, st, so, s, d, ss, dstr, sw, sh, dw, dh, x0, y0);
+}
 
-  if (interior) {
-    // vertical (6,26,26,6)+32 >> 6 on whole source words, straight from global memory
-    for (int i = threadIdx.x; i < D2_H * D2_WORDS; i += blockDim.x) {
-      const int ty = i / D2_WORDS, c = i - ty * D2_WORDS;
-      const unsigned *col = reinterpret_cast<const unsigned *> (s + (ptrdiff_t) (2 * (y0 + ty) - 1) * ss + 2 * x0 - 4) + c;
-      unsigned lo[4], hi[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const unsigned r = __ldg (reinterpret_cast<const unsigned *> (reinterpret_cast<const uint8_t *> (col) + (ptrdiff_t) j * ss));
-        lo[j] = __byte_perm (r, 0, 0x4140);
-        hi[j] = __byte_perm (r, 0, 0x4342);
-      }
-      const unsigned vlo = ((6u * (lo[0] + lo[3]) + 26u * (lo[1] + lo[2]) + 0x00200020u) >> 6) & 0x00ff00ffu;
-      const unsigned vhi = ((6u * (hi[0] + hi[3]) + 26u * (hi[1] + hi[2]) + 0x00200020u) >> 6) & 0x00ff00ffu;
-      st[ty][c] = __byte_perm (vlo, vhi, 0x6420);
-    }
-    __syncthreads ();
-    // horizontal pass: output pixels x..x+3 use b[-1..8], b[k] = tmp[2x+k]
-    for (int i = threadIdx.x; i < D2_H * (D2_W / 4); i += blockDim.x) {
-      const int ty = i / (D2_W / 4), g = i - ty * (D2_W / 4);
-      const unsigned *t = &st[ty][2 * g];          // t[0] = b[-4..-1], t[1] = b[0..3], t[2] = b[4..7], t[3] = b[8..11]
-      unsigned u[8];                                // u[k] = b[k-1 .. k+2]
-      u[0] = __funnelshift_r (t[0], t[1], 24);
-      u[1] = t[1];
-      u[2] = __funnelshift_r (t[1], t[2], 8);
-      u[3] = __funnelshift_r (t[1], t[2], 16);
-      u[4] = __funnelshift_r (t[1], t[2], 24);
-      u[5] = t[2];
-      u[6] = __funnelshift_r (t[2], t[3], 8);
-      u[7] = __funnelshift_r (t[2], t[3], 16);
-      unsigned p[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) p[k] = __byte_perm (u[k], 0, 0x4240);   // (b[k-1], b[k+1])
-      // outputs (0,1): 6*(b-1,b1) + 26*(b0,b2) + 26*(b1,b3) + 6*(b2,b4); outputs (2,3) four further on
-      const unsigned o01 = ((6u * (p[0] + p[3]) + 26u * (p[1] + p[2]) + 0x00200020u) >> 6) & 0x00ff00ffu;
-      const unsigned o23 = ((6u * (p[4] + p[7]) + 26u * (p[5] + p[6]) + 0x00200020u) >> 6) & 0x00ff00ffu;
-      *reinterpret_cast<unsigned *> (d + (ptrdiff_t) (y0 + ty) * dstr + x0 + 4 * g) = __byte_perm (o01, o23, 0x6420);
-    }
-    return;
-  }
+// ---- downsample, any alignment: one pixel at a time ----------------------------------------
+__global__ void __launch_bounds__ (256)
+downsample_kernel_pixel (const DownArgs a)
+{
+  __shared__ unsigned st[D2_H][D2_WORDS + 1];
 
-  // ---- edge tiles: per-pixel path with clamped indices and the fused border replication
+  const TilePos tp = tile_pos (a.tiles);
+  const int comp = tp.comp, pic = blockIdx.y;
+  const int sw = a.sw[comp], sh = a.sh[comp], dw = a.dw[comp], dh = a.dh[comp];
+  const int x0 = tp.bx * D2_W, y0 = tp.by * D2_H;
+  if (x0 >= dw || y0 >= dh) return;
+  const uint8_t *s = reinterpret_cast<const uint8_t *> (plane_ptr (a.src, pic, comp));
+  uint8_t *d = reinterpret_cast<uint8_t *> (plane_ptr (a.dst, pic, comp));
+  const int ss = a.src.stride[comp], dstr = a.dst.stride[comp];
+
+  // per-pixel path with clamped indices and the fused border replication
   uint8_t *sm = reinterpret_cast<uint8_t *> (&st[0][0]);
   static_assert (D2_H * D2_BW <= D2_H * (D2_WORDS + 1) * 4, "byte tile fits");
   for (int i = threadIdx.x; i < D2_H * D2_BW; i += blockDim.x) {
@@ -650,6 +725,21 @@ upsample_impl (const sb2_slab *frames, int extension, int fuse_edge, void *strea
 
 static int downsample_impl (const sb2_slab *src, const sb2_slab *dst, int dst_ext, void *stream);
 
+// 0: by alignment; 1 / 2: force the word / per-pixel kernel; SB2_DOWNSAMPLE_KERNEL sets the initial value
+static int g_downsample_variant = -1;
+static thread_local int g_downsample_last = 0;
+extern "C" void sb2_downsample_force_kernel (int which) { g_downsample_variant = which < 0 || which > 2 ? 0 : which; }
+extern "C" int sb2_downsample_last_kernel (void) { return g_downsample_last; }
+static int downsample_forced ()
+{
+  if (g_downsample_variant < 0) {
+    const char *v = getenv ("SB2_DOWNSAMPLE_KERNEL");
+    g_downsample_variant = v ? atoi (v) : 0;
+    if (g_downsample_variant < 0 || g_downsample_variant > 2) g_downsample_variant = 0;
+  }
+  return g_downsample_variant;
+}
+
 extern "C" int
 sb2_downsample (const sb2_slab *src, const sb2_slab *dst, void *stream)
 {
@@ -695,9 +785,18 @@ downsample_impl (const sb2_slab *src, const sb2_slab *dst, int dst_ext, void *st
   (void) maxw; (void) maxh;
   if (src->count > 65535) return set_error (SB2_ERR_ARG, "sb2_downsample: at most 65535 pictures per call");
   const dim3 grid = make_tile_grid (a.tiles, src->ncomp, a.dw, a.dh, D2_W, D2_H, src->count);
+  // the word kernel needs 4-byte aligned rows on both sides
+  bool words = (((size_t) src->base | src->picture_pitch | (size_t) dst->base | dst->picture_pitch) & 3) == 0;
+  for (int c = 0; c < src->ncomp; c++)
+    if ((src->offset[c] | (size_t) src->stride[c] | dst->offset[c] | (size_t) dst->stride[c]) & 3) words = false;
+  const int force = downsample_forced ();
+  if (force == 1 && !words) return set_error (SB2_ERR_UNSUPPORTED, "sb2_downsample: the word kernel needs 4-byte aligned rows");
+  if (force == 2) words = false;
+  g_downsample_last = words ? 1 : 2;
   {
-    LaunchScope scope ("downsample", bytes, as_stream (stream));
-    downsample_kernel_v2<<<grid, 256, 0, as_stream (stream)>>> (a);
+    LaunchScope scope (words ? "downsample" : "downsample_pixel", bytes, as_stream (stream));
+    if (words) downsample_kernel_words<<<grid, 256, 0, as_stream (stream)>>> (a);
+    else downsample_kernel_pixel<<<grid, 256, 0, as_stream (stream)>>> (a);
   }
   return check_cuda (cudaGetLastError (), "downsample_kernel launch");
 }

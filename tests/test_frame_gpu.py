@@ -14,6 +14,7 @@ GOLD = np.load(os.path.join(helpers.GOLDEN_DIR, "frame.npz"))
 
 UP_KERNELS = {"auto": 0, "words": 1, "pixel": 2}
 UP_RAN = {1: 0, 2: 0}
+DOWN_RAN = {1: 0, 2: 0}
 
 
 @pytest.fixture(params=list(UP_KERNELS))
@@ -23,8 +24,10 @@ def up_kernel(request):
     forced on a layout it cannot take raises, and the case is skipped for it."""
     from schroedinger_b200 import lib
     lib.sb2_upsample_force_kernel(UP_KERNELS[request.param])
+    lib.sb2_downsample_force_kernel(UP_KERNELS[request.param])       # the downsampler has the same pair
     yield request.param
     lib.sb2_upsample_force_kernel(0)
+    lib.sb2_downsample_force_kernel(0)
 
 
 def gpu_upsampled(imgs, ext):
@@ -98,8 +101,8 @@ def test_upsample_420_frame_1080p(cuda, up_kernel):
 
 @pytest.mark.parametrize("shape", [(10, 10), (39, 39), (7, 11), (2, 2), (5, 1), (1, 7), (99, 135),
                                    (1080, 1920), (16, 17), (33, 64)])
-def test_downsample(cuda, shape):
-    from schroedinger_b200 import device as dev
+def test_downsample(cuda, shape, up_kernel):
+    from schroedinger_b200 import device as dev, lib
     h, w = shape
     rng = np.random.default_rng(h + w)
     img = rng.integers(0, 256, size=(h, w)).astype(np.uint8)
@@ -107,6 +110,7 @@ def test_downsample(cuda, shape):
     dst = dev.PictureSlab(dev.FrameLayout("u8", [((w + 1) // 2, (h + 1) // 2)], 8), 1)
     src.upload(0, 0, img)
     dev.downsample(src, dst)
+    DOWN_RAN[lib.sb2_downsample_last_kernel()] += 1
     dev.mc_edgeextend(dst)
     want = helpers.cpu_downsample(ORACLE, "oracle", img)
     assert np.array_equal(dst.download(0, 0), want)
@@ -116,7 +120,7 @@ def test_downsample(cuda, shape):
     assert np.array_equal(dst.download(0, 0, with_border=True), pl.phase(0))
 
 
-def test_downsample_golden(cuda):
+def test_downsample_golden(cuda, up_kernel):
     from schroedinger_b200 import device as dev
     idx = 0
     while f"down{idx}_img" in GOLD.files:
@@ -166,3 +170,4 @@ def test_upsample_both_kernels_ran(cuda, up_kernel):
     assert gpu_upsampled([img], 32) is not None
     assert lib.sb2_upsample_last_kernel() == {"auto": 1, "words": 1, "pixel": 2}[up_kernel]
     assert UP_RAN[1] > 0 and UP_RAN[2] > 0
+    assert DOWN_RAN[1] > 0 and DOWN_RAN[2] > 0
