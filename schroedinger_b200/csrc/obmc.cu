@@ -357,14 +357,14 @@ using namespace sb2;
 // case through all three); the environment variable SB2_OBMC_KERNEL sets the initial value
 static int g_obmc_variant = -1;
 static thread_local int g_obmc_last = 0;
-extern "C" void sb2_obmc_force_kernel (int which) { g_obmc_variant = which < 0 || which > 3 ? 0 : which; }
+extern "C" void sb2_obmc_force_kernel (int which) { g_obmc_variant = which < 0 || which > 4 ? 0 : which; }
 extern "C" int sb2_obmc_last_kernel (void) { return g_obmc_last; }
 static int forced_variant ()
 {
   if (g_obmc_variant < 0) {
     const char *v = getenv ("SB2_OBMC_KERNEL");
     g_obmc_variant = v ? atoi (v) : 0;
-    if (g_obmc_variant < 0 || g_obmc_variant > 3) g_obmc_variant = 0;
+    if (g_obmc_variant < 0 || g_obmc_variant > 4) g_obmc_variant = 0;
   }
   return g_obmc_variant;
 }
@@ -451,6 +451,14 @@ sb2_obmc_render (const sb2_obmc_params *p, const void *motion_vectors, size_t mv
   {
     LaunchScope scope (add ? "obmc_render_add" : "obmc_render_sub", bytes, as_stream (stream));
     const int force = forced_variant ();
+    if (force == 4) {
+      const int rc = obmc_blocks_launch (A, ref0, ref1, count, false, as_stream (stream));
+      if (rc == SB2_OK) {
+        g_obmc_last = 4;
+        return check_cuda (cudaGetLastError (), "obmc_kernel_blocks launch");
+      }
+      return set_error (SB2_ERR_UNSUPPORTED, "sb2_obmc_render: the block kernel does not cover this geometry");
+    }
     // 2: the scatter kernel needs 4-byte aligned output rows, 16-byte aligned residual rows, reference
     // planes whose rows are 4-byte aligned (word loads) and a block table that fits
     bool v4_ok = true;
@@ -469,7 +477,7 @@ sb2_obmc_render (const sb2_obmc_params *p, const void *motion_vectors, size_t mv
     // vectors): 6.2 ms against 5.6 ms for the scatter kernel, so it is the choice only
     // where the scatter kernel does not apply -- or when forced
     if (force == 1 || (force == 0 && !v4_ok)) {
-      const int rc = obmc_blocks_launch (A, ref0, ref1, count, as_stream (stream));
+      const int rc = obmc_blocks_launch (A, ref0, ref1, count, true, as_stream (stream));
       if (rc == SB2_OK) {
         g_obmc_last = 1;
         return check_cuda (cudaGetLastError (), "obmc_kernel_blocks launch");

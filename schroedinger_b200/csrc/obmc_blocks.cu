@@ -23,6 +23,7 @@
 
 #include "obmc_common.cuh"
 #include <cuda.h>
+#include <cstddef>
 #include <cstring>
 #include <mutex>
 
@@ -53,14 +54,15 @@ static_assert (sizeof (Blk6) == 32, "two 16-byte reads per table entry");
 struct Maps6 { CUtensorMap m[2][3]; };
 
 struct Smem6 {
-  alignas (128) unsigned char ref[2][R6_BYTES + 128];      // [128 spare bytes][region]
-  alignas (16) int acc[A6_H * A6_P + 4];
+  alignas (128) int acc[A6_H * A6_P + 4];
   alignas (16) Blk6 tab[T6_MAXB];
-  int go[T6_MAXB][2][4];                                   // tap offsets into the reference planes (for blocks not staged)
+  alignas (16) int go[T6_MAXB][2][4];                                   // tap offsets into the reference planes (for blocks not staged)
   unsigned char wx[64], wy[64];
   alignas (16) unsigned lane[32][12];                      // per lane of a pass: wb[8], accumulator word, region byte, need | late << 8 | on << 16, -
   alignas (8) unsigned long long bar;
+  alignas (128) unsigned char ref[2][R6_BYTES + 128];      // [128 spare bytes][region]; LAST: absent when nothing is staged
 };
+constexpr size_t SMEM6_UNSTAGED = offsetof (Smem6, ref);
 
 __device__ __forceinline__ unsigned s6_u32 (const void *p) { return (unsigned) __cvta_generic_to_shared (p); }
 
@@ -77,10 +79,14 @@ __device__ __forceinline__ uint2 lds8 (unsigned addr)
 // (global: only the words holding the `need` bytes asked for are touched -- the last row of a slab has nothing after it)
 __device__ __forceinline__ uint2 ldg8 (const uint8_t *p, int need)
 {
-  const unsigned mis = (unsigned) ((size_t) p & 3);
-  const unsigned *w = reinterpret_cast<const unsigned *> (p - mis);
-  const unsigned w0 = __ldg (w), w1 = (int) mis + need > 4 ? __ldg (w + 1) : 0u, w2 = (int) mis + need > 8 ? __ldg (w + 2) : 0u;
-  return make_uint2 (__funnelshift_r (w0, w1, mis * 8), __funnelshift_r (w1, w2, mis * 8));
+  // two 8-byte loads: a warp's request touches a line per block row, so fewer, wider requests
+  const unsigned mis = (unsigned) ((size_t) p & 7);
+  const uint2 *w = reinterpret_cast<const uint2 *> (p - mis);
+  const uint2 a = __ldg (w), b = (int) mis + need > 8 ? __ldg (w + 1) : make_uint2 (0u, 0u);
+  const bool hi = (mis & 4) != 0;
+  const unsigned w0 = hi ? a.y : a.x, w1 = hi ? b.x : a.y, w2 = hi ? b.y : b.x;
+  const unsigned sh = (mis & 3) * 8;
+  return make_uint2 (__funnelshift_r (w0, w1, sh), __funnelshift_r (w1, w2, sh));
 }
 
 // shared-memory reduction, predicated on `on` without a branch
@@ -128,8 +134,11 @@ __device__ __forceinline__ uint2 predict8 (unsigned w, const int (&o)[4], LD ld)
   return make_uint2 (taps4 (sx, w), taps4 (sy, w));
 }
 
-template <bool SIMPLE>
-__global__ void __launch_bounds__ (T6_THREADS, 2)
+// STAGED = false: the same kernel without the staged regions -- every block reads its taps from global
+// memory (the path the staged kernel keeps for outlier vectors).  A quarter of the shared memory and
+// half the registers: four CTAs an SM instead of two.
+template <bool SIMPLE, bool STAGED>
+__global__ void __launch_bounds__ (T6_THREADS, STAGED ? 2 : 4)
 obmc_kernel_blocks (const ObmcArgs A, const TileGrid tiles, const __grid_constant__ Maps6 maps)
 {
   extern __shared__ unsigned char smem_raw[];
@@ -155,7 +164,7 @@ obmc_kernel_blocks (const ObmcArgs A, const TileGrid tiles, const __grid_constan
   // ---- one bulk tensor copy per reference: the region around the tile, all four phases
   const int rx0 = tx0 - R6_MX, ry0 = ty0 - R6_MY;
   const int nref = A.has_ref1 ? 2 : 1;
-  if (threadIdx.x == 0) {
+  if (STAGED && threadIdx.x == 0) {
     const unsigned bar = s6_u32 (&S.bar);
     asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
     asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -259,7 +268,7 @@ obmc_kernel_blocks (const ObmcArgs A, const TileGrid tiles, const __grid_constan
         const int u = hx + (t2 & 1), v = hy + (t2 >> 1);
         const int ph = ((v & 1) << 1) | (u & 1);
         const int ox = (u >> 1) - rx0, oy = (v >> 1) - ry0;
-        inside = inside && ox >= 0 && oy >= 0 && ox + 8 * ipr + 4 <= R6_W && oy + yblen <= R6_H;
+        inside = STAGED && inside && ox >= 0 && oy >= 0 && ox + 8 * ipr + 4 <= R6_W && oy + yblen <= R6_H;
         e.o[r][t2] = (unsigned short) (ph * R6_PLANE + oy * R6_W + ox + R6_BIAS);
         go[t2] = ph * (rs >> 2) + (v >> 1) * rs + (u >> 1);
       }
@@ -273,7 +282,7 @@ obmc_kernel_blocks (const ObmcArgs A, const TileGrid tiles, const __grid_constan
     S.tab[t] = e;
   }
   __syncthreads ();
-  {
+  if (STAGED) {
     const unsigned bar = s6_u32 (&S.bar);
     unsigned done = 0, tries = 0;
     while (!done) {
@@ -282,7 +291,7 @@ obmc_kernel_blocks (const ObmcArgs A, const TileGrid tiles, const __grid_constan
       if (!done && ++tries > (1u << 24)) __trap ();           // a copy that never lands is an error, not a hang
     }
   }
-  const unsigned reg0 = s6_u32 (&S.ref[0][128]) - R6_BIAS, reg1 = s6_u32 (&S.ref[1][128]) - R6_BIAS;
+  const unsigned reg0 = STAGED ? s6_u32 (&S.ref[0][128]) - R6_BIAS : 0u, reg1 = STAGED ? s6_u32 (&S.ref[1][128]) - R6_BIAS : 0u;
 
   // ---- blocks: lane = (block of the pass, block row r, 8-pixel item h); constants from S.lane
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -315,23 +324,25 @@ obmc_kernel_blocks (const ObmcArgs A, const TileGrid tiles, const __grid_constan
     if (mode != 0) {
       uint2 p0 = make_uint2 (0, 0), p1 = make_uint2 (0, 0);
       if (mode & 1) {
-        if (e0.x & 8) {
+        if (STAGED && (e0.x & 8)) {
           const int o[4] = { (int) (e1.x & 0xffff), (int) (e1.x >> 16), (int) (e1.y & 0xffff), (int) (e1.y >> 16) };
           const unsigned base = reg0 + reg_lane;
           p0 = predict8 (e0.z, o, [&] (int off) { return lds8 (base + off); });
         } else {
-          const int o[4] = { S.go[t][0][0], S.go[t][0][1], S.go[t][0][2], S.go[t][0][3] };
+          const int4 gv = *reinterpret_cast<const int4 *> (&S.go[t][0][0]);
+          const int o[4] = { gv.x, gv.y, gv.z, gv.w };
           const uint8_t *base = ref0 + (ptrdiff_t) r * rs0 + 8 * h;
           p0 = predict8 (e0.z, o, [&] (int off) { return ldg8 (base + off, need); });
         }
       }
       if (mode & 2) {
-        if (e0.x & 16) {
+        if (STAGED && (e0.x & 16)) {
           const int o[4] = { (int) (e1.z & 0xffff), (int) (e1.z >> 16), (int) (e1.w & 0xffff), (int) (e1.w >> 16) };
           const unsigned base = reg1 + reg_lane;
           p1 = predict8 (e0.w, o, [&] (int off) { return lds8 (base + off); });
         } else {
-          const int o[4] = { S.go[t][1][0], S.go[t][1][1], S.go[t][1][2], S.go[t][1][3] };
+          const int4 gv = *reinterpret_cast<const int4 *> (&S.go[t][1][0]);
+          const int o[4] = { gv.x, gv.y, gv.z, gv.w };
           const uint8_t *base = ref1 + (ptrdiff_t) r * rs1 + 8 * h;
           p1 = predict8 (e0.w, o, [&] (int off) { return ldg8 (base + off, need); });
         }
@@ -505,7 +516,7 @@ static bool make_ref_map6 (CUtensorMap *tm, const sb2_slab *s, int c)
       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int obmc_blocks_launch (const ObmcArgs &A, const sb2_slab *ref0, const sb2_slab *ref1, int count, cudaStream_t st)
+int obmc_blocks_launch (const ObmcArgs &A, const sb2_slab *ref0, const sb2_slab *ref1, int count, bool staged, cudaStream_t st)
 {
   for (int c = 0; c < A.ncomp; c++) {
     const int ipr = (A.xblen[c] + 7) >> 3;
@@ -518,23 +529,41 @@ int obmc_blocks_launch (const ObmcArgs &A, const sb2_slab *ref0, const sb2_slab 
   Maps6 maps;
   memset (&maps, 0, sizeof (maps));
   for (int c = 0; c < A.ncomp; c++) {
-    if (!make_ref_map6 (&maps.m[0][c], ref0, c)) return SB2_ERR_UNSUPPORTED;
-    if (ref1 && !make_ref_map6 (&maps.m[1][c], ref1, c)) return SB2_ERR_UNSUPPORTED;
+    if (staged) {
+      if (!make_ref_map6 (&maps.m[0][c], ref0, c)) return SB2_ERR_UNSUPPORTED;
+      if (ref1 && !make_ref_map6 (&maps.m[1][c], ref1, c)) return SB2_ERR_UNSUPPORTED;
+    }
+    // the global path (all of the unstaged kernel, the outliers of the staged one) loads 8-byte words
+    if ((ref0->stride[c] & 31) || (ref1 && (ref1->stride[c] & 31)) || (ref0->offset[c] & 7) || (ref1 && (ref1->offset[c] & 7)))
+      return SB2_ERR_UNSUPPORTED;
   }
+  if ((((size_t) ref0->base | ref0->picture_pitch) & 7) || (ref1 && (((size_t) ref1->base | ref1->picture_pitch) & 7)))
+    return SB2_ERR_UNSUPPORTED;
   TileGrid tiles;
   const dim3 grid = make_tile_grid (tiles, A.ncomp, A.w, A.h, T6_W, T6_H, count);
-  const size_t smem = sizeof (Smem6) + 128;
+  const size_t smem = (staged ? sizeof (Smem6) : SMEM6_UNSTAGED) + 128;
   const bool simple = (A.w1 == 1 && A.w2 == 1 && A.bits == 1);
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once (once, [&] {
-    attr_err = cudaFuncSetAttribute (obmc_kernel_blocks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    const int big = (int) sizeof (Smem6) + 128, small = (int) SMEM6_UNSTAGED + 128;
+    attr_err = cudaFuncSetAttribute (obmc_kernel_blocks<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute (obmc_kernel_blocks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+      attr_err = cudaFuncSetAttribute (obmc_kernel_blocks<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (attr_err == cudaSuccess && small > 48 * 1024) {
+      attr_err = cudaFuncSetAttribute (obmc_kernel_blocks<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+      if (attr_err == cudaSuccess)
+        attr_err = cudaFuncSetAttribute (obmc_kernel_blocks<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+    }
   });
   if (attr_err != cudaSuccess) return SB2_ERR_UNSUPPORTED;
-  if (simple) obmc_kernel_blocks<true><<<grid, T6_THREADS, smem, st>>> (A, tiles, maps);
-  else obmc_kernel_blocks<false><<<grid, T6_THREADS, smem, st>>> (A, tiles, maps);
+  if (staged) {
+    if (simple) obmc_kernel_blocks<true, true><<<grid, T6_THREADS, smem, st>>> (A, tiles, maps);
+    else obmc_kernel_blocks<false, true><<<grid, T6_THREADS, smem, st>>> (A, tiles, maps);
+  } else {
+    if (simple) obmc_kernel_blocks<true, false><<<grid, T6_THREADS, smem, st>>> (A, tiles, maps);
+    else obmc_kernel_blocks<false, false><<<grid, T6_THREADS, smem, st>>> (A, tiles, maps);
+  }
   return SB2_OK;
 }
 

@@ -177,6 +177,6 @@ __device__ __forceinline__ uint2 fetch4x4 (const uint8_t *ref, const BlkRef &br,
 // obmc_blocks.cu: reference regions staged by TMA, one block per warp pass, for blocks of at most 32
 // (row, 8-pixel item) lanes on frames with a 32-pixel border.  Returns SB2_OK when it launched,
 // SB2_ERR_UNSUPPORTED when the caller should take another kernel.
-int obmc_blocks_launch (const ObmcArgs &A, const sb2_slab *ref0, const sb2_slab *ref1, int count, cudaStream_t st);
+int obmc_blocks_launch (const ObmcArgs &A, const sb2_slab *ref0, const sb2_slab *ref1, int count, bool staged, cudaStream_t st);
 
 }  // namespace sb2

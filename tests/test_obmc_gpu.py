@@ -12,7 +12,7 @@ from tests.golden import make_golden as mg
 pytestmark = pytest.mark.gpu
 ORACLE = helpers.load_oracle()
 GOLD = np.load(os.path.join(helpers.GOLDEN_DIR, "motion.npz"))
-KERNELS = {"auto": 0, "tma": 1, "scatter": 2, "pixel": 3}
+KERNELS = {"auto": 0, "tma": 1, "scatter": 2, "pixel": 3, "blocks": 4}
 RAN = {k: 0 for k in KERNELS}
 
 
@@ -64,7 +64,7 @@ def gpu_obmc(case, add, count=1):
             return None
         raise
     which = lib.sb2_obmc_last_kernel()
-    RAN[{1: "tma", 2: "scatter", 3: "pixel"}[which]] += 1
+    RAN[{1: "tma", 2: "scatter", 3: "pixel", 4: "blocks"}[which]] += 1
     return [[(acc.download(p, c), res.download(p, c), out.download(p, c)) for c in range(3)]
             for p in range(count)]
 
@@ -127,6 +127,6 @@ def test_obmc_every_kernel_ran(cuda, obmc_kernel):
     from schroedinger_b200 import lib
     case = helpers.ObmcCase(ORACLE, 96, 64, rng=np.random.default_rng(5))
     assert gpu_obmc(case, 1) is not None
-    want = {"auto": 2, "tma": 1, "scatter": 2, "pixel": 3}[obmc_kernel]
+    want = {"auto": 2, "tma": 1, "scatter": 2, "pixel": 3, "blocks": 4}[obmc_kernel]
     assert lib.sb2_obmc_last_kernel() == want
     assert RAN["tma"] > 0 and RAN["scatter"] > 0 and (obmc_kernel == "auto" or RAN[obmc_kernel] > 0)
