@@ -46,4 +46,29 @@ compat_shim_hbm_new (SchroParams * params, int levels, int enable_chroma_me,
   return schro_hbm_new (&fx->frame, 0);
 }
 
+/* the same for the rough search: schro_rough_me_new (frame, frame->ref_frame[ref]) as
+ * schro_encoder_motion_predict_rough calls it (schromotionest.c:72-75) */
+SchroRoughME *
+compat_shim_rough_me_new (SchroParams * params, int levels, int ref, SchroFrame ** src, SchroFrame ** reff,
+    void **fixture_out)
+{
+  ShimFixture *fx = calloc (1, sizeof (ShimFixture));
+  int i;
+  fx->encoder.downsample_levels = levels;
+  fx->frame.encoder = &fx->encoder;
+  fx->ref_frame.encoder = &fx->encoder;
+  fx->frame.params = *params;
+  fx->frame.ref_frame[ref] = &fx->ref_frame;
+  fx->frame.filtered_frame = src[0];
+  fx->ref_frame.filtered_frame = reff[0];
+  fx->frame.have_downsampling = TRUE;
+  fx->ref_frame.have_downsampling = TRUE;
+  for (i = 0; i < levels; i++) {
+    fx->frame.downsampled_frames[i] = src[i + 1];
+    fx->ref_frame.downsampled_frames[i] = reff[i + 1];
+  }
+  *fixture_out = fx;
+  return schro_rough_me_new (&fx->frame, fx->frame.ref_frame[ref]);
+}
+
 void compat_shim_free (void *fixture) { free (fixture); }

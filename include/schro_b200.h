@@ -220,6 +220,24 @@ int sb2_hbm_scan_hint (const sb2_hbm_params *params, const sb2_slab *src_level,
     const void *parent_field, void *out_field, size_t field_picture_pitch,
     void *workspace, size_t workspace_bytes, void *stream);
 
+/* The rough ("bigblock") motion search, one pyramid level for `count` independent (picture,
+ * reference) pairs.  Luma only; sb2_hbm_params.use_chroma / chroma shifts are
+ * ignored.  Fields as in sb2_hbm_scan_hint; every entry is initialised as schro_motion_field_set
+ * (mf, 0, 1) does, entries on the 1<<shift grid receive the search result.
+ * sb2_rough_scan_nohint = schro_rough_me_heirarchical_scan_nohint (schroedinger/schroroughmotion.c:62-143):
+ *   full search of +-distance around every block (no dependency between blocks).
+ * sb2_rough_scan_hint = schro_rough_me_heirarchical_scan_hint (:145-300): candidates zero / four
+ *   nearest parents (field of level shift+1) / left, up, up-left of this level, then a +-distance scan.
+ * A block that lies entirely outside its level's frame keeps the zero vector at a hint level (the
+ * reference reads stale memory there, oracle/oracle_rough.c). */
+size_t sb2_rough_workspace_bytes (int x_num_blocks, int y_num_blocks, int count);
+int sb2_rough_scan_nohint (const sb2_hbm_params *params, const sb2_slab *src_level,
+    const sb2_slab *ref_level, int extension, int shift, int distance, void *out_field,
+    size_t field_picture_pitch, void *stream);
+int sb2_rough_scan_hint (const sb2_hbm_params *params, const sb2_slab *src_level,
+    const sb2_slab *ref_level, int extension, int shift, int distance, const void *parent_field,
+    void *out_field, size_t field_picture_pitch, void *workspace, size_t workspace_bytes, void *stream);
+
 /* schro_metric_absdiff_u8 (schroedinger/schrometric.c:10-29) for `n` independent block
  * pairs: sad[i] = SAD(a + a_offset[i], b + b_offset[i]) over width x height. */
 int sb2_sad_u8 (const uint8_t *a, int a_stride, const uint8_t *b, int b_stride,

@@ -411,6 +411,30 @@ void schro_hbm_scan (SchroHierBm *schro_hbm);
 void schro_hierarchical_bm_scan_hint (SchroHierBm *schro_hbm, int shift, int h_range);
 SchroMotionField *schro_hbm_motion_field (SchroHierBm *schro_hbm, int level);
 
+/* ---- rough (bigblock) motion search (schroedinger/schromotionest.h:50-76, schroroughmotion.c) ----
+ * SchroRoughME as the reference lays it out; callers read motion_fields[1] / [2] directly
+ * (schromotionest.c:535, 742; schroglobalest.c:25), so every level function brings its field
+ * back to the host before it returns.  schro_rough_me_new (SchroEncoderFrame *, SchroEncoderFrame *)
+ * reads the encoder structure; the library exports the constructor with those things passed
+ * explicitly and compat/schro_rough_me_new.c is the reference-side half (as for schro_hbm_new). */
+#define SCHRO_MAX_HIER_LEVELS 8                         /* schroedinger/schromotionest.h:20 */
+struct _SchroEncoderFrame;
+typedef struct _SchroRoughME {
+  struct _SchroEncoderFrame *encoder_frame;
+  struct _SchroEncoderFrame *ref_frame;
+  SchroMotionField *motion_fields[SCHRO_MAX_HIER_LEVELS];
+} SchroRoughME;
+/* frames[0] = the filtered picture, frames[i] = pyramid level i, i <= levels
+ * (encoder->downsample_levels); ref = which of ref_frame[0] / [1] `ref_frame` is */
+SchroRoughME *schro_rough_me_new_from_frames (struct _SchroEncoderFrame *frame,
+    struct _SchroEncoderFrame *ref_frame, SchroParams *params, int ref, int levels,
+    SchroFrame **src_frames, SchroFrame **ref_frames);
+void schro_rough_me_free (SchroRoughME *rme);
+void schro_rough_me_heirarchical_scan (SchroRoughME *rme);
+void schro_rough_me_heirarchical_scan_nohint (SchroRoughME *rme, int shift, int distance);
+void schro_rough_me_heirarchical_scan_hint (SchroRoughME *rme, int shift, int distance);
+
+
 #ifdef __cplusplus
 }
 #endif

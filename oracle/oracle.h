@@ -136,6 +136,15 @@ uint32_t oracle_metric_scan_get_min (const uint32_t *metrics, const uint32_t *ch
 int oracle_metric_fast_block (const OraclePyrLevel *src, const OraclePyrLevel *ref, int bw, int bh, int x,
     int y, int dx, int dy);
 
+/* Rough (bigblock) motion search (oracle_rough.c): one level of
+ * schro_rough_me_heirarchical_scan_nohint / _hint (schroedinger/schroroughmotion.c:62-300).
+ * mf: output field (x_num_blocks*y_num_blocks), parent: field of level shift+1. */
+void oracle_rough_scan_nohint (const OraclePyrLevel *src, const OraclePyrLevel *ref, int xbsep, int ybsep,
+    int x_num_blocks, int y_num_blocks, int ref_index, int shift, int distance, OracleMotionVector *mf);
+void oracle_rough_scan_hint (const OraclePyrLevel *src, const OraclePyrLevel *ref, int xbsep, int ybsep,
+    int x_num_blocks, int y_num_blocks, int ref_index, int shift, int distance,
+    const OracleMotionVector *parent, OracleMotionVector *mf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -354,6 +354,74 @@ ref_hbm_run (const RefHbmParams *hp, void **src, const int *src_stride, void **r
   free (enc);
 }
 
+/* ---- rough (bigblock) motion search: schro_rough_me_heirarchical_scan
+ * (schroedinger/schroroughmotion.c:46-60) = _nohint (levels, 12) then _hint (l, 4) for l = levels-1 .. 1;
+ * with other distances the two functions are called directly in that order.
+ * fields: (levels+1) arrays of x_num_blocks*y_num_blocks vectors, index = level (level 0 stays zero). */
+void
+ref_rough_run (const RefHbmParams *hp, int nohint_distance, int hint_distance, void **src, const int *src_stride,
+    void **ref, const int *ref_stride, SchroMotionVector *fields, int *x_num_blocks, int *y_num_blocks)
+{
+  SchroEncoder *enc = calloc (1, sizeof (SchroEncoder));
+  SchroEncoderFrame *fs = calloc (1, sizeof (SchroEncoderFrame));
+  SchroEncoderFrame *fr = calloc (1, sizeof (SchroEncoderFrame));
+  SchroVideoFormat vf;
+  SchroFrameFormat fmt;
+  SchroRoughME *rme;
+  int i, n, l;
+
+  ref_init ();
+  memset (&vf, 0, sizeof (vf));
+  vf.width = hp->width;
+  vf.height = hp->height;
+  vf.chroma_format = hp->chroma_format;
+  fmt = schro_params_get_frame_format (8, hp->chroma_format);
+  enc->downsample_levels = hp->levels;
+  for (i = 0; i < 2; i++) {
+    SchroEncoderFrame *f = i ? fr : fs;
+    f->encoder = enc;
+    f->params.video_format = &vf;
+    f->params.xbsep_luma = hp->xbsep;
+    f->params.ybsep_luma = hp->ybsep;
+    f->params.xblen_luma = hp->xbsep;
+    f->params.yblen_luma = hp->ybsep;
+    f->params.num_refs = 1;
+    schro_params_calculate_mc_sizes (&f->params);
+    f->have_downsampling = TRUE;
+  }
+  fs->filtered_frame = load_frame (fmt, hp->width, hp->height, src, src_stride);
+  fr->filtered_frame = load_frame (fmt, hp->width, hp->height, ref, ref_stride);
+  schro_encoder_frame_downsample (fs);
+  schro_encoder_frame_downsample (fr);
+  fs->ref_frame[hp->ref_index] = fr;
+
+  rme = schro_rough_me_new (fs, fr);
+  if (nohint_distance == 12 && hint_distance == 4) {
+    schro_rough_me_heirarchical_scan (rme);
+  } else {
+    schro_rough_me_heirarchical_scan_nohint (rme, hp->levels, nohint_distance);
+    for (l = hp->levels - 1; l >= 1; l--) schro_rough_me_heirarchical_scan_hint (rme, l, hint_distance);
+  }
+  n = fs->params.x_num_blocks * fs->params.y_num_blocks;
+  *x_num_blocks = fs->params.x_num_blocks;
+  *y_num_blocks = fs->params.y_num_blocks;
+  for (l = 0; l <= hp->levels; l++) {
+    SchroMotionField *mf = rme->motion_fields[l];
+    if (mf) memcpy (fields + (size_t) l * n, mf->motion_vectors, sizeof (SchroMotionVector) * n);
+    else memset (fields + (size_t) l * n, 0, sizeof (SchroMotionVector) * n);
+  }
+  schro_rough_me_free (rme);
+  for (i = 0; i < hp->levels; i++) {
+    schro_frame_unref (fs->downsampled_frames[i]);
+    schro_frame_unref (fr->downsampled_frames[i]);
+  }
+  schro_frame_unref (fs->filtered_frame);
+  schro_frame_unref (fr->filtered_frame);
+  free (fs);
+  free (fr);
+  free (enc);
+}
+
 /* schro_metric_absdiff_u8 (schroedinger/schrometric.c:10) */
 /* schro_metric_scan_setup / _do_scan / _get_min and schro_metric_fast_block
  * (schroedinger/schrometric.c:31-214, 380-414) on two 4:2:0 u8 pictures loaded into frames with a

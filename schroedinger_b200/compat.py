@@ -179,6 +179,22 @@ _proto("schro_hbm_scan", None, [ctypes.POINTER(SchroHierBm)])
 _proto("schro_hierarchical_bm_scan_hint", None, [ctypes.POINTER(SchroHierBm), ctypes.c_int, ctypes.c_int])
 _proto("schro_hbm_motion_field", ctypes.POINTER(SchroMotionField), [ctypes.POINTER(SchroHierBm), ctypes.c_int])
 
+
+
+class SchroRoughME(ctypes.Structure):
+    """schroedinger/schromotionest.h:50-55"""
+    _fields_ = [("encoder_frame", ctypes.c_void_p), ("ref_frame", ctypes.c_void_p),
+                ("motion_fields", ctypes.POINTER(SchroMotionField) * 8)]
+
+
+_proto("schro_rough_me_new_from_frames", ctypes.POINTER(SchroRoughME),
+       [ctypes.c_void_p, ctypes.c_void_p, ParamsP, ctypes.c_int, ctypes.c_int, ctypes.POINTER(FrameP),
+        ctypes.POINTER(FrameP)])
+_proto("schro_rough_me_free", None, [ctypes.POINTER(SchroRoughME)])
+_proto("schro_rough_me_heirarchical_scan", None, [ctypes.POINTER(SchroRoughME)])
+_proto("schro_rough_me_heirarchical_scan_nohint", None, [ctypes.POINTER(SchroRoughME), ctypes.c_int, ctypes.c_int])
+_proto("schro_rough_me_heirarchical_scan_hint", None, [ctypes.POINTER(SchroRoughME), ctypes.c_int, ctypes.c_int])
+
 _NP = {0x00: np.uint8, 0x04: np.int16, 0x08: np.int32}
 
 

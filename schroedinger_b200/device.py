@@ -386,3 +386,44 @@ def hbm_scan(params, src_pyr, ref_pyr, level0_range=3, fields=None, workspace=No
         hbm_scan_hint(params, src_pyr.slabs[l], ref_pyr.slabs[l], l, r,
                       fields[l + 1] if l < levels else None, fields[l], workspace, stream)
     return fields
+
+
+def rough_scan_nohint(params, src_level, ref_level, shift, distance, out, stream=None):
+    """schro_rough_me_heirarchical_scan_nohint for every (picture, reference) pair; out: uint8 CUDA
+    tensor of count x nblocks x 20 bytes."""
+    require_cuda()
+    n = params.x_num_blocks * params.y_num_blocks
+    check(lib.sb2_rough_scan_nohint(
+        ctypes.byref(params), ctypes.byref(src_level.slab), ctypes.byref(ref_level.slab),
+        src_level.layout.extension, shift, distance, ctypes.c_void_p(out.data_ptr()), ctypes.c_size_t(n),
+        _stream_ptr(stream)), "sb2_rough_scan_nohint")
+
+
+def rough_scan_hint(params, src_level, ref_level, shift, distance, parent, out, workspace=None, stream=None):
+    """schro_rough_me_heirarchical_scan_hint; parent = the field of level shift + 1."""
+    require_cuda()
+    n = params.x_num_blocks * params.y_num_blocks
+    ws = workspace or _default_ws
+    ptr, size = ws.get(lib.sb2_rough_workspace_bytes(params.x_num_blocks, params.y_num_blocks, src_level.count))
+    check(lib.sb2_rough_scan_hint(
+        ctypes.byref(params), ctypes.byref(src_level.slab), ctypes.byref(ref_level.slab),
+        src_level.layout.extension, shift, distance, ctypes.c_void_p(parent.data_ptr()),
+        ctypes.c_void_p(out.data_ptr()), ctypes.c_size_t(n), ptr, size, _stream_ptr(stream)),
+        "sb2_rough_scan_hint")
+
+
+def rough_scan(params, src_pyr, ref_pyr, nohint_distance=12, hint_distance=4, fields=None, workspace=None,
+               stream=None):
+    """schro_rough_me_heirarchical_scan (schroedinger/schroroughmotion.c:46-60): fields[level] for
+    level = levels .. 1 (fields[0] is not produced by the rough search)."""
+    levels = src_pyr.levels
+    count = src_pyr.slabs[0].count
+    n = params.x_num_blocks * params.y_num_blocks
+    if fields is None:
+        fields = [None] + [torch.empty(count * n * 20, dtype=torch.uint8, device="cuda") for _ in range(levels)]
+    rough_scan_nohint(params, src_pyr.slabs[levels], ref_pyr.slabs[levels], levels, nohint_distance,
+                      fields[levels], stream)
+    for l in range(levels - 1, 0, -1):
+        rough_scan_hint(params, src_pyr.slabs[l], ref_pyr.slabs[l], l, hint_distance, fields[l + 1], fields[l],
+                        workspace, stream)
+    return fields

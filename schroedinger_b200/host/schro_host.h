@@ -59,6 +59,10 @@ void *sb2h_pool_alloc (size_t bytes);
 void sb2h_pool_free (void *ptr);
 void *sb2h_dev_buffer (Sb2hContext *cx, int which, size_t bytes);
 
+/* a u8 pyramid level as a one-picture slab: zero-copy for CUDA-domain frames, else uploaded once into
+ * *cache (a pool block the caller frees); returns 1 when it enqueued an upload out of page-locked memory */
+int sb2h_level_slab (Sb2hContext *cx, SchroFrame *f, void **cache, sb2_slab *slab);
+
 static inline int sb2h_bpp (SchroFrameFormat format)
 {
   switch (SCHRO_FRAME_FORMAT_DEPTH (format)) {

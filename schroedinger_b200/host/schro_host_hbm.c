@@ -136,8 +136,8 @@ schro_hbm_motion_field (SchroHierBm *hbm, int level)
 
 /* returns 1 when it enqueued an upload out of page-locked host memory (the caller then waits
  * before returning: the DMA engine reads that memory after the copy call) */
-static int
-level_slab (Sb2hContext *cx, SchroFrame *f, void **cache, sb2_slab *slab)
+int
+sb2h_level_slab (Sb2hContext *cx, SchroFrame *f, void **cache, sb2_slab *slab)
 {
   const size_t bytes = (size_t) f->components[0].length + f->components[1].length + f->components[2].length;
   char *base;
@@ -184,8 +184,8 @@ prepare_level (Sb2hContext *cx, SchroHierBm *hbm, int shift, LevelIn *in)
   SchroParams *params = hbm->params;
   const size_t n = (size_t) params->x_num_blocks * params->y_num_blocks;
   SB2H_ASSERT (shift >= 0 && shift <= hbm->hierarchy_levels);
-  in->staged = level_slab (cx, hbm->downsampled_src[shift], &h->dev_src[shift], &in->ss);
-  in->staged |= level_slab (cx, hbm->downsampled_ref[shift], &h->dev_ref[shift], &in->rs);
+  in->staged = sb2h_level_slab (cx, hbm->downsampled_src[shift], &h->dev_src[shift], &in->ss);
+  in->staged |= sb2h_level_slab (cx, hbm->downsampled_ref[shift], &h->dev_ref[shift], &in->rs);
   if (!h->dev_ws) {
     h->ws_bytes = sb2_hbm_workspace_bytes (params->x_num_blocks, params->y_num_blocks, 1);
     h->dev_ws = sb2h_pool_alloc (h->ws_bytes);

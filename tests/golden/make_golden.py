@@ -107,6 +107,22 @@ def hbm_golden(ref):
     print("hbm.npz:", len(out), "arrays")
 
 
+# (width, height, levels, ref_index, pan, nohint distance, hint distance): sizes the block grid covers exactly
+ROUGH_GOLDEN_CASES = [(256, 128, 2, 0, (5, 3), 12, 4), (512, 256, 3, 1, (-7, 2), 12, 4), (640, 384, 4, 0, (11, -6), 12, 4),
+                      (256, 192, 3, 0, (4, -4), 7, 2), (384, 256, 2, 0, (20, 9), 20, 6)]
+
+
+def rough_golden(ref):
+    """schro_rough_me_heirarchical_scan of the compiled reference"""
+    out = {}
+    for idx, (w, h, lv, ri, pan, dn, dh) in enumerate(ROUGH_GOLDEN_CASES):
+        s, r = helpers.panning_pair(w, h, np.random.default_rng(3000 + idx), pan)
+        out[f"r{idx}_fields"] = helpers.ref_rough(ref, s, r, w, h, levels=lv, ref_index=ri, nohint_distance=dn,
+                                                  hint_distance=dh)
+    np.savez_compressed(os.path.join(helpers.GOLDEN_DIR, "rough.npz"), **out)
+    print("rough.npz:", len(out), "arrays")
+
+
 def glue_golden(ref):
     """schro_frame_convert / schro_frame_add / schro_frame_subtract of the compiled reference."""
     rng = np.random.default_rng(20261019)
@@ -181,7 +197,7 @@ def main():
     if ref is None:
         raise SystemExit("oracle/_ref/libschro_ref.so missing: run `make ref` where /root/reference exists")
     wavelet_golden(ref)
-    for name in ("frame_golden", "motion_golden", "hbm_golden", "glue_golden", "dequant_golden", "metric_scan_golden"):
+    for name in ("frame_golden", "motion_golden", "hbm_golden", "rough_golden", "glue_golden", "dequant_golden", "metric_scan_golden"):
         fn = globals().get(name)
         if fn:
             fn(ref)

@@ -405,6 +405,61 @@ def ref_hbm(ref, src_planes, ref_planes, width, height, xbsep=8, ybsep=8, levels
     return fields, pyr
 
 
+def oracle_rough(oracle, src_planes, ref_planes, width, height, xbsep=8, ybsep=8, levels=4, ref_index=0,
+                 nohint_distance=12, hint_distance=4):
+    """schro_rough_me_heirarchical_scan through the oracle -> fields[level] (level 0 stays zero)."""
+    ext = max(xbsep, ybsep)
+    ps = build_pyramid(oracle, "oracle", src_planes, levels, ext=ext)
+    pr = build_pyramid(oracle, "oracle", ref_planes, levels, ext=ext)
+    nbx, nby = hbm_block_counts(width, height, xbsep, ybsep)
+    fields = np.zeros((levels + 1, nbx * nby), dtype=MV_DTYPE)
+    oracle.oracle_rough_scan_nohint.restype = None
+    oracle.oracle_rough_scan_hint.restype = None
+    s, rr = pyr_level_struct(ps[levels]), pyr_level_struct(pr[levels])
+    oracle.oracle_rough_scan_nohint(ctypes.byref(s), ctypes.byref(rr), xbsep, ybsep, nbx, nby, ref_index, levels,
+                                    nohint_distance, fields[levels].ctypes.data_as(ctypes.c_void_p))
+    for l in range(levels - 1, 0, -1):
+        s, rr = pyr_level_struct(ps[l]), pyr_level_struct(pr[l])
+        oracle.oracle_rough_scan_hint(ctypes.byref(s), ctypes.byref(rr), xbsep, ybsep, nbx, nby, ref_index, l,
+                                      hint_distance, fields[l + 1].ctypes.data_as(ctypes.c_void_p),
+                                      fields[l].ctypes.data_as(ctypes.c_void_p))
+    return fields, ps, pr
+
+
+def ref_rough(ref, src_planes, ref_planes, width, height, xbsep=8, ybsep=8, levels=4, ref_index=0,
+              nohint_distance=12, hint_distance=4):
+    """The same through the compiled reference (schro_rough_me_heirarchical_scan when the distances
+    are the reference's own 12 / 4)."""
+    nbx, nby = hbm_block_counts(width, height, xbsep, ybsep)
+    P = ctypes.c_void_p * 3
+    I = ctypes.c_int * 3
+    hp = RefHbmParams(width, height, 2, xbsep, ybsep, levels, 0, ref_index, 0)
+    nx, ny = ctypes.c_int(), ctypes.c_int()
+    fields = np.zeros((levels + 1, nbx * nby), dtype=MV_DTYPE)
+    fn = ref.ref_rough_run
+    fn.restype = None
+    fn(ctypes.byref(hp), nohint_distance, hint_distance,
+       P(*[a.ctypes.data for a in src_planes]), I(*[a.strides[0] for a in src_planes]),
+       P(*[a.ctypes.data for a in ref_planes]), I(*[a.strides[0] for a in ref_planes]),
+       fields.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nx), ctypes.byref(ny))
+    assert (nx.value, ny.value) == (nbx, nby)
+    return fields
+
+
+def rough_inside_mask(width, height, xbsep, ybsep, nbx, nby, level):
+    """Blocks of `level`'s grid that overlap that level's frame (the others are where the
+    reference's result is undefined, oracle_rough.c)."""
+    w, h = width, height
+    for _ in range(level):
+        w, h = (w + 1) // 2, (h + 1) // 2
+    skip = 1 << level
+    m = np.zeros((nby, nbx), dtype=bool)
+    for j in range(0, nby, skip):
+        for i in range(0, nbx, skip):
+            m[j, i] = (i >> level) * xbsep < w and (j >> level) * ybsep < h
+    return m.reshape(-1)
+
+
 # ---- combine / convert glue (SURVEY.md 8f rank 2) --------------------------------------------
 DEPTH_DTYPE = {0: np.uint8, 1: np.int16, 2: np.int32}
 

@@ -86,3 +86,71 @@ def test_schro_hbm_new_through_the_shim(cuda):
             assert np.array_equal(got[f], want[l][f]), (l, f)
     lib.schro_hbm_unref(hbm)
     shim.compat_shim_free(fixture)
+
+
+# ---- compat/schro_rough_me_new.c (schroroughmotion.c:21-33) -----------------------------------------
+ROUGH_OBJ = os.path.join(helpers.ROOT, "oracle", "_ref", "obj", "compat_schro_rough_me_new.o")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference headers not present on this box")
+def test_rough_shim_compiles_against_reference_headers():
+    subprocess.check_call(["bash", os.path.join(helpers.ROOT, "oracle", "build_ref.sh")],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    syms = subprocess.check_output(["nm", ROUGH_OBJ], text=True).split("\n")
+    defined = {l.split()[-1] for l in syms if " T " in l}
+    undefined = {l.split()[-1] for l in syms if l.strip().startswith("U ")}
+    assert defined == {"schro_rough_me_new"}
+    assert {u for u in undefined if u.startswith("schro_")} == {"schro_rough_me_new_from_frames", "schro_debug_log"}
+    out = subprocess.check_output(["nm", "-D", os.path.join(helpers.ROOT, "schroedinger_b200", "libschro_b200.so")],
+                                  text=True)
+    assert " T schro_rough_me_new_from_frames" in out and " T schro_rough_me_new\n" not in out
+    for name in ("schro_rough_me_free", "schro_rough_me_heirarchical_scan", "schro_rough_me_heirarchical_scan_nohint",
+                 "schro_rough_me_heirarchical_scan_hint"):
+        assert f" T {name}\n" in out, name
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(SHIM), reason="oracle/_ref/libcompat_shim.so was not built")
+def test_schro_rough_me_new_through_the_shim(cuda):
+    from schroedinger_b200 import compat, lib
+    from tests.test_host_api_gpu import _new_u8_frame
+    oracle = helpers.load_oracle()
+    from schroedinger_b200._lib import LIB_PATH
+    ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    shim = ctypes.CDLL(SHIM)
+    shim.compat_shim_rough_me_new.restype = ctypes.c_void_p
+    shim.compat_shim_free.argtypes = [ctypes.c_void_p]
+    w, h, levels = 320, 192, 3
+    s, r = helpers.panning_pair(w, h, np.random.default_rng(22), (5, -3))
+    want, _, _ = helpers.oracle_rough(oracle, s, r, w, h, levels=levels, ref_index=1)
+    params = compat.make_params(w, h, xbsep=8, ybsep=8, xblen=12, yblen=12)
+
+    def pyramid(planes):
+        frames = [_new_u8_frame(compat, lib, w, h, 32, True, planes)]
+        lib.schro_frame_mc_edgeextend(frames[0])
+        cw, ch = w, h
+        for _ in range(levels):
+            cw, ch = (cw + 1) // 2, (ch + 1) // 2
+            f = compat.frame_new_and_alloc(None, compat.FORMAT_U8_420, cw, ch, 8, 0)
+            lib.schro_frame_downsample(f, frames[-1])
+            lib.schro_frame_mc_edgeextend(f)
+            frames.append(f)
+        return frames
+
+    fs, fr = pyramid(s), pyramid(r)
+    arr = compat.FrameP * (levels + 1)
+    fixture = ctypes.c_void_p()
+    addr = shim.compat_shim_rough_me_new(ctypes.byref(params), levels, 1, arr(*fs), arr(*fr), ctypes.byref(fixture))
+    assert addr
+    rme = ctypes.cast(addr, ctypes.POINTER(compat.SchroRoughME))
+    assert rme.contents.encoder_frame and rme.contents.ref_frame
+    lib.schro_rough_me_heirarchical_scan(rme)
+    n = params.x_num_blocks * params.y_num_blocks
+    for l in range(levels, 0, -1):
+        mf = rme.contents.motion_fields[l]
+        got = np.ctypeslib.as_array(ctypes.cast(mf.contents.motion_vectors, ctypes.POINTER(ctypes.c_uint8)),
+                                    shape=(n * 20,)).view(helpers.MV_DTYPE)
+        for f in ("flags", "metric", "chroma_metric", "v"):
+            assert np.array_equal(got[f], want[l][f]), (l, f)
+    lib.schro_rough_me_free(rme)
+    shim.compat_shim_free(fixture)
