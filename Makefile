@@ -33,7 +33,7 @@ bench_native/libsb2_e2e_driver.so: bench_native/e2e_driver.c include/schro_b200_
 	    -Lschroedinger_b200 -lschro_b200 -lpthread -Wl,-rpath,'$$ORIGIN/../schroedinger_b200'
 
 oracle/liboracle.so: $(ORACLE_SRCS) oracle/oracle.h $(wildcard oracle/*.inc)
-	$(CC) -std=gnu99 -O2 -Wall -fPIC -fwrapv -shared -o $@ $(ORACLE_SRCS)
+	$(CC) -std=gnu99 -O2 -Wall -fPIC -fwrapv -ffp-contract=off -shared -o $@ $(ORACLE_SRCS)
 
 ref:
 	bash oracle/build_ref.sh

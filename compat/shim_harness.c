@@ -71,4 +71,32 @@ compat_shim_rough_me_new (SchroParams * params, int levels, int ref, SchroFrame 
   return schro_rough_me_new (&fx->frame, fx->frame.ref_frame[ref]);
 }
 
+/* the sub-pel refinement: schro_encoder_motion_predict_subpel_deep (me) on a SchroMe stand-in.  The real
+ * SchroMe is private to schromotionest.c, so the five accessors the shim calls are defined here over
+ * this fixture -- in the reference's tree they are the reference's own (schromotionest.c:2789-2885). */
+struct _SchroMe {
+  SchroParams *params;
+  double lambda;
+  SchroFrame *src, *ref[2];
+  SchroMotionField *mf[2];
+};
+SchroParams *schro_me_params (SchroMe * me) { return me->params; }
+double schro_me_lambda (SchroMe * me) { return me->lambda; }
+SchroFrame *schro_me_src (SchroMe * me) { return me->src; }
+SchroFrame *schro_me_ref (SchroMe * me, int ref) { return me->ref[ref]; }
+SchroMotionField *schro_me_subpel_mf (SchroMe * me, int ref) { return me->mf[ref]; }
+
+void
+compat_shim_subpel_deep (SchroParams * params, double lambda, SchroFrame * src, SchroFrame ** refs, SchroMotionField ** mfs)
+{
+  struct _SchroMe me;
+  int r;
+  memset (&me, 0, sizeof (me));
+  me.params = params;
+  me.lambda = lambda;
+  me.src = src;
+  for (r = 0; r < params->num_refs; r++) { me.ref[r] = refs[r]; me.mf[r] = mfs[r]; }
+  schro_encoder_motion_predict_subpel_deep (&me);
+}
+
 void compat_shim_free (void *fixture) { free (fixture); }

@@ -238,6 +238,31 @@ int sb2_rough_scan_hint (const sb2_hbm_params *params, const sb2_slab *src_level
     const sb2_slab *ref_level, int extension, int shift, int distance, const void *parent_field,
     void *out_field, size_t field_picture_pitch, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Sub-pel refinement of one reference's motion field, in place, for `count` independent pictures
+ * (SURVEY.md 8f rank 3): schro_encoder_motion_predict_subpel_deep
+ * (schroedinger/schromotionest.c:246-355) for one value of `ref`.
+ *   orig        the source pictures (u8; the luma plane is used); orig_extension = that frame's
+ *               `extension`, which only enters the reference's probe range test (:306-312)
+ *   upref       the upsampled reference pictures (four half-pel phases, edge-extended by
+ *               upref_extension = 32 as schro_upsampled_frame_upsample leaves them)
+ *   field       device field (x_num_blocks*y_num_blocks SchroMotionVector per picture): on entry the
+ *               integer-pel vectors and metrics (the level-0 field of hierarchical block matching,
+ *               schroedinger/schroencoder.c:2306-2315), on return vectors in units of
+ *               2^-mv_precision pixels and the SADs of the probes that won
+ *   lambda      schro_me_lambda: score = entropy + lambda * SAD in double precision */
+typedef struct {
+  int xblen, yblen;                     /* params->xbsep_luma, ybsep_luma */
+  int x_num_blocks, y_num_blocks;       /* at most 1024 block rows */
+  int mv_precision;                     /* passes mvprec = 1 .. mv_precision */
+  int ref_index;
+  int orig_extension;
+  double lambda;
+} sb2_subpel_params;
+size_t sb2_subpel_workspace_bytes (int x_num_blocks, int y_num_blocks, int count);
+int sb2_subpel_refine (const sb2_subpel_params *params, const sb2_slab *orig, const sb2_slab *upref,
+    int upref_extension, void *field, size_t field_picture_pitch, void *workspace, size_t workspace_bytes,
+    void *stream);
+
 /* schro_metric_absdiff_u8 (schroedinger/schrometric.c:10-29) for `n` independent block
  * pairs: sad[i] = SAD(a + a_offset[i], b + b_offset[i]) over width x height. */
 int sb2_sad_u8 (const uint8_t *a, int a_stride, const uint8_t *b, int b_stride,

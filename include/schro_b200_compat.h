@@ -435,6 +435,18 @@ void schro_rough_me_heirarchical_scan_nohint (SchroRoughME *rme, int shift, int 
 void schro_rough_me_heirarchical_scan_hint (SchroRoughME *rme, int shift, int distance);
 
 
+/* ---- sub-pel refinement (schroedinger/schromotionest.c:246-355) ----
+ * schro_encoder_motion_predict_subpel_deep (SchroMe *) reads a structure private to schromotionest.c
+ * through five accessors; this is the same function with those five things passed explicitly
+ * (compat/schro_subpel_deep.c keeps the reference's symbol on top of it):
+ *   params             schro_me_params: xbsep_luma, ybsep_luma, x/y_num_blocks, num_refs, mv_precision
+ *   lambda             schro_me_lambda
+ *   orig_frame         schro_me_src: the (filtered) source picture, u8
+ *   upsampled_refs[r]  schro_me_ref (me, r): the upsampled reference pictures (upsampled here if not yet)
+ *   subpel_mfs[r]      schro_me_subpel_mf (me, r): refined in place */
+void schro_b200_motion_predict_subpel_deep (SchroParams *params, double lambda, SchroFrame *orig_frame,
+    SchroFrame **upsampled_refs, SchroMotionField **subpel_mfs);
+
 #ifdef __cplusplus
 }
 #endif

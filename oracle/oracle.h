@@ -145,6 +145,14 @@ void oracle_rough_scan_hint (const OraclePyrLevel *src, const OraclePyrLevel *re
     int x_num_blocks, int y_num_blocks, int ref_index, int shift, int distance,
     const OracleMotionVector *parent, OracleMotionVector *mf);
 
+/* Sub-pel refinement of one reference's motion field in place (oracle_subpel.c):
+ * schro_encoder_motion_predict_subpel_deep (schroedinger/schromotionest.c:246-355) for one reference.
+ * orig: luma pixel (0,0) of the source picture (frame extension orig_ext -- it only enters the range
+ * test); upref: phase-0 luma pixel (0,0) of the upsampled reference, rstride its 4-phase row stride. */
+void oracle_subpel_refine (const uint8_t *orig, int orig_stride, int width, int height, int orig_ext,
+    const uint8_t *upref, int rstride, int xblen, int yblen, int x_num_blocks, int y_num_blocks,
+    int mv_precision, int ref_index, double lambda, OracleMotionVector *mf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -422,6 +422,73 @@ ref_rough_run (const RefHbmParams *hp, int nohint_distance, int hint_distance, v
   free (enc);
 }
 
+/* ---- sub-pel refinement: schro_encoder_motion_predict_subpel_deep (schroedinger/schromotionest.c:246-355)
+ * through a SchroMe built by the reference's own schro_me_new (:2758-2774).  The reference pictures are
+ * edge-extended and upsampled by the reference; fields[r] (x_num_blocks*y_num_blocks vectors) are refined
+ * in place.  q: width, height, xbsep, ybsep, mv_precision, num_refs. */
+void
+ref_subpel_run (const int *q, double lambda, void **src, const int *src_stride, void **ref0, const int *ref0_stride,
+    void **ref1, const int *ref1_stride, SchroMotionVector *field0, SchroMotionVector *field1,
+    int *x_num_blocks, int *y_num_blocks)
+{
+  SchroEncoder *enc = calloc (1, sizeof (SchroEncoder));
+  SchroEncoderFrame *fs = calloc (1, sizeof (SchroEncoderFrame));
+  SchroEncoderFrame *fr[2];
+  SchroHierBm fake_hbm[2];
+  SchroVideoFormat vf;
+  SchroFrameFormat fmt;
+  SchroMe *me;
+  int r, n;
+  const int num_refs = q[5];
+
+  ref_init ();
+  memset (&vf, 0, sizeof (vf));
+  vf.width = q[0];
+  vf.height = q[1];
+  vf.chroma_format = SCHRO_CHROMA_420;
+  fmt = schro_params_get_frame_format (8, SCHRO_CHROMA_420);
+  fs->encoder = enc;
+  fs->params.video_format = &vf;
+  fs->params.xbsep_luma = q[2];
+  fs->params.ybsep_luma = q[3];
+  fs->params.xblen_luma = q[2];
+  fs->params.yblen_luma = q[3];
+  fs->params.num_refs = num_refs;
+  fs->params.mv_precision = q[4];
+  schro_params_calculate_mc_sizes (&fs->params);
+  fs->frame_me_lambda = lambda;
+  fs->filtered_frame = load_frame (fmt, q[0], q[1], src, src_stride);
+  memset (fake_hbm, 0, sizeof (fake_hbm));
+  for (r = 0; r < num_refs; r++) {
+    fr[r] = calloc (1, sizeof (SchroEncoderFrame));
+    fr[r]->upsampled_original_frame = load_frame (fmt, q[0], q[1], r ? ref1 : ref0, r ? ref1_stride : ref0_stride);
+    schro_upsampled_frame_upsample (fr[r]->upsampled_original_frame);
+    fs->ref_frame[r] = fr[r];
+    fake_hbm[r].ref_count = 2;          /* schro_me_new refs it, schro_me_free unrefs it: never freed */
+    fs->hier_bm[r] = &fake_hbm[r];
+  }
+  n = fs->params.x_num_blocks * fs->params.y_num_blocks;
+  *x_num_blocks = fs->params.x_num_blocks;
+  *y_num_blocks = fs->params.y_num_blocks;
+  me = schro_me_new (fs);
+  for (r = 0; r < num_refs; r++) {
+    SchroMotionField *mf = schro_motion_field_new (fs->params.x_num_blocks, fs->params.y_num_blocks);
+    memcpy (mf->motion_vectors, r ? field1 : field0, sizeof (SchroMotionVector) * n);
+    schro_me_set_subpel_mf (me, mf, r);
+  }
+  schro_encoder_motion_predict_subpel_deep (me);
+  for (r = 0; r < num_refs; r++)
+    memcpy (r ? field1 : field0, schro_me_subpel_mf (me, r)->motion_vectors, sizeof (SchroMotionVector) * n);
+  schro_me_free (me);                   /* frees the fields */
+  for (r = 0; r < num_refs; r++) {
+    schro_frame_unref (fr[r]->upsampled_original_frame);
+    free (fr[r]);
+  }
+  schro_frame_unref (fs->filtered_frame);
+  free (fs);
+  free (enc);
+}
+
 /* schro_metric_absdiff_u8 (schroedinger/schrometric.c:10) */
 /* schro_metric_scan_setup / _do_scan / _get_min and schro_metric_fast_block
  * (schroedinger/schrometric.c:31-214, 380-414) on two 4:2:0 u8 pictures loaded into frames with a

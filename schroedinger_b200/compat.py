@@ -195,6 +195,11 @@ _proto("schro_rough_me_heirarchical_scan", None, [ctypes.POINTER(SchroRoughME)])
 _proto("schro_rough_me_heirarchical_scan_nohint", None, [ctypes.POINTER(SchroRoughME), ctypes.c_int, ctypes.c_int])
 _proto("schro_rough_me_heirarchical_scan_hint", None, [ctypes.POINTER(SchroRoughME), ctypes.c_int, ctypes.c_int])
 
+_proto("schro_motion_field_new", ctypes.POINTER(SchroMotionField), [ctypes.c_int, ctypes.c_int])
+_proto("schro_motion_field_free", None, [ctypes.POINTER(SchroMotionField)])
+_proto("schro_b200_motion_predict_subpel_deep", None,
+       [ParamsP, ctypes.c_double, FrameP, ctypes.POINTER(FrameP), ctypes.POINTER(ctypes.POINTER(SchroMotionField))])
+
 _NP = {0x00: np.uint8, 0x04: np.int16, 0x08: np.int32}
 
 

@@ -427,3 +427,18 @@ def rough_scan(params, src_pyr, ref_pyr, nohint_distance=12, hint_distance=4, fi
         rough_scan_hint(params, src_pyr.slabs[l], ref_pyr.slabs[l], l, hint_distance, fields[l + 1], fields[l],
                         workspace, stream)
     return fields
+
+
+def subpel_refine(orig, upref, field, xblen, yblen, x_num_blocks, y_num_blocks, mv_precision, ref_index, lam,
+                  workspace=None, stream=None):
+    """schro_encoder_motion_predict_subpel_deep for one reference: `field` (uint8 CUDA tensor,
+    count x nblocks x 20 bytes) is refined in place."""
+    from ._lib import SubpelParams
+    require_cuda()
+    n = x_num_blocks * y_num_blocks
+    p = SubpelParams(xblen, yblen, x_num_blocks, y_num_blocks, mv_precision, ref_index, orig.layout.extension, lam)
+    ws = workspace or _default_ws
+    ptr, size = ws.get(lib.sb2_subpel_workspace_bytes(x_num_blocks, y_num_blocks, orig.count))
+    check(lib.sb2_subpel_refine(ctypes.byref(p), ctypes.byref(orig.slab), ctypes.byref(upref.slab),
+                                upref.layout.extension, ctypes.c_void_p(field.data_ptr()), ctypes.c_size_t(n),
+                                ptr, size, _stream_ptr(stream)), "sb2_subpel_refine")

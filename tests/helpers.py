@@ -460,6 +460,71 @@ def rough_inside_mask(width, height, xbsep, ybsep, nbx, nby, level):
     return m.reshape(-1)
 
 
+def subpel_case(oracle, width, height, rng, pans=((5, 3), (-4, 2)), levels=2, num_refs=2):
+    """A source picture, `num_refs` panned references and, per reference, the level-0 field of
+    hierarchical block matching (what schro_encoder's deep estimation hands to the sub-pel refinement,
+    schroedinger/schroencoder.c:2302-2320).  Returns (src_planes, [ref_planes], [field])."""
+    src, refs, fields = None, [], []
+    base_rng = np.random.default_rng(int(rng.integers(1 << 30)))
+    state = base_rng.bit_generator.state
+    for r in range(num_refs):
+        base_rng.bit_generator.state = state           # the same base picture for every reference
+        s, rf = panning_pair(width, height, base_rng, pans[r])
+        if src is None:
+            src = s
+        f, _, _ = oracle_hbm(oracle, src, rf, width, height, levels=levels, ref_index=r)
+        refs.append(rf)
+        fields.append(f[0].copy())
+    return src, refs, fields
+
+
+def _luma_up(oracle, plane_img):
+    pl = HostPlane(plane_img.shape[1], plane_img.shape[0], ext=32, upsampled=True)
+    pl.set_image(plane_img)
+    cpu_edgeextend(oracle, "oracle", pl)
+    cpu_upsample(oracle, "oracle", pl)
+    return pl
+
+
+def oracle_subpel(oracle, src, refs, fields, width, height, xblen=8, yblen=8, mv_precision=2, lam=0.1, orig_ext=32):
+    """schro_encoder_motion_predict_subpel_deep through the oracle; returns the refined fields."""
+    nbx, nby = hbm_block_counts(width, height, xblen, yblen)
+    fn = oracle.oracle_subpel_refine
+    fn.restype = None
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                   ctypes.c_void_p]
+    y = np.ascontiguousarray(src[0])
+    out = []
+    for r, rf in enumerate(refs):
+        up = _luma_up(oracle, rf[0])
+        f = fields[r].copy()
+        fn(y.ctypes.data, y.strides[0], width, height, orig_ext, up.buf.ctypes.data + up.origin, up.stride,
+           xblen, yblen, nbx, nby, mv_precision, r, lam, f.ctypes.data)
+        out.append(f)
+    return out
+
+
+def ref_subpel(ref, src, refs, fields, width, height, xblen=8, yblen=8, mv_precision=2, lam=0.1):
+    """The same through the compiled reference (a SchroMe built by its own schro_me_new)."""
+    nbx, nby = hbm_block_counts(width, height, xblen, yblen)
+    P = ctypes.c_void_p * 3
+    I = ctypes.c_int * 3
+    q = (ctypes.c_int * 6)(width, height, xblen, yblen, mv_precision, len(refs))
+    out = [f.copy() for f in fields]
+    nx, ny = ctypes.c_int(), ctypes.c_int()
+    fn = ref.ref_subpel_run
+    fn.restype = None
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_double] + [ctypes.c_void_p] * 10
+    r1 = refs[1] if len(refs) > 1 else refs[0]
+    fn(q, lam, P(*[a.ctypes.data for a in src]), I(*[a.strides[0] for a in src]),
+       P(*[a.ctypes.data for a in refs[0]]), I(*[a.strides[0] for a in refs[0]]),
+       P(*[a.ctypes.data for a in r1]), I(*[a.strides[0] for a in r1]),
+       out[0].ctypes.data, out[1].ctypes.data if len(out) > 1 else None, ctypes.byref(nx), ctypes.byref(ny))
+    assert (nx.value, ny.value) == (nbx, nby)
+    return out
+
+
 # ---- combine / convert glue (SURVEY.md 8f rank 2) --------------------------------------------
 DEPTH_DTYPE = {0: np.uint8, 1: np.int16, 2: np.int32}
 
