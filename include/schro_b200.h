@@ -104,6 +104,13 @@ int sb2_iwt_inverse (const sb2_slab *src, const sb2_slab *dst, int is_s32,
  * half-height multiples of 8 or 16) and by a generic tile kernel otherwise.  on != 0 sends every
  * component to the generic kernel (tests run both on the same input; also SB2_IWT_GENERIC=1). */
 void sb2_iwt_force_generic (int on);
+/* on != 0: the inverse transform runs its last two levels (1 and 0) as ONE fused launch -- level 1's
+ * output stays in shared memory, never in HBM -- for the filters DD 9/7, DD 13/7 and Daubechies 9/7 on
+ * planes the register-chunk kernels cover.  Off by default: measured on B200 the fused launch moves a
+ * quarter less DRAM traffic but takes 1.36 ms against 1.00 ms per 32 2160p pictures, because the halo of
+ * level 1 is recomputed per tile on an issue-bound kernel (tools/time_wavelet_fused.py).
+ * The environment variable SB2_IWT_FUSED=1 turns it on as well.  Results are identical either way. */
+void sb2_iwt_enable_fused (int on);
 
 /* ---- reference-frame preparation (u8) ------------------------------------ */
 

@@ -81,6 +81,7 @@ _opt("sb2_obmc_last_kernel", ctypes.c_int, [])
 _opt("sb2_hbm_workspace_bytes", ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int])
 _opt("sb2_hbm_force_generic", None, [ctypes.c_int])
 _opt("sb2_iwt_force_generic", None, [ctypes.c_int])
+_opt("sb2_iwt_enable_fused", None, [ctypes.c_int])
 _opt("sb2_upsample_force_kernel", None, [ctypes.c_int])
 _opt("sb2_upsample_last_kernel", ctypes.c_int, [])
 _opt("sb2_downsample_force_kernel", None, [ctypes.c_int])

@@ -646,6 +646,221 @@ wavelet_inv_fast_kernel (const LevelArgs a)
 }
 
 
+// ---- fused inverse kernel: levels 1 and 0 in one launch -------------------------------------
+// BASELINE.json's "multi-level fused tiles": the CTA of a level-0 output tile first computes the part
+// of level 1's output (= level 0's LL band) its tile needs -- the tile's LL window plus the filter's
+// halo -- into shared memory, then runs the level-0 tile exactly like wavelet_inv_fast_kernel with
+// the LL rows coming from there.  Level 1's dense plane is never written to or read from HBM (2/3 of
+// a plane per picture saved); the price is the halo: a 64 x 32 LL window needs 72 x 40 level-1
+// outputs (1.41 x level 1's arithmetic) and 88 x 56 level-1 inputs per band pair.
+// Stage 1 uses the same register-chunk lifting: two vertical chunks of C1 = 10 pair rows, then
+// NPX / CH1 horizontal chunks.  The window is clamped INTO the plane (not cut at its edge), so that a
+// chunk that reaches a picture edge ends exactly there -- what chunk_lift's edge extension assumes.
+struct FusedArgs {
+  LevelArgs l0;     // level 0: dense = output, bands = level-0 bands; l0.ll is unused
+  PlaneSet bands1;  // the coefficient plane at level 1's stride
+  PlaneSet ll1;     // level 1's LL input (w/4 x h/4)
+};
+
+template <typename T, int F, int CS> struct FusedGeom {
+  typedef FastGeom<T, F, CS> B;
+  static constexpr int HP = B::HP;
+  static constexpr int HPE = (HP + 1) & ~1;                   // even halo: the window starts on a level-1 pair
+  static constexpr int C1 = (THH + 2 * HPE) / 4;              // pair rows per vertical chunk (two chunks)
+  static constexpr int NPY = 2 * C1;                          // level-1 pair rows of the window
+  static constexpr int NPX = (TWH + 2 * B::HK) / 2;           // level-1 pair columns of the window
+  static constexpr int CH1 = NPX % 12 == 0 ? 12 : 10;         // horizontal chunk
+  static constexpr int NQ = NPX / CH1;
+  static constexpr int NC1 = NPX + 2 * HP;                    // columns per segment after the vertical pass
+  static constexpr int NV1 = C1 + 2 * HP;
+  static constexpr int NH1 = CH1 + 2 * HP;
+  static constexpr int ROWS = 2 * NPY;                        // level-1 output rows of the window
+  static constexpr int WPE = 4 / (int) sizeof (T);            // elements per 32-bit word
+  static constexpr int S1P = ((2 * NC1 + WPE - 1) / WPE | 1) * WPE;     // odd number of words: lanes = rows conflict-free
+  static constexpr int LLP = ((2 * NPX + WPE - 1) / WPE | 1) * WPE;
+  static constexpr int V1ITEMS = 2 * 2 * NC1;
+  static constexpr int H1ITEMS = ROWS * NQ;
+  static constexpr size_t LL_BYTES = ((size_t) ROWS * LLP * sizeof (T) + 15) / 16 * 16;
+  static constexpr size_t SMEM = B::SMEM + LL_BYTES;
+  static_assert ((THH + 2 * HPE) % 4 == 0 && NPX % CH1 == 0, "window does not split into chunks");
+  static_assert (V1ITEMS <= B::NT && H1ITEMS <= B::NT, "stage 1 needs more threads than the tile kernel has");
+  static_assert ((size_t) ROWS * S1P * sizeof (T) <= B::SMEM, "stage-1 buffer must fit the tile buffer it aliases");
+};
+
+template <typename T, int F, int CS>
+__global__ void __launch_bounds__ (FastGeom<T, F, CS>::NT)
+wavelet_inv_fused2_kernel (const FusedArgs fa)
+{
+  typedef FastGeom<T, F, CS> G;
+  typedef FusedGeom<T, F, CS> U;
+  extern __shared__ __align__ (16) unsigned char smem_raw[];
+  T *sm = reinterpret_cast<T *> (smem_raw);
+  T *lls = reinterpret_cast<T *> (smem_raw + G::SMEM);
+  const LevelArgs &a = fa.l0;
+
+  const TileId tile = level_tile (a);
+  const int comp = tile.comp, pic = blockIdx.y;
+  const int w = a.w[comp], h = a.h[comp];
+  const int n = w >> 1, m = h >> 1;
+  const int kx0 = tile.bx * TWH, ky0 = tile.by * THH;
+  if (kx0 >= n || ky0 >= m) return;
+  constexpr int SH = filter_shift (F);
+  const int tid = threadIdx.x;
+
+  // ---- stage 1: level 1's output rows [2 sy1, 2 sy1 + ROWS) x columns [2 sx1, 2 sx1 + 2 NPX) -> lls ----
+  const int n1 = n >> 1, m1 = m >> 1;
+  const int sx1 = max (0, min ((kx0 - G::HK) >> 1, n1 - U::NPX));
+  const int sy1 = max (0, min ((ky0 - U::HPE) >> 1, m1 - U::NPY));
+  {
+    const T *bands1 = reinterpret_cast<const T *> (plane_ptr (fa.bands1, pic, comp));
+    const T *ll1 = reinterpret_cast<const T *> (plane_ptr (fa.ll1, pic, comp));
+    const size_t bs1 = fa.bands1.stride[comp] / sizeof (T), ls1 = fa.ll1.stride[comp] / sizeof (T);
+    if (tid < U::V1ITEMS) {
+      const int chunk = tid / (2 * U::NC1), col = tid - chunk * (2 * U::NC1);
+      const int seg = col >= U::NC1, j = col - seg * U::NC1;
+      const int kx = sx1 - U::HP + j;
+      const int kyc = sy1 + chunk * U::C1;
+      if (kx >= 0 && kx < n1) {
+        int E[U::NV1], O[U::NV1];
+        const T *pe = seg ? bands1 + n1 + kx : ll1 + kx;
+        const size_t es = seg ? 2 * bs1 : ls1;
+        const T *po = bands1 + bs1 + seg * n1 + kx;
+        const bool lo = kyc == 0, hi = kyc + U::C1 >= m1;
+        if (!lo && !hi) {
+          pe += (size_t) (kyc - U::HP) * es;
+          po += (size_t) (kyc - U::HP) * 2 * bs1;
+#pragma unroll
+          for (int r = 0; r < U::NV1; r++) {
+            E[r] = pe[(size_t) r * es];
+            O[r] = po[(size_t) r * 2 * bs1];
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < U::NV1; r++) {
+            const int ky = kyc - U::HP + r;
+            const bool ok = ky >= 0 && ky < m1;
+            E[r] = ok ? (int) pe[(size_t) ky * es] : 0;
+            O[r] = ok ? (int) po[(size_t) ky * 2 * bs1] : 0;
+          }
+        }
+        chunk_lift<T, F, true, U::NV1, U::HP> (E, O, lo, hi);
+        T *out = sm + (size_t) (chunk * 2 * U::C1) * U::S1P + col;
+#pragma unroll
+        for (int r = 0; r < U::C1; r++) {
+          out[(size_t) (2 * r) * U::S1P] = (T) E[U::HP + r];
+          out[(size_t) (2 * r + 1) * U::S1P] = (T) O[U::HP + r];
+        }
+      }
+    }
+    __syncthreads ();
+    if (tid < U::H1ITEMS) {
+      const int q = tid / U::ROWS, row = tid - q * U::ROWS;     // lanes = rows
+      const int k0 = sx1 + q * U::CH1;
+      int E[U::NH1], O[U::NH1];
+      const T *rowp = sm + (size_t) row * U::S1P + q * U::CH1;
+#pragma unroll
+      for (int i = 0; i < U::NH1; i++) { E[i] = rowp[i]; O[i] = rowp[U::NC1 + i]; }
+      chunk_lift<T, F, true, U::NH1, U::HP> (E, O, k0 == 0, k0 + U::CH1 >= n1);
+      T *orow = lls + (size_t) row * U::LLP + 2 * q * U::CH1;
+#pragma unroll
+      for (int i = 0; i < U::CH1; i++) {
+        int e = E[U::HP + i], o = O[U::HP + i];
+        if (SH) { e = Ar<T>::add (e, 1) >> 1; o = Ar<T>::add (o, 1) >> 1; }
+        orow[2 * i] = (T) e;
+        orow[2 * i + 1] = (T) o;
+      }
+    }
+    __syncthreads ();
+  }
+
+  // ---- level 0, as wavelet_inv_fast_kernel, the LL rows read from lls ----
+  T *dense = reinterpret_cast<T *> (plane_ptr (a.dense, pic, comp));
+  const T *bands = reinterpret_cast<const T *> (plane_ptr (a.bands, pic, comp));
+  const size_t ds = a.dense.stride[comp] / sizeof (T);
+  const size_t bs = a.bands.stride[comp] / sizeof (T);
+  if (tid < G::VITEMS) {
+    const int chunk = tid / (2 * G::NKV), col = tid - chunk * (2 * G::NKV);
+    const int seg = col >= G::NKV, cseg = col - seg * G::NKV;
+    const int kx = kx0 - G::HK + cseg;
+    const int kyc = ky0 + chunk * G::C;
+    if (kx >= 0 && kx < n && kyc < m) {
+      int E[G::NV], O[G::NV];
+      const T *po = bands + bs + seg * n + kx;
+      const bool lo = kyc == 0, hi = kyc + G::C >= m;
+      if (seg) {
+        const T *pe = bands + n + kx;
+#pragma unroll
+        for (int r = 0; r < G::NV; r++) {
+          const int ky = kyc - G::HP + r;
+          const bool ok = ky >= 0 && ky < m;
+          E[r] = ok ? (int) pe[(size_t) ky * 2 * bs] : 0;
+          O[r] = ok ? (int) po[(size_t) ky * 2 * bs] : 0;
+        }
+      } else {
+        const T *pe = lls + (kx - 2 * sx1) - (ptrdiff_t) (2 * sy1) * U::LLP;
+#pragma unroll
+        for (int r = 0; r < G::NV; r++) {
+          const int ky = kyc - G::HP + r;
+          const bool ok = ky >= 0 && ky < m;
+          E[r] = ok ? (int) pe[(ptrdiff_t) ky * U::LLP] : 0;
+          O[r] = ok ? (int) po[(size_t) ky * 2 * bs] : 0;
+        }
+      }
+      chunk_lift<T, F, true, G::NV, G::HP> (E, O, lo, hi);
+      T *out = sm + (size_t) (chunk * 2 * G::C) * G::PITCH + col;
+#pragma unroll
+      for (int r = 0; r < G::C; r++) {
+        out[(size_t) (2 * r) * G::PITCH] = (T) E[G::HP + r];
+        out[(size_t) (2 * r + 1) * G::PITCH] = (T) O[G::HP + r];
+      }
+    }
+  }
+  __syncthreads ();
+
+  const int hw = tid >> 5, lane = tid & 31;
+  const int q = hw % (TWH / G::CH);
+  const int row = (hw / (TWH / G::CH)) * 32 + lane;
+  const int k0 = kx0 + q * G::CH;
+  const bool hact = tid < G::HITEMS && k0 < n && (2 * ky0 + row) < h;
+  int E[G::NH], O[G::NH];
+  if (hact) {
+    const T *rowp = sm + (size_t) row * G::PITCH + q * G::CH;
+#pragma unroll
+    for (int i = 0; i < G::NH; i += G::VEC) {
+      Vec16<T>::load (rowp + i, &E[i]);
+      Vec16<T>::load (rowp + G::NKV + i, &O[i]);
+    }
+    chunk_lift<T, F, true, G::NH, G::HK> (E, O, k0 == 0, k0 + G::CH >= n);
+  }
+  __syncthreads ();
+  if (hact) {
+    T *orow = sm + (size_t) row * G::PITCH + 2 * q * G::CH;
+    if (SH) {
+#pragma unroll
+      for (int i = 0; i < G::CH; i++) {
+        E[G::HK + i] = Ar<T>::add (E[G::HK + i], 1) >> 1;
+        O[G::HK + i] = Ar<T>::add (O[G::HK + i], 1) >> 1;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < G::CH; i += Vec16<T>::PAIRS)
+      Vec16<T>::store_pairs (orow + 2 * i, &E[G::HK + i], &O[G::HK + i]);
+  }
+  __syncthreads ();
+  {
+    const int tw = min (2 * TWH, w - 2 * kx0);
+    const int th = min (2 * THH, h - 2 * ky0);
+    const int vpr = tw / G::VEC;
+    const int total = th * vpr;
+    for (int i = tid; i < total; i += G::NT) {
+      const int r = i / vpr, x = i - r * vpr;
+      const int4 v = *reinterpret_cast<const int4 *> (sm + (size_t) r * G::PITCH + x * G::VEC);
+      *reinterpret_cast<int4 *> (dense + (size_t) (2 * ky0 + r) * ds + 2 * kx0 + x * G::VEC) = v;
+    }
+  }
+}
+
+
 // ---- fast forward kernel ---------------------------------------------------------------
 // Mirror image of the fast inverse kernel: the tile (with its halo) is copied in with
 // coalesced 128-bit loads, each thread lifts one row x one chunk of column pairs out of
@@ -817,6 +1032,71 @@ static int launch_fast_inverse (LevelArgs a, const int *comps, int nsel, int cou
   return check_cuda (cudaGetLastError (), "wavelet_inv_fast_kernel launch");
 }
 
+// 0: one launch per level (default -- measured faster), 1: levels 1 + 0 fused whenever the
+// shapes allow (sb2_iwt_enable_fused, or SB2_IWT_FUSED=1 in the environment)
+static int g_iwt_fused = -1;
+static bool iwt_fused_enabled ()
+{
+  if (g_iwt_fused < 0) {
+    const char *v = getenv ("SB2_IWT_FUSED");
+    g_iwt_fused = (v && atoi (v)) ? 1 : 0;
+  }
+  return g_iwt_fused != 0;
+}
+
+// can levels 1 + 0 of the inverse transform run fused for every component?  (a0 = level 0's arguments)
+template <typename T, int F>
+static bool fused2_supported (const LevelArgs &a0)
+{
+  if (!(F == 0 || F == 2 || F == 6)) return false;
+  if constexpr (F == 0 || F == 2 || F == 6) {
+    typedef FusedGeom<T, F, 16> U;
+    for (int c = 0; c < a0.ncomp; c++) {
+      if (fast_inverse_chunk<T, F> (a0, c) != 16) return false;
+      if ((a0.w[c] >> 2) < U::NPX || (a0.h[c] >> 2) < U::NPY || (a0.w[c] & 3) || (a0.h[c] & 3)) return false;
+    }
+    return true;
+  }
+  return false;
+}
+
+template <typename T, int F>
+static int launch_fused2 (const LevelArgs &a0, const PlaneSet &bands1, const PlaneSet &ll1, int count, cudaStream_t stream)
+{
+  if constexpr (F == 0 || F == 2 || F == 6) {
+    typedef FastGeom<T, F, 16> FG;
+    typedef FusedGeom<T, F, 16> U;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute (wavelet_inv_fused2_kernel<T, F, 16>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int) U::SMEM);
+      if (e != cudaSuccess) return check_cuda (e, "cudaFuncSetAttribute(wavelet fused)");
+      attr_set = true;
+    }
+    FusedArgs fa;
+    fa.l0 = a0;
+    fa.l0.ncomp_total = a0.ncomp;
+    fa.bands1 = bands1;
+    fa.ll1 = ll1;
+    int comps[SB2_MAX_COMPONENTS];
+    for (int c = 0; c < a0.ncomp; c++) comps[c] = c;
+    const dim3 grid = level_grid (fa.l0, comps, a0.ncomp, count);
+    char tag[48] = "";
+    double bytes = 0;
+    if (profiling ()) {
+      snprintf (tag, sizeof (tag), "wavelet_inv_%s_f%d_w%d_fused2", sizeof (T) == 4 ? "s32" : "s16", F, a0.w[0]);
+      // levels 1 and 0 together: every coefficient of the two levels read once, the picture written once
+      for (int c = 0; c < a0.ncomp; c++) bytes += 2.0 * a0.w[c] * a0.h[c] * sizeof (T) * count;
+    }
+    {
+      LaunchScope scope (tag, bytes, stream);
+      wavelet_inv_fused2_kernel<T, F, 16><<<grid, FG::NT, U::SMEM, stream>>> (fa);
+    }
+    return check_cuda (cudaGetLastError (), "wavelet_inv_fused2_kernel launch");
+  }
+  return set_error (SB2_ERR_UNSUPPORTED, "no fused kernel for filter %d", F);
+}
+
 template <typename T, int F, int CS>
 static int launch_fast_forward (LevelArgs a, const int *comps, int nsel, int count, cudaStream_t stream,
     const char *tag, double bytes)
@@ -922,6 +1202,26 @@ static int launch_level_any (bool inv, int is_s32, int filter, const LevelArgs &
                : launch_level_f<int32_t, false> (filter, a, count, s);
   return inv ? launch_level_f<int16_t, true> (filter, a, count, s)
              : launch_level_f<int16_t, false> (filter, a, count, s);
+}
+
+template <typename T>
+static bool fused2_supported_f (int filter, const LevelArgs &a0)
+{
+  switch (filter) {
+    case 0: return fused2_supported<T, 0> (a0);
+    case 2: return fused2_supported<T, 2> (a0);
+    case 6: return fused2_supported<T, 6> (a0);
+    default: return false;
+  }
+}
+template <typename T>
+static int launch_fused2_f (int filter, const LevelArgs &a0, const PlaneSet &bands1, const PlaneSet &ll1, int count, cudaStream_t s)
+{
+  switch (filter) {
+    case 0: return launch_fused2<T, 0> (a0, bands1, ll1, count, s);
+    case 2: return launch_fused2<T, 2> (a0, bands1, ll1, count, s);
+    default: return launch_fused2<T, 6> (a0, bands1, ll1, count, s);
+  }
 }
 
 // Workspace: per picture, per component: T1 (w/2 x h/2), T0 (w/4 x h/4) and, for
@@ -1091,12 +1391,32 @@ static int iwt_run (bool inv, const sb2_slab *src, const sb2_slab *dst, int is_s
   // inverse: level l = depth-1 .. 0
   //   LL <- (l==depth-1 ? src (stride<<(l+1)) : T[(l+1)&1]);  bands <- src (stride<<l);
   //   Y  -> (l==0 ? dst (or FULL when in place) : T[l&1])
-  for (int l = depth - 1; l >= 0; l--) {
+  // levels 1 and 0 run as one fused launch when every component's shape allows (level 1's output then
+  // never goes through HBM); the deeper levels, and everything else, run one launch per level
+  bool fused = false;
+  if (depth >= 2 && iwt_fused_enabled () && !iwt_generic_forced ()) {
+    for (int c = 0; c < src->ncomp; c++) { a.w[c] = src->width[c]; a.h[c] = src->height[c]; }
+    a.bands = S;
+    a.ll = T1;
+    a.dense = in_place ? FULL : D;
+    fused = is_s32 ? fused2_supported_f<int32_t> (filter, a) : fused2_supported_f<int16_t> (filter, a);
+  }
+  for (int l = depth - 1; l >= (fused ? 2 : 0); l--) {
     for (int c = 0; c < src->ncomp; c++) { a.w[c] = src->width[c] >> l; a.h[c] = src->height[c] >> l; }
     a.ll = (l == depth - 1) ? scaled (S, l + 1) : (((l + 1) & 1) ? T1 : T0);
     a.bands = scaled (S, l);
     a.dense = (l == 0) ? (in_place ? FULL : D) : ((l & 1) ? T1 : T0);
     rc = launch_level_any (true, is_s32, filter, a, src->count, st);
+    if (rc) return rc;
+  }
+  if (fused) {
+    for (int c = 0; c < src->ncomp; c++) { a.w[c] = src->width[c]; a.h[c] = src->height[c]; }
+    a.bands = S;
+    a.ll = T1;                                     // unused by the fused kernel
+    a.dense = in_place ? FULL : D;
+    const PlaneSet ll1 = depth == 2 ? scaled (S, 2) : T0;
+    rc = is_s32 ? launch_fused2_f<int32_t> (filter, a, scaled (S, 1), ll1, src->count, st)
+                : launch_fused2_f<int16_t> (filter, a, scaled (S, 1), ll1, src->count, st);
     if (rc) return rc;
   }
   if (in_place) return copy_back (dst, workspace, L, bpp, st);
@@ -1128,3 +1448,4 @@ sb2_iwt_inverse (const sb2_slab *src, const sb2_slab *dst, int is_s32, int filte
 }
 
 extern "C" void sb2_iwt_force_generic (int on) { sb2::g_iwt_generic = on ? 1 : 0; }
+extern "C" void sb2_iwt_enable_fused (int on) { sb2::g_iwt_fused = on ? 1 : 0; }

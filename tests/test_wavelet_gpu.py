@@ -147,3 +147,39 @@ def test_generic_kernel_forced_on_fast_path_shapes(cuda, filt, dtype):
                 assert np.array_equal(got[forced], want), (filt, dtype, (h, w), d, forced)
             assert all(t.endswith("_generic") for t in tags[1]) and tags[1]
             assert not any(t.endswith("_generic") for t in tags[0]) and tags[0]
+
+
+@pytest.mark.parametrize("dtype", [np.int16, np.int32])
+@pytest.mark.parametrize("filt", [0, 2, 6])
+def test_fused_last_two_levels(cuda, filt, dtype):
+    """Levels 1 + 0 of the inverse as one fused launch (wavelet_inv_fused2_kernel) against the oracle and
+    against the one-launch-per-level path on the same input: single-tile planes (both picture edges in
+    one window), partial tiles, many tiles, 4:2:0 frames, depths 2..4, in place, full-range values."""
+    from schroedinger_b200 import lib
+    from tests.test_hbm_gpu import launched_tags
+    rng = np.random.default_rng(700 + filt)
+    amp_full = 32767 if dtype == np.int16 else 2 ** 31 - 1
+    npx = 40 if dtype == np.int16 else 36                     # smallest plane: n/2 >= NPX, m/2 >= 20
+    w0 = (4 * npx + 31) // 32 * 32
+    shapes = [((96, w0), 2), ((128, w0 + 32), 2), ((160, 352), 3), ((288, 544), 2), ((544, 960), 4), ((1088, 1920), 3)]
+    for (h, w), depth in shapes:
+        for amp in (600, amp_full):
+            planes = [rng.integers(-amp, amp + 1, size=(h, w)).astype(dtype)]
+            if (h // 2) % (1 << depth) == 0 and (w // 2) % (1 << depth) == 0 and h >= 288:
+                planes += [rng.integers(-amp, amp + 1, size=(h // 2, w // 2)).astype(dtype) for _ in range(2)]
+            want = [helpers.cpu_wavelet(ORACLE, "oracle", "inv", p.copy(), filt, depth) for p in planes]
+            for fused in (1, 0):
+                lib.sb2_iwt_enable_fused(fused)
+                try:
+                    got = {}
+                    tags = launched_tags(lambda: got.__setitem__(0, gpu_iwt("inv", planes, filt, depth)))
+                    got_ip = gpu_iwt("inv", planes, filt, depth, in_place=True)
+                finally:
+                    lib.sb2_iwt_enable_fused(0)
+                for c in range(len(planes)):
+                    assert np.array_equal(got[0][c], want[c]), (filt, dtype, (h, w), depth, amp, fused, c)
+                    assert np.array_equal(got_ip[c], want[c]), (filt, dtype, (h, w), depth, amp, fused, c, "in place")
+                # the fused kernel needs every component to be eligible (chroma of the small frames is not)
+                eligible = all(p.shape[1] // 4 >= npx and p.shape[0] // 4 >= 20 and p.shape[1] % 32 == 0 and p.shape[0] % 32 == 0
+                               for p in planes)
+                assert any(t.endswith("_fused2") for t in tags) == bool(fused and eligible), (tags, fused, eligible, (h, w))
