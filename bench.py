@@ -625,6 +625,74 @@ def time_device_resident(torch, st, steps, warmup, barrier):
     return e0.elapsed_time(e1)
 
 
+# Measured on the pool's B200 by tools/vabsdiff_probe.cu (profiles/r02g_vabsdiff_probe.txt): the byte-SAD
+# instruction VABSDIFF4.U8.ACC issues at 64 lanes / clock / SM = 18.58 T lane-operations/s at 1965 MHz --
+# the roofline of the dependency-free full search (its DRAM traffic is negligible: 1 GB/s).
+VABSDIFF4_PEAK_TOPS = 18.58
+
+
+def next_rows(torch, dev, world, all_ranks, barrier):
+    """Device-resident timings of SURVEY.md 8f's rows 3 and 4 (sub-pel refinement, rough / bigblock
+    search), which sit beside the picture core rather than in its step: the encoder runs either the
+    hierarchical block matcher of the main step or the rough search (schromotionest.c:66-90)."""
+    out = {}
+
+    class OneStage:
+        def __init__(self, fn):
+            self.step = fn
+
+    def timed(fn, steps=10):
+        return all_ranks(time_device_resident(torch, OneStage(fn), steps, 3, barrier), "max") / steps
+
+    # ---- rough search: the full search on its own (every 8x8 block of 1080p pictures, +-12) and the chain
+    w, h, count = 1920, 1080, 32
+    rng = np.random.default_rng(99)
+    nbx, nby = block_counts(w, h)
+    ps, pr = dev.Pyramid(w, h, count, HBM_LEVELS), dev.Pyramid(w, h, count, HBM_LEVELS)
+    orig = ps.slabs[0]
+    up = dev.PictureSlab(dev.FrameLayout.yuv420("u8", w, h, 32, True), count)
+    for p in range(count):
+        ref = textured_frame(w, h, rng)
+        src = textured_frame(w, h, rng, picture_pan(p))
+        for c in range(3):
+            ps.slabs[0].upload(p, c, src[c])
+            pr.slabs[0].upload(p, c, ref[c])
+            up.upload(p, c, ref[c])
+    ps.build()
+    pr.build()
+    dev.edgeextend_upsample(up)
+    prm = dev.HbmParams(BLOCK["xbsep"], BLOCK["ybsep"], nbx, nby, 0, 0, 1, 1)
+    fld = torch.empty(count * nbx * nby * 20, dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: dev.rough_scan_nohint(prm, ps.slabs[0], pr.slabs[0], 0, 12, fld))
+    lane_ops = (w // 8) * (h // 8) * count * 625 * 16          # 8x8 block x 625 positions = 16 four-byte SADs each
+    tops = lane_ops / (ms * 1e-3) / 1e12
+    out["rough_full_search_1080p"] = {
+        "what": "schro_rough_me_heirarchical_scan_nohint on level 0: every 8x8 block of 1080p pictures, +-12 (625 positions)",
+        "batch_per_gpu": count, "value": round(count * world / (ms * 1e-3), 1), "unit": "frames/s",
+        "launch_ms": round(ms, 4),
+        "roofline": {"bound": "alu (VABSDIFF4.U8.ACC)", "achieved": round(tops, 2), "peak": VABSDIFF4_PEAK_TOPS,
+                     "unit": "T lane-ops/s", "frac": round(tops / VABSDIFF4_PEAK_TOPS, 4),
+                     "peak_source": "measured (tools/vabsdiff_probe.cu, profiles/r02g_vabsdiff_probe.txt)"}}
+    fields = dev.rough_scan(prm, ps, pr)
+    ms = timed(lambda: dev.rough_scan(prm, ps, pr, fields=fields))
+    out["rough_me_1080p"] = {
+        "what": "schro_rough_me_heirarchical_scan: full search +-12 at level 4, hint levels 3..1 (+-4)",
+        "batch_per_gpu": count, "value": round(count * world / (ms * 1e-3), 1), "unit": "frames/s", "ms_per_step": round(ms, 4)}
+    # ---- sub-pel refinement of the level-0 field of the block matcher, one reference, quarter-pel
+    hf = dev.hbm_scan(prm, ps, pr, 3)
+    f0 = hf[0].clone()
+    work = f0.clone()
+
+    def subpel():
+        work.copy_(f0)
+        dev.subpel_refine(orig, up, work, BLOCK["xbsep"], BLOCK["ybsep"], nbx, nby, 2, 0, 0.1)
+    ms = timed(subpel)
+    out["subpel_refine_1080p"] = {
+        "what": "schro_encoder_motion_predict_subpel_deep, one reference, mv_precision 2 (two passes of 8 probes per block)",
+        "batch_per_gpu": count, "value": round(count * world / (ms * 1e-3), 1), "unit": "frames/s", "ms_per_step": round(ms, 4)}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -759,6 +827,8 @@ def run_ours(args):
                            "value": round(ospec["batch"] * world * 20 / (ms * 1e-3), 1), "unit": "frames/s",
                            "alg_GBps": round(alg * 20 / (ms * 1e-3) / 1e9, 1)}
             del ost
+        torch.cuda.empty_cache()
+        other.update(next_rows(torch, dev, world, all_ranks, barrier))
 
     if rank != 0:
         if world > 1:

@@ -238,6 +238,9 @@ int sb2_hbm_scan_hint (const sb2_hbm_params *params, const sb2_slab *src_level,
  * A block that lies entirely outside its level's frame keeps the zero vector at a hint level (the
  * reference reads stale memory there, oracle/oracle_rough.c). */
 size_t sb2_rough_workspace_bytes (int x_num_blocks, int y_num_blocks, int count);
+/* the full search stages each block's reference window in shared memory; on != 0 makes it read every row
+ * segment from global memory instead (the path partial blocks and unaligned layouts take) -- tests run both */
+void sb2_rough_force_unstaged (int on);
 int sb2_rough_scan_nohint (const sb2_hbm_params *params, const sb2_slab *src_level,
     const sb2_slab *ref_level, int extension, int shift, int distance, void *out_field,
     size_t field_picture_pitch, void *stream);

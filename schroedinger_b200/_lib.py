@@ -89,6 +89,7 @@ _opt("sb2_downsample_last_kernel", ctypes.c_int, [])
 _opt("sb2_hbm_scan_hint", ctypes.c_int, [ctypes.c_void_p, _SP, _SP, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                         ctypes.c_size_t, ctypes.c_void_p])
+_opt("sb2_rough_force_unstaged", None, [ctypes.c_int])
 _opt("sb2_rough_workspace_bytes", ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int])
 _opt("sb2_rough_scan_nohint", ctypes.c_int, [ctypes.c_void_p, _SP, _SP, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p])

@@ -31,6 +31,7 @@ struct RoughArgs {
   int width, height, ext;           // luma size of this pyramid level, its edge extension
   int bw, bh, nbx, nby, ref_index, shift, distance;
   int rows, cols, count;
+  int staged;                       // full search: stage the window in shared memory (tests turn it off to run both paths)
 };
 
 struct RoughWin { int xmin, ymin, scan_w, scan_h; };
@@ -125,10 +126,83 @@ rough_scan_warp (const uint8_t *sblk, int ss, const uint8_t *rp, int rs, const R
   return warp_min64 (best);
 }
 
+// The same scan with the reference window staged in shared memory: lane = window ROW for the copy
+// (up to three aligned 16-byte pieces of its row, one memory round trip for the whole window), lane =
+// window COLUMN for the arithmetic, which then reads its 8-byte row segments from shared memory (lanes
+// read consecutive bytes: no bank conflicts).  For full 8 x 8 blocks and windows of at most 25 x 25
+// positions on 16-byte aligned rows; key = (SAD << 16 | a << 8 | b) fits 32 bits (SAD <= 16320).
+constexpr int RS_PITCH = 48;                              // bytes per staged row: 15 + 25 + 7 <= 48
+template <int MAXH>
+__device__ __forceinline__ unsigned
+rough_scan_warp_staged (const uint8_t *sblk, int ss, const uint8_t *rp, int rs, const RoughWin &wn, unsigned *buf, int lane)
+{
+  uint2 srow[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) srow[r] = __ldg (reinterpret_cast<const uint2 *> (sblk + (ptrdiff_t) r * ss));
+  const uint8_t *win = rp + (ptrdiff_t) wn.ymin * rs + wn.xmin;
+  const unsigned off = (unsigned) ((size_t) win & 15);
+  const int need = (int) off + wn.scan_w + 7;               // bytes of a staged row that are read below
+  if (lane < wn.scan_h + 7) {
+    const uint4 *g = reinterpret_cast<const uint4 *> (win - off + (ptrdiff_t) lane * rs);
+    uint4 *d = reinterpret_cast<uint4 *> (buf + lane * (RS_PITCH / 4));
+    const uint4 v0 = __ldg (g);
+    uint4 v1 = make_uint4 (0, 0, 0, 0), v2 = v1;
+    if (need > 16) v1 = __ldg (g + 1);
+    if (need > 32) v2 = __ldg (g + 2);
+    d[0] = v0; d[1] = v1; d[2] = v2;
+  }
+  __syncwarp ();
+  const int a = min (lane, wn.scan_w - 1);                  // idle lanes repeat the last column
+  const unsigned bo = off + (unsigned) a;
+  const unsigned *w = buf + (bo >> 2);
+  const unsigned sh = (bo & 3) * 8;
+  unsigned acc[MAXH];
+#pragma unroll
+  for (int j = 0; j < MAXH; j++) acc[j] = 0;
+  if (wn.scan_h == MAXH) {
+    // the interior block (the whole window fits the frame): straight-line code, no row guards
+#pragma unroll
+    for (int rho = 0; rho < MAXH + 7; rho++) {
+      const unsigned w0 = w[rho * (RS_PITCH / 4)], w1 = w[rho * (RS_PITCH / 4) + 1], w2 = w[rho * (RS_PITCH / 4) + 2];
+      const unsigned bx = __funnelshift_r (w0, w1, sh), by = __funnelshift_r (w1, w2, sh);
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const int j = rho - r;
+        if (j >= 0 && j < MAXH) acc[j] = sad_acc (srow[r].y, by, sad_acc (srow[r].x, bx, acc[j]));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int rho = 0; rho < MAXH + 7; rho++) {
+      if (rho < wn.scan_h + 7) {                            // warp-uniform: rows the window has
+        const unsigned w0 = w[rho * (RS_PITCH / 4)], w1 = w[rho * (RS_PITCH / 4) + 1], w2 = w[rho * (RS_PITCH / 4) + 2];
+        const unsigned bx = __funnelshift_r (w0, w1, sh), by = __funnelshift_r (w1, w2, sh);
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          const int j = rho - r;
+          if (j >= 0 && j < MAXH) acc[j] = sad_acc (srow[r].y, by, sad_acc (srow[r].x, bx, acc[j]));
+        }
+      }
+    }
+  }
+  unsigned best = 0xffffffffu;
+  if (lane < wn.scan_w) {
+    const unsigned low = (unsigned) a << 8;
+#pragma unroll
+    for (int j = 0; j < MAXH; j++) {
+      const unsigned key = acc[j] * 65536u + (low + (unsigned) j);
+      if (j < wn.scan_h) best = min (best, key);
+    }
+  }
+  __syncwarp ();
+  return __reduce_min_sync (0xffffffffu, best);
+}
+
 template <int MAXH>
 __global__ void __launch_bounds__ (128)
 rough_full_kernel (const RoughArgs A)
 {
+  __shared__ __align__ (16) unsigned stage[4][MAXH <= 25 ? 32 * RS_PITCH / 4 : 4];
   const int lane = threadIdx.x & 31;
   const long long g = (long long) blockIdx.x * 4 + (threadIdx.x >> 5);
   const int per_pic = A.rows * A.cols;
@@ -148,10 +222,19 @@ rough_full_kernel (const RoughArgs A)
   const uint8_t *rp = reinterpret_cast<const uint8_t *> (plane_ptr (A.ref, pic, 0));
   const int ss = A.src.stride[0], rs = A.ref.stride[0];
   const bool aligned = ((((size_t) sp | (size_t) ss | (size_t) x) & 7) == 0) && ((((size_t) rp | (size_t) rs) & 3) == 0);
-  const unsigned long long k = rough_scan_warp<MAXH> (sp + (ptrdiff_t) y * ss + x, ss, rp, rs, wn, bw, bh, aligned, lane);
+  int a, b;
+  unsigned metric;
+  if (MAXH <= 25 && aligned && A.staged && bw == 8 && bh == 8 && wn.scan_w <= 25 && wn.scan_h <= MAXH &&
+      ((((size_t) (rp - A.ext)) | (size_t) rs) & 15) == 0) {
+    const unsigned k = rough_scan_warp_staged<(MAXH <= 25 ? MAXH : 1)> (sp + (ptrdiff_t) y * ss + x, ss, rp, rs, wn,
+        stage[threadIdx.x >> 5], lane);
+    metric = k >> 16; a = (int) ((k >> 8) & 0xff); b = (int) (k & 0xff);
+  } else {
+    const unsigned long long k = rough_scan_warp<MAXH> (sp + (ptrdiff_t) y * ss + x, ss, rp, rs, wn, bw, bh, aligned, lane);
+    metric = (unsigned) (k >> 32); a = (int) ((k >> 8) & 0xffff); b = (int) (k & 0xff);
+  }
   if (lane == 0) {
-    const int a = (int) ((k >> 8) & 0xffff), b = (int) (k & 0xff);
-    o->metric = (uint32_t) (k >> 32);
+    o->metric = metric;
     o->v[A.ref_index] = (int16_t) ((wn.xmin + a - x) << A.shift);
     o->v[2 + A.ref_index] = (int16_t) ((wn.ymin + b - y) << A.shift);
   }
@@ -265,6 +348,10 @@ rough_hint_kernel (const RoughArgs A)
 
 using namespace sb2;
 
+// 1: the full search stages its windows in shared memory (default), 0: every row segment from global memory
+static int g_rough_staged = 1;
+extern "C" void sb2_rough_force_unstaged (int on) { g_rough_staged = on ? 0 : 1; }
+
 static size_t rough_words_bytes (size_t blocks) { return (blocks * sizeof (unsigned long long) + 255) & ~(size_t) 255; }
 
 extern "C" size_t
@@ -305,6 +392,7 @@ rough_args (RoughArgs &A, const char *who, const sb2_hbm_params *p, const sb2_sl
   A.rows = ceil_div (A.nby, 1 << shift);
   A.cols = ceil_div (A.nbx, 1 << shift);
   A.count = src_level->count;
+  A.staged = g_rough_staged;
   return SB2_OK;
 }
 

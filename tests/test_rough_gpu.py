@@ -15,6 +15,16 @@ ORACLE = helpers.load_oracle()
 GOLD = np.load(os.path.join(helpers.GOLDEN_DIR, "rough.npz"))
 
 
+@pytest.fixture(params=["staged", "unstaged"], autouse=True)
+def full_search_path(request):
+    """Every test runs twice: the full search with its windows staged in shared memory (default) and
+    with every row segment read from global memory (sb2_rough_force_unstaged)."""
+    from schroedinger_b200 import lib
+    lib.sb2_rough_force_unstaged(1 if request.param == "unstaged" else 0)
+    yield request.param
+    lib.sb2_rough_force_unstaged(0)
+
+
 def gpu_rough(pairs, width, height, levels, ref_index=0, xbsep=8, ybsep=8, dists=(12, 4)):
     from schroedinger_b200 import device as dev
     count = len(pairs)
