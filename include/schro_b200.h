@@ -326,6 +326,10 @@ int sb2_frame_convert (const sb2_slab *src, int src_depth, const sb2_slab *dst, 
     void *stream);
 int sb2_frame_add (const sb2_slab *dst, const sb2_slab *src, int src_depth, int subtract,
     void *stream);
+/* schro_frame_shift_left / schro_frame_shift_right (schroedinger/schroframe.c:1238-1291), in place:
+ * right == 0: x << shift with 16-bit wrap (s16 only); right != 0: (x + ((1 << shift) >> 1)) >> shift,
+ * the add wrapping at the sample width (depth 1: s16, 2: s32). */
+int sb2_frame_shift (const sb2_slab *frames, int depth, int shift, int right, void *stream);
 
 /* ------------------------------------------------------------------------
  * Dequantisation of a coefficient frame in place: what

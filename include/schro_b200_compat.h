@@ -299,6 +299,10 @@ void schro_frame_unref (SchroFrame *frame);
 SchroFrame *schro_frame_dup (SchroFrame *frame);
 SchroFrame *schro_frame_dup_extended (SchroFrame *frame, int extension);
 SchroFrame *schro_frame_dup_full (SchroFrame *frame, int extension, int is_upsampled);
+/* schroedinger/schroframe.h: in-place shifts (schroframe.c:1238-1291) and the frame checksum (:1817-1861) */
+void schro_frame_shift_left (SchroFrame *frame, int shift);
+void schro_frame_shift_right (SchroFrame *frame, int shift);
+void schro_frame_md5 (SchroFrame *frame, uint32_t *state);
 /* schroedinger/schrocuda.h:14-16 / schrogpuframe.h:14-15: move a frame between domains */
 void schro_frame_to_gpu (SchroFrame *dest, SchroFrame *src);
 void schro_gpuframe_to_cpu (SchroFrame *dest, SchroFrame *src);

@@ -574,6 +574,26 @@ ref_frame_add (void **dst, const int *dstride, int dwidth, int dheight,
   else schro_frame_add (&d, &s);
 }
 
+/* schro_frame_shift_left / _right (schroedinger/schroframe.c:1238-1291) and schro_frame_md5 (:1817-1861) */
+void
+ref_frame_shift (void **planes, const int *stride, int depth, int width, int height, int shift, int right)
+{
+  SchroFrame f;
+  ref_init ();
+  fake_frame3 (&f, fmt420 (depth), planes, stride, width, height, 0, 0);
+  if (right) schro_frame_shift_right (&f, shift);
+  else schro_frame_shift_left (&f, shift);
+}
+
+void
+ref_frame_md5 (void **planes, const int *stride, int depth, int width, int height, uint32_t *state)
+{
+  SchroFrame f;
+  ref_init ();
+  fake_frame3 (&f, fmt420 (depth), planes, stride, width, height, 0, 0);
+  schro_frame_md5 (&f, state);
+}
+
 /* ---- dequantisation: the reference's own subband geometry
  * (schro_subband_get_frame_data, schro_subband_get_position) and Orc kernels, driven codeblock by
  * codeblock the way schro_decoder_decode_subband does (schrodecoder.c:3559-3576, 3395-3448). */

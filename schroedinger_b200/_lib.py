@@ -60,6 +60,7 @@ _opt("sb2_upsample", ctypes.c_int, [_SP, ctypes.c_int, ctypes.c_void_p])
 _opt("sb2_downsample", ctypes.c_int, [_SP, _SP, ctypes.c_void_p])
 _opt("sb2_downsample_edgeextend", ctypes.c_int, [_SP, _SP, ctypes.c_int, ctypes.c_void_p])
 _opt("sb2_frame_convert", ctypes.c_int, [_SP, ctypes.c_int, _SP, ctypes.c_int, ctypes.c_void_p])
+_opt("sb2_frame_shift", ctypes.c_int, [_SP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p])
 _opt("sb2_frame_add", ctypes.c_int, [_SP, _SP, ctypes.c_int, ctypes.c_int, ctypes.c_void_p])
 
 

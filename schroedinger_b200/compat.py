@@ -195,6 +195,9 @@ _proto("schro_rough_me_heirarchical_scan", None, [ctypes.POINTER(SchroRoughME)])
 _proto("schro_rough_me_heirarchical_scan_nohint", None, [ctypes.POINTER(SchroRoughME), ctypes.c_int, ctypes.c_int])
 _proto("schro_rough_me_heirarchical_scan_hint", None, [ctypes.POINTER(SchroRoughME), ctypes.c_int, ctypes.c_int])
 
+_proto("schro_frame_shift_left", None, [FrameP, ctypes.c_int])
+_proto("schro_frame_shift_right", None, [FrameP, ctypes.c_int])
+_proto("schro_frame_md5", None, [FrameP, ctypes.POINTER(ctypes.c_uint32)])
 _proto("schro_motion_field_new", ctypes.POINTER(SchroMotionField), [ctypes.c_int, ctypes.c_int])
 _proto("schro_motion_field_free", None, [ctypes.POINTER(SchroMotionField)])
 _proto("schro_b200_motion_predict_subpel_deep", None,

@@ -177,7 +177,69 @@ static void launch_convert (const GlueArgs &a, const dim3 &grid, cudaStream_t st
 
 }  // namespace sb2
 
+namespace sb2 {
+// schro_frame_shift_left / _right (schroedinger/schroframe.c:1238-1291): in place, every sample of
+// every component.  left: shlw (16-bit wrap); right: addw / addl of (1 << shift) >> 1, then an
+// arithmetic shift (orc_lshift_s16_ip, orc_add_const_rshift_s16 / _s32, schroorc.orc:146-163, 207-218).
+struct ShiftArgs {
+  TileGrid tiles;
+  PlaneSet p;
+  int w[SB2_MAX_COMPONENTS], h[SB2_MAX_COMPONENTS];
+  int shift, right;
+};
+
+template <typename T>
+__global__ void __launch_bounds__ (256)
+shift_kernel (const ShiftArgs a)
+{
+  const TilePos t = tile_pos (a.tiles);
+  const int comp = t.comp, pic = blockIdx.y;
+  const int x0 = (t.bx * 256 + threadIdx.x) * 4, y = t.by;
+  if (x0 >= a.w[comp] || y >= a.h[comp]) return;
+  T *row = reinterpret_cast<T *> (plane_ptr (a.p, pic, comp) + (size_t) y * a.p.stride[comp]);
+  const int n = min (4, a.w[comp] - x0);
+  const int rnd = (1 << a.shift) >> 1;
+  for (int k = 0; k < n; k++) {
+    const int v = (int) row[x0 + k];
+    int r;
+    if (!a.right) r = (int) ((unsigned) v << a.shift);
+    else if (sizeof (T) == 2) r = (int) (short) (v + rnd) >> a.shift;
+    else r = (int) ((unsigned) v + (unsigned) rnd) >> a.shift;
+    row[x0 + k] = (T) r;
+  }
+}
+}  // namespace sb2
+
 using namespace sb2;
+
+extern "C" int
+sb2_frame_shift (const sb2_slab *frames, int depth, int shift, int right, void *stream)
+{
+  if (!frames || !frames->base || frames->ncomp < 1 || frames->ncomp > SB2_MAX_COMPONENTS || frames->count < 1 || frames->count > 65535)
+    return set_error (SB2_ERR_ARG, "sb2_frame_shift: bad slab");
+  if (depth < 1 || depth > 2 || shift < 0 || shift > (depth == 1 ? 15 : 31))
+    return set_error (SB2_ERR_ARG, "sb2_frame_shift: depth %d (1: s16, 2: s32) / shift %d", depth, shift);
+  if (!right && depth != 1)
+    return set_error (SB2_ERR_UNSUPPORTED, "sb2_frame_shift: the left shift is s16 only (as the reference, schroframe.c:1238)");
+  ShiftArgs a;
+  a.p = planeset_from_slab (frames);
+  a.shift = shift;
+  a.right = right;
+  double bytes = 0;
+  for (int c = 0; c < SB2_MAX_COMPONENTS; c++) {
+    a.w[c] = c < frames->ncomp ? frames->width[c] : 0;
+    a.h[c] = c < frames->ncomp ? frames->height[c] : 0;
+    bytes += 2.0 * a.w[c] * a.h[c] * (depth == 1 ? 2 : 4) * frames->count;
+  }
+  const dim3 grid = make_tile_grid (a.tiles, frames->ncomp, a.w, a.h, 4 * 256, 1, frames->count);
+  cudaStream_t st = as_stream (stream);
+  {
+    LaunchScope scope (right ? "frame_shift_right" : "frame_shift_left", bytes, st);
+    if (depth == 1) shift_kernel<int16_t><<<grid, 256, 0, st>>> (a);
+    else shift_kernel<int32_t><<<grid, 256, 0, st>>> (a);
+  }
+  return check_cuda (cudaGetLastError (), "shift_kernel launch");
+}
 
 extern "C" int
 sb2_frame_convert (const sb2_slab *src, int src_depth, const sb2_slab *dst, int dst_depth, void *stream)

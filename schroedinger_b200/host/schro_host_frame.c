@@ -259,6 +259,115 @@ schro_frame_subtract (SchroFrame *dest, SchroFrame *src)
   frame_add_sub (dest, src, 1, __func__);
 }
 
+/* schro_frame_shift_left / _right (schroedinger/schroframe.c:1238-1291) */
+static void
+frame_shift (SchroFrame *frame, int shift, int right, const char *who)
+{
+  Sb2hContext *cx = sb2h_context ();
+  Staged s;
+  const int d = depth_code (frame->format, who);
+  if (d == 0 || (!right && d != 1)) sb2h_fatal (who, "unimplemented format 0x%x", (unsigned) frame->format);
+  stage_in (cx, &s, frame, SB2H_BUF_IN, 1);
+  SB2H_CHECK (sb2_frame_shift (&s.slab, d, shift, right, cx->stream), "sb2_frame_shift");
+  stage_out (cx, &s);
+  {
+    Staged *st[1] = { &s };
+    stage_finish (cx, st, 1, 1u);
+  }
+}
+
+void
+schro_frame_shift_left (SchroFrame *frame, int shift)
+{
+  frame_shift (frame, shift, 0, __func__);
+}
+
+void
+schro_frame_shift_right (SchroFrame *frame, int shift)
+{
+  frame_shift (frame, shift, 1, __func__);
+}
+
+/* schro_frame_md5 (schroedinger/schroframe.c:1817-1861): the MD5 block function (RFC 1321) chained
+ * over every row of every component in 64-byte blocks, a row's tail zero-padded to a block; no length
+ * padding, the four state words are the result.  The hash is a serial chain: frames on the device are
+ * brought to the host and hashed there. */
+static void
+md5_block (uint32_t *st, const uint8_t *p)
+{
+  static const uint8_t rot[64] = { 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 5, 9, 14, 20, 5, 9, 14, 20, 5, 9,
+    14, 20, 5, 9, 14, 20, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15,
+    21, 6, 10, 15, 21 };
+  static uint32_t K[64];
+  static int have_k = 0;
+  uint32_t m[16], a = st[0], b = st[1], c = st[2], d = st[3];
+  int i;
+  if (!have_k) {
+    /* floor (2^32 * |sin (i + 1)|), RFC 1321 3.4 -- integers, computed once with a table-free recurrence
+     * would need libm; the constants are public and fixed, so they are listed */
+    static const uint32_t k[64] = {
+      0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501,
+      0x698098d8, 0x8b44f7af, 0xffff5bb1, 0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821,
+      0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453, 0xd8a1e681, 0xe7d3fbc8,
+      0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a,
+      0xfffa3942, 0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70,
+      0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05, 0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665,
+      0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d, 0x85845dd1,
+      0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391 };
+    memcpy (K, k, sizeof (K));
+    have_k = 1;
+  }
+  for (i = 0; i < 16; i++)
+    m[i] = (uint32_t) p[4 * i] | ((uint32_t) p[4 * i + 1] << 8) | ((uint32_t) p[4 * i + 2] << 16) | ((uint32_t) p[4 * i + 3] << 24);
+  for (i = 0; i < 64; i++) {
+    uint32_t f, t;
+    int g;
+    if (i < 16) { f = (b & c) | (~b & d); g = i; }
+    else if (i < 32) { f = (d & b) | (~d & c); g = (5 * i + 1) & 15; }
+    else if (i < 48) { f = b ^ c ^ d; g = (3 * i + 5) & 15; }
+    else { f = c ^ (b | ~d); g = (7 * i) & 15; }
+    t = a + f + K[i] + m[g];
+    a = d; d = c; c = b;
+    b = b + ((t << rot[i]) | (t >> (32 - rot[i])));
+  }
+  st[0] += a; st[1] += b; st[2] += c; st[3] += d;
+}
+
+void
+schro_frame_md5 (SchroFrame *frame, uint32_t *state)
+{
+  Sb2hContext *cx = sb2h_context ();
+  const size_t bytes = frame_region_bytes (frame);
+  uint8_t *host = frame->regions[0], *tmp = NULL;
+  int k, y, x;
+  if (sb2h_mem_kind (frame->regions[0]) == SB2H_MEM_DEVICE) {
+    sb2h_frame_use (cx, frame->regions[0]);
+    tmp = sb2h_pinned_pool_alloc (bytes);
+    SB2H_CUDA (cudaMemcpyAsync (tmp, frame->regions[0], bytes, cudaMemcpyDefault, cx->stream));
+    sb2h_sync (cx);
+    host = tmp;
+  }
+  state[0] = 0x67452301;
+  state[1] = 0xefcdab89;
+  state[2] = 0x98badcfe;
+  state[3] = 0x10325476;
+  for (k = 0; k < 3; k++) {
+    const SchroFrameData *c = &frame->components[k];
+    /* the reference walks `width` BYTES of every line whatever the sample size (schroframe.c:1833-1846) */
+    for (y = 0; y < c->height; y++) {
+      const uint8_t *line = host + ((const uint8_t *) c->data - (const uint8_t *) frame->regions[0]) + (size_t) c->stride * y;
+      for (x = 0; x + 63 < c->width; x += 64) md5_block (state, line + x);
+      if (x < c->width) {
+        uint8_t pad[64];
+        memcpy (pad, line + x, (size_t) (c->width - x));
+        memset (pad + (c->width - x), 0, (size_t) (64 - (c->width - x)));
+        md5_block (state, pad);
+      }
+    }
+  }
+  if (tmp) sb2h_pinned_pool_free (tmp);
+}
+
 /* ---- OBMC ------------------------------------------------------------------ */
 SchroMotion *
 schro_motion_new (SchroParams *params, SchroFrame *ref1, SchroFrame *ref2)

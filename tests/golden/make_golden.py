@@ -123,6 +123,37 @@ def rough_golden(ref):
     print("rough.npz:", len(out), "arrays")
 
 
+SHIFT_MD5_CASES = [(1, 70, 46, 3), (1, 128, 64, 1), (2, 70, 46, 5), (2, 200, 120, 2), (0, 200, 120, 0), (0, 64, 32, 0), (1, 66, 30, 7)]
+
+
+def shift_md5_inputs(idx, depth, w, h):
+    rng = np.random.default_rng(7000 + idx)
+    return helpers.random_planes(rng, depth, w, h, True)
+
+
+def shift_md5_golden(ref):
+    """schro_frame_shift_left / _right and schro_frame_md5 of the compiled reference (4:2:0 frames)"""
+    import ctypes
+    out = {}
+    P, I = ctypes.c_void_p * 3, ctypes.c_int * 3
+    for idx, (depth, w, h, shift) in enumerate(SHIFT_MD5_CASES):
+        planes = shift_md5_inputs(idx, depth, w, h)
+        state = (ctypes.c_uint32 * 4)()
+        ref.ref_frame_md5(P(*[a.ctypes.data for a in planes]), I(*[a.strides[0] for a in planes]), depth, w, h, state)
+        out[f"m{idx}_md5"] = np.array(list(state), np.uint32)
+        if depth == 0:
+            continue
+        for right in (0, 1):
+            if not right and depth != 1:
+                continue
+            q = [a.copy() for a in planes]
+            ref.ref_frame_shift(P(*[a.ctypes.data for a in q]), I(*[a.strides[0] for a in q]), depth, w, h, shift, right)
+            for c in range(3):
+                out[f"s{idx}_{right}_{c}"] = q[c]
+    np.savez_compressed(os.path.join(helpers.GOLDEN_DIR, "shift_md5.npz"), **out)
+    print("shift_md5.npz:", len(out), "arrays")
+
+
 def glue_golden(ref):
     """schro_frame_convert / schro_frame_add / schro_frame_subtract of the compiled reference."""
     rng = np.random.default_rng(20261019)
@@ -197,7 +228,7 @@ def main():
     if ref is None:
         raise SystemExit("oracle/_ref/libschro_ref.so missing: run `make ref` where /root/reference exists")
     wavelet_golden(ref)
-    for name in ("frame_golden", "motion_golden", "hbm_golden", "rough_golden", "glue_golden", "dequant_golden", "metric_scan_golden"):
+    for name in ("frame_golden", "motion_golden", "hbm_golden", "rough_golden", "shift_md5_golden", "glue_golden", "dequant_golden", "metric_scan_golden"):
         fn = globals().get(name)
         if fn:
             fn(ref)
