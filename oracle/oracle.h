@@ -153,6 +153,16 @@ void oracle_subpel_refine (const uint8_t *orig, int orig_stride, int width, int 
     const uint8_t *upref, int rstride, int xblen, int yblen, int x_num_blocks, int y_num_blocks,
     int mv_precision, int ref_index, double lambda, OracleMotionVector *mf);
 
+/* The low-delay slice decoder (oracle_lowdelay.c): schro_decoder_decode_lowdelay_transform_data
+ * (schroedinger/schrolowdelay.c:99-761) + DC prediction (schroedinger/schrodecoder.c:3219-3277) for one picture.
+ * data: the picture's slices back to back; planes / strides (in SAMPLES) / widths / heights: the three
+ * coefficient planes (in-place subband layout); quant_matrix[1 + 3 * depth]; the reference's quantiser
+ * tables (61 entries).  orc16 != 0: the s16 "fast" path's 16-bit dequantiser (and its length-field width). */
+void oracle_lowdelay_decode (const uint8_t *data, int data_bytes, int slice_bytes_num, int slice_bytes_denom, int n_horiz_slices,
+    int n_vert_slices, int transform_depth, const int *quant_matrix, const uint32_t *table_quant,
+    const uint32_t *table_offset, void **planes, const int *strides, const int *widths, const int *heights,
+    int is_s32, int orc16);
+
 #ifdef __cplusplus
 }
 #endif

@@ -594,6 +594,46 @@ ref_frame_md5 (void **planes, const int *stride, int depth, int width, int heigh
   schro_frame_md5 (&f, state);
 }
 
+/* ---- low-delay slice decoder: schro_decoder_decode_lowdelay_transform_data (schroedinger/schrolowdelay.c:745-761)
+ * on a SchroPicture that carries what the function reads: params, lowdelay_buffer, transform_frame.
+ * q: luma width, luma height (iwt sizes; chroma = half), transform_depth, n_horiz_slices, n_vert_slices,
+ * slice_bytes_num, slice_bytes_denom, is_s32, path (0: the dispatcher, 1: force _slow, 2: force _fast). */
+#include <schroedinger/schrodecoder.h>
+void schro_decoder_decode_lowdelay_transform_data_slow (SchroPicture * picture);
+void schro_decoder_decode_lowdelay_transform_data_fast (SchroPicture * picture);
+void
+ref_lowdelay_decode (const int *q, const int *quant_matrix, const uint8_t *data, int data_bytes, void **planes,
+    const int *strides)
+{
+  SchroPicture *pic = calloc (1, sizeof (SchroPicture));
+  SchroBuffer buf;
+  SchroFrame f;
+  int i;
+  ref_init ();
+  memset (&buf, 0, sizeof (buf));
+  buf.data = (unsigned char *) data;
+  buf.length = (unsigned) data_bytes;
+  buf.ref_count = 1;
+  fake_frame3 (&f, q[7] ? SCHRO_FRAME_FORMAT_S32_420 : SCHRO_FRAME_FORMAT_S16_420, planes, strides, q[0], q[1], 0, 0);
+  pic->params.transform_depth = q[2];
+  pic->params.iwt_luma_width = q[0];
+  pic->params.iwt_luma_height = q[1];
+  pic->params.iwt_chroma_width = q[0] / 2;
+  pic->params.iwt_chroma_height = q[1] / 2;
+  pic->params.n_horiz_slices = q[3];
+  pic->params.n_vert_slices = q[4];
+  pic->params.slice_bytes_num = q[5];
+  pic->params.slice_bytes_denom = q[6];
+  pic->params.is_lowdelay = TRUE;
+  for (i = 0; i < 1 + 3 * q[2]; i++) pic->params.quant_matrix[i] = quant_matrix[i];
+  pic->lowdelay_buffer = &buf;
+  pic->transform_frame = &f;
+  if (q[8] == 1) schro_decoder_decode_lowdelay_transform_data_slow (pic);
+  else if (q[8] == 2) schro_decoder_decode_lowdelay_transform_data_fast (pic);
+  else schro_decoder_decode_lowdelay_transform_data (pic);
+  free (pic);
+}
+
 /* ---- dequantisation: the reference's own subband geometry
  * (schro_subband_get_frame_data, schro_subband_get_position) and Orc kernels, driven codeblock by
  * codeblock the way schro_decoder_decode_subband does (schrodecoder.c:3559-3576, 3395-3448). */

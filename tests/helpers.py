@@ -525,6 +525,126 @@ def ref_subpel(ref, src, refs, fields, width, height, xblen=8, yblen=8, mv_preci
     return out
 
 
+# ---- low-delay slices (schroedinger/schrolowdelay.c) -----------------------------------------------
+class BitWriter:
+    def __init__(self):
+        self.bits = []
+
+    def put(self, value, n):
+        self.bits += [(value >> (n - 1 - i)) & 1 for i in range(n)]
+
+    def sint(self, v):
+        """interleaved exp-Golomb, schro_pack_encode_sint (schroedinger/schropack.c:149-180)"""
+        a = abs(int(v)) + 1
+        n = a.bit_length()
+        for i in range(n - 1):
+            self.bits += [0, (a >> (n - 2 - i)) & 1]
+        self.bits.append(1)
+        if v:
+            self.bits.append(1 if v < 0 else 0)
+
+
+def ilog2up(x):
+    return int(x).bit_length()
+
+
+def lowdelay_slice_sizes(num, denom, nh, nv):
+    n_bytes, rem = num // denom, num % denom
+    acc, sizes = 0, []
+    for _ in range(nh * nv):
+        acc += rem
+        extra = 0
+        if acc >= denom:
+            extra, acc = 1, acc - denom
+        sizes.append(n_bytes + extra)
+    return sizes
+
+
+def lowdelay_band_blocks(width, height, depth, nh, nv, sx, sy):
+    """(row slice, column slice) of every subband's codeblock of slice (sx, sy) inside a width x height
+    coefficient plane in the in-place layout (schro_subband_get_frame_data + schro_frame_data_get_codeblock)."""
+    out = []
+    for index in range(1 + 3 * depth):
+        level = 0 if index == 0 else (index - 1) // 3
+        orient = 0 if index == 0 else (index - 1) % 3 + 1
+        shift = depth - level
+        bw, bh = width >> shift, height >> shift
+        step = 1 << shift
+        x0, x1 = bw * sx // nh, bw * (sx + 1) // nh
+        y0, y1 = bh * sy // nv, bh * (sy + 1) // nv
+        ry = [y * step + (step >> 1 if orient & 2 else 0) for y in range(y0, y1)]
+        cx = [x + (bw if orient & 1 else 0) for x in range(x0, x1)]
+        out.append((ry, cx))
+    return out
+
+
+def lowdelay_encode(quantised, depth, nh, nv, num, denom, rng, base_indices=None, truncate=0.0, fast_lengths=False):
+    """Packs quantised coefficient planes (three 2-D int arrays, in-place subband layout) into low-delay
+    slices.  Coefficients that do not fit a slice are dropped from the end (the decoder then reads 1 bits =
+    zeros / negative signs, schrounpack.c:96-103); `truncate` > 0 cuts the declared luma length of that
+    fraction of the slices short on purpose.  Returns (bytes, base_index per slice)."""
+    sizes = lowdelay_slice_sizes(num, denom, nh, nv)
+    n_bytes = num // denom
+    out = bytearray()
+    bases = []
+    k = 0
+    for sy in range(nv):
+        for sx in range(nh):
+            nbytes = sizes[k]
+            total = 8 * nbytes
+            base = int(base_indices[k]) if base_indices is not None else int(rng.integers(0, 60))    # the fast path has tables for base < 60 only (schrolowdelay.c:473)
+            bases.append(base)
+            lb = ilog2up(8 * (n_bytes if fast_lengths else nbytes))
+            yw, uw = BitWriter(), BitWriter()
+            for (ry, cx) in lowdelay_band_blocks(quantised[0].shape[1], quantised[0].shape[0], depth, nh, nv, sx, sy):
+                for y in ry:
+                    for x in cx:
+                        yw.sint(quantised[0][y, x])
+            for (ry, cx) in lowdelay_band_blocks(quantised[1].shape[1], quantised[1].shape[0], depth, nh, nv, sx, sy):
+                for y in ry:
+                    for x in cx:
+                        uw.sint(quantised[1][y, x])
+                        uw.sint(quantised[2][y, x])
+            room = total - 7 - lb
+            ylen = min(len(yw.bits), room, (1 << lb) - 1)
+            if truncate and rng.random() < truncate:
+                ylen = int(rng.integers(0, ylen + 1))
+            w = BitWriter()
+            w.put(base, 7)
+            w.put(ylen, lb)
+            w.bits += yw.bits[:ylen]
+            w.bits += uw.bits[:max(0, room - ylen)]
+            w.bits += [int(b) for b in rng.integers(0, 2, size=max(0, total - len(w.bits)))]     # junk padding
+            bits = np.array(w.bits[:total], dtype=np.uint8)
+            out += np.packbits(bits).tobytes()
+            k += 1
+    return bytes(out), bases
+
+
+def cpu_lowdelay(lib, prefix, data, width, height, depth, nh, nv, num, denom, quant_matrix, is_s32, path=0, tables=None):
+    """Decode through the oracle (prefix "oracle"; path != 0 selects the 16-bit dequantiser of the s16 fast
+    path) or the compiled reference (prefix "ref"; path 0 dispatcher, 1 _slow, 2 _fast).  Returns three planes."""
+    dt = np.int32 if is_s32 else np.int16
+    planes = [np.full((height, width), -1, dt), np.full((height // 2, width // 2), -1, dt), np.full((height // 2, width // 2), -1, dt)]
+    P = ctypes.c_void_p * 3
+    I = ctypes.c_int * 3
+    qm = (ctypes.c_int * len(quant_matrix))(*quant_matrix)
+    buf = (ctypes.c_uint8 * (len(data) + 8)).from_buffer_copy(data + b"\0" * 8)
+    if prefix == "ref":
+        q = (ctypes.c_int * 9)(width, height, depth, nh, nv, num, denom, int(is_s32), path)
+        fn = lib.ref_lowdelay_decode
+        fn.restype = None
+        fn(q, qm, buf, len(data), P(*[a.ctypes.data for a in planes]), I(*[a.strides[0] for a in planes]))
+    else:
+        tq, to, _ = tables
+        fn = lib.oracle_lowdelay_decode
+        fn.restype = None
+        fn(buf, len(data), num, denom, nh, nv, depth, qm, tq.ctypes.data_as(ctypes.c_void_p), to.ctypes.data_as(ctypes.c_void_p),
+           P(*[a.ctypes.data for a in planes]), I(*[a.strides[0] // a.itemsize for a in planes]),
+           I(width, width // 2, width // 2), I(height, height // 2, height // 2), int(is_s32), int(path))
+    return planes
+
+
 # ---- combine / convert glue (SURVEY.md 8f rank 2) --------------------------------------------
 DEPTH_DTYPE = {0: np.uint8, 1: np.int16, 2: np.int32}
 

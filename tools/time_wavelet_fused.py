@@ -50,6 +50,10 @@ def run(name, depth_name, filt, depth, w, h, count, iters=20):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "only-d2":
+        # under ncu: one configuration, few iterations (every launch is replayed)
+        run("Daub 9/7 s32 2160p d2", "s32", 6, 2, 3840, 2176, 32, iters=2)
+        sys.exit(0)
     run("Daub 9/7 s32 2160p d5", "s32", 6, 5, 3840, 2176, 32)
     run("Daub 9/7 s32 2160p d2", "s32", 6, 2, 3840, 2176, 32)
     run("DD 9/7 s16 1080p d4", "s16", 0, 4, 1920, 1088, 64)
