@@ -360,6 +360,27 @@ int sb2_dequantise (const sb2_slab *coeffs, int is_s32, const sb2_dequant_params
 int sb2_dequantise_widen (const sb2_slab *quantised_s16, const sb2_slab *coeffs_s32,
     const sb2_dequant_params *p, const int32_t *quant, size_t quant_picture_pitch, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Low-delay slice decoder (second half): schro_decoder_decode_lowdelay_transform_data
+ * (schroedinger/schrolowdelay.c:99-761) + DC prediction of the LL band (schroedinger/schrodecoder.c:3219-3277)
+ * for `count` pictures: the compressed slices go in, dequantised coefficients in the in-place subband
+ * layout come out (then sb2_iwt_inverse).  One thread per slice.
+ *   slices          device: per picture the slices back to back (SchroPicture.lowdelay_buffer->data),
+ *                   pictures `picture_pitch` bytes apart, `picture_bytes` valid bytes each
+ *   coeffs          three-component coefficient frames (s16, or s32 with is_s32), sizes = the iwt sizes
+ *   table_quant / table_offset   the reference's schro_table_quant / schro_table_offset_1_2 (61 entries)
+ * Which dequantiser runs follows the reference's dispatcher (:745-761): the 16-bit Orc program for s16
+ * frames whose chroma LL band divides by the slice grid, the plain-C one otherwise. */
+typedef struct {
+  int transform_depth;
+  int n_horiz_slices, n_vert_slices;
+  int slice_bytes_num, slice_bytes_denom;
+  int quant_matrix[1 + 3 * SB2_DEQUANT_MAX_LEVELS];
+  uint32_t table_quant[61], table_offset[61];
+} sb2_lowdelay_params;
+int sb2_lowdelay_decode (const sb2_lowdelay_params *params, const uint8_t *slices, size_t picture_bytes,
+    size_t picture_pitch, const sb2_slab *coeffs, int is_s32, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,17 @@ _opt("sb2_dequantise", ctypes.c_int, [_SP, ctypes.c_int, ctypes.POINTER(DequantP
                                       ctypes.c_size_t, ctypes.c_void_p])
 _opt("sb2_dequantise_widen", ctypes.c_int, [_SP, _SP, ctypes.POINTER(DequantParams), ctypes.c_void_p,
                                             ctypes.c_size_t, ctypes.c_void_p])
+
+
+class LowdelayParams(ctypes.Structure):
+    """Mirror of sb2_lowdelay_params."""
+    _fields_ = [("transform_depth", ctypes.c_int), ("n_horiz_slices", ctypes.c_int), ("n_vert_slices", ctypes.c_int),
+                ("slice_bytes_num", ctypes.c_int), ("slice_bytes_denom", ctypes.c_int), ("quant_matrix", ctypes.c_int * 19),
+                ("table_quant", ctypes.c_uint32 * 61), ("table_offset", ctypes.c_uint32 * 61)]
+
+
+_opt("sb2_lowdelay_decode", ctypes.c_int, [ctypes.POINTER(LowdelayParams), ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                          _SP, ctypes.c_int, ctypes.c_void_p])
 _opt("sb2_edgeextend_upsample", ctypes.c_int, [_SP, ctypes.c_int, ctypes.c_void_p])
 _opt("sb2_obmc_render", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, _SP, _SP, _SP,
                                       _SP, ctypes.c_int, ctypes.c_int, _SP, ctypes.c_void_p])

@@ -442,3 +442,23 @@ def subpel_refine(orig, upref, field, xblen, yblen, x_num_blocks, y_num_blocks, 
     check(lib.sb2_subpel_refine(ctypes.byref(p), ctypes.byref(orig.slab), ctypes.byref(upref.slab),
                                 upref.layout.extension, ctypes.c_void_p(field.data_ptr()), ctypes.c_size_t(n),
                                 ptr, size, _stream_ptr(stream)), "sb2_subpel_refine")
+
+
+def lowdelay_decode(slices, picture_bytes, coeffs, depth, n_horiz_slices, n_vert_slices, slice_bytes_num,
+                    slice_bytes_denom, quant_matrix, table_quant, table_offset, picture_pitch=None, stream=None):
+    """schro_decoder_decode_lowdelay_transform_data + DC prediction for every picture of `coeffs`;
+    slices: uint8 CUDA tensor holding the pictures' slice buffers `picture_pitch` bytes apart."""
+    from ._lib import LowdelayParams
+    require_cuda()
+    p = LowdelayParams()
+    p.transform_depth, p.n_horiz_slices, p.n_vert_slices = depth, n_horiz_slices, n_vert_slices
+    p.slice_bytes_num, p.slice_bytes_denom = slice_bytes_num, slice_bytes_denom
+    for i, v in enumerate(quant_matrix):
+        p.quant_matrix[i] = int(v)
+    for i in range(61):
+        p.table_quant[i] = int(table_quant[i])
+        p.table_offset[i] = int(table_offset[i])
+    check(lib.sb2_lowdelay_decode(ctypes.byref(p), ctypes.c_void_p(slices.data_ptr()), ctypes.c_size_t(picture_bytes),
+                                  ctypes.c_size_t(picture_pitch if picture_pitch is not None else picture_bytes),
+                                  ctypes.byref(coeffs.slab), 1 if coeffs.layout.depth == "s32" else 0, _stream_ptr(stream)),
+          "sb2_lowdelay_decode")

@@ -154,6 +154,30 @@ def shift_md5_golden(ref):
     print("shift_md5.npz:", len(out), "arrays")
 
 
+LOWDELAY_GOLDEN_CASES = [(64, 32, 2, 4, 2, 97, 2, 0, 0.0), (96, 64, 3, 3, 4, 640, 3, 0, 0.3), (128, 64, 3, 8, 4, 40, 1, 1, 0.0),
+                         (96, 96, 2, 6, 6, 33, 1, 1, 0.5), (480, 288, 4, 15, 9, 75, 2, 0, 0.0), (192, 128, 4, 5, 3, 301, 1, 0, 0.2)]
+
+
+def lowdelay_golden(ref):
+    """schro_decoder_decode_lowdelay_transform_data of the compiled reference on slices packed by
+    tests/helpers.lowdelay_encode (the bytes are stored: the packer draws random padding)."""
+    from tests.test_oracle_lowdelay import quantised_planes
+    out = {}
+    for idx, (w, h, depth, nh, nv, num, denom, is_s32, trunc) in enumerate(LOWDELAY_GOLDEN_CASES):
+        rng = np.random.default_rng(8000 + idx)
+        qm = [int(v) for v in rng.integers(0, 8, size=1 + 3 * depth)]
+        aligned = ((w // 2) >> depth) % nh == 0 and ((h // 2) >> depth) % nv == 0
+        data, _ = helpers.lowdelay_encode(quantised_planes(rng, w, h, 300), depth, nh, nv, num, denom, rng, truncate=trunc,
+                                          fast_lengths=aligned and not is_s32)
+        planes = helpers.cpu_lowdelay(ref, "ref", data, w, h, depth, nh, nv, num, denom, qm, is_s32, 0)
+        out[f"l{idx}_data"] = np.frombuffer(data, np.uint8)
+        out[f"l{idx}_qm"] = np.array(qm, np.int32)
+        for c in range(3):
+            out[f"l{idx}_out{c}"] = planes[c]
+    np.savez_compressed(os.path.join(helpers.GOLDEN_DIR, "lowdelay.npz"), **out)
+    print("lowdelay.npz:", len(out), "arrays")
+
+
 def glue_golden(ref):
     """schro_frame_convert / schro_frame_add / schro_frame_subtract of the compiled reference."""
     rng = np.random.default_rng(20261019)
@@ -228,7 +252,7 @@ def main():
     if ref is None:
         raise SystemExit("oracle/_ref/libschro_ref.so missing: run `make ref` where /root/reference exists")
     wavelet_golden(ref)
-    for name in ("frame_golden", "motion_golden", "hbm_golden", "rough_golden", "shift_md5_golden", "glue_golden", "dequant_golden", "metric_scan_golden"):
+    for name in ("frame_golden", "motion_golden", "hbm_golden", "rough_golden", "shift_md5_golden", "lowdelay_golden", "glue_golden", "dequant_golden", "metric_scan_golden"):
         fn = globals().get(name)
         if fn:
             fn(ref)

@@ -1,0 +1,112 @@
+"""GPU parity: the low-delay slice decoder (sb2_lowdelay_decode) against the oracle and against golden
+outputs of the compiled reference (tests/golden/lowdelay.npz), bit-exact: well-formed slices, truncated
+and overflowing slices, luma lengths that run into the next slice, arbitrary bytes, values that wrap."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers
+from tests.golden import make_golden as mg
+
+pytestmark = pytest.mark.gpu
+ORACLE = helpers.load_oracle()
+GOLD = np.load(os.path.join(helpers.GOLDEN_DIR, "lowdelay.npz"))
+DQ = np.load(os.path.join(helpers.GOLDEN_DIR, "dequant.npz"))
+TABLES = (DQ["table_quant"], DQ["table_offset_1_2"], DQ["table_offset_3_8"])
+
+
+def gpu_lowdelay(datas, w, h, depth, nh, nv, num, denom, qm, is_s32):
+    """datas: list of per-picture slice buffers (bytes), decoded as one batch."""
+    from schroedinger_b200 import device as dev
+    count = len(datas)
+    nbytes = len(datas[0])
+    pitch = (nbytes + 255) // 256 * 256
+    buf = np.full(count * pitch, 0xA5, np.uint8)
+    for p, d in enumerate(datas):
+        buf[p * pitch:p * pitch + nbytes] = np.frombuffer(d, np.uint8)
+    slices = torch.from_numpy(buf).cuda()
+    coeffs = dev.PictureSlab(dev.FrameLayout.yuv420("s32" if is_s32 else "s16", w, h), count)
+    coeffs.buf.fill_(0x5a)
+    dev.lowdelay_decode(slices, nbytes, coeffs, depth, nh, nv, num, denom, qm, TABLES[0], TABLES[1], picture_pitch=pitch)
+    torch.cuda.synchronize()
+    return [[coeffs.download(p, c) for c in range(3)] for p in range(count)]
+
+
+def oracle_decode(data, w, h, depth, nh, nv, num, denom, qm, is_s32):
+    aligned = ((w // 2) >> depth) % nh == 0 and ((h // 2) >> depth) % nv == 0
+    return helpers.cpu_lowdelay(ORACLE, "oracle", data, w, h, depth, nh, nv, num, denom, qm, is_s32,
+                                1 if (aligned and not is_s32) else 0, TABLES)
+
+
+def test_lowdelay_golden(cuda):
+    for idx, case in enumerate(mg.LOWDELAY_GOLDEN_CASES):
+        w, h, depth, nh, nv, num, denom, is_s32 = case[:8]
+        data, qm = GOLD[f"l{idx}_data"].tobytes(), [int(v) for v in GOLD[f"l{idx}_qm"]]
+        got = gpu_lowdelay([data], w, h, depth, nh, nv, num, denom, qm, is_s32)[0]
+        for c in range(3):
+            assert np.array_equal(got[c], GOLD[f"l{idx}_out{c}"]), (idx, c)
+
+
+@pytest.mark.parametrize("case", [
+    (64, 32, 2, 4, 2, 97, 2, 0), (96, 64, 3, 3, 4, 640, 3, 0), (128, 64, 3, 8, 4, 40, 1, 0), (128, 64, 3, 8, 4, 40, 1, 1),
+    (96, 96, 2, 6, 6, 33, 1, 1), (480, 288, 4, 15, 9, 75, 2, 0), (192, 128, 4, 5, 3, 301, 1, 0)])
+def test_lowdelay_vs_oracle(cuda, case):
+    w, h, depth, nh, nv, num, denom, is_s32 = case
+    rng = np.random.default_rng(sum(case))
+    from tests.test_oracle_lowdelay import quantised_planes
+    aligned = ((w // 2) >> depth) % nh == 0 and ((h // 2) >> depth) % nv == 0
+    fast = aligned and not is_s32
+    datas, qms = [], None
+    qm = [int(v) for v in rng.integers(0, 8, size=1 + 3 * depth)]
+    for (truncate, amp, scale) in ((0.0, 200, 1), (0.5, 200, 1), (0.0, 6000, 4), (0.0, 200, 0.34)):
+        q = quantised_planes(rng, w, h, amp)
+        n2 = max(4 * denom, int(num * scale))
+        if n2 != num:
+            continue
+        datas.append(helpers.lowdelay_encode(q, depth, nh, nv, num, denom, rng, truncate=truncate, fast_lengths=fast)[0])
+    # arbitrary bytes: luma lengths run into the following slices; the last slices are kept inside the buffer
+    sizes = helpers.lowdelay_slice_sizes(num, denom, nh, nv)
+    raw = rng.integers(0, 256, size=sum(sizes), dtype=np.uint8)
+    pos = 0
+    for sz in sizes:
+        bits = np.unpackbits(raw[pos:pos + sz])
+        lb = helpers.ilog2up(8 * ((num // denom) if fast else sz))
+        ylen = int("".join(map(str, bits[7:7 + lb])), 2)
+        left = 8 * (sum(sizes) - pos) - 7 - lb
+        if ylen > left:
+            ylen = int(rng.integers(0, left + 1))
+            bits[7:7 + lb] = [(ylen >> (lb - 1 - i)) & 1 for i in range(lb)]
+        raw[pos:pos + sz] = np.packbits(bits)
+        pos += sz
+    datas.append(bytes(raw))
+    got = gpu_lowdelay(datas, w, h, depth, nh, nv, num, denom, qm, is_s32)
+    for p, d in enumerate(datas):
+        want = oracle_decode(d, w, h, depth, nh, nv, num, denom, qm, is_s32)
+        for c in range(3):
+            assert np.array_equal(got[p][c], want[c]), (case, p, c)
+
+
+def test_lowdelay_1080p_then_inverse_transform(cuda):
+    """BASELINE configs[1]: 1080p low-delay intra pictures, DD 9/7 depth 4: slices -> coefficients -> picture."""
+    from schroedinger_b200 import device as dev
+    from tests.test_oracle_lowdelay import quantised_planes
+    w, h, depth, nh, nv, num, denom = 1920, 1088, 4, 60, 34, 190, 1
+    rng = np.random.default_rng(12)
+    qm = [0, 2, 2, 4, 2, 2, 4, 4, 4, 6, 6, 6, 8]
+    q = quantised_planes(rng, w, h, 60)
+    data = helpers.lowdelay_encode(q, depth, nh, nv, num, denom, rng, fast_lengths=True)[0]
+    want = oracle_decode(data, w, h, depth, nh, nv, num, denom, qm, 0)
+    got = gpu_lowdelay([data, data], w, h, depth, nh, nv, num, denom, qm, 0)
+    for p in range(2):
+        for c in range(3):
+            assert np.array_equal(got[p][c], want[c]), (p, c)
+    # and on through the inverse wavelet
+    layout = dev.FrameLayout.yuv420("s16", w, h)
+    a, b = dev.PictureSlab(layout, 1), dev.PictureSlab(layout, 1)
+    for c in range(3):
+        a.upload(0, c, want[c])
+    dev.iwt_inverse(a, b, 0, depth)
+    for c in range(3):
+        assert np.array_equal(b.download(0, c), helpers.cpu_wavelet(ORACLE, "oracle", "inv", want[c].copy(), 0, depth)), c

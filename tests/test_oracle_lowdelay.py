@@ -29,7 +29,7 @@ CASES = [
     (128, 64, 3, 8, 4, 40, 1, 0),
     (128, 64, 3, 8, 4, 40, 1, 1),         # s32: always the slow_s32 path
     (96, 96, 2, 6, 6, 33, 1, 1),
-    (1920 // 4, 1088 // 4, 4, 15, 17, 75, 2, 0),
+    (480, 288, 4, 15, 9, 75, 2, 0),
 ]
 
 
