@@ -99,4 +99,23 @@ compat_shim_subpel_deep (SchroParams * params, double lambda, SchroFrame * src, 
   schro_encoder_motion_predict_subpel_deep (&me);
 }
 
+/* the low-delay slice decoder: schro_decoder_decode_lowdelay_transform_data (picture) on a SchroPicture as the
+ * reference declares it (schrodecoder.h), filled with what the function reads */
+#include <schroedinger/schrodecoder.h>
+void
+compat_shim_lowdelay (SchroParams * params, unsigned char *data, int length, SchroFrame * transform_frame)
+{
+  SchroPicture *pic = calloc (1, sizeof (SchroPicture));
+  SchroBuffer buf;
+  memset (&buf, 0, sizeof (buf));
+  buf.data = data;
+  buf.length = (unsigned) length;
+  buf.ref_count = 1;
+  pic->params = *params;
+  pic->lowdelay_buffer = &buf;
+  pic->transform_frame = transform_frame;
+  schro_decoder_decode_lowdelay_transform_data (pic);
+  free (pic);
+}
+
 void compat_shim_free (void *fixture) { free (fixture); }

@@ -451,6 +451,15 @@ void schro_rough_me_heirarchical_scan_hint (SchroRoughME *rme, int shift, int di
 void schro_b200_motion_predict_subpel_deep (SchroParams *params, double lambda, SchroFrame *orig_frame,
     SchroFrame **upsampled_refs, SchroMotionField **subpel_mfs);
 
+/* ---- low-delay slices (schroedinger/schrolowdelay.c:745-761) ----
+ * schro_decoder_decode_lowdelay_transform_data (SchroPicture *) with the three things it reads from the picture
+ * passed explicitly (compat/schro_lowdelay.c keeps the reference's symbol): picture->params,
+ * picture->lowdelay_buffer->data / ->length, picture->transform_frame (s16 or s32, host or CUDA domain).
+ * The compressed slices are what goes to the GPU; the dequantised, DC-predicted coefficients are left in the
+ * frame, ready for schro_frame_inverse_iwt_transform. */
+void schro_b200_decode_lowdelay_transform_data (SchroParams *params, const uint8_t *data, int length,
+    SchroFrame *transform_frame);
+
 #ifdef __cplusplus
 }
 #endif

@@ -368,6 +368,75 @@ schro_frame_md5 (SchroFrame *frame, uint32_t *state)
   if (tmp) sb2h_pinned_pool_free (tmp);
 }
 
+/* ---- low-delay slices -------------------------------------------------------
+ * schro_decoder_decode_lowdelay_transform_data (schroedinger/schrolowdelay.c:745-761) takes a
+ * SchroPicture; it reads three things from it: params, lowdelay_buffer->data and transform_frame
+ * (compat/schro_lowdelay.c is the reference-side half).  The quantiser tables are the Dirac
+ * specification's (quant factor 4 * 2^(q/4) in its integer form, offsets (f + 1) / 2), the values of
+ * schro_table_quant / schro_table_offset_1_2 (schroedinger/schrotables.c); tests/test_lowdelay_gpu.py checks
+ * them against the reference's tables. */
+static void
+lowdelay_tables (uint32_t *quant, uint32_t *offset)
+{
+  int q;
+  for (q = 0; q < 61; q++) {
+    const uint64_t base = (uint64_t) 1 << (q / 4);
+    uint64_t f;
+    switch (q & 3) {
+      case 0: f = 4 * base; break;
+      case 1: f = (503829 * base + 52958) / 105917; break;
+      case 2: f = (665857 * base + 58854) / 117708; break;
+      default: f = (440253 * base + 32722) / 65444; break;
+    }
+    quant[q] = (uint32_t) f;
+    offset[q] = q == 0 ? 1 : (q == 1 ? 2 : (uint32_t) ((f + 1) / 2));
+  }
+}
+
+void
+schro_b200_decode_lowdelay_transform_data (SchroParams *params, const uint8_t *data, int length, SchroFrame *transform_frame)
+{
+  Sb2hContext *cx = sb2h_context ();
+  Staged s;
+  sb2_lowdelay_params p;
+  const int d = depth_code (transform_frame->format, __func__);
+  const int covered = !((params->iwt_luma_width | params->iwt_luma_height | params->iwt_chroma_width | params->iwt_chroma_height)
+      & ((1 << params->transform_depth) - 1));
+  void *dev_data;
+  int i;
+  SB2H_ASSERT (params && data && length > 0 && transform_frame);
+  if (d == 0) sb2h_fatal (__func__, "the transform frame must be s16 or s32 (format 0x%x)", (unsigned) transform_frame->format);
+  /* the reference's own preconditions (schrolowdelay.c:579-582) */
+  SB2H_ASSERT ((params->iwt_luma_width % params->n_horiz_slices) == 0 && (params->iwt_luma_height % params->n_vert_slices) == 0);
+  SB2H_ASSERT ((params->iwt_chroma_width % params->n_horiz_slices) == 0 && (params->iwt_chroma_height % params->n_vert_slices) == 0);
+  memset (&p, 0, sizeof (p));
+  p.transform_depth = params->transform_depth;
+  p.n_horiz_slices = params->n_horiz_slices;
+  p.n_vert_slices = params->n_vert_slices;
+  p.slice_bytes_num = params->slice_bytes_num;
+  p.slice_bytes_denom = params->slice_bytes_denom;
+  for (i = 0; i < 1 + 3 * params->transform_depth; i++) p.quant_matrix[i] = params->quant_matrix[i];
+  lowdelay_tables (p.table_quant, p.table_offset);
+  dev_data = sb2h_pool_alloc ((size_t) length + 16);
+  SB2H_CUDA (cudaMemcpyAsync (dev_data, data, (size_t) length, cudaMemcpyDefault, cx->stream));
+  /* every sample of the frame is written when the sizes are multiples of 1 << depth: a host frame then needs no upload */
+  stage_in (cx, &s, transform_frame, SB2H_BUF_IN, !covered);
+  /* the frame's components may be larger than the iwt area (never smaller): describe the iwt area */
+  s.slab.width[0] = params->iwt_luma_width;
+  s.slab.height[0] = params->iwt_luma_height;
+  s.slab.width[1] = s.slab.width[2] = params->iwt_chroma_width;
+  s.slab.height[1] = s.slab.height[2] = params->iwt_chroma_height;
+  SB2H_CHECK (sb2_lowdelay_decode (&p, dev_data, (size_t) length, (size_t) length, &s.slab, d == 2, cx->stream), "sb2_lowdelay_decode");
+  stage_out (cx, &s);
+  sb2h_pool_free (dev_data);
+  {
+    Staged *st[1] = { &s };
+    stage_finish (cx, st, 1, 1u);
+  }
+  /* the slice bytes may be pageable or page-locked host memory the caller reuses: wait for the upload */
+  if (sb2h_mem_kind (data) != SB2H_MEM_DEVICE) sb2h_sync (cx);
+}
+
 /* ---- OBMC ------------------------------------------------------------------ */
 SchroMotion *
 schro_motion_new (SchroParams *params, SchroFrame *ref1, SchroFrame *ref2)

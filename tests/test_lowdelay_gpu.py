@@ -110,3 +110,57 @@ def test_lowdelay_1080p_then_inverse_transform(cuda):
     dev.iwt_inverse(a, b, 0, depth)
     for c in range(3):
         assert np.array_equal(b.download(0, c), helpers.cpu_wavelet(ORACLE, "oracle", "inv", want[c].copy(), 0, depth)), c
+
+
+SHIM = os.path.join(helpers.ROOT, "oracle", "_ref", "libcompat_shim.so")
+
+
+@pytest.mark.parametrize("via_shim", [False, True])
+@pytest.mark.parametrize("domain_kind", ["malloc", "cuda"])
+def test_lowdelay_drop_in(cuda, via_shim, domain_kind):
+    """schro_b200_decode_lowdelay_transform_data (and the reference-side schro_decoder_decode_lowdelay_transform_data
+    on a SchroPicture) -> schro_frame_inverse_iwt_transform, on a malloc'd and on a CUDA-domain transform frame; the
+    library's own quantiser tables (the Dirac specification's formulas) against the reference's."""
+    import ctypes
+    from schroedinger_b200 import compat, lib
+    from tests.test_oracle_lowdelay import quantised_planes
+    if via_shim and not os.path.exists(SHIM):
+        pytest.skip("oracle/_ref/libcompat_shim.so was not built")
+    w, h, depth, nh, nv, num, denom = 480, 288, 4, 15, 9, 150, 1
+    rng = np.random.default_rng(77)
+    qm = [0, 1, 1, 2, 1, 1, 2, 2, 2, 3, 3, 3, 4]
+    data = helpers.lowdelay_encode(quantised_planes(rng, w, h, 100), depth, nh, nv, num, denom, rng, fast_lengths=True)[0]
+    want = oracle_decode(data, w, h, depth, nh, nv, num, denom, qm, 0)
+    params = compat.make_params(w, h, wavelet_filter_index=0, transform_depth=depth, iwt_luma_width=w, iwt_luma_height=h)
+    params.is_lowdelay = 1
+    params.n_horiz_slices, params.n_vert_slices = nh, nv
+    params.slice_bytes_num, params.slice_bytes_denom = num, denom
+    params.iwt_chroma_width, params.iwt_chroma_height = w // 2, h // 2
+    for i, v in enumerate(qm):
+        params.quant_matrix[i] = v
+    domain = compat.cuda_domain() if domain_kind == "cuda" else None
+    f = compat.frame_new_and_alloc(domain, compat.FORMAT_S16_420, w, h, 0, 0)
+    buf = ctypes.create_string_buffer(data, len(data))
+    if via_shim:
+        from schroedinger_b200._lib import LIB_PATH
+        ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+        shim = ctypes.CDLL(SHIM)
+        shim.compat_shim_lowdelay.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        shim.compat_shim_lowdelay(ctypes.byref(params), buf, len(data), f)
+    else:
+        lib.schro_b200_decode_lowdelay_transform_data(ctypes.byref(params), buf, len(data), f)
+    host = f
+    if domain_kind == "cuda":
+        host = compat.frame_new_and_alloc(None, compat.FORMAT_S16_420, w, h, 0, 0)
+        lib.schro_gpuframe_to_cpu(host, f)
+    for c in range(3):
+        assert np.array_equal(np.array(compat.frame_plane(host, c)), want[c]), (c, "coefficients")
+    lib.schro_frame_inverse_iwt_transform(f, ctypes.byref(params))
+    if domain_kind == "cuda":
+        lib.schro_gpuframe_to_cpu(host, f)
+    for c in range(3):
+        pic = helpers.cpu_wavelet(ORACLE, "oracle", "inv", want[c].copy(), 0, depth)
+        assert np.array_equal(np.array(compat.frame_plane(host, c)), pic), (c, "picture")
+    if host is not f:
+        lib.schro_frame_unref(host)
+    lib.schro_frame_unref(f)
