@@ -693,6 +693,131 @@ def next_rows(torch, dev, world, all_ranks, barrier):
     return out
 
 
+def _lowdelay_slice(rng, nbytes, n_luma, n_chroma2, base):
+    """One well-formed low-delay slice (schroedinger/schrolowdelay.c:101-178): 7-bit base index, luma length,
+    luma then interleaved chroma coefficients as interleaved exp-Golomb codes, zero-run tail trimmed by the
+    1-bit guard; values drawn like a quantised residual (mostly 0 / +-1)."""
+    def code(v):
+        a = abs(int(v)) + 1
+        n = a.bit_length()
+        bits = []
+        for i in range(n - 1):
+            bits += [0, (a >> (n - 2 - i)) & 1]
+        bits.append(1)
+        if v:
+            bits.append(1 if v < 0 else 0)
+        return bits
+    lb = (8 * nbytes).bit_length()
+    room = 8 * nbytes - 7 - lb
+    vals = (rng.geometric(0.55, size=n_luma + n_chroma2) - 1) * rng.choice([-1, 1], size=n_luma + n_chroma2)
+    ybits, uvbits = [], []
+    for v in vals[:n_luma]:
+        ybits += code(v)
+    for v in vals[n_luma:]:
+        uvbits += code(v)
+    ylen = min(len(ybits), (2 * room) // 3)
+    bits = [(base >> (6 - i)) & 1 for i in range(7)] + [(ylen >> (lb - 1 - i)) & 1 for i in range(lb)]
+    bits += ybits[:ylen] + uvbits[:room - ylen]
+    bits += [1] * (8 * nbytes - len(bits))
+    return np.packbits(np.array(bits[:8 * nbytes], np.uint8))
+
+
+def lowdelay_rows(torch, dev, lib, world, all_ranks, barrier, e2e_threads=32):
+    """BASELINE configs[1] as a decoder sees it: VC-2 low-delay intra 1080p pictures arrive as compressed
+    slices (60 x 34 slices of 190 bytes = 388 KB per picture), are decoded + dequantised + DC-predicted on
+    the device, inverse-transformed (DD 9/7, 4 levels, s16) and converted to 8 bits.  Device-resident for a
+    batch, and end to end through the drop-in C API (pinned host slices up, pinned u8 pictures down)."""
+    from schroedinger_b200 import compat
+    w, h, depth, nh, nv, nbytes, count = 1920, 1088, 4, 60, 34, 190, 64
+    rng = np.random.default_rng(4242)
+    templates = [_lowdelay_slice(rng, nbytes, 32 * 32, 2 * 16 * 16, int(rng.integers(8, 28))) for _ in range(16)]
+    pic_bytes = nh * nv * nbytes
+    pitch = (pic_bytes + 255) // 256 * 256
+    host = np.zeros((count, pitch), np.uint8)
+    for p in range(count):
+        pick = rng.integers(0, len(templates), size=nh * nv)
+        host[p, :pic_bytes] = np.concatenate([templates[k] for k in pick])
+    slices = torch.from_numpy(host.reshape(-1)).cuda()
+    qm = [0, 2, 2, 4, 2, 2, 4, 4, 4, 6, 6, 6, 8]
+    tq, to = [], []
+    for q in range(61):                                       # the Dirac specification's quantiser tables
+        base = 1 << (q // 4)
+        f = [4 * base, (503829 * base + 52958) // 105917, (665857 * base + 58854) // 117708, (440253 * base + 32722) // 65444][q & 3]
+        tq.append(f)
+        to.append(1 if q == 0 else 2 if q == 1 else (f + 1) // 2)
+    coeffs = dev.PictureSlab(dev.FrameLayout.yuv420("s16", w, h), count)
+    pict = dev.PictureSlab(dev.FrameLayout.yuv420("s16", w, h), count)
+    out8 = dev.PictureSlab(dev.FrameLayout.yuv420("u8", w, 1080), count)
+
+    class OneStage:
+        def __init__(self, fn):
+            self.step = fn
+
+    def step():
+        dev.lowdelay_decode(slices, pic_bytes, coeffs, depth, nh, nv, nbytes, 1, qm, tq, to, picture_pitch=pitch)
+        dev.iwt_inverse(coeffs, pict, 0, depth)
+        dev.frame_convert(pict, out8)
+    lib.sb2_profile_reset()
+    ms = all_ranks(time_device_resident(torch, OneStage(step), 10, 3, barrier), "max") / 10
+    lib.sb2_profile_enable(1)
+    step()
+    torch.cuda.synchronize()
+    lib.sb2_profile_enable(0)
+    kern = {k: round(v["ms"], 4) for k, v in collect_profile(lib).items()}
+    lib.sb2_profile_reset()
+    res = {"what": "VC-2 low-delay intra 1080p decode (BASELINE configs[1]): 2040 slices of 190 bytes per picture -> "
+                   "slice decode + dequantise + DC prediction -> inverse DD 9/7 4-level s16 -> 8-bit picture",
+           "batch_per_gpu": count, "value": round(count * world / (ms * 1e-3), 1), "unit": "frames/s",
+           "ms_per_step": round(ms, 4), "kernel_ms": kern, "compressed_bytes_per_picture": pic_bytes}
+    del coeffs, pict, out8
+    # ---- end to end through the drop-in API: one picture per call chain, a pool of host threads
+    params = compat.make_params(w, 1080, wavelet_filter_index=0, transform_depth=depth, iwt_luma_width=w, iwt_luma_height=h)
+    params.is_lowdelay = 1
+    params.n_horiz_slices, params.n_vert_slices = nh, nv
+    params.slice_bytes_num, params.slice_bytes_denom = nbytes, 1
+    for i, v in enumerate(qm):
+        params.quant_matrix[i] = v
+    A = compat.frame_new_and_alloc
+    pinned, cuda = compat.pinned_domain(), compat.cuda_domain()
+    # the slices of each picture in page-locked memory (a u8 frame's luma plane serves as the buffer)
+    bufs = []
+    for p in range(count):
+        f = A(pinned, compat.FORMAT_U8_444, pitch // 16, 16, 0, 0)
+        ctypes.memmove(f.contents.components[0].data, host[p].ctypes.data, pic_bytes)
+        bufs.append(f)
+    outs = [A(pinned, compat.FORMAT_U8_420, w, 1080, 0, 0) for _ in range(count)]
+    th = [dict(coef=A(cuda, compat.FORMAT_S16_420, w, h, 0, 0), u8=A(cuda, compat.FORMAT_U8_420, w, 1080, 0, 0))
+          for _ in range(e2e_threads)]
+
+    path = os.path.join(ROOT, "bench_native", "libsb2_e2e_driver.so")
+    drv = ctypes.CDLL(path)
+
+    class Job(ctypes.Structure):
+        _fields_ = [("nthreads", ctypes.c_int), ("npictures", ctypes.c_int), ("slice_bytes", ctypes.c_int),
+                    ("params", ctypes.POINTER(compat.SchroParams)), ("slices", ctypes.POINTER(ctypes.c_void_p)),
+                    ("out_host", ctypes.POINTER(compat.FrameP)), ("coef_dev", ctypes.POINTER(compat.FrameP)),
+                    ("u8_dev", ctypes.POINTER(compat.FrameP))]
+    job = Job(e2e_threads, count, pic_bytes, ctypes.pointer(params),
+              (ctypes.c_void_p * count)(*[f.contents.components[0].data for f in bufs]),
+              (compat.FrameP * count)(*outs), (compat.FrameP * e2e_threads)(*[t["coef"] for t in th]),
+              (compat.FrameP * e2e_threads)(*[t["u8"] for t in th]))
+    drv.sb2_e2e_lowdelay_run.restype = ctypes.c_double
+    drv.sb2_e2e_lowdelay_run(ctypes.byref(job), 1)
+    barrier()
+    steps = 8
+    wall = all_ranks(drv.sb2_e2e_lowdelay_run(ctypes.byref(job), steps), "max")
+    res["e2e"] = {"value": round(count * world * steps / wall, 1), "unit": "frames/s",
+                  "h2d_bytes_per_step": pic_bytes * count, "d2h_bytes_per_step": 1920 * 1080 * 3 // 2 * count,
+                  "api": f"schro_b200_decode_lowdelay_transform_data, schro_frame_inverse_iwt_transform, schro_frame_convert, "
+                         f"schro_gpuframe_to_cpu; {e2e_threads} host threads (pthreads, bench_native/e2e_driver.c), pinned slices and pictures"}
+    for f in bufs + outs:
+        lib.schro_frame_unref(f)
+    for t in th:
+        lib.schro_frame_unref(t["coef"])
+        lib.schro_frame_unref(t["u8"])
+    return {"lowdelay_1080p": res}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -829,6 +954,8 @@ def run_ours(args):
             del ost
         torch.cuda.empty_cache()
         other.update(next_rows(torch, dev, world, all_ranks, barrier))
+        torch.cuda.empty_cache()
+        other.update(lowdelay_rows(torch, dev, lib, world, all_ranks, barrier))
 
     if rank != 0:
         if world > 1:

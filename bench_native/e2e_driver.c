@@ -226,3 +226,61 @@ sb2_e2e_stop (void)
   pthread_barrier_destroy (&g_start);
   pthread_barrier_destroy (&g_end);
 }
+
+/* ---- low-delay intra decode (BASELINE configs[1]): compressed slices in, 8-bit pictures out ----
+ * A self-contained run: `nthreads` pthreads share the pictures round-robin, each picture is
+ *   schro_b200_decode_lowdelay_transform_data -> schro_frame_inverse_iwt_transform -> schro_frame_convert ->
+ *   schro_gpuframe_to_cpu
+ * on the thread's own CUDA-domain frames.  Returns the wall-clock seconds of `steps` passes over the pictures. */
+typedef struct {
+  int nthreads, npictures, slice_bytes;
+  SchroParams *params;
+  const uint8_t **slices;      /* [npictures] page-locked slice buffers */
+  SchroFrame **out_host;       /* [npictures] page-locked u8 pictures */
+  SchroFrame **coef_dev;       /* [nthreads] CUDA-domain coefficient frames (iwt size) */
+  SchroFrame **u8_dev;         /* [nthreads] CUDA-domain u8 pictures */
+} Sb2LowdelayJob;
+
+typedef struct { const Sb2LowdelayJob *job; int t, steps; pthread_barrier_t *start; } LdWorker;
+
+static void *
+ld_worker (void *arg)
+{
+  LdWorker *w = arg;
+  const Sb2LowdelayJob *j = w->job;
+  const long total = (long) w->steps * j->npictures;
+  long k;
+  pthread_barrier_wait (w->start);
+  for (k = w->t; k < total; k += j->nthreads) {
+    const int i = (int) (k % j->npictures);
+    schro_b200_decode_lowdelay_transform_data (j->params, j->slices[i], j->slice_bytes, j->coef_dev[w->t]);
+    schro_frame_inverse_iwt_transform (j->coef_dev[w->t], j->params);
+    schro_frame_convert (j->u8_dev[w->t], j->coef_dev[w->t]);
+    schro_gpuframe_to_cpu (j->out_host[i], j->u8_dev[w->t]);
+  }
+  schro_b200_thread_release ();
+  return NULL;
+}
+
+double
+sb2_e2e_lowdelay_run (const Sb2LowdelayJob *job, int steps)
+{
+  pthread_t *th = calloc ((size_t) job->nthreads, sizeof (pthread_t));
+  LdWorker *w = calloc ((size_t) job->nthreads, sizeof (LdWorker));
+  pthread_barrier_t start;
+  double t0;
+  int t;
+  pthread_barrier_init (&start, NULL, (unsigned) job->nthreads + 1);
+  for (t = 0; t < job->nthreads; t++) {
+    w[t].job = job; w[t].t = t; w[t].steps = steps; w[t].start = &start;
+    pthread_create (&th[t], NULL, ld_worker, &w[t]);
+  }
+  pthread_barrier_wait (&start);
+  t0 = now ();
+  for (t = 0; t < job->nthreads; t++) pthread_join (th[t], NULL);
+  t0 = now () - t0;
+  pthread_barrier_destroy (&start);
+  free (th);
+  free (w);
+  return t0;
+}
