@@ -722,7 +722,7 @@ def _lowdelay_slice(rng, nbytes, n_luma, n_chroma2, base):
     return np.packbits(np.array(bits[:8 * nbytes], np.uint8))
 
 
-def lowdelay_rows(torch, dev, lib, world, all_ranks, barrier, e2e_threads=32):
+def lowdelay_rows(torch, dev, lib, world, all_ranks, barrier, e2e_threads=12):
     """BASELINE configs[1] as a decoder sees it: VC-2 low-delay intra 1080p pictures arrive as compressed
     slices (60 x 34 slices of 190 bytes = 388 KB per picture), are decoded + dequantised + DC-predicted on
     the device, inverse-transformed (DD 9/7, 4 levels, s16) and converted to 8 bits.  Device-resident for a
@@ -805,7 +805,12 @@ def lowdelay_rows(torch, dev, lib, world, all_ranks, barrier, e2e_threads=32):
     drv.sb2_e2e_lowdelay_run(ctypes.byref(job), 1)
     barrier()
     steps = 8
+    tm = (ctypes.c_double * 4)()
+    drv.sb2_e2e_lowdelay_times(tm)
     wall = all_ranks(drv.sb2_e2e_lowdelay_run(ctypes.byref(job), steps), "max")
+    drv.sb2_e2e_lowdelay_times(tm)
+    res["e2e_call_ms"] = {k: round(tm[i] / (steps * count) * 1e3, 3) for i, k in enumerate(
+        ("decode_lowdelay", "inverse_iwt", "convert", "gpuframe_to_cpu"))}
     res["e2e"] = {"value": round(count * world * steps / wall, 1), "unit": "frames/s",
                   "h2d_bytes_per_step": pic_bytes * count, "d2h_bytes_per_step": 1920 * 1080 * 3 // 2 * count,
                   "api": f"schro_b200_decode_lowdelay_transform_data, schro_frame_inverse_iwt_transform, schro_frame_convert, "

@@ -242,6 +242,14 @@ typedef struct {
 } Sb2LowdelayJob;
 
 typedef struct { const Sb2LowdelayJob *job; int t, steps; pthread_barrier_t *start; } LdWorker;
+/* wall-clock seconds per call, summed per thread (sb2_e2e_lowdelay_times reads and clears them) */
+static double g_ld_times[64][4];
+void
+sb2_e2e_lowdelay_times (double *out)
+{
+  int t, k;
+  for (k = 0; k < 4; k++) { out[k] = 0; for (t = 0; t < 64; t++) { out[k] += g_ld_times[t][k]; g_ld_times[t][k] = 0; } }
+}
 
 static void *
 ld_worker (void *arg)
@@ -253,10 +261,17 @@ ld_worker (void *arg)
   pthread_barrier_wait (w->start);
   for (k = w->t; k < total; k += j->nthreads) {
     const int i = (int) (k % j->npictures);
+    const double t0 = now ();
     schro_b200_decode_lowdelay_transform_data (j->params, j->slices[i], j->slice_bytes, j->coef_dev[w->t]);
+    const double t1 = now ();
     schro_frame_inverse_iwt_transform (j->coef_dev[w->t], j->params);
+    const double t2 = now ();
     schro_frame_convert (j->u8_dev[w->t], j->coef_dev[w->t]);
+    const double t3 = now ();
     schro_gpuframe_to_cpu (j->out_host[i], j->u8_dev[w->t]);
+    const double t4 = now ();
+    g_ld_times[w->t & 63][0] += t1 - t0; g_ld_times[w->t & 63][1] += t2 - t1;
+    g_ld_times[w->t & 63][2] += t3 - t2; g_ld_times[w->t & 63][3] += t4 - t3;
   }
   schro_b200_thread_release ();
   return NULL;

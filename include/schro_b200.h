@@ -378,6 +378,9 @@ typedef struct {
   int quant_matrix[1 + 3 * SB2_DEQUANT_MAX_LEVELS];
   uint32_t table_quant[61], table_offset[61];
 } sb2_lowdelay_params;
+/* the slice kernel stages each CTA's slices in shared memory; on != 0 makes it read them from global memory
+ * (what slices too large to stage get) -- tests run both */
+void sb2_lowdelay_force_unstaged (int on);
 int sb2_lowdelay_decode (const sb2_lowdelay_params *params, const uint8_t *slices, size_t picture_bytes,
     size_t picture_pitch, const sb2_slab *coeffs, int is_s32, void *stream);
 

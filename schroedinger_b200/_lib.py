@@ -83,6 +83,7 @@ class LowdelayParams(ctypes.Structure):
                 ("table_quant", ctypes.c_uint32 * 61), ("table_offset", ctypes.c_uint32 * 61)]
 
 
+_opt("sb2_lowdelay_force_unstaged", None, [ctypes.c_int])
 _opt("sb2_lowdelay_decode", ctypes.c_int, [ctypes.POINTER(LowdelayParams), ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
                                           _SP, ctypes.c_int, ctypes.c_void_p])
 _opt("sb2_edgeextend_upsample", ctypes.c_int, [_SP, ctypes.c_int, ctypes.c_void_p])

@@ -30,6 +30,7 @@ struct LowdelayArgs {
   long long data_bytes;              // bytes of one picture's slices
   int width[3], height[3];
   int depth, nh, nv, n_bytes, remainder, denom, count, orc16;
+  int tile_bytes;                    // dynamic shared memory of the slice kernel (0: read the slices from global memory)
 };
 
 // quantiser tables (61 entries each, the reference's schro_table_quant / schro_table_offset_1_2) and the
@@ -40,11 +41,21 @@ struct LowdelayTables {
 };
 
 struct BitReader {
-  const uint8_t *data;
+  const uint8_t *data;              // the picture's slice buffer in global memory
+  const uint8_t *tile;              // the CTA's slices staged in shared memory: bytes [tile_lo, tile_hi) of the buffer
+  long long tile_lo, tile_hi;
   long long pos, end;               // next bit to load into the buffer / first bit past the part
   unsigned long long buf;           // MSB-aligned
   int n;                            // valid bits in buf
-  __device__ __forceinline__ void init (const uint8_t *d, long long p, long long e) { data = d; pos = p; end = e; buf = 0; n = 0; }
+  __device__ __forceinline__ void init (const uint8_t *d, const uint8_t *t, long long lo, long long hi, long long p, long long e)
+  {
+    data = d; tile = t; tile_lo = lo; tile_hi = hi; pos = p; end = e; buf = 0; n = 0;
+  }
+  __device__ __forceinline__ unsigned byte_at (long long i) const
+  {
+    // a luma part that runs past its slice may leave the staged range: those bytes come from global memory
+    return (i >= tile_lo && i < tile_hi) ? tile[i - tile_lo] : data[i];
+  }
   __device__ __forceinline__ void fill ()
   {
     // byte-aligned after the first load; past `end` the stream is all ones (schrounpack.c:96-103)
@@ -53,7 +64,7 @@ struct BitReader {
       const int sh = (int) (pos & 7);
       if (pos >= end) b = 0xffu;
       else {
-        b = data[pos >> 3];
+        b = byte_at (pos >> 3);
         if (pos - sh + 8 > end) b |= 0xffu >> (int) (end - (pos - sh));
       }
       if (sh) {                      // first, unaligned load: drop the bits before pos
@@ -122,29 +133,52 @@ __device__ __forceinline__ int ld_dequant (int q, int factor, int offset, int or
   return ((int) ((unsigned) q * (unsigned) factor + (unsigned) offset + 2u)) >> 2;
 }
 
+constexpr int LD_THREADS = 128;
+constexpr int LD_TILE_BYTES = 48 * 1024;       // staged when the CTA's slices fit (128 slices of up to 384 bytes)
+
 template <typename T>
-__global__ void __launch_bounds__ (128)
+__global__ void __launch_bounds__ (LD_THREADS)
 lowdelay_slice_kernel (const LowdelayArgs A, const LowdelayTables c_ld)
 {
-  const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ __align__ (16) uint8_t tile[];
   const int per_pic = A.nh * A.nv;
-  if (g >= (long long) per_pic * A.count) return;
-  const int pic = (int) (g / per_pic), k = (int) (g - (long long) pic * per_pic);
-  const int sy = k / A.nh, sx = k - sy * A.nh;
-  // slice k starts after k * n_bytes + floor (k * remainder / denom) bytes (the accumulator of :620-632)
-  const long long off = (long long) k * A.n_bytes + ((long long) k * A.remainder) / A.denom;
-  const int slice_bytes = A.n_bytes + (int) (((long long) (k + 1) * A.remainder) / A.denom - ((long long) k * A.remainder) / A.denom);
+  // a CTA's threads take consecutive slices of ONE picture, so their bytes are one contiguous range
+  const int ctas_per_pic = (per_pic + LD_THREADS - 1) / LD_THREADS;
+  const int pic = blockIdx.x / ctas_per_pic, k0 = (blockIdx.x - pic * ctas_per_pic) * LD_THREADS;
+  const int k = k0 + threadIdx.x;
   const uint8_t *data = A.data + (size_t) pic * A.data_pitch;
+  // slice k starts after k * n_bytes + floor (k * remainder / denom) bytes (the accumulator of :620-632)
+  auto slice_off = [&] (int kk) { return (long long) kk * A.n_bytes + ((long long) kk * A.remainder) / A.denom; };
+  const int k1 = min (k0 + LD_THREADS, per_pic);
+  const long long lo = slice_off (k0), hi = slice_off (k1);
+  long long tile_lo = 0, tile_hi = 0;
+  if (A.tile_bytes >= hi - lo) {
+    // coalesced copy of the CTA's slices: the bit readers then run out of shared memory, with no global-memory
+    // latency inside their serial chains
+    const long long a0 = lo & ~15LL;
+    for (long long i = a0 + 16LL * threadIdx.x; i < hi; i += 16LL * LD_THREADS) {
+      if (i + 16 <= A.data_bytes && (((size_t) data) & 15) == 0)
+        *reinterpret_cast<uint4 *> (tile + (i - a0)) = *reinterpret_cast<const uint4 *> (data + i);
+      else
+        for (int b = 0; b < 16; b++) if (i + b < A.data_bytes) tile[i - a0 + b] = data[i + b];
+    }
+    tile_lo = a0; tile_hi = min (hi, A.data_bytes);
+  }
+  __syncthreads ();
+  if (k >= per_pic) return;
+  const int sy = k / A.nh, sx = k - sy * A.nh;
+  const long long off = slice_off (k);
+  const int slice_bytes = (int) (slice_off (k + 1) - off);
   BitReader yb, uvb;
-  yb.init (data, 8 * off, 8 * (off + slice_bytes));
+  yb.init (data, tile, tile_lo, tile_hi, 8 * off, 8 * (off + slice_bytes));
   const int base_index = (int) yb.get (7);
   const int lenbits = 32 - __clz (8 * (A.orc16 ? A.n_bytes : slice_bytes));        // ilog2up (:87-97)
   const long long y_length = (long long) yb.get (lenbits);
   const long long y_start = 8 * off + 7 + lenbits;
   // the luma part ends where its declared length says (even past the slice, schrounpack.c:49-60), only the
   // end of the picture's buffer stops it; the chroma part runs from there to the end of the slice
-  yb.init (data, y_start, min (y_start + y_length, 8 * A.data_bytes));
-  uvb.init (data, y_start + y_length, 8 * (off + slice_bytes));
+  yb.init (data, tile, tile_lo, tile_hi, y_start, min (y_start + y_length, 8 * A.data_bytes));
+  uvb.init (data, tile, tile_lo, tile_hi, y_start + y_length, 8 * (off + slice_bytes));
   const int nbands = 1 + 3 * A.depth;
 #pragma unroll 1
   for (int c = 0; c < 2; c++) {
@@ -215,6 +249,10 @@ lowdelay_dc_kernel (const LowdelayArgs A)
 
 using namespace sb2;
 
+// tests run the slice kernel both ways: slices staged in shared memory (default) and read from global memory
+static int g_lowdelay_unstaged = 0;
+extern "C" void sb2_lowdelay_force_unstaged (int on) { g_lowdelay_unstaged = on ? 1 : 0; }
+
 extern "C" int
 sb2_lowdelay_decode (const sb2_lowdelay_params *p, const uint8_t *slices, size_t picture_bytes, size_t picture_pitch,
     const sb2_slab *coeffs, int is_s32, void *stream)
@@ -263,9 +301,19 @@ sb2_lowdelay_decode (const sb2_lowdelay_params *p, const uint8_t *slices, size_t
   for (int c = 0; c < 3; c++) coef += (double) coeffs->width[c] * coeffs->height[c];
   {
     LaunchScope scope ("lowdelay_slices", ((double) total + coef * bpp) * coeffs->count, st);
-    const unsigned ctas = (unsigned) ((nslices * coeffs->count + 127) / 128);
-    if (is_s32) lowdelay_slice_kernel<int32_t><<<ctas, 128, 0, st>>> (A, t);
-    else lowdelay_slice_kernel<int16_t><<<ctas, 128, 0, st>>> (A, t);
+    const long long ctas_per_pic = (nslices + LD_THREADS - 1) / LD_THREADS;
+    const unsigned ctas = (unsigned) (ctas_per_pic * coeffs->count);
+    // bytes of LD_THREADS consecutive slices (+ one for the fractional sizes, + alignment slack)
+    const long long need = (n_bytes + 1) * LD_THREADS + 32;
+    A.tile_bytes = (need <= LD_TILE_BYTES && !g_lowdelay_unstaged) ? (int) need : 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute (lowdelay_slice_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, LD_TILE_BYTES);
+      cudaFuncSetAttribute (lowdelay_slice_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, LD_TILE_BYTES);
+      attr_set = true;
+    }
+    if (is_s32) lowdelay_slice_kernel<int32_t><<<ctas, LD_THREADS, A.tile_bytes, st>>> (A, t);
+    else lowdelay_slice_kernel<int16_t><<<ctas, LD_THREADS, A.tile_bytes, st>>> (A, t);
   }
   {
     LaunchScope scope ("lowdelay_dc_predict", 2.0 * coef / (1 << (2 * p->transform_depth)) * bpp * coeffs->count, st);

@@ -49,6 +49,11 @@ void sb2h_frame_wrote (Sb2hContext *cx, const void *region);
 const void *sb2h_region_of (const void *ptr);
 void sb2h_ptr_use (Sb2hContext *cx, const void *ptr);
 void sb2h_ptr_wrote (Sb2hContext *cx, const void *ptr);
+/* the calling thread's spare region for in-place transforms of CUDA-domain frames (core.c): take returns a region of
+ * exactly that domain and size or NULL; put keeps `region` (allocated from `domain`) as the spare and returns 1 when no
+ * other thread ever touched it and the thread has no spare yet, else returns 0 and the caller frees it */
+void *sb2h_spare_take (Sb2hContext *cx, SchroMemoryDomain *domain, int size);
+int sb2h_spare_put (Sb2hContext *cx, SchroMemoryDomain *domain, void *region, int size);
 /* process-wide pool of page-locked host blocks, reused by exact size */
 void *sb2h_pinned_pool_alloc (size_t bytes);
 int sb2h_pinned_pool_free (void *ptr);     /* 0 if ptr is not a pool block */

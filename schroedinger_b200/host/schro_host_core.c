@@ -79,6 +79,9 @@ static void sb2h_pool_release_all (void);
 
 #define SB2H_MAX_CTX 128
 static Sb2hContext *g_ctx[SB2H_MAX_CTX];        /* live per-thread contexts, under g_device_mutex */
+/* per-thread spare region of the in-place transforms (see sb2h_spare_take below) */
+static struct { SchroMemoryDomain *domain; void *ptr; int size; } g_spare[SB2H_MAX_CTX];
+static pthread_mutex_t g_spare_mutex = PTHREAD_MUTEX_INITIALIZER;
 
 /* Give the calling thread's stream, staging buffers and pooled device blocks back.  Worker
  * threads are expected to be long-lived (as SchroAsync's are); a thread that does exit
@@ -97,6 +100,15 @@ schro_b200_thread_release (void)
   int i, last;
   if (!cx) return;
   cudaStreamSynchronize (cx->stream);
+  {
+    /* the thread's spare transform region goes back to its domain (everything on the stream has finished) */
+    SchroMemoryDomain *d = NULL;
+    void *p = NULL;
+    pthread_mutex_lock (&g_spare_mutex);
+    if (g_spare[cx->slot].ptr) { d = g_spare[cx->slot].domain; p = g_spare[cx->slot].ptr; g_spare[cx->slot].ptr = NULL; }
+    pthread_mutex_unlock (&g_spare_mutex);
+    if (p) schro_memory_domain_memfree (d, p);
+  }
   pthread_mutex_lock (&g_device_mutex);
   g_ctx[cx->slot] = NULL;
   for (i = 0, last = 1; i < SB2H_MAX_CTX; i++)
@@ -225,6 +237,63 @@ frame_take_users (const void *region, unsigned long long *users)
   }
   pthread_mutex_unlock (&g_write_mutex);
   return known;
+}
+
+/* ---- per-thread spare region for the in-place transforms ------------------------------------
+ * An in-place wavelet transform of a CUDA-domain frame writes into a second region and swaps (host
+ * wavelet layer).  Going through the domain for that -- free the old region, allocate the next call's new one
+ * -- makes the workers wait on each other: a freed region with work in flight is parked, and an allocation
+ * of that size waits (on the host, holding the domain's lock) for the parked blocks of EVERY worker.  So a
+ * thread keeps the region it has just transformed OUT OF as its spare for the next call, provided no other
+ * thread ever touched that region (its reuse is then ordered by the thread's own stream). */
+void *
+sb2h_spare_take (Sb2hContext *cx, SchroMemoryDomain *domain, int size)
+{
+  void *p = NULL;
+  pthread_mutex_lock (&g_spare_mutex);
+  if (g_spare[cx->slot].ptr && g_spare[cx->slot].domain == domain && g_spare[cx->slot].size == size) {
+    p = g_spare[cx->slot].ptr;
+    g_spare[cx->slot].ptr = NULL;
+  }
+  pthread_mutex_unlock (&g_spare_mutex);
+  return p;
+}
+
+int
+sb2h_spare_put (Sb2hContext *cx, SchroMemoryDomain *domain, void *region, int size)
+{
+  int k, i, only_me = 1, kept = 0;
+  pthread_mutex_lock (&g_write_mutex);
+  k = write_slot (region, 0);
+  if (k >= 0)
+    for (i = 0; i < SB2H_MAX_CTX / 64; i++) {
+      unsigned long long u = g_writes[k].users[i];
+      if (i == cx->slot / 64) u &= ~(1ull << (cx->slot % 64));
+      if (u) only_me = 0;
+    }
+  if (k >= 0 && g_writes[k].stream && g_writes[k].stream != cx->stream) only_me = 0;
+  pthread_mutex_unlock (&g_write_mutex);
+  if (!only_me) return 0;
+  pthread_mutex_lock (&g_spare_mutex);
+  if (!g_spare[cx->slot].ptr) {
+    g_spare[cx->slot].domain = domain;
+    g_spare[cx->slot].ptr = region;
+    g_spare[cx->slot].size = size;
+    kept = 1;
+  }
+  pthread_mutex_unlock (&g_spare_mutex);
+  return kept;
+}
+
+/* a domain is going away (its regions are released with it), or a thread is: forget / hand back the spares */
+static void
+spare_forget_domain (SchroMemoryDomain *domain)
+{
+  int c;
+  pthread_mutex_lock (&g_spare_mutex);
+  for (c = 0; c < SB2H_MAX_CTX; c++)
+    if (g_spare[c].domain == domain) g_spare[c].ptr = NULL;
+  pthread_mutex_unlock (&g_spare_mutex);
 }
 
 void
@@ -591,6 +660,7 @@ schro_memory_domain_free (SchroMemoryDomain *domain)
 {
   int i;
   SB2H_ASSERT (domain != NULL);
+  spare_forget_domain (domain);
   if (domain->flags & SCHRO_MEMORY_DOMAIN_CUDA) {
     pthread_mutex_lock (domain->mutex);
     limbo_reap (domain, 1);

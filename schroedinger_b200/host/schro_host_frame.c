@@ -417,7 +417,10 @@ schro_b200_decode_lowdelay_transform_data (SchroParams *params, const uint8_t *d
   p.slice_bytes_denom = params->slice_bytes_denom;
   for (i = 0; i < 1 + 3 * params->transform_depth; i++) p.quant_matrix[i] = params->quant_matrix[i];
   lowdelay_tables (p.table_quant, p.table_offset);
-  dev_data = sb2h_pool_alloc ((size_t) length + 16);
+  /* the thread's own staging buffer, not the shared block pool: a pool block freed with this call's work still
+   * in flight would make the next taker's stream wait for it, chaining the workers' decodes one behind another
+   * (measured: 3.6 ms per call with 8 workers against 0.5 ms of GPU work) */
+  dev_data = sb2h_dev_buffer (cx, SB2H_BUF_AUX0, (size_t) length + 16);
   SB2H_CUDA (cudaMemcpyAsync (dev_data, data, (size_t) length, cudaMemcpyDefault, cx->stream));
   /* every sample of the frame is written when the sizes are multiples of 1 << depth: a host frame then needs no upload */
   stage_in (cx, &s, transform_frame, SB2H_BUF_IN, !covered);
@@ -428,7 +431,6 @@ schro_b200_decode_lowdelay_transform_data (SchroParams *params, const uint8_t *d
   s.slab.height[1] = s.slab.height[2] = params->iwt_chroma_height;
   SB2H_CHECK (sb2_lowdelay_decode (&p, dev_data, (size_t) length, (size_t) length, &s.slab, d == 2, cx->stream), "sb2_lowdelay_decode");
   stage_out (cx, &s);
-  sb2h_pool_free (dev_data);
   {
     Staged *st[1] = { &s };
     stage_finish (cx, st, 1, 1u);

@@ -192,7 +192,8 @@ frame_iwt_swap (SchroFrame *frame, SchroParams *params, int inverse)
     sin.height[k] = frame->components[k].height;
   }
   sb2h_frame_use (cx, old_region);
-  new_region = schro_memory_domain_alloc (frame->domain, (int) total);
+  new_region = sb2h_spare_take (cx, frame->domain, (int) total);
+  if (!new_region) new_region = schro_memory_domain_alloc (frame->domain, (int) total);
   sb2h_frame_use (cx, new_region);
   sout = sin;
   sout.base = new_region;
@@ -209,7 +210,10 @@ frame_iwt_swap (SchroFrame *frame, SchroParams *params, int inverse)
   for (k = 0; k < 3; k++)
     frame->components[k].data = new_region + sin.offset[k];
   frame->regions[0] = new_region;
-  schro_memory_domain_memfree (frame->domain, old_region);
+  /* the old region becomes this thread's spare for its next transform when only this thread ever used it;
+   * otherwise the domain parks it until every thread's work on it has finished */
+  if (!sb2h_spare_put (cx, frame->domain, old_region, (int) total))
+    schro_memory_domain_memfree (frame->domain, old_region);
   return 1;
 }
 

@@ -17,6 +17,15 @@ DQ = np.load(os.path.join(helpers.GOLDEN_DIR, "dequant.npz"))
 TABLES = (DQ["table_quant"], DQ["table_offset_1_2"], DQ["table_offset_3_8"])
 
 
+@pytest.fixture(params=["staged", "unstaged"], autouse=True)
+def slice_source(request):
+    """Every test runs twice: slices staged in shared memory (default) and read from global memory."""
+    from schroedinger_b200 import lib
+    lib.sb2_lowdelay_force_unstaged(1 if request.param == "unstaged" else 0)
+    yield request.param
+    lib.sb2_lowdelay_force_unstaged(0)
+
+
 def gpu_lowdelay(datas, w, h, depth, nh, nv, num, denom, qm, is_s32):
     """datas: list of per-picture slice buffers (bytes), decoded as one batch."""
     from schroedinger_b200 import device as dev
