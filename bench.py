@@ -43,6 +43,11 @@ def workload_spec(name):
         return dict(width=1920, height=1080, iwt_w=1920, iwt_h=1088, depth_name="s16", filter=1,
                     transform_depth=4, batch=64, full_core=False,
                     label="1080p 4:2:0 8-bit: inverse LeGall 5/3 4-level s16 only (BASELINE configs[0], inverse half)")
+    if name == "picture_core_1080p":
+        return dict(width=1920, height=1080, iwt_w=1920, iwt_h=1088, depth_name="s16", filter=0,
+                    transform_depth=4, batch=64,
+                    label="1080p 4:2:0 8-bit, all stages: inverse DD 9/7 4-level s16 + half-pel upsample + 1/4-pel OBMC "
+                          "render (2 refs, 12x12/8x8; BASELINE configs[3]) + 4-level hierarchical SAD block matching")
     if name == "picture_core_cif":       # tiny, for CPU-side testing of bench.py itself
         return dict(width=352, height=288, iwt_w=352, iwt_h=288, depth_name="s32", filter=6,
                     transform_depth=5, batch=4, label="CIF test workload, all stages")
@@ -850,13 +855,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from schroedinger_b200 import sharding
+
     def all_ranks(value, op):
         """max / min of a float over the ranks (device-side all-reduce; identity for one rank)"""
-        if world == 1:
-            return value
-        t = torch.tensor([value], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.MIN)
-        return float(t.item())
+        if op == "max":
+            return sharding.max_over_ranks(value, device="cuda")
+        return -sharding.max_over_ranks(-value, device="cuda")
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -947,16 +952,27 @@ def run_ours(args):
     if args.workload == "picture_core_2160p" and not args.no_other:
         del st                                        # its slabs go back to the allocator
         torch.cuda.empty_cache()
-        for name in ("wavelet_1080p_dd97", "wavelet_1080p_legall"):
+        for name in ("wavelet_1080p_dd97", "wavelet_1080p_legall", "picture_core_1080p"):
             ospec = workload_spec(name)
             ospec["overlap"] = False
             ost = Stages(ospec, torch, dev)
-            ms = all_ranks(time_device_resident(torch, ost, 20, 3, barrier), "max")
+            nst = 20 if not ospec.get("full_core", True) else 10
+            ms = all_ranks(time_device_resident(torch, ost, nst, 3, barrier), "max")
             alg = sum(s["alg_bytes"] for s in ost.stages)
             other[name] = {"what": ospec["label"], "batch_per_gpu": ospec["batch"],
-                           "value": round(ospec["batch"] * world * 20 / (ms * 1e-3), 1), "unit": "frames/s",
-                           "alg_GBps": round(alg * 20 / (ms * 1e-3) / 1e9, 1)}
+                           "value": round(ospec["batch"] * world * nst / (ms * 1e-3), 1), "unit": "frames/s",
+                           "alg_GBps": round(alg * nst / (ms * 1e-3) / 1e9, 1)}
+            if ospec.get("full_core", True):
+                # per-kernel times of one more step (CUDA events per launch), as for the headline workload
+                lib.sb2_profile_reset()
+                lib.sb2_profile_enable(1)
+                ost.step()
+                torch.cuda.synchronize()
+                lib.sb2_profile_enable(0)
+                other[name]["kernel_ms"] = {k: round(v["ms"], 4) for k, v in sorted(collect_profile(lib).items())}
+                lib.sb2_profile_reset()
             del ost
+            torch.cuda.empty_cache()
         torch.cuda.empty_cache()
         other.update(next_rows(torch, dev, world, all_ranks, barrier))
         torch.cuda.empty_cache()
@@ -969,7 +985,7 @@ def run_ours(args):
 
     peak, peak_src = peaks()
     ms_per_step = elapsed_ms / args.steps
-    value = B * world * args.steps / (elapsed_ms * 1e-3)
+    value = sharding.aggregate_throughput(B * args.steps, elapsed_ms * 1e-3, world)
     # dominant kernel = largest share of device time in the timed region
     dom_tag, dom = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, None)
     # DRAM bytes per launch come from the committed ncu capture of the same command (valid for the

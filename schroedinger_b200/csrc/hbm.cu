@@ -320,7 +320,12 @@ hbm_level_kernel (const HbmArgs A)
       } else if ((lane == 7 || (lane == 8 && i > 0)) && words_up) {
         const unsigned long long *wp = words_up + bi - (lane == 8 ? 1 : 0);
         unsigned long long wv = ld_word (wp);
-        while (!(wv >> 63)) { __nanosleep (POLL_NS); wv = ld_word (wp); }
+        unsigned polls = 0;
+        while (!(wv >> 63)) {
+          __nanosleep (POLL_NS);
+          wv = ld_word (wp);
+          if (++polls > (1u << 25)) __trap ();     // seconds of waiting on a row that has started: an error, not a hang
+        }
         cdx = (int) (short) (wv >> 16); cdy = (int) (short) wv; valid = true;
       }
       __syncwarp ();

@@ -378,10 +378,14 @@ hbm_wave_kernel (const HbmArgs A, const uint2 *__restrict__ stat, int ngroups)
       // critical path, its polling would take issue slots and L2 requests from the producer
       unsigned long long w = nextw;
       unsigned ns = SB2_WAVE_POLL_NS;
+      unsigned polls = 0;
       while (!(w >> 63)) {
         __nanosleep (ns);
         ns = min (ns * 2, 1024u);
         w = ld_word (words_up + t);
+        // a producer holds a smaller ticket and is running: seconds of waiting mean a broken launch, which
+        // must end as an error, not as a hung GPU
+        if (++polls > (1u << 22)) __trap ();
       }
       nextw = t + 1 < cols ? ld_word (words_up + t + 1) : 0ull;
       if (q == 0) {

@@ -284,10 +284,11 @@ rough_hint_kernel (const RoughArgs A)
     // up / up-left: every lane polls the same two words (warp-uniform wait, see hbm_wave.cu)
     if (words_up) {
       unsigned long long wu = ld_word (words_up + bi), wl = bi > 0 ? ld_word (words_up + bi - 1) : (1ull << 63);
-      unsigned ns = 32;
+      unsigned ns = 32, polls = 0;
       while (!((wu & wl) >> 63)) {
         __nanosleep (ns);
         if (ns < 1024) ns <<= 1;
+        if (++polls > (1u << 22)) __trap ();       // seconds of waiting on a row that has started: an error, not a hang
         wu = ld_word (words_up + bi);
         if (bi > 0) wl = ld_word (words_up + bi - 1);
       }

@@ -262,18 +262,31 @@ sb2h_spare_take (Sb2hContext *cx, SchroMemoryDomain *domain, int size)
 int
 sb2h_spare_put (Sb2hContext *cx, SchroMemoryDomain *domain, void *region, int size)
 {
-  int k, i, only_me = 1, kept = 0;
+  unsigned long long users[SB2H_MAX_CTX / 64];
+  cudaStream_t last = NULL;
+  int k, i, c, only_me = 1, kept = 0;
   pthread_mutex_lock (&g_write_mutex);
   k = write_slot (region, 0);
-  if (k >= 0)
-    for (i = 0; i < SB2H_MAX_CTX / 64; i++) {
-      unsigned long long u = g_writes[k].users[i];
-      if (i == cx->slot / 64) u &= ~(1ull << (cx->slot % 64));
-      if (u) only_me = 0;
-    }
-  if (k >= 0 && g_writes[k].stream && g_writes[k].stream != cx->stream) only_me = 0;
+  for (i = 0; i < SB2H_MAX_CTX / 64; i++) users[i] = k >= 0 ? g_writes[k].users[i] : 0;
+  if (k >= 0) last = g_writes[k].stream;
   pthread_mutex_unlock (&g_write_mutex);
+  /* other threads count only while they are alive and have un-waited work (a thread that has waited, or has
+   * gone -- it synchronises its stream on the way out -- cannot have anything in flight on the region) */
+  pthread_mutex_lock (&g_device_mutex);
+  for (c = 0; c < SB2H_MAX_CTX; c++) {
+    if (c == cx->slot || !g_ctx[c] || !g_ctx[c]->dirty) continue;
+    if (((users[c / 64] >> (c % 64)) & 1) || (last && g_ctx[c]->stream == last)) only_me = 0;
+  }
+  pthread_mutex_unlock (&g_device_mutex);
   if (!only_me) return 0;
+  pthread_mutex_lock (&g_write_mutex);
+  if (k >= 0) {
+    /* a new life for the region: only this thread's stream matters from here on */
+    for (i = 0; i < SB2H_MAX_CTX / 64; i++) g_writes[k].users[i] = 0;
+    g_writes[k].users[cx->slot / 64] = 1ull << (cx->slot % 64);
+    if (g_writes[k].stream != cx->stream) g_writes[k].stream = NULL;
+  }
+  pthread_mutex_unlock (&g_write_mutex);
   pthread_mutex_lock (&g_spare_mutex);
   if (!g_spare[cx->slot].ptr) {
     g_spare[cx->slot].domain = domain;

@@ -4,7 +4,7 @@
 # wavelet DRAM bytes, the rough full search).  Outputs under gpurun_out/; tools/summarise_profiles.py
 # turns them into the files committed under profiles/.
 set -x
-R=${1:-r02i}
+R=${1:-r02k}
 ARGS="--steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-other"
 timeout 300 python bench.py $ARGS > gpurun_out/${R}_plain.json 2> gpurun_out/${R}_plain.err || exit 1
 # (the set-up's torch fill / copy kernels -- several hundred since every picture of a batch differs -- are filtered out)

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Per-kernel SASS mnemonic counts of the product library's cubins (no GPU needed): which byte-SIMD /
 # TMA / vector-memory instructions each kernel really contains.  Output: profiles/<R>_sass_excerpts.txt
-R=${1:-r02i}
+R=${1:-r02k}
 OUT=profiles/${R}_sass_excerpts.txt
 {
   echo "SASS mnemonic counts per kernel (cuobjdump -sass build/*.o, sm_100a, static counts; $(nvcc --version | tail -1))"
