@@ -293,3 +293,60 @@ def test_polling_wait_mode_and_thread_sync(cuda, monkeypatch):
         lib.schro_frame_unref(f)
     lib.schro_memory_domain_free(cuda_dom)
     lib.schro_memory_domain_free(pinned)
+
+
+def test_in_place_transforms_with_the_spare_region(cuda):
+    """The per-thread spare region of the in-place transforms (host core: sb2h_spare_take / _put): a worker that
+    transforms its own persistent CUDA-domain frame over and over swaps between two regions without going
+    through the domain; a frame that wanders between workers (uploaded on A, transformed on B, transformed back
+    on C, downloaded on A) must not be taken as anyone's spare while another worker still has work on it."""
+    from schroedinger_b200 import compat, lib
+    nthreads, rounds = 6, 10
+    params, pinned, hosts, wants = _coef_frames(compat, nthreads, 5)
+    cuda_dom = compat.cuda_domain()
+    iw, ih = params.iwt_luma_width, params.iwt_luma_height
+    outs = [compat.frame_new_and_alloc(pinned, compat.FORMAT_S16_420, iw, ih) for _ in range(nthreads)]
+    own = [compat.frame_new_and_alloc(cuda_dom, compat.FORMAT_S16_420, iw, ih) for _ in range(nthreads)]
+    bad = []
+
+    def worker(t):
+        def go():
+            for r in range(rounds):
+                lib.schro_frame_to_gpu(own[t], hosts[t])
+                lib.schro_frame_inverse_iwt_transform(own[t], ctypes.byref(params))
+                if r % 3 == 2:                                   # and back again: forward of the inverse = the input
+                    lib.schro_frame_iwt_transform(own[t], ctypes.byref(params))
+                    lib.schro_frame_inverse_iwt_transform(own[t], ctypes.byref(params))
+                lib.schro_gpuframe_to_cpu(outs[t], own[t])
+                for c in range(3):
+                    if not np.array_equal(compat.frame_plane(outs[t], c), wants[t][c]):
+                        bad.append((t, r, c))
+            lib.schro_b200_thread_release()
+        return go
+
+    _run_threads([worker(t) for t in range(nthreads)])
+    assert not bad, bad[:5]
+    # a wandering frame: every step on another thread, no waits in between except the final download
+    wander = compat.frame_new_and_alloc(cuda_dom, compat.FORMAT_S16_420, iw, ih)
+    steps = [lambda: lib.schro_frame_to_gpu(wander, hosts[0]),
+             lambda: lib.schro_frame_inverse_iwt_transform(wander, ctypes.byref(params)),
+             lambda: lib.schro_frame_iwt_transform(wander, ctypes.byref(params)),
+             lambda: lib.schro_frame_inverse_iwt_transform(wander, ctypes.byref(params)),
+             lambda: lib.schro_gpuframe_to_cpu(outs[0], wander)]
+    for rnd in range(4):
+        for c in range(3):
+            compat.frame_plane(outs[0], c)[...] = 0
+        for k, fn in enumerate(steps):
+            # a fresh thread per step; in the first round the threads leave their contexts registered (with work
+            # possibly still in flight), later rounds release them -- both states of "another thread" for the spare
+            def step(fn=fn, keep=(rnd == 0 and k in (1, 2, 3))):
+                fn()
+                if not keep:
+                    lib.schro_b200_thread_release()
+            _run_threads([step])
+        for c in range(3):
+            assert np.array_equal(compat.frame_plane(outs[0], c), wants[0][c]), (rnd, c)
+    for f in outs + hosts + own + [wander]:
+        lib.schro_frame_unref(f)
+    lib.schro_memory_domain_free(cuda_dom)
+    lib.schro_memory_domain_free(pinned)
