@@ -269,6 +269,8 @@ typedef struct {
   double lambda;
 } sb2_subpel_params;
 size_t sb2_subpel_workspace_bytes (int x_num_blocks, int y_num_blocks, int count);
+/* full 8 x 8 blocks take a word-wide probe path; on != 0 sends every block through the per-pixel path (tests run both) */
+void sb2_subpel_force_generic (int on);
 int sb2_subpel_refine (const sb2_subpel_params *params, const sb2_slab *orig, const sb2_slab *upref,
     int upref_extension, void *field, size_t field_picture_pitch, void *workspace, size_t workspace_bytes,
     void *stream);

@@ -118,6 +118,7 @@ class SubpelParams(ctypes.Structure):
                 ("orig_extension", ctypes.c_int), ("lambda_", ctypes.c_double)]
 
 
+_opt("sb2_subpel_force_generic", None, [ctypes.c_int])
 _opt("sb2_subpel_workspace_bytes", ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int])
 _opt("sb2_subpel_refine", ctypes.c_int, [ctypes.POINTER(SubpelParams), _SP, _SP, ctypes.c_int, ctypes.c_void_p,
                                         ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p])

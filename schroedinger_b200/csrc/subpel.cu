@@ -30,6 +30,7 @@ struct SubpelArgs {
   unsigned *rec;                    // [count][nby * nbx][12]: mask, vector, metric, -, err[8]
   int width, height, orig_ext;
   int xblen, yblen, nbx, nby, ref_index, mvprec, count;
+  int fast;                         // full 8 x 8 blocks take the word-wide probe path (tests turn it off to run both)
   double lambda;
 };
 
@@ -78,20 +79,62 @@ subpel_probe_kernel (const SubpelArgs A)
   const uint8_t *rp = reinterpret_cast<const uint8_t *> (plane_ptr (A.ref, pic, 0));
   const int os = A.orig.stride[0], rs = A.ref.stride[0];
   unsigned mask = 0, my_err = 0;
-  const int npix = w * h;
-#pragma unroll 1
-  for (int k = 0; k < 8; k++) {
+  if (A.fast && w == 8 && h == 8 && A.xblen == 8 && A.yblen == 8 && ((((size_t) op | (size_t) os) & 7) == 0) &&
+      ((((size_t) rp | (size_t) rs) & 3) == 0)) {
+    // full 8 x 8 block: four lanes per probe, two rows of eight pixels each; every sub-pel case is the 4-tap sum
+    // (w00 s00 + w01 s01 + w10 s10 + w11 s11 + 8) >> 4 on packed 16-bit pairs (obmc_common.cuh: the copy is w00 = 16,
+    // the two avgub cases 8 / 8), four pixels per word load, the SAD four bytes at a time
+    const int k = lane >> 2, r0 = (lane & 3) * 2;
     const int px = x + probe_dx (k), py = y + probe_dy (k);
-    if (!(x_min < px) || !(x_max > px + A.xblen - 1) || !(x_min < py) || !(y_max > py + A.yblen - 1)) continue;   // warp-uniform
+    const bool ok = (x_min < px) && (x_max > px + A.xblen - 1) && (x_min < py) && (y_max > py + A.yblen - 1);
     unsigned e = 0;
-    for (int p = lane; p < npix; p += 32) {
-      const int b = p / w, a = p - b * w;
-      e += (unsigned) abs ((int) __ldg (op + (ptrdiff_t) b * os + a) - subpel_sample (rp, rs, A.mvprec, px, py, a, b));
-    }
+    if (ok) {
+      BlkRef br;
+      {
+        int qx = px, qy = py, rx = 0, ry = 0, hx = px, hy = py;
+        const int q = rs >> 2;
+        if (A.mvprec >= 2) {
+          if (A.mvprec == 2) { qx <<= 1; qy <<= 1; }
+          hx = qx >> 2; hy = qy >> 2; rx = qx & 3; ry = qy & 3;
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync (0xffffffffu, e, o);
-    mask |= 1u << k;
-    if (lane == k) my_err = e;
+        for (int t = 0; t < 4; t++) {
+          const int u = hx + (t & 1), v = hy + (t >> 1);
+          br.o[t] = (((v & 1) << 1) | (u & 1)) * q + (v >> 1) * rs + (u >> 1);
+        }
+        const unsigned w00 = (4 - ry) * (4 - rx), w01 = (4 - ry) * rx, w10 = ry * (4 - rx), w11 = ry * rx;
+        br.w = w00 | (w01 << 8) | (w10 << 16) | (w11 << 24);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const uint2 o8 = __ldg (reinterpret_cast<const uint2 *> (op + (ptrdiff_t) (r0 + r) * os));
+        const uint2 a = fetch4x4 (rp, br, (r0 + r) * rs), b = fetch4x4 (rp, br, (r0 + r) * rs + 4);
+        e += __vsadu4 (o8.x, __byte_perm (a.x, a.y, 0x6420)) + __vsadu4 (o8.y, __byte_perm (b.x, b.y, 0x6420));
+      }
+    }
+    e += __shfl_xor_sync (0xffffffffu, e, 1);
+    e += __shfl_xor_sync (0xffffffffu, e, 2);
+    mask = __ballot_sync (0xffffffffu, ok && (lane & 3) == 0);
+    // bit 4k of the ballot -> bit k
+    mask = ((mask >> 0) & 1) | ((mask >> 3) & 2) | ((mask >> 6) & 4) | ((mask >> 9) & 8) | ((mask >> 12) & 16) |
+        ((mask >> 15) & 32) | ((mask >> 18) & 64) | ((mask >> 21) & 128);
+    my_err = __shfl_sync (0xffffffffu, e, (lane & 7) * 4);          // lane k < 8 takes probe k's sum
+  } else {
+    const int npix = w * h;
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) {
+      const int px = x + probe_dx (k), py = y + probe_dy (k);
+      if (!(x_min < px) || !(x_max > px + A.xblen - 1) || !(x_min < py) || !(y_max > py + A.yblen - 1)) continue;   // warp-uniform
+      unsigned e = 0;
+      for (int p = lane; p < npix; p += 32) {
+        const int b = p / w, a = p - b * w;
+        e += (unsigned) abs ((int) __ldg (op + (ptrdiff_t) b * os + a) - subpel_sample (rp, rs, A.mvprec, px, py, a, b));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync (0xffffffffu, e, o);
+      mask |= 1u << k;
+      if (lane == k) my_err = e;
+    }
   }
   if (lane < 8) rec[4 + lane] = my_err;
   if (lane == 0) { rec[0] = mask; rec[1] = (unsigned) (dvx & 0xffff) | ((unsigned) (dvy & 0xffff) << 16); rec[2] = mv->metric; }
@@ -167,6 +210,10 @@ subpel_decide_kernel (const SubpelArgs A)
 
 using namespace sb2;
 
+// tests run the probe kernel both ways: the word-wide path for full 8 x 8 blocks (default) and the per-pixel path
+static int g_subpel_generic = 0;
+extern "C" void sb2_subpel_force_generic (int on) { g_subpel_generic = on ? 1 : 0; }
+
 extern "C" size_t
 sb2_subpel_workspace_bytes (int x_num_blocks, int y_num_blocks, int count)
 {
@@ -215,6 +262,7 @@ sb2_subpel_refine (const sb2_subpel_params *p, const sb2_slab *orig, const sb2_s
   A.ref_index = p->ref_index;
   A.count = orig->count;
   A.lambda = p->lambda;
+  A.fast = g_subpel_generic ? 0 : 1;
   cudaStream_t st = as_stream (stream);
   const long long warps = (long long) A.nbx * A.nby * A.count;
   // algorithmic bytes of a pass: the source picture once, the reference's four phase planes once, the field twice

@@ -16,6 +16,16 @@ ORACLE = helpers.load_oracle()
 SHIM = os.path.join(helpers.ROOT, "oracle", "_ref", "libcompat_shim.so")
 
 
+@pytest.fixture(params=["words", "pixels"], autouse=True)
+def probe_path(request):
+    """Every test runs twice: full 8 x 8 blocks through the word-wide probe path (default) and through the
+    per-pixel path every other block takes (sb2_subpel_force_generic)."""
+    from schroedinger_b200 import lib
+    lib.sb2_subpel_force_generic(1 if request.param == "pixels" else 0)
+    yield request.param
+    lib.sb2_subpel_force_generic(0)
+
+
 def jitter(fields, rng, frac=3):
     for r, f in enumerate(fields):
         idx = rng.choice(len(f), len(f) // frac, replace=False)
