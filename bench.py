@@ -751,7 +751,6 @@ def lowdelay_rows(torch, dev, lib, world, all_ranks, barrier, e2e_threads=12):
         tq.append(f)
         to.append(1 if q == 0 else 2 if q == 1 else (f + 1) // 2)
     coeffs = dev.PictureSlab(dev.FrameLayout.yuv420("s16", w, h), count)
-    pict = dev.PictureSlab(dev.FrameLayout.yuv420("s16", w, h), count)
     out8 = dev.PictureSlab(dev.FrameLayout.yuv420("u8", w, 1080), count)
 
     class OneStage:
@@ -760,8 +759,7 @@ def lowdelay_rows(torch, dev, lib, world, all_ranks, barrier, e2e_threads=12):
 
     def step():
         dev.lowdelay_decode(slices, pic_bytes, coeffs, depth, nh, nv, nbytes, 1, qm, tq, to, picture_pitch=pitch)
-        dev.iwt_inverse(coeffs, pict, 0, depth)
-        dev.frame_convert(pict, out8)
+        dev.iwt_inverse_convert(coeffs, out8, 0, depth)
     lib.sb2_profile_reset()
     ms = all_ranks(time_device_resident(torch, OneStage(step), 10, 3, barrier), "max") / 10
     lib.sb2_profile_enable(1)
@@ -771,10 +769,11 @@ def lowdelay_rows(torch, dev, lib, world, all_ranks, barrier, e2e_threads=12):
     kern = {k: round(v["ms"], 4) for k, v in collect_profile(lib).items()}
     lib.sb2_profile_reset()
     res = {"what": "VC-2 low-delay intra 1080p decode (BASELINE configs[1]): 2040 slices of 190 bytes per picture -> "
-                   "slice decode + dequantise + DC prediction -> inverse DD 9/7 4-level s16 -> 8-bit picture",
+                   "slice decode + dequantise + DC prediction -> inverse DD 9/7 4-level s16 with the conversion to the 8-bit "
+                   "picture fused into its last level",
            "batch_per_gpu": count, "value": round(count * world / (ms * 1e-3), 1), "unit": "frames/s",
            "ms_per_step": round(ms, 4), "kernel_ms": kern, "compressed_bytes_per_picture": pic_bytes}
-    del coeffs, pict, out8
+    del coeffs, out8
     # ---- end to end through the drop-in API: one picture per call chain, a pool of host threads
     params = compat.make_params(w, 1080, wavelet_filter_index=0, transform_depth=depth, iwt_luma_width=w, iwt_luma_height=h)
     params.is_lowdelay = 1
@@ -815,10 +814,10 @@ def lowdelay_rows(torch, dev, lib, world, all_ranks, barrier, e2e_threads=12):
     wall = all_ranks(drv.sb2_e2e_lowdelay_run(ctypes.byref(job), steps), "max")
     drv.sb2_e2e_lowdelay_times(tm)
     res["e2e_call_ms"] = {k: round(tm[i] / (steps * count) * 1e3, 3) for i, k in enumerate(
-        ("decode_lowdelay", "inverse_iwt", "convert", "gpuframe_to_cpu"))}
+        ("decode_lowdelay", "(unused)", "inverse_iwt_combine", "gpuframe_to_cpu"))}
     res["e2e"] = {"value": round(count * world * steps / wall, 1), "unit": "frames/s",
                   "h2d_bytes_per_step": pic_bytes * count, "d2h_bytes_per_step": 1920 * 1080 * 3 // 2 * count,
-                  "api": f"schro_b200_decode_lowdelay_transform_data, schro_frame_inverse_iwt_transform, schro_frame_convert, "
+                  "api": f"schro_b200_decode_lowdelay_transform_data, schro_b200_frame_inverse_iwt_combine, "
                          f"schro_gpuframe_to_cpu; {e2e_threads} host threads (pthreads, bench_native/e2e_driver.c), pinned slices and pictures"}
     for f in bufs + outs:
         lib.schro_frame_unref(f)

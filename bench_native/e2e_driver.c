@@ -229,8 +229,8 @@ sb2_e2e_stop (void)
 
 /* ---- low-delay intra decode (BASELINE configs[1]): compressed slices in, 8-bit pictures out ----
  * A self-contained run: `nthreads` pthreads share the pictures round-robin, each picture is
- *   schro_b200_decode_lowdelay_transform_data -> schro_frame_inverse_iwt_transform -> schro_frame_convert ->
- *   schro_gpuframe_to_cpu
+ *   schro_b200_decode_lowdelay_transform_data -> schro_b200_frame_inverse_iwt_combine (inverse transform with the
+ *   conversion to 8 bits fused into its last level) -> schro_gpuframe_to_cpu
  * on the thread's own CUDA-domain frames.  Returns the wall-clock seconds of `steps` passes over the pictures. */
 typedef struct {
   int nthreads, npictures, slice_bytes;
@@ -264,9 +264,8 @@ ld_worker (void *arg)
     const double t0 = now ();
     schro_b200_decode_lowdelay_transform_data (j->params, j->slices[i], j->slice_bytes, j->coef_dev[w->t]);
     const double t1 = now ();
-    schro_frame_inverse_iwt_transform (j->coef_dev[w->t], j->params);
     const double t2 = now ();
-    schro_frame_convert (j->u8_dev[w->t], j->coef_dev[w->t]);
+    schro_b200_frame_inverse_iwt_combine (j->u8_dev[w->t], j->coef_dev[w->t], j->params, 0);
     const double t3 = now ();
     schro_gpuframe_to_cpu (j->out_host[i], j->u8_dev[w->t]);
     const double t4 = now ();

@@ -103,6 +103,17 @@ int sb2_iwt_inverse (const sb2_slab *src, const sb2_slab *dst, int is_s32,
 /* A level is run by register-chunk kernels where a component's size allows (half-width and
  * half-height multiples of 8 or 16) and by a generic tile kernel otherwise.  on != 0 sends every
  * component to the generic kernel (tests run both on the same input; also SB2_IWT_GENERIC=1). */
+/* Inverse transform with the decoder's combine step fused into its last level: what
+ * schro_decoder_x_combine does for a non-reference intra picture (schroedinger/schrodecoder.c:2054-2061) --
+ * schro_frame_shift_right (frame, shift) when the stream is deeper than the output, then schro_frame_convert
+ * to the 8-bit picture (crop included) -- happens in the epilogue of the level-0 kernel, so the picture leaves
+ * the GPU's registers as u8 and the s16 / s32 plane is never written.  dst_u8: u8 slab of the same component
+ * count, each component no larger than the transform's area.  Needs planes whose half sizes are multiples of 8
+ * (the register-chunk kernels); otherwise SB2_ERR_UNSUPPORTED: call sb2_iwt_inverse + sb2_frame_shift +
+ * sb2_frame_convert.  Workspace as for sb2_iwt_inverse (not in place). */
+int sb2_iwt_inverse_convert (const sb2_slab *src, const sb2_slab *dst_u8, int is_s32, int filter, int depth,
+    int shift, void *workspace, size_t workspace_bytes, void *stream);
+
 void sb2_iwt_force_generic (int on);
 /* on != 0: the inverse transform runs its last two levels (1 and 0) as ONE fused launch -- level 1's
  * output stays in shared memory, never in HBM -- for the filters DD 9/7, DD 13/7 and Daubechies 9/7 on

@@ -451,6 +451,12 @@ void schro_rough_me_heirarchical_scan_hint (SchroRoughME *rme, int shift, int di
 void schro_b200_motion_predict_subpel_deep (SchroParams *params, double lambda, SchroFrame *orig_frame,
     SchroFrame **upsampled_refs, SchroMotionField **subpel_mfs);
 
+/* ---- inverse transform + combine (schroedinger/schrodecoder.c:1809-1853 + 2054-2061) ----
+ * new: schro_frame_inverse_iwt_transform (frame, params) + schro_frame_shift_right (frame, shift) +
+ * schro_frame_convert (output, frame) -- the decoder's path for a non-reference intra picture -- as ONE call;
+ * the 8-bit picture is written by the last wavelet level, the coefficient frame is left as it was. */
+void schro_b200_frame_inverse_iwt_combine (SchroFrame *output, SchroFrame *frame, SchroParams *params, int shift);
+
 /* ---- low-delay slices (schroedinger/schrolowdelay.c:745-761) ----
  * schro_decoder_decode_lowdelay_transform_data (SchroPicture *) with the three things it reads from the picture
  * passed explicitly (compat/schro_lowdelay.c keeps the reference's symbol): picture->params,

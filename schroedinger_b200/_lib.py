@@ -93,6 +93,8 @@ _opt("sb2_obmc_force_kernel", None, [ctypes.c_int])
 _opt("sb2_obmc_last_kernel", ctypes.c_int, [])
 _opt("sb2_hbm_workspace_bytes", ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int])
 _opt("sb2_hbm_force_generic", None, [ctypes.c_int])
+_opt("sb2_iwt_inverse_convert", ctypes.c_int, [_SP, _SP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p])
 _opt("sb2_iwt_force_generic", None, [ctypes.c_int])
 _opt("sb2_iwt_enable_fused", None, [ctypes.c_int])
 _opt("sb2_upsample_force_kernel", None, [ctypes.c_int])

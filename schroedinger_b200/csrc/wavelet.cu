@@ -141,7 +141,29 @@ struct LevelArgs {
   int tile_start[SB2_MAX_COMPONENTS + 1];
   int tiles_x[SB2_MAX_COMPONENTS];
   int ncomp_total;                    // components per picture in the plane sets
+  // fused combine (inverse level 0 only, OUT8 kernels): `dense` is a u8 plane set of out_w x out_h pixels (the
+  // picture: a crop of the transform's area); every sample is shifted right by out_shift with rounding
+  // (schro_frame_shift_right) and converted to 8 bits (schro_frame_convert) on its way out
+  int out_w[SB2_MAX_COMPONENTS], out_h[SB2_MAX_COMPONENTS];
+  int out_shift;
 };
+
+// one sample through schro_frame_shift_right (schroedinger/schroframe.c:1265-1291: add wraps at the sample
+// width) and the s16 / s32 -> u8 converters the library runs (schroorc-dist.c: orc_offsetconvert_u8_s16 /
+// _u8_s32, glue.cu convert_sample) -- the non-reference intra branch of schro_decoder_x_combine
+// (schroedinger/schrodecoder.c:2054-2061)
+template <typename T>
+__device__ __forceinline__ unsigned combine_to_u8 (int v, int shift)
+{
+  if (shift) {
+    const int rnd = (1 << shift) >> 1;
+    v = sizeof (T) == 2 ? ((int) (short) (v + rnd)) >> shift : ((int) ((unsigned) v + (unsigned) rnd)) >> shift;
+  }
+  int t;
+  if (sizeof (T) == 2) t = (int) (short) (v + 128);
+  else t = (int) (short) min (max ((int) ((unsigned) v + 128u), 0), 65535);
+  return (unsigned) min (max (t, 0), 255);
+}
 
 struct TileId { int comp, bx, by; };
 __device__ __forceinline__ TileId level_tile (const LevelArgs &a)
@@ -534,7 +556,7 @@ template <> struct Vec16<int16_t> {
   static constexpr int PAIRS = 4;
 };
 
-template <typename T, int F, int CS>
+template <typename T, int F, int CS, bool OUT8 = false>
 __global__ void __launch_bounds__ (FastGeom<T, F, CS>::NT)
 wavelet_inv_fast_kernel (const LevelArgs a)
 {
@@ -637,10 +659,37 @@ wavelet_inv_fast_kernel (const LevelArgs a)
     const int th = min (2 * THH, h - 2 * ky0);
     const int vpr = tw / G::VEC;                         // 16-byte vectors per row
     const int total = th * vpr;
-    for (int i = tid; i < total; i += G::NT) {
-      const int r = i / vpr, x = i - r * vpr;
-      const int4 v = *reinterpret_cast<const int4 *> (sm + (size_t) r * G::PITCH + x * G::VEC);
-      *reinterpret_cast<int4 *> (dense + (size_t) (2 * ky0 + r) * ds + 2 * kx0 + x * G::VEC) = v;
+    if (OUT8) {
+      // fused combine: the picture leaves as 8-bit samples (a quarter / half of the bytes), cropped to its size
+      uint8_t *out = reinterpret_cast<uint8_t *> (plane_ptr (a.dense, pic, comp));
+      const size_t os = (size_t) a.dense.stride[comp];
+      const int ow = a.out_w[comp], oh = a.out_h[comp];
+      for (int i = tid; i < total; i += G::NT) {
+        const int r = i / vpr, x = i - r * vpr;
+        const int py = 2 * ky0 + r, px = 2 * kx0 + x * G::VEC;
+        if (py >= oh || px >= ow) continue;
+        int v[G::VEC];
+        Vec16<T>::load (sm + (size_t) r * G::PITCH + x * G::VEC, v);
+        unsigned lo = 0, hi = 0;
+#pragma unroll
+        for (int k = 0; k < G::VEC; k++) {
+          const unsigned b = combine_to_u8<T> (v[k], a.out_shift);
+          if (k < 4) lo |= b << (8 * k); else hi |= b << (8 * (k - 4));
+        }
+        uint8_t *o = out + (size_t) py * os + px;
+        if (px + G::VEC <= ow && (((size_t) o) & (G::VEC - 1)) == 0) {
+          if (G::VEC == 4) *reinterpret_cast<unsigned *> (o) = lo;
+          else *reinterpret_cast<uint2 *> (o) = make_uint2 (lo, hi);
+        } else {
+          for (int k = 0; k < G::VEC && px + k < ow; k++) o[k] = (uint8_t) ((k < 4 ? lo >> (8 * k) : hi >> (8 * (k - 4))) & 0xff);
+        }
+      }
+    } else {
+      for (int i = tid; i < total; i += G::NT) {
+        const int r = i / vpr, x = i - r * vpr;
+        const int4 v = *reinterpret_cast<const int4 *> (sm + (size_t) r * G::PITCH + x * G::VEC);
+        *reinterpret_cast<int4 *> (dense + (size_t) (2 * ky0 + r) * ds + 2 * kx0 + x * G::VEC) = v;
+      }
     }
   }
 }
@@ -1097,6 +1146,63 @@ static int launch_fused2 (const LevelArgs &a0, const PlaneSet &bands1, const Pla
   return set_error (SB2_ERR_UNSUPPORTED, "no fused kernel for filter %d", F);
 }
 
+// level 0 of the inverse with the combine fused in (u8 out); every component must take the register-chunk kernel
+template <typename T, int F>
+static int launch_inverse_level0_u8 (LevelArgs a, int count, cudaStream_t stream)
+{
+  // the chunk choice does not look at `dense` alignment here (the u8 stores check their own), only at the sizes
+  int sel[3][SB2_MAX_COMPONENTS], nsel[3] = { 0, 0, 0 };
+  for (int c = 0; c < a.ncomp; c++) {
+    const int n = a.w[c] >> 1, m = a.h[c] >> 1;
+    const int k = (n % 16 == 0 && m % 16 == 0 && filter_halo (F) <= 4) ? 1 : (n % 8 == 0 && m % 8 == 0) ? 2 : 0;
+    if (!k) return set_error (SB2_ERR_UNSUPPORTED, "fused inverse + convert needs planes whose half sizes are multiples of 8");
+    sel[k][nsel[k]++] = c;
+  }
+  a.ncomp_total = a.ncomp;
+  for (int k = 1; k < 3; k++) {
+    if (!nsel[k]) continue;
+    LevelArgs b = a;
+    const dim3 grid = level_grid (b, sel[k], nsel[k], count);
+    char tag[48] = "";
+    double bytes = 0;
+    if (profiling ()) {
+      snprintf (tag, sizeof (tag), "wavelet_inv_%s_f%d_w%d_u8", sizeof (T) == 4 ? "s32" : "s16", F, a.w[sel[k][0]]);
+      for (int i = 0; i < nsel[k]; i++) bytes += (double) a.w[sel[k][i]] * a.h[sel[k][i]] * (sizeof (T) + 1) * count;
+    }
+    cudaError_t e;
+    if (k == 1) {
+      typedef FastGeom<T, F, 16> FG;
+      e = cudaFuncSetAttribute (wavelet_inv_fast_kernel<T, F, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FG::SMEM);
+      if (e != cudaSuccess) return check_cuda (e, "cudaFuncSetAttribute(wavelet u8)");
+      LaunchScope scope (tag, bytes, stream);
+      wavelet_inv_fast_kernel<T, F, 16, true><<<grid, FG::NT, FG::SMEM, stream>>> (b);
+    } else {
+      typedef FastGeom<T, F, 8> FG;
+      e = cudaFuncSetAttribute (wavelet_inv_fast_kernel<T, F, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FG::SMEM);
+      if (e != cudaSuccess) return check_cuda (e, "cudaFuncSetAttribute(wavelet u8)");
+      LaunchScope scope (tag, bytes, stream);
+      wavelet_inv_fast_kernel<T, F, 8, true><<<grid, FG::NT, FG::SMEM, stream>>> (b);
+    }
+    e = cudaGetLastError ();
+    if (e != cudaSuccess) return check_cuda (e, "wavelet_inv_fast_kernel<u8> launch");
+  }
+  return SB2_OK;
+}
+
+template <typename T>
+static int launch_inverse_level0_u8_f (int filter, const LevelArgs &a, int count, cudaStream_t s)
+{
+  switch (filter) {
+    case 0: return launch_inverse_level0_u8<T, 0> (a, count, s);
+    case 1: return launch_inverse_level0_u8<T, 1> (a, count, s);
+    case 2: return launch_inverse_level0_u8<T, 2> (a, count, s);
+    case 3: return launch_inverse_level0_u8<T, 3> (a, count, s);
+    case 4: return launch_inverse_level0_u8<T, 4> (a, count, s);
+    case 5: return launch_inverse_level0_u8<T, 5> (a, count, s);
+    default: return launch_inverse_level0_u8<T, 6> (a, count, s);
+  }
+}
+
 template <typename T, int F, int CS>
 static int launch_fast_forward (LevelArgs a, const int *comps, int nsel, int count, cudaStream_t stream,
     const char *tag, double bytes)
@@ -1423,7 +1529,67 @@ static int iwt_run (bool inv, const sb2_slab *src, const sb2_slab *dst, int is_s
   return SB2_OK;
 }
 
+// inverse transform with the combine fused into its last level: levels depth-1 .. 1 as iwt_run does them, level 0
+// through the OUT8 kernels straight into the u8 picture
+static int iwt_inverse_convert_run (const sb2_slab *src, const sb2_slab *dst, int is_s32, int filter, int depth, int shift,
+    void *workspace, size_t workspace_bytes, void *stream)
+{
+  const int bpp = is_s32 ? 4 : 2;
+  if (!src || !dst || !src->base || !dst->base) return set_error (SB2_ERR_ARG, "null slab");
+  if (src->ncomp < 1 || src->ncomp > SB2_MAX_COMPONENTS || src->ncomp != dst->ncomp || src->count != dst->count || src->count < 1 ||
+      src->count > 65535)
+    return set_error (SB2_ERR_ARG, "sb2_iwt_inverse_convert: slab shapes differ");
+  if (depth < 1 || depth > 8 || filter < 0 || filter > 6 || shift < 0 || shift > (is_s32 ? 31 : 15))
+    return set_error (SB2_ERR_ARG, "sb2_iwt_inverse_convert: depth %d / filter %d / shift %d", depth, filter, shift);
+  for (int c = 0; c < src->ncomp; c++) {
+    if (src->width[c] <= 0 || src->height[c] <= 0 || (src->width[c] & ((1 << depth) - 1)) || (src->height[c] & ((1 << depth) - 1)))
+      return set_error (SB2_ERR_ARG, "component %d size %dx%d is not a multiple of 1<<%d", c, src->width[c], src->height[c], depth);
+    if (dst->width[c] < 1 || dst->height[c] < 1 || dst->width[c] > src->width[c] || dst->height[c] > src->height[c])
+      return set_error (SB2_ERR_ARG, "component %d: the picture (%dx%d) must lie inside the transform's area (%dx%d)", c,
+          dst->width[c], dst->height[c], src->width[c], src->height[c]);
+    if ((src->stride[c] % bpp) || (src->offset[c] % bpp)) return set_error (SB2_ERR_ARG, "component %d stride/offset not a multiple of the sample size", c);
+  }
+  const WsLayout L = ws_layout (src, bpp, depth, 0);
+  const size_t need = L.pic_pitch * (size_t) src->count;
+  if (need > 0 && (!workspace || workspace_bytes < need))
+    return set_error (SB2_ERR_WORKSPACE, "wavelet workspace too small: need %zu bytes, have %zu", need, workspace ? workspace_bytes : (size_t) 0);
+  cudaStream_t st = as_stream (stream);
+  const PlaneSet S = planeset_from_slab (src);
+  const PlaneSet T1 = ws_planeset (workspace, L, L.off_t1, L.stride_t1);
+  const PlaneSet T0 = ws_planeset (workspace, L, L.off_t0, L.stride_t0);
+  LevelArgs a;
+  a.ncomp = src->ncomp;
+  a.out_shift = 0;
+  for (int c = 0; c < SB2_MAX_COMPONENTS; c++) a.w[c] = a.h[c] = a.out_w[c] = a.out_h[c] = 0;
+  for (int l = depth - 1; l >= 1; l--) {
+    for (int c = 0; c < src->ncomp; c++) { a.w[c] = src->width[c] >> l; a.h[c] = src->height[c] >> l; }
+    a.ll = (l == depth - 1) ? scaled (S, l + 1) : (((l + 1) & 1) ? T1 : T0);
+    a.bands = scaled (S, l);
+    a.dense = (l & 1) ? T1 : T0;
+    const int rc = launch_level_any (true, is_s32, filter, a, src->count, st);
+    if (rc) return rc;
+  }
+  for (int c = 0; c < src->ncomp; c++) {
+    a.w[c] = src->width[c]; a.h[c] = src->height[c];
+    a.out_w[c] = dst->width[c]; a.out_h[c] = dst->height[c];
+  }
+  a.ncomp = src->ncomp;
+  a.ll = depth == 1 ? scaled (S, 1) : T1;
+  a.bands = S;
+  a.dense = planeset_from_slab (dst);
+  a.out_shift = shift;
+  return is_s32 ? launch_inverse_level0_u8_f<int32_t> (filter, a, src->count, st)
+                : launch_inverse_level0_u8_f<int16_t> (filter, a, src->count, st);
+}
+
 }  // namespace sb2
+
+extern "C" int
+sb2_iwt_inverse_convert (const sb2_slab *src, const sb2_slab *dst_u8, int is_s32, int filter, int depth, int shift,
+    void *workspace, size_t workspace_bytes, void *stream)
+{
+  return sb2::iwt_inverse_convert_run (src, dst_u8, is_s32, filter, depth, shift, workspace, workspace_bytes, stream);
+}
 
 extern "C" size_t
 sb2_iwt_workspace_bytes (const sb2_slab *slab, int is_s32, int depth, int in_place)

@@ -462,3 +462,13 @@ def lowdelay_decode(slices, picture_bytes, coeffs, depth, n_horiz_slices, n_vert
                                   ctypes.c_size_t(picture_pitch if picture_pitch is not None else picture_bytes),
                                   ctypes.byref(coeffs.slab), 1 if coeffs.layout.depth == "s32" else 0, _stream_ptr(stream)),
           "sb2_lowdelay_decode")
+
+
+def iwt_inverse_convert(src, dst_u8, filter_index, transform_depth, shift=0, workspace=None, stream=None):
+    """Inverse transform with shift + convert to 8 bits fused into its last level (sb2_iwt_inverse_convert)."""
+    require_cuda()
+    is_s32 = 1 if src.layout.depth == "s32" else 0
+    ws = workspace or _default_ws
+    ptr, size = ws.get(lib.sb2_iwt_workspace_bytes(ctypes.byref(src.slab), is_s32, transform_depth, 0))
+    check(lib.sb2_iwt_inverse_convert(ctypes.byref(src.slab), ctypes.byref(dst_u8.slab), is_s32, filter_index,
+                                      transform_depth, shift, ptr, size, _stream_ptr(stream)), "sb2_iwt_inverse_convert")

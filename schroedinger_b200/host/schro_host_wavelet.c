@@ -246,6 +246,87 @@ schro_frame_inverse_iwt_transform (SchroFrame *frame, SchroParams *params)
   frame_iwt (frame, params, 1);
 }
 
+/* ---- inverse transform + combine in one pass -----------------------------
+ * What the decoder does with a non-reference intra picture after the inverse transform
+ * (schro_decoder_x_combine, schroedinger/schrodecoder.c:2054-2061): schro_frame_shift_right (frame, shift)
+ * when the stream is deeper than the output, then schro_frame_convert (output, frame).  Here the three
+ * steps are one call and -- for planes the register-chunk kernels cover -- one pass: the last wavelet level
+ * writes the 8-bit picture directly.  `frame` (the coefficients) is left untouched; `output` is u8 of the
+ * same chroma format, no larger than the transform's area.  Frames may be host or CUDA-domain memory. */
+void
+schro_b200_frame_inverse_iwt_combine (SchroFrame *output, SchroFrame *frame, SchroParams *params, int shift)
+{
+  Sb2hContext *cx = sb2h_context ();
+  const int is_s32 = depth_is_s32 (frame->format);
+  sb2_slab sin, sout;
+  size_t tin = 0, tout = 0, ws_bytes;
+  char *rin = frame->regions[0], *rout = output->regions[0], *din, *dout;
+  void *ws;
+  int k, rc, host_in, host_out;
+  SB2H_ASSERT (output && frame && params && rin && rout);
+  if (SCHRO_FRAME_FORMAT_DEPTH (output->format) != SCHRO_FRAME_FORMAT_DEPTH_U8 ||
+      SCHRO_FRAME_FORMAT_DEPTH (frame->format) == SCHRO_FRAME_FORMAT_DEPTH_U8 || (output->format & 3) != (frame->format & 3))
+    sb2h_fatal (__func__, "needs an s16 / s32 coefficient frame and a u8 output of the same chroma format (0x%x, 0x%x)",
+        (unsigned) frame->format, (unsigned) output->format);
+  for (k = 0; k < 3; k++) { tin += (size_t) frame->components[k].length; tout += (size_t) output->components[k].length; }
+  host_in = sb2h_mem_kind (rin) != SB2H_MEM_DEVICE;
+  host_out = sb2h_mem_kind (rout) != SB2H_MEM_DEVICE;
+  if (host_in) {
+    din = sb2h_dev_buffer (cx, SB2H_BUF_IN, tin + 256);
+    SB2H_CUDA (cudaMemcpyAsync (din, rin, tin, cudaMemcpyDefault, cx->stream));
+  } else {
+    din = rin;
+    sb2h_frame_use (cx, rin);
+  }
+  if (host_out) {
+    dout = sb2h_dev_buffer (cx, SB2H_BUF_OUT, tout + 256);
+    SB2H_CUDA (cudaMemcpyAsync (dout, rout, tout, cudaMemcpyDefault, cx->stream));     /* keeps borders / padding as they are */
+  } else {
+    dout = rout;
+    sb2h_frame_use (cx, rout);
+  }
+  memset (&sin, 0, sizeof (sin));
+  memset (&sout, 0, sizeof (sout));
+  sin.base = din; sin.picture_pitch = tin; sin.count = 1; sin.ncomp = 3;
+  sout.base = dout; sout.picture_pitch = tout; sout.count = 1; sout.ncomp = 3;
+  for (k = 0; k < 3; k++) {
+    sin.offset[k] = (size_t) ((char *) frame->components[k].data - rin);
+    sin.stride[k] = frame->components[k].stride;
+    sin.width[k] = k ? params->iwt_chroma_width : params->iwt_luma_width;
+    sin.height[k] = k ? params->iwt_chroma_height : params->iwt_luma_height;
+    sout.offset[k] = (size_t) ((char *) output->components[k].data - rout);
+    sout.stride[k] = output->components[k].stride;
+    sout.width[k] = output->components[k].width < sin.width[k] ? output->components[k].width : sin.width[k];
+    sout.height[k] = output->components[k].height < sin.height[k] ? output->components[k].height : sin.height[k];
+  }
+  ws_bytes = sb2_iwt_workspace_bytes (&sin, is_s32, params->transform_depth, 0);
+  ws = sb2h_dev_buffer (cx, SB2H_BUF_WS, ws_bytes);
+  rc = sb2_iwt_inverse_convert (&sin, &sout, is_s32, params->wavelet_filter_index, params->transform_depth, shift, ws, ws_bytes,
+      cx->stream);
+  if (rc == SB2_ERR_UNSUPPORTED) {
+    /* shapes the fused kernel does not cover: the three steps one after the other, into a scratch plane set */
+    sb2_slab stmp = sin;
+    const size_t full = sb2_iwt_workspace_bytes (&sin, is_s32, params->transform_depth, 0);
+    char *tmp = sb2h_dev_buffer (cx, SB2H_BUF_AUX1, tin + 256);
+    (void) full;
+    stmp.base = tmp;
+    SB2H_CHECK (sb2_iwt_inverse (&sin, &stmp, is_s32, params->wavelet_filter_index, params->transform_depth, ws, ws_bytes,
+            cx->stream), "sb2_iwt_inverse");
+    if (shift) SB2H_CHECK (sb2_frame_shift (&stmp, is_s32 ? 2 : 1, shift, 1, cx->stream), "sb2_frame_shift");
+    SB2H_CHECK (sb2_frame_convert (&stmp, is_s32 ? 2 : 1, &sout, 0, cx->stream), "sb2_frame_convert");
+  } else {
+    SB2H_CHECK (rc, "sb2_iwt_inverse_convert");
+  }
+  if (host_out) {
+    SB2H_CUDA (cudaMemcpyAsync (rout, dout, tout, cudaMemcpyDefault, cx->stream));
+    sb2h_sync (cx);
+  } else {
+    sb2h_frame_wrote (cx, rout);
+    cx->dirty = 1;
+    if (host_in) sb2h_sync (cx);          /* the caller may reuse its host coefficients */
+  }
+}
+
 /* ---- dequantisation on the device -------------------------------
  * New entry point (the reference dequantises inside its entropy decoder, codeblock by codeblock:
  * schrodecoder.c:3395-3448): the frame holds the QUANTISED coefficients in the in-place subband
