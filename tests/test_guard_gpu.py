@@ -155,3 +155,82 @@ def test_obmc_stays_inside(cuda, add):
     check(res, "OBMC residual"); check(acc, "OBMC accumulator"); check(out, "OBMC output")
     for r, b in zip(refs, before):
         assert torch.equal(r.whole, b), "OBMC wrote into a reference frame"
+
+
+def test_second_round_kernels_stay_inside_their_buffers(cuda):
+    """The rows added in round 2: low-delay slice decoder, fused inverse + convert, fused two-level inverse, rough
+    search, sub-pel refinement -- slabs between guard zones, motion fields inside patterned tensors."""
+    import torch
+    from schroedinger_b200 import device as dev, lib
+    rng = np.random.default_rng(2)
+    # low-delay slices -> coefficient slab; fused inverse + convert -> u8 slab with a border
+    w, h, depth, nh, nv, nbytes = 256, 128, 3, 8, 4, 70
+    dq = np.load(__import__("os").path.join(helpers.GOLDEN_DIR, "dequant.npz"))
+    data = rng.integers(0, 256, size=2 * nh * nv * nbytes, dtype=np.uint8)
+    for k in range(2 * nh * nv):                           # declared luma lengths inside the slice
+        data[k * nbytes + 1] &= 0x03
+    slices = torch.from_numpy(data).cuda()
+    for name in ("s16", "s32"):
+        coeffs = guarded(dev, torch, dev.FrameLayout.yuv420(name, w, h), 2)
+        dev.lowdelay_decode(slices, nh * nv * nbytes, coeffs, depth, nh, nv, nbytes, 1, [0] * (1 + 3 * depth),
+                            dq["table_quant"], dq["table_offset_1_2"])
+        pic = guarded(dev, torch, dev.FrameLayout.yuv420("u8", w - 6, h - 10, 16), 2)
+        dev.iwt_inverse_convert(coeffs, pic, 0, depth, 1)
+        out = guarded(dev, torch, dev.FrameLayout.yuv420(name, w, h), 2)
+        lib.sb2_iwt_enable_fused(1)
+        try:
+            big = guarded(dev, torch, dev.FrameLayout.yuv420(name, 640, 384), 1)
+            big2 = guarded(dev, torch, dev.FrameLayout.yuv420(name, 640, 384), 1)
+            dev.iwt_inverse(big, big2, 6, 2)
+        finally:
+            lib.sb2_iwt_enable_fused(0)
+        dev.iwt_inverse(coeffs, out, 0, depth)
+        torch.cuda.synchronize()
+        for s_, what in ((coeffs, "lowdelay"), (out, "inverse"), (big2, "fused two-level inverse")):
+            check(s_, what + " " + name)
+        # the u8 picture: only picture pixels may change (its border is not written either)
+        whole = pic.whole.cpu().numpy()
+        assert (whole[:GUARD] == PAT).all() and (whole[-GUARD:] == PAT).all(), "inverse + convert wrote outside the slab"
+        L = pic.layout
+        m = np.zeros(L.pitch * 2 + 256, bool)
+        for p in range(2):
+            for c, (pw, ph) in enumerate(L.comp_sizes):
+                for y in range(ph):
+                    a = p * L.pitch + L.offset[c] + y * L.stride[c]
+                    m[a:a + pw] = True
+        assert (whole[GUARD:-GUARD][~m] == PAT).all(), "inverse + convert wrote outside the picture"
+    # rough search + sub-pel refinement: the fields
+    w, h, levels, count = 200, 104, 2, 2                   # ragged: partial blocks, blocks outside the coarse levels
+    ps, pr = dev.Pyramid(w, h, count, levels, 8), dev.Pyramid(w, h, count, levels, 8)
+    for p in range(count):
+        s, r = helpers.panning_pair(w, h, rng, (3, -2))
+        for c in range(3):
+            ps.slabs[0].upload(p, c, s[c])
+            pr.slabs[0].upload(p, c, r[c])
+    ps.build()
+    pr.build()
+    nbx, nby = helpers.hbm_block_counts(w, h, 8, 8)
+    n = nbx * nby * 20 * count
+    prm = dev.HbmParams(8, 8, nbx, nby, 1, 0, 1, 1)
+
+    def field():
+        t = torch.full((GUARD + n + GUARD,), PAT, dtype=torch.uint8, device="cuda")
+        return t, t[GUARD:GUARD + n]
+    wholes, fields = [None], [None]
+    for _ in range(levels):
+        t, f = field()
+        wholes.append(t)
+        fields.append(f)
+    dev.rough_scan(prm, ps, pr, 12, 4, fields=fields)
+    up = dev.PictureSlab(dev.FrameLayout.yuv420("u8", w, h, 32, True), count)
+    for p in range(count):
+        for c in range(3):
+            up.upload(p, c, pr.slabs[0].download(p, c))
+    dev.edgeextend_upsample(up)
+    t0, f0 = field()
+    f0.zero_()
+    dev.subpel_refine(ps.slabs[0], up, f0, 8, 8, nbx, nby, 3, 1, 0.2)
+    torch.cuda.synchronize()
+    for t in wholes[1:] + [t0]:
+        a = t.cpu().numpy()
+        assert (a[:GUARD] == PAT).all() and (a[-GUARD:] == PAT).all(), "a motion-field kernel wrote outside its field"
