@@ -195,6 +195,17 @@ int sb2_obmc_render (const sb2_obmc_params *params, const void *motion_vectors,
     size_t mv_picture_pitch, const sb2_slab *ref0, const sb2_slab *ref1, const sb2_slab *acc,
     const sb2_slab *residual, int residual_is_s32, int add, const sb2_slab *out, void *stream);
 
+/* schro_motion_render_ref (schroedinger/schromotionref.c:245-330): the per-pixel renderer the reference
+ * switches to whenever the picture has global motion (schroedinger/schromotion.c:113-121).  Same arguments as
+ * sb2_obmc_render, plus global_motion: 2 x 10 ints (SchroGlobalMotion's fields b0 b1 a_exp a00 a01 a10 a11 c_exp c0
+ * c1 for each reference; NULL: all zero) used by the blocks whose using_global bit is set.  Semantics differ
+ * from the block renderer where the reference's do: acc receives clamp (prediction, 0, 255) - 128 and the
+ * prediction is clamped before the residual (s16 only) is added or subtracted.  Blocks at most twice their
+ * separation (a pixel is covered by at most four). */
+int sb2_obmc_render_ref (const sb2_obmc_params *params, const int *global_motion, const void *motion_vectors,
+    size_t mv_picture_pitch, const sb2_slab *ref0, const sb2_slab *ref1, const sb2_slab *acc,
+    const sb2_slab *residual, int add, const sb2_slab *out, void *stream);
+
 /* Three kernels implement the renderer: 1 = one block per warp pass out of TMA-staged reference regions
  * (blocks of at most 32 row x 8-pixel lanes, 32-pixel borders: every Dirac preset), 2 = block-major
  * scatter out of global memory with shared-memory atomics (the default where it applies: measured

@@ -347,6 +347,9 @@ void schro_motion_render (SchroMotion *motion, SchroFrame *dest,
     SchroFrame *addframe, int add, SchroFrame *output_frame);
 void schro_motion_render_u8 (SchroMotion *motion, SchroFrame *dest,
     SchroFrame *addframe, int add, SchroFrame *output_frame);
+/* schroedinger/schromotionref.c:245: the per-pixel renderer; schro_motion_render takes it when params->have_global_motion */
+void schro_motion_render_ref (SchroMotion *motion, SchroFrame *dest, SchroFrame *addframe, int add,
+    SchroFrame *output_frame);
 void schro_motion_init_obmc_weight (SchroMotion *motion);
 
 /* schroedinger/schrometric.h:16-53 */

@@ -100,6 +100,15 @@ void oracle_obmc_render (const OracleObmcParams *p, const OracleMotionVector *mv
     void *residual, int res_stride, int res_is_s32,
     int add, uint8_t *out, int out_stride);
 
+/* One component of schro_motion_render_ref (schroedinger/schromotionref.c:245-330), the per-pixel renderer
+ * the reference switches to when global motion is on (schroedinger/schromotion.c:113-121).  global_motion:
+ * 2 x 10 ints (b0 b1 a_exp a00 a01 a10 a11 c_exp c0 c1 per reference) used by blocks flagged using_global.
+ * width / height: the component's size; strides of acc / residual in SAMPLES.  acc (may be NULL) receives
+ * clamp (prediction) - 128; add != 0: out = clamp (residual + that + 128), else residual -= that. */
+void oracle_obmc_render_ref (const OracleObmcParams *p, const int *global_motion, const OracleMotionVector *mvs,
+    const uint8_t *ref0, const uint8_t *ref1, int rstride, int width, int height, int16_t *acc, int acc_stride,
+    int16_t *residual, int res_stride, int add, uint8_t *out, int out_stride);
+
 /* ---- SAD / hierarchical block matching (oracle_hbm.c) ---- */
 /* schro_metric_absdiff_u8 (schroedinger/schrometric.c:10-29) */
 uint32_t oracle_sad_u8 (const uint8_t *a, int a_stride, const uint8_t *b,

@@ -220,3 +220,98 @@ oracle_obmc_render (const OracleObmcParams *p, const OracleMotionVector *mvs,
     }
   }
 }
+
+/* ---- the reference's per-pixel renderer, which it uses whenever global motion is on ----------------
+ * schro_motion_render_ref (schroedinger/schromotionref.c:245-330): a pixel is the rounded sum of the (at
+ * most four) blocks covering it, each block's pixel weighted by the OBMC ramp (:175-236: picture-edge
+ * pixels take weight 8), fetched pixel by pixel with clamped coordinates
+ * (schro_upsampled_frame_get_pixel_precN, schroedinger/schroframe.c:2033-2046, 2124-2143, 2209-2265); a
+ * block flagged using_global takes its vector from the picture's global-motion model at that pixel
+ * (:22-41).  The prediction is clamped to 0..255 BEFORE the residual is added, unlike the block renderer. */
+static int
+pixel_prec1 (const uint8_t *ref, int rstride, int w, int h, int x, int y)
+{
+  x = clampi (x, 0, w * 2 - 2);
+  y = clampi (y, 0, h * 2 - 2);
+  return halfpel (ref, rstride, x, y, 0, 0);
+}
+
+static int
+pixel_precn (const uint8_t *ref, int rstride, int w, int h, int x, int y, int prec)
+{
+  int hx, hy, rx, ry, v;
+  if (prec == 0) return ref[(ptrdiff_t) clampi (y, 0, h - 1) * rstride + clampi (x, 0, w - 1)];
+  if (prec == 1) return pixel_prec1 (ref, rstride, w, h, x, y);
+  if (prec == 2) { x <<= 1; y <<= 1; }
+  hx = x >> 2; hy = y >> 2; rx = x & 3; ry = y & 3;
+  v = (4 - ry) * (4 - rx) * pixel_prec1 (ref, rstride, w, h, hx, hy)
+      + (4 - ry) * rx * pixel_prec1 (ref, rstride, w, h, hx + 1, hy)
+      + ry * (4 - rx) * pixel_prec1 (ref, rstride, w, h, hx, hy + 1)
+      + ry * rx * pixel_prec1 (ref, rstride, w, h, hx + 1, hy + 1);
+  return (v + 8) >> 4;
+}
+
+static void
+global_vector (const int *gm, int x, int y, int *dx, int *dy)
+{
+  /* gm: b0 b1 a_exp a00 a01 a10 a11 c_exp c0 c1 (SchroGlobalMotion, schroedinger/schroparams.h:18-29) */
+  const int alpha = gm[2], beta = gm[7];
+  const int scale = (1 << beta) - (gm[8] * x + gm[9] * y);
+  *dx = (scale * (gm[3] * x + gm[4] * y + (1 << alpha) * gm[0])) >> (alpha + beta);
+  *dy = (scale * (gm[5] * x + gm[6] * y + (1 << alpha) * gm[1])) >> (alpha + beta);
+}
+
+void
+oracle_obmc_render_ref (const OracleObmcParams *p, const int *global_motion, const OracleMotionVector *mvs,
+    const uint8_t *ref0, const uint8_t *ref1, int rstride, int width, int height, int16_t *acc, int acc_stride,
+    int16_t *residual, int res_stride, int add, uint8_t *out, int out_stride)
+{
+  const int xoff = (p->xblen - p->xbsep) / 2, yoff = (p->yblen - p->ybsep) / 2;
+  const int W = p->xbsep * p->x_num_blocks, H = p->ybsep * p->y_num_blocks;
+  int x, y, di, dj;
+  for (y = 0; y < height; y++)
+    for (x = 0; x < width; x++) {
+      const int i0 = (x + xoff) / p->xbsep - 1, j0 = (y + yoff) / p->ybsep - 1;
+      int value = 0, line;
+      for (dj = 0; dj < 2; dj++)
+        for (di = 0; di < 2; di++) {
+          const int i = i0 + di, j = j0 + dj;
+          int xmin, ymin, xmax, ymax, wx, wy, v = 0, mode;
+          const OracleMotionVector *mv;
+          if (i < 0 || j < 0 || i >= p->x_num_blocks || j >= p->y_num_blocks) continue;
+          xmin = i * p->xbsep - xoff; ymin = j * p->ybsep - yoff;
+          xmax = (i + 1) * p->xbsep + xoff; ymax = (j + 1) * p->ybsep + yoff;
+          if (x < xmin || y < ymin || x >= xmax || y >= ymax) continue;
+          if (xoff == 0 || x < xoff || x >= W - xoff) wx = 8;
+          else if (x - xmin < 2 * xoff) wx = get_ramp (x - xmin, xoff);
+          else if (xmax - 1 - x < 2 * xoff) wx = get_ramp (xmax - 1 - x, xoff);
+          else wx = 8;
+          if (yoff == 0 || y < yoff || y >= H - yoff) wy = 8;
+          else if (y - ymin < 2 * yoff) wy = get_ramp (y - ymin, yoff);
+          else if (ymax - 1 - y < 2 * yoff) wy = get_ramp (ymax - 1 - y, yoff);
+          else wy = 8;
+          mv = &mvs[j * p->x_num_blocks + i];
+          mode = mv->flags & 3;
+          if (mode == 0) v = mv->v[p->comp] + 128;
+          else {
+            int d[2][2], r, s[2] = { 0, 0 };
+            for (r = 0; r < 2; r++) {
+              if (!((mode >> r) & 1)) continue;
+              if ((mv->flags >> 2) & 1) global_vector (global_motion + 10 * r, x, y, &d[r][0], &d[r][1]);
+              else { d[r][0] = mv->v[r]; d[r][1] = mv->v[2 + r]; }
+              d[r][0] >>= p->h_shift; d[r][1] >>= p->v_shift;
+              s[r] = pixel_precn (r ? ref1 : ref0, rstride, width, height, (x << p->mv_precision) + d[r][0],
+                  (y << p->mv_precision) + d[r][1], p->mv_precision);
+            }
+            if (mode == 3) v = p->weight1 * s[0] + p->weight2 * s[1];
+            else v = (p->weight1 + p->weight2) * s[mode == 1 ? 0 : 1];
+            v = (v + (1 << (p->weight_bits - 1))) >> p->weight_bits;
+          }
+          value += v * wx * wy;
+        }
+      line = clampi ((value + 32) >> 6, 0, 255) - 128;
+      if (acc) acc[(ptrdiff_t) y * acc_stride + x] = (int16_t) line;
+      if (add) out[(ptrdiff_t) y * out_stride + x] = (uint8_t) clampi (residual[(ptrdiff_t) y * res_stride + x] + line + 128, 0, 255);
+      else residual[(ptrdiff_t) y * res_stride + x] = (int16_t) (residual[(ptrdiff_t) y * res_stride + x] - line);
+    }
+}

@@ -194,6 +194,12 @@ fake_frame3 (SchroFrame *f, SchroFrameFormat fmt, void **data, const int *stride
   }
 }
 
+/* global-motion model for the next ref_motion_render calls (NULL: off): 2 x 10 ints, SchroGlobalMotion's
+ * fields in order.  With it set, the call goes through the dispatcher schro_motion_render, which switches
+ * to the per-pixel renderer (schroedinger/schromotion.c:113-121). */
+static const int *g_global_motion;
+void ref_set_global_motion (const int *gm) { g_global_motion = gm; }
+
 /* schro_motion_render_u8 (schroedinger/schromotion8.c:700) or, with use_ref_renderer,
  * the golden schro_motion_render_ref (schroedinger/schromotionref.c:245) */
 void
@@ -240,9 +246,16 @@ ref_motion_render (const RefMotionParams *mp, const SchroMotionVector *mvs,
     fake_frame3 (&addframe, res_is_s32 ? s32 : s16, residual, res_stride, mp->width, mp->height, 0, 0);
     if (out) fake_frame3 (&output, u8, out, out_stride, mp->width, mp->height, 0, 0);
   }
+  if (g_global_motion) {
+    params.have_global_motion = TRUE;
+    memcpy (&params.global_motion[0], g_global_motion, sizeof (int) * 10);
+    memcpy (&params.global_motion[1], g_global_motion + 10, sizeof (int) * 10);
+  }
   motion = schro_motion_new (&params, &r0, ref1 ? &r1 : NULL);
   memcpy (motion->motion_vectors, mvs, sizeof (SchroMotionVector) * n);
-  if (use_ref_renderer)
+  if (g_global_motion)
+    schro_motion_render (motion, &dest, &addframe, add, out ? &output : NULL);
+  else if (use_ref_renderer)
     schro_motion_render_ref (motion, &dest, &addframe, add, out ? &output : NULL);
   else
     schro_motion_render_u8 (motion, &dest, &addframe, add, out ? &output : NULL);

@@ -89,6 +89,8 @@ _opt("sb2_lowdelay_decode", ctypes.c_int, [ctypes.POINTER(LowdelayParams), ctype
 _opt("sb2_edgeextend_upsample", ctypes.c_int, [_SP, ctypes.c_int, ctypes.c_void_p])
 _opt("sb2_obmc_render", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, _SP, _SP, _SP,
                                       _SP, ctypes.c_int, ctypes.c_int, _SP, ctypes.c_void_p])
+_opt("sb2_obmc_render_ref", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, _SP, _SP, _SP,
+                                          _SP, ctypes.c_int, _SP, ctypes.c_void_p])
 _opt("sb2_obmc_force_kernel", None, [ctypes.c_int])
 _opt("sb2_obmc_last_kernel", ctypes.c_int, [])
 _opt("sb2_hbm_workspace_bytes", ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int])

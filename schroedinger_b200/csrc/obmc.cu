@@ -330,6 +330,120 @@ obmc_kernel_v4 (const ObmcArgs A)
   }
 }
 
+// ---- the reference's per-pixel renderer (global motion) ----------------------------------------
+// schro_motion_render_ref (schroedinger/schromotionref.c:245-330), which the reference switches to whenever
+// params->have_global_motion is set (schroedinger/schromotion.c:113-121): a pixel is the rounded sum of the
+// (at most four) blocks covering it, each fetched pixel by pixel with clamped coordinates
+// (schro_upsampled_frame_get_pixel_precN, schroedinger/schroframe.c:2033-2046, 2124-2143, 2209-2265); blocks
+// flagged using_global take their vector from the picture's global-motion model at that pixel (:22-41).  The
+// prediction is clamped to 0..255 before the residual is added.  One thread per pixel.
+struct RefRenderArgs {
+  ObmcArgs o;
+  int gm[2][10];                      // b0 b1 a_exp a00 a01 a10 a11 c_exp c0 c1 per reference
+};
+
+__device__ __forceinline__ int ref_ramp (int x, int offset)
+{
+  if (offset == 1) return x == 0 ? 3 : 5;
+  return 1 + (6 * x + offset - 1) / (2 * offset - 1);
+}
+
+__device__ __forceinline__ int ref_pixel_prec1 (const uint8_t *ref, int rstride, int w, int h, int x, int y)
+{
+  x = clampi (x, 0, w * 2 - 2);
+  y = clampi (y, 0, h * 2 - 2);
+  return halfpel (ref, rstride, x, y, 0, 0);
+}
+
+__device__ __forceinline__ int ref_pixel (const uint8_t *ref, int rstride, int w, int h, int x, int y, int prec)
+{
+  if (prec == 0) return __ldg (ref + (ptrdiff_t) clampi (y, 0, h - 1) * rstride + clampi (x, 0, w - 1));
+  if (prec == 1) return ref_pixel_prec1 (ref, rstride, w, h, x, y);
+  if (prec == 2) { x <<= 1; y <<= 1; }
+  const int hx = x >> 2, hy = y >> 2, rx = x & 3, ry = y & 3;
+  const int v = (4 - ry) * (4 - rx) * ref_pixel_prec1 (ref, rstride, w, h, hx, hy)
+      + (4 - ry) * rx * ref_pixel_prec1 (ref, rstride, w, h, hx + 1, hy)
+      + ry * (4 - rx) * ref_pixel_prec1 (ref, rstride, w, h, hx, hy + 1)
+      + ry * rx * ref_pixel_prec1 (ref, rstride, w, h, hx + 1, hy + 1);
+  return (v + 8) >> 4;
+}
+
+__global__ void __launch_bounds__ (256)
+obmc_ref_kernel (const RefRenderArgs R)
+{
+  const ObmcArgs &A = R.o;
+  const int comp = blockIdx.z % A.ncomp, pic = blockIdx.z / A.ncomp;
+  const int width = A.w[comp], height = A.h[comp];
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= width || y >= height) return;
+  const int xbsep = A.xbsep[comp], ybsep = A.ybsep[comp], xblen = A.xblen[comp], yblen = A.yblen[comp];
+  const int xoff = (xblen - xbsep) / 2, yoff = (yblen - ybsep) / 2;
+  const int W = xbsep * A.nbx, H = ybsep * A.nby;
+  const uint8_t *ref0 = reinterpret_cast<const uint8_t *> (plane_ptr (A.ref0, pic, comp));
+  const uint8_t *ref1 = A.has_ref1 ? reinterpret_cast<const uint8_t *> (plane_ptr (A.ref1, pic, comp)) : ref0;
+  const int rs0 = A.ref0.stride[comp], rs1 = A.has_ref1 ? A.ref1.stride[comp] : rs0;
+  const MotionVector *mvs = A.mvs + (size_t) pic * A.mv_pitch;
+  const int i0 = (x + xoff) / xbsep - 1, j0 = (y + yoff) / ybsep - 1;
+  int value = 0;
+#pragma unroll
+  for (int dj = 0; dj < 2; dj++)
+#pragma unroll
+    for (int di = 0; di < 2; di++) {
+      const int i = i0 + di, j = j0 + dj;
+      if (i < 0 || j < 0 || i >= A.nbx || j >= A.nby) continue;
+      const int xmin = i * xbsep - xoff, ymin = j * ybsep - yoff;
+      const int xmax = (i + 1) * xbsep + xoff, ymax = (j + 1) * ybsep + yoff;
+      if (x < xmin || y < ymin || x >= xmax || y >= ymax) continue;
+      int wx = 8, wy = 8;
+      if (!(xoff == 0 || x < xoff || x >= W - xoff)) {
+        if (x - xmin < 2 * xoff) wx = ref_ramp (x - xmin, xoff);
+        else if (xmax - 1 - x < 2 * xoff) wx = ref_ramp (xmax - 1 - x, xoff);
+      }
+      if (!(yoff == 0 || y < yoff || y >= H - yoff)) {
+        if (y - ymin < 2 * yoff) wy = ref_ramp (y - ymin, yoff);
+        else if (ymax - 1 - y < 2 * yoff) wy = ref_ramp (ymax - 1 - y, yoff);
+      }
+      const MotionVector *mv = mvs + (size_t) j * A.nbx + i;
+      const unsigned flags = mv->flags;
+      const int mode = flags & 3;
+      int v;
+      if (mode == 0) {
+        v = (int) mv->v[comp] + 128;
+      } else {
+        int s[2] = { 0, 0 };
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          if (!((mode >> r) & 1)) continue;
+          int dx, dy;
+          if ((flags >> 2) & 1) {
+            const int *g = R.gm[r];
+            const int alpha = g[2], beta = g[7];
+            const int scale = (1 << beta) - (g[8] * x + g[9] * y);
+            dx = (scale * (g[3] * x + g[4] * y + (1 << alpha) * g[0])) >> (alpha + beta);
+            dy = (scale * (g[5] * x + g[6] * y + (1 << alpha) * g[1])) >> (alpha + beta);
+          } else {
+            dx = mv->v[r]; dy = mv->v[2 + r];
+          }
+          dx >>= A.hs[comp]; dy >>= A.vs[comp];
+          s[r] = ref_pixel (r ? ref1 : ref0, r ? rs1 : rs0, width, height, (x << A.prec) + dx, (y << A.prec) + dy, A.prec);
+        }
+        v = mode == 3 ? A.w1 * s[0] + A.w2 * s[1] : (A.w1 + A.w2) * s[mode == 1 ? 0 : 1];
+        v = (v + (1 << (A.bits - 1))) >> A.bits;
+      }
+      value += v * wx * wy;
+    }
+  const int line = clampi ((value + 32) >> 6, 0, 255) - 128;
+  if (A.has_acc)
+    reinterpret_cast<short *> (plane_ptr (A.acc, pic, comp) + (size_t) y * A.acc.stride[comp])[x] = (short) line;
+  short *rrow = reinterpret_cast<short *> (plane_ptr (A.res, pic, comp) + (size_t) y * A.res.stride[comp]);
+  if (A.add)
+    reinterpret_cast<uint8_t *> (plane_ptr (A.out, pic, comp))[(size_t) y * A.out.stride[comp] + x] =
+        (uint8_t) clampi ((int) rrow[x] + line + 128, 0, 255);
+  else
+    rrow[x] = (short) ((int) rrow[x] - line);
+}
+
 // schroedinger/schromotion.c:40-79
 static int get_ramp (int x, int offset)
 {
@@ -498,4 +612,71 @@ sb2_obmc_render (const sb2_obmc_params *p, const void *motion_vectors, size_t mv
     }
   }
   return check_cuda (cudaGetLastError (), "obmc_kernel launch");
+}
+
+extern "C" int
+sb2_obmc_render_ref (const sb2_obmc_params *p, const int *global_motion, const void *motion_vectors,
+    size_t mv_picture_pitch, const sb2_slab *ref0, const sb2_slab *ref1, const sb2_slab *acc,
+    const sb2_slab *residual, int add, const sb2_slab *out, void *stream)
+{
+  if (!p || !motion_vectors || !ref0 || !residual) return set_error (SB2_ERR_ARG, "sb2_obmc_render_ref: null argument");
+  if (add && !out) return set_error (SB2_ERR_ARG, "sb2_obmc_render_ref: add needs an output slab");
+  if (p->mv_precision < 0 || p->mv_precision > 3 || p->picture_weight_bits < 1)
+    return set_error (SB2_ERR_ARG, "sb2_obmc_render_ref: mv_precision %d / weight bits %d", p->mv_precision, p->picture_weight_bits);
+  if (p->xblen < p->xbsep || p->yblen < p->ybsep || p->xbsep < 1 || p->ybsep < 1 || p->xblen > 2 * p->xbsep || p->yblen > 2 * p->ybsep)
+    return set_error (SB2_ERR_ARG, "sb2_obmc_render_ref: bad block geometry %dx%d sep %dx%d", p->xblen, p->yblen, p->xbsep, p->ybsep);
+  const int ncomp = residual->ncomp, count = residual->count;
+  if (ncomp < 1 || ncomp > SB2_MAX_COMPONENTS || ref0->ncomp != ncomp || ref0->count != count ||
+      (ref1 && (ref1->ncomp != ncomp || ref1->count != count)) || (out && (out->ncomp != ncomp || out->count != count)) ||
+      (acc && (acc->ncomp != ncomp || acc->count != count)))
+    return set_error (SB2_ERR_ARG, "sb2_obmc_render_ref: slab shapes differ");
+  RefRenderArgs R;
+  ObmcArgs &A = R.o;
+  A.ref0 = planeset_from_slab (ref0);
+  A.ref1 = planeset_from_slab (ref1 ? ref1 : ref0);
+  A.acc = planeset_from_slab (acc ? acc : residual);
+  A.res = planeset_from_slab (residual);
+  A.out = planeset_from_slab (out ? out : residual);
+  A.mvs = static_cast<const MotionVector *> (motion_vectors);
+  A.mv_pitch = mv_picture_pitch;
+  A.nbx = p->x_num_blocks;
+  A.nby = p->y_num_blocks;
+  A.prec = p->mv_precision;
+  A.w1 = p->picture_weight_1;
+  A.w2 = p->picture_weight_2;
+  A.bits = p->picture_weight_bits;
+  A.ncomp = ncomp;
+  A.add = add;
+  A.res_is_s32 = 0;
+  A.has_ref1 = ref1 != nullptr;
+  A.has_acc = acc != nullptr;
+  for (int r = 0; r < 2; r++)
+    for (int k = 0; k < 10; k++) R.gm[r][k] = global_motion ? global_motion[10 * r + k] : 0;
+  // the rendered area is that of dest (schromotionref.c:267: comp = dest->components + k)
+  const sb2_slab *area = acc ? acc : (add ? out : residual);
+  int maxw = 0, maxh = 0;
+  double bytes = 0;
+  for (int c = 0; c < SB2_MAX_COMPONENTS; c++) {
+    A.w[c] = A.h[c] = A.xbsep[c] = A.ybsep[c] = A.xblen[c] = A.yblen[c] = A.hs[c] = A.vs[c] = 0;
+    if (c >= ncomp) continue;
+    const int hs = c ? p->chroma_h_shift : 0, vs = c ? p->chroma_v_shift : 0;
+    A.w[c] = area->width[c];
+    A.h[c] = area->height[c];
+    const sb2_slab *all[4] = { residual, out, acc, ref0 };
+    for (const sb2_slab *s : all)
+      if (s && (s->width[c] < A.w[c] || s->height[c] < A.h[c]))
+        return set_error (SB2_ERR_ARG, "sb2_obmc_render_ref: component %d: a plane is smaller than the rendered area", c);
+    A.xbsep[c] = p->xbsep >> hs; A.ybsep[c] = p->ybsep >> vs;
+    A.xblen[c] = p->xblen >> hs; A.yblen[c] = p->yblen >> vs;
+    A.hs[c] = hs; A.vs[c] = vs;
+    maxw = max (maxw, A.w[c]);
+    maxh = max (maxh, A.h[c]);
+    bytes += (double) A.w[c] * A.h[c] * count * (4.0 * (ref1 ? 2 : 1) + 2 + (add ? 1 : 2));
+  }
+  dim3 grid (ceil_div (maxw, 32), ceil_div (maxh, 8), ncomp * count);
+  {
+    LaunchScope scope (add ? "obmc_render_ref_add" : "obmc_render_ref_sub", bytes, as_stream (stream));
+    obmc_ref_kernel<<<grid, 256, 0, as_stream (stream)>>> (R);
+  }
+  return check_cuda (cudaGetLastError (), "obmc_ref_kernel launch");
 }

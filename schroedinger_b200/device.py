@@ -472,3 +472,17 @@ def iwt_inverse_convert(src, dst_u8, filter_index, transform_depth, shift=0, wor
     ptr, size = ws.get(lib.sb2_iwt_workspace_bytes(ctypes.byref(src.slab), is_s32, transform_depth, 0))
     check(lib.sb2_iwt_inverse_convert(ctypes.byref(src.slab), ctypes.byref(dst_u8.slab), is_s32, filter_index,
                                       transform_depth, shift, ptr, size, _stream_ptr(stream)), "sb2_iwt_inverse_convert")
+
+
+def obmc_render_ref(params, global_motion, mvs, ref0, ref1, residual, add, out=None, acc=None, stream=None):
+    """schro_motion_render_ref (what schro_motion_render runs when the picture has global motion);
+    global_motion: 20 ints or None."""
+    require_cuda()
+    n = params.x_num_blocks * params.y_num_blocks
+    null = ctypes.POINTER(Slab)()
+    gm = (ctypes.c_int * 20)(*[int(v) for v in global_motion]) if global_motion is not None else None
+    check(lib.sb2_obmc_render_ref(
+        ctypes.byref(params), gm, ctypes.c_void_p(mvs.data_ptr()), ctypes.c_size_t(n),
+        ctypes.byref(ref0.slab), ctypes.byref(ref1.slab) if ref1 is not None else null,
+        ctypes.byref(acc.slab) if acc is not None else null, ctypes.byref(residual.slab), 1 if add else 0,
+        ctypes.byref(out.slab) if out is not None else null, _stream_ptr(stream)), "sb2_obmc_render_ref")

@@ -495,9 +495,9 @@ schro_motion_init_obmc_weight (SchroMotion *motion)
   }
 }
 
-void
-schro_motion_render_u8 (SchroMotion *motion, SchroFrame *dest, SchroFrame *addframe, int add,
-    SchroFrame *output_frame)
+static void
+motion_render (SchroMotion *motion, SchroFrame *dest, SchroFrame *addframe, int add,
+    SchroFrame *output_frame, int use_ref_renderer)
 {
   Sb2hContext *cx = sb2h_context ();
   SchroParams *params = motion->params;
@@ -508,9 +508,6 @@ schro_motion_render_u8 (SchroMotion *motion, SchroFrame *dest, SchroFrame *addfr
   int res_is_s32;
 
   if (params->num_refs == 1) SB2H_ASSERT (params->picture_weight_2 == 1);   /* schromotion8.c:711 */
-  if (params->have_global_motion)
-    sb2h_fatal (__func__, "global motion is outside the B200 picture core (the reference falls back to "
-        "its per-pixel renderer, schromotion.c:113-121)");
   if (add && !output_frame) sb2h_fatal (__func__, "add needs an output frame");
   require_u8 (motion->src1, __func__);
   if (motion->src1->extension < 32 || !motion->src1->is_upsampled)
@@ -540,8 +537,21 @@ schro_motion_render_u8 (SchroMotion *motion, SchroFrame *dest, SchroFrame *addfr
   SB2H_CUDA (cudaMemcpyAsync (dmv, motion->motion_vectors, nmv * sizeof (SchroMotionVector),
           cudaMemcpyDefault, cx->stream));
   /* the rendered area is dest's (schromotion8.c:722-751); addframe may be iwt-padded */
-  SB2H_CHECK (sb2_obmc_render (&p, dmv, nmv, &r0.slab, motion->src2 ? &r1.slab : NULL, &acc.slab,
-          &res.slab, res_is_s32, add, output_frame ? &out.slab : NULL, cx->stream), "sb2_obmc_render");
+  if (use_ref_renderer) {
+    /* global motion: the reference's per-pixel renderer (schromotion.c:113-121, schromotionref.c:245-330) */
+    int gm[20], r;
+    if (res_is_s32) sb2h_fatal (__func__, "the per-pixel renderer adds s16 residuals only (schromotionref.c:252)");
+    for (r = 0; r < 2; r++) {
+      const SchroGlobalMotion *g = &params->global_motion[r];
+      const int v[10] = { g->b0, g->b1, g->a_exp, g->a00, g->a01, g->a10, g->a11, g->c_exp, g->c0, g->c1 };
+      memcpy (gm + 10 * r, v, sizeof (v));
+    }
+    SB2H_CHECK (sb2_obmc_render_ref (&p, gm, dmv, nmv, &r0.slab, motion->src2 ? &r1.slab : NULL, &acc.slab,
+            &res.slab, add, output_frame ? &out.slab : NULL, cx->stream), "sb2_obmc_render_ref");
+  } else {
+    SB2H_CHECK (sb2_obmc_render (&p, dmv, nmv, &r0.slab, motion->src2 ? &r1.slab : NULL, &acc.slab,
+            &res.slab, res_is_s32, add, output_frame ? &out.slab : NULL, cx->stream), "sb2_obmc_render");
+  }
   stage_out (cx, &acc);
   if (add) stage_out (cx, &out);
   else stage_out (cx, &res);
@@ -555,10 +565,26 @@ schro_motion_render_u8 (SchroMotion *motion, SchroFrame *dest, SchroFrame *addfr
 }
 
 void
+schro_motion_render_u8 (SchroMotion *motion, SchroFrame *dest, SchroFrame *addframe, int add,
+    SchroFrame *output_frame)
+{
+  motion_render (motion, dest, addframe, add, output_frame, 0);
+}
+
+/* schroedinger/schromotionref.c:245 */
+void
+schro_motion_render_ref (SchroMotion *motion, SchroFrame *dest, SchroFrame *addframe, int add,
+    SchroFrame *output_frame)
+{
+  motion_render (motion, dest, addframe, add, output_frame, 1);
+}
+
+/* the dispatcher (schroedinger/schromotion.c:95-155): global motion takes the per-pixel renderer */
+void
 schro_motion_render (SchroMotion *motion, SchroFrame *dest, SchroFrame *addframe, int add,
     SchroFrame *output_frame)
 {
-  schro_motion_render_u8 (motion, dest, addframe, add, output_frame);
+  motion_render (motion, dest, addframe, add, output_frame, motion->params->have_global_motion ? 1 : 0);
 }
 
 /* ---- SAD primitives ---------------------------------------------------------- */

@@ -249,6 +249,50 @@ def oracle_obmc(oracle, case, add):
     return res
 
 
+def oracle_obmc_ref(oracle, case, add, global_motion):
+    """The reference's per-pixel renderer (schro_motion_render_ref) through the oracle; global_motion: 20 ints."""
+    res = []
+    fn = oracle.oracle_obmc_render_ref
+    fn.restype = None
+    gm = (ctypes.c_int * 20)(*[int(v) for v in global_motion])
+    for k, (w, h) in enumerate(case.comp_sizes):
+        p = OracleObmcParams(**case.comp_params(k))
+        acc = np.zeros((h, w), np.int16)
+        resid = case.residual[k].astype(np.int16).copy()
+        out = np.zeros((h, w), np.uint8)
+        r1 = case.ref1[k].ptr if case.ref1 else None
+        fn(ctypes.byref(p), gm, case.mvs.ctypes.data_as(ctypes.c_void_p), case.ref0[k].ptr, r1, case.ref0[k].stride, w, h,
+           acc.ctypes.data_as(ctypes.c_void_p), acc.strides[0] // 2, resid.ctypes.data_as(ctypes.c_void_p),
+           resid.strides[0] // 2, 1 if add else 0, out.ctypes.data_as(ctypes.c_void_p), out.strides[0])
+        res.append((acc, resid, out))
+    return res
+
+
+def ref_obmc_global(ref, case, add, global_motion):
+    """schro_motion_render with have_global_motion set through the compiled reference."""
+    gm = (ctypes.c_int * 20)(*[int(v) for v in global_motion])
+    ref.ref_set_global_motion(gm)
+    try:
+        return ref_obmc(ref, case, add)
+    finally:
+        ref.ref_set_global_motion(None)
+
+
+def global_motion_case(oracle, width, height, rng, **kw):
+    """An ObmcCase in which a third of the blocks use the picture's global-motion model, plus that model:
+    a slight zoom / rotation / pan per reference (a_exp = 8) with a small perspective term."""
+    case = ObmcCase(oracle, width, height, rng, **kw)
+    mv = case.mvs
+    use = rng.random(len(mv)) < 0.35
+    mv["flags"] = np.where(use & ((mv["flags"] & 3) != 0), mv["flags"] | 4, mv["flags"])
+    gm = []
+    for r in range(2):
+        # b0 b1 a_exp a00 a01 a10 a11 c_exp c0 c1: the vector is the model's displacement, ((A x + 2^a b) * scale) >> (a + c)
+        gm += [int(rng.integers(-6, 7)), int(rng.integers(-6, 7)), 8, int(rng.integers(-3, 4)), int(rng.integers(-2, 3)),
+               int(rng.integers(-2, 3)), int(rng.integers(-3, 4)), 12, int(rng.integers(-1, 2)), int(rng.integers(-1, 2))]
+    return case, gm
+
+
 def ref_obmc(ref, case, add, use_ref_renderer=False):
     """Same through the unmodified reference (schro_motion_render_u8 or _ref)."""
     P = ctypes.c_void_p * 3
