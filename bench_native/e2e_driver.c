@@ -241,7 +241,7 @@ typedef struct {
   SchroFrame **u8_dev;         /* [nthreads] CUDA-domain u8 pictures */
 } Sb2LowdelayJob;
 
-typedef struct { const Sb2LowdelayJob *job; int t, steps; pthread_barrier_t *start; } LdWorker;
+typedef struct { const Sb2LowdelayJob *job; int t, steps; pthread_barrier_t *start, *end; } LdWorker;
 /* wall-clock seconds per call, summed per thread (sb2_e2e_lowdelay_times reads and clears them) */
 static double g_ld_times[64][4];
 void
@@ -258,6 +258,11 @@ ld_worker (void *arg)
   const Sb2LowdelayJob *j = w->job;
   const long total = (long) w->steps * j->npictures;
   long k;
+  /* one untimed picture first: the thread's streams and staging buffers come into being here (cudaMalloc is a
+   * device-wide stall), and go away after the end barrier (cudaFree is another) -- outside the timed region */
+  schro_b200_decode_lowdelay_transform_data (j->params, j->slices[w->t % j->npictures], j->slice_bytes, j->coef_dev[w->t]);
+  schro_b200_frame_inverse_iwt_combine (j->u8_dev[w->t], j->coef_dev[w->t], j->params, 0);
+  schro_gpuframe_to_cpu (j->out_host[w->t % j->npictures], j->u8_dev[w->t]);
   pthread_barrier_wait (w->start);
   for (k = w->t; k < total; k += j->nthreads) {
     const int i = (int) (k % j->npictures);
@@ -272,6 +277,7 @@ ld_worker (void *arg)
     g_ld_times[w->t & 63][0] += t1 - t0; g_ld_times[w->t & 63][1] += t2 - t1;
     g_ld_times[w->t & 63][2] += t3 - t2; g_ld_times[w->t & 63][3] += t4 - t3;
   }
+  pthread_barrier_wait (w->end);
   schro_b200_thread_release ();
   return NULL;
 }
@@ -281,19 +287,80 @@ sb2_e2e_lowdelay_run (const Sb2LowdelayJob *job, int steps)
 {
   pthread_t *th = calloc ((size_t) job->nthreads, sizeof (pthread_t));
   LdWorker *w = calloc ((size_t) job->nthreads, sizeof (LdWorker));
-  pthread_barrier_t start;
+  pthread_barrier_t start, end;
   double t0;
   int t;
   pthread_barrier_init (&start, NULL, (unsigned) job->nthreads + 1);
+  pthread_barrier_init (&end, NULL, (unsigned) job->nthreads + 1);
   for (t = 0; t < job->nthreads; t++) {
-    w[t].job = job; w[t].t = t; w[t].steps = steps; w[t].start = &start;
+    w[t].job = job; w[t].t = t; w[t].steps = steps; w[t].start = &start; w[t].end = &end;
     pthread_create (&th[t], NULL, ld_worker, &w[t]);
   }
   pthread_barrier_wait (&start);
   t0 = now ();
-  for (t = 0; t < job->nthreads; t++) pthread_join (th[t], NULL);
+  pthread_barrier_wait (&end);
   t0 = now () - t0;
+  for (t = 0; t < job->nthreads; t++) pthread_join (th[t], NULL);
   pthread_barrier_destroy (&start);
+  pthread_barrier_destroy (&end);
+  free (th);
+  free (w);
+  return t0;
+}
+
+/* the same pictures through the batched drop-in: every worker hands `batch` pictures at a time to
+ * schro_b200_decode_lowdelay_pictures (one launch per stage and one wait per batch) */
+typedef struct { const Sb2LowdelayJob *job; int t, steps, batch; pthread_barrier_t *start, *end; } LdBatchWorker;
+
+static void *
+ld_batch_worker (void *arg)
+{
+  LdBatchWorker *w = arg;
+  const Sb2LowdelayJob *j = w->job;
+  const long nb = ((long) w->steps * j->npictures) / w->batch;
+  const uint8_t **data = calloc ((size_t) w->batch, sizeof (*data));
+  SchroFrame **outs = calloc ((size_t) w->batch, sizeof (*outs));
+  long b;
+  int k;
+  for (k = 0; k < w->batch; k++) { data[k] = j->slices[k % j->npictures]; outs[k] = j->out_host[(w->t * w->batch + k) % j->npictures]; }
+  schro_b200_decode_lowdelay_pictures (j->params, w->batch, data, j->slice_bytes, outs, 0, 0);     /* untimed: buffers */
+  pthread_barrier_wait (w->start);
+  for (b = w->t; b < nb; b += j->nthreads) {
+    for (k = 0; k < w->batch; k++) {
+      const int i = (int) ((b * w->batch + k) % j->npictures);
+      data[k] = j->slices[i];
+      outs[k] = j->out_host[i];
+    }
+    schro_b200_decode_lowdelay_pictures (j->params, w->batch, data, j->slice_bytes, outs, 0, 0);
+  }
+  pthread_barrier_wait (w->end);
+  free (data);
+  free (outs);
+  schro_b200_thread_release ();
+  return NULL;
+}
+
+double
+sb2_e2e_lowdelay_run_batched (const Sb2LowdelayJob *job, int steps, int batch)
+{
+  pthread_t *th = calloc ((size_t) job->nthreads, sizeof (pthread_t));
+  LdBatchWorker *w = calloc ((size_t) job->nthreads, sizeof (LdBatchWorker));
+  pthread_barrier_t start, end;
+  double t0;
+  int t;
+  pthread_barrier_init (&start, NULL, (unsigned) job->nthreads + 1);
+  pthread_barrier_init (&end, NULL, (unsigned) job->nthreads + 1);
+  for (t = 0; t < job->nthreads; t++) {
+    w[t].job = job; w[t].t = t; w[t].steps = steps; w[t].batch = batch; w[t].start = &start; w[t].end = &end;
+    pthread_create (&th[t], NULL, ld_batch_worker, &w[t]);
+  }
+  pthread_barrier_wait (&start);
+  t0 = now ();
+  pthread_barrier_wait (&end);
+  t0 = now () - t0;
+  for (t = 0; t < job->nthreads; t++) pthread_join (th[t], NULL);
+  pthread_barrier_destroy (&start);
+  pthread_barrier_destroy (&end);
   free (th);
   free (w);
   return t0;

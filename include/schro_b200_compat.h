@@ -460,6 +460,13 @@ void schro_b200_motion_predict_subpel_deep (SchroParams *params, double lambda, 
  * the 8-bit picture is written by the last wavelet level, the coefficient frame is left as it was. */
 void schro_b200_frame_inverse_iwt_combine (SchroFrame *output, SchroFrame *frame, SchroParams *params, int shift);
 
+/* new: a batch of n independent low-delay intra pictures (one `params`, n slice buffers of `length` bytes, n u8
+ * output frames of one layout in host memory) decoded with one launch per stage and one wait:
+ * slices -> coefficients -> inverse transform with the shift / conversion to 8 bits fused in.  The batched
+ * counterpart of schro_b200_decode_lowdelay_transform_data + schro_b200_frame_inverse_iwt_combine. */
+void schro_b200_decode_lowdelay_pictures (SchroParams *params, int n, const uint8_t *const *data, int length,
+    SchroFrame *const *outputs, int is_s32, int shift);
+
 /* ---- low-delay slices (schroedinger/schrolowdelay.c:745-761) ----
  * schro_decoder_decode_lowdelay_transform_data (SchroPicture *) with the three things it reads from the picture
  * passed explicitly (compat/schro_lowdelay.c keeps the reference's symbol): picture->params,

@@ -199,6 +199,8 @@ _proto("schro_frame_shift_left", None, [FrameP, ctypes.c_int])
 _proto("schro_frame_shift_right", None, [FrameP, ctypes.c_int])
 _proto("schro_frame_md5", None, [FrameP, ctypes.POINTER(ctypes.c_uint32)])
 _proto("schro_b200_frame_inverse_iwt_combine", None, [FrameP, FrameP, ParamsP, ctypes.c_int])
+_proto("schro_b200_decode_lowdelay_pictures", None, [ParamsP, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                                                     ctypes.POINTER(FrameP), ctypes.c_int, ctypes.c_int])
 _proto("schro_b200_decode_lowdelay_transform_data", None, [ParamsP, ctypes.c_void_p, ctypes.c_int, FrameP])
 _proto("schro_motion_field_new", ctypes.POINTER(SchroMotionField), [ctypes.c_int, ctypes.c_int])
 _proto("schro_motion_field_free", None, [ctypes.POINTER(SchroMotionField)])

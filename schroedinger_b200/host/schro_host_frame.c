@@ -439,6 +439,101 @@ schro_b200_decode_lowdelay_transform_data (SchroParams *params, const uint8_t *d
   if (sb2h_mem_kind (data) != SB2H_MEM_DEVICE) sb2h_sync (cx);
 }
 
+/* A batch of low-delay intra pictures in one go: what a caller that holds several independent pictures (an
+ * intra-only stream: every picture is its own GOP) should use instead of one call chain per picture --
+ * the slices of all pictures are uploaded, then ONE slice-decode launch, ONE inverse transform with the
+ * combine fused into its last level, and the 8-bit pictures come back; one wait for the whole batch.
+ * Equivalent to, for every i: schro_b200_decode_lowdelay_transform_data (params, data[i], length, T),
+ * schro_b200_frame_inverse_iwt_combine (outputs[i], T, params, shift).  All pictures share `params`;
+ * data[i] point to `length` bytes each (pinned memory for full-rate DMA); outputs[i] are u8 host frames of
+ * one layout.  Falls back to the per-picture calls when the fused kernel does not cover the shape. */
+void
+schro_b200_decode_lowdelay_pictures (SchroParams *params, int n, const uint8_t *const *data, int length,
+    SchroFrame *const *outputs, int is_s32, int shift)
+{
+  Sb2hContext *cx = sb2h_context ();
+  sb2_lowdelay_params p;
+  sb2_slab coef, out;
+  const int bpp = is_s32 ? 4 : 2;
+  const size_t pitch = ((size_t) length + 255) & ~(size_t) 255;
+  size_t coef_pic = 0, out_pic = 0, ws_bytes;
+  char *dev_data, *dev_coef, *dev_out;
+  void *ws;
+  int i, k, rc;
+  SB2H_ASSERT (params && n > 0 && data && outputs && length > 0);
+  memset (&p, 0, sizeof (p));
+  p.transform_depth = params->transform_depth;
+  p.n_horiz_slices = params->n_horiz_slices;
+  p.n_vert_slices = params->n_vert_slices;
+  p.slice_bytes_num = params->slice_bytes_num;
+  p.slice_bytes_denom = params->slice_bytes_denom;
+  for (i = 0; i < 1 + 3 * params->transform_depth; i++) p.quant_matrix[i] = params->quant_matrix[i];
+  lowdelay_tables (p.table_quant, p.table_offset);
+  /* device slabs: dense coefficient planes (stride = width rounded up to 16 bytes), the outputs' own layout */
+  memset (&coef, 0, sizeof (coef));
+  memset (&out, 0, sizeof (out));
+  coef.ncomp = out.ncomp = 3;
+  coef.count = out.count = n;
+  for (k = 0; k < 3; k++) {
+    const SchroFrameData *oc = &outputs[0]->components[k];
+    coef.width[k] = k ? params->iwt_chroma_width : params->iwt_luma_width;
+    coef.height[k] = k ? params->iwt_chroma_height : params->iwt_luma_height;
+    coef.stride[k] = (coef.width[k] * bpp + 15) & ~15;
+    coef.offset[k] = coef_pic;
+    coef_pic += ((size_t) coef.stride[k] * coef.height[k] + 255) & ~(size_t) 255;
+    out.width[k] = oc->width < coef.width[k] ? oc->width : coef.width[k];
+    out.height[k] = oc->height < coef.height[k] ? oc->height : coef.height[k];
+    out.stride[k] = oc->stride;
+    out.offset[k] = (size_t) ((char *) oc->data - (char *) outputs[0]->regions[0]);
+    out_pic += (size_t) oc->length;
+  }
+  out_pic = (out_pic + 255) & ~(size_t) 255;
+  coef.picture_pitch = coef_pic;
+  out.picture_pitch = out_pic;
+  dev_data = sb2h_dev_buffer (cx, SB2H_BUF_AUX0, pitch * n + 256);
+  dev_coef = sb2h_dev_buffer (cx, SB2H_BUF_IN, coef_pic * n + 256);
+  dev_out = sb2h_dev_buffer (cx, SB2H_BUF_OUT, out_pic * n + 256);
+  coef.base = dev_coef;
+  out.base = dev_out;
+  for (i = 0; i < n; i++)
+    SB2H_CUDA (cudaMemcpyAsync (dev_data + pitch * i, data[i], (size_t) length, cudaMemcpyDefault, cx->stream));
+  if ((params->iwt_luma_width | params->iwt_luma_height | params->iwt_chroma_width | params->iwt_chroma_height)
+      & ((1 << params->transform_depth) - 1))
+    SB2H_CUDA (cudaMemsetAsync (dev_coef, 0, coef_pic * n, cx->stream));       /* samples no subband covers */
+  SB2H_CHECK (sb2_lowdelay_decode (&p, (const uint8_t *) dev_data, (size_t) length, pitch, &coef, is_s32, cx->stream),
+      "sb2_lowdelay_decode");
+  ws_bytes = sb2_iwt_workspace_bytes (&coef, is_s32, params->transform_depth, 0);
+  ws = sb2h_dev_buffer (cx, SB2H_BUF_WS, ws_bytes);
+  rc = sb2_iwt_inverse_convert (&coef, &out, is_s32, params->wavelet_filter_index, params->transform_depth, shift, ws,
+      ws_bytes, cx->stream);
+  if (rc == SB2_ERR_UNSUPPORTED) {
+    /* shapes the fused kernel does not cover: in place, then shift and convert */
+    ws_bytes = sb2_iwt_workspace_bytes (&coef, is_s32, params->transform_depth, 1);
+    ws = sb2h_dev_buffer (cx, SB2H_BUF_WS, ws_bytes);
+    SB2H_CHECK (sb2_iwt_inverse (&coef, &coef, is_s32, params->wavelet_filter_index, params->transform_depth, ws, ws_bytes,
+            cx->stream), "sb2_iwt_inverse");
+    if (shift) SB2H_CHECK (sb2_frame_shift (&coef, is_s32 ? 2 : 1, shift, 1, cx->stream), "sb2_frame_shift");
+    SB2H_CHECK (sb2_frame_convert (&coef, is_s32 ? 2 : 1, &out, 0, cx->stream), "sb2_frame_convert");
+  } else {
+    SB2H_CHECK (rc, "sb2_iwt_inverse_convert");
+  }
+  for (i = 0; i < n; i++) {
+    if (outputs[i]->extension == 0) {
+      /* no border: the region is the three planes back to back -- one DMA per picture (the few bytes of row
+       * padding beyond a plane's width carry no meaning) */
+      SB2H_CUDA (cudaMemcpyAsync (outputs[i]->regions[0], dev_out + out_pic * i, frame_region_bytes (outputs[i]),
+              cudaMemcpyDefault, cx->stream));
+      continue;
+    }
+    /* frames with a border: plane by plane, so that the border stays as it is */
+    for (k = 0; k < 3; k++)
+      sb2h_copy_rect (cx, (char *) outputs[i]->regions[0] + out.offset[k], (size_t) out.stride[k],
+          dev_out + out_pic * i + out.offset[k], (size_t) out.stride[k], (size_t) out.width[k], out.height[k]);
+  }
+  cx->dirty = 1;
+  sb2h_sync (cx);
+}
+
 /* ---- OBMC ------------------------------------------------------------------ */
 SchroMotion *
 schro_motion_new (SchroParams *params, SchroFrame *ref1, SchroFrame *ref2)

@@ -173,3 +173,37 @@ def test_lowdelay_drop_in(cuda, via_shim, domain_kind):
     if host is not f:
         lib.schro_frame_unref(host)
     lib.schro_frame_unref(f)
+
+
+def test_lowdelay_batch_drop_in(cuda):
+    """schro_b200_decode_lowdelay_pictures: n pictures per call = the per-picture chain, for a shape the fused
+    inverse + convert covers and for one it does not."""
+    import ctypes
+    from schroedinger_b200 import compat, lib
+    from tests.test_oracle_lowdelay import quantised_planes
+    from tests.test_iwt_convert_gpu import want_pictures
+    for (w, h, depth, nh, nv, num, pw, ph, shift) in ((480, 288, 4, 15, 9, 150, 480, 270, 0), (104, 72, 2, 13, 9, 40, 100, 70, 1)):
+        rng = np.random.default_rng(w)
+        qm = [int(v) for v in rng.integers(0, 4, size=1 + 3 * depth)]
+        params = compat.make_params(pw, ph, wavelet_filter_index=0, transform_depth=depth, iwt_luma_width=w, iwt_luma_height=h)
+        params.is_lowdelay = 1
+        params.n_horiz_slices, params.n_vert_slices = nh, nv
+        params.slice_bytes_num, params.slice_bytes_denom = num, 1
+        params.iwt_chroma_width, params.iwt_chroma_height = w // 2, h // 2
+        for i, v in enumerate(qm):
+            params.quant_matrix[i] = v
+        n = 5
+        aligned = ((w // 2) >> depth) % nh == 0 and ((h // 2) >> depth) % nv == 0
+        datas = [helpers.lowdelay_encode(quantised_planes(rng, w, h, 60), depth, nh, nv, num, 1, rng, fast_lengths=aligned)[0]
+                 for _ in range(n)]
+        bufs = [ctypes.create_string_buffer(d, len(d)) for d in datas]
+        outs = [compat.frame_new_and_alloc(None, compat.FORMAT_U8_420, pw, ph, 0, 0) for _ in range(n)]
+        lib.schro_b200_decode_lowdelay_pictures(ctypes.byref(params), n, (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b in bufs]),
+                                                len(datas[0]), (compat.FrameP * n)(*outs), 0, shift)
+        for i in range(n):
+            coeffs = oracle_decode(datas[i], w, h, depth, nh, nv, num, 1, qm, 0)
+            want = want_pictures(coeffs, 0, depth, shift, pw, ph)
+            for c in range(3):
+                assert np.array_equal(np.array(compat.frame_plane(outs[i], c)), want[c]), ((w, h), i, c)
+        for f in outs:
+            lib.schro_frame_unref(f)
