@@ -27,6 +27,10 @@ typedef struct {
   cudaStream_t stream_hi;  /* highest-priority side stream for the latency-bound wavefront kernels */
   cudaEvent_t ev_fork, ev_join;
   cudaEvent_t sync_ev;     /* blocking-sync event: waiting threads sleep instead of spinning */
+  void *pin;               /* page-locked staging block for small host arrays that arrive in pageable memory */
+  size_t pin_size;
+  cudaEvent_t pin_ev;      /* the last DMA out of `pin` */
+  int pin_busy;
   volatile int dirty;      /* work was enqueued on `stream` that no call has waited for yet */
   int slot;                /* index in the process-wide context table */
 } Sb2hContext;
@@ -63,6 +67,10 @@ int sb2h_pinned_pool_free (void *ptr);     /* 0 if ptr is not a pool block */
 void *sb2h_pool_alloc (size_t bytes);
 void sb2h_pool_free (void *ptr);
 void *sb2h_dev_buffer (Sb2hContext *cx, int which, size_t bytes);
+/* Upload of a host array that may live in pageable memory without a pageable cudaMemcpyAsync (which waits for
+ * everything queued on the stream before it and holds the driver's lock while it stages): the bytes are copied
+ * by the CPU into the thread's page-locked staging block and DMA'd from there; returns at once */
+void sb2h_upload_staged (Sb2hContext *cx, void *dev_dst, const void *host_src, size_t bytes);
 
 /* a u8 pyramid level as a one-picture slab: zero-copy for CUDA-domain frames, else uploaded once into
  * *cache (a pool block the caller frees); returns 1 when it enqueued an upload out of page-locked memory */

@@ -116,11 +116,13 @@ schro_b200_thread_release (void)
   pthread_mutex_unlock (&g_device_mutex);
   for (i = 0; i < SB2H_NBUF; i++)
     if (cx->dev[i]) cudaFree (cx->dev[i]);
+  if (cx->pin) cudaFreeHost (cx->pin);
+  if (cx->pin_ev) cudaEventDestroy (cx->pin_ev);
   if (last) sb2h_pool_release_all ();
   cudaEventDestroy (cx->sync_ev);
   cudaEventDestroy (cx->ev_fork);
   cudaEventDestroy (cx->ev_join);
-  cudaStreamDestroy (cx->stream_hi);
+  if (cx->stream_hi != cx->stream) cudaStreamDestroy (cx->stream_hi);
   cudaStreamDestroy (cx->stream);
   free (cx);
   tl_cx = NULL;
@@ -142,7 +144,10 @@ sb2h_context (void)
     {
       int lo = 0, hi = 0;
       SB2H_CUDA (cudaDeviceGetStreamPriorityRange (&lo, &hi));
-      SB2H_CUDA (cudaStreamCreateWithPriority (&tl_cx->stream_hi, cudaStreamNonBlocking, hi));
+      /* SB2_HOST_ONE_STREAM=1: the wavefront kernels share the thread's ordering stream (an experiment knob: with
+       * more streams than the device has hardware queues, streams that share a queue wait on each other) */
+      if (getenv ("SB2_HOST_ONE_STREAM") && atoi (getenv ("SB2_HOST_ONE_STREAM"))) tl_cx->stream_hi = tl_cx->stream;
+      else SB2H_CUDA (cudaStreamCreateWithPriority (&tl_cx->stream_hi, cudaStreamNonBlocking, hi));
       SB2H_CUDA (cudaEventCreateWithFlags (&tl_cx->ev_fork, cudaEventDisableTiming));
       SB2H_CUDA (cudaEventCreateWithFlags (&tl_cx->ev_join, cudaEventDisableTiming));
     }
@@ -345,6 +350,30 @@ sb2h_dev_buffer (Sb2hContext *cx, int which, size_t bytes)
   return cx->dev[which];
 }
 
+void
+sb2h_upload_staged (Sb2hContext *cx, void *dev_dst, const void *host_src, size_t bytes)
+{
+  if (bytes == 0) return;
+  if (sb2h_mem_kind (host_src) != SB2H_MEM_PAGEABLE) {
+    SB2H_CUDA (cudaMemcpyAsync (dev_dst, host_src, bytes, cudaMemcpyDefault, cx->stream));
+    return;
+  }
+  if (cx->pin_busy) {                      /* the previous DMA out of the block (long finished in practice) */
+    SB2H_CUDA (cudaEventSynchronize (cx->pin_ev));
+    cx->pin_busy = 0;
+  }
+  if (cx->pin_size < bytes) {
+    if (cx->pin) SB2H_CUDA (cudaFreeHost (cx->pin));
+    cx->pin_size = (bytes + 0xfffff) & ~(size_t) 0xfffff;
+    SB2H_CUDA (cudaHostAlloc (&cx->pin, cx->pin_size, cudaHostAllocDefault));
+    if (!cx->pin_ev) SB2H_CUDA (cudaEventCreateWithFlags (&cx->pin_ev, cudaEventDisableTiming));
+  }
+  memcpy (cx->pin, host_src, bytes);
+  SB2H_CUDA (cudaMemcpyAsync (dev_dst, cx->pin, bytes, cudaMemcpyHostToDevice, cx->stream));
+  SB2H_CUDA (cudaEventRecord (cx->pin_ev, cx->stream));
+  cx->pin_busy = 1;
+}
+
 /* Process-wide pool of device blocks, reused by exact size (no cudaMalloc / cudaFree -- and so no
  * device-wide synchronisation -- in steady state).  A block may be handed back by another thread
  * than the one that allocated it (SchroAsync moves the stages of a picture between workers), and
@@ -359,19 +388,25 @@ sb2h_pool_alloc (size_t bytes)
 {
   Sb2hContext *cx = sb2h_context ();
   int i, free_slot = -1, idle_slot = -1;
-  void *p;
+  void *p, *old = NULL;
+  cudaEvent_t old_ev = NULL;
+  /* No CUDA call is made with the pool's lock held: a call that has to wait (cudaMalloc behind a busy device, an
+   * enqueue behind a full channel) would otherwise stall every other worker's alloc and free with it.  A slot that
+   * is marked in use belongs to one thread, so its event and pointer can be touched outside the lock. */
   pthread_mutex_lock (&g_pool_mutex);
   for (i = 0; i < SB2H_POOL_SLOTS; i++) {
     if (g_pool[i].ptr && !g_pool[i].in_use) {
       if (g_pool[i].bytes == bytes) {
+        const int wait = g_pool[i].ev_valid;
+        cudaEvent_t ev = g_pool[i].ev;
         g_pool[i].in_use = 1;
         p = g_pool[i].ptr;
-        if (g_pool[i].ev_valid) {
-          /* (under the lock: the event is re-recorded by the next free of this slot) */
-          SB2H_CUDA (cudaStreamWaitEvent (cx->stream, g_pool[i].ev, 0));
-          SB2H_CUDA (cudaStreamWaitEvent (cx->stream_hi, g_pool[i].ev, 0));
-        }
         pthread_mutex_unlock (&g_pool_mutex);
+        if (wait) {
+          /* (the event is only re-recorded by the next free of this slot, which is this caller's) */
+          SB2H_CUDA (cudaStreamWaitEvent (cx->stream, ev, 0));
+          if (cx->stream_hi != cx->stream) SB2H_CUDA (cudaStreamWaitEvent (cx->stream_hi, ev, 0));
+        }
         return p;
       }
       if (idle_slot < 0) idle_slot = i;
@@ -381,16 +416,24 @@ sb2h_pool_alloc (size_t bytes)
   if (free_slot < 0) {
     /* table full: recycle an idle block of another size */
     if (idle_slot < 0) sb2h_fatal (__func__, "device block pool exhausted (%d blocks in use)", SB2H_POOL_SLOTS);
-    if (g_pool[idle_slot].ev_valid) SB2H_CUDA (cudaEventSynchronize (g_pool[idle_slot].ev));
-    SB2H_CUDA (cudaFree (g_pool[idle_slot].ptr));
-    g_pool[idle_slot].ptr = NULL;
+    old = g_pool[idle_slot].ptr;
+    if (g_pool[idle_slot].ev_valid) old_ev = g_pool[idle_slot].ev;
     free_slot = idle_slot;
   }
-  SB2H_CUDA (cudaMalloc (&g_pool[free_slot].ptr, bytes + 256));
-  g_pool[free_slot].bytes = bytes;
+  /* reserve the slot: in use, with a pointer no caller can hold, until the block exists */
+  g_pool[free_slot].ptr = (void *) &g_pool[free_slot];
+  g_pool[free_slot].bytes = 0;
   g_pool[free_slot].in_use = 1;
   g_pool[free_slot].ev_valid = 0;
-  p = g_pool[free_slot].ptr;
+  pthread_mutex_unlock (&g_pool_mutex);
+  if (old) {
+    if (old_ev) SB2H_CUDA (cudaEventSynchronize (old_ev));
+    SB2H_CUDA (cudaFree (old));
+  }
+  SB2H_CUDA (cudaMalloc (&p, bytes + 256));
+  pthread_mutex_lock (&g_pool_mutex);
+  g_pool[free_slot].ptr = p;
+  g_pool[free_slot].bytes = bytes;
   pthread_mutex_unlock (&g_pool_mutex);
   return p;
 }
@@ -399,21 +442,22 @@ void
 sb2h_pool_free (void *ptr)
 {
   Sb2hContext *cx;
-  int i;
+  cudaEvent_t ev = NULL;
+  int i, slot = -1;
   if (!ptr) return;
   cx = sb2h_context ();
   pthread_mutex_lock (&g_pool_mutex);
   for (i = 0; i < SB2H_POOL_SLOTS; i++)
-    if (g_pool[i].ptr == ptr) {
-      if (!g_pool[i].ev) SB2H_CUDA (cudaEventCreateWithFlags (&g_pool[i].ev, cudaEventDisableTiming));
-      SB2H_CUDA (cudaEventRecord (g_pool[i].ev, cx->stream));
-      g_pool[i].ev_valid = 1;
-      g_pool[i].in_use = 0;
-      pthread_mutex_unlock (&g_pool_mutex);
-      return;
-    }
+    if (g_pool[i].ptr == ptr && g_pool[i].in_use) { slot = i; ev = g_pool[i].ev; break; }
   pthread_mutex_unlock (&g_pool_mutex);
-  sb2h_fatal (__func__, "%p is not a pooled device block", ptr);
+  if (slot < 0) sb2h_fatal (__func__, "%p is not a pooled device block in use", ptr);
+  if (!ev) SB2H_CUDA (cudaEventCreateWithFlags (&ev, cudaEventDisableTiming));
+  SB2H_CUDA (cudaEventRecord (ev, cx->stream));
+  pthread_mutex_lock (&g_pool_mutex);
+  g_pool[slot].ev = ev;
+  g_pool[slot].ev_valid = 1;
+  g_pool[slot].in_use = 0;
+  pthread_mutex_unlock (&g_pool_mutex);
 }
 
 /* idle blocks go back to the driver when the last thread context is released */
@@ -441,7 +485,7 @@ void *
 sb2h_pinned_pool_alloc (size_t bytes)
 {
   int i, free_slot = -1;
-  void *p = NULL;
+  void *p = NULL, *old = NULL;
   pthread_mutex_lock (&g_pinned_mutex);
   for (i = 0; i < SB2H_PINNED_SLOTS; i++) {
     if (g_pinned[i].ptr && !g_pinned[i].in_use && g_pinned[i].bytes == bytes) {
@@ -451,22 +495,29 @@ sb2h_pinned_pool_alloc (size_t bytes)
     }
     if (!g_pinned[i].ptr && free_slot < 0) free_slot = i;
   }
-  if (!p) {
-    if (free_slot < 0) {
-      for (i = 0; i < SB2H_PINNED_SLOTS; i++)
-        if (!g_pinned[i].in_use) {
-          SB2H_CUDA (cudaFreeHost (g_pinned[i].ptr));
-          g_pinned[i].ptr = NULL;
-          free_slot = i;
-          break;
-        }
-      if (free_slot < 0) sb2h_fatal (__func__, "pinned block pool exhausted");
-    }
-    SB2H_CUDA (cudaHostAlloc (&g_pinned[free_slot].ptr, bytes, cudaHostAllocPortable));
-    g_pinned[free_slot].bytes = bytes;
-    g_pinned[free_slot].in_use = 1;
-    p = g_pinned[free_slot].ptr;
+  if (p) {
+    pthread_mutex_unlock (&g_pinned_mutex);
+    return p;
   }
+  if (free_slot < 0) {
+    for (i = 0; i < SB2H_PINNED_SLOTS; i++)
+      if (!g_pinned[i].in_use) {
+        old = g_pinned[i].ptr;
+        free_slot = i;
+        break;
+      }
+    if (free_slot < 0) sb2h_fatal (__func__, "pinned block pool exhausted");
+  }
+  /* the slot is reserved (in use, pointer nobody holds) while the driver call runs outside the lock */
+  g_pinned[free_slot].ptr = (void *) &g_pinned[free_slot];
+  g_pinned[free_slot].bytes = 0;
+  g_pinned[free_slot].in_use = 1;
+  pthread_mutex_unlock (&g_pinned_mutex);
+  if (old) SB2H_CUDA (cudaFreeHost (old));
+  SB2H_CUDA (cudaHostAlloc (&p, bytes, cudaHostAllocPortable));
+  pthread_mutex_lock (&g_pinned_mutex);
+  g_pinned[free_slot].ptr = p;
+  g_pinned[free_slot].bytes = bytes;
   pthread_mutex_unlock (&g_pinned_mutex);
   return p;
 }
@@ -506,9 +557,11 @@ sb2h_copy_rect (Sb2hContext *cx, void *dst, size_t dst_stride, const void *src,
 typedef struct {
   SchroMemoryDomain *domain;
   int slot, nev;
+  unsigned long long seq;          /* order of parking: the oldest parked block is the likeliest to be free */
   cudaEvent_t ev[SB2H_MAX_CTX];
 } Sb2hLimbo;
 static Sb2hLimbo *g_limbo[SB2H_LIMBO];
+static unsigned long long g_limbo_seq;
 static cudaEvent_t g_evpool[SB2H_LIMBO * 4];
 static int g_nevpool;
 static pthread_mutex_t g_limbo_mutex = PTHREAD_MUTEX_INITIALIZER;
@@ -709,22 +762,27 @@ schro_memory_domain_alloc (SchroMemoryDomain *domain, int size)
   if (!ptr && (domain->flags & SCHRO_MEMORY_DOMAIN_CUDA)) {
     /* a parked block of this size beats a new cudaMalloc (which would stall the whole device,
      * and a caller that never waits would otherwise grow the domain without bound) */
-    int parked = 0;
+    Sb2hLimbo *l = NULL;
+    int at = -1;
     pthread_mutex_lock (&g_limbo_mutex);
     for (i = 0; i < SB2H_LIMBO; i++)
-      if (g_limbo[i] && g_limbo[i]->domain == domain && domain->slots[g_limbo[i]->slot].size == size) parked = 1;
+      if (g_limbo[i] && g_limbo[i]->domain == domain && domain->slots[g_limbo[i]->slot].size == size &&
+          (at < 0 || g_limbo[i]->seq < g_limbo[at]->seq)) at = i;
+    if (at >= 0) { l = g_limbo[at]; g_limbo[at] = NULL; }
     pthread_mutex_unlock (&g_limbo_mutex);
-    if (parked) {
-      limbo_reap (domain, 1);
-      for (i = 0; i < SCHRO_MEMORY_DOMAIN_SLOTS; i++) {
-        unsigned int f = domain->slots[i].flags;
-        if ((f & SCHRO_MEMORY_DOMAIN_SLOT_ALLOCATED) && !(f & SCHRO_MEMORY_DOMAIN_SLOT_IN_USE) &&
-            domain->slots[i].size == size) {
-          domain->slots[i].flags |= SCHRO_MEMORY_DOMAIN_SLOT_IN_USE;
-          ptr = domain->slots[i].ptr;
-          break;
-        }
-      }
+    if (l) {
+      /* the block is this caller's now (its slot stays marked in use throughout); the wait for the work that
+       * was in flight when it was handed back happens with no lock held, so other threads' allocs and frees
+       * of the domain go on meanwhile */
+      int k;
+      pthread_mutex_unlock (domain->mutex);
+      for (k = 0; k < l->nev; k++) SB2H_CUDA (cudaEventSynchronize (l->ev[k]));
+      pthread_mutex_lock (&g_limbo_mutex);
+      for (k = 0; k < l->nev; k++) evpool_put (l->ev[k]);
+      pthread_mutex_unlock (&g_limbo_mutex);
+      ptr = domain->slots[l->slot].ptr;
+      free (l);
+      return ptr;
     }
   }
   if (!ptr) {
@@ -773,7 +831,7 @@ schro_memory_domain_memfree (SchroMemoryDomain *domain, void *ptr)
         if (l->nev) {
           pthread_mutex_lock (&g_limbo_mutex);
           for (k = 0; k < SB2H_LIMBO && g_limbo[k]; k++) ;
-          if (k < SB2H_LIMBO) g_limbo[k] = l;
+          if (k < SB2H_LIMBO) { l->seq = g_limbo_seq++; g_limbo[k] = l; }
           pthread_mutex_unlock (&g_limbo_mutex);
           if (k == SB2H_LIMBO) {
             /* no room to park it: wait here */

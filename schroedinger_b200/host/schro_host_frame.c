@@ -629,8 +629,8 @@ motion_render (SchroMotion *motion, SchroFrame *dest, SchroFrame *addframe, int 
   stage_in (cx, &res, addframe, SB2H_BUF_AUX1, 1);
   if (output_frame) stage_in (cx, &out, output_frame, SB2H_BUF_AUX2, 1);
   dmv = sb2h_dev_buffer (cx, SB2H_BUF_AUX3, nmv * sizeof (SchroMotionVector));
-  SB2H_CUDA (cudaMemcpyAsync (dmv, motion->motion_vectors, nmv * sizeof (SchroMotionVector),
-          cudaMemcpyDefault, cx->stream));
+  /* the vectors come from plain malloc'd memory (schro_motion_new): staged through the thread's page-locked block */
+  sb2h_upload_staged (cx, dmv, motion->motion_vectors, nmv * sizeof (SchroMotionVector));
   /* the rendered area is dest's (schromotion8.c:722-751); addframe may be iwt-padded */
   if (use_ref_renderer) {
     /* global motion: the reference's per-pixel renderer (schromotion.c:113-121, schromotionref.c:245-330) */

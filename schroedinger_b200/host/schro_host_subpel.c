@@ -36,7 +36,7 @@ schro_b200_motion_predict_subpel_deep (SchroParams *params, double lambda, Schro
     if (!up->upsample_done) schro_upsampled_frame_upsample (up);
     sb2h_level_slab (cx, up, &dev_ref[ref], &rs);
     dev_field[ref] = sb2h_pool_alloc (n * sizeof (SchroMotionVector));
-    SB2H_CUDA (cudaMemcpyAsync (dev_field[ref], mf->motion_vectors, n * sizeof (SchroMotionVector), cudaMemcpyDefault, cx->stream));
+    sb2h_upload_staged (cx, dev_field[ref], mf->motion_vectors, n * sizeof (SchroMotionVector));
     memset (&p, 0, sizeof (p));
     p.xblen = params->xbsep_luma;
     p.yblen = params->ybsep_luma;

@@ -17,7 +17,7 @@ names = ["H2D coefficients", "inverse wavelet", "motion render", "edge-extend + 
          "pyramid", "hbm_new", "hbm_scan", "scan_hint level 0", "hbm_unref"]
 out = (ctypes.c_double * 16)()
 hf.drv.sb2_e2e_times(1, None)
-N, wall = 6, 0.0
+N, wall = 10, 0.0
 hf.drv.sb2_e2e_step.restype = ctypes.c_double
 for _ in range(N):
     wall += hf.drv.sb2_e2e_step()
