@@ -297,6 +297,39 @@ int sb2_subpel_refine (const sb2_subpel_params *params, const sb2_slab *orig, co
     int upref_extension, void *field, size_t field_picture_pitch, void *workspace, size_t workspace_bytes,
     void *stream);
 
+/* The split-2 pass of the encoder's mode decision for every picture of the slabs: schro_do_split2 +
+ * schro_motion_copy_to (schroedinger/schromotionest.c:1601-1802, 1511-1523) for every superblock, the first
+ * step of schro_mode_decision (:2587-2685).  Per block the candidates are each reference's sub-pel vector
+ * (luma SAD from the field + chroma SADs, schro_get_split2_metric :1527-1594), both together
+ * (schro_metric_get_biref) and a DC block (schro_block_average :481-516); cost = entropy + lambda * error.
+ *   orig            the source picture, three u8 components
+ *   upref0/upref1   the upsampled (4-phase), edge-extended references, three components (upref1 and field1
+ *                   may be NULL with one reference)
+ *   field0/field1   device fields of the two references at mv_precision (the sub-pel refinement's output,
+ *                   copied into split2_mf at schroedinger/schroencoder.c:2340-2349), pictures
+ *                   `field_picture_pitch` vectors apart
+ *   motion          receives x_num_blocks * y_num_blocks decided SchroMotionVectors per picture
+ *   sb_error / sb_entropy   SchroBlock.error / .entropy of every superblock, (x_num_blocks / 4) *
+ *                   (y_num_blocks / 4) ints per picture, pictures packed; SchroBlock.score =
+ *                   entropy + lambda * error
+ * Results are the reference's bit for bit, including where its behaviour is accidental (a single-reference
+ * winner records the luma metric only; with mv_precision >= 2 the bi-reference metrics are taken on a scratch
+ * block the three components share) -- see csrc/split2.cu. */
+typedef struct {
+  int xblen, yblen;                     /* params->xbsep_luma, ybsep_luma */
+  int x_num_blocks, y_num_blocks;       /* multiples of 4; at most 1024 block rows */
+  int mv_precision;                     /* 0..3 */
+  int num_refs;                         /* 1 or 2 */
+  int chroma_h_shift, chroma_v_shift;
+  int orig_extension;                   /* extension of the source frame (enters the bi-reference range test) */
+  double lambda;                        /* schro_me_lambda */
+} sb2_split2_params;
+size_t sb2_split2_workspace_bytes (int x_num_blocks, int y_num_blocks, int count);
+int sb2_split2_decide (const sb2_split2_params *params, const sb2_slab *orig, const sb2_slab *upref0,
+    const sb2_slab *upref1, int upref_extension, const void *field0, const void *field1,
+    size_t field_picture_pitch, void *motion, size_t motion_picture_pitch, int *sb_error, int *sb_entropy,
+    void *workspace, size_t workspace_bytes, void *stream);
+
 /* schro_metric_absdiff_u8 (schroedinger/schrometric.c:10-29) for `n` independent block
  * pairs: sad[i] = SAD(a + a_offset[i], b + b_offset[i]) over width x height. */
 int sb2_sad_u8 (const uint8_t *a, int a_stride, const uint8_t *b, int b_stride,

@@ -154,6 +154,30 @@ void oracle_rough_scan_hint (const OraclePyrLevel *src, const OraclePyrLevel *re
     int x_num_blocks, int y_num_blocks, int ref_index, int shift, int distance,
     const OracleMotionVector *parent, OracleMotionVector *mf);
 
+/* schro_pack_estimate_sint (schroedinger/schropack.c:204-226) and one pixel of a block fetched at sub-pel
+ * precision 0..3 (schroedinger/schroframe.c:2458-2482), shared by oracle_subpel.c and oracle_split2.c */
+int oracle_bits_sint (int value);
+int oracle_subpel_sample (const uint8_t *ref, int rstride, int prec, int x, int y, int a, int b);
+
+/* Split-2 pass of the mode decision (oracle_split2.c): schro_do_split2 + schro_motion_copy_to
+ * (schroedinger/schromotionest.c:1601-1802, 1511-1523) for every superblock.  src: pixel (0,0) of the three
+ * source planes; ref0 / ref1: phase-0 pixel (0,0) of the three planes of each upsampled reference (ref1
+ * unused with one reference), rstride their 4-phase row strides; field0 / field1: the references' sub-pel
+ * fields.  motion: x_num_blocks * y_num_blocks decided blocks; sb_error / sb_entropy: per superblock. */
+typedef struct {
+  int width, height;            /* luma */
+  int h_shift, v_shift;
+  int orig_ext;                 /* extension of the source frame (enters the bi-reference range test) */
+  int xblen, yblen;             /* = xbsep_luma, ybsep_luma */
+  int x_num_blocks, y_num_blocks;
+  int mv_precision, num_refs;
+  double lambda;
+} OracleSplit2Params;
+void oracle_split2_decide (const OracleSplit2Params *p, const uint8_t *const src[3], const int src_stride[3],
+    const uint8_t *const ref0[3], const uint8_t *const ref1[3], const int rstride[3],
+    const OracleMotionVector *field0, const OracleMotionVector *field1, OracleMotionVector *motion,
+    int *sb_error, int *sb_entropy);
+
 /* Sub-pel refinement of one reference's motion field in place (oracle_subpel.c):
  * schro_encoder_motion_predict_subpel_deep (schroedinger/schromotionest.c:246-355) for one reference.
  * orig: luma pixel (0,0) of the source picture (frame extension orig_ext -- it only enters the range

@@ -29,8 +29,14 @@ bits_uint (int value)
   return n + n - 1;
 }
 
-static int
-bits_sint (int value)
+int oracle_bits_sint (int value);
+int oracle_subpel_sample (const uint8_t *ref, int rstride, int prec, int x, int y, int a, int b);
+#define bits_sint oracle_bits_sint
+#define subpel_sample oracle_subpel_sample
+
+/* schro_pack_estimate_sint (schroedinger/schropack.c:204-226) */
+int
+oracle_bits_sint (int value)
 {
   int n;
   if (value < 0) value = -value;
@@ -53,11 +59,13 @@ half_sample (const uint8_t *ref, int rstride, int u, int v, int a, int b)
   return ref[(ptrdiff_t) ph * (rstride >> 2) + (ptrdiff_t) ((v >> 1) + b) * rstride + (u >> 1) + a];
 }
 
-/* pixel (a, b) of the block fetched at (x, y) in units of 2^-prec pixels, prec 1..3 */
-static int
-subpel_sample (const uint8_t *ref, int rstride, int prec, int x, int y, int a, int b)
+/* pixel (a, b) of the block fetched at (x, y) in units of 2^-prec pixels, prec 0..3
+ * (schro_upsampled_frame_get_block_fast_precN, schroedinger/schroframe.c:2458-2482) */
+int
+oracle_subpel_sample (const uint8_t *ref, int rstride, int prec, int x, int y, int a, int b)
 {
   int hx, hy, rx, ry;
+  if (prec == 0) return ref[(ptrdiff_t) (y + b) * rstride + x + a];
   if (prec == 1) return half_sample (ref, rstride, x, y, a, b);
   if (prec == 2) { x <<= 1; y <<= 1; }
   hx = x >> 2; hy = y >> 2; rx = x & 3; ry = y & 3;

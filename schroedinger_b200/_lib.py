@@ -126,6 +126,19 @@ _opt("sb2_subpel_force_generic", None, [ctypes.c_int])
 _opt("sb2_subpel_workspace_bytes", ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int])
 _opt("sb2_subpel_refine", ctypes.c_int, [ctypes.POINTER(SubpelParams), _SP, _SP, ctypes.c_int, ctypes.c_void_p,
                                         ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p])
+
+class Split2Params(ctypes.Structure):
+    """Mirror of sb2_split2_params."""
+    _fields_ = [("xblen", ctypes.c_int), ("yblen", ctypes.c_int), ("x_num_blocks", ctypes.c_int),
+                ("y_num_blocks", ctypes.c_int), ("mv_precision", ctypes.c_int), ("num_refs", ctypes.c_int),
+                ("chroma_h_shift", ctypes.c_int), ("chroma_v_shift", ctypes.c_int), ("orig_extension", ctypes.c_int),
+                ("lambda_", ctypes.c_double)]
+
+
+_opt("sb2_split2_workspace_bytes", ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int])
+_opt("sb2_split2_decide", ctypes.c_int, [ctypes.POINTER(Split2Params), _SP, _SP, _SP, ctypes.c_int, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p])
 _opt("sb2_metric_scan", ctypes.c_int, [_SP, _SP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p])
 _opt("sb2_metric_block_sad3", ctypes.c_int, [_SP, _SP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

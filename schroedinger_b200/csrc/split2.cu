@@ -1,0 +1,411 @@
+// split2.cu -- the split-2 pass of the encoder's mode decision for sm_100a.
+//
+// Bit-exact replacement for schro_do_split2 + schro_motion_copy_to (schroedinger/schromotionest.c:
+// 1601-1802, 1511-1523) applied to every superblock, the first step schro_mode_decision (:2587-2685)
+// takes for each of them.  Per block inside the picture the candidates are each reference's sub-pel
+// vector (luma SAD from the field + chroma SADs at the halved vector, schro_get_split2_metric
+// :1527-1594), both vectors together (schro_metric_get_biref, schroedinger/schrometric.c:273-304) and
+// a DC block (schro_block_average, :481-516); the cost is entropy + lambda * error, the entropy taken
+// against the DECIDED left / up / up-left blocks (schro_motion_block_estimate_entropy :1243-1282,
+// schro_motion_vector_prediction schroedinger/schromotion.c:315-368).
+//
+// The reference does all of it in one loop.  Here, as for the sub-pel refinement (subpel.cu):
+//   split2_candidates_kernel  every pixel sum of a block depends on the block's own field entries only:
+//                             one warp per block, every block of every picture in parallel;
+//   split2_decide_kernel      the decisions form a wavefront: one CTA per picture, one thread per
+//                             block row, row j one block behind row j-1, the decided vectors and modes
+//                             handed down through a 3-deep shared-memory ring.
+// Three properties of the reference are reproduced because results depend on them (oracle_split2.c
+// spells them out): a single-reference winner records the luma metric only as its error; with
+// mv_precision >= 2 the bi-reference fetches of the three components share one scratch block, so the
+// luma metric sees the V prediction in its top-left corner and the U metric is taken against the V
+// prediction; with one reference the DC candidate is tried whenever the best error is positive.
+
+#include "obmc_common.cuh"
+#include <climits>
+#include <math_constants.h>
+
+namespace sb2 {
+
+struct Split2Args {
+  PlaneSet orig, ref[2];
+  const MotionVector *field[2];
+  size_t field_pitch;
+  MotionVector *motion;
+  size_t motion_pitch;
+  int *sb_error, *sb_entropy;       // [count][nsb]
+  unsigned *rec;                    // [count][nby * nbx][8]
+  int pw[3], ph[3];                 // plane sizes
+  int hs, vs, orig_ext, ref_ext;
+  int xblen, yblen, nbx, nby, prec, num_refs, count;
+  double lambda;
+};
+
+constexpr unsigned S2_INSIDE = 1u, S2_BIREF = 2u;
+
+// one sample of the upsampled reference at half-pel (u, v) + pixel offset (a, b); coordinates are
+// held inside the reference's border so that a field with wild vectors cannot read outside the slab
+// (the reference does not test these fetches; fields produced by the search never need the clamp)
+struct RefPlane {
+  const uint8_t *p;
+  int stride, w, h, ext;
+};
+
+__device__ __forceinline__ int half_sample (const RefPlane &r, int u, int v, int a, int b)
+{
+  const int ph = ((v & 1) << 1) | (u & 1);
+  const int x = min (max ((u >> 1) + a, -r.ext), r.w + r.ext - 1), y = min (max ((v >> 1) + b, -r.ext), r.h + r.ext - 1);
+  return __ldg (r.p + (ptrdiff_t) ph * (r.stride >> 2) + (ptrdiff_t) y * r.stride + x);
+}
+
+// schro_upsampled_frame_get_block_fast_precN (schroedinger/schroframe.c:2458-2482), one pixel
+__device__ __forceinline__ int sample (const RefPlane &r, int prec, int x, int y, int a, int b)
+{
+  if (prec == 0) return half_sample (r, x << 1, y << 1, a, b);
+  if (prec == 1) return half_sample (r, x, y, a, b);
+  if (prec == 2) { x <<= 1; y <<= 1; }
+  const int hx = x >> 2, hy = y >> 2, rx = x & 3, ry = y & 3;
+  const int s00 = half_sample (r, hx, hy, a, b);
+  if ((rx | ry) == 0) return s00;
+  if (ry == 0 && rx == 2) return (s00 + half_sample (r, hx + 1, hy, a, b) + 1) >> 1;
+  if (ry == 2 && rx == 0) return (s00 + half_sample (r, hx, hy + 1, a, b) + 1) >> 1;
+  const int s01 = half_sample (r, hx + 1, hy, a, b);
+  const int s10 = half_sample (r, hx, hy + 1, a, b);
+  const int s11 = half_sample (r, hx + 1, hy + 1, a, b);
+  return ((4 - ry) * (4 - rx) * s00 + (4 - ry) * rx * s01 + ry * (4 - rx) * s10 + ry * rx * s11 + 8) >> 4;
+}
+
+__device__ __forceinline__ unsigned warp_sum (unsigned v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync (0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__ (128)
+split2_candidates_kernel (const Split2Args A)
+{
+  const int lane = threadIdx.x & 31;
+  const long long g = (long long) blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int per_pic = A.nbx * A.nby;
+  if (g >= (long long) A.count * per_pic) return;
+  const int pic = (int) (g / per_pic), blk = (int) (g - (long long) pic * per_pic);
+  const int by = blk / A.nbx, bx = blk - by * A.nbx;
+  unsigned *rec = A.rec + ((size_t) pic * per_pic + blk) * 8;
+  if (!(A.pw[0] > bx * A.xblen) || !(A.ph[0] > by * A.yblen)) {
+    if (lane == 0) rec[0] = 0;
+    return;
+  }
+  int cwk[3], chk[3], w[3], h[3], os[3];
+  const uint8_t *op[3];
+  RefPlane rp[2][3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    cwk[k] = k ? A.xblen >> A.hs : A.xblen;
+    chk[k] = k ? A.yblen >> A.vs : A.yblen;
+    w[k] = min (cwk[k], A.pw[k] - bx * cwk[k]);
+    h[k] = min (chk[k], A.ph[k] - by * chk[k]);
+    os[k] = A.orig.stride[k];
+    op[k] = reinterpret_cast<const uint8_t *> (plane_ptr (A.orig, pic, k)) + (ptrdiff_t) (by * chk[k]) * os[k] + bx * cwk[k];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      rp[r][k].p = reinterpret_cast<const uint8_t *> (plane_ptr (A.ref[r], pic, k));
+      rp[r][k].stride = A.ref[r].stride[k];
+      rp[r][k].w = A.pw[k];
+      rp[r][k].h = A.ph[k];
+      rp[r][k].ext = A.ref_ext;
+    }
+  }
+  const MotionVector *f[2] = { A.field[0] + (size_t) pic * A.field_pitch + blk, A.field[1] + (size_t) pic * A.field_pitch + blk };
+  unsigned flags = S2_INSIDE, chroma[2] = { 0, 0 }, bi_luma = 0, bi_chroma = 0, dc_error = 0;
+  int dc[3];
+
+  // DC block: rounded mean and the absolute deviations from it, per component
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int n = w[k] * h[k];
+    unsigned s = 0;
+    for (int p = lane; p < n; p += 32) { const int b = p / w[k], a = p - b * w[k]; s += __ldg (op[k] + (ptrdiff_t) b * os[k] + a); }
+    s = warp_sum (s);
+    const int ave = ((int) s + n / 2) / n;
+    unsigned e = 0;
+    for (int p = lane; p < n; p += 32) { const int b = p / w[k], a = p - b * w[k]; e += (unsigned) abs (ave - (int) __ldg (op[k] + (ptrdiff_t) b * os[k] + a)); }
+    dc_error += warp_sum (e);
+    dc[k] = ave - 128;
+  }
+
+  // each reference alone: U + V SADs at the halved vector (skipped, as in the reference, when the field holds no metric)
+  int vx[2], vy[2];
+  for (int r = 0; r < A.num_refs; r++) {
+    vx[r] = f[r]->v[r];
+    vy[r] = f[r]->v[2 + r];
+    if (f[r]->metric == (unsigned) INT_MAX) continue;
+    const int n = w[1] * h[1];
+    unsigned e = 0;
+    for (int p = lane; p < 2 * n; p += 32) {
+      const int k = p < n ? 1 : 2, q = p < n ? p : p - n;
+      const int b = q / w[1], a = q - b * w[1];
+      const int x = (vx[r] >> A.hs) + ((bx * cwk[1]) << A.prec), y = (vy[r] >> A.vs) + ((by * chk[1]) << A.prec);
+      e += (unsigned) abs ((int) __ldg (op[k] + (ptrdiff_t) b * os[k] + a) - sample (rp[r][k], A.prec, x, y, a, b));
+    }
+    chroma[r] = warp_sum (e);
+  }
+
+  // both references: the range test on the luma blocks, then the three metrics
+  if (A.num_refs > 1) {
+    const int xmin = -A.orig_ext, ymin = -A.orig_ext, xmax = (A.pw[0] << A.prec) + A.orig_ext, ymax = (A.ph[0] << A.prec) + A.orig_ext;
+    bool ok = true;
+    int px[3][2], py[3][2];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        px[k][r] = (k ? vx[r] >> A.hs : vx[r]) + bx * (cwk[k] << A.prec);
+        py[k][r] = (k ? vy[r] >> A.vs : vy[r]) + by * (chk[k] << A.prec);
+      }
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+      if (xmin > px[0][r] || ymin > py[0][r] || !(xmax > px[0][r] + w[0] - 1) || !(ymax > py[0][r] + h[0] - 1)) ok = false;
+    if (ok) {
+      flags |= S2_BIREF;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int n = w[k] * h[k];
+        unsigned e = 0;
+        for (int p = lane; p < n; p += 32) {
+          const int b = p / w[k], a = p - b * w[k];
+          // which component's prediction the reference's shared scratch block holds at (a, b)
+          const int kk = (A.prec >= 2 && (k == 1 || (a < w[2] && b < h[2]))) ? 2 : k;
+          const int p0 = sample (rp[0][kk], A.prec, px[kk][0], py[kk][0], a, b);
+          const int p1 = sample (rp[1][kk], A.prec, px[kk][1], py[kk][1], a, b);
+          e += (unsigned) abs ((int) __ldg (op[k] + (ptrdiff_t) b * os[k] + a) - ((p0 + p1 + 1) >> 1));
+        }
+        e = warp_sum (e);
+        if (k == 0) bi_luma = e; else bi_chroma += e;
+      }
+    }
+  }
+  if (lane == 0) {
+    uint4 *o = reinterpret_cast<uint4 *> (rec);
+    o[0] = make_uint4 (flags, chroma[0], chroma[1], bi_luma);
+    o[1] = make_uint4 (bi_chroma, dc_error, (unsigned) (dc[0] & 0xffff) | ((unsigned) (dc[1] & 0xffff) << 16), (unsigned) (dc[2] & 0xffff));
+  }
+}
+
+// schro_pack_estimate_sint (schroedinger/schropack.c:204-226)
+__device__ __forceinline__ int s2_bits_sint (int v)
+{
+  const unsigned a = (unsigned) abs (v);
+  const int n = 32 - __clz (a + 1);
+  return n + n - 1 + (a ? 1 : 0);
+}
+__device__ __forceinline__ int s2_med3 (int a, int b, int c) { return max (min (a, b), min (max (a, b), c)); }
+
+// a decided block as its neighbours see it: vector of reference 0, vector of reference 1, pred_mode
+struct Decided {
+  unsigned v0, v1, mode;
+};
+
+// schro_motion_vector_prediction (schroedinger/schromotion.c:315-368) from up to three decided neighbours
+__device__ __forceinline__ void s2_predict (const Decided *nb, int n_nb, int mode, int &px, int &py)
+{
+  int vx[3], vy[3], n = 0;
+  for (int t = 0; t < n_nb; t++)
+    if (nb[t].mode & mode) {
+      const unsigned v = mode == 1 ? nb[t].v0 : nb[t].v1;
+      vx[n] = (int) (short) (v & 0xffff);
+      vy[n] = (int) (short) (v >> 16);
+      n++;
+    }
+  if (n == 0) { px = 0; py = 0; }
+  else if (n == 1) { px = vx[0]; py = vy[0]; }
+  else if (n == 2) { px = (vx[0] + vx[1] + 1) >> 1; py = (vy[0] + vy[1] + 1) >> 1; }
+  else { px = s2_med3 (vx[0], vx[1], vx[2]); py = s2_med3 (vy[0], vy[1], vy[2]); }
+}
+
+__global__ void __launch_bounds__ (1024)
+split2_decide_kernel (const Split2Args A)
+{
+  __shared__ unsigned ring_v0[3][1024], ring_v1[3][1024];
+  __shared__ unsigned char ring_mode[3][1024];
+  const int pic = blockIdx.x, j = threadIdx.x;
+  const int per_pic = A.nbx * A.nby, nsbx = A.nbx >> 2;
+  const uint4 *rec = reinterpret_cast<const uint4 *> (A.rec + (size_t) pic * per_pic * 8);
+  const MotionVector *f0 = A.field[0] + (size_t) pic * A.field_pitch, *f1 = A.field[1] + (size_t) pic * A.field_pitch;
+  MotionVector *motion = A.motion + (size_t) pic * A.motion_pitch;
+  int *sb_error = A.sb_error + (size_t) pic * nsbx * (A.nby >> 2), *sb_entropy = A.sb_entropy + (size_t) pic * nsbx * (A.nby >> 2);
+  const bool row = j < A.nby;
+  const int cw = A.xblen >> A.hs, ch = A.yblen >> A.vs;
+  Decided left = { 0, 0, 0 };
+  int acc_error = 0, acc_entropy = 0;
+  const int steps = A.nbx + A.nby - 1;
+  for (int s = 0; s < steps; s++) {
+    const int i = s - j;
+    if (row && i >= 0 && i < A.nbx) {
+      const int blk = j * A.nbx + i;
+      const uint4 c0 = __ldg (rec + (size_t) blk * 2);
+      MotionVector best;
+      best.flags = (2u << 3) | 1u; best.metric = 0; best.chroma_metric = 0; best.v[0] = best.v[1] = best.v[2] = best.v[3] = 0;
+      int best_error = 0, best_entropy = 2;
+      if (c0.x & S2_INSIDE) {
+        const uint4 c1 = __ldg (rec + (size_t) blk * 2 + 1);
+        Decided nb[3];
+        int n_nb = 0;
+        if (i > 0) nb[n_nb++] = left;
+        if (j > 0) { nb[n_nb].v0 = ring_v0[(s + 2) % 3][j - 1]; nb[n_nb].v1 = ring_v1[(s + 2) % 3][j - 1]; nb[n_nb].mode = ring_mode[(s + 2) % 3][j - 1]; n_nb++; }
+        if (i > 0 && j > 0) { nb[n_nb].v0 = ring_v0[(s + 1) % 3][j - 1]; nb[n_nb].v1 = ring_v1[(s + 1) % 3][j - 1]; nb[n_nb].mode = ring_mode[(s + 1) % 3][j - 1]; n_nb++; }
+        const int w0 = min (A.xblen, A.pw[0] - i * A.xblen), h0 = min (A.yblen, A.ph[0] - j * A.yblen);
+        const int w1 = min (cw, A.pw[1] - i * cw), h1 = min (ch, A.ph[1] - j * ch);
+        double min_score = CUDART_INF;
+        int entropy[2] = { 0, 0 };
+        best_entropy = INT_MAX;
+        best_error = INT_MAX;
+        MotionVector mv = best;
+        const unsigned chroma[2] = { c0.y, c0.z };
+        MotionVector fr[2];
+        fr[0] = f0[blk];
+        if (A.num_refs > 1) fr[1] = f1[blk];
+        for (int r = 0; r < A.num_refs; r++) {
+          mv = fr[r];
+          mv.flags = (mv.flags & ~0x1fu) | (2u << 3) | (unsigned) (r + 1);
+          int px, py;
+          s2_predict (nb, n_nb, r + 1, px, py);
+          entropy[r] = s2_bits_sint (mv.v[r] - px) + s2_bits_sint (mv.v[2 + r] - py);
+          int error;
+          if (mv.metric == (unsigned) INT_MAX) error = INT_MAX;
+          else { mv.chroma_metric = chroma[r]; error = (int) (chroma[r] + mv.metric); }
+          const double score = __dadd_rn ((double) entropy[r], __dmul_rn ((double) error, A.lambda));
+          if (min_score > score) { min_score = score; best = mv; best_entropy = entropy[r]; best_error = (int) mv.metric; }
+        }
+        int width0 = 0, height0 = 0, width1 = 0, height1 = 0;
+        if (A.num_refs > 1) {
+          mv.v[0] = fr[0].v[0]; mv.v[2] = fr[0].v[2]; mv.v[1] = fr[1].v[1]; mv.v[3] = fr[1].v[3];
+          mv.flags = (mv.flags & ~0x7u) | 3u;
+          width0 = w0; height0 = h0; width1 = w1; height1 = h1;
+          if (c0.x & S2_BIREF) {
+            mv.metric = c0.w;
+            mv.chroma_metric = c1.x;
+            const double score = __dadd_rn ((double) (entropy[0] + entropy[1]), __dmul_rn ((double) (mv.metric + mv.chroma_metric), A.lambda));
+            if (min_score > score) {
+              best_error = (int) (mv.metric + mv.chroma_metric);
+              best_entropy = entropy[0] + entropy[1];
+              best = mv;
+              min_score = score;
+            }
+          }
+        }
+        if (4 * (width0 * height0 + 2 * width1 * height1) < best_error) {
+          mv.flags = (mv.flags & ~0x1fu) | (2u << 3);
+          mv.v[0] = (int16_t) (c1.z & 0xffff); mv.v[1] = (int16_t) (c1.z >> 16); mv.v[2] = (int16_t) (c1.w & 0xffff);
+          const int error = (int) c1.y;
+          mv.metric = c1.y;
+          const int dc_entropy = s2_bits_sint (mv.v[0]) + s2_bits_sint (mv.v[1]) + s2_bits_sint (mv.v[2]);
+          if (error < best_error) { best = mv; best_error = error; best_entropy = dc_entropy; }
+        }
+      }
+      motion[blk] = best;
+      acc_error = (int) ((unsigned) acc_error + (unsigned) best_error);
+      acc_entropy = (int) ((unsigned) acc_entropy + (unsigned) best_entropy);
+      if ((i & 3) == 3 || i == A.nbx - 1) {
+        atomicAdd (sb_error + (j >> 2) * nsbx + (i >> 2), acc_error);
+        atomicAdd (sb_entropy + (j >> 2) * nsbx + (i >> 2), acc_entropy);
+        acc_error = acc_entropy = 0;
+      }
+      const unsigned mode = best.flags & 3u;
+      left.v0 = (unsigned) (best.v[0] & 0xffff) | ((unsigned) (best.v[2] & 0xffff) << 16);
+      left.v1 = (unsigned) (best.v[1] & 0xffff) | ((unsigned) (best.v[3] & 0xffff) << 16);
+      left.mode = mode;
+      ring_v0[s % 3][j] = left.v0;
+      ring_v1[s % 3][j] = left.v1;
+      ring_mode[s % 3][j] = (unsigned char) mode;
+    }
+    __syncthreads ();
+  }
+}
+
+}  // namespace sb2
+
+using namespace sb2;
+
+extern "C" size_t
+sb2_split2_workspace_bytes (int x_num_blocks, int y_num_blocks, int count)
+{
+  return (size_t) x_num_blocks * (size_t) y_num_blocks * (size_t) count * 32;
+}
+
+extern "C" int
+sb2_split2_decide (const sb2_split2_params *p, const sb2_slab *orig, const sb2_slab *upref0, const sb2_slab *upref1,
+    int upref_extension, const void *field0, const void *field1, size_t field_picture_pitch, void *motion,
+    size_t motion_picture_pitch, int *sb_error, int *sb_entropy, void *workspace, size_t workspace_bytes, void *stream)
+{
+  if (!p || !orig || !upref0 || !field0 || !motion || !sb_error || !sb_entropy)
+    return set_error (SB2_ERR_ARG, "sb2_split2_decide: null argument");
+  if (p->num_refs < 1 || p->num_refs > 2 || (p->num_refs == 2 && (!upref1 || !field1)))
+    return set_error (SB2_ERR_ARG, "sb2_split2_decide: num_refs %d needs that many references and fields", p->num_refs);
+  if (orig->ncomp != 3 || upref0->ncomp != 3 || orig->count != upref0->count ||
+      (p->num_refs == 2 && (upref1->ncomp != 3 || upref1->count != orig->count)))
+    return set_error (SB2_ERR_ARG, "sb2_split2_decide: need three-component slabs of equal count");
+  if (p->xblen < 1 || p->yblen < 1 || p->x_num_blocks < 4 || p->y_num_blocks < 4 || (p->x_num_blocks & 3) || (p->y_num_blocks & 3) ||
+      p->mv_precision < 0 || p->mv_precision > 3 || p->chroma_h_shift < 0 || p->chroma_h_shift > 1 ||
+      p->chroma_v_shift < 0 || p->chroma_v_shift > 1 || (p->xblen >> p->chroma_h_shift) < 1 || (p->yblen >> p->chroma_v_shift) < 1)
+    return set_error (SB2_ERR_ARG, "sb2_split2_decide: bad parameters");
+  if (p->y_num_blocks > 1024)
+    return set_error (SB2_ERR_UNSUPPORTED, "sb2_split2_decide: more than 1024 block rows (%d)", p->y_num_blocks);
+  for (int k = 0; k < 3; k++) {
+    const sb2_slab *refs[2] = { upref0, p->num_refs == 2 ? upref1 : upref0 };
+    for (int r = 0; r < 2; r++)
+      if (refs[r]->width[k] != orig->width[k] || refs[r]->height[k] != orig->height[k])
+        return set_error (SB2_ERR_ARG, "sb2_split2_decide: picture and reference %d differ in size (component %d)", r, k);
+  }
+  if (orig->width[1] != orig->width[2] || orig->height[1] != orig->height[2] ||
+      orig->width[1] != ((orig->width[0] + (1 << p->chroma_h_shift) - 1) >> p->chroma_h_shift) ||
+      orig->height[1] != ((orig->height[0] + (1 << p->chroma_v_shift) - 1) >> p->chroma_v_shift))
+    return set_error (SB2_ERR_ARG, "sb2_split2_decide: chroma planes do not match the chroma shifts");
+  if (upref_extension < 2)
+    return set_error (SB2_ERR_ARG, "sb2_split2_decide: the references need a border");
+  const size_t need = sb2_split2_workspace_bytes (p->x_num_blocks, p->y_num_blocks, orig->count);
+  if (!workspace || workspace_bytes < need || ((size_t) workspace & 15) != 0)
+    return set_error (SB2_ERR_WORKSPACE, "sb2_split2_decide: workspace %zu < %zu (or not 16-byte aligned)", workspace_bytes, need);
+  Split2Args A;
+  A.orig = planeset_from_slab (orig);
+  A.ref[0] = planeset_from_slab (upref0);
+  A.ref[1] = planeset_from_slab (p->num_refs == 2 ? upref1 : upref0);
+  A.field[0] = static_cast<const MotionVector *> (field0);
+  A.field[1] = static_cast<const MotionVector *> (p->num_refs == 2 ? field1 : field0);
+  A.field_pitch = field_picture_pitch;
+  A.motion = static_cast<MotionVector *> (motion);
+  A.motion_pitch = motion_picture_pitch;
+  A.sb_error = sb_error;
+  A.sb_entropy = sb_entropy;
+  A.rec = static_cast<unsigned *> (workspace);
+  for (int k = 0; k < 3; k++) { A.pw[k] = orig->width[k]; A.ph[k] = orig->height[k]; }
+  A.hs = p->chroma_h_shift;
+  A.vs = p->chroma_v_shift;
+  A.orig_ext = p->orig_extension;
+  A.ref_ext = upref_extension;
+  A.xblen = p->xblen;
+  A.yblen = p->yblen;
+  A.nbx = p->x_num_blocks;
+  A.nby = p->y_num_blocks;
+  A.prec = p->mv_precision;
+  A.num_refs = p->num_refs;
+  A.count = orig->count;
+  A.lambda = p->lambda;
+  cudaStream_t st = as_stream (stream);
+  const size_t nsb = (size_t) (A.nbx >> 2) * (A.nby >> 2) * A.count;
+  cudaError_t e = cudaMemsetAsync (sb_error, 0, nsb * sizeof (int), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync (sb_entropy, 0, nsb * sizeof (int), st);
+  if (e != cudaSuccess) return check_cuda (e, "sb2_split2_decide: clearing the superblock sums");
+  const long long warps = (long long) A.nbx * A.nby * A.count;
+  {
+    // algorithmic bytes: the source once, each reference's four phase planes once (1.5 bytes per luma pixel each), the fields, the records
+    const double px = 1.5 * A.pw[0] * A.ph[0] * A.count;
+    LaunchScope scope ("split2_candidates", px * (1.0 + 4.0 * A.num_refs) + (20.0 * A.num_refs + 32.0) * A.nbx * A.nby * A.count, st);
+    split2_candidates_kernel<<<(unsigned) ((warps + 3) / 4), 128, 0, st>>> (A);
+  }
+  {
+    LaunchScope scope ("split2_decide", (32.0 + 20.0 * A.num_refs + 20.0) * A.nbx * A.nby * A.count, st);
+    split2_decide_kernel<<<A.count, min (1024, (A.nby + 31) & ~31), 0, st>>> (A);
+  }
+  return check_cuda (cudaGetLastError (), "split2 kernels launch");
+}

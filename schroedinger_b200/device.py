@@ -444,6 +444,33 @@ def subpel_refine(orig, upref, field, xblen, yblen, x_num_blocks, y_num_blocks, 
                                 ptr, size, _stream_ptr(stream)), "sb2_subpel_refine")
 
 
+def split2_decide(orig, uprefs, fields, xblen, yblen, x_num_blocks, y_num_blocks, mv_precision, lam,
+                  workspace=None, stream=None):
+    """The split-2 pass of schro_mode_decision (schro_do_split2 for every superblock) for every picture:
+    uprefs / fields are lists of one or two upsampled reference slabs / uint8 CUDA tensors (count x nblocks x 20
+    bytes, vectors at mv_precision).  Returns (motion, sb_error, sb_entropy) as CUDA tensors."""
+    import torch
+    from ._lib import Split2Params
+    require_cuda()
+    n = x_num_blocks * y_num_blocks
+    nsb = (x_num_blocks // 4) * (y_num_blocks // 4)
+    count = orig.count
+    p = Split2Params(xblen, yblen, x_num_blocks, y_num_blocks, mv_precision, len(uprefs), 1, 1, orig.layout.extension, lam)
+    motion = torch.empty(count * n * 20, dtype=torch.uint8, device="cuda")
+    sb_error = torch.empty(count * nsb, dtype=torch.int32, device="cuda")
+    sb_entropy = torch.empty(count * nsb, dtype=torch.int32, device="cuda")
+    ws = workspace or _default_ws
+    ptr, size = ws.get(lib.sb2_split2_workspace_bytes(x_num_blocks, y_num_blocks, count))
+    two = len(uprefs) > 1
+    check(lib.sb2_split2_decide(ctypes.byref(p), ctypes.byref(orig.slab), ctypes.byref(uprefs[0].slab),
+                                ctypes.byref(uprefs[1].slab) if two else None, uprefs[0].layout.extension,
+                                ctypes.c_void_p(fields[0].data_ptr()), ctypes.c_void_p(fields[1].data_ptr()) if two else None,
+                                ctypes.c_size_t(n), ctypes.c_void_p(motion.data_ptr()), ctypes.c_size_t(n),
+                                ctypes.c_void_p(sb_error.data_ptr()), ctypes.c_void_p(sb_entropy.data_ptr()),
+                                ptr, size, _stream_ptr(stream)), "sb2_split2_decide")
+    return motion, sb_error.view(count, nsb), sb_entropy.view(count, nsb)
+
+
 def lowdelay_decode(slices, picture_bytes, coeffs, depth, n_horiz_slices, n_vert_slices, slice_bytes_num,
                     slice_bytes_denom, quant_matrix, table_quant, table_offset, picture_pitch=None, stream=None):
     """schro_decoder_decode_lowdelay_transform_data + DC prediction for every picture of `coeffs`;

@@ -569,6 +569,79 @@ def ref_subpel(ref, src, refs, fields, width, height, xblen=8, yblen=8, mv_preci
     return out
 
 
+# ---- split-2 pass of the mode decision (schroedinger/schromotionest.c:1601-1802) ------------------------
+REF_ME_PATH = os.path.join(ROOT, "oracle", "_ref", "libschro_ref_me.so")
+
+
+def load_ref_me():
+    """schromotionest.c's file-static functions (oracle/ref_me_static.c), or None."""
+    if not os.path.exists(REF_ME_PATH) or not os.path.exists(REF_PATH):
+        return None
+    ctypes.CDLL(REF_PATH, mode=ctypes.RTLD_GLOBAL)
+    return ctypes.CDLL(REF_ME_PATH, mode=ctypes.RTLD_LOCAL)
+
+
+class OracleSplit2Params(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("width", "height", "h_shift", "v_shift", "orig_ext", "xblen", "yblen",
+                                            "x_num_blocks", "y_num_blocks", "mv_precision", "num_refs")] + [("lam", ctypes.c_double)]
+
+
+def split2_case(oracle, width, height, rng, mv_precision=2, num_refs=2, pans=((5, 3), (-4, 2)), lam=0.1):
+    """Source, references and the references' sub-pel fields (block matching, then the sub-pel refinement:
+    what schro_encoder_mode_decision copies into split2_mf, schroedinger/schroencoder.c:2340-2349)."""
+    src, refs, fields = subpel_case(oracle, width, height, rng, pans=pans, num_refs=num_refs)
+    if mv_precision > 0:
+        fields = oracle_subpel(oracle, src, refs, fields, width, height, 8, 8, mv_precision, lam)
+    return src, refs, fields
+
+
+def oracle_split2(oracle, src, refs, fields, width, height, xblen=8, yblen=8, mv_precision=2, lam=0.1, orig_ext=32):
+    """-> (motion, sb_error, sb_entropy) through oracle_split2_decide"""
+    nbx, nby = hbm_block_counts(width, height, xblen, yblen)
+    p = OracleSplit2Params(width, height, 1, 1, orig_ext, xblen, yblen, nbx, nby, mv_precision, len(refs), lam)
+    P = ctypes.c_void_p * 3
+    I = ctypes.c_int * 3
+    srcs = [np.ascontiguousarray(a) for a in src]
+    ups = [[_luma_up(oracle, a) for a in rf] for rf in refs]
+    motion = np.zeros(nbx * nby, MV_DTYPE)
+    nsb = (nbx // 4) * (nby // 4)
+    sb_error, sb_entropy = np.zeros(nsb, np.int32), np.zeros(nsb, np.int32)
+    up1 = ups[1] if len(ups) > 1 else ups[0]
+    f1 = fields[1] if len(fields) > 1 else fields[0]
+    fn = oracle.oracle_split2_decide
+    fn.restype = None
+    fn.argtypes = [ctypes.c_void_p] * 11
+    fn(ctypes.byref(p), P(*[a.ctypes.data for a in srcs]), I(*[a.strides[0] for a in srcs]),
+       P(*[u.buf.ctypes.data + u.origin for u in ups[0]]), P(*[u.buf.ctypes.data + u.origin for u in up1]),
+       I(*[u.stride for u in ups[0]]), fields[0].ctypes.data, f1.ctypes.data, motion.ctypes.data,
+       sb_error.ctypes.data, sb_entropy.ctypes.data)
+    return motion, sb_error, sb_entropy
+
+
+def ref_split2(ref_me, src, refs, fields, width, height, xblen=8, yblen=8, mv_precision=2, lam=0.1):
+    """The same through the compiled reference's schro_do_split2 (oracle/ref_me_static.c)."""
+    nbx, nby = hbm_block_counts(width, height, xblen, yblen)
+    P = ctypes.c_void_p * 3
+    I = ctypes.c_int * 3
+    q = (ctypes.c_int * 6)(width, height, xblen, yblen, mv_precision, len(refs))
+    f = [x.copy() for x in fields]
+    motion = np.zeros(nbx * nby, MV_DTYPE)
+    nsb = (nbx // 4) * (nby // 4)
+    sb_error, sb_entropy = np.zeros(nsb, np.int32), np.zeros(nsb, np.int32)
+    nx, ny = ctypes.c_int(), ctypes.c_int()
+    r1 = refs[1] if len(refs) > 1 else refs[0]
+    fn = ref_me.ref_split2_pass
+    fn.restype = None
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_double] + [ctypes.c_void_p] * 13
+    fn(q, lam, P(*[a.ctypes.data for a in src]), I(*[a.strides[0] for a in src]),
+       P(*[a.ctypes.data for a in refs[0]]), I(*[a.strides[0] for a in refs[0]]),
+       P(*[a.ctypes.data for a in r1]), I(*[a.strides[0] for a in r1]),
+       f[0].ctypes.data, f[1].ctypes.data if len(f) > 1 else None, motion.ctypes.data,
+       sb_error.ctypes.data, sb_entropy.ctypes.data, ctypes.byref(nx), ctypes.byref(ny))
+    assert (nx.value, ny.value) == (nbx, nby)
+    return motion, sb_error, sb_entropy
+
+
 # ---- low-delay slices (schroedinger/schrolowdelay.c) -----------------------------------------------
 class BitWriter:
     def __init__(self):
