@@ -695,6 +695,11 @@ def next_rows(torch, dev, world, all_ranks, barrier):
     out["subpel_refine_1080p"] = {
         "what": "schro_encoder_motion_predict_subpel_deep, one reference, mv_precision 2 (two passes of 8 probes per block)",
         "batch_per_gpu": count, "value": round(count * world / (ms * 1e-3), 1), "unit": "frames/s", "ms_per_step": round(ms, 4)}
+    # ---- split-2 pass of the mode decision on the refined field (one reference here: the row's pictures have one)
+    ms = timed(lambda: dev.split2_decide(orig, [up], [work], BLOCK["xbsep"], BLOCK["ybsep"], nbx, nby, 2, 0.1))
+    out["mode_decision_split2_1080p"] = {
+        "what": "schro_do_split2 for every superblock (chroma SADs, DC candidates, entropy + lambda * error decisions), one reference, mv_precision 2",
+        "batch_per_gpu": count, "value": round(count * world / (ms * 1e-3), 1), "unit": "frames/s", "ms_per_step": round(ms, 4)}
     return out
 
 

@@ -325,6 +325,8 @@ typedef struct {
   double lambda;                        /* schro_me_lambda */
 } sb2_split2_params;
 size_t sb2_split2_workspace_bytes (int x_num_blocks, int y_num_blocks, int count);
+/* full 8 x 8 blocks take a fixed lane map; on != 0 sends every block through the per-pixel path (tests run both) */
+void sb2_split2_force_generic (int on);
 int sb2_split2_decide (const sb2_split2_params *params, const sb2_slab *orig, const sb2_slab *upref0,
     const sb2_slab *upref1, int upref_extension, const void *field0, const void *field1,
     size_t field_picture_pitch, void *motion, size_t motion_picture_pitch, int *sb_error, int *sb_entropy,

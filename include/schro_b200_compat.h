@@ -454,6 +454,18 @@ void schro_rough_me_heirarchical_scan_hint (SchroRoughME *rme, int shift, int di
 void schro_b200_motion_predict_subpel_deep (SchroParams *params, double lambda, SchroFrame *orig_frame,
     SchroFrame **upsampled_refs, SchroMotionField **subpel_mfs);
 
+/* ---- split-2 pass of the mode decision (schroedinger/schromotionest.c:1601-1802, 1511-1523) ----
+ * schro_do_split2 (static, takes the private SchroMe) + schro_motion_copy_to for every superblock in raster
+ * order: what schro_mode_decision (:2587-2685) produces when the split-1 / split-0 candidates never win.
+ * The things schro_do_split2 reads through the SchroMe accessors are passed explicitly:
+ *   params, lambda, orig_frame, upsampled_refs[r]   as for the sub-pel refinement above
+ *   split2_mfs[r]      schro_me_split2_mf (me, r): the references' sub-pel fields (read only)
+ *   motion             schro_me_motion: motion->motion_vectors receives the decided blocks
+ *   sb_error / sb_entropy   SchroBlock.error / .entropy per superblock ((x_num_blocks / 4) * (y_num_blocks / 4)
+ *                      ints, raster order; either may be NULL); SchroBlock.score = entropy + lambda * error */
+void schro_b200_mode_decision_split2 (SchroParams *params, double lambda, SchroFrame *orig_frame,
+    SchroFrame **upsampled_refs, SchroMotionField **split2_mfs, SchroMotion *motion, int *sb_error, int *sb_entropy);
+
 /* ---- inverse transform + combine (schroedinger/schrodecoder.c:1809-1853 + 2054-2061) ----
  * new: schro_frame_inverse_iwt_transform (frame, params) + schro_frame_shift_right (frame, shift) +
  * schro_frame_convert (output, frame) -- the decoder's path for a non-reference intra picture -- as ONE call;

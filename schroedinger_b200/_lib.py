@@ -135,6 +135,7 @@ class Split2Params(ctypes.Structure):
                 ("lambda_", ctypes.c_double)]
 
 
+_opt("sb2_split2_force_generic", None, [ctypes.c_int])
 _opt("sb2_split2_workspace_bytes", ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int])
 _opt("sb2_split2_decide", ctypes.c_int, [ctypes.POINTER(Split2Params), _SP, _SP, _SP, ctypes.c_int, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,

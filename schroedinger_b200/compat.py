@@ -207,6 +207,10 @@ _proto("schro_motion_field_free", None, [ctypes.POINTER(SchroMotionField)])
 _proto("schro_b200_motion_predict_subpel_deep", None,
        [ParamsP, ctypes.c_double, FrameP, ctypes.POINTER(FrameP), ctypes.POINTER(ctypes.POINTER(SchroMotionField))])
 
+_proto("schro_b200_mode_decision_split2", None,
+       [ParamsP, ctypes.c_double, FrameP, ctypes.POINTER(FrameP), ctypes.POINTER(ctypes.POINTER(SchroMotionField)),
+        ctypes.POINTER(SchroMotion), ctypes.c_void_p, ctypes.c_void_p])
+
 _NP = {0x00: np.uint8, 0x04: np.int16, 0x08: np.int32}
 
 

@@ -82,6 +82,37 @@ __device__ __forceinline__ unsigned warp_sum (unsigned v)
   return v;
 }
 
+// the four taps of a block fetched at (x, y) in units of 2^-prec pixels, as offsets from the plane's pixel (0, 0),
+// with the unified weights of obmc_common.cuh; [x0, x1] x [y0, y1] = the pixels the taps of sample (0, 0) touch
+__device__ __forceinline__ void s2_blkref (BlkRef &br, int rstride, int prec, int x, int y, int &x0, int &x1, int &y0, int &y1)
+{
+  const int q = rstride >> 2;
+  int hx, hy, rx = 0, ry = 0;
+  if (prec == 0) { hx = x << 1; hy = y << 1; }
+  else if (prec == 1) { hx = x; hy = y; }
+  else {
+    if (prec == 2) { x <<= 1; y <<= 1; }
+    hx = x >> 2; hy = y >> 2; rx = x & 3; ry = y & 3;
+  }
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const int u = hx + (t & 1), v = hy + (t >> 1);
+    br.o[t] = (((v & 1) << 1) | (u & 1)) * q + (v >> 1) * rstride + (u >> 1);
+  }
+  const unsigned w00 = (4 - ry) * (4 - rx), w01 = (4 - ry) * rx, w10 = ry * (4 - rx), w11 = ry * rx;
+  br.w = w00 | (w01 << 8) | (w10 << 16) | (w11 << 24);
+  x0 = hx >> 1; x1 = (hx + 1) >> 1; y0 = hy >> 1; y1 = (hy + 1) >> 1;
+}
+
+// sum within each half of the warp (lanes 0-15, lanes 16-31)
+__device__ __forceinline__ unsigned half_sum (unsigned v)
+{
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync (0xffffffffu, v, o);
+  return v;
+}
+
+template <bool FAST_OK>
 __global__ void __launch_bounds__ (128)
 split2_candidates_kernel (const Split2Args A)
 {
@@ -119,55 +150,118 @@ split2_candidates_kernel (const Split2Args A)
   const MotionVector *f[2] = { A.field[0] + (size_t) pic * A.field_pitch + blk, A.field[1] + (size_t) pic * A.field_pitch + blk };
   unsigned flags = S2_INSIDE, chroma[2] = { 0, 0 }, bi_luma = 0, bi_chroma = 0, dc_error = 0;
   int dc[3];
-
-  // DC block: rounded mean and the absolute deviations from it, per component
+  // vectors and fetch positions: luma for the bi-reference candidate, chroma for it and for each reference alone
+  int vx[2] = { 0, 0 }, vy[2] = { 0, 0 }, lx[2], ly[2], cx[2], cy[2];
+  bool have[2] = { false, false };
 #pragma unroll
-  for (int k = 0; k < 3; k++) {
-    const int n = w[k] * h[k];
-    unsigned s = 0;
-    for (int p = lane; p < n; p += 32) { const int b = p / w[k], a = p - b * w[k]; s += __ldg (op[k] + (ptrdiff_t) b * os[k] + a); }
-    s = warp_sum (s);
-    const int ave = ((int) s + n / 2) / n;
-    unsigned e = 0;
-    for (int p = lane; p < n; p += 32) { const int b = p / w[k], a = p - b * w[k]; e += (unsigned) abs (ave - (int) __ldg (op[k] + (ptrdiff_t) b * os[k] + a)); }
-    dc_error += warp_sum (e);
-    dc[k] = ave - 128;
-  }
-
-  // each reference alone: U + V SADs at the halved vector (skipped, as in the reference, when the field holds no metric)
-  int vx[2], vy[2];
-  for (int r = 0; r < A.num_refs; r++) {
-    vx[r] = f[r]->v[r];
-    vy[r] = f[r]->v[2 + r];
-    if (f[r]->metric == (unsigned) INT_MAX) continue;
-    const int n = w[1] * h[1];
-    unsigned e = 0;
-    for (int p = lane; p < 2 * n; p += 32) {
-      const int k = p < n ? 1 : 2, q = p < n ? p : p - n;
-      const int b = q / w[1], a = q - b * w[1];
-      const int x = (vx[r] >> A.hs) + ((bx * cwk[1]) << A.prec), y = (vy[r] >> A.vs) + ((by * chk[1]) << A.prec);
-      e += (unsigned) abs ((int) __ldg (op[k] + (ptrdiff_t) b * os[k] + a) - sample (rp[r][k], A.prec, x, y, a, b));
+  for (int r = 0; r < 2; r++) {
+    if (r < A.num_refs) {
+      vx[r] = f[r]->v[r];
+      vy[r] = f[r]->v[2 + r];
+      have[r] = f[r]->metric != (unsigned) INT_MAX;
     }
-    chroma[r] = warp_sum (e);
+    lx[r] = vx[r] + bx * (cwk[0] << A.prec);
+    ly[r] = vy[r] + by * (chk[0] << A.prec);
+    cx[r] = (vx[r] >> A.hs) + bx * (cwk[1] << A.prec);
+    cy[r] = (vy[r] >> A.vs) + by * (chk[1] << A.prec);
   }
-
-  // both references: the range test on the luma blocks, then the three metrics
-  if (A.num_refs > 1) {
+  bool biref = A.num_refs > 1;
+  if (biref) {
     const int xmin = -A.orig_ext, ymin = -A.orig_ext, xmax = (A.pw[0] << A.prec) + A.orig_ext, ymax = (A.ph[0] << A.prec) + A.orig_ext;
-    bool ok = true;
-    int px[3][2], py[3][2];
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        px[k][r] = (k ? vx[r] >> A.hs : vx[r]) + bx * (cwk[k] << A.prec);
-        py[k][r] = (k ? vy[r] >> A.vs : vy[r]) + by * (chk[k] << A.prec);
-      }
 #pragma unroll
     for (int r = 0; r < 2; r++)
-      if (xmin > px[0][r] || ymin > py[0][r] || !(xmax > px[0][r] + w[0] - 1) || !(ymax > py[0][r] + h[0] - 1)) ok = false;
-    if (ok) {
-      flags |= S2_BIREF;
+      if (xmin > lx[r] || ymin > ly[r] || !(xmax > lx[r] + w[0] - 1) || !(ymax > ly[r] + h[0] - 1)) biref = false;
+    if (biref) flags |= S2_BIREF;
+  }
+
+  // full 8 x 8 blocks (4 x 4 chroma) whose taps all lie inside the references' borders: fixed lane -> pixel map,
+  // tap offsets and weights once per block, every source pixel loaded once
+  bool fast = FAST_OK && w[0] == 8 && h[0] == 8 && w[1] == 4 && h[1] == 4 && A.xblen == 8 && A.yblen == 8 &&
+      os[1] == os[2] && rp[0][1].stride == rp[0][2].stride && rp[1][1].stride == rp[1][2].stride;
+  BlkRef bl[2], bc[2];
+  if (fast) {
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      if (r >= A.num_refs) continue;
+      int x0, x1, y0, y1;
+      s2_blkref (bc[r], rp[r][1].stride, A.prec, cx[r], cy[r], x0, x1, y0, y1);
+      if (x0 < -A.ref_ext || y0 < -A.ref_ext || x1 + 3 > A.pw[1] + A.ref_ext - 1 || y1 + 3 > A.ph[1] + A.ref_ext - 1) fast = false;
+      if (biref) {
+        s2_blkref (bl[r], rp[r][0].stride, A.prec, lx[r], ly[r], x0, x1, y0, y1);
+        if (x0 < -A.ref_ext || y0 < -A.ref_ext || x1 + 7 > A.pw[0] + A.ref_ext - 1 || y1 + 7 > A.ph[0] + A.ref_ext - 1) fast = false;
+      }
+    }
+  }
+  if (fast) {
+    const int la = lane & 7, lb = lane >> 3;                       // luma: pixels (la, lb) and (la, lb + 4)
+    const int ca = lane & 3, cb = (lane >> 2) & 3;                 // chroma: pixel (ca, cb) of U (lanes 0-15) or V (16-31)
+    const bool is_v = lane >= 16;
+    const int ya = __ldg (op[0] + (ptrdiff_t) lb * os[0] + la), yb = __ldg (op[0] + (ptrdiff_t) (lb + 4) * os[0] + la);
+    const int c = __ldg ((is_v ? op[2] : op[1]) + (ptrdiff_t) cb * os[1] + ca);
+    {
+      const int ave_y = ((int) warp_sum ((unsigned) (ya + yb)) + 32) >> 6;
+      const int ave_c = ((int) half_sum ((unsigned) c) + 8) >> 4;
+      dc_error = warp_sum ((unsigned) (abs (ave_y - ya) + abs (ave_y - yb) + abs (ave_c - c)));
+      dc[0] = ave_y - 128;
+      dc[1] = __shfl_sync (0xffffffffu, ave_c, 0) - 128;
+      dc[2] = __shfl_sync (0xffffffffu, ave_c, 16) - 128;
+    }
+    int pc[2] = { 0, 0 };                                          // this lane's chroma prediction from each reference
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      if (r >= A.num_refs) continue;
+      pc[r] = fetch1 (is_v ? rp[r][2].p : rp[r][1].p, bc[r], cb * rp[r][1].stride + ca);
+      chroma[r] = warp_sum ((unsigned) abs (c - pc[r]));
+    }
+    if (biref) {
+      // mv_precision >= 2: the reference's scratch block holds the V prediction where the chroma block lies
+      const bool shared_scratch = A.prec >= 2;
+      int v0 = pc[0], v1 = pc[1];
+      if (shared_scratch) {
+        v0 = __shfl_sync (0xffffffffu, pc[0], (lane & 15) + 16);
+        v1 = __shfl_sync (0xffffffffu, pc[1], (lane & 15) + 16);
+      }
+      bi_chroma = warp_sum ((unsigned) abs (c - ((v0 + v1 + 1) >> 1)));
+      int p0a, p1a;
+      if (shared_scratch && la < 4) {
+        p0a = fetch1 (rp[0][2].p, bc[0], lb * rp[0][1].stride + la);
+        p1a = fetch1 (rp[1][2].p, bc[1], lb * rp[1][1].stride + la);
+      } else {
+        p0a = fetch1 (rp[0][0].p, bl[0], lb * rp[0][0].stride + la);
+        p1a = fetch1 (rp[1][0].p, bl[1], lb * rp[1][0].stride + la);
+      }
+      const int p0b = fetch1 (rp[0][0].p, bl[0], (lb + 4) * rp[0][0].stride + la);
+      const int p1b = fetch1 (rp[1][0].p, bl[1], (lb + 4) * rp[1][0].stride + la);
+      bi_luma = warp_sum ((unsigned) (abs (ya - ((p0a + p1a + 1) >> 1)) + abs (yb - ((p0b + p1b + 1) >> 1))));
+    }
+  } else {
+    // DC block: rounded mean and the absolute deviations from it, per component
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int n = w[k] * h[k];
+      unsigned s = 0;
+      for (int p = lane; p < n; p += 32) { const int b = p / w[k], a = p - b * w[k]; s += __ldg (op[k] + (ptrdiff_t) b * os[k] + a); }
+      s = warp_sum (s);
+      const int ave = ((int) s + n / 2) / n;
+      unsigned e = 0;
+      for (int p = lane; p < n; p += 32) { const int b = p / w[k], a = p - b * w[k]; e += (unsigned) abs (ave - (int) __ldg (op[k] + (ptrdiff_t) b * os[k] + a)); }
+      dc_error += warp_sum (e);
+      dc[k] = ave - 128;
+    }
+    // each reference alone: U + V SADs at the halved vector (skipped, as in the reference, when the field holds no metric)
+    for (int r = 0; r < A.num_refs; r++) {
+      if (!have[r]) continue;
+      const int n = w[1] * h[1];
+      unsigned e = 0;
+      for (int p = lane; p < 2 * n; p += 32) {
+        const int k = p < n ? 1 : 2, q = p < n ? p : p - n;
+        const int b = q / w[1], a = q - b * w[1];
+        e += (unsigned) abs ((int) __ldg (op[k] + (ptrdiff_t) b * os[k] + a) - sample (rp[r][k], A.prec, cx[r], cy[r], a, b));
+      }
+      chroma[r] = warp_sum (e);
+    }
+    // both references
+    if (biref) {
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         const int n = w[k] * h[k];
@@ -176,8 +270,8 @@ split2_candidates_kernel (const Split2Args A)
           const int b = p / w[k], a = p - b * w[k];
           // which component's prediction the reference's shared scratch block holds at (a, b)
           const int kk = (A.prec >= 2 && (k == 1 || (a < w[2] && b < h[2]))) ? 2 : k;
-          const int p0 = sample (rp[0][kk], A.prec, px[kk][0], py[kk][0], a, b);
-          const int p1 = sample (rp[1][kk], A.prec, px[kk][1], py[kk][1], a, b);
+          const int p0 = sample (rp[0][kk], A.prec, kk ? cx[0] : lx[0], kk ? cy[0] : ly[0], a, b);
+          const int p1 = sample (rp[1][kk], A.prec, kk ? cx[1] : lx[1], kk ? cy[1] : ly[1], a, b);
           e += (unsigned) abs ((int) __ldg (op[k] + (ptrdiff_t) b * os[k] + a) - ((p0 + p1 + 1) >> 1));
         }
         e = warp_sum (e);
@@ -327,6 +421,11 @@ split2_decide_kernel (const Split2Args A)
 
 using namespace sb2;
 
+// tests run the candidates kernel both ways: the fixed lane map for full 8 x 8 blocks (default) and the per-pixel
+// path every other block takes
+static int g_split2_generic = 0;
+extern "C" void sb2_split2_force_generic (int on) { g_split2_generic = on ? 1 : 0; }
+
 extern "C" size_t
 sb2_split2_workspace_bytes (int x_num_blocks, int y_num_blocks, int count)
 {
@@ -401,7 +500,8 @@ sb2_split2_decide (const sb2_split2_params *p, const sb2_slab *orig, const sb2_s
     // algorithmic bytes: the source once, each reference's four phase planes once (1.5 bytes per luma pixel each), the fields, the records
     const double px = 1.5 * A.pw[0] * A.ph[0] * A.count;
     LaunchScope scope ("split2_candidates", px * (1.0 + 4.0 * A.num_refs) + (20.0 * A.num_refs + 32.0) * A.nbx * A.nby * A.count, st);
-    split2_candidates_kernel<<<(unsigned) ((warps + 3) / 4), 128, 0, st>>> (A);
+    if (g_split2_generic) split2_candidates_kernel<false><<<(unsigned) ((warps + 3) / 4), 128, 0, st>>> (A);
+    else split2_candidates_kernel<true><<<(unsigned) ((warps + 3) / 4), 128, 0, st>>> (A);
   }
   {
     LaunchScope scope ("split2_decide", (32.0 + 20.0 * A.num_refs + 20.0) * A.nbx * A.nby * A.count, st);

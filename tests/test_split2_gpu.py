@@ -11,6 +11,16 @@ pytestmark = pytest.mark.gpu
 ORACLE = helpers.load_oracle()
 
 
+@pytest.fixture(params=["lanes", "pixels"], autouse=True)
+def candidates_path(request):
+    """Every test runs twice: full 8 x 8 blocks through the fixed lane map (default) and through the per-pixel
+    path every other block takes (sb2_split2_force_generic)."""
+    from schroedinger_b200 import lib
+    lib.sb2_split2_force_generic(1 if request.param == "pixels" else 0)
+    yield request.param
+    lib.sb2_split2_force_generic(0)
+
+
 def gpu_split2(cases, w, h, prec, lam):
     """cases: list of (src, refs, fields), run as one batch."""
     from schroedinger_b200 import device as dev
@@ -145,3 +155,36 @@ def test_split2_1080p_properties(cuda):
     # reference 0 is the picture itself: zero chroma error, so it wins wherever its entropy does not lose
     assert ((m["flags"][0][inside] & 3) == 1).mean() > 0.9
     assert int(sb_entropy.sum()) > 0
+
+
+@pytest.mark.parametrize("nrefs", [1, 2])
+def test_split2_drop_in(cuda, nrefs):
+    """schro_b200_mode_decision_split2 on host SchroFrames / SchroMotionFields / SchroMotion."""
+    import ctypes
+    from schroedinger_b200 import compat, lib
+    from tests import test_subpel_gpu as ts
+    w, h, prec, lam = 176, 144, 2, 0.2
+    rng = np.random.default_rng(61 + nrefs)
+    src, refs, fields = helpers.split2_case(ORACLE, w, h, rng, prec, nrefs, lam=lam)
+    want = helpers.oracle_split2(ORACLE, src, refs, fields, w, h, 8, 8, prec, lam)
+    params = compat.make_params(w, h, xbsep=8, ybsep=8, xblen=12, yblen=12)
+    params.num_refs = nrefs
+    params.mv_precision = prec
+    ts.compat_nbx[0], ts.compat_nbx[1] = params.x_num_blocks, params.y_num_blocks
+    fo, ups, mfs = ts._frames_and_fields(compat, lib, w, h, src, refs, fields)
+    FP = compat.FrameP * 2
+    MP = ctypes.POINTER(compat.SchroMotionField) * 2
+    motion = lib.schro_motion_new(ctypes.byref(params), None, None)
+    n = params.x_num_blocks * params.y_num_blocks
+    nsb = n // 16
+    sb_error, sb_entropy = np.zeros(nsb, np.int32), np.zeros(nsb, np.int32)
+    lib.schro_b200_mode_decision_split2(ctypes.byref(params), lam, fo, FP(*ups), MP(*mfs), motion,
+                                        sb_error.ctypes.data, sb_entropy.ctypes.data)
+    got = np.ctypeslib.as_array(ctypes.cast(motion.contents.motion_vectors, ctypes.POINTER(ctypes.c_uint8)),
+                                shape=(n * 20,)).view(helpers.MV_DTYPE)
+    check((got, sb_error, sb_entropy), want, ("drop-in", nrefs))
+    for r in range(nrefs):
+        lib.schro_motion_field_free(mfs[r])
+        lib.schro_frame_unref(ups[r])
+    lib.schro_motion_free(motion)
+    lib.schro_frame_unref(fo)
