@@ -113,7 +113,7 @@ __device__ __forceinline__ unsigned half_sum (unsigned v)
 }
 
 template <bool FAST_OK>
-__global__ void __launch_bounds__ (128)
+__global__ void __launch_bounds__ (128, 5)
 split2_candidates_kernel (const Split2Args A)
 {
   const int lane = threadIdx.x & 31;
@@ -249,14 +249,17 @@ split2_candidates_kernel (const Split2Args A)
       dc[k] = ave - 128;
     }
     // each reference alone: U + V SADs at the halved vector (skipped, as in the reference, when the field holds no metric)
-    for (int r = 0; r < A.num_refs; r++) {
-      if (!have[r]) continue;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      if (r >= A.num_refs || !have[r]) continue;
       const int n = w[1] * h[1];
       unsigned e = 0;
       for (int p = lane; p < 2 * n; p += 32) {
-        const int k = p < n ? 1 : 2, q = p < n ? p : p - n;
+        const bool v = p >= n;
+        const int q = v ? p - n : p;
         const int b = q / w[1], a = q - b * w[1];
-        e += (unsigned) abs ((int) __ldg (op[k] + (ptrdiff_t) b * os[k] + a) - sample (rp[r][k], A.prec, cx[r], cy[r], a, b));
+        const int o = __ldg ((v ? op[2] : op[1]) + (ptrdiff_t) b * (v ? os[2] : os[1]) + a);
+        e += (unsigned) abs (o - (v ? sample (rp[r][2], A.prec, cx[r], cy[r], a, b) : sample (rp[r][1], A.prec, cx[r], cy[r], a, b)));
       }
       chroma[r] = warp_sum (e);
     }
@@ -268,10 +271,12 @@ split2_candidates_kernel (const Split2Args A)
         unsigned e = 0;
         for (int p = lane; p < n; p += 32) {
           const int b = p / w[k], a = p - b * w[k];
-          // which component's prediction the reference's shared scratch block holds at (a, b)
-          const int kk = (A.prec >= 2 && (k == 1 || (a < w[2] && b < h[2]))) ? 2 : k;
-          const int p0 = sample (rp[0][kk], A.prec, kk ? cx[0] : lx[0], kk ? cy[0] : ly[0], a, b);
-          const int p1 = sample (rp[1][kk], A.prec, kk ? cx[1] : lx[1], kk ? cy[1] : ly[1], a, b);
+          // the reference's shared scratch block holds the V prediction where the chroma block lies
+          const bool v = k == 2 || (A.prec >= 2 && (k == 1 || (a < w[2] && b < h[2])));
+          int p0, p1;
+          if (v) { p0 = sample (rp[0][2], A.prec, cx[0], cy[0], a, b); p1 = sample (rp[1][2], A.prec, cx[1], cy[1], a, b); }
+          else if (k == 1) { p0 = sample (rp[0][1], A.prec, cx[0], cy[0], a, b); p1 = sample (rp[1][1], A.prec, cx[1], cy[1], a, b); }
+          else { p0 = sample (rp[0][0], A.prec, lx[0], ly[0], a, b); p1 = sample (rp[1][0], A.prec, lx[1], ly[1], a, b); }
           e += (unsigned) abs ((int) __ldg (op[k] + (ptrdiff_t) b * os[k] + a) - ((p0 + p1 + 1) >> 1));
         }
         e = warp_sum (e);
@@ -300,21 +305,21 @@ struct Decided {
   unsigned v0, v1, mode;
 };
 
-// schro_motion_vector_prediction (schroedinger/schromotion.c:315-368) from up to three decided neighbours
-__device__ __forceinline__ void s2_predict (const Decided *nb, int n_nb, int mode, int &px, int &py)
+// schro_motion_vector_prediction (schroedinger/schromotion.c:315-368) from the three decided neighbours (left, up,
+// up-left; `have` says which exist): those predicted from reference `mode` count -- one: its vector, two: their
+// rounded mean, three: the median
+__device__ __forceinline__ void s2_predict (const Decided &l, const Decided &u, const Decided &ul, unsigned have, int mode, int &px, int &py)
 {
-  int vx[3], vy[3], n = 0;
-  for (int t = 0; t < n_nb; t++)
-    if (nb[t].mode & mode) {
-      const unsigned v = mode == 1 ? nb[t].v0 : nb[t].v1;
-      vx[n] = (int) (short) (v & 0xffff);
-      vy[n] = (int) (short) (v >> 16);
-      n++;
-    }
-  if (n == 0) { px = 0; py = 0; }
-  else if (n == 1) { px = vx[0]; py = vy[0]; }
-  else if (n == 2) { px = (vx[0] + vx[1] + 1) >> 1; py = (vy[0] + vy[1] + 1) >> 1; }
-  else { px = s2_med3 (vx[0], vx[1], vx[2]); py = s2_med3 (vy[0], vy[1], vy[2]); }
+  const bool b0 = (have & 1u) && (l.mode & mode), b1 = (have & 2u) && (u.mode & mode), b2 = (have & 4u) && (ul.mode & mode);
+  const unsigned w0 = mode == 1 ? l.v0 : l.v1, w1 = mode == 1 ? u.v0 : u.v1, w2 = mode == 1 ? ul.v0 : ul.v1;
+  const int x0 = (int) (short) (w0 & 0xffff), y0 = (int) (short) (w0 >> 16);
+  const int x1 = (int) (short) (w1 & 0xffff), y1 = (int) (short) (w1 >> 16);
+  const int x2 = (int) (short) (w2 & 0xffff), y2 = (int) (short) (w2 >> 16);
+  const int n = (int) b0 + (int) b1 + (int) b2;
+  const int sx = (b0 ? x0 : 0) + (b1 ? x1 : 0) + (b2 ? x2 : 0), sy = (b0 ? y0 : 0) + (b1 ? y1 : 0) + (b2 ? y2 : 0);
+  if (n == 3) { px = s2_med3 (x0, x1, x2); py = s2_med3 (y0, y1, y2); }
+  else if (n == 2) { px = (sx + 1) >> 1; py = (sy + 1) >> 1; }
+  else { px = sx; py = sy; }
 }
 
 __global__ void __launch_bounds__ (1024)
@@ -333,21 +338,38 @@ split2_decide_kernel (const Split2Args A)
   Decided left = { 0, 0, 0 };
   int acc_error = 0, acc_entropy = 0;
   const int steps = A.nbx + A.nby - 1;
+  // the next block's record and field entries are in flight while the current block is decided
+  uint4 n0 = make_uint4 (0, 0, 0, 0), n1 = n0;
+  MotionVector nf[2];
+  nf[0].flags = nf[0].metric = nf[0].chroma_metric = 0; nf[0].v[0] = nf[0].v[1] = nf[0].v[2] = nf[0].v[3] = 0;
+  nf[1] = nf[0];
+  if (row) {
+    const int blk = j * A.nbx;
+    n0 = __ldg (rec + (size_t) blk * 2); n1 = __ldg (rec + (size_t) blk * 2 + 1);
+    nf[0] = f0[blk];
+    if (A.num_refs > 1) nf[1] = f1[blk];
+  }
   for (int s = 0; s < steps; s++) {
     const int i = s - j;
     if (row && i >= 0 && i < A.nbx) {
       const int blk = j * A.nbx + i;
-      const uint4 c0 = __ldg (rec + (size_t) blk * 2);
+      const uint4 c0 = n0, c1 = n1;
+      MotionVector fr[2];
+      fr[0] = nf[0];
+      fr[1] = nf[1];
+      if (i + 1 < A.nbx) {
+        n0 = __ldg (rec + (size_t) (blk + 1) * 2); n1 = __ldg (rec + (size_t) (blk + 1) * 2 + 1);
+        nf[0] = f0[blk + 1];
+        if (A.num_refs > 1) nf[1] = f1[blk + 1];
+      }
       MotionVector best;
       best.flags = (2u << 3) | 1u; best.metric = 0; best.chroma_metric = 0; best.v[0] = best.v[1] = best.v[2] = best.v[3] = 0;
       int best_error = 0, best_entropy = 2;
       if (c0.x & S2_INSIDE) {
-        const uint4 c1 = __ldg (rec + (size_t) blk * 2 + 1);
-        Decided nb[3];
-        int n_nb = 0;
-        if (i > 0) nb[n_nb++] = left;
-        if (j > 0) { nb[n_nb].v0 = ring_v0[(s + 2) % 3][j - 1]; nb[n_nb].v1 = ring_v1[(s + 2) % 3][j - 1]; nb[n_nb].mode = ring_mode[(s + 2) % 3][j - 1]; n_nb++; }
-        if (i > 0 && j > 0) { nb[n_nb].v0 = ring_v0[(s + 1) % 3][j - 1]; nb[n_nb].v1 = ring_v1[(s + 1) % 3][j - 1]; nb[n_nb].mode = ring_mode[(s + 1) % 3][j - 1]; n_nb++; }
+        Decided up = { 0, 0, 0 }, ul = { 0, 0, 0 };
+        const unsigned have = (i > 0 ? 1u : 0u) | (j > 0 ? 2u : 0u) | (i > 0 && j > 0 ? 4u : 0u);
+        if (j > 0) { up.v0 = ring_v0[(s + 2) % 3][j - 1]; up.v1 = ring_v1[(s + 2) % 3][j - 1]; up.mode = ring_mode[(s + 2) % 3][j - 1]; }
+        if (i > 0 && j > 0) { ul.v0 = ring_v0[(s + 1) % 3][j - 1]; ul.v1 = ring_v1[(s + 1) % 3][j - 1]; ul.mode = ring_mode[(s + 1) % 3][j - 1]; }
         const int w0 = min (A.xblen, A.pw[0] - i * A.xblen), h0 = min (A.yblen, A.ph[0] - j * A.yblen);
         const int w1 = min (cw, A.pw[1] - i * cw), h1 = min (ch, A.ph[1] - j * ch);
         double min_score = CUDART_INF;
@@ -356,14 +378,13 @@ split2_decide_kernel (const Split2Args A)
         best_error = INT_MAX;
         MotionVector mv = best;
         const unsigned chroma[2] = { c0.y, c0.z };
-        MotionVector fr[2];
-        fr[0] = f0[blk];
-        if (A.num_refs > 1) fr[1] = f1[blk];
-        for (int r = 0; r < A.num_refs; r++) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          if (r >= A.num_refs) continue;
           mv = fr[r];
           mv.flags = (mv.flags & ~0x1fu) | (2u << 3) | (unsigned) (r + 1);
           int px, py;
-          s2_predict (nb, n_nb, r + 1, px, py);
+          s2_predict (left, up, ul, have, r + 1, px, py);
           entropy[r] = s2_bits_sint (mv.v[r] - px) + s2_bits_sint (mv.v[2 + r] - py);
           int error;
           if (mv.metric == (unsigned) INT_MAX) error = INT_MAX;
