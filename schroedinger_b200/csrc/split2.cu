@@ -104,6 +104,16 @@ __device__ __forceinline__ void s2_blkref (BlkRef &br, int rstride, int prec, in
   x0 = hx >> 1; x1 = (hx + 1) >> 1; y0 = hy >> 1; y1 = (hy + 1) >> 1;
 }
 
+// one pixel through the unified 4-tap sum, all four taps loaded whatever their weights (the caller has checked
+// that they lie inside the plane's border): no branch between the loads of consecutive fetches, so they overlap
+__device__ __forceinline__ int s2_fetch (const uint8_t *ref, const BlkRef &br, int pix)
+{
+  const int s00 = __ldg (ref + br.o[0] + pix), s01 = __ldg (ref + br.o[1] + pix);
+  const int s10 = __ldg (ref + br.o[2] + pix), s11 = __ldg (ref + br.o[3] + pix);
+  const unsigned w = br.w;
+  return ((int) (w & 0xff) * s00 + (int) ((w >> 8) & 0xff) * s01 + (int) ((w >> 16) & 0xff) * s10 + (int) (w >> 24) * s11 + 8) >> 4;
+}
+
 // sum within each half of the warp (lanes 0-15, lanes 16-31)
 __device__ __forceinline__ unsigned half_sum (unsigned v)
 {
@@ -196,8 +206,24 @@ split2_candidates_kernel (const Split2Args A)
     const int la = lane & 7, lb = lane >> 3;                       // luma: pixels (la, lb) and (la, lb + 4)
     const int ca = lane & 3, cb = (lane >> 2) & 3;                 // chroma: pixel (ca, cb) of U (lanes 0-15) or V (16-31)
     const bool is_v = lane >= 16;
+    // every load of the block first ...
     const int ya = __ldg (op[0] + (ptrdiff_t) lb * os[0] + la), yb = __ldg (op[0] + (ptrdiff_t) (lb + 4) * os[0] + la);
     const int c = __ldg ((is_v ? op[2] : op[1]) + (ptrdiff_t) cb * os[1] + ca);
+    int pc[2] = { 0, 0 };                                          // this lane's chroma prediction from each reference
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+      if (r < A.num_refs) pc[r] = s2_fetch (is_v ? rp[r][2].p : rp[r][1].p, bc[r], cb * rp[r][1].stride + ca);
+    // mv_precision >= 2: the reference's scratch block holds the V prediction where the chroma block lies
+    const bool shared_scratch = A.prec >= 2;
+    int p0a = 0, p1a = 0, p0b = 0, p1b = 0;
+    if (biref) {
+      const bool corner = shared_scratch && la < 4;
+      p0a = s2_fetch (corner ? rp[0][2].p : rp[0][0].p, corner ? bc[0] : bl[0], corner ? lb * rp[0][1].stride + la : lb * rp[0][0].stride + la);
+      p1a = s2_fetch (corner ? rp[1][2].p : rp[1][0].p, corner ? bc[1] : bl[1], corner ? lb * rp[1][1].stride + la : lb * rp[1][0].stride + la);
+      p0b = s2_fetch (rp[0][0].p, bl[0], (lb + 4) * rp[0][0].stride + la);
+      p1b = s2_fetch (rp[1][0].p, bl[1], (lb + 4) * rp[1][0].stride + la);
+    }
+    // ... then the sums
     {
       const int ave_y = ((int) warp_sum ((unsigned) (ya + yb)) + 32) >> 6;
       const int ave_c = ((int) half_sum ((unsigned) c) + 8) >> 4;
@@ -206,32 +232,16 @@ split2_candidates_kernel (const Split2Args A)
       dc[1] = __shfl_sync (0xffffffffu, ave_c, 0) - 128;
       dc[2] = __shfl_sync (0xffffffffu, ave_c, 16) - 128;
     }
-    int pc[2] = { 0, 0 };                                          // this lane's chroma prediction from each reference
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
-      if (r >= A.num_refs) continue;
-      pc[r] = fetch1 (is_v ? rp[r][2].p : rp[r][1].p, bc[r], cb * rp[r][1].stride + ca);
-      chroma[r] = warp_sum ((unsigned) abs (c - pc[r]));
-    }
+    for (int r = 0; r < 2; r++)
+      if (r < A.num_refs) chroma[r] = warp_sum ((unsigned) abs (c - pc[r]));
     if (biref) {
-      // mv_precision >= 2: the reference's scratch block holds the V prediction where the chroma block lies
-      const bool shared_scratch = A.prec >= 2;
       int v0 = pc[0], v1 = pc[1];
       if (shared_scratch) {
         v0 = __shfl_sync (0xffffffffu, pc[0], (lane & 15) + 16);
         v1 = __shfl_sync (0xffffffffu, pc[1], (lane & 15) + 16);
       }
       bi_chroma = warp_sum ((unsigned) abs (c - ((v0 + v1 + 1) >> 1)));
-      int p0a, p1a;
-      if (shared_scratch && la < 4) {
-        p0a = fetch1 (rp[0][2].p, bc[0], lb * rp[0][1].stride + la);
-        p1a = fetch1 (rp[1][2].p, bc[1], lb * rp[1][1].stride + la);
-      } else {
-        p0a = fetch1 (rp[0][0].p, bl[0], lb * rp[0][0].stride + la);
-        p1a = fetch1 (rp[1][0].p, bl[1], lb * rp[1][0].stride + la);
-      }
-      const int p0b = fetch1 (rp[0][0].p, bl[0], (lb + 4) * rp[0][0].stride + la);
-      const int p1b = fetch1 (rp[1][0].p, bl[1], (lb + 4) * rp[1][0].stride + la);
       bi_luma = warp_sum ((unsigned) (abs (ya - ((p0a + p1a + 1) >> 1)) + abs (yb - ((p0b + p1b + 1) >> 1))));
     }
   } else {
