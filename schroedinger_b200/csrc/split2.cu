@@ -127,10 +127,11 @@ __global__ void __launch_bounds__ (128, 5)
 split2_candidates_kernel (const Split2Args A)
 {
   const int lane = threadIdx.x & 31;
-  const long long g = (long long) blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int per_pic = A.nbx * A.nby;
-  if (g >= (long long) A.count * per_pic) return;
-  const int pic = (int) (g / per_pic), blk = (int) (g - (long long) pic * per_pic);
+  // (32-bit index arithmetic: the launcher refuses more than 2^31 blocks per launch)
+  const unsigned g = blockIdx.x * 4u + (threadIdx.x >> 5);
+  const unsigned per_pic = (unsigned) (A.nbx * A.nby);
+  if (g >= (unsigned) A.count * per_pic) return;
+  const int pic = (int) (g / per_pic), blk = (int) (g - (unsigned) pic * per_pic);
   const int by = blk / A.nbx, bx = blk - by * A.nbx;
   unsigned *rec = A.rec + ((size_t) pic * per_pic + blk) * 8;
   if (!(A.pw[0] > bx * A.xblen) || !(A.ph[0] > by * A.yblen)) {
@@ -527,6 +528,7 @@ sb2_split2_decide (const sb2_split2_params *p, const sb2_slab *orig, const sb2_s
   if (e == cudaSuccess) e = cudaMemsetAsync (sb_entropy, 0, nsb * sizeof (int), st);
   if (e != cudaSuccess) return check_cuda (e, "sb2_split2_decide: clearing the superblock sums");
   const long long warps = (long long) A.nbx * A.nby * A.count;
+  if (warps >= (1ll << 31)) return set_error (SB2_ERR_UNSUPPORTED, "sb2_split2_decide: more than 2^31 blocks in one launch");
   {
     // algorithmic bytes: the source once, each reference's four phase planes once (1.5 bytes per luma pixel each), the fields, the records
     const double px = 1.5 * A.pw[0] * A.ph[0] * A.count;

@@ -58,10 +58,11 @@ __global__ void __launch_bounds__ (128)
 subpel_probe_kernel (const SubpelArgs A)
 {
   const int lane = threadIdx.x & 31;
-  const long long g = (long long) blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int per_pic = A.nbx * A.nby;
-  if (g >= (long long) A.count * per_pic) return;
-  const int pic = (int) (g / per_pic), blk = (int) (g - (long long) pic * per_pic);
+  // (32-bit index arithmetic: the launcher refuses more than 2^31 blocks per launch)
+  const unsigned g = blockIdx.x * 4u + (threadIdx.x >> 5);
+  const unsigned per_pic = (unsigned) (A.nbx * A.nby);
+  if (g >= (unsigned) A.count * per_pic) return;
+  const int pic = (int) (g / per_pic), blk = (int) (g - (unsigned) pic * per_pic);
   const int j = blk / A.nbx, i = blk - j * A.nbx;
   const MotionVector *mv = A.field + (size_t) pic * A.field_pitch + blk;
   unsigned *rec = A.rec + ((size_t) pic * per_pic + blk) * 12;
@@ -265,6 +266,7 @@ sb2_subpel_refine (const sb2_subpel_params *p, const sb2_slab *orig, const sb2_s
   A.fast = g_subpel_generic ? 0 : 1;
   cudaStream_t st = as_stream (stream);
   const long long warps = (long long) A.nbx * A.nby * A.count;
+  if (warps >= (1ll << 31)) return set_error (SB2_ERR_UNSUPPORTED, "sb2_subpel_refine: more than 2^31 blocks in one launch");
   // algorithmic bytes of a pass: the source picture once, the reference's four phase planes once, the field twice
   const double bytes = 5.0 * A.width * A.height * A.count + 40.0 * A.nbx * A.nby * A.count;
   for (int prec = 1; prec <= p->mv_precision; prec++) {
