@@ -247,12 +247,39 @@ def metric_scan_golden(ref):
     print("metric_scan.npz:", len(t.QUERIES), "queries")
 
 
+# (width, height, mv_precision, num_refs, lambda, seed)
+SPLIT2_GOLDEN_CASES = [(96, 80, 2, 2, 0.1, 1), (96, 80, 3, 2, 1.0, 2), (128, 64, 1, 2, 0.3, 3), (100, 70, 2, 1, 0.25, 4),
+                       (96, 80, 0, 2, 0.05, 5)]
+
+
+def split2_inputs(oracle, idx, case):
+    """pictures from the seed; the sub-pel fields come from the fixture (they are outputs of the oracle's search)"""
+    w, h, prec, nrefs, lam, seed = case
+    return helpers.split2_case(oracle, w, h, np.random.default_rng(9000 + seed), prec, nrefs, lam=lam)
+
+
+def split2_golden(ref):
+    """schro_do_split2 + schro_motion_copy_to of the compiled reference for every superblock (oracle/ref_me_static.c)"""
+    ref_me = helpers.load_ref_me()
+    oracle = helpers.load_oracle()
+    out = {}
+    for idx, case in enumerate(SPLIT2_GOLDEN_CASES):
+        w, h, prec, nrefs, lam, seed = case
+        src, refs, fields = split2_inputs(oracle, idx, case)
+        motion, sb_error, sb_entropy = helpers.ref_split2(ref_me, src, refs, fields, w, h, 8, 8, prec, lam)
+        for r, f in enumerate(fields):
+            out[f"s{idx}_field{r}"] = f
+        out[f"s{idx}_motion"], out[f"s{idx}_sb_error"], out[f"s{idx}_sb_entropy"] = motion, sb_error, sb_entropy
+    np.savez_compressed(os.path.join(helpers.GOLDEN_DIR, "split2.npz"), **out)
+    print("split2.npz:", len(out), "arrays")
+
+
 def main():
     ref = helpers.load_ref()
     if ref is None:
         raise SystemExit("oracle/_ref/libschro_ref.so missing: run `make ref` where /root/reference exists")
     wavelet_golden(ref)
-    for name in ("frame_golden", "motion_golden", "hbm_golden", "rough_golden", "shift_md5_golden", "lowdelay_golden", "glue_golden", "dequant_golden", "metric_scan_golden"):
+    for name in ("frame_golden", "motion_golden", "hbm_golden", "rough_golden", "shift_md5_golden", "lowdelay_golden", "glue_golden", "dequant_golden", "metric_scan_golden", "split2_golden"):
         fn = globals().get(name)
         if fn:
             fn(ref)

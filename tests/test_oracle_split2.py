@@ -8,7 +8,21 @@ from tests import helpers
 
 ref_me = helpers.load_ref_me()
 oracle = helpers.load_oracle()
-pytestmark = pytest.mark.skipif(ref_me is None, reason="oracle/_ref not built")
+needs_ref = pytest.mark.skipif(ref_me is None, reason="oracle/_ref not built")
+
+
+def _golden_check():
+    import os
+    from tests.golden import make_golden as mg
+    gold = np.load(os.path.join(helpers.GOLDEN_DIR, "split2.npz"))
+    for idx, case in enumerate(mg.SPLIT2_GOLDEN_CASES):
+        w, h, prec, nrefs, lam, seed = case
+        src, refs, _ = mg.split2_inputs(oracle, idx, case)
+        fields = [gold[f"s{idx}_field{r}"] for r in range(nrefs)]
+        got = helpers.oracle_split2(oracle, src, refs, fields, w, h, 8, 8, prec, lam)
+        for f in ("flags", "metric", "chroma_metric", "v"):
+            assert np.array_equal(got[0][f], gold[f"s{idx}_motion"][f]), (idx, f)
+        assert np.array_equal(got[1], gold[f"s{idx}_sb_error"]) and np.array_equal(got[2], gold[f"s{idx}_sb_entropy"]), idx
 
 
 def _check(w, h, prec, lam, seed, num_refs=2, pans=((5, 3), (-4, 2)), mutate=None):
@@ -27,12 +41,14 @@ def _check(w, h, prec, lam, seed, num_refs=2, pans=((5, 3), (-4, 2)), mutate=Non
     return [int((modes == m).sum()) for m in range(4)]
 
 
+@needs_ref
 @pytest.mark.parametrize("prec", [0, 1, 2, 3])
 @pytest.mark.parametrize("lam", [0.0, 0.1, 2.0])
 def test_split2_matches_reference(prec, lam):
     _check(176, 144, prec, lam, seed=prec * 7 + int(lam))
 
 
+@needs_ref
 def test_split2_mode_mix():
     """A picture whose halves favour different references, plus flat patches that go DC."""
     def mutate(src, refs, fields, rng):
@@ -48,12 +64,14 @@ def test_split2_mode_mix():
     assert all(c > 0 for c in counts), counts                                           # DC, ref 0, ref 1 and biref all occur
 
 
+@needs_ref
 def test_split2_single_reference_and_ragged():
     _check(200, 104, 2, 0.25, seed=3, num_refs=1)
     _check(100, 70, 3, 0.05, seed=4)
     _check(100, 70, 1, 0.5, seed=5, num_refs=1)
 
 
+@needs_ref
 def test_split2_biref_range_test():
     """Vectors near the edge of the extended frame: the bi-reference candidate is dropped (:1719-1724)."""
     def mutate(src, refs, fields, rng):
@@ -64,3 +82,9 @@ def test_split2_biref_range_test():
             f["v"][idx, 2 + r] = rng.integers(-30, 31, size=len(idx))
     _check(176, 144, 1, 0.1, seed=21, mutate=mutate)
     _check(176, 144, 0, 0.1, seed=22, mutate=mutate)
+
+
+def test_oracle_vs_golden_fixture():
+    """tests/golden/split2.npz holds outputs of the compiled reference (make_golden.py: split2_golden); this
+    comparison also runs where oracle/_ref is absent."""
+    _golden_check()

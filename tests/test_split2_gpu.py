@@ -188,3 +188,16 @@ def test_split2_drop_in(cuda, nrefs):
         lib.schro_frame_unref(ups[r])
     lib.schro_motion_free(motion)
     lib.schro_frame_unref(fo)
+
+
+def test_split2_vs_golden_fixture(cuda):
+    """Against outputs of the compiled reference itself (tests/golden/split2.npz)."""
+    import os
+    from tests.golden import make_golden as mg
+    gold = np.load(os.path.join(helpers.GOLDEN_DIR, "split2.npz"))
+    for idx, case in enumerate(mg.SPLIT2_GOLDEN_CASES):
+        w, h, prec, nrefs, lam, seed = case
+        src, refs, _ = mg.split2_inputs(ORACLE, idx, case)
+        fields = [gold[f"s{idx}_field{r}"] for r in range(nrefs)]
+        got = gpu_split2([(src, refs, fields)], w, h, prec, lam)[0]
+        check(got, (gold[f"s{idx}_motion"], gold[f"s{idx}_sb_error"], gold[f"s{idx}_sb_entropy"]), ("golden", idx))
