@@ -122,8 +122,8 @@ __device__ __forceinline__ unsigned half_sum (unsigned v)
   return v;
 }
 
-template <bool FAST_OK>
-__global__ void __launch_bounds__ (128, 5)
+template <bool FAST_OK, int MINB>
+__global__ void __launch_bounds__ (128, MINB)
 split2_candidates_kernel (const Split2Args A)
 {
   const int lane = threadIdx.x & 31;
@@ -533,8 +533,10 @@ sb2_split2_decide (const sb2_split2_params *p, const sb2_slab *orig, const sb2_s
     // algorithmic bytes: the source once, each reference's four phase planes once (1.5 bytes per luma pixel each), the fields, the records
     const double px = 1.5 * A.pw[0] * A.ph[0] * A.count;
     LaunchScope scope ("split2_candidates", px * (1.0 + 4.0 * A.num_refs) + (20.0 * A.num_refs + 32.0) * A.nbx * A.nby * A.count, st);
-    if (g_split2_generic) split2_candidates_kernel<false><<<(unsigned) ((warps + 3) / 4), 128, 0, st>>> (A);
-    else split2_candidates_kernel<true><<<(unsigned) ((warps + 3) / 4), 128, 0, st>>> (A);
+    const unsigned grid = (unsigned) ((warps + 3) / 4);
+    // the kernel waits for loads most of the time: 8 CTAs per SM at 64 registers (112 bytes spilled) beat 5 at 96 by 20 %
+    if (g_split2_generic) split2_candidates_kernel<false, 5><<<grid, 128, 0, st>>> (A);
+    else split2_candidates_kernel<true, 8><<<grid, 128, 0, st>>> (A);
   }
   {
     LaunchScope scope ("split2_decide", (32.0 + 20.0 * A.num_refs + 20.0) * A.nbx * A.nby * A.count, st);
