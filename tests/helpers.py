@@ -577,7 +577,8 @@ def load_ref_me():
     """schromotionest.c's file-static functions (oracle/ref_me_static.c), or None."""
     if not os.path.exists(REF_ME_PATH) or not os.path.exists(REF_PATH):
         return None
-    ctypes.CDLL(REF_PATH, mode=ctypes.RTLD_GLOBAL)
+    # RTLD_LOCAL: libschro_ref.so comes in as its dependency (rpath $ORIGIN); making the reference's schro_*
+    # symbols global would capture the bindings of everything loaded later (the compat shims, the product library)
     return ctypes.CDLL(REF_ME_PATH, mode=ctypes.RTLD_LOCAL)
 
 
