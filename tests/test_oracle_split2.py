@@ -88,3 +88,27 @@ def test_oracle_vs_golden_fixture():
     """tests/golden/split2.npz holds outputs of the compiled reference (make_golden.py: split2_golden); this
     comparison also runs where oracle/_ref is absent."""
     _golden_check()
+
+
+def _synthetic_fields(rng, w, h, bs, prec, nrefs):
+    nbx, nby = helpers.hbm_block_counts(w, h, bs, bs)
+    fields = [np.zeros(nbx * nby, helpers.MV_DTYPE) for _ in range(nrefs)]
+    for r, f in enumerate(fields):
+        f["flags"] = r + 1
+        f["v"][:, r] = rng.integers(-6 << prec, (6 << prec) + 1, size=nbx * nby)
+        f["v"][:, 2 + r] = rng.integers(-6 << prec, (6 << prec) + 1, size=nbx * nby)
+        f["metric"] = rng.integers(0, 3000, size=nbx * nby)
+    return fields
+
+
+@needs_ref
+@pytest.mark.parametrize("w,h,bs,prec", [(192, 144, 12, 2), (256, 128, 16, 3), (96, 64, 4, 1), (200, 104, 12, 0)])
+def test_split2_other_block_sizes(w, h, bs, prec):
+    rng = np.random.default_rng(w + bs + prec)
+    src, refs, _ = helpers.subpel_case(oracle, w, h, rng)
+    fields = _synthetic_fields(rng, w, h, bs, prec, 2)
+    want = helpers.ref_split2(ref_me, src, refs, fields, w, h, bs, bs, prec, 0.2)
+    got = helpers.oracle_split2(oracle, src, refs, fields, w, h, bs, bs, prec, 0.2)
+    for f in ("flags", "metric", "chroma_metric", "v"):
+        assert np.array_equal(got[0][f], want[0][f]), f
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])

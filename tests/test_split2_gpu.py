@@ -21,11 +21,11 @@ def candidates_path(request):
     lib.sb2_split2_force_generic(0)
 
 
-def gpu_split2(cases, w, h, prec, lam):
+def gpu_split2(cases, w, h, prec, lam, bs=8):
     """cases: list of (src, refs, fields), run as one batch."""
     from schroedinger_b200 import device as dev
     count = len(cases)
-    nbx, nby = helpers.hbm_block_counts(w, h, 8, 8)
+    nbx, nby = helpers.hbm_block_counts(w, h, bs, bs)
     orig = dev.PictureSlab(dev.FrameLayout.yuv420("u8", w, h, 32), count)
     nrefs = len(cases[0][1])
     for p, (src, refs, fields) in enumerate(cases):
@@ -40,7 +40,7 @@ def gpu_split2(cases, w, h, prec, lam):
         dev.edgeextend_upsample(up)
         ups.append(up)
         flds.append(torch.from_numpy(np.concatenate([c[2][r] for c in cases]).view(np.uint8).copy()).cuda())
-    motion, sb_error, sb_entropy = dev.split2_decide(orig, ups, flds, 8, 8, nbx, nby, prec, lam)
+    motion, sb_error, sb_entropy = dev.split2_decide(orig, ups, flds, bs, bs, nbx, nby, prec, lam)
     torch.cuda.synchronize()
     motion = motion.cpu().numpy().view(helpers.MV_DTYPE).reshape(count, nbx * nby)
     return [(motion[p], sb_error[p].cpu().numpy(), sb_entropy[p].cpu().numpy()) for p in range(count)]
@@ -201,3 +201,14 @@ def test_split2_vs_golden_fixture(cuda):
         fields = [gold[f"s{idx}_field{r}"] for r in range(nrefs)]
         got = gpu_split2([(src, refs, fields)], w, h, prec, lam)[0]
         check(got, (gold[f"s{idx}_motion"], gold[f"s{idx}_sb_error"], gold[f"s{idx}_sb_entropy"]), ("golden", idx))
+
+
+@pytest.mark.parametrize("w,h,bs,prec", [(192, 144, 12, 2), (256, 128, 16, 3), (96, 64, 4, 1), (200, 104, 12, 0)])
+def test_split2_other_block_sizes(cuda, w, h, bs, prec):
+    from tests.test_oracle_split2 import _synthetic_fields
+    rng = np.random.default_rng(w + bs + prec)
+    src, refs, _ = helpers.subpel_case(ORACLE, w, h, rng)
+    fields = _synthetic_fields(rng, w, h, bs, prec, 2)
+    want = helpers.oracle_split2(ORACLE, src, refs, fields, w, h, bs, bs, prec, 0.2)
+    got = gpu_split2([(src, refs, fields)], w, h, prec, 0.2, bs)
+    check(got[0], want, (w, h, bs, prec))
