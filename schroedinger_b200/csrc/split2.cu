@@ -311,6 +311,9 @@ __device__ __forceinline__ int s2_bits_sint (int v)
 }
 __device__ __forceinline__ int s2_med3 (int a, int b, int c) { return max (min (a, b), min (max (a, b), c)); }
 
+constexpr int S2_PF = 8;
+__device__ __forceinline__ void prefetch_l1 (const void *p) { asm volatile ("prefetch.global.L1 [%0];" :: "l" (p)); }
+
 // a decided block as its neighbours see it: vector of reference 0, vector of reference 1, pred_mode
 struct Decided {
   unsigned v0, v1, mode;
@@ -359,6 +362,11 @@ split2_decide_kernel (const Split2Args A)
     n0 = __ldg (rec + (size_t) blk * 2); n1 = __ldg (rec + (size_t) blk * 2 + 1);
     nf[0] = f0[blk];
     if (A.num_refs > 1) nf[1] = f1[blk];
+    for (int k = 1; k < S2_PF && k < A.nbx; k += 4) {     // four 32-byte records to a line; row j idles j steps before it starts
+      prefetch_l1 (rec + (size_t) (blk + k) * 2);
+      prefetch_l1 (f0 + blk + k);
+      if (A.num_refs > 1) prefetch_l1 (f1 + blk + k);
+    }
   }
   for (int s = 0; s < steps; s++) {
     const int i = s - j;
@@ -372,6 +380,13 @@ split2_decide_kernel (const Split2Args A)
         n0 = __ldg (rec + (size_t) (blk + 1) * 2); n1 = __ldg (rec + (size_t) (blk + 1) * 2 + 1);
         nf[0] = f0[blk + 1];
         if (A.num_refs > 1) nf[1] = f1[blk + 1];
+      }
+      // a step lasts as long as its slowest row: without this nearly every step has some row whose next record misses
+      // the caches and pays a DRAM round trip; the lines a row needs S2_PF blocks from now are requested here
+      if (i + S2_PF < A.nbx) {
+        prefetch_l1 (rec + (size_t) (blk + S2_PF) * 2);
+        prefetch_l1 (f0 + blk + S2_PF);
+        if (A.num_refs > 1) prefetch_l1 (f1 + blk + S2_PF);
       }
       MotionVector best;
       best.flags = (2u << 3) | 1u; best.metric = 0; best.chroma_metric = 0; best.v[0] = best.v[1] = best.v[2] = best.v[3] = 0;

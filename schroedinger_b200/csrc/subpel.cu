@@ -168,6 +168,9 @@ subpel_decide_kernel (const SubpelArgs A)
     if (row && i >= 0 && i < A.nbx) {
       const uint4 c0 = n0, c1 = n1, c2 = n2;
       if (i + 1 < A.nbx) { const uint4 *r = rec + (size_t) (j * A.nbx + i + 1) * 3; n0 = __ldg (r); n1 = __ldg (r + 1); n2 = __ldg (r + 2); }
+      // a step lasts as long as its slowest row: request the line a row needs eight blocks from now, so that the load
+      // above hits the L1 instead of paying a DRAM round trip in some row at nearly every step
+      if (i + 8 < A.nbx) asm volatile ("prefetch.global.L1 [%0];" :: "l" (rec + (size_t) (j * A.nbx + i + 8) * 3));
       unsigned result = c0.y;
       if (!(c0.x & SKIP)) {
         int dx = (int) (short) (c0.y & 0xffff), dy = (int) (short) (c0.y >> 16);
