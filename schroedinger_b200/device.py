@@ -445,7 +445,7 @@ def subpel_refine(orig, upref, field, xblen, yblen, x_num_blocks, y_num_blocks, 
 
 
 def split2_decide(orig, uprefs, fields, xblen, yblen, x_num_blocks, y_num_blocks, mv_precision, lam,
-                  workspace=None, stream=None):
+                  workspace=None, stream=None, out=None):
     """The split-2 pass of schro_mode_decision (schro_do_split2 for every superblock) for every picture:
     uprefs / fields are lists of one or two upsampled reference slabs / uint8 CUDA tensors (count x nblocks x 20
     bytes, vectors at mv_precision).  Returns (motion, sb_error, sb_entropy) as CUDA tensors."""
@@ -456,9 +456,13 @@ def split2_decide(orig, uprefs, fields, xblen, yblen, x_num_blocks, y_num_blocks
     nsb = (x_num_blocks // 4) * (y_num_blocks // 4)
     count = orig.count
     p = Split2Params(xblen, yblen, x_num_blocks, y_num_blocks, mv_precision, len(uprefs), 1, 1, orig.layout.extension, lam)
-    motion = torch.empty(count * n * 20, dtype=torch.uint8, device="cuda")
-    sb_error = torch.empty(count * nsb, dtype=torch.int32, device="cuda")
-    sb_entropy = torch.empty(count * nsb, dtype=torch.int32, device="cuda")
+    if out is not None:                 # caller-provided (motion uint8 [count*n*20], sb_error / sb_entropy int32 [count*nsb])
+        motion, sb_error, sb_entropy = out
+        assert motion.numel() == count * n * 20 and sb_error.numel() == count * nsb and sb_entropy.numel() == count * nsb
+    else:
+        motion = torch.empty(count * n * 20, dtype=torch.uint8, device="cuda")
+        sb_error = torch.empty(count * nsb, dtype=torch.int32, device="cuda")
+        sb_entropy = torch.empty(count * nsb, dtype=torch.int32, device="cuda")
     ws = workspace or _default_ws
     ptr, size = ws.get(lib.sb2_split2_workspace_bytes(x_num_blocks, y_num_blocks, count))
     two = len(uprefs) > 1

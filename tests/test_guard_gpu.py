@@ -230,7 +230,18 @@ def test_second_round_kernels_stay_inside_their_buffers(cuda):
     t0, f0 = field()
     f0.zero_()
     dev.subpel_refine(ps.slabs[0], up, f0, 8, 8, nbx, nby, 3, 1, 0.2)
+    # the split-2 pass of the mode decision on that field: decided blocks and the superblock sums
+    tm, fm = field()
+    nsb = (nbx // 4) * (nby // 4) * count
+    te = torch.full((GUARD // 4 + nsb + GUARD // 4,), 0x25A5A5A5, dtype=torch.int32, device="cuda")
+    tn = te.clone()
+    dev.split2_decide(ps.slabs[0], [up], [f0], 8, 8, nbx, nby, 3, 0.2,
+                      out=(fm, te[GUARD // 4:GUARD // 4 + nsb], tn[GUARD // 4:GUARD // 4 + nsb]))
     torch.cuda.synchronize()
-    for t in wholes[1:] + [t0]:
+    for t in wholes[1:] + [t0, tm]:
         a = t.cpu().numpy()
         assert (a[:GUARD] == PAT).all() and (a[-GUARD:] == PAT).all(), "a motion-field kernel wrote outside its field"
+    for t in (te, tn):
+        a = t.cpu().numpy()
+        assert (a[:GUARD // 4] == 0x25A5A5A5).all() and (a[-GUARD // 4:] == 0x25A5A5A5).all(), "superblock sums overran"
+        assert (a[GUARD // 4:-GUARD // 4] != 0x25A5A5A5).all(), "a superblock sum was never written"
