@@ -112,3 +112,25 @@ def test_split2_other_block_sizes(w, h, bs, prec):
     for f in ("flags", "metric", "chroma_metric", "v"):
         assert np.array_equal(got[0][f], want[0][f]), f
     assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(8))
+def test_split2_random_sweep(seed):
+    """random size (ragged or not), precision, number of references, lambda, block size and field mutations"""
+    rng = np.random.default_rng(1000 + seed)
+    bs = int(rng.choice([4, 8, 8, 12, 16]))
+    w = int(rng.integers(5, 14)) * 16 + int(rng.choice([0, 0, 2, 6, 10]))
+    h = int(rng.integers(4, 10)) * 16 + int(rng.choice([0, 0, 2, 6, 10]))
+    prec, nrefs, lam = int(rng.integers(0, 4)), int(rng.integers(1, 3)), float(rng.choice([0.0, 0.03, 0.3, 3.0]))
+    src, refs, _ = helpers.subpel_case(oracle, w, h, rng, num_refs=nrefs)
+    fields = _synthetic_fields(rng, w, h, bs, prec, nrefs)
+    if seed & 1:                                   # flat patches: DC blocks
+        for k in range(3):
+            hh, ww = src[k].shape
+            src[k][hh // 3:2 * hh // 3, ww // 4:3 * ww // 4] = 60 + 30 * k
+    want = helpers.ref_split2(ref_me, src, refs, fields, w, h, bs, bs, prec, lam)
+    got = helpers.oracle_split2(oracle, src, refs, fields, w, h, bs, bs, prec, lam)
+    for f in ("flags", "metric", "chroma_metric", "v"):
+        assert np.array_equal(got[0][f], want[0][f]), (seed, bs, w, h, prec, nrefs, lam, f)
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
