@@ -72,3 +72,14 @@ def test_subpel_vectors_at_the_range_limits():
             f["v"][:, r] = np.clip(f["v"][:, r], -6, 6)
             f["v"][:, 2 + r] = np.clip(f["v"][:, 2 + r], -6, 6)
     _check(128, 96, 2, 0.1, seed=8, mutate=mutate_safe)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_subpel_random_sweep(seed):
+    """random size, precision, lambda, block size, number of references"""
+    rng = np.random.default_rng(500 + seed)
+    bs = int(rng.choice([8, 8, 12, 16]))
+    w = int(rng.integers(6, 14)) * 16 + int(rng.choice([0, 0, 4, 10]))
+    h = int(rng.integers(4, 10)) * 16 + int(rng.choice([0, 0, 6, 12]))
+    prec, lam, nrefs = int(rng.integers(1, 4)), float(rng.choice([0.0, 0.02, 0.5, 4.0])), int(rng.integers(1, 3))
+    _check(w, h, prec, lam, seed=600 + seed, num_refs=nrefs, bs=bs)
